@@ -1,0 +1,145 @@
+"""ctypes binding of libgdf_b200.so (C ABI declared in include/gdf.h).
+
+There is no CPU fallback: if the shared library is missing the import of any compute entry point raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgdf_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+GDF_MAX_LEVELS = 4
+
+# every symbol include/gdf.h declares (checked by tests/test_abi.py against the header text)
+EXPORTS = [
+    "gdf_last_error", "gdf_abi_version",
+    "gdf_create", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
+    "gdf_encode_noise", "gdf_denoise_capture",
+    "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
+    "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
+    "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
+    "gdf_op_resize_concat",
+]
+
+
+class CaptureSeg(ctypes.Structure):
+    _fields_ = [("ptr_dev", c_void_p), ("col_begin", c_int), ("col_end", c_int), ("ld", c_int)]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [
+        ("alpha", c_float), ("n_out", c_int),
+        ("bias_dev", c_void_p), ("bias_m_dev", c_void_p), ("row_batch_bias_dev", c_void_p),
+        ("rows_per_batch", c_int), ("act", c_int),
+        ("col_scale_dev", c_void_p),
+        ("residual_dev", c_void_p), ("ld_res", c_int),
+        ("out_scale", c_float),
+        ("out_dev", c_void_p), ("ld_out", c_int), ("out_batch_stride", c_int64),
+        ("out2_dev", c_void_p), ("ld_out2", c_int),
+        ("out_f32_dev", c_void_p), ("ld_out_f32", c_int),
+        ("cap_pre_dev", c_void_p), ("ld_cap_pre", c_int),
+        ("cap", CaptureSeg * 3), ("num_cap", c_int),
+    ]
+
+
+class ResizeSrc(ctypes.Structure):
+    _fields_ = [("ptr_dev", c_void_p), ("h", c_int), ("w", c_int), ("C", c_int), ("c_off", c_int)]
+
+
+class UNetArch(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("out_channels", c_int), ("num_levels", c_int),
+        ("block_out_channels", c_int * GDF_MAX_LEVELS), ("layers_per_block", c_int),
+        ("down_has_attn", c_int * GDF_MAX_LEVELS), ("up_has_attn", c_int * GDF_MAX_LEVELS),
+        ("transformer_depth", c_int * GDF_MAX_LEVELS), ("num_heads", c_int * GDF_MAX_LEVELS),
+        ("cross_attention_dim", c_int), ("use_linear_projection", c_int),
+        ("addition_time_embed_dim", c_int), ("projection_class_embeddings_input_dim", c_int),
+        ("norm_num_groups", c_int), ("norm_eps", c_float),
+    ]
+
+
+class VaeArch(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("latent_channels", c_int), ("num_levels", c_int),
+        ("block_out_channels", c_int * GDF_MAX_LEVELS), ("layers_per_block", c_int),
+        ("norm_num_groups", c_int), ("norm_eps", c_float), ("scaling_factor", c_float),
+    ]
+
+
+class Slot(ctypes.Structure):
+    _fields_ = [("offset_bytes", c_int64), ("channels", c_int), ("height", c_int), ("width", c_int),
+                ("order", c_int)]
+
+
+class GdfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libgdf_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GdfError(
+            "libgdf_b200.so not found at %s - build it with `python -m generic_diffusion_feature_b200.build` "
+            "(there is no CPU / PyTorch fallback for the extraction path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gdf_last_error.restype = ctypes.c_char_p
+    lib.gdf_op_groupnorm_workspace_floats.restype = c_int64
+    lib.gdf_op_groupnorm_workspace_floats.argtypes = [c_int, c_int]
+    P = c_void_p
+    lib.gdf_op_linear.argtypes = [P, c_int64, c_int, c_int, P, c_int, c_int, ctypes.POINTER(Epilogue), c_int,
+                                  c_int64, c_int64, c_int, P]
+    lib.gdf_op_conv3x3.argtypes = [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, ctypes.POINTER(Epilogue),
+                                   c_int, P]
+    lib.gdf_op_pack_conv_weight.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
+    lib.gdf_op_groupnorm.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P]
+    lib.gdf_op_layernorm.argtypes = [P, P, P, P, c_int64, c_int, c_float, P, P, c_int, P]
+    lib.gdf_op_attention.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_float, P]
+    lib.gdf_op_softmax_rows.argtypes = [P, c_int64, c_int, c_int, P]
+    lib.gdf_op_upsample_nearest2x.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
+    lib.gdf_op_im2col_small.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P]
+    lib.gdf_op_qsample.argtypes = [P, P, P, c_float, c_float, c_float, c_float, P, P, P, c_int, c_int, P]
+    lib.gdf_op_cast_f32_to_bf16.argtypes = [P, P, c_int64, P]
+    lib.gdf_op_resize_concat.argtypes = [ctypes.POINTER(ResizeSrc), c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+    if hasattr(lib, "gdf_create"):
+        lib.gdf_create.argtypes = [ctypes.POINTER(UNetArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
+        lib.gdf_destroy.argtypes = [P]
+        lib.gdf_load_weights.argtypes = [P, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(P),
+                                         ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, P]
+        lib.gdf_finalize_weights.argtypes = [P, P]
+        lib.gdf_plan.argtypes = [P, ctypes.POINTER(ctypes.c_char_p), c_int, c_int, c_int, ctypes.POINTER(Slot),
+                                 ctypes.POINTER(c_int64)]
+        lib.gdf_encode_noise.argtypes = [P, P, P, P, c_float, c_float, c_float, P, P]
+        lib.gdf_denoise_capture.argtypes = [P, c_float, P, c_int, P, P, P, P, P]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GdfError("gdf error %d: %s" % (rc, load().gdf_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "gdf kernels take device tensors only"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,294 @@
+// Flash-style attention forward (online softmax, no N x N materialisation), head_dim 64, bf16 in/out,
+// fp32 softmax + accumulation. Reference call site: F.scaled_dot_product_attention in
+// feature/diffusers/models/attention_processor.py:3311-3313 (self- and cross-attention, Nk = 77 for text).
+// Q/K/V are read in place from the token-major projection outputs (head h = columns [64h, 64h+64)), so the
+// q/k/v captures written by the projection GEMM epilogue and the attention input are the same tensors.
+//
+// v1 data path: cp.async double-buffered K/V tiles in XOR-swizzled shared memory, ldmatrix fragments,
+// mma.sync.m16n8k16 (legacy tensor path). The tcgen05/TMEM variant replaces the two mma loops; the softmax
+// and pipeline structure stay.
+#include "ops.h"
+
+namespace gdf {
+
+constexpr int kAttBM = 128;   // query rows per CTA (8 warps x 16)
+constexpr int kAttBN = 64;    // kv rows per tile
+constexpr int kAttD = 64;
+constexpr int kAttThreads = 256;
+constexpr int kAttSmem = (kAttBM * kAttD + 4 * kAttBN * kAttD) * 2;  // Q + 2x(K,V) = 48 KB
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// tile row r, 16-byte chunk c (0..7) -> byte offset inside a [rows][64] bf16 tile with XOR swizzle
+__device__ __forceinline__ int swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention64_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk,
+                   const bf16* __restrict__ V, int ldv, bf16* __restrict__ O, int ldo, int Nq, int Nk,
+                   float scale_log2) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  uint8_t* sQ = att_smem;
+  uint8_t* sK = att_smem + kAttBM * kAttD * 2;
+  uint8_t* sV = sK + 2 * kAttBN * kAttD * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kAttBM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const bf16* Qb = Q + ((long long)b * Nq) * ldq + h * kAttD;
+  const bf16* Kb = K + ((long long)b * Nk) * ldk + h * kAttD;
+  const bf16* Vb = V + ((long long)b * Nk) * ldv + h * kAttD;
+
+  // ---- Q tile (rows beyond Nq are zero-filled)
+  for (int i = tid; i < kAttBM * 8; i += kAttThreads) {
+    const int r = i >> 3, c = i & 7;
+    const int qr = q0 + r;
+    const bool ok = qr < Nq;
+    cp_async16(sQ + swz(r, c), Qb + (long long)(ok ? qr : 0) * ldq + c * 8, ok ? 16 : 0);
+  }
+  auto load_kv = [&](int tile, int buf) {
+    const int k0 = tile * kAttBN;
+    for (int i = tid; i < kAttBN * 8; i += kAttThreads) {
+      const int r = i >> 3, c = i & 7;
+      const int kr = k0 + r;
+      const bool ok = kr < Nk;
+      const long long ro = (long long)(ok ? kr : 0);
+      cp_async16(sK + buf * kAttBN * kAttD * 2 + swz(r, c), Kb + ro * ldk + c * 8, ok ? 16 : 0);
+      cp_async16(sV + buf * kAttBN * kAttD * 2 + swz(r, c), Vb + ro * ldv + c * 8, ok ? 16 : 0);
+    }
+  };
+  const int ntiles = (Nk + kAttBN - 1) / kAttBN;
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o_acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  uint32_t qf[4][4];
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) {
+      load_kv(t + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], sQ + swz(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+    }
+    const uint8_t* sKb = sK + buf * kAttBN * kAttD * 2;
+    const uint8_t* sVb = sV + buf * kAttBN * kAttD * 2;
+
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s_acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_acc[i][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int nb2 = 0; nb2 < 4; ++nb2) {   // pairs of 8-wide kv blocks
+        uint32_t kf[4];
+        ldmatrix_x4(kf, sKb + swz(nb2 * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s_acc[nb2 * 2], qf[ks], kf[0], kf[1]);
+        mma_bf16_16816(s_acc[nb2 * 2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    // ---- scale, mask, online softmax
+    const int kv0 = t * kAttBN;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kv0 + nb * 8 + (lane & 3) * 2 + (j & 1);
+        float v = s_acc[nb][j] * scale_log2;
+        if (col >= Nk) v = -INFINITY;
+        s_acc[nb][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      alpha[r] = exp2f(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const float p0 = exp2f(s_acc[nb][0] - m_run[0]);
+      const float p1 = exp2f(s_acc[nb][1] - m_run[0]);
+      const float p2 = exp2f(s_acc[nb][2] - m_run[1]);
+      const float p3 = exp2f(s_acc[nb][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      // A fragment of P for k-step nb/2: a0,a1 from even block, a2,a3 from odd block
+      pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * alpha[r] + rs[r];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      o_acc[nb][0] *= alpha[0];
+      o_acc[nb][1] *= alpha[0];
+      o_acc[nb][2] *= alpha[1];
+      o_acc[nb][3] *= alpha[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {       // 16 kv rows per step
+#pragma unroll
+      for (int db2 = 0; db2 < 4; ++db2) {  // pairs of 8-wide d blocks
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, sVb + swz(ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), db2 * 2 + (lane >> 4)));
+        mma_bf16_16816(o_acc[db2 * 2], pf[ks], vf[0], vf[1]);
+        mma_bf16_16816(o_acc[db2 * 2 + 1], pf[ks], vf[2], vf[3]);
+      }
+    }
+    __syncthreads();  // everyone done with buf before it is refilled
+  }
+
+  // ---- finalise: O / l, stage through this warp's rows of sQ, coalesced 16 B stores
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+  const int r0 = warp * 16 + (lane >> 2);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int colb = ((lane & 3) * 2) * 2;  // byte offset inside the 16 B chunk
+    *reinterpret_cast<uint32_t*>(sQ + swz(r0, nb) + colb) = pack_bf16x2(o_acc[nb][0] * inv0, o_acc[nb][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + swz(r0 + 8, nb) + colb) = pack_bf16x2(o_acc[nb][2] * inv1, o_acc[nb][3] * inv1);
+  }
+  __syncwarp();
+  bf16* Ob = O + ((long long)b * Nq) * ldo + h * kAttD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane;
+    const int r = warp * 16 + (idx >> 3), c = idx & 7;
+    const int qr = q0 + r;
+    if (qr < Nq) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+      *reinterpret_cast<uint4*>(Ob + (long long)qr * ldo + c * 8) = v;
+    }
+  }
+}
+
+cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
+                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
+  dim3 grid((Nq + kAttBM - 1) / kAttBM, heads, B);
+  attention64_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
+                                                            scale * 1.4426950408889634f);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ row softmax
+// In-place softmax over bf16 rows (VAE mid-block single-head attention, d = 512: scores are materialised by the
+// batched GEMM, normalised here, then multiplied with V by a second GEMM).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(bf16* __restrict__ S, long long rows, int cols, int ld) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  bf16* s = S + row * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = cols / 8;
+  float mx = -INFINITY;
+  for (int v = tid; v < nv; v += 256) {
+    const uint4 u = reinterpret_cast<const uint4*>(s)[v];
+    float2 f;
+    f = unpack_bf16x2(u.x); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.y); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.z); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.w); mx = fmaxf(mx, fmaxf(f.x, f.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int v = tid; v < nv; v += 256) {
+    const uint4 u = reinterpret_cast<const uint4*>(s)[v];
+    float2 f;
+    f = unpack_bf16x2(u.x); sum += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.y); sum += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.z); sum += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.w); sum += __expf(f.x - mx) + __expf(f.y - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int v = tid; v < nv; v += 256) {
+    uint4 u = reinterpret_cast<const uint4*>(s)[v];
+    float2 f;
+    f = unpack_bf16x2(u.x); u.x = pack_bf16x2(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+    f = unpack_bf16x2(u.y); u.y = pack_bf16x2(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+    f = unpack_bf16x2(u.z); u.z = pack_bf16x2(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+    f = unpack_bf16x2(u.w); u.w = pack_bf16x2(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+    reinterpret_cast<uint4*>(s)[v] = u;
+  }
+}
+
+cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaStream_t stream) {
+  if (cols % 8 != 0 || ld % 8 != 0 || rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(S, rows, cols, ld);
+  return cudaGetLastError();
+}
+
+}  // namespace gdf

@@ -1,0 +1,217 @@
+// Bandwidth-bound helpers around the GEMMs: q_sample, nearest upsample, tiny-Cin im2col, dtype casts,
+// weight packing and the conditioning-embedding math (sinusoids + small fp32 linears).
+#include "ops.h"
+
+namespace gdf {
+
+// ---------------------------------------------------------------- nearest 2x upsample (NHWC bf16)
+// Reference: F.interpolate(scale_factor=2.0, mode="nearest") in feature/diffusers/models/upsampling.py:176-179.
+__global__ void upsample_nearest2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                          int C8) {
+  const long long total = (long long)B * (2 * H) * (2 * W) * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    y[i] = __ldg(x + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c);
+  }
+}
+cudaError_t launch_upsample_nearest2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t stream) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  upsample_nearest2x_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                        reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- im2col for Cin in {3, 4}
+// One thread per output pixel writes one 128-byte row A[m, 0..63] (k = (ky*3+kx)*Cin + c, zero padded).
+__global__ void im2col_small_kernel(const float* __restrict__ src_f32, const bf16* __restrict__ src_bf16,
+                                    bf16* __restrict__ A, int B, int H, int W, int Cin) {
+  const long long total = (long long)B * H * W;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(m % W);
+    long long r = m / W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    float v[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = y + ky - 1, ix = x + kx - 1;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        for (int c = 0; c < Cin; ++c) {
+          float t;
+          if (src_f32) t = __ldg(src_f32 + (((long long)b * Cin + c) * H + iy) * W + ix);
+          else t = __bfloat162float(src_bf16[(((long long)b * H + iy) * W + ix) * Cin + c]);
+          v[(ky * 3 + kx) * Cin + c] = t;
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(A + m * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 o;
+      o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+      o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+      o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+      o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+      dst[q] = o;
+    }
+  }
+}
+cudaError_t launch_im2col_small(const float* src_nchw_f32, const bf16* src_nhwc_bf16, bf16* A, int B, int H, int W,
+                                int Cin, cudaStream_t stream) {
+  if (Cin * 9 > 64 || (!src_nchw_f32 == !src_nhwc_bf16)) return cudaErrorInvalidValue;
+  const long long total = (long long)B * H * W;
+  const int blocks = (int)((total + 127) / 128 < 148 * 32 ? (total + 127) / 128 : 148 * 32);
+  im2col_small_kernel<<<blocks, 128, 0, stream>>>(src_nchw_f32, src_nhwc_bf16, A, B, H, W, Cin);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- posterior sample + q_sample
+// z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps_vae) * scaling_factor      (DiagonalGaussianDistribution.sample)
+// x_t = sqrt_ab * z + sqrt_1m_ab * eps_q                                      (scheduler.add_noise)
+// model input = x_t * input_scale                                            (scheduler.scale_model_input)
+__global__ void qsample_kernel(const float* __restrict__ moments, const float* __restrict__ eps_vae,
+                               const float* __restrict__ eps_q, float sf, float sqrt_ab, float sqrt_1m_ab,
+                               float input_scale, bf16* __restrict__ latent, __half* __restrict__ cap,
+                               float* __restrict__ latents_nchw, int B, int HW) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int p = (int)(i % HW);
+    const float* mo = moments + i * 8;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float mean = mo[c];
+      const float logvar = fminf(fmaxf(mo[4 + c], -30.f), 20.f);
+      const long long ni = ((long long)b * 4 + c) * HW + p;
+      const float z = (mean + expf(0.5f * logvar) * eps_vae[ni]) * sf;
+      const float xt = sqrt_ab * z + sqrt_1m_ab * eps_q[ni];
+      const float xin = xt * input_scale;
+      if (latents_nchw) latents_nchw[ni] = xt;
+      latent[i * 4 + c] = __float2bfloat16_rn(xin);
+      if (cap) cap[i * 4 + c] = __float2half_rn(xin);
+    }
+  }
+}
+cudaError_t launch_qsample(const float* moments, const float* eps_vae, const float* eps_q, float scaling_factor,
+                           float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc, __half* cap_unet_in,
+                           float* latents_nchw_f32, int B, int HW, cudaStream_t stream) {
+  const long long total = (long long)B * HW;
+  const int blocks = (int)((total + 255) / 256);
+  qsample_kernel<<<blocks, 256, 0, stream>>>(moments, eps_vae, eps_q, scaling_factor, sqrt_ab, sqrt_1m_ab,
+                                             input_scale, latent_nhwc, cap_unet_in, latents_nchw_f32, B, HW);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f16_kernel(const bf16* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(__bfloat162float(x[i]));
+}
+static int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  return (int)(b < 148 * 32 ? (b < 1 ? 1 : b) : 148 * 32);
+}
+cudaError_t launch_cast_f32_to_bf16(const float* x, bf16* y, long long n, cudaStream_t stream) {
+  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, stream>>>(x, y, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_cast_bf16_to_f16(const bf16* x, __half* y, long long n, cudaStream_t stream) {
+  cast_bf16_f16_kernel<<<grid_for(n), 256, 0, stream>>>(x, y, n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- conv weight packing
+// w[O][I][kh][kw] fp32 -> out[O_pad][k_pad] bf16, k = (ky*kw+kx)*I + c, zero padding rows/cols.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int O, int O_pad, int I,
+                                        int kh, int kw, int k_pad) {
+  const long long total = (long long)O_pad * k_pad;
+  const int Kreal = kh * kw * I;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % k_pad);
+    const int o = (int)(i / k_pad);
+    float v = 0.f;
+    if (o < O && k < Kreal) {
+      const int c = k % I;
+      const int tap = k / I;
+      const int ky = tap / kw, kx = tap % kw;
+      v = w[(((long long)o * I + c) * kh + ky) * kw + kx];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+cudaError_t launch_pack_conv_weight(const float* w_oihw, bf16* out, int O, int O_pad, int I, int kh, int kw, int k_pad,
+                                    cudaStream_t stream) {
+  pack_conv_weight_kernel<<<grid_for((long long)O_pad * k_pad), 256, 0, stream>>>(w_oihw, out, O, O_pad, I, kh, kw,
+                                                                                k_pad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- conditioning embeddings (fp32, tiny)
+// Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): emb = t * exp(-ln(10000) * i / half), out = [cos|sin]
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, j = i % half;
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);
+  const float a = t[r] * freq;
+  out[(long long)r * dim + j] = cosf(a);
+  out[(long long)r * dim + half + j] = sinf(a);
+}
+cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim, cudaStream_t stream) {
+  const int total = n * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, out, n, dim);
+  return cudaGetLastError();
+}
+
+// y[b, n] = (silu_in ? silu(x) : x)[b, :] . W[n, :] + bias[n]; one warp per output element.
+__global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
+                                    int act_in_silu, int act_out_silu) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (long long)B * N) return;
+  const int b = (int)(o / N), n = (int)(o % N);
+  const float* xr = x + (long long)b * K;
+  const float* wr = W + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = xr[k];
+    if (act_in_silu) xv = xv / (1.f + expf(-xv));
+    acc += xv * __ldg(wr + k);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float r = acc + (bias ? bias[n] : 0.f);
+    if (act_out_silu) r = r / (1.f + expf(-r));
+    y[o] = r;
+  }
+}
+cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
+                                int act_in_silu, int act_out_silu, cudaStream_t stream) {
+  const long long outs = (long long)B * N;
+  small_linear_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, stream>>>(x, W, b, y, B, K, N, act_in_silu, act_out_silu);
+  return cudaGetLastError();
+}
+
+}  // namespace gdf

@@ -1,0 +1,59 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a, shared by every dense contraction on the extraction path:
+//   linear layers (QKV, attention out-proj, FFN, proj_in/out, time-embedding MLPs),
+//   3x3 convolutions as implicit GEMM (stride 1 and stride 2, zero padding by TMA out-of-bounds fill),
+//   batched GEMMs (VAE single-head attention QK^T and PV).
+// Reference call sites this replaces: nn.Conv2d in feature/diffusers/models/resnet.py:341,366,
+// downsampling.py:147, upsampling.py:186-190; nn.Linear in attention_processor.py:3281-3289,3319,
+// attention.py:1253-1257 (FeedForward), transformers/transformer_2d.py:179,207.
+#pragma once
+#include "ptx.cuh"
+
+namespace gdf {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one swizzle row
+constexpr int kMaxBlockN = 256;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+constexpr int kStageBytesB = kMaxBlockN * kBlockK * 2;
+constexpr int kGemmSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2 };
+enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3 };
+
+struct CaptureSeg {   // fp16 side output of columns [col_begin, col_end) into a feature-arena slot
+  __half* ptr;        // slot base; element (row, col) goes to ptr[row * ld + (col - col_begin)]
+  int col_begin, col_end, ld;
+};
+
+struct GemmParams {
+  // ---- problem
+  int M, N, K;          // N counts accumulator columns (for GEGLU: 2x the output width)
+  int n_out;            // valid output columns (<= N, or <= N/2 for GEGLU); padding columns are dropped
+  int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
+  int num_m_tiles, num_n_tiles, num_k_blocks, batch;
+  int a_mode;
+  int b_batched;        // 1: B has a batch dimension, 0: shared
+  // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows
+  int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;
+  // ---- epilogue
+  float alpha;                 // accumulator scale (1.0 default)
+  const float* bias;           // [N] column bias (already permuted for GEGLU) or null
+  const float* bias_m;         // [M] row bias (transposed products) or null
+  const float* row_batch_bias; // [M / rows_per_batch, N] e.g. time-embedding projection, or null
+  int rows_per_batch;
+  int act;
+  const float* col_scale;      // [M / rows_per_batch, Nout] per-sample column gate applied before residual, or null
+  const __nv_bfloat16* residual; int ld_res;   // added after activation
+  float out_scale;             // multiplies (acc + residual), = 1/output_scale_factor
+  __nv_bfloat16* out;  int ld_out;  long long out_batch_stride;
+  __nv_bfloat16* out2; int ld_out2;            // second destination (skip-concat slice) or null
+  float* out_f32; int ld_out_f32;              // optional fp32 destination
+  __half* cap_pre; int ld_cap_pre;             // fp16 capture before residual add ("increment")
+  CaptureSeg cap[3];                           // fp16 captures of the final value
+  int num_cap;
+};
+
+}  // namespace gdf

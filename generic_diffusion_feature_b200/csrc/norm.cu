@@ -1,0 +1,242 @@
+// Fused GroupNorm(+SiLU) and LayerNorm(+AdaLN modulation) for NHWC / token-major bf16 activations.
+// HBM-bound: 128-bit coalesced accesses, fp32 statistics, warp-shuffle + shared-memory reductions.
+// Reference arithmetic: torch.nn.GroupNorm + SiLU in feature/diffusers/models/resnet.py:327-328,351,363,
+// unet/unet_2d_condition.py:1305-1306, transformers/transformer_2d.py:484; nn.LayerNorm and the
+// ada_norm_single modulation in feature/diffusers/models/attention.py:498-503,539,565,570-572.
+#include "ops.h"
+
+namespace gdf {
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxChunks = 64;
+constexpr int kGnMaxSlots = 2;  // channel slots (8 channels each) per thread: supports C <= 4096
+
+struct GnMap {      // thread -> (channel slot(s), pixel lane) mapping shared by both GroupNorm kernels
+  int c8;           // C / 8
+  int lanes;        // pixel lanes per block
+  int slots;        // slots per thread
+};
+__host__ __device__ inline GnMap gn_map(int C) {
+  GnMap m;
+  m.c8 = C / 8;
+  if (m.c8 <= kGnThreads) {
+    m.lanes = kGnThreads / m.c8;
+    m.slots = 1;
+  } else {
+    m.lanes = 1;
+    m.slots = (m.c8 + kGnThreads - 1) / kGnThreads;
+  }
+  return m;
+}
+
+size_t gn_workspace_floats(int B, int G) { return (size_t)B * kGnMaxChunks * G * 2 + (size_t)B * G * 2; }
+
+// Pass 1: per (chunk, image) partial sum / sum of squares per group.
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int nchunks) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const GnMap m = gn_map(C);
+  const int cpg = C / G;
+  if (threadIdx.x < 64) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int pix_per_chunk = (HW + nchunks - 1) / nchunks;
+  const int p0 = chunk * pix_per_chunk;
+  const int p1 = min(HW, p0 + pix_per_chunk);
+  const int lane_p = (m.slots == 1) ? (threadIdx.x / m.c8) : 0;
+  const bool active = (m.slots > 1) || (lane_p < m.lanes);
+  for (int si = 0; si < m.slots; ++si) {
+    const int slot = (m.slots == 1) ? (threadIdx.x % m.c8) : (threadIdx.x + si * kGnThreads);
+    if (!active || slot >= m.c8) continue;
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    const bf16* base = x + ((long long)b * HW) * C + slot * 8;
+    for (int p = p0 + lane_p; p < p1; p += m.lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * C));
+      float2 f;
+      f = unpack_bf16x2(u.x); sum[0] += f.x; sq[0] += f.x * f.x; sum[1] += f.y; sq[1] += f.y * f.y;
+      f = unpack_bf16x2(u.y); sum[2] += f.x; sq[2] += f.x * f.x; sum[3] += f.y; sq[3] += f.y * f.y;
+      f = unpack_bf16x2(u.z); sum[4] += f.x; sq[4] += f.x * f.x; sum[5] += f.y; sq[5] += f.y * f.y;
+      f = unpack_bf16x2(u.w); sum[6] += f.x; sq[6] += f.x * f.x; sum[7] += f.y; sq[7] += f.y * f.y;
+    }
+    // fold the 8 channels into their groups (a slot may straddle group boundaries)
+    int g_prev = (slot * 8) / cpg;
+    float gs = 0.f, gq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (slot * 8 + j) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], gs);
+        atomicAdd(&s_sq[g_prev], gq);
+        gs = gq = 0.f;
+        g_prev = g;
+      }
+      gs += sum[j];
+      gq += sq[j];
+    }
+    atomicAdd(&s_sum[g_prev], gs);
+    atomicAdd(&s_sq[g_prev], gq);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float* dst = partial + (((long long)b * nchunks + chunk) * G + threadIdx.x) * 2;
+    dst[0] = s_sum[threadIdx.x];
+    dst[1] = s_sq[threadIdx.x];
+  }
+}
+
+// Pass 2: reduce partials (double), normalise, affine, optional SiLU.
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ partial, int HW, int C, int G,
+                       int nchunks, float eps, int silu) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const GnMap m = gn_map(C);
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    double s = 0.0, q = 0.0;
+    const float* src = partial + ((long long)b * nchunks * G + threadIdx.x) * 2;
+    for (int c = 0; c < nchunks; ++c) {
+      s += (double)src[(long long)c * G * 2];
+      q += (double)src[(long long)c * G * 2 + 1];
+    }
+    const double n = (double)HW * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int pix_per_chunk = (HW + nchunks - 1) / nchunks;
+  const int p0 = chunk * pix_per_chunk;
+  const int p1 = min(HW, p0 + pix_per_chunk);
+  const int lane_p = (m.slots == 1) ? (threadIdx.x / m.c8) : 0;
+  const bool active = (m.slots > 1) || (lane_p < m.lanes);
+  for (int si = 0; si < m.slots; ++si) {
+    const int slot = (m.slots == 1) ? (threadIdx.x % m.c8) : (threadIdx.x + si * kGnThreads);
+    if (!active || slot >= m.c8) continue;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = slot * 8 + j;
+      const int g = c / cpg;
+      const float a = s_rstd[g] * __ldg(gamma + c);
+      sc[j] = a;
+      sh[j] = __ldg(beta + c) - s_mean[g] * a;
+    }
+    const long long base = ((long long)b * HW) * C + slot * 8;
+    for (int p = p0 + lane_p; p < p1; p += m.lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)p * C));
+      float v[8];
+      float2 f;
+      f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+      f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+      f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+      f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = v[j] * sc[j] + sh[j];
+        v[j] = silu ? silu_f(t) : t;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]);
+      o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(y + base + (long long)p * C) = o;
+    }
+  }
+}
+
+cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                             float eps, bool silu, float* workspace, cudaStream_t stream) {
+  if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > kGnThreads * kGnMaxSlots) return cudaErrorInvalidValue;
+  int nchunks = (HW + 31) / 32;
+  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
+  if (nchunks < 1) nchunks = 1;
+  dim3 grid(nchunks, B);
+  groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, workspace, HW, C, G, nchunks);
+  groupnorm_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, y, gamma, beta, workspace, HW, C, G, nchunks, eps,
+                                                          silu ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// One warp per token row; two passes over the row (second pass hits L1).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long long M, int C, float eps, const float* __restrict__ mod_scale,
+                 const float* __restrict__ mod_shift, int rows_per_batch) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const bf16* xr = x + row * C;
+  const int nv = C / 8;
+  float s = 0.f, q = 0.f;
+  for (int v = lane; v < nv; v += 32) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+    float2 f;
+    f = unpack_bf16x2(u.x); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.y); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.z); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.w); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float mean = s / C;
+  const float var = fmaxf(q / C - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float* ms = nullptr;
+  const float* mh = nullptr;
+  if (mod_scale) {
+    const long long b = row / rows_per_batch;
+    ms = mod_scale + b * C;
+    mh = mod_shift + b * C;
+  }
+  bf16* yr = y + row * C;
+  for (int v = lane; v < nv; v += 32) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+    float t[8];
+    float2 f;
+    f = unpack_bf16x2(u.x); t[0] = f.x; t[1] = f.y;
+    f = unpack_bf16x2(u.y); t[2] = f.x; t[3] = f.y;
+    f = unpack_bf16x2(u.z); t[4] = f.x; t[5] = f.y;
+    f = unpack_bf16x2(u.w); t[6] = f.x; t[7] = f.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      float r = (t[j] - mean) * rstd;
+      if (gamma) r = r * __ldg(gamma + c) + __ldg(beta + c);
+      if (ms) r = r * (1.f + __ldg(ms + c)) + __ldg(mh + c);
+      t[j] = r;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(t[0], t[1]);
+    o.y = pack_bf16x2(t[2], t[3]);
+    o.z = pack_bf16x2(t[4], t[5]);
+    o.w = pack_bf16x2(t[6], t[7]);
+    reinterpret_cast<uint4*>(yr)[v] = o;
+  }
+}
+
+cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* beta, long long M, int C,
+                             float eps, const float* mod_scale, const float* mod_shift, int rows_per_batch,
+                             cudaStream_t stream) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  const int rows_per_block = 8;
+  const long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift,
+                                                        rows_per_batch > 0 ? rows_per_batch : 1);
+  return cudaGetLastError();
+}
+
+}  // namespace gdf

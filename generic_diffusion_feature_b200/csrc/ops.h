@@ -1,0 +1,105 @@
+// Internal op layer: every kernel of the extraction path behind a plain host function. The C ABI
+// (gdf_api.cu) and the model executor (executor.cu) are both written against this header.
+#pragma once
+#include "gemm_sm100.cuh"
+#include "host_util.h"
+
+namespace gdf {
+
+typedef __nv_bfloat16 bf16;
+
+// A fully prepared GEMM launch: tensor maps + parameters. Built once at plan time, replayed per step.
+struct GemmLaunch {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  GemmParams p;
+};
+
+struct Epilogue {           // everything optional; zero-initialise then fill
+  float alpha = 1.f;
+  int n_out = 0;              // valid output columns; 0 = all (N, or N/2 for GEGLU)
+  const float* bias = nullptr;
+  const float* bias_m = nullptr;
+  const float* row_batch_bias = nullptr;
+  int rows_per_batch = 0;
+  int act = kActNone;
+  const float* col_scale = nullptr;
+  const bf16* residual = nullptr; int ld_res = 0;
+  float out_scale = 1.f;
+  bf16* out = nullptr; int ld_out = 0; long long out_batch_stride = 0;
+  bf16* out2 = nullptr; int ld_out2 = 0;
+  float* out_f32 = nullptr; int ld_out_f32 = 0;
+  __half* cap_pre = nullptr; int ld_cap_pre = 0;
+  CaptureSeg cap[3] = {};
+  int num_cap = 0;
+};
+
+int choose_block_n(int N, bool geglu);
+
+// C[M,N] = A[M,K] * W[N,K]^T, optionally batched (A: batch x M x K with a_batch_stride elements,
+// W shared when w_batch_stride == 0).
+int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, const bf16* W, int N, int ldw,
+                 const Epilogue& e, int batch = 1, long long a_batch_stride = 0, long long w_batch_stride = 0,
+                 int block_n = 0);
+
+// 3x3 convolution, NHWC bf16 contiguous input X[B, Hin, Win, Cin], packed weights Wp[Cout_padded][9*Cin]
+// (k = (ky*3+kx)*Cin + c). stride 1: pad 1. stride 2: pad_lo 1 (UNet, symmetric pad 1) or 0 (VAE, pad (0,1,0,1)).
+// Output rows are pixels of the output grid in (b, y, x) order; N = Cout (accumulator columns, multiple of 16).
+int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int N, int stride,
+                  int pad_lo, const Epilogue& e, int block_n = 0);
+
+cudaError_t launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, cudaStream_t stream);
+inline cudaError_t launch_gemm(const GemmLaunch& g, cudaStream_t s) { return launch_gemm(g.map_a, g.map_b, g.p, s); }
+
+// ---- normalisation (norm.cu)
+// GroupNorm(+SiLU) over NHWC bf16 x[B, HW, C] -> y[B, HW, C]; stats in fp32, workspace >= gn_workspace_floats().
+size_t gn_workspace_floats(int B, int G);
+cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                             float eps, bool silu, float* workspace, cudaStream_t stream);
+// LayerNorm over rows of x[M, C] (ld = C) with optional affine and optional per-sample modulation
+// y = LN(x) * (1 + scale[b]) + shift[b] (PixArt AdaLN-single), rows_per_batch rows per sample.
+cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* beta, long long M, int C,
+                             float eps, const float* mod_scale, const float* mod_shift, int rows_per_batch,
+                             cudaStream_t stream);
+
+// ---- attention (attention.cu): softmax(Q K^T * scale) V per (batch, head), head_dim 64.
+// Q[B*Nq, ldq] / K,V[B*Nk, ldk/ldv] / O[B*Nq, ldo]; head h lives in columns [h*64, h*64+64).
+cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
+                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
+// Row softmax in place over bf16 S[rows, cols] (ld), fp32 math (VAE single-head attention).
+cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaStream_t stream);
+
+// ---- elementwise / data movement (eltwise.cu)
+cudaError_t launch_upsample_nearest2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t stream);
+// im2col for tiny Cin (3 or 4): X -> A[M, 64] bf16 with k = (ky*3+kx)*Cin + c, zero padded to 64.
+//   src_nchw_f32: image (B, Cin, H, W) fp32;  src_nhwc_bf16: (B, H, W, Cin) bf16. Exactly one is non-null.
+cudaError_t launch_im2col_small(const float* src_nchw_f32, const bf16* src_nhwc_bf16, bf16* A, int B, int H, int W,
+                                int Cin, cudaStream_t stream);
+// Posterior sample + scaling + q_sample + scale_model_input (reference: pipeline_pixart_sigma.py:644-673,
+// diffusion_feature.py:406). moments: NHWC fp32 [B, HW, 8] (mean 0..3, logvar 4..7); eps_*: NCHW fp32 (B,4,h,w).
+cudaError_t launch_qsample(const float* moments, const float* eps_vae, const float* eps_q, float scaling_factor,
+                           float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc, __half* cap_unet_in,
+                           float* latents_nchw_f32, int B, int HW, cudaStream_t stream);
+cudaError_t launch_cast_f32_to_bf16(const float* x, bf16* y, long long n, cudaStream_t stream);
+cudaError_t launch_cast_bf16_to_f16(const bf16* x, __half* y, long long n, cudaStream_t stream);
+// fp32 OIHW conv weight -> bf16 [O_pad][kh*kw*I] (k = (ky*kw+kx)*I + c), rows >= O zero.
+cudaError_t launch_pack_conv_weight(const float* w_oihw, bf16* out, int O, int O_pad, int I, int kh, int kw,
+                                    int k_pad, cudaStream_t stream);
+// Sinusoidal timestep embedding (flip_sin_to_cos=True, freq_shift=0): out[n, dim] = [cos | sin].
+cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim, cudaStream_t stream);
+// small fp32 GEMV-style linear for the conditioning MLPs: y[B, N] = act(x[B, K]) W[N, K]^T + b
+cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
+                                int act_in_silu, int act_out_silu, cudaStream_t stream);
+
+// ---- feature stack + correspondence (stack.cu)
+struct ResizeSrc {
+  const __half* ptr;  // fp16 NHWC map [B, h*w, C]
+  int h, w, C, c_off; // c_off: channel offset inside the stack
+};
+// Bilinear (align_corners=False) resize of every map to (OH, OW) + channel concat. out_nhwc: [B, OH*OW, Ctot]
+// (fp16); out_nchw: [B, Ctot, OH, OW] (reference layout). sumsq (optional): [B, OH*OW] fp32 accumulated
+// squared L2 norm per pixel of the NHWC stack.
+cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, int OH, int OW, int Ctot,
+                                 __half* out_nhwc, __half* out_nchw, float* sumsq, cudaStream_t stream);
+
+}  // namespace gdf

@@ -1,0 +1,144 @@
+// Host-side construction of GEMM / implicit-GEMM launches (tensor maps + tiling).
+#include "ops.h"
+#include <string.h>
+
+namespace gdf {
+
+static int gcd_int(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+int choose_block_n(int N, bool geglu) {
+  const int step = geglu ? 64 : 32;
+  if (N <= kMaxBlockN && !geglu) return ((N + 15) / 16) * 16;
+  for (int bn = kMaxBlockN; bn >= step; bn -= step)
+    if (N % bn == 0) return bn;
+  return geglu ? 128 : 128;
+}
+
+static void fill_epilogue(GemmParams& p, const Epilogue& e) {
+  p.alpha = e.alpha;
+  p.n_out = e.n_out > 0 ? e.n_out : (e.act == kActGeglu ? p.N / 2 : p.N);
+  p.bias = e.bias;
+  p.bias_m = e.bias_m;
+  p.row_batch_bias = e.row_batch_bias;
+  p.rows_per_batch = e.rows_per_batch;
+  p.act = e.act;
+  p.col_scale = e.col_scale;
+  p.residual = e.residual;
+  p.ld_res = e.ld_res;
+  p.out_scale = e.out_scale;
+  p.out = e.out;
+  p.ld_out = e.ld_out;
+  p.out_batch_stride = e.out_batch_stride;
+  p.out2 = e.out2;
+  p.ld_out2 = e.ld_out2;
+  p.out_f32 = e.out_f32;
+  p.ld_out_f32 = e.ld_out_f32;
+  p.cap_pre = e.cap_pre;
+  p.ld_cap_pre = e.ld_cap_pre;
+  p.num_cap = e.num_cap;
+  for (int i = 0; i < 3; ++i) p.cap[i] = e.cap[i];
+}
+
+int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, const bf16* W, int N, int ldw,
+                 const Epilogue& e, int batch, long long a_batch_stride, long long w_batch_stride, int block_n) {
+  memset(g, 0, sizeof(*g));
+  GemmParams& p = g->p;
+  const bool geglu = (e.act == kActGeglu);
+  if (block_n <= 0) block_n = choose_block_n(N, geglu);
+  if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 64 != 0))
+    return fail(GDF_ERR_INVALID, "build_linear: bad block_n %d", block_n);
+  if (K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
+    return fail(GDF_ERR_SHAPE, "build_linear: K/lda/ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw);
+  if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffffLL) return fail(GDF_ERR_SHAPE, "build_linear: bad shape");
+  p.M = (int)M;
+  p.N = N;
+  p.K = K;
+  p.block_n = block_n;
+  p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_n_tiles = (N + block_n - 1) / block_n;
+  p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  p.batch = batch;
+  p.a_mode = kALinear;
+  p.b_batched = (w_batch_stride != 0) ? 1 : 0;
+  fill_epilogue(p, e);
+  {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? a_batch_stride : M * (long long)lda) * 2};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
+    GDF_TRY(make_tmap_bf16(&g->map_a, A, 3, dims, str, box));
+  }
+  {
+    const int wb = p.b_batched ? batch : 1;
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)wb};
+    uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    GDF_TRY(make_tmap_bf16(&g->map_b, W, 3, dims, str, box));
+  }
+  return GDF_OK;
+}
+
+int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int N, int stride,
+                  int pad_lo, const Epilogue& e, int block_n) {
+  memset(g, 0, sizeof(*g));
+  GemmParams& p = g->p;
+  if (Cin % kBlockK != 0) return fail(GDF_ERR_SHAPE, "build_conv3x3: Cin=%d must be a multiple of 64", Cin);
+  if (N % 16 != 0) return fail(GDF_ERR_SHAPE, "build_conv3x3: N=%d must be a multiple of 16 (pad the weights)", N);
+  if (stride != 1 && stride != 2) return fail(GDF_ERR_UNSUPPORTED, "build_conv3x3: stride %d", stride);
+  if (stride == 2 && ((Hin | Win) & 1)) return fail(GDF_ERR_SHAPE, "build_conv3x3: stride 2 needs even H, W");
+  if (block_n <= 0) block_n = choose_block_n(N, false);
+  const int H = Hin / stride, W = Win / stride;  // output grid
+  const int tw = gcd_int(W, kBlockM);
+  const int th = gcd_int(H, kBlockM / tw);
+  const int tb = kBlockM / (tw * th);
+  p.M = B * H * W;
+  p.N = N;
+  p.K = 9 * Cin;
+  p.block_n = block_n;
+  p.tiles_x = W / tw;
+  p.tiles_y = H / th;
+  const int tiles_b = (B + tb - 1) / tb;
+  p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+  p.num_n_tiles = (N + block_n - 1) / block_n;
+  p.num_k_blocks = 9 * (Cin / kBlockK);
+  p.batch = 1;
+  p.a_mode = (stride == 1) ? kAConvS1 : kAConvS2;
+  p.b_batched = 0;
+  p.B_img = B;
+  p.H = H;
+  p.W = W;
+  p.tw = tw;
+  p.th = th;
+  p.tb = tb;
+  p.cin_blocks = Cin / kBlockK;
+  p.pad_lo = pad_lo;
+  fill_epilogue(p, e);
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+    GDF_TRY(make_tmap_bf16(&g->map_a, X, 4, dims, str, box));
+  } else {
+    // (B, Hout, 2, Wout, 2*Cin): innermost merges (x parity, channel)
+    uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)W, 2, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {(uint64_t)2 * Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)2 * Win * Cin * 2,
+                       (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)tw, 1, (uint32_t)th, (uint32_t)tb};
+    GDF_TRY(make_tmap_bf16(&g->map_a, X, 5, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)N, 1};
+    uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)N * p.K * 2};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    GDF_TRY(make_tmap_bf16(&g->map_b, Wp, 3, dims, str, box));
+  }
+  return GDF_OK;
+}
+
+}  // namespace gdf

@@ -1,0 +1,191 @@
+/*
+ * gdf.h - C ABI of the B200-native feature-extraction hot path (libgdf_b200.so).
+ *
+ * The reference (Darkbblue/generic-diffusion-feature) is pure Python and has no FFI; its "operator API" for
+ * this path is the Python surface feature/diffusion_feature.py:26-40 (ctor), :222-235 (extract) plus the
+ * internal seam feature/components/feature_extractor.py:83-89 (FeatureGatherer.gather -> FeatureStore.store)
+ * and feature/components/models.py:10 (get_diffusion_model). This header is what a maintainer binds (ctypes,
+ * see INTEGRATION.md) to replace that seam: the denoiser / VAE forward of the diffusers modules and every
+ * gather() call become gdf_encode_noise + gdf_denoise_capture writing straight into a caller-owned arena.
+ *
+ * Conventions
+ *   - every pointer named *_dev is a device pointer owned by the caller (torch allocator); nothing is copied
+ *     to the host; all work is enqueued on the passed cudaStream_t (void* here to stay C-only);
+ *   - return value 0 = OK, negative = error (GDF_ERR_*); gdf_last_error() returns the message of the last
+ *     failure on the calling thread;
+ *   - a handle is thread-compatible: one thread at a time per handle, any number of handles per process
+ *     (the reference runs one extractor per GPU from Python threads, aggregation_network.py:86-93);
+ *   - activations are bf16 NHWC / token-major inside the library; captured features are fp16, laid out
+ *     [B, h*w, C] (token-major) in the arena. FeatureStore.store casts every map to fp16
+ *     (feature_extractor.py:59-60); ViT maps already come back token-major-strided from the reference
+ *     (einops view, :46-48), conv maps are exposed to Python as a permuted (B,C,h,w) view.
+ */
+#ifndef GDF_H_
+#define GDF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDF_OK 0
+#define GDF_ERR_INVALID (-1)
+#define GDF_ERR_CUDA (-2)
+#define GDF_ERR_UNSUPPORTED (-3)
+#define GDF_ERR_MISSING_WEIGHT (-4)
+#define GDF_ERR_SHAPE (-5)
+
+#define GDF_ABI_VERSION 1
+
+typedef struct gdf_handle_s* gdf_handle;
+
+const char* gdf_last_error(void);
+int gdf_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------ model level */
+
+/* Architecture description of the denoiser + VAE encoder; mirrors the diffusers config keys the reference
+ * relies on (unet/unet_2d_condition.py:171-484 ctor arguments). */
+#define GDF_MAX_LEVELS 4
+typedef struct gdf_unet_arch {
+  int in_channels;                    /* 4 */
+  int out_channels;                   /* 4 */
+  int num_levels;                     /* len(block_out_channels) */
+  int block_out_channels[GDF_MAX_LEVELS];
+  int layers_per_block;               /* 2 */
+  int down_has_attn[GDF_MAX_LEVELS];  /* CrossAttnDownBlock2D (1) vs DownBlock2D (0) */
+  int up_has_attn[GDF_MAX_LEVELS];    /* CrossAttnUpBlock2D vs UpBlock2D, in up_blocks order */
+  int transformer_depth[GDF_MAX_LEVELS]; /* transformer_layers_per_block, down order (mid uses the last) */
+  int num_heads[GDF_MAX_LEVELS];      /* attention heads per level, down order */
+  int cross_attention_dim;            /* 768 / 1024 / 2048 */
+  int use_linear_projection;          /* 0: 1x1 conv proj_in/out (SD-1.5), 1: Linear (SD-2.1 / SDXL) */
+  int addition_time_embed_dim;        /* 256 for SDXL text_time conditioning, 0 = none */
+  int projection_class_embeddings_input_dim; /* 2816 for SDXL */
+  int norm_num_groups;                /* 32 */
+  float norm_eps;                     /* 1e-5 */
+} gdf_unet_arch;
+
+typedef struct gdf_vae_arch {
+  int in_channels;                    /* 3 */
+  int latent_channels;                /* 4 */
+  int num_levels;                     /* 4 */
+  int block_out_channels[GDF_MAX_LEVELS]; /* 128,256,512,512 */
+  int layers_per_block;               /* 2 */
+  int norm_num_groups;                /* 32 */
+  float norm_eps;                     /* 1e-6 */
+  float scaling_factor;               /* 0.18215 / 0.13025 */
+} gdf_vae_arch;
+
+/* replaces get_diffusion_model (feature/components/models.py:10): the handle owns packed bf16 weights */
+int gdf_create(const gdf_unet_arch* unet, const gdf_vae_arch* vae, int device, gdf_handle* out);
+int gdf_destroy(gdf_handle h);
+
+/* Weights by diffusers parameter name ("unet.down_blocks.0.resnets.0.conv1.weight", "vae.encoder.conv_in.weight",
+ * ...), fp32 device tensors in their PyTorch layouts (Linear [out,in], Conv2d OIHW). Packed to bf16 on device.
+ * Call repeatedly, then gdf_finalize_weights once (checks that every parameter the architecture needs arrived). */
+int gdf_load_weights(gdf_handle h, const char* const* names, const void* const* ptrs_dev, const int64_t* shapes,
+                     const int* ranks, int n, void* stream);
+int gdf_finalize_weights(gdf_handle h, void* stream);
+
+/* Feature plan: replaces prepare_feature_extractor (feature/components/feature_extractor.py:92-288).
+ * ids are the reference's feature ids (feature/configs/*.json keys). For each accepted id the library returns
+ * the arena slot: byte offset, channels, height, width. cross-k / cross-v are rejected exactly like
+ * FeatureStore.store drops them (feature_extractor.py:38-39): offset = -1. Unknown ids -> GDF_ERR_INVALID. */
+typedef struct gdf_slot {
+  int64_t offset_bytes;               /* -1: id accepted by the grammar but never stored (cross-k/v) */
+  int channels, height, width;
+  int order;                          /* execution order index (the reference's dict insertion order) */
+} gdf_slot;
+int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch, int img_size, gdf_slot* slots_out,
+             int64_t* arena_bytes_out);
+
+/* images -> VAE-encoded, noised, scaled latents (replaces pipe.prepare_latents + scheduler.scale_model_input;
+ * pipelines/pixart_alpha/pipeline_pixart_sigma.py:598-677, diffusion_feature.py:371-380,405-406).
+ *   images_dev : fp32 (B,3,S,S) in [-1,1];  eps_vae_dev / eps_q_dev : fp32 (B,4,S/8,S/8) injected noise
+ *   sqrt_alpha_bar / sqrt_one_minus_alpha_bar : q_sample coefficients of the resolved timestep
+ *   input_scale : scale_model_input factor (Euler: 1/sqrt(sigma^2+1) applied on x = z + sigma*eps)
+ *   latents_out_dev : optional fp32 (B,4,S/8,S/8) copy of the noised latents (before input scaling) */
+int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_dev, const void* eps_q_dev,
+                     float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,
+                     void* stream);
+
+/* One denoiser forward with capture (replaces pipe.unet(...) at diffusion_feature.py:446-465 and every
+ * feature_gatherer.gather call site listed in SURVEY.md 2.2).
+ *   timestep : resolved scheduler timestep (float, e.g. 50.0)
+ *   ctx_dev : fp32 (B, ctx_len, cross_attention_dim) encoder hidden states
+ *   pooled_dev : fp32 (B, 1280) pooled text embeds or NULL; add_time_ids_dev : fp32 (B, 6) or NULL
+ *   arena_dev : caller-owned arena of arena_bytes; noise_pred_out_dev : optional fp32 (B,4,h,w) */
+int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* pooled_dev,
+                        const void* add_time_ids_dev, void* arena_dev, void* noise_pred_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ op level
+ * Each hot kernel behind a plain entry point: used by the parity tests, by bench.py's roofline probe and by the
+ * Python feature-stack / correspondence helpers. */
+
+typedef struct gdf_capture_seg {
+  void* ptr_dev;          /* fp16 destination, row pitch ld */
+  int col_begin, col_end, ld;
+} gdf_capture_seg;
+
+typedef struct gdf_epilogue {
+  float alpha;            /* accumulator scale; 0 is treated as 1 */
+  int n_out;              /* valid output columns, 0 = all */
+  const void* bias_dev;           /* fp32 [N] */
+  const void* bias_m_dev;         /* fp32 [M] */
+  const void* row_batch_bias_dev; /* fp32 [M/rows_per_batch, N] */
+  int rows_per_batch;
+  int act;                /* 0 none, 1 GEGLU(erf), 2 GELU-tanh, 3 SiLU */
+  const void* col_scale_dev;      /* fp32 [M/rows_per_batch, n_out] */
+  const void* residual_dev; int ld_res;    /* bf16 */
+  float out_scale;        /* 0 is treated as 1 */
+  void* out_dev; int ld_out; int64_t out_batch_stride;   /* bf16 */
+  void* out2_dev; int ld_out2;                           /* bf16 */
+  void* out_f32_dev; int ld_out_f32;
+  void* cap_pre_dev; int ld_cap_pre;                     /* fp16, before residual */
+  gdf_capture_seg cap[3]; int num_cap;                   /* fp16, final value */
+} gdf_epilogue;
+
+/* C[M,N] = A[M,K] W[N,K]^T (+ fused epilogue); batch > 1: A/out strided by *_batch_stride elements,
+ * W shared if w_batch_stride == 0. (nn.Linear: attention_processor.py:3281-3289,3319; attention.py:1253-1257) */
+int gdf_op_linear(const void* a_dev, int64_t M, int K, int lda, const void* w_dev, int N, int ldw,
+                  const gdf_epilogue* ep, int batch, int64_t a_batch_stride, int64_t w_batch_stride, int block_n,
+                  void* stream);
+/* 3x3 convolution as implicit GEMM over NHWC bf16 (nn.Conv2d: resnet.py:341,366; downsampling.py:147).
+ * w_packed_dev: bf16 [N][9*Cin], k = (ky*3+kx)*Cin + c (gdf_op_pack_conv_weight). */
+int gdf_op_conv3x3(const void* x_dev, int B, int Hin, int Win, int Cin, const void* w_packed_dev, int N, int stride,
+                   int pad_lo, const gdf_epilogue* ep, int block_n, void* stream);
+int gdf_op_pack_conv_weight(const void* w_oihw_f32_dev, void* out_bf16_dev, int O, int O_pad, int I, int kh, int kw,
+                            int k_pad, void* stream);
+/* GroupNorm(+SiLU) NHWC bf16 (resnet.py:327-328). workspace_dev: fp32, gdf_op_groupnorm_workspace_floats(B,G). */
+int64_t gdf_op_groupnorm_workspace_floats(int B, int G);
+int gdf_op_groupnorm(const void* x_dev, void* y_dev, const void* gamma_dev, const void* beta_dev, int B, int HW,
+                     int C, int G, float eps, int silu, void* workspace_dev, void* stream);
+/* LayerNorm (+ AdaLN-single modulation) (attention.py:498-503,539,565) */
+int gdf_op_layernorm(const void* x_dev, void* y_dev, const void* gamma_dev, const void* beta_dev, int64_t M, int C,
+                     float eps, const void* mod_scale_dev, const void* mod_shift_dev, int rows_per_batch,
+                     void* stream);
+/* softmax(QK^T*scale)V, head_dim 64 (attention_processor.py:3311-3313) */
+int gdf_op_attention(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv, void* o_dev,
+                     int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale, void* stream);
+int gdf_op_softmax_rows(void* s_dev, int64_t rows, int cols, int ld, void* stream);
+int gdf_op_upsample_nearest2x(const void* x_dev, void* y_dev, int B, int H, int W, int C, void* stream);
+int gdf_op_im2col_small(const void* src_nchw_f32_dev, const void* src_nhwc_bf16_dev, void* a_dev, int B, int H,
+                        int W, int Cin, void* stream);
+int gdf_op_qsample(const void* moments_dev, const void* eps_vae_dev, const void* eps_q_dev, float scaling_factor,
+                   float sqrt_ab, float sqrt_1m_ab, float input_scale, void* latent_nhwc_dev, void* cap_unet_in_dev,
+                   void* latents_nchw_f32_dev, int B, int HW, void* stream);
+int gdf_op_cast_f32_to_bf16(const void* x_dev, void* y_dev, int64_t n, void* stream);
+
+/* Feature stack (aggregation_network.py:62-66): bilinear resize of n_src captured maps to (OH, OW) + concat. */
+typedef struct gdf_resize_src {
+  const void* ptr_dev;    /* fp16 [B, h*w, C] */
+  int h, w, C, c_off;
+} gdf_resize_src;
+int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, int OW, int Ctot, void* out_nhwc_dev,
+                         void* out_nchw_dev, void* sumsq_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDF_H_ */

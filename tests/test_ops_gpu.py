@@ -1,0 +1,272 @@
+"""Per-kernel parity tests, called through the C ABI (ctypes -> libgdf_b200.so) on a B200.
+
+Each CUDA kernel is compared with a plain PyTorch fp32 evaluation of the same op on the same seeded inputs.
+Tolerances are for bf16 inputs/outputs with fp32 accumulation: relative L2 error <= 1e-2 (bf16 has 8 bits of
+mantissa, rounding of the output alone is 2^-9 relative) and cosine similarity >= 0.9999.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from generic_diffusion_feature_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    a = a.float().flatten()
+    b = b.float().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def cos_sim(a, b):
+    return F.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0).item()
+
+
+def check_close(got, want, tol=1e-2, what=""):
+    assert torch.isfinite(got.float()).all(), what + ": non-finite output"
+    r, c = rel_err(got, want), cos_sim(got, want)
+    assert r <= tol and c >= 0.9999, "%s: rel_err %.3e cos %.6f" % (what, r, c)
+
+
+def _rand_bf16(gen, *shape, scale=1.0, dev="cuda"):
+    return (torch.randn(*shape, generator=gen, device=dev) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 320, 640), (128, 16, 64), (1024, 1920, 640), (4096, 1280, 5120),
+                                    (77 * 2, 2560, 2048), (130, 640, 2816)])
+def test_linear_bias(cuda_dev, M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = _rand_bf16(g, M, K)
+    w = _rand_bf16(g, N, K, scale=K ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.linear(a, w, ops.make_epilogue(out=out, bias=bias))
+    torch.cuda.synchronize()
+    check_close(out, a.float() @ w.float().T + bias, what="linear %dx%dx%d" % (M, N, K))
+
+
+def test_linear_full_epilogue(cuda_dev):
+    """bias + per-sample row bias + residual + out_scale + pre/post captures + second destination + fp32 out."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, rows, N, K = 3, 200, 640, 320
+    M = B * rows
+    a = _rand_bf16(g, M, K)
+    w = _rand_bf16(g, N, K, scale=K ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    rbb = torch.randn(B, N, generator=g, device="cuda")
+    res = _rand_bf16(g, M, N)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    big = torch.zeros(M, N + 320, dtype=torch.bfloat16, device="cuda")  # concat buffer: write into [:, 320:]
+    out2 = big[:, 320:]
+    of32 = torch.zeros(M, N, device="cuda")
+    cap_pre = torch.zeros(M, N, dtype=torch.float16, device="cuda")
+    cap_a = torch.zeros(M, 320, dtype=torch.float16, device="cuda")
+    cap_b = torch.zeros(M, 320, dtype=torch.float16, device="cuda")
+    ep = ops.make_epilogue(out=out, bias=bias, row_batch_bias=rbb, rows_per_batch=rows, residual=res, out_scale=0.5,
+                           out2=out2, out_f32=of32, cap_pre=cap_pre, caps=[(cap_a, 0, 320), (cap_b, 320, 640)])
+    ops.linear(a, w, ep)
+    torch.cuda.synchronize()
+    pre = a.float() @ w.float().T + bias + rbb.repeat_interleave(rows, 0)
+    want = (pre + res.float()) * 0.5
+    check_close(cap_pre, pre, what="cap_pre")
+    check_close(out, want, what="out")
+    check_close(out2, want, what="out2 (strided)")
+    check_close(of32, want, tol=2e-3, what="out_f32")
+    check_close(cap_a, want[:, :320], what="cap seg 0")
+    check_close(cap_b, want[:, 320:], what="cap seg 1")
+    assert big[:, :320].abs().max().item() == 0, "strided destination wrote outside its slice"
+
+
+def test_linear_geglu(cuda_dev):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, C = 520, 640
+    inner = 4 * C
+    a = _rand_bf16(g, M, C)
+    w = _rand_bf16(g, 2 * inner, C, scale=C ** -0.5)
+    bias = torch.randn(2 * inner, generator=g, device="cuda") * 0.1
+    bn = 256
+    half = bn // 2
+    # interleave value / gate rows per 256-column tile (what the weight packer does for GEGLU)
+    idx = []
+    for t in range(inner // half):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device="cuda")
+    out = torch.zeros(M, inner, dtype=torch.bfloat16, device="cuda")
+    cap = torch.zeros(M, inner, dtype=torch.float16, device="cuda")
+    ep = ops.make_epilogue(out=out, bias=bias[idx].contiguous(), act=ops.ACT_GEGLU, caps=[(cap, 0, inner)])
+    ops.linear(a, w[idx].contiguous(), ep, block_n=bn)
+    torch.cuda.synchronize()
+    proj = a.float() @ w.float().T + bias
+    want = proj[:, :inner] * F.gelu(proj[:, inner:])
+    check_close(out, want, what="geglu out")
+    check_close(cap, want, what="geglu capture")
+
+
+def test_linear_batched_and_rowbias(cuda_dev):
+    """QK^T-style batched product with alpha, and a transposed product with a row (M) bias."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Bt, N, D = 3, 384, 512
+    q = _rand_bf16(g, Bt, N, D)
+    k = _rand_bf16(g, Bt, N, D)
+    s = torch.zeros(Bt, N, N, dtype=torch.bfloat16, device="cuda")
+    ep = ops.make_epilogue(out=s, alpha=D ** -0.5, out_batch_stride=N * N)
+    ops.linear(q, k, ep, batch=Bt, a_batch_stride=N * D, w_batch_stride=N * D)
+    torch.cuda.synchronize()
+    check_close(s, torch.einsum("bnd,bmd->bnm", q.float(), k.float()) * D ** -0.5, what="batched QK^T")
+    # V^T = Wv X^T + b[:, None]
+    x = _rand_bf16(g, N, D)
+    wv = _rand_bf16(g, D, D, scale=D ** -0.5)
+    bv = torch.randn(D, generator=g, device="cuda")
+    vt = torch.zeros(D, N, dtype=torch.bfloat16, device="cuda")
+    ops.linear(wv, x, ops.make_epilogue(out=vt, bias_m=bv))
+    torch.cuda.synchronize()
+    check_close(vt, wv.float() @ x.float().T + bv[:, None], what="transposed product with row bias")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,pad_lo", [
+    (2, 32, 32, 64, 128, 1, 1), (1, 128, 128, 128, 64, 1, 1), (3, 16, 16, 320, 320, 1, 1),
+    (2, 8, 8, 128, 256, 1, 1), (2, 64, 64, 64, 4, 1, 1), (2, 64, 64, 128, 128, 2, 1),
+    (2, 64, 64, 128, 128, 2, 0), (1, 256, 256, 64, 64, 2, 0), (5, 4, 4, 64, 64, 1, 1)])
+def test_conv3x3(cuda_dev, B, H, W, Cin, Cout, stride, pad_lo):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = _rand_bf16(g, B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, device="cuda") * (9 * Cin) ** -0.5
+    bias = torch.randn(Cout, generator=g, device="cuda")
+    wq = w.to(torch.bfloat16).float()
+    if stride == 1:
+        want = F.conv2d(x.float(), wq, bias, padding=1)
+    elif pad_lo == 1:
+        want = F.conv2d(x.float(), wq, bias, stride=2, padding=1)
+    else:
+        want = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wq, bias, stride=2)
+    Ho, Wo = want.shape[-2:]
+    wp = ops.pack_conv_weight(w)
+    npad = wp.shape[0]
+    bias_p = torch.zeros(npad, device="cuda")
+    bias_p[:Cout] = bias
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(B * Ho * Wo, Cout, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3(x_nhwc, wp, ops.make_epilogue(out=out, bias=bias_p, n_out=Cout), stride=stride, pad_lo=pad_lo)
+    torch.cuda.synchronize()
+    got = out.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    check_close(got, want, what="conv3x3 B%d %dx%d %d->%d s%d p%d" % (B, H, W, Cin, Cout, stride, pad_lo))
+
+
+@pytest.mark.parametrize("B,HW,C,silu", [(2, 64 * 64, 320, True), (3, 32 * 32, 1920, True), (2, 128 * 128, 128, True),
+                                         (1, 16 * 16, 2560, False), (2, 1024, 960, True), (2, 77, 640, True)])
+def test_groupnorm(cuda_dev, B, HW, C, silu):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = (torch.randn(B, HW, C, generator=g, device="cuda") * 2 + 0.5).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(C, generator=g, device="cuda")
+    y = ops.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+    torch.cuda.synchronize()
+    want = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    if silu:
+        want = F.silu(want)
+    check_close(y, want.permute(0, 2, 1), what="groupnorm C%d" % C)
+
+
+@pytest.mark.parametrize("M,C,mod", [(1000, 640, False), (333, 1280, False), (512, 1152, True), (64, 320, False)])
+def test_layernorm(cuda_dev, M, C, mod):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(M, C, generator=g, device="cuda") * 3 + 1).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(C, generator=g, device="cuda")
+    if mod:
+        rows = M // 2
+        sc = 0.1 * torch.randn(2, C, generator=g, device="cuda")
+        sh = 0.1 * torch.randn(2, C, generator=g, device="cuda")
+        y = ops.layernorm(x, None, None, 1e-6, sc, sh, rows)
+        want = F.layer_norm(x.float(), (C,), None, None, 1e-6)
+        want = want * (1 + sc.repeat_interleave(rows, 0)) + sh.repeat_interleave(rows, 0)
+    else:
+        y = ops.layernorm(x, gamma, beta, 1e-5)
+        want = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    check_close(y, want, what="layernorm")
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk", [(2, 4, 1024, 1024), (1, 10, 4096, 4096), (2, 5, 1024, 77), (1, 2, 200, 300),
+                                           (3, 1, 64, 64)])
+def test_attention64(cuda_dev, B, heads, Nq, Nk):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    C = heads * 64
+    # q/k/v as column slices of a fused projection output (exercises the row pitch)
+    qkv = _rand_bf16(g, B * Nq, 3 * C) if Nq == Nk else None
+    if qkv is not None:
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q = _rand_bf16(g, B * Nq, C)
+        kv = _rand_bf16(g, B * Nk, 2 * C)
+        k, v = kv[:, :C], kv[:, C:]
+    o = ops.attention(q, k, v, B, heads, Nq, Nk, 64 ** -0.5)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Nq, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Nk, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Nk, heads, 64).transpose(1, 2)
+    want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Nq, C)
+    check_close(o, want, what="attention B%d h%d %dx%d" % (B, heads, Nq, Nk))
+
+
+def test_softmax_rows(cuda_dev):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    s = (torch.randn(300, 2048, generator=g, device="cuda") * 4).to(torch.bfloat16)
+    want = torch.softmax(s.float(), dim=-1)
+    ops.softmax_rows_(s)
+    torch.cuda.synchronize()
+    check_close(s, want, what="softmax rows")
+
+
+def test_upsample_and_im2col(cuda_dev):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(10)
+    x = _rand_bf16(g, 2, 16, 16, 64)
+    y = ops.upsample_nearest2x(x)
+    torch.cuda.synchronize()
+    want = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(y.float(), want), "nearest upsample must be exact"
+    img = torch.rand(2, 3, 32, 32, generator=g, device="cuda") * 2 - 1
+    a = ops.im2col_small(img, nchw_f32=True)
+    torch.cuda.synchronize()
+    cols = F.unfold(img, 3, padding=1)  # (B, C*9, L) with index c*9 + tap
+    cols = cols.view(2, 3, 9, 32 * 32).permute(0, 3, 2, 1).reshape(2 * 32 * 32, 27)  # -> tap*3 + c
+    assert torch.equal(a[:, :27].float(), cols.to(torch.bfloat16).float())
+    assert a[:, 27:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("out_hw", [(128, 128), (48, 48)])
+def test_resize_concat(cuda_dev, out_hw):
+    """aggregation_network.py:62-66: F.interpolate(f, size, mode='bilinear') for every map, then cat."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B = 2
+    maps_nchw = [torch.randn(B, 1280, 32, 32, generator=g, device="cuda").half(),
+                 torch.randn(B, 640, 64, 64, generator=g, device="cuda").half(),
+                 torch.randn(B, 64, 128, 128, generator=g, device="cuda").half()]
+    maps = [m.permute(0, 2, 3, 1).reshape(B, -1, m.shape[1]).contiguous() for m in maps_nchw]
+    r = ops.resize_concat(maps, out_hw, nhwc=True, nchw=True, with_sumsq=True)
+    torch.cuda.synchronize()
+    want = torch.cat([F.interpolate(m, out_hw, mode="bilinear") for m in maps_nchw], dim=1)  # fp16 like the reference
+    got_nchw = r["nchw"]
+    got_nhwc = r["nhwc"].view(B, out_hw[0], out_hw[1], -1).permute(0, 3, 1, 2)
+    # fp16 outputs of the same fp32 interpolation: allow 1 ulp of fp16
+    assert (got_nchw.float() - want.float()).abs().max().item() <= 4e-3
+    assert torch.equal(got_nchw, got_nhwc.contiguous()), "NHWC and NCHW stacks must hold identical values"
+    ss = (r["nhwc"].float() ** 2).sum(-1)
+    assert rel_err(r["sumsq"], ss) < 1e-5
