@@ -1,0 +1,590 @@
+"""CPU oracle of the extraction hot path: a plain-PyTorch fp32 restatement of the reference's arithmetic.
+
+TEST INFRASTRUCTURE ONLY. Nothing under generic_diffusion_feature_b200/ may import this file; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do. It is the checker, never the
+product path.
+
+Pinning status: the reference ships no tests or golden vectors and its arithmetic lives in
+diffusers==0.32.2, which is not installed here. The modules the reference vendors (feature/diffusers/models/
+resnet.py, attention.py, attention_processor.py, transformers/transformer_2d.py, downsampling.py,
+upsampling.py, unet/unet_2d_condition.py) ARE executed in this container through an import shim
+(tools/make_golden.py) and this restatement is checked against them module by module and end to end; the
+resulting vectors are committed under tests/golden/. The un-vendored pieces (unet_2d_blocks wiring,
+embeddings.Timesteps/TimestepEmbedding, activations.GEGLU, AutoencoderKL encoder, schedulers) are restated from
+the published diffusers 0.32.2 semantics -> for those: PARITY UNPINNED.
+
+Every class cites the reference file:line it follows. Attribute names mirror diffusers so that (a) the
+reference's own prepare_feature_extractor (feature/components/feature_extractor.py:92-288) can attach its
+FeatureGatherers to this tree unchanged and (b) state_dict keys equal the diffusers parameter names.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------ capture plumbing
+class FeatureStore:
+    """feature/components/feature_extractor.py:8-80 with train_unet=True semantics (no fp16 / cuda cast), so
+    the oracle returns fp32 maps. Filtering, cross-k/v drop, (b (h w) c -> b c h w) and insertion order kept."""
+
+    def __init__(self, to_store):
+        self.to_store = dict(to_store) if to_store else {}
+        self.accept_all = not to_store
+        self.feats = {}
+
+    def reset(self):
+        self.feats = {}
+
+    def store(self, feat, feat_id):
+        if (feat_id in self.to_store and self.to_store[feat_id]) or self.accept_all:
+            if "cross-k" in feat_id or "cross-v" in feat_id:   # :38-39
+                return
+            if feat.dim() == 3:                                  # :46-48
+                size = int(math.sqrt(feat.shape[1]))
+                feat = feat.reshape(feat.shape[0], size, size, feat.shape[2]).permute(0, 3, 1, 2)
+            self.feats[feat_id] = feat.detach().clone()          # TF.normalize(mean=0,std=1) is an identity clone :56
+
+    @property
+    def stored_feats(self):
+        return self.feats
+
+
+class FeatureGatherer:
+    """feature_extractor.py:83-89"""
+
+    def __init__(self, module_id, feature_store):
+        self.module_id = module_id
+        self.feature_store = feature_store
+
+    def gather(self, feat, feat_id):
+        self.feature_store.store(feat, "-".join([self.module_id, feat_id]))
+
+
+def attach_gatherers(unet, store):
+    """Id grammar of prepare_feature_extractor for UNets (feature_extractor.py:125-249), restated."""
+    unet.feature_gatherer = FeatureGatherer("unet", store)
+
+    def do_level(prefix, level, samplers_attr, sampler_name):
+        for j in range(len(level.resnets)):
+            level.resnets[j].feature_gatherer = FeatureGatherer("-".join(prefix + ["repeat%d" % j, "res"]), store)
+            if hasattr(level, "attentions") and len(level.attentions) > 0:
+                vit = level.attentions[j]
+                vit.feature_gatherer = FeatureGatherer("-".join(prefix + ["repeat%d" % j, "vit"]), store)
+                for k, blk in enumerate(vit.transformer_blocks):
+                    bid = prefix + ["repeat%d" % j, "vit", "block%d" % k]
+                    blk.feature_gatherer = FeatureGatherer("-".join(bid), store)
+                    blk.attn1.feature_gatherer = FeatureGatherer("-".join(bid + ["self"]), store)
+                    blk.attn2.feature_gatherer = FeatureGatherer("-".join(bid + ["cross"]), store)
+                    blk.ff.feature_gatherer = FeatureGatherer("-".join(bid + ["ffn"]), store)
+        samplers = getattr(level, samplers_attr, None)
+        if samplers:
+            for s in samplers:
+                s.feature_gatherer = FeatureGatherer("-".join(prefix + [sampler_name]), store)
+
+    for i, level in enumerate(unet.down_blocks):
+        do_level(["down", "level%d" % i], level, "downsamplers", "downsampler")
+    mid = unet.mid_block
+    for j in range(len(mid.resnets)):
+        mid.resnets[j].feature_gatherer = FeatureGatherer("mid-repeat%d-res" % j, store)
+    mid.attentions[0].feature_gatherer = FeatureGatherer("mid-vit", store)
+    for k, blk in enumerate(mid.attentions[0].transformer_blocks):
+        bid = ["mid", "vit", "block%d" % k]
+        blk.feature_gatherer = FeatureGatherer("-".join(bid), store)
+        blk.attn1.feature_gatherer = FeatureGatherer("-".join(bid + ["self"]), store)
+        blk.attn2.feature_gatherer = FeatureGatherer("-".join(bid + ["cross"]), store)
+        blk.ff.feature_gatherer = FeatureGatherer("-".join(bid + ["ffn"]), store)
+    for i, level in enumerate(unet.up_blocks):
+        do_level(["up", "level%d" % i], level, "upsamplers", "upsampler")
+
+
+def _gather(mod, x, tag):
+    if hasattr(mod, "feature_gatherer"):
+        mod.feature_gatherer.gather(x, tag)
+
+
+# ------------------------------------------------------------------------------------------ building blocks
+class ResnetBlock2D(nn.Module):
+    """feature/diffusers/models/resnet.py:320-379 (time_embedding_norm='default', output_scale_factor=1)."""
+
+    def __init__(self, cin, cout, temb_ch, groups=32, eps=1e-5):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_ch, cout) if temb_ch else None
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb=None):
+        h = self.conv1(F.silu(self.norm1(x)))
+        if self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        _gather(self, h, "increment")
+        out = x + h
+        _gather(self, out, "out")
+        return out
+
+
+class Downsample2D(nn.Module):
+    """feature/diffusers/models/downsampling.py:132-152; padding=0 -> F.pad (0,1,0,1) (VAE encoder)."""
+
+    def __init__(self, ch, padding=1):
+        super().__init__()
+        self.padding = padding
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=padding)
+
+    def forward(self, x):
+        if self.padding == 0:
+            x = F.pad(x, (0, 1, 0, 1))
+        x = self.conv(x)
+        _gather(self, x, "out")
+        return x
+
+
+class Upsample2D(nn.Module):
+    """feature/diffusers/models/upsampling.py:142-195 (nearest x2 then conv3x3)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        _gather(self, x, "out")
+        return x
+
+
+class Attention(nn.Module):
+    """feature/diffusers/models/attention_processor.py:105-297 (ctor) + AttnProcessor2_0 :3244-3331.
+    q/k/v are gathered before the head split (:3291-3294)."""
+
+    def __init__(self, dim, heads, ctx_dim=None, bias=False, out_bias=True):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, bias=bias)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=bias)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim, bias=out_bias), nn.Identity()])
+
+    def forward(self, x, ctx=None):
+        B, N, C = x.shape
+        ctx = x if ctx is None else ctx
+        q, k, v = self.to_q(x), self.to_k(ctx), self.to_v(ctx)
+        _gather(self, q, "q")
+        _gather(self, k, "k")
+        _gather(self, v, "v")
+        d = C // self.heads
+        q = q.view(B, -1, self.heads, d).transpose(1, 2)
+        k = k.view(B, -1, self.heads, d).transpose(1, 2)
+        v = v.view(B, -1, self.heads, d).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v)
+        o = o.transpose(1, 2).reshape(B, -1, C)
+        return self.to_out[0](o)
+
+
+class GEGLU(nn.Module):
+    """[diffusers 0.32.2 activations.GEGLU, un-vendored]: h, g = proj(x).chunk(2); h * gelu_erf(g)."""
+
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+    def forward(self, x):
+        h, g = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(g)
+
+
+class FeedForward(nn.Module):
+    """feature/diffusers/models/attention.py:1209-1258; `inner` gathered after net[0] (:1253-1257)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Identity(), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        for i, m in enumerate(self.net):
+            x = m(x)
+            if i == 0:
+                _gather(self, x, "inner")
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    """feature/diffusers/models/attention.py:469-592, norm_type='layer_norm'."""
+
+    def __init__(self, dim, heads, ctx_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn1 = Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn2 = Attention(dim, heads, ctx_dim)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, ctx):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), ctx) + x
+        x = self.ff(self.norm3(x)) + x
+        _gather(self, x, "out")
+        return x
+
+
+class Transformer2DModel(nn.Module):
+    """feature/diffusers/models/transformers/transformer_2d.py:174-209 (ctor), :403-475 (forward),
+    :482-530 (continuous in/out). GroupNorm eps 1e-6."""
+
+    def __init__(self, dim, heads, depth, ctx_dim, linear_proj, groups=32):
+        super().__init__()
+        self.use_linear_projection = linear_proj
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, ctx_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
+
+    def forward(self, x, ctx):
+        B, C, H, W = x.shape
+        res = x
+        h = self.norm(x)
+        if self.use_linear_projection:
+            h = self.proj_in(h.permute(0, 2, 3, 1).reshape(B, H * W, C))
+        else:
+            h = self.proj_in(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            h = blk(h, ctx)
+        if self.use_linear_projection:
+            h = self.proj_out(h).reshape(B, H, W, C).permute(0, 3, 1, 2)
+        else:
+            h = self.proj_out(h.reshape(B, H, W, C).permute(0, 3, 1, 2))
+        out = h + res
+        _gather(self, out, "out")
+        return out
+
+
+class DownBlock(nn.Module):
+    """[diffusers unet_2d_blocks.CrossAttnDownBlock2D / DownBlock2D, un-vendored] SURVEY Appendix C."""
+
+    def __init__(self, cin, cout, temb, n_layers, has_attn, heads, depth, ctx_dim, linear_proj, add_down, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb, eps=eps)
+                                      for i in range(n_layers)])
+        if has_attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, depth, ctx_dim, linear_proj)
+                                             for _ in range(n_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, h, temb, ctx):
+        skips = []
+        for i, r in enumerate(self.resnets):
+            h = r(h, temb)
+            if hasattr(self, "attentions"):
+                h = self.attentions[i](h, ctx)
+            skips.append(h)
+        if self.downsamplers:
+            h = self.downsamplers[0](h)
+            skips.append(h)
+        return h, skips
+
+
+class MidBlock(nn.Module):
+    """[UNetMidBlock2DCrossAttn, un-vendored]: resnets[0] -> (attn -> resnet)*."""
+
+    def __init__(self, ch, temb, heads, depth, ctx_dim, linear_proj, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb, eps=eps), ResnetBlock2D(ch, ch, temb, eps=eps)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, depth, ctx_dim, linear_proj)])
+
+    def forward(self, h, temb, ctx):
+        h = self.resnets[0](h, temb)
+        h = self.attentions[0](h, ctx)
+        return self.resnets[1](h, temb)
+
+
+class UpBlock(nn.Module):
+    """[CrossAttnUpBlock2D / UpBlock2D, un-vendored]: h = cat([h, skips.pop()], 1); resnet; attn; upsampler."""
+
+    def __init__(self, cin_prev, cout, skip_chs, temb, has_attn, heads, depth, ctx_dim, linear_proj, add_up, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList()
+        for i, sc in enumerate(skip_chs):
+            self.resnets.append(ResnetBlock2D((cin_prev if i == 0 else cout) + sc, cout, temb, eps=eps))
+        if has_attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, depth, ctx_dim, linear_proj)
+                                             for _ in skip_chs])
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, h, skips, temb, ctx):
+        for i, r in enumerate(self.resnets):
+            h = torch.cat([h, skips.pop()], dim=1)
+            h = r(h, temb)
+            if hasattr(self, "attentions"):
+                h = self.attentions[i](h, ctx)
+        if self.upsamplers:
+            h = self.upsamplers[0](h)
+        return h
+
+
+def timestep_embedding(t, dim):
+    """[diffusers embeddings.get_timestep_embedding, flip_sin_to_cos=True, downscale_freq_shift=0]."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    e = t.float()[:, None] * freqs[None]
+    return torch.cat([torch.cos(e), torch.sin(e)], dim=-1)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+UNET_CONFIGS = {
+    # SURVEY.md Appendix B
+    "xl": dict(block_out=(320, 640, 1280), down_attn=(0, 1, 1), up_attn=(1, 1, 0), depth=(1, 2, 10),
+               heads=(5, 10, 20), ctx_dim=2048, linear_proj=True, add_time_dim=256, add_in=2816, eps=1e-5),
+    "1-5": dict(block_out=(320, 640, 1280, 1280), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+                heads=(8, 8, 8, 8), ctx_dim=768, linear_proj=False, add_time_dim=0, add_in=0, eps=1e-5),
+    "2-1": dict(block_out=(320, 640, 1280, 1280), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+                heads=(5, 10, 20, 20), ctx_dim=1024, linear_proj=True, add_time_dim=0, add_in=0, eps=1e-5),
+}
+
+
+class UNet2DConditionModel(nn.Module):
+    """feature/diffusers/models/unet/unet_2d_condition.py:171-484 (ctor), :1040-1319 (forward)."""
+
+    def __init__(self, cfg, layers_per_block=2):
+        super().__init__()
+        self.cfg = cfg
+        bo = cfg["block_out"]
+        temb = bo[0] * 4
+        self.conv_in = nn.Conv2d(4, bo[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(bo[0], temb)
+        if cfg["add_time_dim"]:
+            self.add_embedding = TimestepEmbedding(cfg["add_in"], temb)
+        self.down_blocks = nn.ModuleList()
+        n = len(bo)
+        ch = bo[0]
+        skip_chs = [bo[0]]
+        for i in range(n):
+            cin, ch = ch, bo[i]
+            last = i == n - 1
+            self.down_blocks.append(DownBlock(cin, ch, temb, layers_per_block, cfg["down_attn"][i], cfg["heads"][i],
+                                              cfg["depth"][i], cfg["ctx_dim"], cfg["linear_proj"], not last,
+                                              cfg["eps"]))
+            skip_chs += [ch] * layers_per_block + ([ch] if not last else [])
+        self.mid_block = MidBlock(bo[-1], temb, cfg["heads"][-1], cfg["depth"][-1], cfg["ctx_dim"],
+                                  cfg["linear_proj"], cfg["eps"])
+        self.up_blocks = nn.ModuleList()
+        rev = list(reversed(bo))
+        rheads, rdepth = list(reversed(cfg["heads"])), list(reversed(cfg["depth"]))
+        prev = bo[-1]
+        for i in range(n):
+            cout = rev[i]
+            sk = [skip_chs.pop() for _ in range(layers_per_block + 1)]
+            self.up_blocks.append(UpBlock(prev, cout, sk, temb, cfg["up_attn"][i], rheads[i], rdepth[i],
+                                          cfg["ctx_dim"], cfg["linear_proj"], i != n - 1, cfg["eps"]))
+            prev = cout
+        self.conv_norm_out = nn.GroupNorm(32, bo[0], eps=cfg["eps"])
+        self.conv_out = nn.Conv2d(bo[0], 4, 3, padding=1)
+
+    def forward(self, sample, timestep, ctx, text_embeds=None, time_ids=None):
+        B = sample.shape[0]
+        t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(B)
+        emb = self.time_embedding(timestep_embedding(t, self.cfg["block_out"][0]))        # :1141-1142
+        if self.cfg["add_time_dim"]:                                                      # :968-984 (text_time)
+            te = timestep_embedding(time_ids.flatten(), self.cfg["add_time_dim"]).reshape(B, -1)
+            emb = emb + self.add_embedding(torch.cat([text_embeds, te], dim=-1))
+        _gather(self, sample, "in")                                                       # :1169-1173
+        h = self.conv_in(sample)
+        _gather(self, h, "after-conv-in")
+        skips = [h]
+        for blk in self.down_blocks:
+            h, s = blk(h, emb, ctx)
+            skips += s
+        h = self.mid_block(h, emb, ctx)
+        for blk in self.up_blocks:
+            h = blk(h, skips, emb, ctx)
+        h = self.conv_out(F.silu(self.conv_norm_out(h)))                                  # :1304-1307
+        _gather(self, h, "out")
+        return h
+
+
+# ------------------------------------------------------------------------------------------ VAE encoder
+class VaeAttention(nn.Module):
+    """[diffusers Attention(512, heads=1, dim_head=512, norm_num_groups=32, residual_connection=True, bias=True)]
+    through the 4-D branch of AttnProcessor2_0 (attention_processor.py:3264-3266, 3278-3279, 3323-3329)."""
+
+    def __init__(self, ch, groups=32, eps=1e-6):
+        super().__init__()
+        self.group_norm = nn.GroupNorm(groups, ch, eps=eps)
+        self.to_q = nn.Linear(ch, ch)
+        self.to_k = nn.Linear(ch, ch)
+        self.to_v = nn.Linear(ch, ch)
+        self.to_out = nn.ModuleList([nn.Linear(ch, ch), nn.Identity()])
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        h = self.group_norm(x).view(B, C, H * W).transpose(1, 2)
+        q, k, v = self.to_q(h), self.to_k(h), self.to_v(h)
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        o = self.to_out[0](o)
+        return o.transpose(1, 2).reshape(B, C, H, W) + x
+
+
+class VaeDownBlock(nn.Module):
+    def __init__(self, cin, cout, n_layers, add_down, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, 0, eps=eps)
+                                      for i in range(n_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout, padding=0)]) if add_down else None
+
+    def forward(self, h):
+        for r in self.resnets:
+            h = r(h)
+        if self.downsamplers:
+            h = self.downsamplers[0](h)
+        return h
+
+
+class VaeMidBlock(nn.Module):
+    def __init__(self, ch, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, 0, eps=eps), ResnetBlock2D(ch, ch, 0, eps=eps)])
+        self.attentions = nn.ModuleList([VaeAttention(ch, eps=eps)])
+
+    def forward(self, h):
+        return self.resnets[1](self.attentions[0](self.resnets[0](h)))
+
+
+class VaeEncoder(nn.Module):
+    """[diffusers autoencoders/vae.Encoder + AutoencoderKL.quant_conv, un-vendored] SURVEY 8(a4)."""
+
+    def __init__(self, block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6):
+        super().__init__()
+        self.conv_in = nn.Conv2d(3, block_out[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        ch = block_out[0]
+        for i, co in enumerate(block_out):
+            self.down_blocks.append(VaeDownBlock(ch, co, layers, i != len(block_out) - 1, eps))
+            ch = co
+        self.mid_block = VaeMidBlock(ch, eps)
+        self.conv_norm_out = nn.GroupNorm(32, ch, eps=eps)
+        self.conv_out = nn.Conv2d(ch, 2 * latent, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for b in self.down_blocks:
+            h = b(h)
+        h = self.mid_block(h)
+        return self.conv_out(F.silu(self.conv_norm_out(h)))
+
+
+class Vae(nn.Module):
+    def __init__(self, scaling_factor, **kw):
+        super().__init__()
+        self.encoder = VaeEncoder(**kw)
+        self.quant_conv = nn.Conv2d(8, 8, 1)
+        self.scaling_factor = scaling_factor
+
+    def moments(self, x):
+        return self.quant_conv(self.encoder(x))
+
+
+# ------------------------------------------------------------------------------------------ scheduler math
+def alphas_cumprod(beta_start=0.00085, beta_end=0.012, n=1000):
+    """scaled_linear betas [diffusers schedulers, un-vendored], float32 like diffusers."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def resolve_timestep(version, t):
+    """set_timesteps(1000) + get_timesteps(1000, t/1000) (diffusion_feature.py:288-295,
+    pipeline_pixart_sigma.py:680-714) -> (timestep fed to the denoiser, a, b, input_scale) with
+    x_t = a*z + b*eps (scheduler.add_noise) and model input = x_t * input_scale (scale_model_input)."""
+    t_start = max(1000 - min(int(1000 * (t / 1000)), 1000), 0)
+    ac = alphas_cumprod()
+    if version in ("xl", "pgv2"):          # Euler, spacing 'leading', steps_offset 1: timesteps = [1000..1]
+        ts = float(1000 - t_start)
+        sigma = float(((1 - ac[int(ts)]) / ac[int(ts)]) ** 0.5)
+        return ts, 1.0, sigma, 1.0 / math.sqrt(sigma * sigma + 1.0)
+    if version == "2-1":                   # Euler built from a PNDM config: spacing 'linspace' -> [999..0]
+        ts = float(999 - t_start)
+        sigma = float(((1 - ac[int(ts)]) / ac[int(ts)]) ** 0.5)
+        return ts, 1.0, sigma, 1.0 / math.sqrt(sigma * sigma + 1.0)
+    if version == "1-5":                   # PNDM skip_prk_steps, offset 1: [1000, 999, 999, 998, ..., 1]
+        seq = [1000, 999] + list(range(999, 0, -1))
+        ts = float(seq[t_start])
+        a = float(ac[int(ts)] ** 0.5)
+        b = float((1 - ac[int(ts)]) ** 0.5)
+        return ts, a, b, 1.0
+    raise NotImplementedError(version)
+
+
+def prepare_latents(vae, image, eps_vae, eps_q, a, b):
+    """pipeline_pixart_sigma.py:598-677: z = sample(posterior) * scaling_factor; x_t = add_noise(z, eps, t)."""
+    m = vae.moments(image.float())
+    mean, logvar = m.chunk(2, dim=1)
+    logvar = logvar.clamp(-30.0, 20.0)
+    z = (mean + torch.exp(0.5 * logvar) * eps_vae) * vae.scaling_factor
+    return a * z + b * eps_q
+
+
+def add_time_ids(img_size):
+    """_get_add_time_ids, diffusion_feature.py:534-571 (requires_aesthetics_score False):
+    original_size + crops (0,0) + target_size."""
+    return torch.tensor([[img_size, img_size, 0, 0, img_size, img_size]], dtype=torch.float32)
+
+
+@torch.no_grad()
+def extract(version, unet, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50, img_size=None):
+    """FeatureExtractor.extract (diffusion_feature.py:222-517) for image_type='tensors' already at img_size."""
+    store.reset()
+    B = image.shape[0]
+    ts, a, b, s = resolve_timestep(version, t)
+    latents = prepare_latents(vae, image, eps_vae, eps_q, a, b)
+    x = latents * s
+    ctx_b = ctx.repeat(B, 1, 1) if ctx.shape[0] == 1 else ctx
+    kw = {}
+    if version in ("xl", "pgv2"):
+        kw["text_embeds"] = pooled.repeat(B, 1) if pooled.shape[0] == 1 else pooled
+        kw["time_ids"] = add_time_ids(img_size or image.shape[-1]).repeat(B, 1)
+    noise_pred = unet(x, ts, ctx_b, **kw)
+    return store.stored_feats, latents, noise_pred
+
+
+# ------------------------------------------------------------------------------------------ stack + correspondence
+def resize_concat(feats, out_hw=(128, 128)):
+    """aggregation_network.py:62-66 per batch element: interpolate every map bilinearly, cat over channels."""
+    return torch.cat([F.interpolate(f, out_hw, mode="bilinear") for f in feats], dim=1)
+
+
+def points_to_idxs(points, load_size):
+    """correspondence_utils.py:140-146 (points in (y, x) order)."""
+    import numpy as np
+    py = np.clip(points[:, 0], 0, load_size[1] - 1)
+    px = np.clip(points[:, 1], 0, load_size[0] - 1)
+    return load_size[1] * np.round(py) + np.round(px)
+
+
+def find_nn_source_correspondences(f1, f2, source_points, load_size):
+    """correspondence_utils.py:113-138; returns (points2 (n,2) [y,x], sims (n, hw))."""
+    f1 = F.interpolate(f1, load_size, mode="bilinear")
+    f2 = F.interpolate(f2, load_size, mode="bilinear")
+    idx = torch.from_numpy(points_to_idxs(source_points, load_size)).long()
+    b, c = f1.shape[:2]
+    f1 = f1.view(b, c, -1).permute(0, 2, 1)[:, idx, :]
+    f2 = f2.view(b, c, -1).permute(0, 2, 1)
+    f1 = f1 / torch.linalg.norm(f1, dim=-1)[:, :, None]
+    f2 = f2 / torch.linalg.norm(f2, dim=-1)[:, :, None]
+    sims = torch.matmul(f1, f2.permute(0, 2, 1))
+    n = int(math.sqrt(sims.shape[-1]))
+    p2 = sims.argmax(dim=-1)
+    return torch.stack([p2 // n, p2 % n], dim=-1)[0], sims[0]
