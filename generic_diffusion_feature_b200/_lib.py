@@ -21,7 +21,7 @@ GDF_MAX_LEVELS = 4
 EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
     "gdf_create", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
-    "gdf_encode_noise", "gdf_denoise_capture",
+    "gdf_encode_noise", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
     "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
@@ -124,6 +124,10 @@ def load():
                                  ctypes.POINTER(c_int64)]
         lib.gdf_encode_noise.argtypes = [P, P, P, P, c_float, c_float, c_float, P, P]
         lib.gdf_denoise_capture.argtypes = [P, c_float, P, c_int, P, P, P, P, P]
+        lib.gdf_set_ctx_len.argtypes = [P, c_int]
+        lib.gdf_num_launches.argtypes = [P]
+        lib.gdf_workspace_bytes.argtypes = [P]
+        lib.gdf_workspace_bytes.restype = c_int64
     _lib = lib
     return lib
 

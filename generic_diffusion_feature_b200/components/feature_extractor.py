@@ -1,0 +1,147 @@
+"""Capture plumbing of the B200 path: host-side mirror of feature/components/feature_extractor.py.
+
+In the reference, `prepare_feature_extractor` (feature_extractor.py:92-288) hangs a FeatureGatherer on every
+module and `FeatureStore.store` (:31-76) filters / reshapes / copies each activation as the forward runs. Here
+the same id grammar is compiled once into a *feature plan* (`gdf_plan`): every requested id becomes a slot of
+a preallocated fp16 arena and the producing CUDA kernel writes into it from its epilogue - there are no hooks
+and no copies. `FeatureStore` keeps the reference's attribute surface (to_store, accept_all, stored_feats,
+reset, store_idx) so that code written against the reference keeps working.
+"""
+import ctypes
+import json
+
+import torch
+
+from .. import _lib
+from .._lib import Slot, check
+
+
+def _unet_feature_ids(cfg, layers_per_block=2):
+    """All non-`map` feature ids of a UNet in execution order (same grammar as feature_extractor.py:125-249;
+    reproduces the 472 / 165 non-map ids of feature/configs/config_{xl,15}_full.json)."""
+    ids = ["unet-in", "unet-after-conv-in"]
+    bo = cfg["block_out"]
+    n = len(bo)
+
+    def vit(prefix, depth):
+        for k in range(depth):
+            for tag in ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out"):
+                ids.append("%s-block%d-%s" % (prefix, k, tag))
+        ids.append(prefix + "-out")
+
+    for i in range(n):
+        for j in range(layers_per_block):
+            p = "down-level%d-repeat%d" % (i, j)
+            ids += [p + "-res-increment", p + "-res-out"]
+            if cfg["down_attn"][i]:
+                vit(p + "-vit", cfg["depth"][i])
+        if i != n - 1:
+            ids.append("down-level%d-downsampler-out" % i)
+    ids += ["mid-repeat0-res-increment", "mid-repeat0-res-out"]
+    vit("mid-vit", cfg["depth"][-1])
+    ids += ["mid-repeat1-res-increment", "mid-repeat1-res-out"]
+    for i in range(n):
+        li = n - 1 - i
+        for j in range(layers_per_block + 1):
+            p = "up-level%d-repeat%d" % (i, j)
+            ids += [p + "-res-increment", p + "-res-out"]
+            if cfg["up_attn"][i]:
+                vit(p + "-vit", cfg["depth"][li])
+        if i != n - 1:
+            ids.append("up-level%d-upsampler-out" % i)
+    ids.append("unet-out")
+    return ids
+
+
+class FeatureStore:
+    """Mirror of the reference FeatureStore (feature_extractor.py:8-80) backed by the arena plan."""
+
+    def __init__(self, to_store, resize_ratio, train_unet):
+        if to_store:
+            self.to_store = to_store
+            self.accept_all = False
+        else:
+            self.to_store = {}
+            self.accept_all = True
+        self.feats = {}
+        self.status = "active"
+        self.resize_ratio = resize_ratio
+        self.train_unet = train_unet
+        self.store_idx = None
+
+    def pause(self):
+        self.status = "pause"
+
+    def resume(self):
+        self.status = "active"
+
+    def reset(self):
+        self.feats = {}   # rebinding, like the reference: previously returned dicts stay valid
+
+    @property
+    def stored_feats(self):
+        return self.feats
+
+
+class FeaturePlan:
+    """Compiled selection: ids -> arena slots for one (batch, img_size)."""
+
+    def __init__(self, pipe, ids, batch, img_size):
+        self.ids = list(ids)
+        self.batch = batch
+        self.img_size = img_size
+        lib = pipe.lib
+        n = len(self.ids)
+        c_ids = (ctypes.c_char_p * max(n, 1))(*[i.encode() for i in self.ids])
+        slots = (Slot * max(n, 1))()
+        arena_bytes = ctypes.c_int64(0)
+        with torch.cuda.device(pipe.dev_index):
+            check(lib.gdf_plan(pipe.handle, c_ids, n, batch, img_size, slots, ctypes.byref(arena_bytes)))
+        self.arena_bytes = int(arena_bytes.value)
+        self.slots = [(self.ids[i], int(slots[i].offset_bytes), slots[i].channels, slots[i].height, slots[i].width,
+                       slots[i].order) for i in range(n)]
+        self.launches = int(lib.gdf_num_launches(pipe.handle))
+        self.workspace_bytes = int(lib.gdf_workspace_bytes(pipe.handle))
+
+    def views(self, arena):
+        """dict id -> fp16 (B, C, h, w) view of the arena, insertion order = execution order (the reference's
+        dict order). Token-major storage: like the reference's ViT features (einops view of (B, N, C),
+        feature_extractor.py:46-48) the (B,C,h,w) tensor has channel stride 1."""
+        out = []
+        seen = set()
+        for fid, off, C, H, W, order in self.slots:
+            if off < 0 or fid in seen:
+                continue
+            seen.add(fid)
+            nbytes = self.batch * H * W * C * 2
+            t = arena[off:off + nbytes].view(torch.float16).view(self.batch, H, W, C).permute(0, 3, 1, 2)
+            out.append((order, fid, t))
+        out.sort(key=lambda x: x[0])
+        return {fid: t for _, fid, t in out}
+
+
+def prepare_feature_extractor(version, pipe, config, resize_ratio, train_unet):
+    """Same signature / return type as the reference (feature_extractor.py:92): config is a JSON path, a dict
+    {feature_id: bool} or None/{} for accept-all."""
+    if isinstance(config, str):
+        with open(config, "r") as f:
+            config = json.load(f)
+    if train_unet:
+        raise NotImplementedError("train_unet needs autograd through the kernels (SURVEY.md 8f, not built)")
+    if resize_ratio != 1:
+        raise NotImplementedError("feature_resize > 1 (adaptive_avg_pool2d, feature_extractor.py:51-53) is not "
+                                  "built on the B200 path yet")
+    return FeatureStore(config, resize_ratio, train_unet)
+
+
+def selected_ids(feature_store, pipe):
+    """Ids to plan: enabled JSON keys in file order, or every id of the architecture when accept_all
+    (feature_extractor.py:10-15,36). `map` ids need the attention-probability path and raise."""
+    if feature_store.accept_all:
+        return _unet_feature_ids(pipe.unet_cfg)
+    ids = [k for k, v in feature_store.to_store.items() if v]
+    for k in ids:
+        if "map" in k or k in ("vae-out", "attn"):
+            raise NotImplementedError("feature id '%s' needs the attention-probability / vae-out path, which is "
+                                      "not built on the B200 path yet (SURVEY.md 8f)" % k)
+    return ids

@@ -1,0 +1,319 @@
+"""Model factory of the B200 path: host-side mirror of feature/components/models.py (reference).
+
+`get_diffusion_model(version, dtype, ...)` returns a `B200Pipe`, the object `FeatureExtractor` drives instead
+of a diffusers pipeline: it owns a libgdf_b200 handle (packed bf16 weights on the device) and the architecture /
+scheduler constants the reference reads from `pipe.unet.config`, `pipe.vae.config` and `pipe.scheduler`.
+
+Version strings and error behaviour follow models.py:10-16,173-174: dtype must be 'float16' or 'float32'
+(both select the same bf16-compute kernels; the returned features are fp16 either way, as FeatureStore.store
+casts them, feature_extractor.py:59-60), unknown versions raise NotImplementedError.
+"""
+import ctypes
+import zlib
+
+import torch
+
+from .. import _lib
+from .._lib import UNetArch, VaeArch, check
+
+# SURVEY.md Appendix B (diffusers configs of the checkpoints models.py:18-70 names)
+UNET_CONFIGS = {
+    "xl": dict(block_out=(320, 640, 1280), down_attn=(0, 1, 1), up_attn=(1, 1, 0), depth=(1, 2, 10),
+               heads=(5, 10, 20), ctx_dim=2048, linear_proj=True, add_time_dim=256, add_in=2816, eps=1e-5),
+    "1-5": dict(block_out=(320, 640, 1280, 1280), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+                heads=(8, 8, 8, 8), ctx_dim=768, linear_proj=False, add_time_dim=0, add_in=0, eps=1e-5),
+    "2-1": dict(block_out=(320, 640, 1280, 1280), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+                heads=(5, 10, 20, 20), ctx_dim=1024, linear_proj=True, add_time_dim=0, add_in=0, eps=1e-5),
+}
+UNET_CONFIGS["pgv2"] = UNET_CONFIGS["xl"]
+VAE_CONFIGS = {
+    "xl": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025),
+    "pgv2": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025),
+    "1-5": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.18215),
+    "2-1": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.18215),
+}
+_NOT_BUILT = ("pixart-sigma", "pixart-sigma-512", "pixart-alpha", "if", "hunyuan", "flux")
+
+
+def unet_param_specs(cfg, layers_per_block=2):
+    """(name, shape) of every UNet parameter, diffusers state_dict naming (unet_2d_condition.py:171-484)."""
+    bo = cfg["block_out"]
+    temb = bo[0] * 4
+    out = []
+
+    def lin(n, o, i, bias=True):
+        out.append((n + ".weight", (o, i)))
+        if bias:
+            out.append((n + ".bias", (o,)))
+
+    def conv(n, o, i, k):
+        out.append((n + ".weight", (o, i, k, k)))
+        out.append((n + ".bias", (o,)))
+
+    def norm(n, c):
+        out.append((n + ".weight", (c,)))
+        out.append((n + ".bias", (c,)))
+
+    def resnet(n, cin, cout, temb_ch):
+        norm(n + ".norm1", cin)
+        conv(n + ".conv1", cout, cin, 3)
+        if temb_ch:
+            lin(n + ".time_emb_proj", cout, temb_ch)
+        norm(n + ".norm2", cout)
+        conv(n + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(n + ".conv_shortcut", cout, cin, 1)
+
+    def vit(n, c, depth):
+        norm(n + ".norm", c)
+        if cfg["linear_proj"]:
+            lin(n + ".proj_in", c, c)
+        else:
+            conv(n + ".proj_in", c, c, 1)
+        for k in range(depth):
+            b = "%s.transformer_blocks.%d" % (n, k)
+            norm(b + ".norm1", c)
+            for a, cd in (("attn1", c), ("attn2", cfg["ctx_dim"])):
+                lin(b + "." + a + ".to_q", c, c, bias=False)
+                lin(b + "." + a + ".to_k", c, cd, bias=False)
+                lin(b + "." + a + ".to_v", c, cd, bias=False)
+                lin(b + "." + a + ".to_out.0", c, c)
+                if a == "attn1":
+                    norm(b + ".norm2", c)
+            norm(b + ".norm3", c)
+            lin(b + ".ff.net.0.proj", 8 * c, c)
+            lin(b + ".ff.net.2", c, 4 * c)
+        if cfg["linear_proj"]:
+            lin(n + ".proj_out", c, c)
+        else:
+            conv(n + ".proj_out", c, c, 1)
+
+    conv("conv_in", bo[0], 4, 3)
+    lin("time_embedding.linear_1", temb, bo[0])
+    lin("time_embedding.linear_2", temb, temb)
+    if cfg["add_time_dim"]:
+        lin("add_embedding.linear_1", temb, cfg["add_in"])
+        lin("add_embedding.linear_2", temb, temb)
+    n = len(bo)
+    ch = bo[0]
+    skips = [bo[0]]
+    for i in range(n):
+        cin, ch = ch, bo[i]
+        for j in range(layers_per_block):
+            resnet("down_blocks.%d.resnets.%d" % (i, j), cin if j == 0 else ch, ch, temb)
+            if cfg["down_attn"][i]:
+                vit("down_blocks.%d.attentions.%d" % (i, j), ch, cfg["depth"][i])
+            skips.append(ch)
+        if i != n - 1:
+            conv("down_blocks.%d.downsamplers.0.conv" % i, ch, ch, 3)
+            skips.append(ch)
+    resnet("mid_block.resnets.0", ch, ch, temb)
+    vit("mid_block.attentions.0", ch, cfg["depth"][-1])
+    resnet("mid_block.resnets.1", ch, ch, temb)
+    prev = bo[-1]
+    for i in range(n):
+        li = n - 1 - i
+        cout = bo[li]
+        for j in range(layers_per_block + 1):
+            sk = skips.pop()
+            resnet("up_blocks.%d.resnets.%d" % (i, j), (prev if j == 0 else cout) + sk, cout, temb)
+            if cfg["up_attn"][i]:
+                vit("up_blocks.%d.attentions.%d" % (i, j), cout, cfg["depth"][li])
+        if i != n - 1:
+            conv("up_blocks.%d.upsamplers.0.conv" % i, cout, cout, 3)
+        prev = cout
+    norm("conv_norm_out", bo[0])
+    conv("conv_out", 4, bo[0], 3)
+    return out
+
+
+def vae_param_specs(cfg):
+    """(name, shape) of the VAE-encoder parameters ('encoder.*', 'quant_conv.*'), diffusers naming."""
+    bo = cfg["block_out"]
+    out = []
+
+    def conv(n, o, i, k):
+        out.append((n + ".weight", (o, i, k, k)))
+        out.append((n + ".bias", (o,)))
+
+    def norm(n, c):
+        out.append((n + ".weight", (c,)))
+        out.append((n + ".bias", (c,)))
+
+    def lin(n, o, i):
+        out.append((n + ".weight", (o, i)))
+        out.append((n + ".bias", (o,)))
+
+    def resnet(n, cin, cout):
+        norm(n + ".norm1", cin)
+        conv(n + ".conv1", cout, cin, 3)
+        norm(n + ".norm2", cout)
+        conv(n + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(n + ".conv_shortcut", cout, cin, 1)
+
+    conv("encoder.conv_in", bo[0], 3, 3)
+    ch = bo[0]
+    for i, co in enumerate(bo):
+        for j in range(cfg["layers"]):
+            resnet("encoder.down_blocks.%d.resnets.%d" % (i, j), ch if j == 0 else co, co)
+        ch = co
+        if i != len(bo) - 1:
+            conv("encoder.down_blocks.%d.downsamplers.0.conv" % i, ch, ch, 3)
+    resnet("encoder.mid_block.resnets.0", ch, ch)
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", ch)
+    for p in ("to_q", "to_k", "to_v", "to_out.0"):
+        lin(a + "." + p, ch, ch)
+    resnet("encoder.mid_block.resnets.1", ch, ch)
+    norm("encoder.conv_norm_out", ch)
+    conv("encoder.conv_out", 2 * cfg["latent"], ch, 3)
+    conv("quant_conv", 2 * cfg["latent"], 2 * cfg["latent"], 1)
+    return out
+
+
+_RESIDUAL_OUT = ("conv2.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight")
+
+
+def init_param(name, shape, device="cpu"):
+    """Deterministic synthetic weight for a parameter name: seed = crc32(name);
+    weights ~ N(0, 1/fan_in) (x0.3 on residual-branch output layers so that deep random stacks stay
+    well conditioned), norm gamma = 1 + 0.02 N(0,1), norm beta / biases = 0.02 N(0,1).
+    device='cpu' is bit-reproducible everywhere (used by tests and golden fixtures); a CUDA device uses the
+    CUDA generator (fast path for the 2.6 B-parameter SDXL bench; the oracle then takes .cpu() copies)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(zlib.crc32(name.encode()))
+    r = torch.randn(*shape, generator=g, device=device, dtype=torch.float32)
+    is_norm = ".norm" in name or "group_norm" in name or "conv_norm_out" in name
+    if name.endswith(".bias"):
+        return 0.02 * r
+    if is_norm:
+        return 1.0 + 0.02 * r
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    gain = 0.3 if name.endswith(_RESIDUAL_OUT) else 1.0
+    return r * (gain / fan_in ** 0.5)
+
+
+def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None):
+    """name -> fp32 tensor for 'unet.*' and 'vae.*' (random init; there are no checkpoints offline)."""
+    ucfg = unet_cfg or UNET_CONFIGS[version]
+    vcfg = vae_cfg or VAE_CONFIGS[version]
+    sd = {}
+    for n, s in unet_param_specs(ucfg):
+        sd["unet." + n] = init_param("unet." + n, s, device)
+    for n, s in vae_param_specs(vcfg):
+        sd["vae." + n] = init_param("vae." + n, s, device)
+    return sd
+
+
+def _unet_arch(cfg):
+    a = UNetArch()
+    a.in_channels, a.out_channels = 4, 4
+    a.num_levels = len(cfg["block_out"])
+    a.layers_per_block = 2
+    for i, v in enumerate(cfg["block_out"]):
+        a.block_out_channels[i] = v
+        a.down_has_attn[i] = cfg["down_attn"][i]
+        a.up_has_attn[i] = cfg["up_attn"][i]
+        a.transformer_depth[i] = cfg["depth"][i]
+        a.num_heads[i] = cfg["heads"][i]
+    a.cross_attention_dim = cfg["ctx_dim"]
+    a.use_linear_projection = int(cfg["linear_proj"])
+    a.addition_time_embed_dim = cfg["add_time_dim"]
+    a.projection_class_embeddings_input_dim = cfg["add_in"]
+    a.norm_num_groups = 32
+    a.norm_eps = cfg["eps"]
+    return a
+
+
+def _vae_arch(cfg):
+    a = VaeArch()
+    a.in_channels, a.latent_channels = 3, cfg["latent"]
+    a.num_levels = len(cfg["block_out"])
+    for i, v in enumerate(cfg["block_out"]):
+        a.block_out_channels[i] = v
+    a.layers_per_block = cfg["layers"]
+    a.norm_num_groups = 32
+    a.norm_eps = cfg["eps"]
+    a.scaling_factor = cfg["scaling_factor"]
+    return a
+
+
+class B200Pipe:
+    """What `FeatureExtractor` holds in place of a diffusers pipeline on the B200 path."""
+
+    def __init__(self, version, unet_cfg, vae_cfg, device):
+        self.version = version
+        self.unet_cfg = unet_cfg
+        self.vae_cfg = vae_cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GdfError("the B200 extraction path needs a CUDA device (got %s); there is no CPU fallback"
+                                % device)
+        self.lib = _lib.load()
+        self.handle = ctypes.c_void_p()
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        ua, va = _unet_arch(unet_cfg), _vae_arch(vae_cfg)
+        check(self.lib.gdf_create(ctypes.byref(ua), ctypes.byref(va), self.dev_index, ctypes.byref(self.handle)))
+        self._finalized = False
+
+    def load_state_dict(self, sd, chunk=256):
+        """sd: name -> tensor ('unet.*', 'vae.*'), any float dtype / device; uploaded as fp32."""
+        names = list(sd.keys())
+        with torch.cuda.device(self.dev_index):
+            for s in range(0, len(names), chunk):
+                part = names[s:s + chunk]
+                tens = [sd[n].detach().to(self.device, torch.float32).contiguous() for n in part]
+                c_names = (ctypes.c_char_p * len(part))(*[n.encode() for n in part])
+                c_ptrs = (ctypes.c_void_p * len(part))(*[t.data_ptr() for t in tens])
+                shapes = [d for t in tens for d in t.shape]
+                c_shapes = (ctypes.c_int64 * len(shapes))(*shapes)
+                c_ranks = (ctypes.c_int * len(part))(*[t.dim() for t in tens])
+                check(self.lib.gdf_load_weights(self.handle, c_names, c_ptrs, c_shapes, c_ranks, len(part),
+                                                _lib.stream_ptr()))
+                del tens
+        self._finalized = False
+
+    def finalize(self):
+        if not self._finalized:
+            with torch.cuda.device(self.dev_index):
+                check(self.lib.gdf_finalize_weights(self.handle, _lib.stream_ptr()))
+            self._finalized = True
+
+    def close(self):
+        if self.handle:
+            self.lib.gdf_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename=None, device="cuda",
+                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None):
+    """Mirror of feature/components/models.py:10 for the B200 path.
+
+    There is no network and no checkpoint on disk, so unless `state_dict` (diffusers-named fp32 tensors with
+    'unet.' / 'vae.' prefixes, e.g. read from safetensors by the caller) is given, deterministic synthetic
+    weights are generated by parameter name (`synthetic_state_dict`)."""
+    if dtype not in ("float32", "float16"):
+        raise NotImplementedError                      # models.py:11-16
+    if offline_lora is not None:
+        raise NotImplementedError("LoRA loading is outside the B200 hot path (SURVEY.md 2.1 OUT OF SCOPE)")
+    if version in _NOT_BUILT:
+        raise NotImplementedError("version '%s' is not built on the B200 path yet (UNet families only)" % version)
+    if version not in UNET_CONFIGS and unet_cfg is None:
+        raise NotImplementedError                      # models.py:173-174
+    ucfg = unet_cfg or UNET_CONFIGS[version]
+    vcfg = vae_cfg or VAE_CONFIGS[version]
+    pipe = B200Pipe(version, ucfg, vcfg, device)
+    if state_dict is None:
+        state_dict = synthetic_state_dict(version, weight_device or "cpu", ucfg, vcfg)
+    pipe.load_state_dict(state_dict)
+    pipe.finalize()
+    return pipe

@@ -1,0 +1,1410 @@
+// Model-level C ABI (include/gdf.h): weights, feature plan, VAE-encode + q_sample, denoiser forward with
+// capture. The runtime is native: gdf_plan walks the architecture once, allocates every activation buffer,
+// builds every TMA descriptor / GEMM launch and records a flat op list; gdf_encode_noise and
+// gdf_denoise_capture replay that list on the caller's stream (no Python in the loop, no host sync).
+//
+// Reference control flow being replaced (file:line under /root/reference/feature):
+//   diffusion_feature.py:371-380,405-406   prepare_latents + scale_model_input      -> gdf_encode_noise
+//   diffusion_feature.py:446-465            pipe.unet(...)                            -> gdf_denoise_capture
+//   diffusers/models/unet/unet_2d_condition.py:1040-1319 (forward), resnet.py:320-379, transformers/
+//   transformer_2d.py:403-530, attention.py:469-592,1249-1258, attention_processor.py:3244-3331,
+//   downsampling.py:132-152, upsampling.py:142-195                                  -> op list below
+//   components/feature_extractor.py:31-76,92-288 (store + id grammar)                -> capture slots
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ops.h"
+
+namespace gdf {
+
+struct RawW {
+  float* ptr = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct RunCtx {
+  cudaStream_t stream;
+  char* arena = nullptr;
+  const float* images = nullptr;
+  const float* eps_vae = nullptr;
+  const float* eps_q = nullptr;
+  float qa = 1.f, qb = 0.f, qs = 1.f;
+  float* latents_out = nullptr;
+  float* noise_pred_out = nullptr;
+};
+typedef std::function<int(const RunCtx&)> Op;
+
+#define OP_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(GDF_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------- small kernels
+__global__ void pack_rows_kernel(const float* __restrict__ src, int K, const int* __restrict__ row_idx, int R_out,
+                                 bf16* __restrict__ dst) {
+  const long long total = (long long)R_out * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K), k = (int)(i % K);
+    const int sr = row_idx ? row_idx[r] : r;
+    dst[i] = __float2bfloat16_rn(sr >= 0 ? src[(long long)sr * K + k] : 0.f);
+  }
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n,
+                                  float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (idx[i] >= 0) ? src[idx[i]] : 0.f;
+}
+__global__ void fill_f32_kernel(float* dst, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+__global__ void add_f32_kernel(float* dst, const float* a, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += a[i];
+}
+// moments/noise-pred style NHWC bf16/f32 [B, HW, C] -> NCHW fp32 (B, C, HW)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long r = i / HW;
+    const int c = (int)(r % C), b = (int)(r / C);
+    y[i] = __bfloat162float(x[((long long)b * HW + p) * C + c]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------- buffer pool
+class BufPool {
+ public:
+  ~BufPool() { clear(); }
+  void* acquire(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    auto it = free_.lower_bound(bytes);
+    if (it != free_.end() && it->first <= bytes * 2 + (1 << 20)) {
+      void* p = it->second;
+      size_of_[p] = it->first;
+      free_.erase(it);
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    all_.push_back(p);
+    size_of_[p] = bytes;
+    total_ += bytes;
+    return p;
+  }
+  void release(void* p) {
+    if (!p) return;
+    auto it = size_of_.find(p);
+    if (it == size_of_.end()) return;
+    free_.insert({it->second, p});
+  }
+  void clear() {
+    for (void* p : all_) cudaFree(p);
+    all_.clear();
+    free_.clear();
+    size_of_.clear();
+    total_ = 0;
+  }
+  size_t total() const { return total_; }
+
+ private:
+  std::multimap<size_t, void*> free_;
+  std::unordered_map<void*, size_t> size_of_;
+  std::vector<void*> all_;
+  size_t total_ = 0;
+};
+
+struct Site {  // one capture call site of the reference, in execution order
+  std::string id;
+  int C, H, W;
+};
+
+}  // namespace gdf
+
+using namespace gdf;
+
+struct gdf_handle_s {
+  gdf_unet_arch ua;
+  gdf_vae_arch va;
+  int device = 0;
+  std::unordered_map<std::string, RawW> raw;
+  std::unordered_map<std::string, void*> packed;
+  std::vector<void*> owned;
+  bool finalized = false;
+  // plan
+  bool planned = false;
+  int B = 0, img = 0, L = 0, ctx_len = 77;
+  std::vector<Op> vae_ops, unet_ops;
+  BufPool pool;
+  std::unordered_map<std::string, int> requested;  // id -> index in the caller's list
+  std::vector<gdf_slot> slots;
+  std::vector<Site> sites;
+  int64_t arena_bytes = 0;
+  // run-time staging buffers (device)
+  float* t_dev = nullptr;        // [B]
+  bf16* ctx_bf16 = nullptr;      // [B*ctx_len, ctx_dim]
+  float* add_in = nullptr;       // [B, add_in_dim]
+  float* time_ids_dev = nullptr; // [B*6] pointer set per call (borrowed)
+  const float* ctx_f32 = nullptr;
+  const float* pooled = nullptr;
+  bf16* latent_nhwc = nullptr;   // [B, L*L, 4] model input
+  int64_t unet_in_cap = -1;
+  int gpu_launches = 0;
+};
+
+namespace gdf {
+
+struct Caps {  // arena offsets of the fp16 side outputs of one GEMM (-1 = not requested)
+  int64_t pre = -1;
+  int64_t post[3] = {-1, -1, -1};
+  int c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+  int n = 0;
+  void add(int64_t off, int col_begin, int col_end) {
+    post[n] = off;
+    c0[n] = col_begin;
+    c1[n] = col_end;
+    ++n;
+  }
+};
+
+// ----------------------------------------------------------------------------------------- builder
+class Builder {
+ public:
+  Builder(gdf_handle_s* h, bool dry) : h(h), dry(dry) {}
+  gdf_handle_s* h;
+  bool dry;
+  int err = 0;
+  std::vector<Op>* ops = nullptr;
+  float* gn_ws = nullptr;
+
+  int set_err(int e) {
+    if (!err) err = e;
+    return e;
+  }
+  // ---- weights -------------------------------------------------------------------------------
+  const RawW* raw(const std::string& name) {
+    auto it = h->raw.find(name);
+    if (it == h->raw.end()) {
+      set_err(fail(GDF_ERR_MISSING_WEIGHT, "missing weight '%s'", name.c_str()));
+      return nullptr;
+    }
+    return &it->second;
+  }
+  void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+      set_err(fail(GDF_ERR_CUDA, "cudaMalloc(%zu) failed for weights", bytes));
+      return nullptr;
+    }
+    h->owned.push_back(p);
+    return p;
+  }
+  const float* f32(const std::string& name) {
+    const RawW* r = raw(name);
+    return r ? r->ptr : nullptr;
+  }
+  // fp32 vector zero-padded to n_pad entries
+  const float* f32_pad(const std::string& name, int n_pad) {
+    const std::string key = name + "#pad" + std::to_string(n_pad);
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) return static_cast<const float*>(it->second);
+    const RawW* r = raw(name);
+    if (!r) return nullptr;
+    float* p = static_cast<float*>(dev_alloc((size_t)n_pad * 4));
+    if (!p) return nullptr;
+    cudaMemset(p, 0, (size_t)n_pad * 4);
+    cudaMemcpy(p, r->ptr, (size_t)r->numel * 4, cudaMemcpyDeviceToDevice);
+    h->packed[key] = p;
+    return p;
+  }
+  // rows of [R, K] fp32 matrices stacked and cast to bf16; idx (host) selects/permutes rows of the stack
+  const bf16* rows_bf16(const std::string& key, const std::vector<std::string>& names, const std::vector<int>* idx) {
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) return static_cast<const bf16*>(it->second);
+    int K = -1;
+    int64_t R = 0;
+    for (auto& n : names) {
+      const RawW* r = raw(n);
+      if (!r) return nullptr;
+      const int64_t k = r->numel / r->shape[0];
+      if (K < 0) K = (int)k;
+      if (k != K) {
+        set_err(fail(GDF_ERR_SHAPE, "rows_bf16 %s: inner size mismatch", key.c_str()));
+        return nullptr;
+      }
+      R += r->shape[0];
+    }
+    float* stack = nullptr;
+    const float* src = nullptr;
+    if (names.size() == 1) {
+      src = raw(names[0])->ptr;
+    } else {
+      cudaMalloc(&stack, (size_t)R * K * 4);
+      int64_t off = 0;
+      for (auto& n : names) {
+        const RawW* r = raw(n);
+        cudaMemcpy(stack + off, r->ptr, (size_t)r->numel * 4, cudaMemcpyDeviceToDevice);
+        off += r->numel;
+      }
+      src = stack;
+    }
+    const int R_out = idx ? (int)idx->size() : (int)R;
+    int* idx_dev = nullptr;
+    if (idx) {
+      cudaMalloc(&idx_dev, idx->size() * 4);
+      cudaMemcpy(idx_dev, idx->data(), idx->size() * 4, cudaMemcpyHostToDevice);
+    }
+    bf16* dst = static_cast<bf16*>(dev_alloc((size_t)R_out * K * 2));
+    if (dst) {
+      pack_rows_kernel<<<1024, 256>>>(src, K, idx_dev, R_out, dst);
+      cudaDeviceSynchronize();
+    }
+    if (stack) cudaFree(stack);
+    if (idx_dev) cudaFree(idx_dev);
+    h->packed[key] = dst;
+    return dst;
+  }
+  const bf16* lin(const std::string& name) { return rows_bf16(name + "#bf16", {name}, nullptr); }
+  const float* f32_gather(const std::string& key, const std::string& name, const std::vector<int>& idx) {
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) return static_cast<const float*>(it->second);
+    const RawW* r = raw(name);
+    if (!r) return nullptr;
+    int* idx_dev = nullptr;
+    cudaMalloc(&idx_dev, idx.size() * 4);
+    cudaMemcpy(idx_dev, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
+    float* dst = static_cast<float*>(dev_alloc(idx.size() * 4));
+    if (dst) {
+      gather_f32_kernel<<<((int)idx.size() + 255) / 256, 256>>>(r->ptr, idx_dev, (int)idx.size(), dst);
+      cudaDeviceSynchronize();
+    }
+    cudaFree(idx_dev);
+    h->packed[key] = dst;
+    return dst;
+  }
+  // conv weight OIHW -> bf16 [O_pad][k_pad]
+  const bf16* conv_w(const std::string& name, int* o_pad_out, int k_pad = 0) {
+    const RawW* r = raw(name);
+    if (!r) return nullptr;
+    if (r->shape.size() != 4) {
+      set_err(fail(GDF_ERR_SHAPE, "%s is not a conv weight", name.c_str()));
+      return nullptr;
+    }
+    const int O = (int)r->shape[0], I = (int)r->shape[1], kh = (int)r->shape[2], kw = (int)r->shape[3];
+    const int O_pad = (O + 15) / 16 * 16;
+    if (k_pad == 0) k_pad = kh * kw * I;
+    if (o_pad_out) *o_pad_out = O_pad;
+    const std::string key = name + "#conv" + std::to_string(k_pad);
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) return static_cast<const bf16*>(it->second);
+    bf16* dst = static_cast<bf16*>(dev_alloc((size_t)O_pad * k_pad * 2));
+    if (dst) {
+      launch_pack_conv_weight(r->ptr, dst, O, O_pad, I, kh, kw, k_pad, 0);
+      cudaDeviceSynchronize();
+    }
+    h->packed[key] = dst;
+    return dst;
+  }
+
+  // ---- buffers -------------------------------------------------------------------------------
+  bf16* buf(long long rows, int cols) {
+    if (dry) return nullptr;
+    void* p = h->pool.acquire((size_t)rows * cols * 2);
+    if (!p) set_err(fail(GDF_ERR_CUDA, "out of device memory for a %lld x %d activation", rows, cols));
+    return static_cast<bf16*>(p);
+  }
+  float* fbuf(long long n) {
+    if (dry) return nullptr;
+    void* p = h->pool.acquire((size_t)n * 4);
+    if (!p) set_err(fail(GDF_ERR_CUDA, "out of device memory"));
+    return static_cast<float*>(p);
+  }
+  void rel(void* p) {
+    if (!dry) h->pool.release(p);
+  }
+
+  // ---- capture slots ------------------------------------------------------------------------
+  // Registers a capture site (execution order) and returns its arena offset, or -1 when not requested.
+  int64_t site(const std::string& id, int C, int H, int W) {
+    if (dry) return -1;
+    h->sites.push_back({id, C, H, W});
+    auto it = h->requested.find(id);
+    if (it == h->requested.end()) return -1;
+    gdf_slot& s = h->slots[it->second];
+    if (s.offset_bytes >= 0) return s.offset_bytes;  // duplicate id in the caller's list
+    s.offset_bytes = h->arena_bytes;
+    s.channels = C;
+    s.height = H;
+    s.width = W;
+    s.order = (int)h->sites.size() - 1;
+    h->arena_bytes += (((int64_t)h->B * H * W * C * 2) + 255) & ~int64_t(255);
+    return s.offset_bytes;
+  }
+
+  // ---- op emission --------------------------------------------------------------------------
+  void push_gemm(GemmLaunch& g, const Caps& caps) {
+    GemmParams& p = g.p;
+    p.num_cap = caps.n;
+    for (int i = 0; i < caps.n; ++i) {
+      p.cap[i].ptr = nullptr;
+      p.cap[i].col_begin = caps.c0[i];
+      p.cap[i].col_end = caps.c1[i];
+      p.cap[i].ld = caps.c1[i] - caps.c0[i];
+    }
+    p.cap_pre = nullptr;
+    p.ld_cap_pre = p.n_out;
+    const GemmLaunch gl = g;
+    const Caps c = caps;
+    ops->push_back([gl, c](const RunCtx& rc) -> int {
+      GemmParams p = gl.p;
+      if (c.pre >= 0) p.cap_pre = reinterpret_cast<__half*>(rc.arena + c.pre);
+      for (int i = 0; i < c.n; ++i)
+        if (c.post[i] >= 0) p.cap[i].ptr = reinterpret_cast<__half*>(rc.arena + c.post[i]);
+      OP_CUDA(launch_gemm(gl.map_a, gl.map_b, p, rc.stream));
+      return 0;
+    });
+  }
+  void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e,
+              const Caps& caps = Caps(), int batch = 1, long long abs = 0, long long wbs = 0, int ldw = 0,
+              int block_n = 0) {
+    if (dry || err) return;
+    GemmLaunch g;
+    if (int r = build_linear(&g, A, M, K, lda, W, N, ldw ? ldw : K, e, batch, abs, wbs, block_n)) {
+      set_err(r);
+      return;
+    }
+    push_gemm(g, caps);
+  }
+  void conv3(const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int Npad, int stride, int pad_lo,
+             const Epilogue& e, const Caps& caps = Caps()) {
+    if (dry || err) return;
+    GemmLaunch g;
+    if (int r = build_conv3x3(&g, X, B, Hin, Win, Cin, Wp, Npad, stride, pad_lo, e)) {
+      set_err(r);
+      return;
+    }
+    push_gemm(g, caps);
+  }
+  void groupnorm(const bf16* x, bf16* y, const std::string& prefix, int B, int HW, int C, int G, float eps,
+                 bool silu) {
+    const float* gm = f32(prefix + ".weight");
+    const float* bt = f32(prefix + ".bias");
+    if (dry || err) return;
+    float* ws = gn_ws;
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_groupnorm(x, y, gm, bt, B, HW, C, G, eps, silu, ws, rc.stream));
+      return 0;
+    });
+  }
+  void layernorm(const bf16* x, bf16* y, const std::string& prefix, long long M, int C, float eps) {
+    const float* gm = f32(prefix + ".weight");
+    const float* bt = f32(prefix + ".bias");
+    if (dry || err) return;
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_layernorm(x, y, gm, bt, M, C, eps, nullptr, nullptr, 0, rc.stream));
+      return 0;
+    });
+  }
+  void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int B,
+                 int heads, int Nq, int Nk, float scale) {
+    if (dry || err) return;
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_attention64(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, scale, rc.stream));
+      return 0;
+    });
+  }
+  void small_linear(const float* x, const std::string& prefix, float* y, int B, int K, int N, bool silu_in,
+                    bool silu_out) {
+    const float* W = f32(prefix + ".weight");
+    const float* b = f32(prefix + ".bias");
+    if (dry || err) return;
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_small_linear(x, W, b, y, B, K, N, silu_in, silu_out, rc.stream));
+      return 0;
+    });
+  }
+};
+
+// ----------------------------------------------------------------------------------------- layers
+struct Dest {      // where a layer's output goes
+  bf16* out = nullptr; int ld = 0;    // primary (may be a slice of a skip-concat buffer)
+  bf16* out2 = nullptr; int ld2 = 0;  // optional second copy (skip-concat slice on the down path)
+};
+
+// ResnetBlock2D (resnet.py:320-379). x: [B*H*W, Cin] contiguous. temb: fp32 [B, temb_ch] or null (VAE).
+static void emit_resnet(Builder& b, const std::string& wp, const std::string& fid, const bf16* x, int B, int H, int W,
+                        int Cin, int Cout, const float* emb, int temb_ch, int groups, float eps, const Dest& d) {
+  const long long M = (long long)B * H * W;
+  bf16* t1 = b.buf(M, Cin);
+  b.groupnorm(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true);
+  float* tproj = nullptr;
+  if (emb) {
+    tproj = b.fbuf((long long)B * Cout);
+    b.small_linear(emb, wp + ".time_emb_proj", tproj, B, temb_ch, Cout, true, false);  // Linear(SiLU(temb))
+  }
+  int npad = 0;
+  const bf16* w1 = b.conv_w(wp + ".conv1.weight", &npad);
+  bf16* t2 = b.buf(M, Cout);
+  {
+    Epilogue e;
+    e.bias = b.f32_pad(wp + ".conv1.bias", npad);
+    e.row_batch_bias = tproj;
+    e.rows_per_batch = H * W;
+    e.n_out = Cout;
+    e.out = t2;
+    e.ld_out = Cout;
+    b.conv3(t1, B, H, W, Cin, w1, npad, 1, 1, e);
+  }
+  b.rel(t1);
+  bf16* t3 = b.buf(M, Cout);
+  b.groupnorm(t2, t3, wp + ".norm2", B, H * W, Cout, groups, eps, true);
+  b.rel(t2);
+  const bf16* res = x;
+  bf16* sc = nullptr;
+  if (Cin != Cout) {  // 1x1 conv_shortcut on the raw input
+    int np2 = 0;
+    const bf16* ws = b.conv_w(wp + ".conv_shortcut.weight", &np2);
+    sc = b.buf(M, Cout);
+    Epilogue e;
+    e.bias = b.f32_pad(wp + ".conv_shortcut.bias", np2);
+    e.n_out = Cout;
+    e.out = sc;
+    e.ld_out = Cout;
+    b.linear(x, M, Cin, Cin, ws, np2, e);
+    res = sc;
+  }
+  const bf16* w2 = b.conv_w(wp + ".conv2.weight", &npad);
+  {
+    Epilogue e;
+    e.bias = b.f32_pad(wp + ".conv2.bias", npad);
+    e.n_out = Cout;
+    e.residual = res;
+    e.ld_res = Cout;
+    e.out = d.out;
+    e.ld_out = d.ld;
+    e.out2 = d.out2;
+    e.ld_out2 = d.ld2;
+    Caps caps;
+    if (!fid.empty()) {
+      caps.pre = b.site(fid + "-increment", Cout, H, W);
+      const int64_t o = b.site(fid + "-out", Cout, H, W);
+      caps.add(o, 0, Cout);
+    }
+    b.conv3(t3, B, H, W, Cout, w2, npad, 1, 1, e, caps);
+  }
+  b.rel(t3);
+  b.rel(sc);
+  b.rel(tproj);
+}
+
+// BasicTransformerBlock (attention.py:469-592) on hs [M, C]; returns the new hidden-state buffer.
+static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& fid, bf16* hs, int B, int N, int C,
+                         int heads, int ctx_dim, int hw) {
+  gdf_handle_s* h = b.h;
+  const long long M = (long long)B * N;
+  const float scale = 1.f / sqrtf((float)(C / heads));
+  // ---- self attention
+  bf16* n1 = b.buf(M, C);
+  b.layernorm(hs, n1, wp + ".norm1", M, C, 1e-5f);
+  const bf16* wqkv = b.rows_bf16(wp + ".attn1#qkv", {wp + ".attn1.to_q.weight", wp + ".attn1.to_k.weight",
+                                                     wp + ".attn1.to_v.weight"}, nullptr);
+  bf16* qkv = b.buf(M, 3 * C);
+  {
+    Epilogue e;
+    e.out = qkv;
+    e.ld_out = 3 * C;
+    Caps caps;
+    caps.add(b.site(fid + "-self-q", C, hw, hw), 0, C);
+    caps.add(b.site(fid + "-self-k", C, hw, hw), C, 2 * C);
+    caps.add(b.site(fid + "-self-v", C, hw, hw), 2 * C, 3 * C);
+    b.linear(n1, M, C, C, wqkv, 3 * C, e, caps);
+  }
+  b.rel(n1);
+  bf16* ao = b.buf(M, C);
+  b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale);
+  b.rel(qkv);
+  bf16* hs1 = b.buf(M, C);
+  {
+    Epilogue e;
+    e.bias = b.f32(wp + ".attn1.to_out.0.bias");
+    e.residual = hs;
+    e.ld_res = C;
+    e.out = hs1;
+    e.ld_out = C;
+    b.linear(ao, M, C, C, b.lin(wp + ".attn1.to_out.0.weight"), C, e);
+  }
+  b.rel(ao);
+  b.rel(hs);
+  // ---- cross attention (context K/V: B*ctx_len rows; reference drops cross-k / cross-v, feature_extractor.py:38)
+  bf16* n2 = b.buf(M, C);
+  b.layernorm(hs1, n2, wp + ".norm2", M, C, 1e-5f);
+  bf16* q2 = b.buf(M, C);
+  {
+    Epilogue e;
+    e.out = q2;
+    e.ld_out = C;
+    Caps caps;
+    caps.add(b.site(fid + "-cross-q", C, hw, hw), 0, C);
+    b.linear(n2, M, C, C, b.lin(wp + ".attn2.to_q.weight"), C, e, caps);
+  }
+  b.rel(n2);
+  const long long Mc = (long long)B * h->ctx_len;
+  const bf16* wkv = b.rows_bf16(wp + ".attn2#kv", {wp + ".attn2.to_k.weight", wp + ".attn2.to_v.weight"}, nullptr);
+  bf16* kv = b.buf(Mc, 2 * C);
+  {
+    Epilogue e;
+    e.out = kv;
+    e.ld_out = 2 * C;
+    b.linear(h->ctx_bf16, Mc, ctx_dim, ctx_dim, wkv, 2 * C, e);
+  }
+  bf16* ao2 = b.buf(M, C);
+  b.attention(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, h->ctx_len, scale);
+  b.rel(q2);
+  b.rel(kv);
+  bf16* hs2 = b.buf(M, C);
+  {
+    Epilogue e;
+    e.bias = b.f32(wp + ".attn2.to_out.0.bias");
+    e.residual = hs1;
+    e.ld_res = C;
+    e.out = hs2;
+    e.ld_out = C;
+    b.linear(ao2, M, C, C, b.lin(wp + ".attn2.to_out.0.weight"), C, e);
+  }
+  b.rel(ao2);
+  b.rel(hs1);
+  // ---- feed-forward (GEGLU), attention.py:1249-1258
+  bf16* n3 = b.buf(M, C);
+  b.layernorm(hs2, n3, wp + ".norm3", M, C, 1e-5f);
+  const int inner = 4 * C;
+  const int bn = 256, half = bn / 2;
+  std::vector<int> idx;
+  idx.reserve(2 * inner);
+  for (int t = 0; t < inner / half; ++t) {
+    for (int j = 0; j < half; ++j) idx.push_back(t * half + j);
+    for (int j = 0; j < half; ++j) idx.push_back(inner + t * half + j);
+  }
+  const bf16* w1 = b.rows_bf16(wp + ".ff#geglu", {wp + ".ff.net.0.proj.weight"}, &idx);
+  const float* b1 = b.f32_gather(wp + ".ff#geglu_bias", wp + ".ff.net.0.proj.bias", idx);
+  bf16* ffi = b.buf(M, inner);
+  {
+    Epilogue e;
+    e.act = kActGeglu;
+    e.bias = b1;
+    e.out = ffi;
+    e.ld_out = inner;
+    Caps caps;
+    caps.add(b.site(fid + "-ffn-inner", inner, hw, hw), 0, inner);
+    b.linear(n3, M, C, C, w1, 2 * inner, e, caps, 1, 0, 0, 0, bn);
+  }
+  b.rel(n3);
+  bf16* hs3 = b.buf(M, C);
+  {
+    Epilogue e;
+    e.bias = b.f32(wp + ".ff.net.2.bias");
+    e.residual = hs2;
+    e.ld_res = C;
+    e.out = hs3;
+    e.ld_out = C;
+    Caps caps;
+    caps.add(b.site(fid + "-out", C, hw, hw), 0, C);
+    b.linear(ffi, M, inner, inner, b.lin(wp + ".ff.net.2.weight"), C, e, caps);
+  }
+  b.rel(ffi);
+  b.rel(hs2);
+  return hs3;
+}
+
+// Transformer2DModel (transformers/transformer_2d.py:403-530). x [B*hw*hw, C] contiguous (NHWC == token-major).
+static void emit_vit(Builder& b, const std::string& wp, const std::string& fid, const bf16* x, int B, int hw, int C,
+                     int heads, int depth, int ctx_dim, int groups, const Dest& d) {
+  const int N = hw * hw;
+  const long long M = (long long)B * N;
+  bf16* t = b.buf(M, C);
+  b.groupnorm(x, t, wp + ".norm", B, N, C, groups, 1e-6f, false);
+  bf16* hs = b.buf(M, C);
+  {
+    // Linear (use_linear_projection) or 1x1 conv: the same [C, C] contraction in NHWC
+    Epilogue e;
+    e.bias = b.f32(wp + ".proj_in.bias");
+    e.out = hs;
+    e.ld_out = C;
+    b.linear(t, M, C, C, b.lin(wp + ".proj_in.weight"), C, e);
+  }
+  b.rel(t);
+  for (int k = 0; k < depth; ++k)
+    hs = emit_tblock(b, wp + ".transformer_blocks." + std::to_string(k), fid + "-block" + std::to_string(k), hs, B, N,
+                     C, heads, ctx_dim, hw);
+  {
+    Epilogue e;
+    e.bias = b.f32(wp + ".proj_out.bias");
+    e.residual = x;
+    e.ld_res = C;
+    e.out = d.out;
+    e.ld_out = d.ld;
+    e.out2 = d.out2;
+    e.ld_out2 = d.ld2;
+    Caps caps;
+    caps.add(b.site(fid + "-out", C, hw, hw), 0, C);
+    b.linear(hs, M, C, C, b.lin(wp + ".proj_out.weight"), C, e, caps);
+  }
+  b.rel(hs);
+}
+
+// ----------------------------------------------------------------------------------------- UNet
+struct Skip {
+  int C, hw;
+  bf16* cbuf;   // consumer's concat buffer [M, ld]
+  int ld, col;  // this skip lives in columns [col, col + C)
+};
+
+static int build_unet(Builder& b) {
+  gdf_handle_s* h = b.h;
+  const gdf_unet_arch& a = h->ua;
+  const int B = h->B, nl = a.num_levels, lpb = a.layers_per_block, G = a.norm_num_groups;
+  const float eps = a.norm_eps;
+  const int temb_ch = a.block_out_channels[0] * 4;
+  const std::string U = "unet.";
+  b.ops = &h->unet_ops;
+
+  // ---- skip bookkeeping: channels/resolution of every skip in push order, consumers in pop order
+  std::vector<Skip> skips;
+  {
+    int hw = h->L;
+    skips.push_back({a.block_out_channels[0], hw, nullptr, 0, 0});
+    for (int i = 0; i < nl; ++i) {
+      for (int j = 0; j < lpb; ++j) skips.push_back({a.block_out_channels[i], hw, nullptr, 0, 0});
+      if (i != nl - 1) {
+        hw /= 2;
+        skips.push_back({a.block_out_channels[i], hw, nullptr, 0, 0});
+      }
+    }
+  }
+  // up-path geometry: resnet (i, j) consumes skip index sidx with previous-h channels cprev
+  struct UpRes { int cprev, cskip, cout, hw, sidx; bf16* cbuf; };
+  std::vector<UpRes> upres;
+  {
+    int sidx = (int)skips.size() - 1;
+    int prev = a.block_out_channels[nl - 1];
+    for (int i = 0; i < nl; ++i) {
+      const int cout = a.block_out_channels[nl - 1 - i];
+      for (int j = 0; j < lpb + 1; ++j) {
+        UpRes u;
+        u.cprev = (j == 0) ? prev : cout;
+        u.cskip = skips[sidx].C;
+        u.cout = cout;
+        u.hw = skips[sidx].hw;
+        u.sidx = sidx--;
+        u.cbuf = b.buf((long long)B * u.hw * u.hw, u.cprev + u.cskip);
+        skips[u.sidx].cbuf = u.cbuf;
+        skips[u.sidx].ld = u.cprev + u.cskip;
+        skips[u.sidx].col = u.cprev;
+        upres.push_back(u);
+      }
+      prev = cout;
+    }
+  }
+
+  // ---- conditioning embeddings (unet_2d_condition.py:1141-1162, 910-1002), fp32
+  float* temb_sin = b.fbuf((long long)B * a.block_out_channels[0]);
+  float* emb1 = b.fbuf((long long)B * temb_ch);
+  float* emb = b.fbuf((long long)B * temb_ch);
+  if (!b.dry) {
+    float* t_dev = h->t_dev;
+    const int dim0 = a.block_out_channels[0];
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_timestep_embedding(t_dev, temb_sin, B, dim0, rc.stream));
+      return 0;
+    });
+  }
+  b.small_linear(temb_sin, U + "time_embedding.linear_1", emb1, B, a.block_out_channels[0], temb_ch, false, true);
+  b.small_linear(emb1, U + "time_embedding.linear_2", emb, B, temb_ch, temb_ch, false, false);
+  if (a.addition_time_embed_dim > 0) {
+    const int td = a.addition_time_embed_dim, in_dim = a.projection_class_embeddings_input_dim;
+    const int pooled_dim = in_dim - 6 * td;
+    float* te = b.fbuf((long long)B * 6 * td);
+    float* aug1 = b.fbuf((long long)B * temb_ch);
+    float* aug = b.fbuf((long long)B * temb_ch);
+    if (!b.dry) {
+      gdf_handle_s* hh = h;
+      float* add_in = h->add_in;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        if (!hh->pooled || !hh->time_ids_dev)
+          return fail(GDF_ERR_INVALID, "this UNet needs pooled text embeds and add_time_ids (SDXL text_time)");
+        OP_CUDA(launch_timestep_embedding(hh->time_ids_dev, te, B * 6, td, rc.stream));
+        // add_embeds = cat([text_embeds, time_embeds], -1)  (unet_2d_condition.py:981)
+        OP_CUDA(cudaMemcpy2DAsync(add_in, (size_t)in_dim * 4, hh->pooled, (size_t)pooled_dim * 4,
+                                  (size_t)pooled_dim * 4, B, cudaMemcpyDeviceToDevice, rc.stream));
+        OP_CUDA(cudaMemcpy2DAsync(add_in + pooled_dim, (size_t)in_dim * 4, te, (size_t)6 * td * 4, (size_t)6 * td * 4,
+                                  B, cudaMemcpyDeviceToDevice, rc.stream));
+        return 0;
+      });
+    }
+    b.small_linear(h->add_in, U + "add_embedding.linear_1", aug1, B, in_dim, temb_ch, false, true);
+    b.small_linear(aug1, U + "add_embedding.linear_2", aug, B, temb_ch, temb_ch, false, false);
+    if (!b.dry) {
+      const int n = B * temb_ch;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        add_f32_kernel<<<(n + 255) / 256, 256, 0, rc.stream>>>(emb, aug, n);
+        OP_CUDA(cudaGetLastError());
+        return 0;
+      });
+    }
+  }
+
+  // ---- conv_in (unet_2d_condition.py:1169-1173): latent NHWC [B, L*L, 4] -> im2col(K=36->64) -> GEMM
+  int sidx = 0;  // next skip to produce
+  int hw = h->L;
+  const long long M0 = (long long)B * hw * hw;
+  h->unet_in_cap = b.site("unet-in", a.in_channels, hw, hw);
+  bf16* cur = b.buf(M0, a.block_out_channels[0]);
+  {
+    bf16* col = b.buf(M0, 64);
+    if (!b.dry) {
+      bf16* lat = h->latent_nhwc;
+      const int L = hw, cin = a.in_channels;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_im2col_small(nullptr, lat, col, B, L, L, cin, rc.stream));
+        return 0;
+      });
+    }
+    int npad = 0;
+    const bf16* w = b.conv_w(U + "conv_in.weight", &npad, 64);
+    Epilogue e;
+    e.bias = b.f32_pad(U + "conv_in.bias", npad);
+    e.n_out = a.block_out_channels[0];
+    e.out = cur;
+    e.ld_out = a.block_out_channels[0];
+    e.out2 = skips[sidx].cbuf ? skips[sidx].cbuf + skips[sidx].col : nullptr;
+    e.ld_out2 = skips[sidx].ld;
+    Caps caps;
+    caps.add(b.site("unet-after-conv-in", a.block_out_channels[0], hw, hw), 0, a.block_out_channels[0]);
+    b.linear(col, M0, 64, 64, w, npad, e, caps);
+    b.rel(col);
+    ++sidx;
+  }
+
+  auto skip_dest = [&](bf16* fresh, int C) {
+    Dest d;
+    d.out = fresh;
+    d.ld = C;
+    d.out2 = skips[sidx].cbuf ? skips[sidx].cbuf + skips[sidx].col : nullptr;
+    d.ld2 = skips[sidx].ld;
+    ++sidx;
+    return d;
+  };
+
+  // ---- down blocks
+  int ch = a.block_out_channels[0];
+  for (int i = 0; i < nl; ++i) {
+    const int cout = a.block_out_channels[i];
+    const bool attn = a.down_has_attn[i] != 0;
+    for (int j = 0; j < lpb; ++j) {
+      const std::string wp = U + "down_blocks." + std::to_string(i);
+      const std::string fid = "down-level" + std::to_string(i) + "-repeat" + std::to_string(j);
+      const long long M = (long long)B * hw * hw;
+      bf16* r_out = b.buf(M, cout);
+      Dest d;
+      if (attn) { d.out = r_out; d.ld = cout; } else d = skip_dest(r_out, cout);
+      emit_resnet(b, wp + ".resnets." + std::to_string(j), fid + "-res", cur, B, hw, hw, ch, cout, emb, temb_ch, G, eps,
+                  d);
+      b.rel(cur);
+      cur = r_out;
+      if (attn) {
+        bf16* v_out = b.buf(M, cout);
+        emit_vit(b, wp + ".attentions." + std::to_string(j), fid + "-vit", cur, B, hw, cout, a.num_heads[i],
+                 a.transformer_depth[i], a.cross_attention_dim, G, skip_dest(v_out, cout));
+        b.rel(cur);
+        cur = v_out;
+      }
+      ch = cout;
+    }
+    if (i != nl - 1) {  // Downsample2D: conv3x3 stride 2, padding 1 (downsampling.py:147)
+      const std::string wp = U + "down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
+      int npad = 0;
+      const bf16* w = b.conv_w(wp + ".weight", &npad);
+      const int ho = hw / 2;
+      bf16* o = b.buf((long long)B * ho * ho, ch);
+      const Dest d = skip_dest(o, ch);
+      Epilogue e;
+      e.bias = b.f32_pad(wp + ".bias", npad);
+      e.n_out = ch;
+      e.out = d.out;
+      e.ld_out = d.ld;
+      e.out2 = d.out2;
+      e.ld_out2 = d.ld2;
+      Caps caps;
+      caps.add(b.site("down-level" + std::to_string(i) + "-downsampler-out", ch, ho, ho), 0, ch);
+      b.conv3(cur, B, hw, hw, ch, w, npad, 2, 1, e, caps);
+      b.rel(cur);
+      cur = o;
+      hw = ho;
+    }
+  }
+
+  // ---- mid block: resnet -> vit -> resnet; the last resnet writes into the first up concat buffer
+  {
+    const long long M = (long long)B * hw * hw;
+    const int li = nl - 1;
+    bf16* r0 = b.buf(M, ch);
+    Dest d0;
+    d0.out = r0;
+    d0.ld = ch;
+    emit_resnet(b, U + "mid_block.resnets.0", "mid-repeat0-res", cur, B, hw, hw, ch, ch, emb, temb_ch, G, eps, d0);
+    b.rel(cur);
+    bf16* v = b.buf(M, ch);
+    Dest dv;
+    dv.out = v;
+    dv.ld = ch;
+    emit_vit(b, U + "mid_block.attentions.0", "mid-vit", r0, B, hw, ch, a.num_heads[li], a.transformer_depth[li],
+             a.cross_attention_dim, G, dv);
+    b.rel(r0);
+    Dest d1;
+    d1.out = upres[0].cbuf;
+    d1.ld = upres[0].cprev + upres[0].cskip;
+    emit_resnet(b, U + "mid_block.resnets.1", "mid-repeat1-res", v, B, hw, hw, ch, ch, emb, temb_ch, G, eps, d1);
+    b.rel(v);
+    cur = nullptr;
+  }
+
+  // ---- up blocks
+  size_t ur = 0;
+  bf16* final_h = nullptr;
+  for (int i = 0; i < nl; ++i) {
+    const int li = nl - 1 - i;
+    const int cout = a.block_out_channels[li];
+    const bool attn = a.up_has_attn[i] != 0;
+    const std::string wp = U + "up_blocks." + std::to_string(i);
+    for (int j = 0; j < lpb + 1; ++j, ++ur) {
+      const UpRes& u = upres[ur];
+      const std::string fid = "up-level" + std::to_string(i) + "-repeat" + std::to_string(j);
+      const long long M = (long long)B * hw * hw;
+      const bool last_in_block = (j == lpb);
+      const bool has_up = (i != nl - 1);
+      // destination of this layer's final output
+      Dest nd;
+      bf16* fresh = nullptr;
+      if (!last_in_block) {
+        nd.out = upres[ur + 1].cbuf;
+        nd.ld = upres[ur + 1].cprev + upres[ur + 1].cskip;
+      } else {
+        fresh = b.buf(M, cout);
+        nd.out = fresh;
+        nd.ld = cout;
+      }
+      if (attn) {
+        bf16* r_out = b.buf(M, cout);
+        Dest dr;
+        dr.out = r_out;
+        dr.ld = cout;
+        emit_resnet(b, wp + ".resnets." + std::to_string(j), fid + "-res", u.cbuf, B, hw, hw, u.cprev + u.cskip, cout,
+                    emb, temb_ch, G, eps, dr);
+        emit_vit(b, wp + ".attentions." + std::to_string(j), fid + "-vit", r_out, B, hw, cout, a.num_heads[li],
+                 a.transformer_depth[li], a.cross_attention_dim, G, nd);
+        b.rel(r_out);
+      } else {
+        emit_resnet(b, wp + ".resnets." + std::to_string(j), fid + "-res", u.cbuf, B, hw, hw, u.cprev + u.cskip, cout,
+                    emb, temb_ch, G, eps, nd);
+      }
+      b.rel(u.cbuf);
+      if (last_in_block) {
+        if (has_up) {  // Upsample2D: nearest x2 + conv3x3 (upsampling.py:176-193)
+          bf16* up = b.buf(M * 4, cout);
+          if (!b.dry) {
+            const int hh = hw;
+            bf16* src = fresh;
+            b.ops->push_back([=](const RunCtx& rc) -> int {
+              OP_CUDA(launch_upsample_nearest2x(src, up, B, hh, hh, cout, rc.stream));
+              return 0;
+            });
+          }
+          b.rel(fresh);
+          hw *= 2;
+          int npad = 0;
+          const bf16* w = b.conv_w(wp + ".upsamplers.0.conv.weight", &npad);
+          Epilogue e;
+          e.bias = b.f32_pad(wp + ".upsamplers.0.conv.bias", npad);
+          e.n_out = cout;
+          e.out = upres[ur + 1].cbuf;
+          e.ld_out = upres[ur + 1].cprev + upres[ur + 1].cskip;
+          Caps caps;
+          caps.add(b.site("up-level" + std::to_string(i) + "-upsampler-out", cout, hw, hw), 0, cout);
+          b.conv3(up, B, hw, hw, cout, w, npad, 1, 1, e, caps);
+          b.rel(up);
+        } else {
+          final_h = fresh;
+        }
+      }
+    }
+  }
+
+  // ---- conv_norm_out + SiLU + conv_out (unet_2d_condition.py:1304-1310)
+  {
+    const int c0 = a.block_out_channels[0];
+    const long long M = (long long)B * hw * hw;
+    bf16* t = b.buf(M, c0);
+    b.groupnorm(final_h, t, U + "conv_norm_out", B, hw * hw, c0, G, eps, true);
+    b.rel(final_h);
+    int npad = 0;
+    const bf16* w = b.conv_w(U + "conv_out.weight", &npad);
+    bf16* o = b.buf(M, a.out_channels);
+    Epilogue e;
+    e.bias = b.f32_pad(U + "conv_out.bias", npad);
+    e.n_out = a.out_channels;
+    e.out = o;
+    e.ld_out = a.out_channels;
+    Caps caps;
+    caps.add(b.site("unet-out", a.out_channels, hw, hw), 0, a.out_channels);
+    b.conv3(t, B, hw, hw, c0, w, npad, 1, 1, e, caps);
+    b.rel(t);
+    if (!b.dry) {
+      const int HW = hw * hw, C = a.out_channels;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        if (rc.noise_pred_out) {
+          nhwc_bf16_to_nchw_f32_kernel<<<256, 256, 0, rc.stream>>>(o, rc.noise_pred_out, B, HW, C);
+          OP_CUDA(cudaGetLastError());
+        }
+        return 0;
+      });
+    }
+  }
+  return b.err;
+}
+
+// ----------------------------------------------------------------------------------------- VAE encoder
+static int build_vae(Builder& b) {
+  gdf_handle_s* h = b.h;
+  const gdf_vae_arch& a = h->va;
+  const int B = h->B, G = a.norm_num_groups;
+  const float eps = a.norm_eps;
+  const std::string V = "vae.encoder.";
+  b.ops = &h->vae_ops;
+  int hw = h->img;
+  int ch = a.block_out_channels[0];
+  // conv_in: image fp32 NCHW -> im2col (K = 27 -> 64) -> GEMM
+  bf16* cur = b.buf((long long)B * hw * hw, ch);
+  {
+    bf16* col = b.buf((long long)B * hw * hw, 64);
+    if (!b.dry) {
+      const int S = hw, cin = a.in_channels;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_im2col_small(rc.images, nullptr, col, B, S, S, cin, rc.stream));
+        return 0;
+      });
+    }
+    int npad = 0;
+    const bf16* w = b.conv_w(V + "conv_in.weight", &npad, 64);
+    Epilogue e;
+    e.bias = b.f32_pad(V + "conv_in.bias", npad);
+    e.n_out = ch;
+    e.out = cur;
+    e.ld_out = ch;
+    b.linear(col, (long long)B * hw * hw, 64, 64, w, npad, e);
+    b.rel(col);
+  }
+  for (int i = 0; i < a.num_levels; ++i) {
+    const int cout = a.block_out_channels[i];
+    for (int j = 0; j < a.layers_per_block; ++j) {
+      bf16* o = b.buf((long long)B * hw * hw, cout);
+      Dest d;
+      d.out = o;
+      d.ld = cout;
+      emit_resnet(b, V + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), "", cur, B, hw, hw, ch,
+                  cout, nullptr, 0, G, eps, d);
+      b.rel(cur);
+      cur = o;
+      ch = cout;
+    }
+    if (i != a.num_levels - 1) {  // Downsample2D(padding=0): F.pad (0,1,0,1) + conv s2 (downsampling.py:141-147)
+      const std::string wp = V + "down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
+      int npad = 0;
+      const bf16* w = b.conv_w(wp + ".weight", &npad);
+      const int ho = hw / 2;
+      bf16* o = b.buf((long long)B * ho * ho, ch);
+      Epilogue e;
+      e.bias = b.f32_pad(wp + ".bias", npad);
+      e.n_out = ch;
+      e.out = o;
+      e.ld_out = ch;
+      b.conv3(cur, B, hw, hw, ch, w, npad, 2, 0, e);
+      b.rel(cur);
+      cur = o;
+      hw = ho;
+    }
+  }
+  const long long M = (long long)B * hw * hw;
+  const int N = hw * hw;
+  {  // mid block: resnet, single-head attention (d = ch), resnet
+    bf16* r0 = b.buf(M, ch);
+    Dest d;
+    d.out = r0;
+    d.ld = ch;
+    emit_resnet(b, V + "mid_block.resnets.0", "", cur, B, hw, hw, ch, ch, nullptr, 0, G, eps, d);
+    b.rel(cur);
+    const std::string ap = V + "mid_block.attentions.0";
+    bf16* hn = b.buf(M, ch);
+    b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
+    // Q | K fused projection
+    const bf16* wqk = b.rows_bf16(ap + "#qk", {ap + ".to_q.weight", ap + ".to_k.weight"}, nullptr);
+    std::vector<int> ident;
+    const float* bq = b.f32(ap + ".to_q.bias");
+    const float* bk = b.f32(ap + ".to_k.bias");
+    float* bqk = nullptr;
+    if (!b.dry) {
+      bqk = b.fbuf(2 * ch);
+      cudaMemcpy(bqk, bq, (size_t)ch * 4, cudaMemcpyDeviceToDevice);
+      cudaMemcpy(bqk + ch, bk, (size_t)ch * 4, cudaMemcpyDeviceToDevice);
+    }
+    bf16* qk = b.buf(M, 2 * ch);
+    {
+      Epilogue e;
+      e.bias = bqk;
+      e.out = qk;
+      e.ld_out = 2 * ch;
+      b.linear(hn, M, ch, ch, wqk, 2 * ch, e);
+    }
+    // V^T[b] = Wv hn[b]^T + bv[:, None]  -> [B, ch, N]
+    bf16* vt = b.buf((long long)B * ch, N);
+    {
+      Epilogue e;
+      e.bias_m = b.f32(ap + ".to_v.bias");
+      e.out = vt;
+      e.ld_out = N;
+      e.out_batch_stride = (long long)ch * N;
+      b.linear(b.lin(ap + ".to_v.weight"), ch, ch, ch, hn, N, e, Caps(), B, 0, (long long)N * ch, ch);
+    }
+    b.rel(hn);
+    // S[b] = Q[b] K[b]^T / sqrt(ch)
+    bf16* S = b.buf((long long)B * N, N);
+    {
+      Epilogue e;
+      e.alpha = 1.f / sqrtf((float)ch);
+      e.out = S;
+      e.ld_out = N;
+      e.out_batch_stride = (long long)N * N;
+      b.linear(qk, N, ch, 2 * ch, qk + ch, N, e, Caps(), B, (long long)N * 2 * ch, (long long)N * 2 * ch,
+               2 * ch);
+    }
+    b.rel(qk);
+    if (!b.dry) {
+      const long long rows = (long long)B * N;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_softmax_rows(S, rows, N, N, rc.stream));
+        return 0;
+      });
+    }
+    // O[b] = P[b] V[b]
+    bf16* o = b.buf(M, ch);
+    {
+      Epilogue e;
+      e.out = o;
+      e.ld_out = ch;
+      e.out_batch_stride = (long long)N * ch;
+      b.linear(S, N, N, N, vt, ch, e, Caps(), B, (long long)N * N, (long long)ch * N, N);
+    }
+    b.rel(S);
+    b.rel(vt);
+    bf16* ao = b.buf(M, ch);
+    {
+      Epilogue e;
+      e.bias = b.f32(ap + ".to_out.0.bias");
+      e.residual = r0;
+      e.ld_res = ch;
+      e.out = ao;
+      e.ld_out = ch;
+      b.linear(o, M, ch, ch, b.lin(ap + ".to_out.0.weight"), ch, e);
+    }
+    b.rel(o);
+    b.rel(r0);
+    b.rel(bqk);
+    bf16* r1 = b.buf(M, ch);
+    Dest d1;
+    d1.out = r1;
+    d1.ld = ch;
+    emit_resnet(b, V + "mid_block.resnets.1", "", ao, B, hw, hw, ch, ch, nullptr, 0, G, eps, d1);
+    b.rel(ao);
+    cur = r1;
+  }
+  // conv_norm_out + SiLU + (conv_out . quant_conv folded into one 3x3 conv) -> fp32 moments [M, 8]
+  bf16* t = b.buf(M, ch);
+  b.groupnorm(cur, t, V + "conv_norm_out", B, N, ch, G, eps, true);
+  b.rel(cur);
+  const int nm = 2 * a.latent_channels;
+  {
+    const std::string key = "vae#folded_conv_out";
+    if (!h->raw.count(key + ".weight")) {
+      const RawW* w = b.raw(V + "conv_out.weight");
+      const RawW* bi = b.raw(V + "conv_out.bias");
+      const RawW* wq = b.raw("vae.quant_conv.weight");
+      const RawW* bqv = b.raw("vae.quant_conv.bias");
+      if (w && bi && wq && bqv) {
+        std::vector<float> hw_(w->numel), hb(bi->numel), hq(wq->numel), hbq(bqv->numel);
+        cudaMemcpy(hw_.data(), w->ptr, w->numel * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hb.data(), bi->ptr, bi->numel * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hq.data(), wq->ptr, wq->numel * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hbq.data(), bqv->ptr, bqv->numel * 4, cudaMemcpyDeviceToHost);
+        const int64_t per = w->numel / nm;
+        std::vector<float> fw(w->numel, 0.f), fb(nm, 0.f);
+        for (int o = 0; o < nm; ++o) {
+          double bacc = hbq[o];
+          for (int m = 0; m < nm; ++m) {
+            const float q = hq[o * nm + m];
+            bacc += (double)q * hb[m];
+            for (int64_t k = 0; k < per; ++k) fw[o * per + k] += q * hw_[m * per + k];
+          }
+          fb[o] = (float)bacc;
+        }
+        RawW fwr, fbr;
+        fwr.shape = w->shape;
+        fwr.numel = w->numel;
+        fwr.ptr = static_cast<float*>(b.dev_alloc(w->numel * 4));
+        fbr.shape = {nm};
+        fbr.numel = nm;
+        fbr.ptr = static_cast<float*>(b.dev_alloc(nm * 4));
+        if (fwr.ptr && fbr.ptr) {
+          cudaMemcpy(fwr.ptr, fw.data(), w->numel * 4, cudaMemcpyHostToDevice);
+          cudaMemcpy(fbr.ptr, fb.data(), nm * 4, cudaMemcpyHostToDevice);
+          h->raw[key + ".weight"] = fwr;
+          h->raw[key + ".bias"] = fbr;
+        }
+      }
+    }
+    int npad = 0;
+    const bf16* w = b.conv_w(key + ".weight", &npad);
+    float* moments = b.fbuf(M * nm);
+    Epilogue e;
+    e.bias = b.f32_pad(key + ".bias", npad);
+    e.n_out = nm;
+    e.out_f32 = moments;
+    e.ld_out_f32 = nm;
+    b.conv3(t, B, hw, hw, ch, w, npad, 1, 1, e);
+    b.rel(t);
+    if (!b.dry) {
+      gdf_handle_s* hh = h;
+      const float sf = a.scaling_factor;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        __half* cap = (hh->unet_in_cap >= 0 && rc.arena) ? reinterpret_cast<__half*>(rc.arena + hh->unet_in_cap)
+                                                          : nullptr;
+        OP_CUDA(launch_qsample(moments, rc.eps_vae, rc.eps_q, sf, rc.qa, rc.qb, rc.qs, hh->latent_nhwc, cap,
+                               rc.latents_out, B, N, rc.stream));
+        return 0;
+      });
+    }
+  }
+  return b.err;
+}
+
+static void free_plan(gdf_handle_s* h) {
+  h->vae_ops.clear();
+  h->unet_ops.clear();
+  h->pool.clear();
+  h->sites.clear();
+  h->slots.clear();
+  h->requested.clear();
+  h->arena_bytes = 0;
+  h->planned = false;
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc);
+  h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr;
+}
+
+}  // namespace gdf
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int gdf_create(const gdf_unet_arch* unet, const gdf_vae_arch* vae, int device, gdf_handle* out) {
+  if (!unet || !vae || !out) return fail(GDF_ERR_INVALID, "gdf_create: null argument");
+  if (unet->num_levels < 2 || unet->num_levels > GDF_MAX_LEVELS || vae->num_levels > GDF_MAX_LEVELS)
+    return fail(GDF_ERR_INVALID, "gdf_create: num_levels out of range");
+  GDF_CUDA(cudaSetDevice(device));
+  gdf_handle_s* h = new gdf_handle_s();
+  h->ua = *unet;
+  h->va = *vae;
+  h->device = device;
+  *out = h;
+  return GDF_OK;
+}
+
+int gdf_destroy(gdf_handle h) {
+  if (!h) return GDF_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_plan(h);
+  for (auto& kv : h->raw)
+    if (kv.second.ptr && kv.first.find('#') == std::string::npos) cudaFree(kv.second.ptr);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return GDF_OK;
+}
+
+int gdf_load_weights(gdf_handle h, const char* const* names, const void* const* ptrs_dev, const int64_t* shapes,
+                     const int* ranks, int n, void* stream) {
+  if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t* sp = shapes;
+  for (int i = 0; i < n; ++i) {
+    RawW w;
+    w.numel = 1;
+    for (int d = 0; d < ranks[i]; ++d) {
+      w.shape.push_back(sp[d]);
+      w.numel *= sp[d];
+    }
+    sp += ranks[i];
+    GDF_CUDA(cudaMalloc(&w.ptr, (size_t)(w.numel ? w.numel : 1) * 4));
+    GDF_CUDA(cudaMemcpyAsync(w.ptr, ptrs_dev[i], (size_t)w.numel * 4, cudaMemcpyDeviceToDevice, st));
+    auto it = h->raw.find(names[i]);
+    if (it != h->raw.end()) {
+      cudaFree(it->second.ptr);
+      h->raw.erase(it);
+    }
+    h->raw[names[i]] = w;
+  }
+  GDF_CUDA(cudaStreamSynchronize(st));
+  h->finalized = false;
+  return GDF_OK;
+}
+
+int gdf_finalize_weights(gdf_handle h, void* stream) {
+  (void)stream;
+  if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  // dry walk: touches (and packs) every weight the architecture needs; reports the first missing name
+  const int B0 = h->B, img0 = h->img, L0 = h->L;
+  h->B = 1;
+  h->img = 64;
+  h->L = 8;
+  Builder b(h, true);
+  std::vector<Site> keep_sites = h->sites;
+  int r = build_vae(b);
+  if (!r) r = build_unet(b);
+  h->sites = keep_sites;
+  h->B = B0;
+  h->img = img0;
+  h->L = L0;
+  GDF_CUDA(cudaDeviceSynchronize());
+  if (r) return r;
+  h->finalized = true;
+  return GDF_OK;
+}
+
+int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch, int img_size, gdf_slot* slots_out,
+             int64_t* arena_bytes_out) {
+  if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  if (!h->finalized) return fail(GDF_ERR_INVALID, "gdf_plan: call gdf_finalize_weights first");
+  if (batch < 1 || img_size < 64 || img_size % 64 != 0)
+    return fail(GDF_ERR_SHAPE, "gdf_plan: batch %d / img_size %d unsupported (img_size must be a multiple of 64)",
+                batch, img_size);
+  GDF_CUDA(cudaSetDevice(h->device));
+  GDF_CUDA(cudaDeviceSynchronize());
+  free_plan(h);
+  h->B = batch;
+  h->img = img_size;
+  h->L = img_size / 8;
+  h->slots.assign(n_ids, gdf_slot{-1, 0, 0, 0, -1});
+  for (int i = 0; i < n_ids; ++i) {
+    const std::string id = feature_ids[i];
+    if (id.find("map") != std::string::npos || id == "vae-out" || id == "attn")
+      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps / vae-out are not built yet",
+                  id.c_str());
+    h->requested[id] = i;
+  }
+  const gdf_unet_arch& a = h->ua;
+  GDF_CUDA(cudaMalloc(&h->t_dev, (size_t)batch * 4));
+  GDF_CUDA(cudaMalloc(&h->ctx_bf16, (size_t)batch * h->ctx_len * a.cross_attention_dim * 2));
+  GDF_CUDA(cudaMalloc(&h->latent_nhwc, (size_t)batch * h->L * h->L * a.in_channels * 2));
+  if (a.addition_time_embed_dim > 0)
+    GDF_CUDA(cudaMalloc(&h->add_in, (size_t)batch * a.projection_class_embeddings_input_dim * 4));
+  Builder b(h, false);
+  b.gn_ws = static_cast<float*>(h->pool.acquire(gn_workspace_floats(batch, 64) * 4));
+  // UNet first: registers the capture sites (incl. unet-in, written by the q_sample kernel of the VAE pass)
+  int r = build_unet(b);
+  if (!r) r = build_vae(b);
+  if (r) {
+    free_plan(h);
+    return r;
+  }
+  // every requested id must have been produced by the walk (cross-k/v are accepted and never stored)
+  for (auto& kv : h->requested) {
+    if (h->slots[kv.second].offset_bytes >= 0) continue;
+    const std::string& id = kv.first;
+    if (id.find("cross-k") != std::string::npos || id.find("cross-v") != std::string::npos) continue;
+    std::string msg = "unknown feature id '" + id + "' for this architecture";
+    free_plan(h);
+    return fail(GDF_ERR_INVALID, "%s", msg.c_str());
+  }
+  for (int i = 0; i < n_ids; ++i) {
+    // duplicates in the caller's list share the first slot
+    slots_out[i] = h->slots[h->requested[feature_ids[i]]];
+  }
+  if (arena_bytes_out) *arena_bytes_out = h->arena_bytes > 0 ? h->arena_bytes : 256;
+  h->planned = true;
+  h->gpu_launches = (int)(h->vae_ops.size() + h->unet_ops.size());
+  return GDF_OK;
+}
+
+int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_dev, const void* eps_q_dev,
+                     float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,
+                     void* stream) {
+  if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_encode_noise: no plan");
+  if (!images_dev || !eps_vae_dev || !eps_q_dev) return fail(GDF_ERR_INVALID, "gdf_encode_noise: null input");
+  RunCtx rc;
+  rc.stream = static_cast<cudaStream_t>(stream);
+  rc.images = static_cast<const float*>(images_dev);
+  rc.eps_vae = static_cast<const float*>(eps_vae_dev);
+  rc.eps_q = static_cast<const float*>(eps_q_dev);
+  rc.qa = sqrt_alpha_bar;
+  rc.qb = sqrt_one_minus_alpha_bar;
+  rc.qs = input_scale;
+  rc.latents_out = static_cast<float*>(latents_out_dev);
+  rc.arena = nullptr;  // unet-in is re-captured by gdf_denoise_capture from the stored latent
+  for (auto& op : h->vae_ops) GDF_TRY(op(rc));
+  return GDF_OK;
+}
+
+int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* pooled_dev,
+                        const void* add_time_ids_dev, void* arena_dev, void* noise_pred_out_dev, void* stream) {
+  if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: no plan");
+  if (ctx_len != h->ctx_len)
+    return fail(GDF_ERR_SHAPE, "gdf_denoise_capture: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
+  if (!ctx_dev || !arena_dev) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RunCtx rc;
+  rc.stream = st;
+  rc.arena = static_cast<char*>(arena_dev);
+  rc.noise_pred_out = static_cast<float*>(noise_pred_out_dev);
+  h->pooled = static_cast<const float*>(pooled_dev);
+  h->time_ids_dev = const_cast<float*>(static_cast<const float*>(add_time_ids_dev));
+  fill_f32_kernel<<<(h->B + 255) / 256, 256, 0, st>>>(h->t_dev, timestep, h->B);
+  GDF_CUDA(cudaGetLastError());
+  GDF_CUDA(launch_cast_f32_to_bf16(static_cast<const float*>(ctx_dev), h->ctx_bf16,
+                                   (long long)h->B * h->ctx_len * h->ua.cross_attention_dim, st));
+  if (h->unet_in_cap >= 0)  // unet-in (unet_2d_condition.py:1169-1170): the scaled latent, fp16 token-major
+    GDF_CUDA(launch_cast_bf16_to_f16(h->latent_nhwc, reinterpret_cast<__half*>(rc.arena + h->unet_in_cap),
+                                     (long long)h->B * h->L * h->L * h->ua.in_channels, st));
+  for (auto& op : h->unet_ops) GDF_TRY(op(rc));
+  return GDF_OK;
+}
+
+int gdf_num_launches(gdf_handle h) { return h ? h->gpu_launches : 0; }
+int64_t gdf_workspace_bytes(gdf_handle h) { return h ? (int64_t)h->pool.total() : 0; }
+int gdf_set_ctx_len(gdf_handle h, int ctx_len) {
+  if (!h || ctx_len < 1) return fail(GDF_ERR_INVALID, "gdf_set_ctx_len");
+  if (ctx_len != h->ctx_len) {
+    h->ctx_len = ctx_len;
+    free_plan(h);
+  }
+  return GDF_OK;
+}
+
+}  // extern "C"

@@ -201,7 +201,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint8_t* a_dst = sA + s * kStageBytesA;
           uint8_t* b_dst = sB + s * kStageBytesB;
           if (p.a_mode == kALinear) {
-            tma_load_3d(a_dst, &map_a, &full_bar[s], kb * kBlockK, tc.m_tile * kBlockM, tc.bz);
+            tma_load_3d(a_dst, &map_a, &full_bar[s], kb * kBlockK, tc.m_tile * kBlockM, p.a_batched ? tc.bz : 0);
           } else {
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;

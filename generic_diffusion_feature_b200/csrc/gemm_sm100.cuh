@@ -35,6 +35,7 @@ struct GemmParams {
   int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
+  int a_batched;        // 1: A has a batch dimension, 0: shared across the batch
   int b_batched;        // 1: B has a batch dimension, 0: shared
   // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows
   int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;

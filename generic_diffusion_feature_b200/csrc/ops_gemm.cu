@@ -66,11 +66,12 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
   p.batch = batch;
   p.a_mode = kALinear;
+  p.a_batched = (batch > 1 && a_batch_stride != 0) ? 1 : 0;
   p.b_batched = (w_batch_stride != 0) ? 1 : 0;
   fill_epilogue(p, e);
   {
-    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
-    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? a_batch_stride : M * (long long)lda) * 2};
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a_batched ? batch : 1)};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : M * (long long)lda) * 2};
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
     GDF_TRY(make_tmap_bf16(&g->map_a, A, 3, dims, str, box));
   }

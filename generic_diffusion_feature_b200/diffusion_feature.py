@@ -1,0 +1,186 @@
+"""Drop-in `FeatureExtractor` for the B200 path (mirror of feature/diffusion_feature.py in the reference).
+
+Same constructor and method signatures (diffusion_feature.py:26-40,118-144,149-235,520-527). Underneath, the
+diffusers pipeline is replaced by libgdf_b200.so: `extract` = gdf_encode_noise (VAE encode + posterior sample
++ q_sample + scale_model_input) followed by gdf_denoise_capture (one UNet forward whose kernels write the
+selected activations straight into a preallocated fp16 arena). There is no PyTorch compute on the path and no
+CPU fallback.
+
+Differences a user can observe (all documented in INTEGRATION.md):
+  * returned maps are fp16 CUDA tensors shaped (B, C, h, w) like the reference's, but ALL of them are
+    token-major-strided views of one arena (the reference returns conv maps NCHW-contiguous and ViT maps
+    token-major, feature_extractor.py:46-48); values and indexing are identical, `.contiguous()` restores NCHW;
+  * `extract(..., noise=(eps_vae, eps_q))` optionally injects the two Gaussian draws the reference makes
+    un-seeded (pipeline_pixart_sigma.py:644,671) so that results are reproducible;
+  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion and the DiT families
+    raise NotImplementedError (out of the hot path).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, schedulers
+from ._lib import check
+from .components.feature_extractor import FeaturePlan, prepare_feature_extractor, selected_ids
+from .components.models import get_diffusion_model
+
+
+class FeatureExtractor(nn.Module):
+    def __init__(self,
+                 layer,  # the filename of layer json or a pre-loaded dict
+                 version,  # xl, pgv2, 1-5, 2-1
+                 device,
+                 dtype='float16',
+                 img_size=1024,  # 512 for 1-5, 1024 otherwise
+                 offline_lora=None,
+                 offline_lora_filename=None,
+                 feature_resize=1,
+                 control=None,
+                 attention=None,
+                 train_unet=False,
+                 external_model=None,
+                 ):
+        super().__init__()
+        if control:
+            raise NotImplementedError("ControlNet conditioning is outside the B200 hot path")
+        if attention:
+            raise NotImplementedError("aggregated attention maps are not built on the B200 path yet")
+        if external_model:
+            pipe = external_model            # diffusion_feature.py:46-47: the seam for pre-built pipes
+        else:
+            pipe = get_diffusion_model(version, dtype, offline_lora, offline_lora_filename, device=device)
+        self.feature_store = prepare_feature_extractor(version, pipe, layer, feature_resize, train_unet)
+        self.store_vae_output = bool(self.feature_store.to_store.get('vae-out', False))
+        self.pipe = pipe
+        self.control_pipe = None
+        self.attention_store = None
+        self.version = version
+        self.img_size = img_size
+        self.device = device
+        self.control = control
+        self.attention = attention
+        self._plan = None
+        self._ids = selected_ids(self.feature_store, pipe)
+
+    # ------------------------------------------------------------------------------------------ images
+    def _preprocess_basic(self, x):
+        return x.resize((self.img_size, self.img_size)).convert("RGB")
+
+    def preprocess_image(self, x, is_tensor=False):
+        """PIL -> (1,3,S,S) in [-1,1] (VaeImageProcessor.preprocess semantics: /255, NCHW, 2x-1);
+        tensors pass through (diffusion_feature.py:122-140)."""
+        if is_tensor:
+            return x
+        arr = np.asarray(self._preprocess_basic(x), dtype=np.float32) / 255.0
+        return torch.from_numpy(arr).permute(2, 0, 1)[None] * 2.0 - 1.0
+
+    def restore_from_tensor_to_image(self, x):
+        from PIL import Image
+        x = ((x.detach().float().cpu() / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+        return [Image.fromarray(i.permute(1, 2, 0).numpy()) for i in x]
+
+    # ------------------------------------------------------------------------------------------ prompts
+    def encode_prompt(self, prompt_str=None, prompt_file=None):
+        """The reference encodes text with the pipeline's CLIP encoders (diffusion_feature.py:149-206). No
+        text-encoder weights exist offline, and text encoding is outside the extraction path (empty-prompt
+        conditioning, encoded once): this returns deterministic stand-in embeddings of the right shapes
+        (N(0,1), seeded by the prompt text). Real embeddings can be passed to `extract` directly."""
+        assert prompt_str != None and prompt_file == None or prompt_str == None and prompt_file != None
+        if prompt_file:
+            with open(prompt_file, 'r') as f:
+                prompt_str = f.read()
+        import zlib
+        g = torch.Generator().manual_seed(zlib.crc32(prompt_str.encode()))
+        ctx_dim = self.pipe.unet_cfg["ctx_dim"]
+        emb = torch.randn(1, 77, ctx_dim, generator=g)
+        neg = torch.randn(1, 77, ctx_dim, generator=g)
+        if self.version in ('xl', 'pgv2'):
+            pooled = torch.randn(1, 1280, generator=g)
+            npooled = torch.randn(1, 1280, generator=g)
+            return emb, neg, pooled, npooled
+        return emb, neg, None, None
+
+    def offload_prompt_encoder(self, persistent=False):
+        return None   # no text encoder is resident on the B200 path
+
+    # ------------------------------------------------------------------------------------------ extract
+    def _ensure_plan(self, batch_size):
+        if self._plan is None or self._plan.batch != batch_size or self._plan.img_size != self.img_size:
+            self._plan = FeaturePlan(self.pipe, self._ids, batch_size, self.img_size)
+        return self._plan
+
+    @torch.no_grad()
+    def extract(self,
+                prompts,  # the same as the outputs of the last function
+                batch_size,
+                image,
+                image_type='image',  # otherwise: tensors
+                t=50,
+                denoising_from=None,
+                use_control=False,
+                use_ddim_inversion=False,
+                noise=None,   # extension: (eps_vae, eps_q), each (B,4,S/8,S/8)
+                ):
+        if denoising_from:
+            raise NotImplementedError("denoising_from (multi-step denoise loop) is deprecated in the reference and "
+                                      "not built here")
+        if use_control or use_ddim_inversion:
+            raise NotImplementedError("ControlNet / DDIM inversion are outside the B200 hot path")
+        if self.feature_store.store_idx is not None:
+            raise NotImplementedError("background extraction hooks a generation loop, which is not built here")
+        pipe = self.pipe
+        dev = pipe.device
+        self.feature_store.reset()
+        prompt_embeds, _neg, pooled, _npooled = prompts
+        prompt_embeds = prompt_embeds.repeat(batch_size, 1, 1) if prompt_embeds.shape[0] == 1 else prompt_embeds
+        if pooled is not None and pooled.shape[0] == 1:
+            pooled = pooled.repeat(batch_size, 1)
+        timestep, qa, qb, qs = schedulers.resolve(self.version, t)
+        # 6. prepare image (diffusion_feature.py:357-364)
+        if image_type == 'image':
+            image = torch.concat([self.preprocess_image(r) for r in image], dim=0)
+        image = image.to(dev, torch.float32, non_blocking=True)
+        if image.shape[-2:] != (self.img_size, self.img_size):
+            image = F.interpolate(image, (self.img_size, self.img_size), mode='bilinear')
+        image = image.contiguous()
+        if image.shape[0] != batch_size:
+            raise ValueError("got %d images for batch_size %d" % (image.shape[0], batch_size))
+        plan = self._ensure_plan(batch_size)
+        L = self.img_size // 8
+        if noise is None:
+            eps_vae = torch.randn(batch_size, 4, L, L, device=dev)
+            eps_q = torch.randn(batch_size, 4, L, L, device=dev)
+        else:
+            eps_vae = noise[0].to(dev, torch.float32).contiguous()
+            eps_q = noise[1].to(dev, torch.float32).contiguous()
+        ctx = prompt_embeds.to(dev, torch.float32).contiguous()
+        pooled_d = pooled.to(dev, torch.float32).contiguous() if pooled is not None else None
+        time_ids = None
+        if self.version in ('xl', 'pgv2'):
+            # _get_add_time_ids (diffusion_feature.py:534-571): original_size + crop (0,0) + target_size
+            s = float(self.img_size)
+            time_ids = torch.tensor([[s, s, 0.0, 0.0, s, s]], device=dev).repeat(batch_size, 1).contiguous()
+        arena = torch.empty(plan.arena_bytes, dtype=torch.uint8, device=dev)
+        lib = pipe.lib
+        with torch.cuda.device(pipe.dev_index):
+            st = _lib.stream_ptr()
+            check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb, qs,
+                                       None, st))
+            check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
+                                          _lib.ptr(time_ids), _lib.ptr(arena), None, st))
+        feats = plan.views(arena)
+        if self.feature_store.accept_all:
+            feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
+        self.feature_store.feats = feats
+        # keep inputs alive until the stream has consumed them
+        self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena)
+        return self.feature_store.stored_feats
+
+    def set_background_extraction(self, idxs):
+        self.feature_store.store_idx = idxs
+
+    def get_background_extraction(self):
+        return {k: v['feat'] for k, v in self.feature_store.feats.items()}

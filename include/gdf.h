@@ -99,6 +99,11 @@ typedef struct gdf_slot {
 } gdf_slot;
 int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch, int img_size, gdf_slot* slots_out,
              int64_t* arena_bytes_out);
+/* Encoder-hidden-state length the next plan is built for (default 77, CLIP). Invalidates the current plan. */
+int gdf_set_ctx_len(gdf_handle h, int ctx_len);
+/* Introspection of the current plan: kernels launched per (encode + denoise) pass, internal workspace bytes. */
+int gdf_num_launches(gdf_handle h);
+int64_t gdf_workspace_bytes(gdf_handle h);
 
 /* images -> VAE-encoded, noised, scaled latents (replaces pipe.prepare_latents + scheduler.scale_model_input;
  * pipelines/pixart_alpha/pipeline_pixart_sigma.py:598-677, diffusion_feature.py:371-380,405-406).

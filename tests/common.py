@@ -1,0 +1,59 @@
+"""Shared helpers of the test-suite: seeded synthetic inputs and oracle construction."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import torch_oracle as O  # noqa: E402  (test infrastructure: the checker)
+
+# reduced-width configurations with the SDXL / SD-2.1 topology (every kernel shape class of the full models:
+# skip-concat resnets with 1x1 shortcuts, stride-2 and upsampled convs, multi-depth transformers, head_dim 64)
+TINY_XL = dict(block_out=(64, 128, 256), down_attn=(0, 1, 1), up_attn=(1, 1, 0), depth=(1, 1, 2),
+               heads=(1, 2, 4), ctx_dim=128, linear_proj=True, add_time_dim=32, add_in=64 + 6 * 32, eps=1e-5)
+TINY_21 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+               heads=(1, 2, 4, 4), ctx_dim=128, linear_proj=True, add_time_dim=0, add_in=0, eps=1e-5)
+TINY_VAE = dict(block_out=(64, 64, 128, 128), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025)
+
+
+def make_inputs(batch, img, ctx_dim, pooled_dim=None, ctx_len=77):
+    """Synthetic inputs of SURVEY.md 8d: images rand*2-1 (seed 1234), ctx N(0,1) (1235), pooled (1236),
+    eps_vae / eps_q (1237 / 1238)."""
+    g = lambda s: torch.Generator().manual_seed(s)
+    image = torch.rand(batch, 3, img, img, generator=g(1234)) * 2 - 1
+    ctx = torch.randn(1, ctx_len, ctx_dim, generator=g(1235))
+    pooled = torch.randn(1, pooled_dim, generator=g(1236)) if pooled_dim else None
+    L = img // 8
+    eps_vae = torch.randn(batch, 4, L, L, generator=g(1237))
+    eps_q = torch.randn(batch, 4, L, L, generator=g(1238))
+    return image, ctx, pooled, eps_vae, eps_q
+
+
+def build_oracle(unet_cfg, vae_cfg, sd):
+    """Oracle modules loaded from a 'unet.*' / 'vae.*' state dict (fp32, CPU)."""
+    unet = O.UNet2DConditionModel(unet_cfg)
+    vae = O.Vae(vae_cfg["scaling_factor"], block_out=vae_cfg["block_out"], layers=vae_cfg["layers"],
+                latent=vae_cfg["latent"], eps=vae_cfg["eps"])
+    usd = {k[len("unet."):]: v.float().cpu() for k, v in sd.items() if k.startswith("unet.")}
+    vsd = {k[len("vae."):]: v.float().cpu() for k, v in sd.items() if k.startswith("vae.")}
+    unet.load_state_dict(usd, strict=True)
+    vae.load_state_dict(vsd, strict=True)
+    return unet.eval(), vae.eval()
+
+
+def compare_maps(got, want):
+    """Per-map cosine similarity / relative L2 / max-relative error between two dicts of (B,C,h,w) maps."""
+    rows = []
+    for k, w in want.items():
+        g = got[k].float().cpu()
+        w = w.float()
+        assert g.shape == w.shape, "%s: shape %s vs %s" % (k, tuple(g.shape), tuple(w.shape))
+        gf, wf = g.flatten(), w.flatten()
+        cos = torch.nn.functional.cosine_similarity(gf, wf, dim=0).item()
+        rel = ((gf - wf).norm() / (wf.norm() + 1e-12)).item()
+        maxrel = ((gf - wf).abs().max() / (wf.abs().max() + 1e-12)).item()
+        rows.append((k, cos, rel, maxrel))
+    return rows

@@ -1,0 +1,87 @@
+"""End-to-end parity of the CUDA extraction path against the CPU oracle, through the reference-facing API
+(`FeatureExtractor.extract` -> C ABI -> sm_100a kernels), on identical synthetic weights, inputs and injected
+noise. North-star tolerance: per-feature-map cosine similarity >= 0.999 against the fp32 reference path;
+max-relative error (max |diff| / max |ref|) is reported and bounded at 5e-2 for bf16 compute.
+"""
+import pytest
+import torch
+
+from common import O, TINY_21, TINY_VAE, TINY_XL, build_oracle, compare_maps, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999
+MAXREL_MAX = 5e-2
+
+
+def _run_case(version, ucfg, batch, img, subset=None):
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict(version, "cpu", ucfg, TINY_VAE)
+    pooled_dim = (ucfg["add_in"] - 6 * ucfg["add_time_dim"]) if ucfg["add_time_dim"] else None
+    image, ctx, pooled, eps_vae, eps_q = make_inputs(batch, img, ucfg["ctx_dim"], pooled_dim)
+    ids = _unet_feature_ids(ucfg)
+    if subset:
+        ids = [i for i in ids if subset(i)]
+    layer = {i: True for i in ids}
+    # ---- oracle (CPU fp32)
+    unet, vae = build_oracle(ucfg, TINY_VAE, sd)
+    store = O.FeatureStore(layer)
+    O.attach_gatherers(unet, store)
+    want, _, _ = O.extract(version, unet, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50, img_size=img)
+    # ---- CUDA path through the reference-facing API
+    pipe = models.get_diffusion_model(version, "float16", device="cuda:0", state_dict=sd, unet_cfg=ucfg,
+                                      vae_cfg=TINY_VAE)
+    fe = FeatureExtractor(layer, version, "cuda:0", img_size=img, external_model=pipe)
+    got = fe.extract((ctx, ctx, pooled, pooled), batch, image.cuda(), image_type="tensors", t=50,
+                     noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == list(want.keys()), "feature ids / insertion order differ from the oracle"
+    for v in got.values():
+        assert v.dtype == torch.float16 and v.is_cuda      # feature_extractor.py:59-60
+    rows = compare_maps(got, want)
+    worst = sorted(rows, key=lambda r: r[1])[:5]
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "maps out of tolerance (id, cos, rel, maxrel): %s ; worst: %s" % (bad[:8], worst)
+    return rows
+
+
+def test_tiny_xl_full_set(cuda_dev):
+    rows = _run_case("xl", TINY_XL, batch=2, img=128)
+    assert len(rows) > 60
+
+
+def test_tiny_xl_batch3_img256(cuda_dev):
+    _run_case("xl", TINY_XL, batch=3, img=256,
+              subset=lambda i: i.endswith("-out") or "cross-q" in i or "ffn-inner" in i)
+
+
+def test_tiny_21_full_set(cuda_dev):
+    _run_case("2-1", TINY_21, batch=2, img=128)
+
+
+def test_unknown_id_and_unbuilt_features(cuda_dev):
+    from generic_diffusion_feature_b200._lib import GdfError
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL,
+                                      vae_cfg=TINY_VAE)
+    image, ctx, pooled, eps_vae, eps_q = make_inputs(1, 128, 128, 64)
+    fe = FeatureExtractor({"up-level9-repeat0-res-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
+    with pytest.raises(GdfError):
+        fe.extract((ctx, ctx, pooled, pooled), 1, image, image_type="tensors")
+    with pytest.raises(NotImplementedError):
+        FeatureExtractor({"mid-vit-block0-self-map": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
+    # cross-k / cross-v are accepted and silently dropped, like FeatureStore.store (feature_extractor.py:38-39)
+    fe = FeatureExtractor({"mid-vit-block0-cross-k": True, "mid-vit-out": True}, "xl", "cuda:0", img_size=128,
+                          external_model=pipe)
+    out = fe.extract((ctx, ctx, pooled, pooled), 1, image, image_type="tensors")
+    assert list(out.keys()) == ["mid-vit-out"]
+    with pytest.raises(NotImplementedError):
+        models.get_diffusion_model("xl", "bfloat16")      # models.py:15-16
+    with pytest.raises(NotImplementedError):
+        models.get_diffusion_model("no-such-version", "float16")
