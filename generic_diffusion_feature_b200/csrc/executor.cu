@@ -38,6 +38,33 @@ struct RunCtx {
 };
 typedef std::function<int(const RunCtx&)> Op;
 
+enum OpKind : int { kKindGemm = 0, kKindAttention = 1, kKindGroupNorm = 2, kKindLayerNorm = 3, kKindOther = 4,
+                    kNumKinds = 5 };
+struct OpList {   // flat program: closures + bookkeeping for the profiling pass
+  std::vector<Op> fns;
+  std::vector<int> kinds;
+  std::vector<double> flops;
+  int cur_kind = kKindOther;
+  double cur_flops = 0.0;
+  void push_back(Op f) {
+    fns.push_back(std::move(f));
+    kinds.push_back(cur_kind);
+    flops.push_back(cur_flops);
+    cur_kind = kKindOther;
+    cur_flops = 0.0;
+  }
+  void tag(int kind, double fl) {
+    cur_kind = kind;
+    cur_flops = fl;
+  }
+  void clear() {
+    fns.clear();
+    kinds.clear();
+    flops.clear();
+  }
+  size_t size() const { return fns.size(); }
+};
+
 #define OP_CUDA(expr)                                                                          \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
@@ -145,7 +172,11 @@ struct gdf_handle_s {
   // plan
   bool planned = false;
   int B = 0, img = 0, L = 0, ctx_len = 77;
-  std::vector<Op> vae_ops, unet_ops;
+  OpList vae_ops, unet_ops;
+  bool profile = false;
+  float prof_ms[kNumKinds] = {0, 0, 0, 0, 0};
+  double prof_flops[kNumKinds] = {0, 0, 0, 0, 0};
+  int prof_launches[kNumKinds] = {0, 0, 0, 0, 0};
   BufPool pool;
   std::unordered_map<std::string, int> requested;  // id -> index in the caller's list
   std::vector<gdf_slot> slots;
@@ -185,7 +216,7 @@ class Builder {
   gdf_handle_s* h;
   bool dry;
   int err = 0;
-  std::vector<Op>* ops = nullptr;
+  OpList* ops = nullptr;
   float* gn_ws = nullptr;
 
   int set_err(int e) {
@@ -366,6 +397,8 @@ class Builder {
     p.ld_cap_pre = p.n_out;
     const GemmLaunch gl = g;
     const Caps c = caps;
+    ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
+                            (double)p.batch);
     ops->push_back([gl, c](const RunCtx& rc) -> int {
       GemmParams p = gl.p;
       if (c.pre >= 0) p.cap_pre = reinterpret_cast<__half*>(rc.arena + c.pre);
@@ -402,6 +435,7 @@ class Builder {
     const float* bt = f32(prefix + ".bias");
     if (dry || err) return;
     float* ws = gn_ws;
+    ops->tag(kKindGroupNorm, 0.0);
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_groupnorm(x, y, gm, bt, B, HW, C, G, eps, silu, ws, rc.stream));
       return 0;
@@ -411,6 +445,7 @@ class Builder {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
     if (dry || err) return;
+    ops->tag(kKindLayerNorm, 0.0);
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_layernorm(x, y, gm, bt, M, C, eps, nullptr, nullptr, 0, rc.stream));
       return 0;
@@ -419,6 +454,7 @@ class Builder {
   void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int B,
                  int heads, int Nq, int Nk, float scale) {
     if (dry || err) return;
+    ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * 64.0);
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_attention64(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, scale, rc.stream));
       return 0;
@@ -1219,6 +1255,35 @@ static void free_plan(gdf_handle_s* h) {
   h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr;
 }
 
+static int run_ops(gdf_handle_s* h, OpList& ops, const RunCtx& rc) {
+  if (!h->profile) {
+    for (auto& op : ops.fns) GDF_TRY(op(rc));
+    return GDF_OK;
+  }
+  // profiling pass: one CUDA-event pair per op on the launching stream (ops are serialised on it)
+  const size_t n = ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], rc.stream);
+  int r = GDF_OK;
+  for (size_t i = 0; i < n && r == GDF_OK; ++i) {
+    r = ops.fns[i](rc);
+    cudaEventRecord(ev[i + 1], rc.stream);
+  }
+  cudaStreamSynchronize(rc.stream);
+  if (r == GDF_OK) {
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      h->prof_ms[ops.kinds[i]] += ms;
+      h->prof_flops[ops.kinds[i]] += ops.flops[i];
+      h->prof_launches[ops.kinds[i]] += 1;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return r;
+}
+
 }  // namespace gdf
 
 // ============================================================================================ C ABI
@@ -1368,7 +1433,7 @@ int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_d
   rc.qs = input_scale;
   rc.latents_out = static_cast<float*>(latents_out_dev);
   rc.arena = nullptr;  // unet-in is re-captured by gdf_denoise_capture from the stored latent
-  for (auto& op : h->vae_ops) GDF_TRY(op(rc));
+  GDF_TRY(run_ops(h, h->vae_ops, rc));
   return GDF_OK;
 }
 
@@ -1392,10 +1457,33 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
   if (h->unet_in_cap >= 0)  // unet-in (unet_2d_condition.py:1169-1170): the scaled latent, fp16 token-major
     GDF_CUDA(launch_cast_bf16_to_f16(h->latent_nhwc, reinterpret_cast<__half*>(rc.arena + h->unet_in_cap),
                                      (long long)h->B * h->L * h->L * h->ua.in_channels, st));
-  for (auto& op : h->unet_ops) GDF_TRY(op(rc));
+  GDF_TRY(run_ops(h, h->unet_ops, rc));
   return GDF_OK;
 }
 
+/* Profiling pass: while enabled, encode/denoise record a CUDA-event pair around every kernel launch and
+ * accumulate device time / algorithmic FLOPs / launch counts per kernel kind (0 tcgen05 GEMM+conv, 1 attention,
+ * 2 GroupNorm, 3 LayerNorm, 4 other). Enabling resets the counters. */
+int gdf_profile(gdf_handle h, int enable) {
+  if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  h->profile = enable != 0;
+  if (enable)
+    for (int i = 0; i < kNumKinds; ++i) {
+      h->prof_ms[i] = 0.f;
+      h->prof_flops[i] = 0.0;
+      h->prof_launches[i] = 0;
+    }
+  return GDF_OK;
+}
+int gdf_profile_read(gdf_handle h, float* ms_out, double* flops_out, int* launches_out) {
+  if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  for (int i = 0; i < kNumKinds; ++i) {
+    ms_out[i] = h->prof_ms[i];
+    flops_out[i] = h->prof_flops[i];
+    launches_out[i] = h->prof_launches[i];
+  }
+  return GDF_OK;
+}
 int gdf_num_launches(gdf_handle h) { return h ? h->gpu_launches : 0; }
 int64_t gdf_workspace_bytes(gdf_handle h) { return h ? (int64_t)h->pool.total() : 0; }
 int gdf_set_ctx_len(gdf_handle h, int ctx_len) {

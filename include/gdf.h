@@ -104,6 +104,11 @@ int gdf_set_ctx_len(gdf_handle h, int ctx_len);
 /* Introspection of the current plan: kernels launched per (encode + denoise) pass, internal workspace bytes. */
 int gdf_num_launches(gdf_handle h);
 int64_t gdf_workspace_bytes(gdf_handle h);
+/* Profiling pass (bench.py roofline): while enabled, every kernel launch of encode/denoise is bracketed by a
+ * CUDA-event pair on the launching stream; device ms / algorithmic FLOPs / launches accumulate per kernel kind
+ * (0 tcgen05 GEMM + implicit-GEMM conv, 1 attention, 2 GroupNorm, 3 LayerNorm, 4 other). Arrays of 5. */
+int gdf_profile(gdf_handle h, int enable);
+int gdf_profile_read(gdf_handle h, float* ms_out, double* flops_out, int* launches_out);
 
 /* images -> VAE-encoded, noised, scaled latents (replaces pipe.prepare_latents + scheduler.scale_model_input;
  * pipelines/pixart_alpha/pipeline_pixart_sigma.py:598-677, diffusion_feature.py:371-380,405-406).
