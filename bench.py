@@ -208,7 +208,11 @@ def run_ours(args, rank, world, local):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()      # ncu --profile-from-start off: capture the timed steps only
     ms = timed(step_device, args.steps)
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
@@ -230,6 +234,8 @@ def run_ours(args, rank, world, local):
         flv = (ctypes.c_double * 5)()
         lnv = (ctypes.c_int * 5)()
         _lib.check(lib.gdf_profile_read(pipe.handle, msv, flv, lnv))
+        if args.profile_csv:
+            _lib.check(lib.gdf_profile_dump(pipe.handle, args.profile_csv.encode()))
         _lib.check(lib.gdf_profile(pipe.handle, 0))
         sustained, burst, hbm, how = read_peaks()
         gemm_tflops = flv[0] / (msv[0] * 1e-3) / 1e12 if msv[0] > 0 else 0.0
@@ -291,6 +297,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
+    ap.add_argument("--profile-csv", default=None, help="write the per-launch table of the profiling pass here")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.impl == "reference":

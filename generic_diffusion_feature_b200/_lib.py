@@ -22,7 +22,7 @@ EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
     "gdf_create", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
     "gdf_encode_noise", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
-    "gdf_profile", "gdf_profile_read",
+    "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
     "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
@@ -130,6 +130,7 @@ def load():
         lib.gdf_workspace_bytes.argtypes = [P]
         lib.gdf_workspace_bytes.restype = c_int64
         lib.gdf_profile.argtypes = [P, c_int]
+        lib.gdf_profile_dump.argtypes = [P, ctypes.c_char_p]
         lib.gdf_profile_read.argtypes = [P, ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(c_int)]
     _lib = lib

@@ -44,23 +44,32 @@ struct OpList {   // flat program: closures + bookkeeping for the profiling pass
   std::vector<Op> fns;
   std::vector<int> kinds;
   std::vector<double> flops;
+  std::vector<std::string> labels;
+  std::vector<float> last_ms;
   int cur_kind = kKindOther;
   double cur_flops = 0.0;
+  std::string cur_label;
   void push_back(Op f) {
     fns.push_back(std::move(f));
     kinds.push_back(cur_kind);
     flops.push_back(cur_flops);
+    labels.push_back(cur_label);
+    last_ms.push_back(0.f);
     cur_kind = kKindOther;
     cur_flops = 0.0;
+    cur_label.clear();
   }
-  void tag(int kind, double fl) {
+  void tag(int kind, double fl, const std::string& label = std::string()) {
     cur_kind = kind;
     cur_flops = fl;
+    cur_label = label;
   }
   void clear() {
     fns.clear();
     kinds.clear();
     flops.clear();
+    labels.clear();
+    last_ms.clear();
   }
   size_t size() const { return fns.size(); }
 };
@@ -397,8 +406,14 @@ class Builder {
     p.ld_cap_pre = p.n_out;
     const GemmLaunch gl = g;
     const Caps c = caps;
-    ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
-                            (double)p.batch);
+    {
+      char lbl[160];
+      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d batch=%d act=%d res=%d caps=%d pre=%d tiles=%d",
+               p.a_mode, p.M, p.N, p.K, p.block_n, p.batch, p.act, p.residual ? 1 : 0, caps.n, caps.pre >= 0 ? 1 : 0,
+               p.batch * p.num_m_tiles * p.num_n_tiles);
+      ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
+                              (double)p.batch, lbl);
+    }
     ops->push_back([gl, c](const RunCtx& rc) -> int {
       GemmParams p = gl.p;
       if (c.pre >= 0) p.cap_pre = reinterpret_cast<__half*>(rc.arena + c.pre);
@@ -435,7 +450,7 @@ class Builder {
     const float* bt = f32(prefix + ".bias");
     if (dry || err) return;
     float* ws = gn_ws;
-    ops->tag(kKindGroupNorm, 0.0);
+    ops->tag(kKindGroupNorm, 0.0, "groupnorm HW=" + std::to_string(HW) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_groupnorm(x, y, gm, bt, B, HW, C, G, eps, silu, ws, rc.stream));
       return 0;
@@ -445,7 +460,7 @@ class Builder {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
     if (dry || err) return;
-    ops->tag(kKindLayerNorm, 0.0);
+    ops->tag(kKindLayerNorm, 0.0, "layernorm M=" + std::to_string(M) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_layernorm(x, y, gm, bt, M, C, eps, nullptr, nullptr, 0, rc.stream));
       return 0;
@@ -454,7 +469,8 @@ class Builder {
   void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int B,
                  int heads, int Nq, int Nk, float scale) {
     if (dry || err) return;
-    ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * 64.0);
+    ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * 64.0,
+             "attention heads=" + std::to_string(heads) + " Nq=" + std::to_string(Nq) + " Nk=" + std::to_string(Nk));
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_attention64(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, scale, rc.stream));
       return 0;
@@ -1275,6 +1291,7 @@ static int run_ops(gdf_handle_s* h, OpList& ops, const RunCtx& rc) {
     for (size_t i = 0; i < n; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      ops.last_ms[i] = ms;
       h->prof_ms[ops.kinds[i]] += ms;
       h->prof_flops[ops.kinds[i]] += ops.flops[i];
       h->prof_launches[ops.kinds[i]] += 1;
@@ -1482,6 +1499,24 @@ int gdf_profile_read(gdf_handle h, float* ms_out, double* flops_out, int* launch
     flops_out[i] = h->prof_flops[i];
     launches_out[i] = h->prof_launches[i];
   }
+  return GDF_OK;
+}
+/* Writes the per-launch table of the last profiling pass (phase, index, kind, ms, GFLOP, label) as CSV. */
+int gdf_profile_dump(gdf_handle h, const char* path) {
+  if (!h || !path) return fail(GDF_ERR_INVALID, "gdf_profile_dump");
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(GDF_ERR_INVALID, "cannot open %s", path);
+  fprintf(f, "phase,index,kind,ms,gflop,tflops,label\n");
+  const char* names[2] = {"vae", "unet"};
+  OpList* lists[2] = {&h->vae_ops, &h->unet_ops};
+  for (int l = 0; l < 2; ++l)
+    for (size_t i = 0; i < lists[l]->size(); ++i) {
+      const float ms = lists[l]->last_ms[i];
+      const double fl = lists[l]->flops[i];
+      fprintf(f, "%s,%zu,%d,%.4f,%.3f,%.1f,%s\n", names[l], i, lists[l]->kinds[i], ms, fl / 1e9,
+              ms > 0 ? fl / (ms * 1e-3) / 1e12 : 0.0, lists[l]->labels[i].c_str());
+    }
+  fclose(f);
   return GDF_OK;
 }
 int gdf_num_launches(gdf_handle h) { return h ? h->gpu_launches : 0; }

@@ -109,6 +109,8 @@ int64_t gdf_workspace_bytes(gdf_handle h);
  * (0 tcgen05 GEMM + implicit-GEMM conv, 1 attention, 2 GroupNorm, 3 LayerNorm, 4 other). Arrays of 5. */
 int gdf_profile(gdf_handle h, int enable);
 int gdf_profile_read(gdf_handle h, float* ms_out, double* flops_out, int* launches_out);
+/* CSV of the last profiling pass, one row per kernel launch (phase,index,kind,ms,gflop,tflops,label). */
+int gdf_profile_dump(gdf_handle h, const char* path);
 
 /* images -> VAE-encoded, noised, scaled latents (replaces pipe.prepare_latents + scheduler.scale_model_input;
  * pipelines/pixart_alpha/pipeline_pixart_sigma.py:598-677, diffusion_feature.py:371-380,405-406).
