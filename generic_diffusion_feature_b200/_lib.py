@@ -21,7 +21,7 @@ GDF_MAX_LEVELS = 4
 EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
     "gdf_create", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
-    "gdf_encode_noise", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
+    "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
@@ -124,6 +124,7 @@ def load():
         lib.gdf_plan.argtypes = [P, ctypes.POINTER(ctypes.c_char_p), c_int, c_int, c_int, ctypes.POINTER(Slot),
                                  ctypes.POINTER(c_int64)]
         lib.gdf_encode_noise.argtypes = [P, P, P, P, c_float, c_float, c_float, P, P]
+        lib.gdf_encode_latents.argtypes = [P, P, P, c_float, c_float, c_float, P, P]
         lib.gdf_denoise_capture.argtypes = [P, c_float, P, c_int, P, P, P, P, P]
         lib.gdf_set_ctx_len.argtypes = [P, c_int]
         lib.gdf_num_launches.argtypes = [P]

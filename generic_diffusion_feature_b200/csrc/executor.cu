@@ -104,6 +104,22 @@ __global__ void add_f32_kernel(float* dst, const float* a, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += a[i];
 }
+// latents given directly (prepare_latents, image.shape[1] == 4 branch, pipeline_pixart_sigma.py:623-624):
+// x_t = a*z + b*eps, model input = x_t * s; NCHW fp32 in, NHWC bf16 out
+__global__ void latents_qsample_kernel(const float* __restrict__ z, const float* __restrict__ eps, float a, float b,
+                                       float s, bf16* __restrict__ latent_nhwc, float* __restrict__ latents_out, int B,
+                                       int HW, int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long r = i / HW;
+    const int c = (int)(r % C), bb = (int)(r / C);
+    const float xt = a * z[i] + b * (eps ? eps[i] : 0.f);
+    if (latents_out) latents_out[i] = xt;
+    latent_nhwc[((long long)bb * HW + p) * C + c] = __float2bfloat16_rn(xt * s);
+  }
+}
 // moments/noise-pred style NHWC bf16/f32 [B, HW, C] -> NCHW fp32 (B, C, HW)
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
   const long long total = (long long)B * HW * C;
@@ -1451,6 +1467,18 @@ int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_d
   rc.latents_out = static_cast<float*>(latents_out_dev);
   rc.arena = nullptr;  // unet-in is re-captured by gdf_denoise_capture from the stored latent
   GDF_TRY(run_ops(h, h->vae_ops, rc));
+  return GDF_OK;
+}
+
+int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_dev, float sqrt_alpha_bar,
+                       float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev, void* stream) {
+  if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_encode_latents: no plan");
+  if (!latents_dev) return fail(GDF_ERR_INVALID, "gdf_encode_latents: null input");
+  const int HW = h->L * h->L, C = h->ua.in_channels;
+  latents_qsample_kernel<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(latents_dev), static_cast<const float*>(eps_q_dev), sqrt_alpha_bar,
+      sqrt_one_minus_alpha_bar, input_scale, h->latent_nhwc, static_cast<float*>(latents_out_dev), h->B, HW, C);
+  GDF_CUDA(cudaGetLastError());
   return GDF_OK;
 }
 

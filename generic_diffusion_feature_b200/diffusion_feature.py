@@ -143,7 +143,8 @@ class FeatureExtractor(nn.Module):
         if image_type == 'image':
             image = torch.concat([self.preprocess_image(r) for r in image], dim=0)
         image = image.to(dev, torch.float32, non_blocking=True)
-        if image.shape[-2:] != (self.img_size, self.img_size):
+        is_latents = image.shape[1] == 4      # prepare_latents: 4-channel input is taken as latents (:623-624)
+        if not is_latents and image.shape[-2:] != (self.img_size, self.img_size):
             image = F.interpolate(image, (self.img_size, self.img_size), mode='bilinear')
         image = image.contiguous()
         if image.shape[0] != batch_size:
@@ -167,8 +168,11 @@ class FeatureExtractor(nn.Module):
         lib = pipe.lib
         with torch.cuda.device(pipe.dev_index):
             st = _lib.stream_ptr()
-            check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb, qs,
-                                       None, st))
+            if is_latents:
+                check(lib.gdf_encode_latents(pipe.handle, _lib.ptr(image), _lib.ptr(eps_q), qa, qb, qs, None, st))
+            else:
+                check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb,
+                                           qs, None, st))
             check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
                                           _lib.ptr(time_ids), _lib.ptr(arena), None, st))
         feats = plan.views(arena)

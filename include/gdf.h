@@ -122,6 +122,11 @@ int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_d
                      float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,
                      void* stream);
 
+/* Latents supplied directly: the `image.shape[1] == 4` branch of prepare_latents (pipeline_pixart_sigma.py:623-624)
+ * - no VAE pass; x_t = a*latents + b*eps_q (eps_q_dev may be NULL = no noise), model input = x_t * input_scale. */
+int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_dev, float sqrt_alpha_bar,
+                       float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev, void* stream);
+
 /* One denoiser forward with capture (replaces pipe.unet(...) at diffusion_feature.py:446-465 and every
  * feature_gatherer.gather call site listed in SURVEY.md 2.2).
  *   timestep : resolved scheduler timestep (float, e.g. 50.0)

@@ -1,0 +1,259 @@
+"""CPU-only tests (`-m "not gpu"`): the oracle against the golden fixtures produced from the reference's own code,
+the host logic (id grammar, parameter naming, schedulers, error behaviour, sharding) and the C-ABI surface
+(library loads, exports every symbol include/gdf.h declares; no compute calls)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from common import O, ROOT, TINY_21, TINY_VAE, TINY_XL, build_oracle, make_inputs
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _models():
+    from generic_diffusion_feature_b200.components import models
+    return models
+
+
+# ------------------------------------------------------------------------------------------ oracle vs golden
+@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21)])
+def test_oracle_matches_reference_vendored_unet(fixture, version, cfg):
+    """tests/golden/unet_tiny_*.pt were produced by the reference's vendored UNet2DConditionModel + its own
+    FeatureStore (tools/make_golden.py); the oracle must reproduce every map (fixtures are fp16-rounded)."""
+    gold = torch.load(os.path.join(GOLD, fixture), weights_only=False)
+    sd = _models().synthetic_state_dict(version, "cpu", cfg, TINY_VAE)
+    unet, _ = build_oracle(cfg, TINY_VAE, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers(unet, store)
+    kw = {}
+    if gold["pooled"] is not None:
+        kw = dict(text_embeds=gold["pooled"], time_ids=O.add_time_ids(8 * gold["x"].shape[-1]))
+    with torch.no_grad():
+        out = unet(gold["x"], gold["timestep"], gold["ctx"], **kw)
+    assert list(store.feats.keys()) == gold["ids"]
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        got = store.feats[k]
+        assert got.shape == ref.shape, k
+        tol = 2e-3 * max(1.0, ref.abs().max().item())      # fp16 rounding of the stored fixture
+        assert (got - ref).abs().max().item() <= tol, k
+
+
+def test_oracle_correspondence_matches_reference():
+    gold = torch.load(os.path.join(GOLD, "correspondence.pt"), weights_only=False)
+    pts = gold["points"].numpy()
+    p2, _ = O.find_nn_source_correspondences(gold["f1"], gold["f2"], pts, tuple(gold["load_size"]))
+    assert torch.equal(p2, gold["points2"])
+    assert np.array_equal(O.points_to_idxs(pts, tuple(gold["load_size"])), gold["idx"].numpy())
+
+
+def test_oracle_whole_path_digest():
+    gold = torch.load(os.path.join(GOLD, "extract_tiny_xl.pt"), weights_only=False)
+    sd = _models().synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    unet, vae = build_oracle(TINY_XL, TINY_VAE, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers(unet, store)
+    image, ctx, pooled, ev, eq = make_inputs(1, 64, TINY_XL["ctx_dim"], 64)
+    feats, latents, npred = O.extract("xl", unet, vae, store, image, ctx, pooled, ev, eq, t=50, img_size=64)
+    assert (latents - gold["latents"]).abs().max().item() < 1e-4
+    assert (npred - gold["noise_pred"]).abs().max().item() < 1e-3
+    for k, (m, s, mx) in gold["stats"].items():
+        assert abs(float(feats[k].std()) - s) <= 1e-3 * max(1.0, s), k
+    for k, v in gold["feats_subset"].items():
+        assert (feats[k] - v.float()).abs().max().item() <= 2e-3 * max(1.0, v.float().abs().max().item()), k
+
+
+# ------------------------------------------------------------------------------------------ host logic
+def test_id_grammar_matches_reference_configs():
+    """The planner's id list == the non-map keys of feature/configs/config_{xl,15}_full.json, same order."""
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    ref = json.load(open(os.path.join(GOLD, "reference_ids.json")))
+    m = _models()
+    assert _unet_feature_ids(m.UNET_CONFIGS["xl"]) == ref["ids_xl"] and len(ref["ids_xl"]) == 472
+    assert _unet_feature_ids(m.UNET_CONFIGS["1-5"]) == ref["ids_1-5"] and len(ref["ids_1-5"]) == 165
+    # every practical / legacy config id is a legal id of its architecture
+    for f, ver in (("config_xl_practical.json", "xl"), ("config_xl_legacy.json", "xl"),
+                   ("config_15_practical.json", "1-5"), ("config_15_legacy.json", "1-5")):
+        legal = set(_unet_feature_ids(m.UNET_CONFIGS[ver]))
+        assert set(ref[f].keys()) <= legal, f
+
+
+def _channels_of(fid, cfg):
+    """Channel count of a feature id from the architecture alone (res/vit -> level width, ffn-inner -> 4x)."""
+    bo = cfg["block_out"]
+    n = len(bo)
+    if fid.startswith("mid"):
+        c = bo[-1]
+    elif fid.startswith("down"):
+        c = bo[int(re.match(r"down-level(\d)", fid).group(1))]
+    elif fid.startswith("up"):
+        c = bo[n - 1 - int(re.match(r"up-level(\d)", fid).group(1))]
+    else:
+        c = 4 if fid in ("unet-in", "unet-out") else bo[0]
+    return 4 * c if "ffn-inner" in fid else c
+
+
+def test_feature_len_of_reference_task_configs():
+    """correspondence/correspondence/config_*.json:feature_len == channel sum of the layer config they name."""
+    ref = json.load(open(os.path.join(GOLD, "reference_ids.json")))
+    m = _models()
+    for corr, layer, ver in (("corr_config_sdxl.json", "config_xl_practical.json", "xl"),
+                             ("corr_config_legacy_sdxl.json", "config_xl_legacy.json", "xl"),
+                             ("corr_config_sd15.json", "config_15_practical.json", "1-5"),
+                             ("corr_config_legacy_sd15.json", "config_15_legacy.json", "1-5")):
+        total = sum(_channels_of(k, m.UNET_CONFIGS[ver]) for k, v in ref[layer].items() if v)
+        assert total == ref[corr]["feature_len"], (corr, total)
+
+
+@pytest.mark.parametrize("version", ["xl", "2-1", "1-5"])
+def test_param_specs_match_oracle_modules(version):
+    """Parameter names / shapes of the packer == state_dict of the oracle modules (diffusers naming)."""
+    m = _models()
+    with torch.device("meta"):
+        unet = O.UNet2DConditionModel(O.UNET_CONFIGS[version])
+        vcfg = m.VAE_CONFIGS[version]
+        vae = O.Vae(vcfg["scaling_factor"], block_out=vcfg["block_out"], layers=vcfg["layers"], latent=vcfg["latent"],
+                    eps=vcfg["eps"])
+    want = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    got = dict(m.unet_param_specs(m.UNET_CONFIGS[version]))
+    assert got == want
+    wantv = {k: tuple(v.shape) for k, v in vae.state_dict().items()}
+    assert dict(m.vae_param_specs(vcfg)) == wantv
+    if version == "xl":
+        n = sum(int(np.prod(s)) for s in got.values())
+        assert 2.55e9 < n < 2.60e9           # SDXL UNet, 2.57 B parameters
+
+
+def test_synthetic_weights_are_deterministic_by_name():
+    m = _models()
+    a = m.init_param("unet.conv_in.weight", (320, 4, 3, 3))
+    b = m.init_param("unet.conv_in.weight", (320, 4, 3, 3))
+    c = m.init_param("unet.conv_out.weight", (4, 320, 3, 3))
+    assert torch.equal(a, b) and a.shape != c.shape
+    assert abs(float(m.init_param("x.norm1.weight", (4096,)).mean()) - 1.0) < 0.01
+
+
+@pytest.mark.parametrize("version,t,want_ts", [("xl", 50, 50.0), ("2-1", 50, 49.0), ("1-5", 50, 51.0),
+                                               ("xl", 250, 250.0), ("1-5", 1, 2.0)])
+def test_scheduler_resolution(version, t, want_ts):
+    from generic_diffusion_feature_b200 import schedulers
+    ts, a, b, s = schedulers.resolve(version, t)
+    ots, oa, ob, os_ = O.resolve_timestep(version, t)
+    assert ts == want_ts == ots
+    assert abs(a - oa) < 1e-6 and abs(b - ob) < 1e-5 and abs(s - os_) < 1e-6
+    # both forms are the same q_sample: (a*z + b*eps)*s = sqrt(abar) z + sqrt(1-abar) eps
+    abar = float(O.alphas_cumprod()[int(ts)])
+    assert abs(a * s - abar ** 0.5) < 1e-5 and abs(b * s - (1 - abar) ** 0.5) < 1e-5
+
+
+def test_error_behaviour_mirrors_reference():
+    m = _models()
+    with pytest.raises(NotImplementedError):
+        m.get_diffusion_model("xl", "bfloat16")          # models.py:15-16
+    with pytest.raises(NotImplementedError):
+        m.get_diffusion_model("sd-3", "float16")         # models.py:173-174
+    from generic_diffusion_feature_b200.components.feature_extractor import FeatureStore, prepare_feature_extractor
+    fs = prepare_feature_extractor("xl", None, {"a": True, "b": False}, 1, False)
+    assert isinstance(fs, FeatureStore) and not fs.accept_all and fs.to_store == {"a": True, "b": False}
+    assert prepare_feature_extractor("xl", None, None, 1, False).accept_all      # feature_extractor.py:10-15
+    first = fs.stored_feats
+    fs.reset()
+    assert fs.stored_feats is not first                  # reset() rebinds (feature_extractor.py:28-29)
+
+
+def test_no_cpu_fallback():
+    """The product path refuses to run without a CUDA device instead of falling back."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from generic_diffusion_feature_b200._lib import GdfError
+    m = _models()
+    with pytest.raises(GdfError):
+        m.B200Pipe("xl", m.UNET_CONFIGS["xl"], m.VAE_CONFIGS["xl"], "cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "generic_diffusion_feature_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                imports = [l for l in src.splitlines() if re.match(r"\s*(from|import)\s", l)]
+                assert not any("oracle" in l for l in imports), "%s imports the oracle" % f
+
+
+# ------------------------------------------------------------------------------------------ C ABI surface
+def test_abi_exports_every_declared_symbol():
+    from generic_diffusion_feature_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from generic_diffusion_feature_b200 import build
+        build.build(verbose=False)
+    header = open(os.path.join(ROOT, "include", "gdf.h")).read()
+    declared = sorted(set(re.findall(r"\b(gdf_[a-z0-9_]+)\s*\(", header)))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, "declared in gdf.h but not exported: %s" % missing
+    assert sorted(_lib.EXPORTS) == declared, "python binding list out of sync with gdf.h"
+    lib.gdf_abi_version.restype = ctypes.c_int
+    assert lib.gdf_abi_version() == 1
+    # error plumbing without touching the GPU: null handle -> negative code + message
+    lib.gdf_last_error.restype = ctypes.c_char_p
+    assert lib.gdf_plan(None, None, 0, 1, 1024, None, None) < 0
+    assert b"null handle" in lib.gdf_last_error()
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the C structs have the sizes the C compiler produces (checked with a tiny gcc probe)."""
+    import subprocess
+    import tempfile
+    from generic_diffusion_feature_b200 import _lib
+    src = ('#include <stdio.h>\n#include "gdf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(gdf_epilogue),'
+           'sizeof(gdf_capture_seg), sizeof(gdf_unet_arch), sizeof(gdf_vae_arch), sizeof(gdf_slot),'
+           'sizeof(gdf_resize_src));return 0;}')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o",
+                               os.path.join(d, "p")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
+    got = [ctypes.sizeof(c) for c in (_lib.Epilogue, _lib.CaptureSeg, _lib.UNetArch, _lib.VaeArch, _lib.Slot,
+                                      _lib.ResizeSrc)]
+    assert got == sizes
+
+
+# ------------------------------------------------------------------------------------------ sharding (gloo, 2 ranks)
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from generic_diffusion_feature_b200 import parallel
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n_pairs = 7
+    s, e = parallel.shard_range(n_pairs, rank, world)
+    local = torch.arange(s, e, dtype=torch.int64)[:, None] * torch.ones(1, 3, dtype=torch.int64)
+    counts = [parallel.shard_range(n_pairs, r, world)[1] - parallel.shard_range(n_pairs, r, world)[0]
+              for r in range(world)]
+    allr = parallel.gather_to_rank0(local, counts)
+    mx = parallel.max_over_ranks(10.0 + rank)
+    if rank == 0:
+        q.put((allr[:, 0].tolist(), mx))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    import torch.multiprocessing as mp
+    from generic_diffusion_feature_b200 import parallel
+    assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rows, mx = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert rows == list(range(7)) and mx == 11.0

@@ -85,3 +85,33 @@ def test_unknown_id_and_unbuilt_features(cuda_dev):
         models.get_diffusion_model("xl", "bfloat16")      # models.py:15-16
     with pytest.raises(NotImplementedError):
         models.get_diffusion_model("no-such-version", "float16")
+
+
+@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21)])
+def test_cuda_matches_reference_vendored_unet_golden(cuda_dev, fixture, version, cfg):
+    """CUDA path vs the fixture produced by the REFERENCE's vendored UNet2DConditionModel + FeatureStore
+    (tools/make_golden.py): latents are fed through the 4-channel branch of prepare_latents with zero noise."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", fixture), weights_only=False)
+    sd = models.synthetic_state_dict(version, "cpu", cfg, TINY_VAE)
+    pipe = models.get_diffusion_model(version, "float16", device="cuda:0", state_dict=sd, unet_cfg=cfg,
+                                      vae_cfg=TINY_VAE)
+    img = 8 * gold["x"].shape[-1]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, version, "cuda:0", img_size=img, external_model=pipe)
+    t_use = 51 if version == "2-1" else 50          # the 2-1 Euler list is [999..0]: t=51 resolves to timestep 50
+    ts, a, b, s = schedulers.resolve(version, t_use)
+    assert ts == gold["timestep"]
+    lat = gold["x"] / (a * s)                         # model input = (a*lat + b*0) * s = x
+    zero = torch.zeros_like(gold["x"])
+    got = fe.extract((gold["ctx"], gold["ctx"], gold["pooled"], gold["pooled"]), 1, lat.cuda(), image_type="tensors",
+                     t=t_use, noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"]
+    rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]

@@ -116,8 +116,29 @@ def golden_extract():
     print("extract_tiny_xl.pt: %d maps (oracle)" % len(ids))
 
 
+def golden_ids():
+    """Id sets and channel sums straight from the reference's own JSON artefacts."""
+    import json
+    ref = ref_shim.REF
+    out = {}
+    for key, f in (("xl", "config_xl_full.json"), ("1-5", "config_15_full.json")):
+        cfg = json.load(open(os.path.join(ref, "feature", "configs", f)))
+        out["ids_" + key] = [k for k in cfg if "map" not in k]
+        out["map_ids_" + key] = [k for k in cfg if "map" in k]
+    for f in ("config_xl_practical.json", "config_xl_legacy.json", "config_15_practical.json",
+              "config_15_legacy.json"):
+        out[f] = json.load(open(os.path.join(ref, "feature", "configs", f)))
+    for f in ("config_sdxl.json", "config_sd15.json", "config_legacy_sdxl.json", "config_legacy_sd15.json"):
+        c = json.load(open(os.path.join(ref, "correspondence", "correspondence", f)))
+        out["corr_" + f] = {"layer": c["layer"], "version": c["version"], "feature_len": c["feature_len"],
+                            "img_size": c["img_size"], "t": c["t"]}
+    json.dump(out, open(os.path.join(OUT, "reference_ids.json"), "w"), indent=0)
+    print("reference_ids.json: %d xl ids, %d 1-5 ids" % (len(out["ids_xl"]), len(out["ids_1-5"])))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    golden_ids()
     golden_unet("xl", TINY_XL, "unet_tiny_xl.pt")
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
     golden_correspondence()
