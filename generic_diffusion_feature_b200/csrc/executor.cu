@@ -12,6 +12,7 @@
 //   components/feature_extractor.py:31-76,92-288 (store + id grammar)                -> capture slots
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -409,40 +410,71 @@ class Builder {
   }
 
   // ---- op emission --------------------------------------------------------------------------
+  // capture destinations live in the caller's arena, whose base is only known at run time: the plan records
+  // offsets, the Epilogue carries placeholder pointers, and the launch closure patches pointers + TMA maps
+  static void apply_caps(Epilogue& e, const Caps& caps, int n_out) {
+    __half* const placeholder = reinterpret_cast<__half*>(uintptr_t(256));
+    e.defer_capture_maps = true;
+    if (caps.pre >= 0) {
+      e.cap_pre = placeholder;
+      e.ld_cap_pre = n_out;
+    }
+    e.num_cap = caps.n;
+    for (int i = 0; i < caps.n; ++i) {
+      e.cap[i].ptr = caps.post[i] >= 0 ? placeholder : nullptr;
+      e.cap[i].col_begin = caps.c0[i];
+      e.cap[i].col_end = caps.c1[i];
+      e.cap[i].ld = caps.c1[i] - caps.c0[i];
+    }
+  }
   void push_gemm(GemmLaunch& g, const Caps& caps) {
     GemmParams& p = g.p;
-    p.num_cap = caps.n;
-    for (int i = 0; i < caps.n; ++i) {
-      p.cap[i].ptr = nullptr;
-      p.cap[i].col_begin = caps.c0[i];
-      p.cap[i].col_end = caps.c1[i];
-      p.cap[i].ld = caps.c1[i] - caps.c0[i];
-    }
-    p.cap_pre = nullptr;
-    p.ld_cap_pre = p.n_out;
-    const GemmLaunch gl = g;
-    const Caps c = caps;
     {
       char lbl[160];
-      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d batch=%d act=%d res=%d caps=%d pre=%d tiles=%d",
-               p.a_mode, p.M, p.N, p.K, p.block_n, p.batch, p.act, p.residual ? 1 : 0, caps.n, caps.pre >= 0 ? 1 : 0,
-               p.batch * p.num_m_tiles * p.num_n_tiles);
+      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d st=%d batch=%d act=%d res=%d caps=%d pre=%d tma=%d tiles=%d",
+               p.a_mode, p.M, p.N, p.K, p.block_n, p.num_stages, p.batch, p.act, p.residual ? 1 : 0, caps.n,
+               caps.pre >= 0 ? 1 : 0, p.tma_store, p.batch * p.num_m_tiles * p.num_n_tiles);
       ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
                               (double)p.batch, lbl);
     }
-    ops->push_back([gl, c](const RunCtx& rc) -> int {
-      GemmParams p = gl.p;
-      if (c.pre >= 0) p.cap_pre = reinterpret_cast<__half*>(rc.arena + c.pre);
-      for (int i = 0; i < c.n; ++i)
-        if (c.post[i] >= 0) p.cap[i].ptr = reinterpret_cast<__half*>(rc.arena + c.post[i]);
-      OP_CUDA(launch_gemm(gl.map_a, gl.map_b, p, rc.stream));
+    struct Cached {   // capture maps for the two most recent arena bases (callers alternate between arenas)
+      char* base[2] = {nullptr, nullptr};
+      GemmLaunch g[2];
+      int next = 0;
+    };
+    auto cache = std::make_shared<Cached>();
+    const GemmLaunch gl = g;
+    const Caps c = caps;
+    const bool has_caps = (c.pre >= 0) || (c.n > 0);
+    ops->push_back([gl, c, cache, has_caps](const RunCtx& rc) -> int {
+      if (!has_caps) {
+        OP_CUDA(launch_gemm(gl, rc.stream));
+        return 0;
+      }
+      int slot = -1;
+      for (int i = 0; i < 2; ++i)
+        if (cache->base[i] == rc.arena) slot = i;
+      if (slot < 0) {
+        slot = cache->next;
+        cache->next ^= 1;
+        GemmLaunch& t = cache->g[slot];
+        t = gl;
+        t.p.cap_pre = c.pre >= 0 ? reinterpret_cast<__half*>(rc.arena + c.pre) : nullptr;
+        for (int i = 0; i < c.n; ++i)
+          t.p.cap[i].ptr = c.post[i] >= 0 ? reinterpret_cast<__half*>(rc.arena + c.post[i]) : nullptr;
+        GDF_TRY(build_capture_maps(&t));
+        cache->base[slot] = rc.arena;
+      }
+      OP_CUDA(launch_gemm(cache->g[slot], rc.stream));
       return 0;
     });
   }
-  void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e,
+  void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e0,
               const Caps& caps = Caps(), int batch = 1, long long abs = 0, long long wbs = 0, int ldw = 0,
               int block_n = 0) {
     if (dry || err) return;
+    Epilogue e = e0;
+    apply_caps(e, caps, e.n_out > 0 ? e.n_out : (e.act == kActGeglu ? N / 2 : N));
     GemmLaunch g;
     if (int r = build_linear(&g, A, M, K, lda, W, N, ldw ? ldw : K, e, batch, abs, wbs, block_n)) {
       set_err(r);
@@ -451,8 +483,10 @@ class Builder {
     push_gemm(g, caps);
   }
   void conv3(const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int Npad, int stride, int pad_lo,
-             const Epilogue& e, const Caps& caps = Caps()) {
+             const Epilogue& e0, const Caps& caps = Caps()) {
     if (dry || err) return;
+    Epilogue e = e0;
+    apply_caps(e, caps, e.n_out > 0 ? e.n_out : Npad);
     GemmLaunch g;
     if (int r = build_conv3x3(&g, X, B, Hin, Win, Cin, Wp, Npad, stride, pad_lo, e)) {
       set_err(r);

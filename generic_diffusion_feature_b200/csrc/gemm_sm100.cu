@@ -1,10 +1,11 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution kernel (see gemm_sm100.cuh).
 //
 // Roles (256 threads, 1 CTA per SM, TMEM 512 columns = 2 accumulator stages of 128 lanes x 256 fp32):
-//   warp 0  : TMA producer  (A tile 128x64 bf16, B tile block_n x 64 bf16, 128B swizzle, 4-stage ring)
+//   warp 0  : TMA producer  (A tile 128x64 bf16, B tile block_n x 64 bf16, 128B swizzle, num_stages-deep ring)
 //   warp 1  : MMA issuer    (one elected lane issues tcgen05.mma 128 x block_n x 16, commits to mbarriers)
 //   warp 2  : TMEM allocator / deallocator
-//   warps 4-7: epilogue     (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global)
+//   warps 4-7: epilogue     (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue ->
+//                            swizzled smem staging -> TMA bulk stores; direct 128-bit stores as fallback)
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static persistent tile loop.
 #include "gemm_sm100.cuh"
 #include "host_util.h"
@@ -42,36 +43,58 @@ __device__ __forceinline__ void store16_f16(__half* dst, const float* v) {
   reinterpret_cast<uint4*>(dst)[1] = b;
 }
 
-// Fused epilogue over one chunk of 32 output columns of one row.
-//   v[]    : activated accumulator values (alpha, biases and activation already applied)
-//   ocol0  : first output column of the chunk, ncols_out: output width
-__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, float (&v)[32], long long row, int bidx,
-                                                     int ocol0, int ncols_total, int ncols_out,
-                                                     long long out_batch_off) {
-  // ncols_total: full output width (indexing of per-sample vectors); ncols_out: exclusive column limit of this chunk
-  const bool full = (ocol0 + 32 <= ncols_out);
-  // ---- capture before residual ("increment")
-  if (p.cap_pre) {
-    __half* dst = p.cap_pre + row * p.ld_cap_pre + ocol0;
-    if (full && (p.ld_cap_pre % 8 == 0)) {
-      store16_f16(dst, v);
-      store16_f16(dst + 16, v + 16);
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (ocol0 + j < ncols_out) dst[j] = __float2half_rn(v[j]);
-    }
+// ---------------------------------------------------------------------------------- shared epilogue math
+// Loads 32 accumulator columns starting at TMEM column `c` of this tile and applies alpha, biases, activation.
+__device__ __forceinline__ void load_activate32(const GemmParams& p, uint32_t taddr, int c, int out_tile_w,
+                                                int n_tile, float bm, bool row_ok, int bidx, float* v) {
+  uint32_t raw[32];
+  tmem_ld_32x32(taddr + c, raw);
+  tmem_ld_wait();
+  const int acol0 = n_tile * p.block_n + c;  // accumulator column (bias index)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(raw[j]) * p.alpha + bm;
+    if (p.bias && acol0 + j < p.N) x += __ldg(p.bias + acol0 + j);
+    v[j] = x;
   }
-  // ---- per-sample column gate
-  if (p.col_scale) {
+  if (p.row_batch_bias && row_ok) {
+    const float* rb = p.row_batch_bias + (long long)bidx * p.N + acol0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (acol0 + j < p.N) v[j] += __ldg(rb + j);
+  }
+  if (p.act == kActGeglu) {
+    uint32_t graw[32];
+    tmem_ld_32x32(taddr + out_tile_w + c, graw);
+    tmem_ld_wait();
+    const int gcol0 = acol0 + out_tile_w;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float g = __uint_as_float(graw[j]) * p.alpha;
+      if (p.bias && gcol0 + j < p.N) g += __ldg(p.bias + gcol0 + j);
+      v[j] *= gelu_erf_f(g);
+    }
+  } else if (p.act == kActGeluTanh) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if (p.act == kActSilu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  }
+}
+
+// column gate + residual + output scale on 32 columns of one row (direct global reads of the residual)
+__device__ __forceinline__ void gate_residual32(const GemmParams& p, float* v, long long row, int bidx, int ocol0,
+                                                int ncols_total, int lim, bool row_ok) {
+  if (p.col_scale && row_ok) {
     const float* g = p.col_scale + (long long)bidx * ncols_total + ocol0;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (ocol0 + j < ncols_out) v[j] *= __ldg(g + j);
+      if (ocol0 + j < lim) v[j] *= __ldg(g + j);
   }
-  // ---- residual
-  if (p.residual) {
+  if (p.residual && row_ok) {
     const __nv_bfloat16* r = p.residual + row * p.ld_res + ocol0;
-    if (full && (p.ld_res % 8 == 0)) {
+    if (ocol0 + 32 <= lim && (p.ld_res % 8 == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + q);
@@ -83,80 +106,132 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, float 
       }
     } else {
       for (int j = 0; j < 32; ++j)
-        if (ocol0 + j < ncols_out) v[j] += __bfloat162float(r[j]);
+        if (ocol0 + j < lim) v[j] += __bfloat162float(r[j]);
     }
   }
   if (p.out_scale != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
   }
-  // ---- destinations
-  if (p.out) {
+}
+
+// Direct (non-TMA) stores of one 32-column chunk of one row to every destination.
+__device__ __forceinline__ void direct_store32(const GemmParams& p, const float* vpre, const float* v, long long row,
+                                               int ocol0, int lim, long long out_batch_off, bool skip16) {
+  const bool full = (ocol0 + 32 <= lim);
+  if (p.cap_pre && !skip16) {
+    __half* dst = p.cap_pre + row * p.ld_cap_pre + ocol0;
+    if (full && (p.ld_cap_pre % 8 == 0)) {
+      store16_f16(dst, vpre);
+      store16_f16(dst + 16, vpre + 16);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (ocol0 + j < lim) dst[j] = __float2half_rn(vpre[j]);
+    }
+  }
+  if (p.out && !skip16) {
     __nv_bfloat16* dst = p.out + out_batch_off + row * p.ld_out + ocol0;
     if (full && (p.ld_out % 8 == 0)) {
       store16_bf16(dst, v);
       store16_bf16(dst + 16, v + 16);
     } else {
       for (int j = 0; j < 32; ++j)
-        if (ocol0 + j < ncols_out) dst[j] = __float2bfloat16_rn(v[j]);
+        if (ocol0 + j < lim) dst[j] = __float2bfloat16_rn(v[j]);
     }
   }
-  if (p.out2) {
+  if (p.out2 && !skip16) {
     __nv_bfloat16* dst = p.out2 + row * p.ld_out2 + ocol0;
     if (full && (p.ld_out2 % 8 == 0)) {
       store16_bf16(dst, v);
       store16_bf16(dst + 16, v + 16);
     } else {
       for (int j = 0; j < 32; ++j)
-        if (ocol0 + j < ncols_out) dst[j] = __float2bfloat16_rn(v[j]);
+        if (ocol0 + j < lim) dst[j] = __float2bfloat16_rn(v[j]);
     }
   }
   if (p.out_f32) {
     float* dst = p.out_f32 + row * p.ld_out_f32 + ocol0;
     for (int j = 0; j < 32; ++j)
-      if (ocol0 + j < ncols_out) dst[j] = v[j];
+      if (ocol0 + j < lim) dst[j] = v[j];
   }
+  if (!skip16) {
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    if (s < p.num_cap) {
-      const CaptureSeg& cs = p.cap[s];
-      if (cs.ptr && ocol0 >= cs.col_begin && ocol0 < cs.col_end) {
-        __half* dst = cs.ptr + row * cs.ld + (ocol0 - cs.col_begin);
-        if (ocol0 + 32 <= cs.col_end && (cs.ld % 8 == 0)) {
-          store16_f16(dst, v);
-          store16_f16(dst + 16, v + 16);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (ocol0 + j < cs.col_end) dst[j] = __float2half_rn(v[j]);
+    for (int s = 0; s < 3; ++s) {
+      if (s < p.num_cap) {
+        const CaptureSeg& cs = p.cap[s];
+        if (cs.ptr && ocol0 >= cs.col_begin && ocol0 < cs.col_end) {
+          __half* dst = cs.ptr + row * cs.ld + (ocol0 - cs.col_begin);
+          if (ocol0 + 32 <= cs.col_end && (cs.ld % 8 == 0)) {
+            store16_f16(dst, v);
+            store16_f16(dst + 16, v + 16);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (ocol0 + j < cs.col_end) dst[j] = __float2half_rn(v[j]);
+          }
         }
       }
     }
   }
 }
 
+// ---------------------------------------------------------------------------------- TMA-store staging
+struct StoreCoord {   // origin of this warp's 32-row slice in the destination tensor
+  int c1, c2, c3;     // linear: (row0, batch, -) ; conv: (x, y, b)
+  bool conv;
+};
+// One warp stages its 32 rows x 64 columns (16-bit) into a swizzled [32][128 B] buffer and issues a TMA store.
+template <bool kF16>
+__device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t* stg_warp, int& toggle, int lane,
+                                                const float* v /*64*/, int col, const StoreCoord& sc) {
+  uint8_t* buf = stg_warp + toggle * 4096;
+  if (lane == 0) bulk_wait_read<1>();   // the store that used this buffer two stores ago has drained
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 u;
+    if (kF16) {
+      u.x = pack_f16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_f16x2(v[c * 8 + 2], v[c * 8 + 3]);
+      u.z = pack_f16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_f16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    } else {
+      u.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+      u.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    }
+    *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = u;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (sc.conv) tma_store_4d(map, buf, col, sc.c1, sc.c2, sc.c3);
+    else tma_store_3d(map, buf, col, sc.c1, sc.c2);
+    bulk_commit();
+  }
+  toggle ^= 1;
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kStageBytesA + kStageBytesB));
-  uint64_t* full_bar = bars;                       // [kStages]
-  uint64_t* empty_bar = bars + kStages;            // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;        // [kAccStages]
-  uint64_t* tempty_bar = bars + 2 * kStages + kAccStages;  // [kAccStages]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+  const int stage_bytes = kStageBytesA + p.block_n * kBlockK * 2;
+  uint8_t* stg = smem + kPipeBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes + kStagingBytes);
+  uint64_t* full_bar = bars;                                 // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;                   // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kAccStages]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + kAccStages; // [kAccStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int nstages = p.num_stages;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    if (p.tma_store && p.out) tma_prefetch_desc(&maps.out);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -198,30 +273,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[s], stage_tx_bytes);
-          uint8_t* a_dst = sA + s * kStageBytesA;
-          uint8_t* b_dst = sB + s * kStageBytesB;
+          uint8_t* a_dst = smem + s * stage_bytes;
+          uint8_t* b_dst = a_dst + kStageBytesA;
           if (p.a_mode == kALinear) {
-            tma_load_3d(a_dst, &map_a, &full_bar[s], kb * kBlockK, tc.m_tile * kBlockM, p.a_batched ? tc.bz : 0);
+            tma_load_3d(a_dst, &maps.a, &full_bar[s], kb * kBlockK, tc.m_tile * kBlockM, p.a_batched ? tc.bz : 0);
           } else {
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;
             const int ky = tap / 3, kx = tap - 3 * ky;
             if (p.a_mode == kAConvS1) {
-              tma_load_4d(a_dst, &map_a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+              tma_load_4d(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
             } else {
               // stride-2: input viewed as (B, H, 2, W, 2*Cin) with H, W the OUTPUT extents;
               // input row 2*oy + ky - pad_lo -> parity (t & 1), half-row oy + (t >> 1)
               const int ty = ky - p.pad_lo, tx = kx - p.pad_lo;
               const int ypar = ty & 1, yoff = ty >> 1;
               const int xpar = tx & 1, xoff = tx >> 1;
-              tma_load_5d(a_dst, &map_a, &full_bar[s], xpar * p.cin_blocks * kBlockK + cb * kBlockK, x0 + xoff, ypar,
+              tma_load_5d(a_dst, &maps.a, &full_bar[s], xpar * p.cin_blocks * kBlockK + cb * kBlockK, x0 + xoff, ypar,
                           y0 + yoff, b0);
             }
           }
-          tma_load_3d(b_dst, &map_b, &full_bar[s], kb * kBlockK, tc.n_tile * p.block_n, p.b_batched ? tc.bz : 0);
+          tma_load_3d(b_dst, &maps.b, &full_bar[s], kb * kBlockK, tc.n_tile * p.block_n, p.b_batched ? tc.bz : 0);
         }
         __syncwarp();
-        if (++s == kStages) { s = 0; ph ^= 1; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -239,8 +314,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * kStageBytesA));
-          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * kStageBytesB));
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t da = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -250,7 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
-        if (++s == kStages) { s = 0; ph ^= 1; }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
@@ -263,14 +339,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool geglu = (p.act == kActGeglu);
     const int ncols_out = p.n_out;
     const int out_tile_w = geglu ? p.block_n / 2 : p.block_n;
+    uint8_t* stg_warp = stg + ew * 8192;
+    int toggle = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
-      // ---- row of this thread
+      // ---- row of this thread, origin of this warp's 32-row slice
       long long row;
       bool row_ok;
+      StoreCoord sc;
       if (p.a_mode == kALinear) {
         row = (long long)tc.m_tile * kBlockM + r_in_tile;
         row_ok = row < p.M;
+        sc.conv = false;
+        sc.c1 = tc.m_tile * kBlockM + ew * 32;
+        sc.c2 = tc.bz;
+        sc.c3 = 0;
       } else {
         const int xt = tc.m_tile % p.tiles_x;
         const int r = tc.m_tile / p.tiles_x;
@@ -283,6 +366,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int b = bt * p.tb + tbi;
         row = ((long long)b * p.H + (yt * p.th + ty)) * p.W + (xt * p.tw + tx);
         row_ok = b < p.B_img;
+        const int w0 = ew * 32;   // first row of the warp slice, decomposed the same way
+        sc.conv = true;
+        sc.c1 = xt * p.tw + (w0 % p.tw);
+        sc.c2 = yt * p.th + ((w0 / p.tw) % p.th);
+        sc.c3 = bt * p.tb + (w0 / p.tw) / p.th;
       }
       const int bidx = (p.rows_per_batch > 0) ? (int)(row / p.rows_per_batch) : 0;
       const long long out_batch_off = (long long)tc.bz * p.out_batch_stride;
@@ -292,53 +380,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kMaxBlockN;
 
-      for (int c = 0; c < out_tile_w; c += 32) {
-        uint32_t raw[32];
-        float v[32];
-        tmem_ld_32x32(taddr + c, raw);
-        tmem_ld_wait();
-        const int acol0 = tc.n_tile * p.block_n + c;       // accumulator column (bias index)
-        const int ocol0 = tc.n_tile * out_tile_w + c;      // output column
+      int c = 0;
+      if (p.tma_store) {
+        // ---- 64-column groups: registers -> swizzled smem -> TMA bulk store, one store per destination
+        for (; c + 64 <= out_tile_w; c += 64) {
+          const int ocol0 = tc.n_tile * out_tile_w + c;
+          if (ocol0 >= ncols_out) break;
+          float v[64];
+          load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
+          load_activate32(p, taddr, c + 32, out_tile_w, tc.n_tile, bm, row_ok, bidx, v + 32);
+          if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
+          gate_residual32(p, v, row, bidx, ocol0, ncols_out, ncols_out, row_ok);
+          gate_residual32(p, v + 32, row, bidx, ocol0 + 32, ncols_out, ncols_out, row_ok);
+          if (p.out) stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
+          if (p.out2) stage_and_store<false>(&maps.out2, stg_warp, toggle, lane, v, ocol0, sc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]) * p.alpha + bm;
-          if (p.bias && acol0 + j < p.N) x += __ldg(p.bias + acol0 + j);
-          v[j] = x;
-        }
-        if (p.row_batch_bias && row_ok) {
-          const float* rb = p.row_batch_bias + (long long)bidx * p.N + acol0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (acol0 + j < p.N) v[j] += __ldg(rb + j);
-        }
-        if (geglu) {
-          uint32_t graw[32];
-          tmem_ld_32x32(taddr + out_tile_w + c, graw);
-          tmem_ld_wait();
-          const int gcol0 = acol0 + out_tile_w;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float g = __uint_as_float(graw[j]) * p.alpha;
-            if (p.bias && gcol0 + j < p.N) g += __ldg(p.bias + gcol0 + j);
-            v[j] *= gelu_erf_f(g);
+          for (int s = 0; s < 3; ++s) {
+            if (s < p.num_cap && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end)
+              stage_and_store<true>(&maps.cap[s], stg_warp, toggle, lane, v, ocol0 - p.cap[s].col_begin, sc);
           }
-        } else if (p.act == kActGeluTanh) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-        } else if (p.act == kActSilu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          if (p.out_f32 && row_ok) {
+            direct_store32(p, v, v, row, ocol0, min(ncols_out, ocol0 + 32), out_batch_off, true);
+            direct_store32(p, v + 32, v + 32, row, ocol0 + 32, min(ncols_out, ocol0 + 64), out_batch_off, true);
+          }
         }
-        if (row_ok && ocol0 < ncols_out) {
-          const int lim = min(ncols_out, ocol0 + min(32, out_tile_w - c));
-          epilogue_store_chunk(p, v, row, bidx, ocol0, ncols_out, lim, out_batch_off);
+      }
+      // ---- remaining 32-column chunks (whole tile when TMA stores are off): direct 128-bit stores
+      for (; c < out_tile_w; c += 32) {
+        const int ocol0 = tc.n_tile * out_tile_w + c;
+        float v[32], vpre[32];
+        load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
+        if (p.cap_pre) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vpre[j] = v[j];
         }
+        const int lim = min(ncols_out, ocol0 + min(32, out_tile_w - c));
+        gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok && ocol0 < ncols_out);
+        if (row_ok && ocol0 < ncols_out) direct_store32(p, vpre, v, row, ocol0, lim, out_batch_off, false);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();   // all bulk stores of this warp have completed before the CTA retires
   }
 
   tc_fence_before();
@@ -352,7 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ------------------------------------------------------------------------------------------ host side
 static int g_num_sms = 0;
 
-cudaError_t launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, cudaStream_t stream) {
+cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -366,8 +451,17 @@ cudaError_t launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, cons
   const int total_tiles = p.batch * p.num_m_tiles * p.num_n_tiles;
   if (total_tiles <= 0) return cudaSuccess;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(map_a, map_b, p);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
   return cudaGetLastError();
+}
+
+int gemm_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
 }
 
 }  // namespace gdf

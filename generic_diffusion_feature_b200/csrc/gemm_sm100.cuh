@@ -13,12 +13,13 @@ namespace gdf {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one swizzle row
 constexpr int kMaxBlockN = 256;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
-constexpr int kStageBytesA = kBlockM * kBlockK * 2;
-constexpr int kStageBytesB = kMaxBlockN * kBlockK * 2;
-constexpr int kGemmSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStageBytesA = kBlockM * kBlockK * 2;          // 16 KB
+constexpr int kPipeBytes = 192 * 1024;                       // operand ring: num_stages * (16 KB + block_n * 128 B)
+constexpr int kStagingBytes = 4 * 2 * 4096;                  // epilogue: per warp 2 x [32 rows][128 B] TMA-store buffers
+constexpr int kGemmSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 
 enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2 };
 enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3 };
@@ -33,6 +34,7 @@ struct GemmParams {
   int M, N, K;          // N counts accumulator columns (for GEGLU: 2x the output width)
   int n_out;            // valid output columns (<= N, or <= N/2 for GEGLU); padding columns are dropped
   int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
+  int num_stages;       // operand ring depth: kPipeBytes / (16 KB + block_n * 128 B), <= kMaxStages
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
   int a_batched;        // 1: A has a batch dimension, 0: shared across the batch
@@ -40,6 +42,7 @@ struct GemmParams {
   // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows
   int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;
   // ---- epilogue
+  int tma_store;               // 1: bf16/fp16 destinations go through smem staging + TMA bulk stores
   float alpha;                 // accumulator scale (1.0 default)
   const float* bias;           // [N] column bias (already permuted for GEGLU) or null
   const float* bias_m;         // [M] row bias (transposed products) or null
@@ -55,6 +58,11 @@ struct GemmParams {
   __half* cap_pre; int ld_cap_pre;             // fp16 capture before residual add ("increment")
   CaptureSeg cap[3];                           // fp16 captures of the final value
   int num_cap;
+};
+
+// Tensor maps of one launch: operands + the six possible 16-bit destinations (TMA-store path).
+struct GemmMaps {
+  CUtensorMap a, b, out, out2, cap_pre, cap[3];
 };
 
 }  // namespace gdf

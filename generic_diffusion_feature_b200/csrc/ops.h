@@ -10,8 +10,7 @@ typedef __nv_bfloat16 bf16;
 
 // A fully prepared GEMM launch: tensor maps + parameters. Built once at plan time, replayed per step.
 struct GemmLaunch {
-  CUtensorMap map_a;
-  CUtensorMap map_b;
+  GemmMaps maps;
   GemmParams p;
 };
 
@@ -32,9 +31,10 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   __half* cap_pre = nullptr; int ld_cap_pre = 0;
   CaptureSeg cap[3] = {};
   int num_cap = 0;
+  bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };
 
-int choose_block_n(int N, bool geglu);
+int choose_block_n(int N, bool geglu, int num_m_tiles);
 
 // C[M,N] = A[M,K] * W[N,K]^T, optionally batched (A: batch x M x K with a_batch_stride elements,
 // W shared when w_batch_stride == 0).
@@ -48,8 +48,13 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
 int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int N, int stride,
                   int pad_lo, const Epilogue& e, int block_n = 0);
 
-cudaError_t launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, cudaStream_t stream);
-inline cudaError_t launch_gemm(const GemmLaunch& g, cudaStream_t s) { return launch_gemm(g.map_a, g.map_b, g.p, s); }
+// (Re)builds the TMA-store tensor maps of the capture destinations (cap_pre, cap[0..2]) from the pointers currently
+// in g->p; the executor calls it at run time once the arena base is known. No-op when g->p.tma_store == 0.
+int build_capture_maps(GemmLaunch* g);
+
+cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream);
+inline cudaError_t launch_gemm(const GemmLaunch& g, cudaStream_t s) { return launch_gemm(g.maps, g.p, s); }
+int gemm_num_sms();
 
 // ---- normalisation (norm.cu)
 // GroupNorm(+SiLU) over NHWC bf16 x[B, HW, C] -> y[B, HW, C]; stats in fp32, workspace >= gn_workspace_floats().

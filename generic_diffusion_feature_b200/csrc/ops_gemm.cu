@@ -13,12 +13,82 @@ static int gcd_int(int a, int b) {
   return a;
 }
 
-int choose_block_n(int N, bool geglu) {
-  const int step = geglu ? 64 : 32;
-  if (N <= kMaxBlockN && !geglu) return ((N + 15) / 16) * 16;
-  for (int bn = kMaxBlockN; bn >= step; bn -= step)
-    if (N % bn == 0) return bn;
-  return geglu ? 128 : 128;
+// Tile width by a small cost model: rounds of the persistent grid x (tile width + fixed per-tile overhead),
+// counting the wasted columns of a ragged last N tile. Multiples of 64 keep the TMA-store epilogue on every column.
+int choose_block_n(int N, bool geglu, int num_m_tiles) {
+  if (!geglu && N <= 64) return ((N + 15) / 16) * 16;
+  const int sms = gemm_num_sms();
+  int best = 0;
+  double best_cost = 1e30;
+  const int cands_plain[4] = {256, 192, 128, 64};
+  const int cands_geglu[2] = {256, 128};
+  const int* cands = geglu ? cands_geglu : cands_plain;
+  const int nc = geglu ? 2 : 4;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    if (bn > ((N + 63) / 64) * 64 && bn != 64) continue;
+    const long long tiles = (long long)num_m_tiles * ((N + bn - 1) / bn);
+    const long long rounds = (tiles + sms - 1) / sms;
+    double cost = (double)rounds * (bn + 24);
+    if (bn < 128) cost *= 1.15;   // A tile re-fetched per narrow N tile: L2 traffic penalty
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best ? best : 128;
+}
+
+static int make_store_map(CUtensorMap* m, const GemmParams& p, const void* ptr, int width, int ld,
+                          long long batch_stride) {
+  if (p.a_mode == kALinear) {
+    uint64_t dims[3] = {(uint64_t)width, (uint64_t)p.M, (uint64_t)p.batch};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)(p.batch > 1 ? batch_stride : (long long)p.M * ld) * 2};
+    uint32_t box[3] = {64, 32, 1};
+    return make_tmap_bf16(m, ptr, 3, dims, str, box);
+  }
+  const int cx = p.tw < 32 ? p.tw : 32;
+  const int cy = p.th < 32 / cx ? p.th : 32 / cx;
+  const int cb = 32 / (cx * cy);
+  uint64_t dims[4] = {(uint64_t)width, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B_img};
+  uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)p.W * ld * 2, (uint64_t)p.H * p.W * ld * 2};
+  uint32_t box[4] = {64, (uint32_t)cx, (uint32_t)cy, (uint32_t)cb};
+  return make_tmap_bf16(m, ptr, 4, dims, str, box);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Decide whether the 16-bit destinations can go through TMA stores, and build the maps of out / out2.
+static int setup_stores(GemmLaunch* g) {
+  GemmParams& p = g->p;
+  const int out_tile_w = (p.act == kActGeglu) ? p.block_n / 2 : p.block_n;
+  bool ok = out_tile_w >= 64 && p.n_out >= 64;
+  if (p.out && (p.ld_out % 8 != 0 || !aligned16(p.out) || (p.batch > 1 && p.out_batch_stride % 8 != 0))) ok = false;
+  if (p.out2 && (p.ld_out2 % 8 != 0 || !aligned16(p.out2) || p.batch > 1)) ok = false;
+  if (p.cap_pre && (p.ld_cap_pre % 8 != 0 || p.batch > 1)) ok = false;
+  for (int i = 0; i < p.num_cap; ++i)
+    if (p.cap[i].ld % 8 != 0 || p.cap[i].col_begin % 64 != 0 || p.batch > 1) ok = false;
+  if (!p.out && !p.out2 && !p.cap_pre && p.num_cap == 0) ok = false;
+  p.tma_store = ok ? 1 : 0;
+  if (!ok) return GDF_OK;
+  if (p.out) GDF_TRY(make_store_map(&g->maps.out, p, p.out, p.n_out, p.ld_out, p.out_batch_stride));
+  if (p.out2) GDF_TRY(make_store_map(&g->maps.out2, p, p.out2, p.n_out, p.ld_out2, 0));
+  return GDF_OK;
+}
+
+int build_capture_maps(GemmLaunch* g) {
+  GemmParams& p = g->p;
+  if (!p.tma_store) return GDF_OK;
+  if (p.cap_pre) {
+    if (!aligned16(p.cap_pre)) return fail(GDF_ERR_INVALID, "capture destination not 16-byte aligned");
+    GDF_TRY(make_store_map(&g->maps.cap_pre, p, p.cap_pre, p.n_out, p.ld_cap_pre, 0));
+  }
+  for (int i = 0; i < p.num_cap; ++i) {
+    if (!p.cap[i].ptr) continue;
+    if (!aligned16(p.cap[i].ptr)) return fail(GDF_ERR_INVALID, "capture destination not 16-byte aligned");
+    GDF_TRY(make_store_map(&g->maps.cap[i], p, p.cap[i].ptr, p.cap[i].col_end - p.cap[i].col_begin, p.cap[i].ld, 0));
+  }
+  return GDF_OK;
 }
 
 static void fill_epilogue(GemmParams& p, const Epilogue& e) {
@@ -51,8 +121,8 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   memset(g, 0, sizeof(*g));
   GemmParams& p = g->p;
   const bool geglu = (e.act == kActGeglu);
-  if (block_n <= 0) block_n = choose_block_n(N, geglu);
-  if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 64 != 0))
+  if (block_n <= 0) block_n = choose_block_n(N, geglu, (int)((M + kBlockM - 1) / kBlockM) * batch);
+  if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 128 != 0))
     return fail(GDF_ERR_INVALID, "build_linear: bad block_n %d", block_n);
   if (K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
     return fail(GDF_ERR_SHAPE, "build_linear: K/lda/ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw);
@@ -73,16 +143,19 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a_batched ? batch : 1)};
     uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : M * (long long)lda) * 2};
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
-    GDF_TRY(make_tmap_bf16(&g->map_a, A, 3, dims, str, box));
+    GDF_TRY(make_tmap_bf16(&g->maps.a, A, 3, dims, str, box));
   }
   {
     const int wb = p.b_batched ? batch : 1;
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)wb};
     uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
-    GDF_TRY(make_tmap_bf16(&g->map_b, W, 3, dims, str, box));
+    GDF_TRY(make_tmap_bf16(&g->maps.b, W, 3, dims, str, box));
   }
-  return GDF_OK;
+  p.num_stages = kPipeBytes / (kStageBytesA + block_n * kBlockK * 2);
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  GDF_TRY(setup_stores(g));
+  return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
 
 int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int N, int stride,
@@ -93,11 +166,11 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
   if (N % 16 != 0) return fail(GDF_ERR_SHAPE, "build_conv3x3: N=%d must be a multiple of 16 (pad the weights)", N);
   if (stride != 1 && stride != 2) return fail(GDF_ERR_UNSUPPORTED, "build_conv3x3: stride %d", stride);
   if (stride == 2 && ((Hin | Win) & 1)) return fail(GDF_ERR_SHAPE, "build_conv3x3: stride 2 needs even H, W");
-  if (block_n <= 0) block_n = choose_block_n(N, false);
   const int H = Hin / stride, W = Win / stride;  // output grid
   const int tw = gcd_int(W, kBlockM);
   const int th = gcd_int(H, kBlockM / tw);
   const int tb = kBlockM / (tw * th);
+  if (block_n <= 0) block_n = choose_block_n(N, false, (W / tw) * (H / th) * ((B + tb - 1) / tb));
   p.M = B * H * W;
   p.N = N;
   p.K = 9 * Cin;
@@ -124,22 +197,25 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
-    GDF_TRY(make_tmap_bf16(&g->map_a, X, 4, dims, str, box));
+    GDF_TRY(make_tmap_bf16(&g->maps.a, X, 4, dims, str, box));
   } else {
     // (B, Hout, 2, Wout, 2*Cin): innermost merges (x parity, channel)
     uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)W, 2, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {(uint64_t)2 * Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)2 * Win * Cin * 2,
                        (uint64_t)Hin * Win * Cin * 2};
     uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)tw, 1, (uint32_t)th, (uint32_t)tb};
-    GDF_TRY(make_tmap_bf16(&g->map_a, X, 5, dims, str, box));
+    GDF_TRY(make_tmap_bf16(&g->maps.a, X, 5, dims, str, box));
   }
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)N, 1};
     uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)N * p.K * 2};
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
-    GDF_TRY(make_tmap_bf16(&g->map_b, Wp, 3, dims, str, box));
+    GDF_TRY(make_tmap_bf16(&g->maps.b, Wp, 3, dims, str, box));
   }
-  return GDF_OK;
+  p.num_stages = kPipeBytes / (kStageBytesA + block_n * kBlockK * 2);
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  GDF_TRY(setup_stores(g));
+  return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
 
 }  // namespace gdf
