@@ -179,15 +179,15 @@ struct StoreCoord {   // origin of this warp's 32-row slice in the destination t
   int c1, c2, c3;     // linear: (row0, batch, -) ; conv: (x, y, b)
   bool conv;
 };
-// One warp stages its 32 rows x 64 columns (16-bit) into a swizzled [32][128 B] buffer and issues a TMA store.
+// One warp stages its 32 rows x 32 columns (16-bit, 64 B per row, SWIZZLE_64B) and issues one TMA bulk store.
 template <bool kF16>
 __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t* stg_warp, int& toggle, int lane,
-                                                const float* v /*64*/, int col, const StoreCoord& sc) {
-  uint8_t* buf = stg_warp + toggle * 4096;
+                                                const float* v /*32*/, int col, const StoreCoord& sc) {
+  uint8_t* buf = stg_warp + toggle * 2048;
   if (lane == 0) bulk_wait_read<1>();   // the store that used this buffer two stores ago has drained
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint4 u;
     if (kF16) {
       u.x = pack_f16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_f16x2(v[c * 8 + 2], v[c * 8 + 3]);
@@ -196,7 +196,8 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
       u.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
       u.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
     }
-    *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = u;
+    // 64-byte swizzle: 16 B chunk index XOR address bits [7:9) -> (row >> 1) & 3 for 64 B rows
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = u;
   }
   fence_proxy_async_smem();
   __syncwarp();
@@ -237,7 +238,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kEpilogueWarps);
     }
     fence_barrier_init();
   }
@@ -331,15 +332,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue
-    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may access
+    // ===================================================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column sets
+    const int e = warp - 4;
+    const int ew = e & 3;     // == warp % 4: TMEM lane quadrant this warp may access
+    const int cset = e >> 2;  // this warp handles 32-column chunks with (chunk index & 1) == cset
     const int r_in_tile = ew * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
     const bool geglu = (p.act == kActGeglu);
     const int ncols_out = p.n_out;
     const int out_tile_w = geglu ? p.block_n / 2 : p.block_n;
-    uint8_t* stg_warp = stg + ew * 8192;
+    uint8_t* stg_warp = stg + e * 4096;
     int toggle = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
@@ -380,18 +383,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kMaxBlockN;
 
-      int c = 0;
-      if (p.tma_store) {
-        // ---- 64-column groups: registers -> swizzled smem -> TMA bulk store, one store per destination
-        for (; c + 64 <= out_tile_w; c += 64) {
-          const int ocol0 = tc.n_tile * out_tile_w + c;
-          if (ocol0 >= ncols_out) break;
-          float v[64];
-          load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
-          load_activate32(p, taddr, c + 32, out_tile_w, tc.n_tile, bm, row_ok, bidx, v + 32);
+      for (int c = cset * 32; c < out_tile_w; c += 64) {
+        const int ocol0 = tc.n_tile * out_tile_w + c;
+        if (ocol0 >= ncols_out) break;
+        float v[32];
+        load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
+        const int lim = min(ncols_out, ocol0 + 32);
+        if (p.tma_store) {
+          // registers -> swizzled smem -> one TMA bulk store per destination (rows / columns clipped by the map)
           if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
-          gate_residual32(p, v, row, bidx, ocol0, ncols_out, ncols_out, row_ok);
-          gate_residual32(p, v + 32, row, bidx, ocol0 + 32, ncols_out, ncols_out, row_ok);
+          gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
           if (p.out) stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
           if (p.out2) stage_and_store<false>(&maps.out2, stg_warp, toggle, lane, v, ocol0, sc);
 #pragma unroll
@@ -399,24 +400,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             if (s < p.num_cap && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end)
               stage_and_store<true>(&maps.cap[s], stg_warp, toggle, lane, v, ocol0 - p.cap[s].col_begin, sc);
           }
-          if (p.out_f32 && row_ok) {
-            direct_store32(p, v, v, row, ocol0, min(ncols_out, ocol0 + 32), out_batch_off, true);
-            direct_store32(p, v + 32, v + 32, row, ocol0 + 32, min(ncols_out, ocol0 + 64), out_batch_off, true);
-          }
-        }
-      }
-      // ---- remaining 32-column chunks (whole tile when TMA stores are off): direct 128-bit stores
-      for (; c < out_tile_w; c += 32) {
-        const int ocol0 = tc.n_tile * out_tile_w + c;
-        float v[32], vpre[32];
-        load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
-        if (p.cap_pre) {
+          if (p.out_f32 && row_ok) direct_store32(p, v, v, row, ocol0, lim, out_batch_off, true);
+        } else {
+          float vpre[32];
+          if (p.cap_pre) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vpre[j] = v[j];
+            for (int j = 0; j < 32; ++j) vpre[j] = v[j];
+          }
+          gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
+          if (row_ok) direct_store32(p, vpre, v, row, ocol0, lim, out_batch_off, false);
         }
-        const int lim = min(ncols_out, ocol0 + min(32, out_tile_w - c));
-        gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok && ocol0 < ncols_out);
-        if (row_ok && ocol0 < ncols_out) direct_store32(p, vpre, v, row, ocol0, lim, out_batch_off, false);
       }
       tc_fence_before();
       __syncwarp();

@@ -32,8 +32,8 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 // Build a tiled bf16 tensor map. dims/strides innermost first; strides_bytes has rank-1 entries
-// (stride of dims 1..rank-1); box innermost first. 128B swizzle, zero fill out of bounds.
+// (stride of dims 1..rank-1); box innermost first. swizzle_bytes in {128, 64, 0}; zero fill out of bounds.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128 = true);
+                   const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace gdf

@@ -1,5 +1,6 @@
 // Host-side construction of GEMM / implicit-GEMM launches (tensor maps + tiling).
 #include "ops.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace gdf {
@@ -13,30 +14,30 @@ static int gcd_int(int a, int b) {
   return a;
 }
 
-// Tile width by a small cost model: rounds of the persistent grid x (tile width + fixed per-tile overhead),
-// counting the wasted columns of a ragged last N tile. Multiples of 64 keep the TMA-store epilogue on every column.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Tile width: the kernel is operand-load bound (L2 -> smem bytes per MMA cycle ~ (128 + bn) / bn), so the widest
+// tile that does not waste columns wins; narrower tiles only for narrow N (measured, profiles/r01_probe_gemm.txt).
 int choose_block_n(int N, bool geglu, int num_m_tiles) {
-  if (!geglu && N <= 64) return ((N + 15) / 16) * 16;
-  const int sms = gemm_num_sms();
-  int best = 0;
-  double best_cost = 1e30;
-  const int cands_plain[4] = {256, 192, 128, 64};
-  const int cands_geglu[2] = {256, 128};
-  const int* cands = geglu ? cands_geglu : cands_plain;
-  const int nc = geglu ? 2 : 4;
-  for (int i = 0; i < nc; ++i) {
+  (void)num_m_tiles;
+  const int forced = env_int("GDF_BLOCK_N", 0);   // tuning knob
+  if (forced > 0 && forced % 16 == 0 && forced <= kMaxBlockN && (!geglu || forced % 64 == 0)) return forced;
+  if (geglu) return N >= 256 ? 256 : 128;
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  int best = 256, best_waste = 1 << 30;
+  const int cands[4] = {256, 224, 192, 160};
+  for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
-    if (bn > ((N + 63) / 64) * 64 && bn != 64) continue;
-    const long long tiles = (long long)num_m_tiles * ((N + bn - 1) / bn);
-    const long long rounds = (tiles + sms - 1) / sms;
-    double cost = (double)rounds * (bn + 24);
-    if (bn < 128) cost *= 1.15;   // A tile re-fetched per narrow N tile: L2 traffic penalty
-    if (cost < best_cost) {
-      best_cost = cost;
+    const int waste = ((N + bn - 1) / bn) * bn - N;
+    if (waste * 8 < best_waste * 8 - N) {   // accept a narrower tile only if it saves > 1/8 of N in padded columns
       best = bn;
+      best_waste = waste;
     }
   }
-  return best ? best : 128;
+  return best;
 }
 
 static int make_store_map(CUtensorMap* m, const GemmParams& p, const void* ptr, int width, int ld,
@@ -44,16 +45,16 @@ static int make_store_map(CUtensorMap* m, const GemmParams& p, const void* ptr, 
   if (p.a_mode == kALinear) {
     uint64_t dims[3] = {(uint64_t)width, (uint64_t)p.M, (uint64_t)p.batch};
     uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)(p.batch > 1 ? batch_stride : (long long)p.M * ld) * 2};
-    uint32_t box[3] = {64, 32, 1};
-    return make_tmap_bf16(m, ptr, 3, dims, str, box);
+    uint32_t box[3] = {32, 32, 1};
+    return make_tmap_bf16(m, ptr, 3, dims, str, box, 64);
   }
   const int cx = p.tw < 32 ? p.tw : 32;
   const int cy = p.th < 32 / cx ? p.th : 32 / cx;
   const int cb = 32 / (cx * cy);
   uint64_t dims[4] = {(uint64_t)width, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B_img};
   uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)p.W * ld * 2, (uint64_t)p.H * p.W * ld * 2};
-  uint32_t box[4] = {64, (uint32_t)cx, (uint32_t)cy, (uint32_t)cb};
-  return make_tmap_bf16(m, ptr, 4, dims, str, box);
+  uint32_t box[4] = {32, (uint32_t)cx, (uint32_t)cy, (uint32_t)cb};
+  return make_tmap_bf16(m, ptr, 4, dims, str, box, 64);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -62,13 +63,14 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 static int setup_stores(GemmLaunch* g) {
   GemmParams& p = g->p;
   const int out_tile_w = (p.act == kActGeglu) ? p.block_n / 2 : p.block_n;
-  bool ok = out_tile_w >= 64 && p.n_out >= 64;
+  bool ok = out_tile_w >= 32 && p.n_out >= 32 && p.n_out % 8 == 0;
   if (p.out && (p.ld_out % 8 != 0 || !aligned16(p.out) || (p.batch > 1 && p.out_batch_stride % 8 != 0))) ok = false;
   if (p.out2 && (p.ld_out2 % 8 != 0 || !aligned16(p.out2) || p.batch > 1)) ok = false;
   if (p.cap_pre && (p.ld_cap_pre % 8 != 0 || p.batch > 1)) ok = false;
   for (int i = 0; i < p.num_cap; ++i)
-    if (p.cap[i].ld % 8 != 0 || p.cap[i].col_begin % 64 != 0 || p.batch > 1) ok = false;
+    if (p.cap[i].ld % 8 != 0 || p.cap[i].col_begin % 32 != 0 || p.batch > 1) ok = false;
   if (!p.out && !p.out2 && !p.cap_pre && p.num_cap == 0) ok = false;
+  if (env_int("GDF_TMA_STORE", 1) == 0) ok = false;   // tuning knob
   p.tma_store = ok ? 1 : 0;
   if (!ok) return GDF_OK;
   if (p.out) GDF_TRY(make_store_map(&g->maps.out, p, p.out, p.n_out, p.ld_out, p.out_batch_stride));
@@ -122,7 +124,7 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   GemmParams& p = g->p;
   const bool geglu = (e.act == kActGeglu);
   if (block_n <= 0) block_n = choose_block_n(N, geglu, (int)((M + kBlockM - 1) / kBlockM) * batch);
-  if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 128 != 0))
+  if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 64 != 0))
     return fail(GDF_ERR_INVALID, "build_linear: bad block_n %d", block_n);
   if (K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
     return fail(GDF_ERR_SHAPE, "build_linear: K/lda/ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw);
