@@ -7,6 +7,7 @@
 // v1 data path: cp.async double-buffered K/V tiles in XOR-swizzled shared memory, ldmatrix fragments,
 // mma.sync.m16n8k16 (legacy tensor path). The tcgen05/TMEM variant replaces the two mma loops; the softmax
 // and pipeline structure stay.
+#include <stdlib.h>
 #include "ops.h"
 
 namespace gdf {
@@ -223,6 +224,19 @@ cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, c
     attr_set = true;
   }
   if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
+  {
+    // long KV (self-attention): tcgen05 / TMEM kernel; short KV (text cross-attention, Nk = 77): mma.sync kernel
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* v = getenv("GDF_ATTN_TCGEN05");
+      use_tc = v ? atoi(v) : 1;
+    }
+    if (use_tc && Nk >= 128) {
+      if (launch_attention64_tcgen05(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, scale, stream) != 0)
+        return cudaErrorUnknown;
+      return cudaSuccess;
+    }
+  }
   dim3 grid((Nq + kAttBM - 1) / kAttBM, heads, B);
   attention64_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
                                                             scale * 1.4426950408889634f);

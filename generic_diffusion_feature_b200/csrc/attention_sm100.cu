@@ -1,0 +1,328 @@
+// Flash attention forward on tcgen05 / TMEM / TMA, head_dim 64 (self-attention of the UNet levels).
+// Reference call site: F.scaled_dot_product_attention, feature/diffusers/models/attention_processor.py:3311-3313.
+//
+// One CTA = 2 query tiles of 128 rows (256 queries of one (batch, head)), looping over KV tiles of 128 rows:
+//   warp 0     : TMA producer  (Q tiles once; K and V tiles through two 3-deep rings; 128B swizzle)
+//   warp 1     : MMA issuer    (S_t = Q_t K_j^T : UMMA 128x128x16 x4, K-major operands;
+//                               PV_t = P_t V_j  : UMMA 128x64x16 x8, A = P (bf16, written to smem by the softmax
+//                               warps in the canonical K-major SW128 layout), B = V tile as MN-major operand)
+//   warp 2     : TMEM allocator (512 columns: S_A, S_B 128 each; PV_A, PV_B 64 each)
+//   warps 4-11 : softmax       (2 groups x 4 warps; thread = one query row: two passes over S in TMEM
+//                               (row max, then exp2 / row sum / bf16 P -> smem), running rescale of the fp32
+//                               output accumulator kept in registers, PV partial products read back from TMEM)
+// Q/K/V are read in place from the token-major projection output (head h = columns [64h, 64h+64)).
+#include "ops.h"
+
+namespace gdf {
+
+constexpr int kFaThreads = 384;
+constexpr int kFaRing = 3;
+constexpr int kFaTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+// smem: Q 2 tiles | K ring | V ring | P 2 x (2 blocks of 16 KB) | barriers
+constexpr int kFaOffK = 2 * kFaTile;
+constexpr int kFaOffV = kFaOffK + kFaRing * kFaTile;
+constexpr int kFaOffP = kFaOffV + kFaRing * kFaTile;
+constexpr int kFaOffBar = kFaOffP + 4 * kFaTile;
+constexpr int kFaSmem = kFaOffBar + 256 + 1024;
+
+struct FaParams {
+  int Nq, Nk, heads;
+  int num_kv_tiles;
+  float scale_log2;
+  bf16* O;
+  int ldo;
+};
+
+__global__ void __launch_bounds__(kFaThreads, 1)
+attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                           const __grid_constant__ CUtensorMap map_v, const FaParams p) {
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFaOffBar);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [ring]
+  uint64_t* k_empty = k_full + kFaRing;
+  uint64_t* v_full = k_empty + kFaRing;
+  uint64_t* v_empty = v_full + kFaRing;
+  uint64_t* s_full = v_empty + kFaRing;    // [2] per query tile
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* pv_full = p_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n = p.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kFaRing; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kFaTile);
+      tma_load_3d(smem, &map_q, q_full, h * 64, q0, b);
+      tma_load_3d(smem + kFaTile, &map_q, q_full, h * 64, q0 + 128, b);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&k_empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&k_full[s], kFaTile);
+        tma_load_3d(smem + kFaOffK + s * kFaTile, &map_k, &k_full[s], h * 64, j * 128, b);
+      }
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[s], kFaTile);
+        tma_load_3d(smem + kFaOffV + s * kFaTile, &map_v, &v_full[s], h * 64, j * 128, b);
+      }
+      __syncwarp();
+      if (++s == kFaRing) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);   // B = V tile, MN-major
+    const uint32_t q_addr = smem_u32(smem);
+    const uint32_t k_addr = smem_u32(smem + kFaOffK);
+    const uint32_t v_addr = smem_u32(smem + kFaOffV);
+    const uint32_t p_addr = smem_u32(smem + kFaOffP);
+    auto issue_s = [&](int t, int slot) {   // S_t = Q_t K^T into TMEM columns [t*128, t*128+128)
+      const uint64_t da = umma_desc_kmajor_sw128(q_addr + t * kFaTile);
+      const uint64_t db = umma_desc_kmajor_sw128(k_addr + slot * kFaTile);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + t * 128, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int t, int slot) {  // PV_t = P_t V into TMEM columns [256 + t*64, +64), fresh accumulator
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        // A: P block (k / 4) of 16 KB, 32 B step inside the swizzle row; B: 16 kv rows = 2048 B per step
+        const uint64_t da = umma_desc_kmajor_sw128(p_addr + t * 2 * kFaTile + (k >> 2) * kFaTile) + 2 * (k & 3);
+        const uint64_t db = umma_desc_mnmajor_sw128(v_addr + slot * kFaTile + k * 2048, 8192);
+        umma_f16_ss(tmem_base + 256 + t * 64, da, db, idesc_pv, k != 0);
+      }
+      umma_commit(&pv_full[t]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (lane == 0) {
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n; ++j) {
+      int s1 = s + 1;
+      uint32_t ph1 = ph;
+      if (s1 == kFaRing) { s1 = 0; ph1 ^= 1; }
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], j & 1);     // softmax wrote P_t(j) and is done with S_t(j) and PV_t(j-1)
+        if (t == 0) mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(t, s);
+          if (t == 1) umma_commit(&v_empty[s]);
+        }
+        __syncwarp();
+        if (j + 1 < n) {
+          if (t == 0) mbar_wait(&k_full[s1], ph1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_s(t, s1);
+            if (t == 1) umma_commit(&k_empty[s1]);
+          }
+          __syncwarp();
+        }
+      }
+      s = s1;
+      ph = ph1;
+    }
+  } else if (warp >= 4) {
+    // ================================================= softmax + output accumulation
+    const int e = warp - 4;
+    const int t = e >> 2;        // query tile of this group
+    const int quad = e & 3;      // == warp % 4: TMEM lane quadrant
+    const int r = quad * 32 + lane;              // row inside the query tile
+    const int qrow = q0 + t * 128 + r;
+    const uint32_t t_s = tmem_base + (uint32_t(quad * 32) << 16) + t * 128;
+    const uint32_t t_pv = tmem_base + (uint32_t(quad * 32) << 16) + 256 + t * 64;
+    uint8_t* p_base = smem + kFaOffP + t * 2 * kFaTile;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const int kv0 = j * 128;
+      const bool tail = (kv0 + 128 > p.Nk);
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_s + c * 32, raw);
+        tmem_ld_wait();
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // first tile: exp2(-inf) = 0
+      const float neg_m = -m_new * p.scale_log2;
+      m_run = m_new;
+      // ---- fold in the previous tile's P V (its MMA has been running during pass 1)
+      if (j > 0) {
+        mbar_wait(&pv_full[t], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_pv + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+        }
+      }
+      alpha_prev = alpha;
+      // ---- pass 2: P = exp2(S*scale - m*scale) -> bf16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_s + c * 32, raw);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = ex2_approx(fmaf(__uint_as_float(raw[i]), p.scale_log2, neg_m));
+          if (tail && kv0 + c * 32 + i >= p.Nk) x = 0.f;
+          pv[i] = x;
+          rs += x;
+        }
+        uint8_t* blk = p_base + (c >> 1) * kFaTile + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);
+          u.y = pack_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
+          u.z = pack_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);
+          u.w = pack_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
+          const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      l_run = l_run * alpha + rs;
+      // ---- publish P_t(j): smem writes visible to the tensor core (async proxy), TMEM reads retired
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- last tile's P V, normalise, store (each thread writes its 128-byte output row)
+    mbar_wait(&pv_full[t], (n - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(t_pv + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+    }
+    const float inv = 1.f / l_run;
+    if (qrow < p.Nq) {
+      bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * 64;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(o_acc[q * 8 + 0] * inv, o_acc[q * 8 + 1] * inv);
+        u.y = pack_bf16x2(o_acc[q * 8 + 2] * inv, o_acc[q * 8 + 3] * inv);
+        u.z = pack_bf16x2(o_acc[q * 8 + 4] * inv, o_acc[q * 8 + 5] * inv);
+        u.w = pack_bf16x2(o_acc[q * 8 + 6] * inv, o_acc[q * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[q] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Host: tensor maps over the strided Q / K / V views (cols, rows-per-batch, batch), box 64 x 128 x 1.
+int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
+                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDF_CUDA(cudaFuncSetAttribute(attention64_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
+    attr_set = true;
+  }
+  CUtensorMap mq, mk, mv;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)heads * 64, (uint64_t)Nq, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)Nq * ldq * 2};
+    GDF_TRY(make_tmap_bf16(&mq, Q, 3, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)heads * 64, (uint64_t)Nk, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ldk * 2, (uint64_t)Nk * ldk * 2};
+    GDF_TRY(make_tmap_bf16(&mk, K, 3, dims, str, box));
+    uint64_t strv[2] = {(uint64_t)ldv * 2, (uint64_t)Nk * ldv * 2};
+    GDF_TRY(make_tmap_bf16(&mv, V, 3, dims, strv, box));
+  }
+  FaParams p;
+  p.Nq = Nq;
+  p.Nk = Nk;
+  p.heads = heads;
+  p.num_kv_tiles = (Nk + 127) / 128;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.O = O;
+  p.ldo = ldo;
+  dim3 grid((Nq + 255) / 256, heads, B);
+  attention64_tcgen05_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(mq, mk, mv, p);
+  GDF_CUDA(cudaGetLastError());
+  return GDF_OK;
+}
+
+}  // namespace gdf

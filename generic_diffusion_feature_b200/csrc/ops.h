@@ -71,6 +71,9 @@ cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const f
 // Q[B*Nq, ldq] / K,V[B*Nk, ldk/ldv] / O[B*Nq, ldo]; head h lives in columns [h*64, h*64+64).
 cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
+// tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
+int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
+                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
 // Row softmax in place over bf16 S[rows, cols] (ld), fp32 math (VAE single-head attention).
 cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaStream_t stream);
 

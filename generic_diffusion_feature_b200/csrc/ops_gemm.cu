@@ -27,9 +27,9 @@ int choose_block_n(int N, bool geglu, int num_m_tiles) {
   if (forced > 0 && forced % 16 == 0 && forced <= kMaxBlockN && (!geglu || forced % 64 == 0)) return forced;
   if (geglu) return N >= 256 ? 256 : 128;
   if (N <= 256) return ((N + 15) / 16) * 16;
-  int best = 256, best_waste = 1 << 30;
-  const int cands[4] = {256, 224, 192, 160};
-  for (int i = 0; i < 4; ++i) {
+  int best = 256, best_waste = ((N + 255) / 256) * 256 - N;
+  const int cands[3] = {224, 192, 160};
+  for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const int waste = ((N + bn - 1) / bn) * bn - N;
     if (waste * 8 < best_waste * 8 - N) {   // accept a narrower tile only if it saves > 1/8 of N in padded columns

@@ -184,9 +184,26 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (e.g. V[kv][d] used as B[K=kv][N=d]): rows are K indices, 64 N-elements (128 B) per row,
+// 8-row groups 1024 B apart (SBO); LBO = stride between 64-element N blocks (single block here).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  uint32_t d = 0;
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
+  uint32_t d = b_mn_major << 16;   // bit 16: B major (0 = K-major, 1 = MN-major)
   d |= 1u << 4;          // c_format = F32
   d |= 1u << 7;          // a_format = BF16
   d |= 1u << 10;         // b_format = BF16
