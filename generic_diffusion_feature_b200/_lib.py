@@ -42,7 +42,7 @@ class Epilogue(ctypes.Structure):
         ("col_scale_dev", c_void_p),
         ("residual_dev", c_void_p), ("ld_res", c_int),
         ("out_scale", c_float),
-        ("out_dev", c_void_p), ("ld_out", c_int), ("out_batch_stride", c_int64),
+        ("out_dev", c_void_p), ("ld_out", c_int), ("out_batch_stride", c_int64), ("out_f16_from", c_int),
         ("out2_dev", c_void_p), ("ld_out2", c_int),
         ("out_f32_dev", c_void_p), ("ld_out_f32", c_int),
         ("cap_pre_dev", c_void_p), ("ld_cap_pre", c_int),
@@ -108,7 +108,7 @@ def load():
     lib.gdf_op_groupnorm.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P]
     lib.gdf_op_layernorm.argtypes = [P, P, P, P, c_int64, c_int, c_float, P, P, c_int, P]
     lib.gdf_op_attention.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_float, P]
+                                     c_float, c_int, P]
     lib.gdf_op_softmax_rows.argtypes = [P, c_int64, c_int, c_int, P]
     lib.gdf_op_upsample_nearest2x.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.gdf_op_im2col_small.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P]

@@ -21,6 +21,7 @@ static Epilogue to_epilogue(const gdf_epilogue* ep) {
   e.out = static_cast<bf16*>(ep->out_dev);
   e.ld_out = ep->ld_out;
   e.out_batch_stride = ep->out_batch_stride;
+  e.out_f16_from = ep->out_f16_from;
   e.out2 = static_cast<bf16*>(ep->out2_dev);
   e.ld_out2 = ep->ld_out2;
   e.out_f32 = static_cast<float*>(ep->out_f32_dev);
@@ -90,11 +91,11 @@ int gdf_op_layernorm(const void* x, void* y, const void* gamma, const void* beta
 }
 
 int gdf_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
-                     int heads, int Nq, int Nk, int head_dim, float scale, void* stream) {
+                     int heads, int Nq, int Nk, int head_dim, float scale, int v_f16, void* stream) {
   if (head_dim != 64) return fail(GDF_ERR_UNSUPPORTED, "gdf_op_attention: head_dim %d (only 64)", head_dim);
   GDF_LAUNCH(launch_attention64(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
                                 static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, B, heads, Nq, Nk, scale,
-                                static_cast<cudaStream_t>(stream)));
+                                v_f16, static_cast<cudaStream_t>(stream)));
 }
 
 int gdf_op_softmax_rows(void* s, int64_t rows, int cols, int ld, void* stream) {

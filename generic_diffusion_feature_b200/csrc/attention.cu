@@ -215,8 +215,18 @@ attention64_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__
   }
 }
 
+bool attention_uses_tcgen05(int Nk) {
+  // long KV (self-attention): tcgen05 / TMEM kernel; short KV (text cross-attention, Nk = 77): mma.sync kernel
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* v = getenv("GDF_ATTN_TCGEN05");
+    use_tc = v ? atoi(v) : 1;
+  }
+  return use_tc && Nk >= 128;
+}
+
 cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
-                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream) {
+                               int B, int heads, int Nq, int Nk, float scale, int v_f16, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
@@ -224,18 +234,13 @@ cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, c
     attr_set = true;
   }
   if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
-  {
-    // long KV (self-attention): tcgen05 / TMEM kernel; short KV (text cross-attention, Nk = 77): mma.sync kernel
-    static int use_tc = -1;
-    if (use_tc < 0) {
-      const char* v = getenv("GDF_ATTN_TCGEN05");
-      use_tc = v ? atoi(v) : 1;
+  if (v_f16) {
+    if (!attention_uses_tcgen05(Nk)) return cudaErrorInvalidValue;   // the mma.sync kernel takes bf16 V
+    if (launch_attention64_tcgen05(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, scale, stream) != 0) {
+      fprintf(stderr, "gdf: tcgen05 attention launch failed: %s\n", last_error().c_str());
+      return cudaErrorUnknown;
     }
-    if (use_tc && Nk >= 128) {
-      if (launch_attention64_tcgen05(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, scale, stream) != 0)
-        return cudaErrorUnknown;
-      return cudaSuccess;
-    }
+    return cudaSuccess;
   }
   dim3 grid((Nq + kAttBM - 1) / kAttBM, heads, B);
   attention64_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,

@@ -11,6 +11,7 @@
 //                               (row max, then exp2 / row sum / bf16 P -> smem), running rescale of the fp32
 //                               output accumulator kept in registers, PV partial products read back from TMEM)
 // Q/K/V are read in place from the token-major projection output (head h = columns [64h, 64h+64)).
+#include <stdlib.h>
 #include "ops.h"
 
 namespace gdf {
@@ -47,7 +48,8 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
   uint64_t* s_full = v_empty + kFaRing;    // [2] per query tile
   uint64_t* p_full = s_full + 2;           // [2]
   uint64_t* pv_full = p_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+  uint64_t* s_free = pv_full + 2;          // [2] S_t(j) fully read from TMEM (next S may overwrite it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
@@ -71,6 +73,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);
       mbar_init(&pv_full[t], 1);
+      mbar_init(&s_free[t], 4);
     }
     fence_barrier_init();
   }
@@ -82,6 +85,9 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // register rebalancing: the producer / MMA / allocator warpgroup needs few registers, the softmax warpgroups many
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
 
   if (warp == 0) {
     // ================================================= TMA producer
@@ -109,7 +115,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
   } else if (warp == 1) {
     // ================================================= MMA issuer
     const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
-    const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);   // B = V tile, MN-major
+    const uint32_t idesc_pv = umma_idesc_f16(128, 64, 1);   // A = P (fp16), B = V tile (fp16), MN-major   // A = P (fp16), B = V tile (bf16), MN-major
     const uint32_t q_addr = smem_u32(smem);
     const uint32_t k_addr = smem_u32(smem + kFaOffK);
     const uint32_t v_addr = smem_u32(smem + kFaOffV);
@@ -140,36 +146,44 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       umma_commit(&k_empty[0]);
     }
     __syncwarp();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n; ++j) {
-      int s1 = s + 1;
-      uint32_t ph1 = ph;
-      if (s1 == kFaRing) { s1 = 0; ph1 ^= 1; }
+    // Event-driven issue: each query tile advances on its own barriers (S_t(j+1) once S_t(j) has been read out of
+    // TMEM, PV_t(j) once P_t(j) is in smem), so one group never waits for the other group's softmax.
+    int next_s[2] = {1, 1}, next_pv[2] = {0, 0};
+    int s_issued[kFaRing] = {0, 0, 0}, pv_issued[kFaRing] = {0, 0, 0};
+    while (next_pv[0] < n || next_pv[1] < n) {
+#pragma unroll
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_full[t], j & 1);     // softmax wrote P_t(j) and is done with S_t(j) and PV_t(j-1)
-        if (t == 0) mbar_wait(&v_full[s], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_pv(t, s);
-          if (t == 1) umma_commit(&v_empty[s]);
-        }
-        __syncwarp();
-        if (j + 1 < n) {
-          if (t == 0) mbar_wait(&k_full[s1], ph1);
-          tc_fence_after();
-          if (lane == 0) {
-            issue_s(t, s1);
-            if (t == 1) umma_commit(&k_empty[s1]);
+        if (next_s[t] < n) {
+          const int js = next_s[t], slot = js % kFaRing;
+          if (mbar_try_wait(&s_free[t], (js - 1) & 1) && mbar_try_wait(&k_full[slot], (js / kFaRing) & 1)) {
+            tc_fence_after();
+            if (lane == 0) {
+              issue_s(t, slot);
+              if (s_issued[slot] == 1) umma_commit(&k_empty[slot]);   // both query tiles have consumed K(js)
+            }
+            s_issued[slot] ^= 1;
+            __syncwarp();
+            next_s[t] = js + 1;
           }
-          __syncwarp();
+        }
+        if (next_pv[t] < n) {
+          const int jp = next_pv[t], slot = jp % kFaRing;
+          if (mbar_try_wait(&p_full[t], jp & 1) && mbar_try_wait(&v_full[slot], (jp / kFaRing) & 1)) {
+            tc_fence_after();
+            if (lane == 0) {
+              issue_pv(t, slot);
+              if (pv_issued[slot] == 1) umma_commit(&v_empty[slot]);
+            }
+            pv_issued[slot] ^= 1;
+            __syncwarp();
+            next_pv[t] = jp + 1;
+          }
         }
       }
-      s = s1;
-      ph = ph1;
     }
   } else if (warp >= 4) {
     // ================================================= softmax + output accumulation
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int e = warp - 4;
     const int t = e >> 2;        // query tile of this group
     const int quad = e & 3;      // == warp % 4: TMEM lane quadrant
@@ -187,20 +201,23 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       tc_fence_after();
       const int kv0 = j * 128;
       const bool tail = (kv0 + 128 > p.Nk);
-      // ---- pass 1: row max
+      // ---- pass 1: row max (two 32-column TMEM loads in flight per wait)
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(t_s + c * 32, raw);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_s + c * 32, ra);
+        tmem_ld_32x32(t_s + c * 32 + 32, rb);
         tmem_ld_wait();
         if (!tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (kv0 + c * 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(ra[i]));
+            if (kv0 + c * 32 + 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(rb[i]));
+          }
         }
       }
       const float m_new = fmaxf(m_run, mx);
@@ -211,41 +228,63 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       if (j > 0) {
         mbar_wait(&pv_full[t], (j - 1) & 1);
         tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_pv, ra);
+        tmem_ld_32x32(t_pv + 32, rb);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(t_pv + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+        for (int i = 0; i < 32; ++i) {
+          o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(ra[i]));
+          o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_prev, __uint_as_float(rb[i]));
         }
       }
       alpha_prev = alpha;
-      // ---- pass 2: P = exp2(S*scale - m*scale) -> bf16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum
+      // ---- pass 2: P = exp2(S*scale - m*scale) -> fp16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum.
+      // Two exponentials per MUFU op (ex2.approx.f16x2); the TMEM load of chunk c+1 is in flight meanwhile.
       float rs = 0.f;
+      uint32_t cur[32], nxt[32];
+      tmem_ld_32x32(t_s, cur);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(t_s + c * 32, raw);
-        tmem_ld_wait();
-        float pv[32];
+        if (c < 3) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);
+        uint32_t ph2[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = ex2_approx(fmaf(__uint_as_float(raw[i]), p.scale_log2, neg_m));
-          if (tail && kv0 + c * 32 + i >= p.Nk) x = 0.f;
-          pv[i] = x;
-          rs += x;
+        for (int i = 0; i < 16; ++i) {
+          float x0 = fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, neg_m);
+          float x1 = fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, neg_m);
+          if (tail) {
+            if (kv0 + c * 32 + 2 * i >= p.Nk) x0 = -INFINITY;
+            if (kv0 + c * 32 + 2 * i + 1 >= p.Nk) x1 = -INFINITY;
+          }
+          ph2[i] = ex2_f16x2(x0, x1);
         }
+        // row sum: 4 independent half2 accumulators of 4 pairs each, widened to fp32 per chunk
+        uint32_t a0 = hadd2_u32(hadd2_u32(ph2[0], ph2[1]), hadd2_u32(ph2[2], ph2[3]));
+        uint32_t a1 = hadd2_u32(hadd2_u32(ph2[4], ph2[5]), hadd2_u32(ph2[6], ph2[7]));
+        uint32_t a2 = hadd2_u32(hadd2_u32(ph2[8], ph2[9]), hadd2_u32(ph2[10], ph2[11]));
+        uint32_t a3 = hadd2_u32(hadd2_u32(ph2[12], ph2[13]), hadd2_u32(ph2[14], ph2[15]));
+        rs += (half2_sum_f32(a0) + half2_sum_f32(a1)) + (half2_sum_f32(a2) + half2_sum_f32(a3));
         uint8_t* blk = p_base + (c >> 1) * kFaTile + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
-          u.x = pack_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);
-          u.y = pack_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
-          u.z = pack_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);
-          u.w = pack_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
+          u.x = ph2[q * 4 + 0];
+          u.y = ph2[q * 4 + 1];
+          u.z = ph2[q * 4 + 2];
+          u.w = ph2[q * 4 + 3];
           const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
           *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+        if (c < 3) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+        }
+        if (c == 2) {   // the last chunk of S_t(j) is now in registers: the tensor core may overwrite S_t
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
         }
       }
       l_run = l_run * alpha + rs;
@@ -258,13 +297,16 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
     // ---- last tile's P V, normalise, store (each thread writes its 128-byte output row)
     mbar_wait(&pv_full[t], (n - 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32(t_pv + c * 32, raw);
+    {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_pv, ra);
+      tmem_ld_32x32(t_pv + 32, rb);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+      for (int i = 0; i < 32; ++i) {
+        o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(ra[i]));
+        o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_prev, __uint_as_float(rb[i]));
+      }
     }
     const float inv = 1.f / l_run;
     if (qrow < p.Nq) {

@@ -129,7 +129,11 @@ __device__ __forceinline__ void direct_store32(const GemmParams& p, const float*
         if (ocol0 + j < lim) dst[j] = __float2half_rn(vpre[j]);
     }
   }
-  if (p.out && !skip16) {
+  if (p.out && !skip16 && ocol0 >= p.out_f16_from) {
+    __half* dst = reinterpret_cast<__half*>(p.out + out_batch_off + row * p.ld_out + ocol0);
+    for (int j = 0; j < 32; ++j)
+      if (ocol0 + j < lim) dst[j] = __float2half_rn(v[j]);
+  } else if (p.out && !skip16) {
     __nv_bfloat16* dst = p.out + out_batch_off + row * p.ld_out + ocol0;
     if (full && (p.ld_out % 8 == 0)) {
       store16_bf16(dst, v);
@@ -393,7 +397,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // registers -> swizzled smem -> one TMA bulk store per destination (rows / columns clipped by the map)
           if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
           gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
-          if (p.out) stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
+          if (p.out) {
+            if (ocol0 >= p.out_f16_from) stage_and_store<true>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
+            else stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
+          }
           if (p.out2) stage_and_store<false>(&maps.out2, stg_warp, toggle, lane, v, ocol0, sc);
 #pragma unroll
           for (int s = 0; s < 3; ++s) {

@@ -54,6 +54,7 @@ struct GemmParams {
   const __nv_bfloat16* residual; int ld_res;   // added after activation
   float out_scale;             // multiplies (acc + residual), = 1/output_scale_factor
   __nv_bfloat16* out;  int ld_out;  long long out_batch_stride;
+  int out_f16_from;            // columns >= this are written to `out` as fp16 instead of bf16 (V for fp16 P.V)
   __nv_bfloat16* out2; int ld_out2;            // second destination (skip-concat slice) or null
   float* out_f32; int ld_out_f32;              // optional fp32 destination
   __half* cap_pre; int ld_cap_pre;             // fp16 capture before residual add ("increment")

@@ -26,6 +26,7 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   const bf16* residual = nullptr; int ld_res = 0;
   float out_scale = 1.f;
   bf16* out = nullptr; int ld_out = 0; long long out_batch_stride = 0;
+  int out_f16_from = 0;       // > 0: columns >= this go to `out` as fp16 (multiple of 32)
   bf16* out2 = nullptr; int ld_out2 = 0;
   float* out_f32 = nullptr; int ld_out_f32 = 0;
   __half* cap_pre = nullptr; int ld_cap_pre = 0;
@@ -69,8 +70,11 @@ cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const f
 
 // ---- attention (attention.cu): softmax(Q K^T * scale) V per (batch, head), head_dim 64.
 // Q[B*Nq, ldq] / K,V[B*Nk, ldk/ldv] / O[B*Nq, ldo]; head h lives in columns [h*64, h*64+64).
+// v_f16: V holds fp16 bit patterns (written by the projection GEMM with out_f16_from): enables the tcgen05 kernel,
+// whose P.V product runs in fp16 (P = exp2 computed two-per-MUFU-op in half2).
 cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
-                               int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
+                               int B, int heads, int Nq, int Nk, float scale, int v_f16, cudaStream_t stream);
+bool attention_uses_tcgen05(int Nk);
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);

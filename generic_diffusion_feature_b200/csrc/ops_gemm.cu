@@ -108,6 +108,7 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.out = e.out;
   p.ld_out = e.ld_out;
   p.out_batch_stride = e.out_batch_stride;
+  p.out_f16_from = e.out_f16_from > 0 ? e.out_f16_from : (1 << 30);
   p.out2 = e.out2;
   p.ld_out2 = e.ld_out2;
   p.out_f32 = e.out_f32;

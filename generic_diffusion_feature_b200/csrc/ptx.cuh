@@ -201,7 +201,33 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// two exponentials per MUFU op: 2^x on a packed half2 (inputs <= 0 after max subtraction; fp16 range is ample)
+__device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
+  uint32_t h, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));   // low half = a, high half = b
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  return y;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ float half2_sum_f32(uint32_t a) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&a);
+  const float2 f = __half22float2(h);
+  return f.x + f.y;
+}
+
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
+// fp16 x fp16 variant (A and B must share the 16-bit type: a mixed f16/bf16 descriptor is an illegal instruction)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
+  uint32_t d = b_mn_major << 16;
+  d |= 1u << 4;          // c_format = F32, a_format = b_format = F16 (0)
+  d |= (N >> 3) << 17;
+  d |= (M >> 4) << 24;
+  return d;
+}
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
   uint32_t d = b_mn_major << 16;   // bit 16: B major (0 = K-major, 1 = MN-major)
   d |= 1u << 4;          // c_format = F32

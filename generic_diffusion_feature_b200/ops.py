@@ -11,7 +11,7 @@ ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3
 
 def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_per_batch=0, act=ACT_NONE,
                   col_scale=None, residual=None, out_scale=1.0, alpha=1.0, out2=None, out_f32=None, cap_pre=None,
-                  caps=(), n_out=0, out_batch_stride=0):
+                  caps=(), n_out=0, out_batch_stride=0, out_f16_from=0):
     e = Epilogue()
     e.alpha = alpha
     e.n_out = n_out
@@ -29,6 +29,7 @@ def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_pe
         e.out_dev = ptr(out)
         e.ld_out = out.stride(-2)
         e.out_batch_stride = out_batch_stride
+        e.out_f16_from = out_f16_from
     if out2 is not None:
         e.out2_dev = ptr(out2)
         e.ld_out2 = out2.stride(-2)
@@ -93,12 +94,13 @@ def layernorm(x, gamma, beta, eps, mod_scale=None, mod_shift=None, rows_per_batc
     return y
 
 
-def attention(q, k, v, B, heads, Nq, Nk, scale, head_dim=64):
-    """q: bf16 [B*Nq, >=heads*64] (pitch q.stride(0)); k, v: [B*Nk, ...]. Returns bf16 [B*Nq, heads*64]."""
+def attention(q, k, v, B, heads, Nq, Nk, scale, head_dim=64, v_f16=False):
+    """q: bf16 [B*Nq, >=heads*64] (pitch q.stride(0)); k, v: [B*Nk, ...]. Returns bf16 [B*Nq, heads*64].
+    v_f16: v is a float16 tensor (tcgen05 kernel, Nk >= 128); otherwise bf16 (mma.sync kernel)."""
     lib = _lib.load()
     o = torch.empty(B * Nq, heads * head_dim, dtype=torch.bfloat16, device=q.device)
     check(lib.gdf_op_attention(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), o.stride(0), B,
-                               heads, Nq, Nk, head_dim, scale, stream_ptr()))
+                               heads, Nq, Nk, head_dim, scale, int(v_f16), stream_ptr()))
     return o
 
 

@@ -157,6 +157,7 @@ typedef struct gdf_epilogue {
   const void* residual_dev; int ld_res;    /* bf16 */
   float out_scale;        /* 0 is treated as 1 */
   void* out_dev; int ld_out; int64_t out_batch_stride;   /* bf16 */
+  int out_f16_from;       /* > 0: columns >= this are written to out as fp16 (V of a fused QKV projection) */
   void* out2_dev; int ld_out2;                           /* bf16 */
   void* out_f32_dev; int ld_out_f32;
   void* cap_pre_dev; int ld_cap_pre;                     /* fp16, before residual */
@@ -182,9 +183,10 @@ int gdf_op_groupnorm(const void* x_dev, void* y_dev, const void* gamma_dev, cons
 int gdf_op_layernorm(const void* x_dev, void* y_dev, const void* gamma_dev, const void* beta_dev, int64_t M, int C,
                      float eps, const void* mod_scale_dev, const void* mod_shift_dev, int rows_per_batch,
                      void* stream);
-/* softmax(QK^T*scale)V, head_dim 64 (attention_processor.py:3311-3313) */
+/* softmax(QK^T*scale)V, head_dim 64 (attention_processor.py:3311-3313). q, k bf16; v bf16 (v_f16 = 0, mma.sync
+ * kernel) or fp16 bit patterns (v_f16 = 1, tcgen05/TMEM kernel, needs Nk >= 128). */
 int gdf_op_attention(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv, void* o_dev,
-                     int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale, void* stream);
+                     int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale, int v_f16, void* stream);
 int gdf_op_softmax_rows(void* s_dev, int64_t rows, int cols, int ld, void* stream);
 int gdf_op_upsample_nearest2x(const void* x_dev, void* y_dev, int B, int H, int W, int C, void* stream);
 int gdf_op_im2col_small(const void* src_nchw_f32_dev, const void* src_nhwc_bf16_dev, void* a_dev, int B, int H,

@@ -202,8 +202,12 @@ def test_layernorm(cuda_dev, M, C, mod):
 
 @pytest.mark.parametrize("B,heads,Nq,Nk", [(2, 4, 1024, 1024), (1, 10, 4096, 4096), (2, 5, 1024, 77), (1, 2, 200, 300),
                                            (3, 1, 64, 64)])
-def test_attention64(cuda_dev, B, heads, Nq, Nk):
+@pytest.mark.parametrize("v_f16", [False, True])
+def test_attention64(cuda_dev, B, heads, Nq, Nk, v_f16):
+    """v_f16=False: mma.sync kernel (bf16 V); v_f16=True: tcgen05/TMEM kernel (fp16 V and P, needs Nk >= 128)."""
     ops = _ops()
+    if v_f16 and Nk < 128:
+        pytest.skip("the tcgen05 kernel serves self-attention (Nk >= 128)")
     g = torch.Generator(device="cuda").manual_seed(8)
     C = heads * 64
     # q/k/v as column slices of a fused projection output (exercises the row pitch)
@@ -214,13 +218,49 @@ def test_attention64(cuda_dev, B, heads, Nq, Nk):
         q = _rand_bf16(g, B * Nq, C)
         kv = _rand_bf16(g, B * Nk, 2 * C)
         k, v = kv[:, :C], kv[:, C:]
-    o = ops.attention(q, k, v, B, heads, Nq, Nk, 64 ** -0.5)
+    if v_f16:
+        v = v.float().half().contiguous()
+    o = ops.attention(q, k, v, B, heads, Nq, Nk, 64 ** -0.5, v_f16=v_f16)
     torch.cuda.synchronize()
     qf = q.float().reshape(B, Nq, heads, 64).transpose(1, 2)
     kf = k.float().reshape(B, Nk, heads, 64).transpose(1, 2)
     vf = v.float().reshape(B, Nk, heads, 64).transpose(1, 2)
     want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Nq, C)
-    check_close(o, want, what="attention B%d h%d %dx%d" % (B, heads, Nq, Nk))
+    check_close(o, want, what="attention B%d h%d %dx%d f16=%d" % (B, heads, Nq, Nk, v_f16))
+
+
+def test_attention_peaked_softmax(cuda_dev):
+    """Large score range (peaked rows) through the half2-exp path of the tcgen05 kernel."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(18)
+    B, heads, N = 1, 2, 512
+    C = heads * 64
+    q = _rand_bf16(g, B * N, C, scale=4.0)
+    k = _rand_bf16(g, B * N, C, scale=4.0)
+    v = torch.randn(B * N, C, generator=g, device="cuda").half()
+    o = ops.attention(q, k, v, B, heads, N, N, 64 ** -0.5, v_f16=True)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, N, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, N, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, N, heads, 64).transpose(1, 2)
+    want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * N, C)
+    check_close(o, want, tol=2e-2, what="peaked attention")
+
+
+def test_linear_mixed_output_dtype(cuda_dev):
+    """Fused QKV projection whose V columns are written as fp16 bit patterns (out_f16_from)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(19)
+    M, C = 700, 128
+    a = _rand_bf16(g, M, C)
+    w = _rand_bf16(g, 3 * C, C, scale=C ** -0.5)
+    out = torch.zeros(M, 3 * C, dtype=torch.bfloat16, device="cuda")
+    ops.linear(a, w, ops.make_epilogue(out=out, out_f16_from=2 * C))
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().T
+    check_close(out[:, :2 * C], want[:, :2 * C], what="q|k columns (bf16)")
+    v16 = out[:, 2 * C:].contiguous().view(torch.float16)
+    check_close(v16, want[:, 2 * C:], what="v columns (fp16)")
 
 
 def test_softmax_rows(cuda_dev):

@@ -56,7 +56,10 @@ def main():
                                   ("cross 64^2", 8, 10, 4096, 77), ("cross 32^2", 8, 20, 1024, 77)]:
         C = heads * 64
         q, k, v = rb(B * N, C), rb(B * Nk, C), rb(B * Nk, C)
-        ms = timeit(lambda: ops.attention(q, k, v, B, heads, N, Nk, 0.125))
+        f16 = Nk >= 128
+        if f16:
+            v = v.half()
+        ms = timeit(lambda: ops.attention(q, k, v, B, heads, N, Nk, 0.125, v_f16=f16))
         print("attention %-12s : %8.3f ms  %7.1f TFLOP/s" % (name, ms, 4.0 * B * heads * N * Nk * 64 / ms / 1e9))
     # ---- norms
     for name, B, HW, C in [("gn 128^2 320", 8, 16384, 320), ("gn 128^2 960", 8, 16384, 960), ("gn 32^2 1280", 8, 1024, 1280),
