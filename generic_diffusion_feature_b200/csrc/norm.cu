@@ -8,7 +8,7 @@
 namespace gdf {
 
 constexpr int kGnThreads = 256;
-constexpr int kGnMaxChunks = 64;
+constexpr int kGnMaxChunks = 256;
 constexpr int kGnMaxSlots = 2;  // channel slots (8 channels each) per thread: supports C <= 4096
 
 struct GnMap {      // thread -> (channel slot(s), pixel lane) mapping shared by both GroupNorm kernels
@@ -55,14 +55,22 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
     const bf16* base = x + ((long long)b * HW) * C + slot * 8;
-    for (int p = p0 + lane_p; p < p1; p += m.lanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * C));
+    auto acc = [&](const uint4& u) {
       float2 f;
       f = unpack_bf16x2(u.x); sum[0] += f.x; sq[0] += f.x * f.x; sum[1] += f.y; sq[1] += f.y * f.y;
       f = unpack_bf16x2(u.y); sum[2] += f.x; sq[2] += f.x * f.x; sum[3] += f.y; sq[3] += f.y * f.y;
       f = unpack_bf16x2(u.z); sum[4] += f.x; sq[4] += f.x * f.x; sum[5] += f.y; sq[5] += f.y * f.y;
       f = unpack_bf16x2(u.w); sum[6] += f.x; sq[6] += f.x * f.x; sum[7] += f.y; sq[7] += f.y * f.y;
+    };
+    int p = p0 + lane_p;
+    for (; p + 3 * m.lanes < p1; p += 4 * m.lanes) {   // four independent 128-bit loads in flight per thread
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * C));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (long long)(p + m.lanes) * C));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (long long)(p + 2 * m.lanes) * C));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (long long)(p + 3 * m.lanes) * C));
+      acc(u0); acc(u1); acc(u2); acc(u3);
     }
+    for (; p < p1; p += m.lanes) acc(__ldg(reinterpret_cast<const uint4*>(base + (long long)p * C)));
     // fold the 8 channels into their groups (a slot may straddle group boundaries)
     int g_prev = (slot * 8) / cpg;
     float gs = 0.f, gq = 0.f;
@@ -89,28 +97,37 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, 
   }
 }
 
-// Pass 2: reduce partials (double), normalise, affine, optional SiLU.
+// Pass 1b: one block per image reduces the per-chunk partials in double precision -> (mean, rstd) per group.
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int HW, int C,
+                                          int G, int nchunks, float eps) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, q = 0.0;
+  const float* src = partial + ((long long)b * nchunks * G + g) * 2;
+  for (int c = 0; c < nchunks; ++c) {
+    s += (double)src[(long long)c * G * 2];
+    q += (double)src[(long long)c * G * 2 + 1];
+  }
+  const double n = (double)HW * (C / G);
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[(b * G + g) * 2] = (float)mean;
+  stats[(b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// Pass 2: normalise, affine, optional SiLU.
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ partial, int HW, int C, int G,
-                       int nchunks, float eps, int silu) {
+                       int nchunks, int silu) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const GnMap m = gn_map(C);
   const int cpg = C / G;
   if (threadIdx.x < G) {
-    double s = 0.0, q = 0.0;
-    const float* src = partial + ((long long)b * nchunks * G + threadIdx.x) * 2;
-    for (int c = 0; c < nchunks; ++c) {
-      s += (double)src[(long long)c * G * 2];
-      q += (double)src[(long long)c * G * 2 + 1];
-    }
-    const double n = (double)HW * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[threadIdx.x] = partial[(b * G + threadIdx.x) * 2];       // `partial` is the finalised stats array here
+    s_rstd[threadIdx.x] = partial[(b * G + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   const int pix_per_chunk = (HW + nchunks - 1) / nchunks;
@@ -131,6 +148,7 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
       sh[j] = __ldg(beta + c) - s_mean[g] * a;
     }
     const long long base = ((long long)b * HW) * C + slot * 8;
+#pragma unroll 4
     for (int p = p0 + lane_p; p < p1; p += m.lanes) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)p * C));
       float v[8];
@@ -157,18 +175,23 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
 cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
                              float eps, bool silu, float* workspace, cudaStream_t stream) {
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > kGnThreads * kGnMaxSlots) return cudaErrorInvalidValue;
-  int nchunks = (HW + 31) / 32;
+  // enough chunks to fill the chip (>= ~4 blocks per SM across the batch), at least 32 pixels per chunk
+  int nchunks = (148 * 4 + B - 1) / B;
+  if (nchunks > (HW + 31) / 32) nchunks = (HW + 31) / 32;
   if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
   if (nchunks < 1) nchunks = 1;
   dim3 grid(nchunks, B);
+  float* stats = workspace + (size_t)B * kGnMaxChunks * G * 2;
   groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, workspace, HW, C, G, nchunks);
-  groupnorm_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, y, gamma, beta, workspace, HW, C, G, nchunks, eps,
-                                                          silu ? 1 : 0);
+  groupnorm_finalize_kernel<<<B, 64, 0, stream>>>(workspace, stats, HW, C, G, nchunks, eps);
+  groupnorm_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, y, gamma, beta, stats, HW, C, G, nchunks, silu ? 1 : 0);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
-// One warp per token row; two passes over the row (second pass hits L1).
+// One warp per token row; the row lives in registers between the statistics and the normalisation (one global
+// read, one write). kV = 128-bit vectors per lane (C <= 256 * kV).
+template <int kV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long long M, int C, float eps, const float* __restrict__ mod_scale,
@@ -176,16 +199,22 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* 
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  const bf16* xr = x + row * C;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
   const int nv = C / 8;
+  uint4 u[kV];
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
+    u[i] = (v < nv) ? __ldg(xr + v) : make_uint4(0, 0, 0, 0);
+  }
   float s = 0.f, q = 0.f;
-  for (int v = lane; v < nv; v += 32) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
     float2 f;
-    f = unpack_bf16x2(u.x); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
-    f = unpack_bf16x2(u.y); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
-    f = unpack_bf16x2(u.z); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
-    f = unpack_bf16x2(u.w); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u[i].x); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u[i].y); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u[i].z); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u[i].w); s += f.x + f.y; q += f.x * f.x + f.y * f.y;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -202,20 +231,31 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* 
     ms = mod_scale + b * C;
     mh = mod_shift + b * C;
   }
-  bf16* yr = y + row * C;
-  for (int v = lane; v < nv; v += 32) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + v);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
+    if (v >= nv) continue;
     float t[8];
     float2 f;
-    f = unpack_bf16x2(u.x); t[0] = f.x; t[1] = f.y;
-    f = unpack_bf16x2(u.y); t[2] = f.x; t[3] = f.y;
-    f = unpack_bf16x2(u.z); t[4] = f.x; t[5] = f.y;
-    f = unpack_bf16x2(u.w); t[6] = f.x; t[7] = f.y;
+    f = unpack_bf16x2(u[i].x); t[0] = f.x; t[1] = f.y;
+    f = unpack_bf16x2(u[i].y); t[2] = f.x; t[3] = f.y;
+    f = unpack_bf16x2(u[i].z); t[4] = f.x; t[5] = f.y;
+    f = unpack_bf16x2(u[i].w); t[6] = f.x; t[7] = f.y;
+    float gm[8], bt[8];
+    if (gamma) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+      gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+      bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
       float r = (t[j] - mean) * rstd;
-      if (gamma) r = r * __ldg(gamma + c) + __ldg(beta + c);
+      if (gamma) r = r * gm[j] + bt[j];
       if (ms) r = r * (1.f + __ldg(ms + c)) + __ldg(mh + c);
       t[j] = r;
     }
@@ -224,7 +264,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* 
     o.y = pack_bf16x2(t[2], t[3]);
     o.z = pack_bf16x2(t[4], t[5]);
     o.w = pack_bf16x2(t[6], t[7]);
-    reinterpret_cast<uint4*>(yr)[v] = o;
+    yr[v] = o;
   }
 }
 
@@ -234,8 +274,18 @@ cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const f
   if (C % 8 != 0) return cudaErrorInvalidValue;
   const int rows_per_block = 8;
   const long long blocks = (M + rows_per_block - 1) / rows_per_block;
-  layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift,
-                                                        rows_per_batch > 0 ? rows_per_batch : 1);
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : 1;
+  const int nv = C / 8;
+  if (nv <= 64)
+    layernorm_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+  else if (nv <= 96)
+    layernorm_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+  else if (nv <= 160)
+    layernorm_kernel<5><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+  else if (nv <= 384)
+    layernorm_kernel<12><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
