@@ -143,4 +143,13 @@ int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, i
                                   static_cast<cudaStream_t>(stream)));
 }
 
+int64_t gdf_correspond_workspace_floats(int n, int hw, int C) { return (int64_t)corr_workspace_floats(n, hw, C); }
+
+int gdf_correspond(const void* stack_src, const void* stack_tgt, int C, int hw, int load_hw, const void* query_yx,
+                   int n, void* idx_out, void* workspace, void* stream) {
+  return launch_correspond(static_cast<const __half*>(stack_src), static_cast<const __half*>(stack_tgt), C, hw, load_hw,
+                           static_cast<const int*>(query_yx), n, static_cast<long long*>(idx_out),
+                           static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -306,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n);
+    const uint32_t idesc = p.in_f16 ? umma_idesc_f16(kBlockM, p.block_n) : umma_idesc_bf16(kBlockM, p.block_n);
     int s = 0;
     uint32_t ph = 0;
     int as = 0;

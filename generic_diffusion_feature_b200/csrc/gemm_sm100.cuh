@@ -38,6 +38,7 @@ struct GemmParams {
   int num_stages;       // operand ring depth: kPipeBytes / (16 KB + block_n * 128 B), <= kMaxStages
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
+  int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)
   int a_batched;        // 1: A has a batch dimension, 0: shared across the batch
   int b_batched;        // 1: B has a batch dimension, 0: shared
   // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows

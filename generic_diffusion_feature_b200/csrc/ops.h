@@ -32,6 +32,7 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   __half* cap_pre = nullptr; int ld_cap_pre = 0;
   CaptureSeg cap[3] = {};
   int num_cap = 0;
+  bool in_f16 = false;              // operands are fp16 instead of bf16
   bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };
 
@@ -113,5 +114,14 @@ struct ResizeSrc {
 // squared L2 norm per pixel of the NHWC stack.
 cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, int OH, int OW, int Ctot,
                                  __half* out_nhwc, __half* out_nchw, float* sumsq, cudaStream_t stream);
+
+// ---- correspondence (stack.cu): cosine-similarity arg-max of n query points against a target stack, evaluated in
+// the exact low-resolution form of correspondence_utils.find_nn_source_correspondences (:113-138):
+//   sims_up(i, p) = bilinear_p( q_i . F2 ) / | bilinear_p(F2) |   (bilinear interpolation is linear)
+// stack1 / stack2: fp16 NHWC [hw*hw, C]; query_yx: int32 (n, 2) positions on the load x load grid;
+// idx_out: int64 (n) flat index into the load x load grid. workspace floats: corr_workspace_floats().
+size_t corr_workspace_floats(int n, int hw, int C);
+int launch_correspond(const __half* stack1, const __half* stack2, int C, int hw, int load, const int* query_yx, int n,
+                      long long* idx_out, float* workspace, cudaStream_t stream);
 
 }  // namespace gdf

@@ -139,6 +139,7 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
   p.batch = batch;
   p.a_mode = kALinear;
+  p.in_f16 = e.in_f16 ? 1 : 0;
   p.a_batched = (batch > 1 && a_batch_stride != 0) ? 1 : 0;
   p.b_batched = (w_batch_stride != 0) ? 1 : 0;
   fill_epilogue(p, e);

@@ -159,3 +159,206 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
 }
 
 }  // namespace gdf
+
+// =============================================================================================== correspondence
+// find_nn_source_correspondences (correspondence/correspondence/correspondence_utils.py:113-138) upsamples both
+// stacks to load x load, gathers the query rows, L2-normalises, multiplies (n x load^2 x C GEMM) and takes the
+// arg-max. Bilinear interpolation is linear, so the same similarities are obtained from the LOW-resolution product
+// q . F2^T (n x hw^2 x C, 16x fewer FLOPs at 128 -> 512) interpolated per query, divided by the norm of the
+// interpolated target vector, which follows from 5 Gram maps of neighbouring low-resolution pixels.
+namespace gdf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// q[i, :] = bilinear_up(stack1)[query_i] as fp16 (one warp per query)
+__global__ void __launch_bounds__(256)
+corr_gather_queries_kernel(const __half* __restrict__ s1, int C, int hw, int load, const int* __restrict__ qyx, int n,
+                           __half* __restrict__ q) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float sc = (float)hw / (float)load;
+  const BilinearTap ty = bilinear_tap(qyx[2 * i], hw, sc), tx = bilinear_tap(qyx[2 * i + 1], hw, sc);
+  const int C8 = C / 8;
+  const uint4* b = reinterpret_cast<const uint4*>(s1);
+  for (int v = lane; v < C8; v += 32) {
+    const uint4 v00 = __ldg(b + ((long long)ty.i0 * hw + tx.i0) * C8 + v);
+    const uint4 v01 = __ldg(b + ((long long)ty.i0 * hw + tx.i1) * C8 + v);
+    const uint4 v10 = __ldg(b + ((long long)ty.i1 * hw + tx.i0) * C8 + v);
+    const uint4 v11 = __ldg(b + ((long long)ty.i1 * hw + tx.i1) * C8 + v);
+    float o[8];
+    blend8(v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1, o);
+    uint4 u;
+    u.x = pack_f16x2(o[0], o[1]);
+    u.y = pack_f16x2(o[2], o[3]);
+    u.z = pack_f16x2(o[4], o[5]);
+    u.w = pack_f16x2(o[6], o[7]);
+    reinterpret_cast<uint4*>(q + (long long)i * C)[v] = u;
+  }
+}
+
+// Gram maps of stack2: g[0] = <f,f>, g[1] = <f, right>, g[2] = <f, down>, g[3] = <f, down-right>,
+// g[4] = <right, down> (one warp per low-resolution pixel; neighbours clamped at the border)
+__global__ void __launch_bounds__(256)
+corr_gram_kernel(const __half* __restrict__ s2, int C, int hw, float* __restrict__ gram) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= hw * hw) return;
+  const int y = p / hw, x = p % hw;
+  const int x1 = min(x + 1, hw - 1), y1 = min(y + 1, hw - 1);
+  const int C8 = C / 8;
+  const uint4* b = reinterpret_cast<const uint4*>(s2);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+  for (int v = lane; v < C8; v += 32) {
+    const uint4 f = __ldg(b + ((long long)y * hw + x) * C8 + v);
+    const uint4 r = __ldg(b + ((long long)y * hw + x1) * C8 + v);
+    const uint4 d = __ldg(b + ((long long)y1 * hw + x) * C8 + v);
+    const uint4 e = __ldg(b + ((long long)y1 * hw + x1) * C8 + v);
+    const __half2* pf = reinterpret_cast<const __half2*>(&f);
+    const __half2* pr = reinterpret_cast<const __half2*>(&r);
+    const __half2* pd = reinterpret_cast<const __half2*>(&d);
+    const __half2* pe = reinterpret_cast<const __half2*>(&e);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 ff = __half22float2(pf[j]), fr = __half22float2(pr[j]);
+      const float2 fd = __half22float2(pd[j]), fe = __half22float2(pe[j]);
+      a0 += ff.x * ff.x + ff.y * ff.y;
+      a1 += ff.x * fr.x + ff.y * fr.y;
+      a2 += ff.x * fd.x + ff.y * fd.y;
+      a3 += ff.x * fe.x + ff.y * fe.y;
+      a4 += fr.x * fd.x + fr.y * fd.y;
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+  if (lane == 0) {
+    const int n = hw * hw;
+    gram[p] = a0;
+    gram[n + p] = a1;
+    gram[2 * n + p] = a2;
+    gram[3 * n + p] = a3;
+    gram[4 * n + p] = a4;
+  }
+}
+
+// inverse norm of the bilinearly interpolated target vector at every load x load position
+__global__ void __launch_bounds__(256)
+corr_invnorm_kernel(const float* __restrict__ gram, int hw, int load, float* __restrict__ invnorm) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= load * load) return;
+  const int oy = p / load, ox = p % load;
+  const float sc = (float)hw / (float)load;
+  const BilinearTap ty = bilinear_tap(oy, hw, sc), tx = bilinear_tap(ox, hw, sc);
+  const int n = hw * hw;
+  const float* G0 = gram;
+  const float* Gx = gram + n;
+  const float* Gy = gram + 2 * n;
+  const float* Gd = gram + 3 * n;
+  const float* Ga = gram + 4 * n;
+  const int i00 = ty.i0 * hw + tx.i0, i01 = ty.i0 * hw + tx.i1, i10 = ty.i1 * hw + tx.i0, i11 = ty.i1 * hw + tx.i1;
+  const bool dx = tx.i1 != tx.i0, dy = ty.i1 != ty.i0;
+  const float a00 = ty.w0 * tx.w0, a01 = ty.w0 * tx.w1, a10 = ty.w1 * tx.w0, a11 = ty.w1 * tx.w1;
+  // pairwise inner products of the four taps (coinciding taps at the border fall back to the self product)
+  const float g0001 = dx ? Gx[i00] : G0[i00];
+  const float g1011 = dx ? Gx[i10] : G0[i10];
+  const float g0010 = dy ? Gy[i00] : G0[i00];
+  const float g0111 = dy ? Gy[i01] : G0[i01];
+  const float g0011 = (dx && dy) ? Gd[i00] : (dx ? Gx[i00] : (dy ? Gy[i00] : G0[i00]));
+  const float g0110 = (dx && dy) ? Ga[i00] : (dx ? Gx[i00] : (dy ? Gy[i00] : G0[i00]));
+  float s = a00 * a00 * G0[i00] + a01 * a01 * G0[i01] + a10 * a10 * G0[i10] + a11 * a11 * G0[i11];
+  s += 2.f * (a00 * a01 * g0001 + a10 * a11 * g1011 + a00 * a10 * g0010 + a01 * a11 * g0111 + a00 * a11 * g0011 +
+              a01 * a10 * g0110);
+  invnorm[p] = rsqrtf(fmaxf(s, 1e-30f));
+}
+
+// arg-max over the load x load grid of bilinear(sims_lr[i]) * invnorm; one block per query, first index wins ties
+__global__ void __launch_bounds__(256)
+corr_argmax_kernel(const float* __restrict__ sims, const float* __restrict__ invnorm, int hw, int load, int n,
+                   long long* __restrict__ idx_out) {
+  extern __shared__ float srow[];   // hw*hw low-resolution similarities of this query
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  const int i = blockIdx.x;
+  const int nlr = hw * hw;
+  for (int k = threadIdx.x; k < nlr; k += blockDim.x) srow[k] = sims[(long long)i * nlr + k];
+  __syncthreads();
+  const float sc = (float)hw / (float)load;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int row = threadIdx.x >> 5; row < load; row += 8) {
+    const BilinearTap ty = bilinear_tap(row, hw, sc);
+    const float* r0 = srow + ty.i0 * hw;
+    const float* r1 = srow + ty.i1 * hw;
+    for (int ox = threadIdx.x & 31; ox < load; ox += 32) {
+      const BilinearTap tx = bilinear_tap(ox, hw, sc);
+      const float v = (ty.w0 * (tx.w0 * r0[tx.i0] + tx.w1 * r0[tx.i1]) + ty.w1 * (tx.w0 * r1[tx.i0] + tx.w1 * r1[tx.i1])) *
+                      __ldg(invnorm + row * load + ox);
+      const int p = row * load + ox;
+      if (v > best || (v == best && p < best_i)) {
+        best = v;
+        best_i = p;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) {
+      best = ov;
+      best_i = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_v[threadIdx.x >> 5] = best;
+    red_i[threadIdx.x >> 5] = best_i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (red_v[w] > best || (red_v[w] == best && red_i[w] < best_i)) {
+        best = red_v[w];
+        best_i = red_i[w];
+      }
+    idx_out[i] = best_i;
+  }
+}
+
+size_t corr_workspace_floats(int n, int hw, int C) {
+  // q (fp16, n*C halves) | sims (n*hw*hw) | gram (5*hw*hw) | invnorm: sized by the caller's load (<= 1024^2)
+  return (size_t)n * C / 2 + 64 + (size_t)n * hw * hw + 5 * (size_t)hw * hw + (size_t)1024 * 1024;
+}
+
+int launch_correspond(const __half* stack1, const __half* stack2, int C, int hw, int load, const int* query_yx, int n,
+                      long long* idx_out, float* workspace, cudaStream_t stream) {
+  if (C % 8 != 0 || load > 1024 || hw * hw * 4 > 200 * 1024) return fail(GDF_ERR_SHAPE, "launch_correspond: bad shape");
+  __half* q = reinterpret_cast<__half*>(workspace);
+  float* sims = workspace + ((size_t)n * C / 2 + 63) / 64 * 64;
+  float* gram = sims + (size_t)n * hw * hw;
+  float* invnorm = gram + 5 * (size_t)hw * hw;
+  corr_gather_queries_kernel<<<(n + 7) / 8, 256, 0, stream>>>(stack1, C, hw, load, query_yx, n, q);
+  corr_gram_kernel<<<(hw * hw + 7) / 8, 256, 0, stream>>>(stack2, C, hw, gram);
+  corr_invnorm_kernel<<<(load * load + 255) / 256, 256, 0, stream>>>(gram, hw, load, invnorm);
+  // similarity GEMM on the tensor cores: sims[n, hw*hw] = q[n, C] . stack2[hw*hw, C]^T (fp16 operands, fp32 out)
+  GemmLaunch g;
+  Epilogue e;
+  e.in_f16 = true;
+  e.out_f32 = sims;
+  e.ld_out_f32 = hw * hw;
+  GDF_TRY(build_linear(&g, reinterpret_cast<const bf16*>(q), n, C, C, reinterpret_cast<const bf16*>(stack2), hw * hw,
+                       C, e));
+  GDF_CUDA(launch_gemm(g, stream));
+  static bool attr = false;
+  if (!attr) {
+    GDF_CUDA(cudaFuncSetAttribute(corr_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  corr_argmax_kernel<<<n, 256, (size_t)hw * hw * 4, stream>>>(sims, invnorm, hw, load, n, idx_out);
+  GDF_CUDA(cudaGetLastError());
+  return GDF_OK;
+}
+
+}  // namespace gdf

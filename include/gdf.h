@@ -204,6 +204,16 @@ typedef struct gdf_resize_src {
 int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, int OW, int Ctot, void* out_nhwc_dev,
                          void* out_nchw_dev, void* sumsq_dev, void* stream);
 
+/* Correspondence (correspondence/correspondence/correspondence_utils.py:113-146 find_nn_source_correspondences):
+ * for n query points (int32 (n,2) [y,x], already rounded/clipped like points_to_idxs :140-146) on the
+ * load_hw x load_hw grid of the source image, the flat index (int64, y*load_hw + x) of the most cosine-similar
+ * position of the target image. stacks: fp16 NHWC [hw*hw, C] (gdf_op_resize_concat, one image each).
+ * Evaluated in the exact low-resolution form (similarity GEMM n x hw^2 x C on the tensor cores + interpolated
+ * arg-max); workspace: fp32, gdf_correspond_workspace_floats(n, hw, C). */
+int64_t gdf_correspond_workspace_floats(int n, int hw, int C);
+int gdf_correspond(const void* stack_src_dev, const void* stack_tgt_dev, int C, int hw, int load_hw,
+                   const void* query_yx_dev, int n, void* idx_out_dev, void* workspace_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
