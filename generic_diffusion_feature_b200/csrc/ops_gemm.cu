@@ -158,6 +158,8 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   }
   p.num_stages = kPipeBytes / (kStageBytesA + block_n * kBlockK * 2);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (env_int("GDF_MAX_STAGES", 0) > 0 && p.num_stages > env_int("GDF_MAX_STAGES", 0))
+    p.num_stages = env_int("GDF_MAX_STAGES", 0);   // tuning knob
   GDF_TRY(setup_stores(g));
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }

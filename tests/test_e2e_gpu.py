@@ -115,3 +115,34 @@ def test_cuda_matches_reference_vendored_unet_golden(cuda_dev, fixture, version,
     rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})
     bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
     assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+
+
+def test_full_size_sdxl_1024_parity(cuda_dev):
+    """BASELINE.json configs[1] at full size (SDXL 1024x1024, all 472 non-map activations, batch 1) against the CPU
+    oracle on the box's host cores (~10 s on 16 cores): every map cosine >= 0.999, max-relative error <= 5e-2."""
+    import os
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    torch.set_num_threads(os.cpu_count())
+    ucfg, vcfg = models.UNET_CONFIGS["xl"], models.VAE_CONFIGS["xl"]
+    sd = models.synthetic_state_dict("xl", "cuda:0")      # CUDA generator: fast for 2.6 B parameters
+    image, ctx, pooled, ev, eq = make_inputs(1, 1024, 2048, 1280)
+    ids = _unet_feature_ids(ucfg)
+    assert len(ids) == 472
+    layer = {i: True for i in ids}
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd)
+    fe = FeatureExtractor(layer, "xl", "cuda:0", img_size=1024, external_model=pipe)
+    got = fe.extract((ctx, ctx, pooled, pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    torch.cuda.synchronize()
+    got = {k: v.float().cpu() for k, v in got.items()}
+    sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    del sd, fe, pipe
+    unet, vae = build_oracle(ucfg, vcfg, sd_cpu)
+    store = O.FeatureStore(layer)
+    O.attach_gatherers(unet, store)
+    want, _, _ = O.extract("xl", unet, vae, store, image, ctx, pooled, ev, eq, t=50, img_size=1024)
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "full-size maps out of tolerance: %s" % bad[:8]
