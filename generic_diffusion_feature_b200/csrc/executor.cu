@@ -517,8 +517,18 @@ class Builder {
     });
   }
   void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int B,
-                 int heads, int Nq, int Nk, float scale, int v_f16) {
+                 int heads, int Nq, int Nk, float scale, int v_f16, int head_dim) {
     if (dry || err) return;
+    if (head_dim != 64) {
+      ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * head_dim,
+               "attention heads=" + std::to_string(heads) + " d=" + std::to_string(head_dim) + " Nq=" +
+                   std::to_string(Nq) + " Nk=" + std::to_string(Nk));
+      ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_attention_generic(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, head_dim, scale, rc.stream));
+        return 0;
+      });
+      return;
+    }
     ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * 64.0,
              "attention heads=" + std::to_string(heads) + " Nq=" + std::to_string(Nq) + " Nk=" + std::to_string(Nk));
     ops->push_back([=](const RunCtx& rc) -> int {
@@ -617,7 +627,8 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
   const long long M = (long long)B * N;
   const float scale = 1.f / sqrtf((float)(C / heads));
   // ---- self attention
-  const bool self_tc = attention_uses_tcgen05(N);
+  const int hd = C / heads;
+  const bool self_tc = (hd == 64) && attention_uses_tcgen05(N);
   bf16* n1 = b.buf(M, C);
   b.layernorm(hs, n1, wp + ".norm1", M, C, 1e-5f);
   const bf16* wqkv = b.rows_bf16(wp + ".attn1#qkv", {wp + ".attn1.to_q.weight", wp + ".attn1.to_k.weight",
@@ -636,7 +647,7 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
   }
   b.rel(n1);
   bf16* ao = b.buf(M, C);
-  b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, self_tc ? 1 : 0);
+  b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, self_tc ? 1 : 0, hd);
   b.rel(qkv);
   bf16* hs1 = b.buf(M, C);
   {
@@ -673,7 +684,7 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     b.linear(h->ctx_bf16, Mc, ctx_dim, ctx_dim, wkv, 2 * C, e);
   }
   bf16* ao2 = b.buf(M, C);
-  b.attention(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, h->ctx_len, scale, 0);
+  b.attention(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, h->ctx_len, scale, 0, hd);
   b.rel(q2);
   b.rel(kv);
   bf16* hs2 = b.buf(M, C);

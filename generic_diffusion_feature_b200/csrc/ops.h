@@ -76,6 +76,10 @@ cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const f
 cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, int v_f16, cudaStream_t stream);
 bool attention_uses_tcgen05(int Nk);
+// head dims other than 64 (multiple of 8, <= 160): mma.sync kernel templated on the padded head dim
+cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O,
+                                     int ldo, int B, int heads, int Nq, int Nk, int D, float scale,
+                                     cudaStream_t stream);
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);

@@ -98,7 +98,7 @@ def attention(q, k, v, B, heads, Nq, Nk, scale, head_dim=64, v_f16=False):
     """q: bf16 [B*Nq, >=heads*64] (pitch q.stride(0)); k, v: [B*Nk, ...]. Returns bf16 [B*Nq, heads*64].
     v_f16: v is a float16 tensor (tcgen05 kernel, Nk >= 128); otherwise bf16 (mma.sync kernel)."""
     lib = _lib.load()
-    o = torch.empty(B * Nq, heads * head_dim, dtype=torch.bfloat16, device=q.device)
+    o = torch.zeros(B * Nq, heads * head_dim, dtype=torch.bfloat16, device=q.device)
     check(lib.gdf_op_attention(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), o.stride(0), B,
                                heads, Nq, Nk, head_dim, scale, int(v_f16), stream_ptr()))
     return o

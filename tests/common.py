@@ -16,6 +16,9 @@ TINY_XL = dict(block_out=(64, 128, 256), down_attn=(0, 1, 1), up_attn=(1, 1, 0),
                heads=(1, 2, 4), ctx_dim=128, linear_proj=True, add_time_dim=32, add_in=64 + 6 * 32, eps=1e-5)
 TINY_21 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
                heads=(1, 2, 4, 4), ctx_dim=128, linear_proj=True, add_time_dim=0, add_in=0, eps=1e-5)
+# SD-1.5 topology: 1x1-conv proj_in/out, 8 heads per level -> head dims 8 / 16 / 32 / 32 (generic attention kernel)
+TINY_15 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
+               heads=(8, 8, 8, 8), ctx_dim=128, linear_proj=False, add_time_dim=0, add_in=0, eps=1e-5)
 TINY_VAE = dict(block_out=(64, 64, 128, 128), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025)
 
 

@@ -6,7 +6,7 @@ max-relative error (max |diff| / max |ref|) is reported and bounded at 5e-2 for 
 import pytest
 import torch
 
-from common import O, TINY_21, TINY_VAE, TINY_XL, build_oracle, compare_maps, make_inputs
+from common import O, TINY_15, TINY_21, TINY_VAE, TINY_XL, build_oracle, compare_maps, make_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -60,6 +60,11 @@ def test_tiny_xl_batch3_img256(cuda_dev):
 
 def test_tiny_21_full_set(cuda_dev):
     _run_case("2-1", TINY_21, batch=2, img=128)
+
+
+def test_tiny_15_full_set(cuda_dev):
+    """SD-1.5 topology: conv proj_in/out, PNDM timestep (t=50 -> 51), head dims != 64."""
+    _run_case("1-5", TINY_15, batch=2, img=128)
 
 
 def test_unknown_id_and_unbuilt_features(cuda_dev):

@@ -231,6 +231,25 @@ def test_attention64(cuda_dev, B, heads, Nq, Nk, v_f16):
     check_close(o, want, what="attention B%d h%d %dx%d f16=%d" % (B, heads, Nq, Nk, v_f16))
 
 
+@pytest.mark.parametrize("D,heads,Nq,Nk", [(40, 8, 1024, 1024), (80, 8, 256, 256), (160, 8, 200, 77), (72, 16, 512, 300),
+                                          (8, 8, 256, 256), (32, 4, 100, 100)])
+def test_attention_other_head_dims(cuda_dev, D, heads, Nq, Nk):
+    """SD-1.5 (40/80/160) and PixArt (72) head dims through the padded-head-dim kernel."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(28)
+    B, C = 2, heads * D
+    q = _rand_bf16(g, B * Nq, C)
+    kv = _rand_bf16(g, B * Nk, 2 * C)
+    k, v = kv[:, :C], kv[:, C:]
+    o = ops.attention(q, k, v, B, heads, Nq, Nk, D ** -0.5, head_dim=D)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Nq, heads, D).transpose(1, 2)
+    kf = k.float().reshape(B, Nk, heads, D).transpose(1, 2)
+    vf = v.float().reshape(B, Nk, heads, D).transpose(1, 2)
+    want = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Nq, C)
+    check_close(o, want, what="attention d=%d" % D)
+
+
 def test_attention_peaked_softmax(cuda_dev):
     """Large score range (peaked rows) through the half2-exp path of the tcgen05 kernel."""
     ops = _ops()
