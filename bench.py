@@ -164,6 +164,8 @@ def run_ours(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line of the contract
         dist.init_process_group("nccl", device_id=torch.device(dev))
     B = args.batch
     pipe = get_diffusion_model("xl", "float16", device=dev, weight_device=dev)
