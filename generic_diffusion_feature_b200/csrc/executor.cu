@@ -431,8 +431,8 @@ class Builder {
     GemmParams& p = g.p;
     {
       char lbl[160];
-      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d st=%d batch=%d act=%d res=%d caps=%d pre=%d tma=%d tiles=%d",
-               p.a_mode, p.M, p.N, p.K, p.block_n, p.num_stages, p.batch, p.act, p.residual ? 1 : 0, caps.n,
+      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d cg=%d st=%d batch=%d act=%d res=%d caps=%d pre=%d tma=%d tiles=%d",
+               p.a_mode, p.M, p.N, p.K, p.block_n, p.cta_group, p.num_stages, p.batch, p.act, p.residual ? 1 : 0, caps.n,
                caps.pre >= 0 ? 1 : 0, p.tma_store, p.batch * p.num_m_tiles * p.num_n_tiles);
       ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
                               (double)p.batch, lbl);

@@ -213,22 +213,122 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
   toggle ^= 1;
 }
 
+// ---------------------------------------------------------------------------------- lean epilogue (fast path)
+// The epilogue is instruction-issue bound at small K (profiles/r01_s3_gemm_epilogue.md): the fast path handles full,
+// 16-byte-aligned 32-column chunks with vector loads and no per-element predicates; everything else takes the
+// generic path above.
+__device__ __forceinline__ void ldg_f32x32(const float* src, float* dst) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+    dst[q * 4 + 0] = f.x; dst[q * 4 + 1] = f.y; dst[q * 4 + 2] = f.z; dst[q * 4 + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void add_f32x32(const float* src, float* v) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+    v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+  }
+}
+__device__ __forceinline__ void mul_f32x32(const float* src, float* v) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+    v[q * 4 + 0] *= f.x; v[q * 4 + 1] *= f.y; v[q * 4 + 2] *= f.z; v[q * 4 + 3] *= f.w;
+  }
+}
+// Phi(g) * g with the Abramowitz-Stegun 7.1.26 erfc tail: gelu_erf(g) = g * (g >= 0 ? 1 - h : h),
+// h = 0.5 * poly(t) * t * exp(-g^2 / 2), t = 1 / (1 + 0.3275911 |g| / sqrt(2)); |abs err| <= 1e-7.
+__device__ __forceinline__ float gelu_erf_lean(float g) {
+  const float ag = fabsf(g);
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678f, ag, 1.f));
+  float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx(g * g * (-0.5f * 1.4426950408889634f));
+  const float h = q * t * e;
+  return g * (g >= 0.f ? 1.f - h : h);
+}
+
+template <bool kF16>
+__device__ __forceinline__ void stage_chunk(uint8_t* buf, const int (&swz)[4], const float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    if (kF16) {
+      u.x = pack_f16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_f16x2(v[c * 8 + 2], v[c * 8 + 3]);
+      u.z = pack_f16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_f16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    } else {
+      u.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+      u.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    }
+    *reinterpret_cast<uint4*>(buf + swz[c]) = u;
+  }
+}
+__device__ __forceinline__ void issue_store(const CUtensorMap* map, const uint8_t* buf, int col, const StoreCoord& sc) {
+  if (sc.conv) tma_store_4d(map, buf, col, sc.c1, sc.c2, sc.c3);
+  else tma_store_3d(map, buf, col, sc.c1, sc.c2);
+}
+// Stage 32x32 values once and send them to up to two destinations of the same 16-bit type.
+template <bool kF16>
+__device__ __forceinline__ void stage_and_store2(const CUtensorMap* map_a, int col_a, const CUtensorMap* map_b,
+                                                 int col_b, uint8_t* stg_warp, int& toggle, int lane,
+                                                 const int (&swz)[4], const float* v, const StoreCoord& sc) {
+  uint8_t* buf = stg_warp + toggle * 2048;
+  if (lane == 0) bulk_wait_read<1>();   // the store group that used this buffer two groups ago has drained
+  __syncwarp();
+  stage_chunk<kF16>(buf, swz, v);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    issue_store(map_a, buf, col_a, sc);
+    if (map_b) issue_store(map_b, buf, col_b, sc);
+    bulk_commit();
+  }
+  toggle ^= 1;
+}
+
+struct ResidualRegs { uint4 u[4]; };
+__device__ __forceinline__ void residual_prefetch(ResidualRegs& r, const __nv_bfloat16* src) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r.u[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+}
+__device__ __forceinline__ void residual_add(const ResidualRegs& r, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 f;
+    f = unpack_bf16x2(r.u[q].x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+    f = unpack_bf16x2(r.u[q].y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+    f = unpack_bf16x2(r.u[q].z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+    f = unpack_bf16x2(r.u[q].w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+  }
+}
+
+// CG = 1: one CTA per 128 x block_n tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x block_n
+// tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 A rows and HALF of the B rows, the leader (even)
+// CTA issues the MMAs for both, and each CTA's TMEM receives its own 128 accumulator rows.  Operand bytes pulled
+// from L2 per MMA cycle drop from (128 + bn) to (128 + bn / 2) rows, which is what bounds this kernel.
+template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = kStageBytesA + p.block_n * kBlockK * 2;
+  const int b_rows = p.block_n / CG;                         // B rows staged by this CTA
+  const int stage_bytes = kStageBytesA + b_rows * kBlockK * 2;
   uint8_t* stg = smem + kPipeBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes + kStagingBytes);
-  uint64_t* full_bar = bars;                                 // [kMaxStages]
+  uint64_t* full_bar = bars;                                 // [kMaxStages]  (CG = 2: the leader's are used)
   uint64_t* empty_bar = bars + kMaxStages;                   // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kAccStages]
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + kAccStages; // [kAccStages]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + kAccStages; // [kAccStages]  (CG = 2: the leader's are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nstages = p.num_stages;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -242,101 +342,131 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpilogueWarps);
+      mbar_init(&tempty_bar[i], CG * kEpilogueWarps);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.batch * p.num_m_tiles * p.num_n_tiles;
-  const uint32_t stage_tx_bytes = (kBlockM + p.block_n) * kBlockK * 2;
+  // work unit = CG vertically adjacent 128-row tiles x one block_n column tile
+  const int num_m_units = (p.num_m_tiles + CG - 1) / CG;
+  const int total_units = p.batch * num_m_units * p.num_n_tiles;
+  const int unit0 = blockIdx.x / CG;
+  const int unit_step = gridDim.x / CG;
+  const uint32_t stage_tx_bytes = (CG * kBlockM + p.block_n) * kBlockK * 2;   // bytes landing per stage, all CTAs
+
+  // register rebalancing: producer / MMA / allocator warpgroup needs few registers, the two epilogue warpgroups many
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (every CTA loads its own A rows / B half)
     int s = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    for (int t = unit0; t < total_units; t += unit_step) {
+      const int mu = t % num_m_units;
+      const int r0 = t / num_m_units;
+      const int n_tile = r0 % p.num_n_tiles;
+      const int bz = r0 / p.num_n_tiles;
+      const int m_tile = mu * CG + (int)cta_rank;
       int x0 = 0, y0 = 0, b0 = 0;
       if (p.a_mode != kALinear) {
-        const int xt = tc.m_tile % p.tiles_x;
-        const int r = tc.m_tile / p.tiles_x;
+        const int xt = m_tile % p.tiles_x;
+        const int r = m_tile / p.tiles_x;
         const int yt = r % p.tiles_y;
         const int bt = r / p.tiles_y;
         x0 = xt * p.tw;
         y0 = yt * p.th;
-        b0 = bt * p.tb;
+        b0 = bt * p.tb;           // >= B_img for the padding tile of an odd tile count: TMA zero-fills
       }
+      const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[s], stage_tx_bytes);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_tx_bytes);
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + kStageBytesA;
           if (p.a_mode == kALinear) {
-            tma_load_3d(a_dst, &maps.a, &full_bar[s], kb * kBlockK, tc.m_tile * kBlockM, p.a_batched ? tc.bz : 0);
+            if (CG == 2) tma_load_3d_pair(a_dst, &maps.a, &full_bar[s], kb * kBlockK, m_tile * kBlockM, p.a_batched ? bz : 0);
+            else tma_load_3d(a_dst, &maps.a, &full_bar[s], kb * kBlockK, m_tile * kBlockM, p.a_batched ? bz : 0);
           } else {
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;
             const int ky = tap / 3, kx = tap - 3 * ky;
             if (p.a_mode == kAConvS1) {
-              tma_load_4d(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+              if (CG == 2) tma_load_4d_pair(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
+              else tma_load_4d(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
             } else {
               // stride-2: input viewed as (B, H, 2, W, 2*Cin) with H, W the OUTPUT extents;
               // input row 2*oy + ky - pad_lo -> parity (t & 1), half-row oy + (t >> 1)
               const int ty = ky - p.pad_lo, tx = kx - p.pad_lo;
               const int ypar = ty & 1, yoff = ty >> 1;
               const int xpar = tx & 1, xoff = tx >> 1;
-              tma_load_5d(a_dst, &maps.a, &full_bar[s], xpar * p.cin_blocks * kBlockK + cb * kBlockK, x0 + xoff, ypar,
-                          y0 + yoff, b0);
+              const int c0 = xpar * p.cin_blocks * kBlockK + cb * kBlockK;
+              if (CG == 2) tma_load_5d_pair(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
+              else tma_load_5d(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
             }
           }
-          tma_load_3d(b_dst, &maps.b, &full_bar[s], kb * kBlockK, tc.n_tile * p.block_n, p.b_batched ? tc.bz : 0);
+          if (CG == 2) tma_load_3d_pair(b_dst, &maps.b, &full_bar[s], kb * kBlockK, b_row0, p.b_batched ? bz : 0);
+          else tma_load_3d(b_dst, &maps.b, &full_bar[s], kb * kBlockK, b_row0, p.b_batched ? bz : 0);
         }
         __syncwarp();
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    const uint32_t idesc = p.in_f16 ? umma_idesc_f16(kBlockM, p.block_n) : umma_idesc_bf16(kBlockM, p.block_n);
-    int s = 0;
-    uint32_t ph = 0;
-    int as = 0;
-    uint32_t aph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      mbar_wait(&tempty_bar[as], aph ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + as * kMaxBlockN;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+    // ===================================================== MMA issuer (leader CTA only when CG = 2)
+    if (cta_rank == 0) {
+      const uint32_t idesc = p.in_f16 ? umma_idesc_f16(CG * kBlockM, p.block_n) : umma_idesc_bf16(CG * kBlockM, p.block_n);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = unit0; t < total_units; t += unit_step) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint64_t da = umma_desc_kmajor_sw128(a_addr);
-          const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
+        const uint32_t tmem_acc = tmem_base + as * kMaxBlockN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+            const uint64_t da = umma_desc_kmajor_sw128(a_addr);
+            const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (CG == 2) {
+              umma_commit_pair(&empty_bar[s], 3);       // frees this stage in both CTAs
+              if (kb == p.num_k_blocks - 1) umma_commit_pair(&tfull_bar[as], 3);
+            } else {
+              umma_commit(&empty_bar[s]);
+              if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+            }
           }
-          umma_commit(&empty_bar[s]);
-          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        if (++as == kAccStages) { as = 0; aph ^= 1; }
       }
-      if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column sets
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int e = warp - 4;
     const int ew = e & 3;     // == warp % 4: TMEM lane quadrant this warp may access
     const int cset = e >> 2;  // this warp handles 32-column chunks with (chunk index & 1) == cset
@@ -348,8 +478,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int out_tile_w = geglu ? p.block_n / 2 : p.block_n;
     uint8_t* stg_warp = stg + e * 4096;
     int toggle = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    int swz[4];   // byte offsets of this lane's four 16 B pieces in a [32 rows][64 B] SWIZZLE_64B staging buffer
+#pragma unroll
+    for (int c = 0; c < 4; ++c) swz[c] = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+    for (int t = unit0; t < total_units; t += unit_step) {
+      TileCoord tc;
+      {
+        const int mu = t % num_m_units;
+        const int r0 = t / num_m_units;
+        tc.n_tile = r0 % p.num_n_tiles;
+        tc.bz = r0 / p.num_n_tiles;
+        tc.m_tile = mu * CG + (int)cta_rank;
+      }
       // ---- row of this thread, origin of this warp's 32-row slice
       long long row;
       bool row_ok;
@@ -379,20 +519,117 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         sc.c2 = yt * p.th + ((w0 / p.tw) % p.th);
         sc.c3 = bt * p.tb + (w0 / p.tw) / p.th;
       }
-      const int bidx = (p.rows_per_batch > 0) ? (int)(row / p.rows_per_batch) : 0;
+      const int bidx = (p.rows_per_batch > 0 && row_ok) ? (int)(row / p.rows_per_batch) : 0;
       const long long out_batch_off = (long long)tc.bz * p.out_batch_stride;
       const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + row) : 0.f;
+
+      // per-row operand bases of the lean path (null rows of a padding tile read nothing)
+      const float* rbb = (p.row_batch_bias && row_ok) ? p.row_batch_bias + (long long)bidx * p.N : nullptr;
+      const float* csrow = (p.col_scale && row_ok) ? p.col_scale + (long long)bidx * ncols_out : nullptr;
+      const __nv_bfloat16* resrow = (p.residual && row_ok) ? p.residual + row * p.ld_res : nullptr;
+      ResidualRegs rnext;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rnext.u[q] = make_uint4(0u, 0u, 0u, 0u);
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kMaxBlockN;
 
+      bool have_res = false;
       for (int c = cset * 32; c < out_tile_w; c += 64) {
         const int ocol0 = tc.n_tile * out_tile_w + c;
         if (ocol0 >= ncols_out) break;
+        const int acol0 = tc.n_tile * p.block_n + c;  // accumulator column (bias index)
+        const int lim = min(ncols_out, ocol0 + 32);
+        const bool fast = p.fast_epi && (ocol0 + 32 <= ncols_out) && (acol0 + (geglu ? out_tile_w : 0) + 32 <= p.N);
+        if (fast) {
+          // ---- lean path: TMEM load in flight while the bias vectors arrive; residual prefetched one chunk ahead
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + c, raw);
+          float v[32];
+          if (p.bias) ldg_f32x32(p.bias + acol0, v);
+          else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          ResidualRegs rcur = rnext;
+          const bool cur_res = have_res;
+          have_res = false;
+          if (resrow) {
+            if (!cur_res) residual_prefetch(rcur, resrow + ocol0);
+            const int nc = c + 64, nocol0 = ocol0 + 64;
+            if (nc < out_tile_w && nocol0 + 32 <= ncols_out) {
+              residual_prefetch(rnext, resrow + nocol0);
+              have_res = true;
+            }
+          }
+          tmem_ld_wait();
+          if (p.alpha == 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]) + bm;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += fmaf(__uint_as_float(raw[j]), p.alpha, bm);
+          }
+          if (rbb) add_f32x32(rbb + acol0, v);
+          if (geglu) {
+            tmem_ld_32x32(taddr + out_tile_w + c, raw);
+            float gb[32];
+            const int gcol0 = acol0 + out_tile_w;
+            if (p.bias) ldg_f32x32(p.bias + gcol0, gb);
+            else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gb[j] = 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_lean(fmaf(__uint_as_float(raw[j]), p.alpha, gb[j]));
+          } else if (p.act == kActGeluTanh) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+          } else if (p.act == kActSilu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+          if (p.cap_pre)
+            stage_and_store2<true>(&maps.cap_pre, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
+          if (csrow) mul_f32x32(csrow + ocol0, v);
+          if (resrow) residual_add(rcur, v);
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+          }
+          if (p.out && ocol0 >= p.out_f16_from) {
+            stage_and_store2<true>(&maps.out, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
+            if (p.out2) stage_and_store2<false>(&maps.out2, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
+          } else if (p.out) {
+            stage_and_store2<false>(&maps.out, ocol0, p.out2 ? &maps.out2 : nullptr, ocol0, stg_warp, toggle, lane, swz,
+                                    v, sc);
+          } else if (p.out2) {
+            stage_and_store2<false>(&maps.out2, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
+          }
+          {
+            // fp16 captures of the final value: one staging pass feeds every segment that contains this chunk
+            const CUtensorMap* m0 = nullptr;
+            const CUtensorMap* m1 = nullptr;
+            int c0 = 0, c1 = 0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              if (s < p.num_cap && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end) {
+                if (!m0) { m0 = &maps.cap[s]; c0 = ocol0 - p.cap[s].col_begin; }
+                else if (!m1) { m1 = &maps.cap[s]; c1 = ocol0 - p.cap[s].col_begin; }
+                else stage_and_store2<true>(&maps.cap[s], ocol0 - p.cap[s].col_begin, nullptr, 0, stg_warp, toggle, lane,
+                                            swz, v, sc);
+              }
+            }
+            if (m0) stage_and_store2<true>(m0, c0, m1, c1, stg_warp, toggle, lane, swz, v, sc);
+          }
+          if (p.out_f32 && row_ok) direct_store32(p, v, v, row, ocol0, lim, out_batch_off, true);
+          continue;
+        }
+        have_res = false;
         float v[32];
         load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
-        const int lim = min(ncols_out, ocol0 + 32);
         if (p.tma_store) {
           // registers -> swizzled smem -> one TMA bulk store per destination (rows / columns clipped by the map)
           if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
@@ -420,39 +657,88 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA issuer waits for both
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
     if (lane == 0) bulk_wait<0>();   // all bulk stores of this warp have completed before the CTA retires
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: neither CTA retires while its peer still uses it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 static int g_num_sms = 0;
+static int g_pair_ctas = 0;   // CTAs the device keeps resident as clusters of 2 (<= g_num_sms)
+
+static cudaError_t gemm_init_once() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_num_sms & ~1);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kGemmSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, gemm_tcgen05_kernel<2>, &cfg) == cudaSuccess && nclusters > 0)
+    g_pair_ctas = 2 * nclusters;
+  else
+    g_pair_ctas = 0;
+  (void)cudaGetLastError();
+  if (g_pair_ctas > g_num_sms) g_pair_ctas = g_num_sms & ~1;
+  done = true;
+  return cudaSuccess;
+}
 
 cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kGemmSmemBytes);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
+  cudaError_t e = gemm_init_once();
+  if (e != cudaSuccess) return e;
+  const int cg = p.cta_group == 2 ? 2 : 1;
+  const int num_m_units = (p.num_m_tiles + cg - 1) / cg;
+  const int total_units = p.batch * num_m_units * p.num_n_tiles;
+  if (total_units <= 0) return cudaSuccess;
+  if (cg == 1) {
+    const int grid = total_units < g_num_sms ? total_units : g_num_sms;
+    gemm_tcgen05_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
+    return cudaGetLastError();
   }
-  const int total_tiles = p.batch * p.num_m_tiles * p.num_n_tiles;
-  if (total_tiles <= 0) return cudaSuccess;
-  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
-  return cudaGetLastError();
+  if (g_pair_ctas < 2) return cudaErrorInvalidConfiguration;
+  const int grid = 2 * total_units < g_pair_ctas ? 2 * total_units : g_pair_ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kGemmSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, maps, p);
 }
 
 int gemm_num_sms() {

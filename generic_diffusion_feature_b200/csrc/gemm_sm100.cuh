@@ -35,7 +35,8 @@ struct GemmParams {
   int M, N, K;          // N counts accumulator columns (for GEGLU: 2x the output width)
   int n_out;            // valid output columns (<= N, or <= N/2 for GEGLU); padding columns are dropped
   int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
-  int num_stages;       // operand ring depth: kPipeBytes / (16 KB + block_n * 128 B), <= kMaxStages
+  int num_stages;       // operand ring depth: kPipeBytes / (16 KB + block_n / cta_group * 128 B), <= kMaxStages
+  int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
   int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)
@@ -45,6 +46,7 @@ struct GemmParams {
   int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;
   // ---- epilogue
   int tma_store;               // 1: bf16/fp16 destinations go through smem staging + TMA bulk stores
+  int fast_epi;                // 1: tma_store and every fp32 / residual operand is 16-byte aligned (lean epilogue path)
   float alpha;                 // accumulator scale (1.0 default)
   const float* bias;           // [N] column bias (already permuted for GEGLU) or null
   const float* bias_m;         // [M] row bias (transposed products) or null

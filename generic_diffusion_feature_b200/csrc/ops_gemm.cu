@@ -40,6 +40,23 @@ int choose_block_n(int N, bool geglu, int num_m_tiles) {
   return best;
 }
 
+// CTA pair (256-row tiles, half of B per CTA) whenever the tile shape allows it; GDF_CTA_GROUP=1|2 forces.
+static int choose_cta_group(int block_n, int num_m_tiles) {
+  const int forced = env_int("GDF_CTA_GROUP", 0);
+  const bool can = (block_n % 32 == 0) && block_n >= 32;
+  if (forced == 1) return 1;
+  if (forced == 2) return can ? 2 : 1;
+  return (can && num_m_tiles >= 2) ? 2 : 1;
+}
+
+static void finish_tiling(GemmParams& p) {
+  p.cta_group = choose_cta_group(p.block_n, p.num_m_tiles);
+  p.num_stages = kPipeBytes / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (env_int("GDF_MAX_STAGES", 0) > 0 && p.num_stages > env_int("GDF_MAX_STAGES", 0))
+    p.num_stages = env_int("GDF_MAX_STAGES", 0);   // tuning knob
+}
+
 static int make_store_map(CUtensorMap* m, const GemmParams& p, const void* ptr, int width, int ld,
                           long long batch_stride) {
   if (p.a_mode == kALinear) {
@@ -72,7 +89,16 @@ static int setup_stores(GemmLaunch* g) {
   if (!p.out && !p.out2 && !p.cap_pre && p.num_cap == 0) ok = false;
   if (env_int("GDF_TMA_STORE", 1) == 0) ok = false;   // tuning knob
   p.tma_store = ok ? 1 : 0;
+  p.fast_epi = 0;
   if (!ok) return GDF_OK;
+  {
+    bool f = env_int("GDF_FAST_EPI", 1) != 0;
+    if (p.bias && !aligned16(p.bias)) f = false;
+    if (p.row_batch_bias && (!aligned16(p.row_batch_bias) || p.N % 4 != 0)) f = false;
+    if (p.col_scale && (!aligned16(p.col_scale) || p.n_out % 4 != 0)) f = false;
+    if (p.residual && (!aligned16(p.residual) || p.ld_res % 8 != 0)) f = false;
+    p.fast_epi = f ? 1 : 0;
+  }
   if (p.out) GDF_TRY(make_store_map(&g->maps.out, p, p.out, p.n_out, p.ld_out, p.out_batch_stride));
   if (p.out2) GDF_TRY(make_store_map(&g->maps.out2, p, p.out2, p.n_out, p.ld_out2, 0));
   return GDF_OK;
@@ -149,17 +175,14 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
     GDF_TRY(make_tmap_bf16(&g->maps.a, A, 3, dims, str, box));
   }
+  finish_tiling(p);
   {
     const int wb = p.b_batched ? batch : 1;
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)wb};
     uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(block_n / p.cta_group), 1};
     GDF_TRY(make_tmap_bf16(&g->maps.b, W, 3, dims, str, box));
   }
-  p.num_stages = kPipeBytes / (kStageBytesA + block_n * kBlockK * 2);
-  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-  if (env_int("GDF_MAX_STAGES", 0) > 0 && p.num_stages > env_int("GDF_MAX_STAGES", 0))
-    p.num_stages = env_int("GDF_MAX_STAGES", 0);   // tuning knob
   GDF_TRY(setup_stores(g));
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
@@ -212,14 +235,13 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
     uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)tw, 1, (uint32_t)th, (uint32_t)tb};
     GDF_TRY(make_tmap_bf16(&g->maps.a, X, 5, dims, str, box));
   }
+  finish_tiling(p);
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)N, 1};
     uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)N * p.K * 2};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(block_n / p.cta_group), 1};
     GDF_TRY(make_tmap_bf16(&g->maps.b, Wp, 3, dims, str, box));
   }
-  p.num_stages = kPipeBytes / (kStageBytesA + block_n * kBlockK * 2);
-  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   GDF_TRY(setup_stores(g));
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
