@@ -8,7 +8,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libgdf_b200.so")
+# GDF_LIB_PATH: A/B timing of two builds of the same library on one GPU box (tools/, not a fallback)
+LIB_PATH = os.environ.get("GDF_LIB_PATH") or os.path.join(_PKG, "libgdf_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

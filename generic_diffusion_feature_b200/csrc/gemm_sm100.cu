@@ -187,8 +187,9 @@ struct StoreCoord {   // origin of this warp's 32-row slice in the destination t
 template <bool kF16>
 __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t* stg_warp, int& toggle, int lane,
                                                 const float* v /*32*/, int col, const StoreCoord& sc) {
-  uint8_t* buf = stg_warp + toggle * 2048;
-  if (lane == 0) bulk_wait_read<1>();   // the store that used this buffer two stores ago has drained
+  (void)toggle;
+  uint8_t* buf = stg_warp;              // generic path: one buffer, fully drained around every store
+  if (lane == 0) bulk_wait_read<0>();
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -209,8 +210,9 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
     if (sc.conv) tma_store_4d(map, buf, col, sc.c1, sc.c2, sc.c3);
     else tma_store_3d(map, buf, col, sc.c1, sc.c2);
     bulk_commit();
+    bulk_wait_read<0>();
   }
-  toggle ^= 1;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------- lean epilogue (fast path)
@@ -271,20 +273,27 @@ __device__ __forceinline__ void issue_store(const CUtensorMap* map, const uint8_
   if (sc.conv) tma_store_4d(map, buf, col, sc.c1, sc.c2, sc.c3);
   else tma_store_3d(map, buf, col, sc.c1, sc.c2);
 }
-// Stage 32x32 values once and send them to up to two destinations of the same 16-bit type.
+// One round of the lean path: stage 32 rows x (32 or 64) columns once (two [32 rows][64 B] SWIZZLE_64B buffers) and
+// send them to up to two destinations of the same 16-bit type. Each warp owns 4 buffers = 2 rounds in flight:
+// before restaging a buffer pair, every bulk group but the most recent one must have finished reading.
 template <bool kF16>
-__device__ __forceinline__ void stage_and_store2(const CUtensorMap* map_a, int col_a, const CUtensorMap* map_b,
-                                                 int col_b, uint8_t* stg_warp, int& toggle, int lane,
-                                                 const int (&swz)[4], const float* v, const StoreCoord& sc) {
-  uint8_t* buf = stg_warp + toggle * 2048;
-  if (lane == 0) bulk_wait_read<1>();   // the store group that used this buffer two groups ago has drained
+__device__ __forceinline__ void store_round(const CUtensorMap* map_a, int col_a, const CUtensorMap* map_b, int col_b,
+                                            bool two, uint8_t* stg_warp, int& toggle, int lane, const int (&swz)[4],
+                                            const float* v0, const float* v1, const StoreCoord& sc) {
+  uint8_t* buf = stg_warp + toggle * 4096;
+  if (lane == 0) bulk_wait_read<1>();
   __syncwarp();
-  stage_chunk<kF16>(buf, swz, v);
+  stage_chunk<kF16>(buf, swz, v0);
+  if (two) stage_chunk<kF16>(buf + 2048, swz, v1);
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
     issue_store(map_a, buf, col_a, sc);
-    if (map_b) issue_store(map_b, buf, col_b, sc);
+    if (two) issue_store(map_a, buf + 2048, col_a + 32, sc);
+    if (map_b) {
+      issue_store(map_b, buf, col_b, sc);
+      if (two) issue_store(map_b, buf + 2048, col_b + 32, sc);
+    }
     bulk_commit();
   }
   toggle ^= 1;
@@ -310,7 +319,7 @@ __device__ __forceinline__ void residual_add(const ResidualRegs& r, float* v) {
 // tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 A rows and HALF of the B rows, the leader (even)
 // CTA issues the MMAs for both, and each CTA's TMEM receives its own 128 accumulator rows.  Operand bytes pulled
 // from L2 per MMA cycle drop from (128 + bn) to (128 + bn / 2) rows, which is what bounds this kernel.
-template <int CG>
+template <int CG, bool kGeglu>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -368,7 +377,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const uint32_t stage_tx_bytes = (CG * kBlockM + p.block_n) * kBlockK * 2;   // bytes landing per stage, all CTAs
 
   // register rebalancing: producer / MMA / allocator warpgroup needs few registers, the two epilogue warpgroups many
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
 
   if (warp == 0) {
     // ===================================================== TMA producer (every CTA loads its own A rows / B half)
@@ -466,17 +475,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column sets
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int e = warp - 4;
     const int ew = e & 3;     // == warp % 4: TMEM lane quadrant this warp may access
     const int cset = e >> 2;  // this warp handles 32-column chunks with (chunk index & 1) == cset
     const int r_in_tile = ew * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
-    const bool geglu = (p.act == kActGeglu);
+    constexpr bool geglu = kGeglu;   // host dispatch: p.act == kActGeglu
     const int ncols_out = p.n_out;
     const int out_tile_w = geglu ? p.block_n / 2 : p.block_n;
-    uint8_t* stg_warp = stg + e * 4096;
+    uint8_t* stg_warp = stg + e * 8192;   // 4 staging buffers of 2 KB per warp
     int toggle = 0;
     int swz[4];   // byte offsets of this lane's four 16 B pieces in a [32 rows][64 B] SWIZZLE_64B staging buffer
 #pragma unroll
@@ -525,109 +534,148 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
       // per-row operand bases of the lean path (null rows of a padding tile read nothing)
       const float* rbb = (p.row_batch_bias && row_ok) ? p.row_batch_bias + (long long)bidx * p.N : nullptr;
-      const float* csrow = (p.col_scale && row_ok) ? p.col_scale + (long long)bidx * ncols_out : nullptr;
-      const __nv_bfloat16* resrow = (p.residual && row_ok) ? p.residual + row * p.ld_res : nullptr;
-      ResidualRegs rnext;
+      const float* csrow = (!kGeglu && p.col_scale && row_ok) ? p.col_scale + (long long)bidx * ncols_out : nullptr;
+      // (GEGLU launches carry no residual / column gate on the lean path: checked on the host)
+      const __nv_bfloat16* resrow = (!kGeglu && p.residual && row_ok) ? p.residual + row * p.ld_res : nullptr;
+      ResidualRegs rr[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rnext.u[q] = make_uint4(0u, 0u, 0u, 0u);
+      for (int q = 0; q < 4; ++q) rr[0].u[q] = rr[1].u[q] = make_uint4(0u, 0u, 0u, 0u);
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kMaxBlockN;
 
+      // ---- lean path: rounds of 64 columns (two 32-column halves), TMEM loads / bias vectors / residual prefetch
+      // in flight together, one fence + one elected TMA issue per destination and round
       bool have_res = false;
-      for (int c = cset * 32; c < out_tile_w; c += 64) {
-        const int ocol0 = tc.n_tile * out_tile_w + c;
-        if (ocol0 >= ncols_out) break;
-        const int acol0 = tc.n_tile * p.block_n + c;  // accumulator column (bias index)
-        const int lim = min(ncols_out, ocol0 + 32);
-        const bool fast = p.fast_epi && (ocol0 + 32 <= ncols_out) && (acol0 + (geglu ? out_tile_w : 0) + 32 <= p.N);
-        if (fast) {
-          // ---- lean path: TMEM load in flight while the bias vectors arrive; residual prefetched one chunk ahead
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + c, raw);
-          float v[32];
-          if (p.bias) ldg_f32x32(p.bias + acol0, v);
-          else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      int c_done = cset * 64;    // first column this warp still has to handle on the generic path
+      if (p.fast_epi) {
+        for (int c = cset * 64; c < out_tile_w; c += 128) {
+          const int ocol0 = tc.n_tile * out_tile_w + c;
+          if (ocol0 >= ncols_out) { c_done = out_tile_w; break; }
+          const int acol0 = tc.n_tile * p.block_n + c;  // accumulator column (bias index)
+          const int gofs = geglu ? out_tile_w : 0;
+          const bool two = (c + 32 < out_tile_w) && (ocol0 + 32 < ncols_out);
+          const int wcols = two ? 64 : 32;
+          if (ocol0 + wcols > ncols_out || acol0 + gofs + wcols > p.N) { c_done = c; break; }   // ragged: generic path
+          c_done = c + 128;
+          uint32_t raw[2][32];
+          tmem_ld_32x32(taddr + c, raw[0]);
+          if (two) tmem_ld_32x32(taddr + c + 32, raw[1]);
+          if (resrow && !have_res) {     // first round of the tile (or after a ragged one): load now
+            residual_prefetch(rr[0], resrow + ocol0);
+            if (two) residual_prefetch(rr[1], resrow + ocol0 + 32);
           }
-          ResidualRegs rcur = rnext;
-          const bool cur_res = have_res;
           have_res = false;
-          if (resrow) {
-            if (!cur_res) residual_prefetch(rcur, resrow + ocol0);
-            const int nc = c + 64, nocol0 = ocol0 + 64;
-            if (nc < out_tile_w && nocol0 + 32 <= ncols_out) {
-              residual_prefetch(rnext, resrow + nocol0);
+          tmem_ld_wait();
+          float v[2][32];   // aliases raw: the accumulator registers are converted in place
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh == 1 && !two) break;
+            if (p.alpha == 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) + bm;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh][j] = fmaf(__uint_as_float(raw[hh][j]), p.alpha, bm);
+            }
+            if (p.bias) add_f32x32(p.bias + acol0 + hh * 32, v[hh]);
+            if (rbb) add_f32x32(rbb + acol0 + hh * 32, v[hh]);
+          }
+          if (geglu) {
+            uint32_t graw[2][32];
+            tmem_ld_32x32(taddr + out_tile_w + c, graw[0]);
+            if (two) tmem_ld_32x32(taddr + out_tile_w + c + 32, graw[1]);
+            const int gcol0 = acol0 + out_tile_w;
+            tmem_ld_wait();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              if (hh == 1 && !two) break;
+              float g[32];   // aliases graw[hh]
+#pragma unroll
+              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * p.alpha;
+              if (p.bias) add_f32x32(p.bias + gcol0 + hh * 32, g);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh][j] *= gelu_erf_lean(g[j]);
+            }
+          } else if (p.act == kActGeluTanh) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[0][j] = gelu_tanh_f(v[0][j]); v[1][j] = gelu_tanh_f(v[1][j]); }
+          } else if (p.act == kActSilu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[0][j] = silu_f(v[0][j]); v[1][j] = silu_f(v[1][j]); }
+          }
+          if (p.cap_pre)
+            store_round<true>(&maps.cap_pre, ocol0, nullptr, 0, two, stg_warp, toggle, lane, swz, v[0], v[1], sc);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh == 1 && !two) break;
+            if (csrow) mul_f32x32(csrow + ocol0 + hh * 32, v[hh]);
+            if (resrow) residual_add(rr[hh], v[hh]);
+            if (p.out_scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh][j] *= p.out_scale;
+            }
+          }
+          if (resrow) {   // the residual registers are free again: fetch the next full round while this one is stored
+            const int nc = c + 128, nocol0 = ocol0 + 128;
+            if (nc + 64 <= out_tile_w && nocol0 + 64 <= ncols_out) {
+              residual_prefetch(rr[0], resrow + nocol0);
+              residual_prefetch(rr[1], resrow + nocol0 + 32);
               have_res = true;
             }
           }
-          tmem_ld_wait();
-          if (p.alpha == 1.f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]) + bm;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += fmaf(__uint_as_float(raw[j]), p.alpha, bm);
-          }
-          if (rbb) add_f32x32(rbb + acol0, v);
-          if (geglu) {
-            tmem_ld_32x32(taddr + out_tile_w + c, raw);
-            float gb[32];
-            const int gcol0 = acol0 + out_tile_w;
-            if (p.bias) ldg_f32x32(p.bias + gcol0, gb);
-            else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) gb[j] = 0.f;
+          // destinations of the final value; a dtype / capture-segment boundary in the middle of the round
+          // (all boundaries are multiples of 32 columns) splits it into two single-half rounds
+          auto emit = [&](int col, bool tw, const float* va, const float* vb) {
+            if (p.out && col >= p.out_f16_from) {
+              store_round<true>(&maps.out, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
+              if (p.out2) store_round<false>(&maps.out2, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
+            } else if (p.out) {
+              store_round<false>(&maps.out, col, p.out2 ? &maps.out2 : nullptr, col, tw, stg_warp, toggle, lane, swz, va,
+                                 vb, sc);
+            } else if (p.out2) {
+              store_round<false>(&maps.out2, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
             }
-            tmem_ld_wait();
+            if (p.num_cap > 0) {
+              const CUtensorMap* m0 = nullptr;
+              const CUtensorMap* m1 = nullptr;
+              int c0 = 0, c1 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_lean(fmaf(__uint_as_float(raw[j]), p.alpha, gb[j]));
-          } else if (p.act == kActGeluTanh) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-          } else if (p.act == kActSilu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-          }
-          if (p.cap_pre)
-            stage_and_store2<true>(&maps.cap_pre, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
-          if (csrow) mul_f32x32(csrow + ocol0, v);
-          if (resrow) residual_add(rcur, v);
-          if (p.out_scale != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
-          }
-          if (p.out && ocol0 >= p.out_f16_from) {
-            stage_and_store2<true>(&maps.out, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
-            if (p.out2) stage_and_store2<false>(&maps.out2, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
-          } else if (p.out) {
-            stage_and_store2<false>(&maps.out, ocol0, p.out2 ? &maps.out2 : nullptr, ocol0, stg_warp, toggle, lane, swz,
-                                    v, sc);
-          } else if (p.out2) {
-            stage_and_store2<false>(&maps.out2, ocol0, nullptr, 0, stg_warp, toggle, lane, swz, v, sc);
-          }
-          {
-            // fp16 captures of the final value: one staging pass feeds every segment that contains this chunk
-            const CUtensorMap* m0 = nullptr;
-            const CUtensorMap* m1 = nullptr;
-            int c0 = 0, c1 = 0;
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              if (s < p.num_cap && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end) {
-                if (!m0) { m0 = &maps.cap[s]; c0 = ocol0 - p.cap[s].col_begin; }
-                else if (!m1) { m1 = &maps.cap[s]; c1 = ocol0 - p.cap[s].col_begin; }
-                else stage_and_store2<true>(&maps.cap[s], ocol0 - p.cap[s].col_begin, nullptr, 0, stg_warp, toggle, lane,
-                                            swz, v, sc);
+              for (int s = 0; s < 3; ++s) {
+                if (s < p.num_cap && p.cap[s].ptr && col >= p.cap[s].col_begin && col < p.cap[s].col_end) {
+                  if (!m0) { m0 = &maps.cap[s]; c0 = col - p.cap[s].col_begin; }
+                  else if (!m1) { m1 = &maps.cap[s]; c1 = col - p.cap[s].col_begin; }
+                }
               }
+              if (m0) store_round<true>(m0, c0, m1, c1, tw, stg_warp, toggle, lane, swz, va, vb, sc);
             }
-            if (m0) stage_and_store2<true>(m0, c0, m1, c1, stg_warp, toggle, lane, swz, v, sc);
+          };
+          bool split = false;
+          if (two) {
+            const int mid = ocol0 + 32;
+            split = (p.out && p.out_f16_from == mid);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              if (s < p.num_cap && p.cap[s].ptr && (p.cap[s].col_begin == mid || p.cap[s].col_end == mid)) split = true;
           }
-          if (p.out_f32 && row_ok) direct_store32(p, v, v, row, ocol0, lim, out_batch_off, true);
-          continue;
+          if (!split) emit(ocol0, two, v[0], v[1]);
+          else {
+            emit(ocol0, false, v[0], v[0]);
+            emit(ocol0 + 32, false, v[1], v[1]);
+          }
+          if (p.out_f32 && row_ok) {
+            direct_store32(p, v[0], v[0], row, ocol0, ocol0 + 32, out_batch_off, true);
+            if (two) direct_store32(p, v[1], v[1], row, ocol0 + 32, ocol0 + 64, out_batch_off, true);
+          }
         }
-        have_res = false;
+      }
+      // ---- generic path: whatever the lean path left (ragged tiles, unaligned operands, no TMA store), 32 columns
+      // at a time; this warp owns the 64-column groups with (group index & 1) == cset
+      for (int c = c_done; c < out_tile_w; c += ((c & 32) ? 96 : 32)) {
+        const int ocol0 = tc.n_tile * out_tile_w + c;
+        if (ocol0 >= ncols_out) break;
+        const int lim = min(ncols_out, ocol0 + 32);
         float v[32];
         load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
         if (p.tma_store) {
@@ -682,10 +730,14 @@ static int g_pair_ctas = 0;   // CTAs the device keeps resident as clusters of 2
 static cudaError_t gemm_init_once() {
   static bool done = false;
   if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kGemmSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return e;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -702,7 +754,7 @@ static cudaError_t gemm_init_once() {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, gemm_tcgen05_kernel<2>, &cfg) == cudaSuccess && nclusters > 0)
+  if (cudaOccupancyMaxActiveClusters(&nclusters, gemm_tcgen05_kernel<2, false>, &cfg) == cudaSuccess && nclusters > 0)
     g_pair_ctas = 2 * nclusters;
   else
     g_pair_ctas = 0;
@@ -721,7 +773,8 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   if (total_units <= 0) return cudaSuccess;
   if (cg == 1) {
     const int grid = total_units < g_num_sms ? total_units : g_num_sms;
-    gemm_tcgen05_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
+    if (p.act == kActGeglu) gemm_tcgen05_kernel<1, true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
+    else gemm_tcgen05_kernel<1, false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
     return cudaGetLastError();
   }
   if (g_pair_ctas < 2) return cudaErrorInvalidConfiguration;
@@ -738,7 +791,8 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, maps, p);
+  if (p.act == kActGeglu) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, maps, p);
 }
 
 int gemm_num_sms() {

@@ -18,8 +18,8 @@ constexpr int kAccStages = 2;
 constexpr int kEpilogueWarps = 8;   // 4 TMEM lane quadrants x 2 interleaved column sets
 constexpr int kGemmThreads = 128 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int kStageBytesA = kBlockM * kBlockK * 2;          // 16 KB
-constexpr int kPipeBytes = 192 * 1024;                       // operand ring: num_stages * (16 KB + block_n * 128 B)
-constexpr int kStagingBytes = kEpilogueWarps * 2 * 2048;     // epilogue: per warp 2 x [32 rows][64 B] TMA-store buffers
+constexpr int kPipeBytes = 160 * 1024;                       // operand ring: num_stages * (16 KB + block_n / cta_group * 128 B)
+constexpr int kStagingBytes = kEpilogueWarps * 4 * 2048;     // epilogue: per warp 4 x [32 rows][64 B] TMA-store buffers
 constexpr int kGemmSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 
 enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2 };

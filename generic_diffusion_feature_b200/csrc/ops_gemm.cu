@@ -43,7 +43,7 @@ int choose_block_n(int N, bool geglu, int num_m_tiles) {
 // CTA pair (256-row tiles, half of B per CTA) whenever the tile shape allows it; GDF_CTA_GROUP=1|2 forces.
 static int choose_cta_group(int block_n, int num_m_tiles) {
   const int forced = env_int("GDF_CTA_GROUP", 0);
-  const bool can = (block_n % 32 == 0) && block_n >= 32;
+  const bool can = (block_n % 16 == 0) && block_n >= 32;
   if (forced == 1) return 1;
   if (forced == 2) return can ? 2 : 1;
   return (can && num_m_tiles >= 2) ? 2 : 1;
@@ -97,6 +97,7 @@ static int setup_stores(GemmLaunch* g) {
     if (p.row_batch_bias && (!aligned16(p.row_batch_bias) || p.N % 4 != 0)) f = false;
     if (p.col_scale && (!aligned16(p.col_scale) || p.n_out % 4 != 0)) f = false;
     if (p.residual && (!aligned16(p.residual) || p.ld_res % 8 != 0)) f = false;
+    if (p.act == kActGeglu && (p.residual || p.col_scale)) f = false;   // lean GEGLU path has neither
     p.fast_epi = f ? 1 : 0;
   }
   if (p.out) GDF_TRY(make_store_map(&g->maps.out, p, p.out, p.n_out, p.ld_out, p.out_batch_stride));

@@ -189,7 +189,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
