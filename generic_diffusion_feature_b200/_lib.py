@@ -21,7 +21,7 @@ GDF_MAX_LEVELS = 4
 # every symbol include/gdf.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
-    "gdf_create", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
+    "gdf_create", "gdf_create_dit", "gdf_denoise_capture_dit", "gdf_op_attention_bias", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
     "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
@@ -75,6 +75,13 @@ class VaeArch(ctypes.Structure):
     ]
 
 
+class DitArch(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("out_channels", c_int), ("patch_size", c_int), ("num_layers", c_int),
+        ("num_heads", c_int), ("head_dim", c_int), ("caption_channels", c_int), ("norm_eps", c_float),
+    ]
+
+
 class Slot(ctypes.Structure):
     _fields_ = [("offset_bytes", c_int64), ("channels", c_int), ("height", c_int), ("width", c_int),
                 ("order", c_int)]
@@ -110,6 +117,8 @@ def load():
     lib.gdf_op_layernorm.argtypes = [P, P, P, P, c_int64, c_int, c_float, P, P, c_int, P]
     lib.gdf_op_attention.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_float, c_int, P]
+    lib.gdf_op_attention_bias.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_float, P, P]
     lib.gdf_op_softmax_rows.argtypes = [P, c_int64, c_int, c_int, P]
     lib.gdf_op_upsample_nearest2x.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.gdf_op_im2col_small.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P]
@@ -121,6 +130,8 @@ def load():
     lib.gdf_correspond.argtypes = [P, P, c_int, c_int, c_int, P, c_int, P, P, P]
     if hasattr(lib, "gdf_create"):
         lib.gdf_create.argtypes = [ctypes.POINTER(UNetArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
+        lib.gdf_create_dit.argtypes = [ctypes.POINTER(DitArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
+        lib.gdf_denoise_capture_dit.argtypes = [P, c_float, P, c_int, P, P, P, P]
         lib.gdf_destroy.argtypes = [P]
         lib.gdf_load_weights.argtypes = [P, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(P),
                                          ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, P]

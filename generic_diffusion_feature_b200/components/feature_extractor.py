@@ -53,6 +53,16 @@ def _unet_feature_ids(cfg, layers_per_block=2):
     return ids
 
 
+def _dit_feature_ids(cfg):
+    """Ids of the PixArt branch of prepare_feature_extractor (feature_extractor.py:259-286) that
+    FeatureStore.store keeps, in execution order: per block self-q/k/v, cross-q, ffn-inner, out."""
+    ids = []
+    for k in range(cfg["layers"]):
+        for tag in ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out"):
+            ids.append("vit-block%d-%s" % (k, tag))
+    return ids
+
+
 class FeatureStore:
     """Mirror of the reference FeatureStore (feature_extractor.py:8-80) backed by the arena plan."""
 
@@ -138,7 +148,7 @@ def selected_ids(feature_store, pipe):
     """Ids to plan: enabled JSON keys in file order, or every id of the architecture when accept_all
     (feature_extractor.py:10-15,36). `map` ids need the attention-probability path and raise."""
     if feature_store.accept_all:
-        return _unet_feature_ids(pipe.unet_cfg)
+        return _dit_feature_ids(pipe.dit_cfg) if getattr(pipe, "dit_cfg", None) else _unet_feature_ids(pipe.unet_cfg)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:
         if "map" in k or k in ("vae-out", "attn"):

@@ -14,7 +14,7 @@ import zlib
 import torch
 
 from .. import _lib
-from .._lib import UNetArch, VaeArch, check
+from .._lib import DitArch, UNetArch, VaeArch, check
 
 # SURVEY.md Appendix B (diffusers configs of the checkpoints models.py:18-70 names)
 UNET_CONFIGS = {
@@ -32,7 +32,63 @@ VAE_CONFIGS = {
     "1-5": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.18215),
     "2-1": dict(block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6, scaling_factor=0.18215),
 }
-_NOT_BUILT = ("pixart-sigma", "pixart-sigma-512", "pixart-alpha", "if", "hunyuan", "flux")
+# [PixArt-alpha/PixArt-Sigma-XL-2-{1024,512}-MS transformer/config.json, from memory; SURVEY.md row a16]
+DIT_CONFIGS = {
+    "pixart-sigma": dict(layers=28, heads=16, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=4096,
+                         sample_size=128, interpolation_scale=2.0, eps=1e-6),
+    "pixart-sigma-512": dict(layers=28, heads=16, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=4096,
+                             sample_size=64, interpolation_scale=1.0, eps=1e-6),
+}
+VAE_CONFIGS["pixart-sigma"] = VAE_CONFIGS["xl"]          # PixArt-Sigma ships the SDXL VAE
+VAE_CONFIGS["pixart-sigma-512"] = VAE_CONFIGS["xl"]
+_NOT_BUILT = ("pixart-alpha", "if", "hunyuan", "flux")
+
+
+def dit_param_specs(cfg):
+    """(name, shape) of every PixArtTransformer2DModel parameter / persistent buffer, diffusers naming."""
+    C = cfg["heads"] * cfg["head_dim"]
+    grid = cfg["sample_size"] // cfg["patch"]
+    out = []
+
+    def lin(n, o, i):
+        out.append((n + ".weight", (o, i)))
+        out.append((n + ".bias", (o,)))
+
+    out.append(("pos_embed.proj.weight", (C, cfg["in_ch"], cfg["patch"], cfg["patch"])))
+    out.append(("pos_embed.proj.bias", (C,)))
+    out.append(("pos_embed.pos_embed", (1, grid * grid, C)))
+    lin("adaln_single.emb.timestep_embedder.linear_1", C, 256)
+    lin("adaln_single.emb.timestep_embedder.linear_2", C, C)
+    lin("adaln_single.linear", 6 * C, C)
+    lin("caption_projection.linear_1", C, cfg["caption_dim"])
+    lin("caption_projection.linear_2", C, C)
+    for k in range(cfg["layers"]):
+        b = "transformer_blocks.%d" % k
+        out.append((b + ".scale_shift_table", (6, C)))
+        for a in ("attn1", "attn2"):
+            for pn in ("to_q", "to_k", "to_v", "to_out.0"):
+                lin("%s.%s.%s" % (b, a, pn), C, C)
+        lin(b + ".ff.net.0.proj", 4 * C, C)
+        lin(b + ".ff.net.2", C, 4 * C)
+    out.append(("scale_shift_table", (2, C)))
+    lin("proj_out", cfg["patch"] * cfg["patch"] * cfg["out_ch"], C)
+    return out
+
+
+def sincos_pos_embed_2d(dim, grid, base_size, interpolation_scale):
+    """[diffusers embeddings.get_2d_sincos_pos_embed]: the constant table PatchEmbed registers as the persistent
+    buffer `pos_embed` (so a real checkpoint's state_dict carries it); generated here for synthetic weights."""
+    import numpy as np
+    pos = np.arange(grid, dtype=np.float32).astype(np.float64) / (grid / base_size) / interpolation_scale
+    gw = np.tile(pos[None, :], (grid, 1)).reshape(-1)
+    gh = np.tile(pos[:, None], (1, grid)).reshape(-1)
+    quarter = dim // 4
+    omega = 1.0 / 10000 ** (np.arange(quarter, dtype=np.float64) / quarter)
+
+    def one(p):
+        o = p[:, None] * omega[None]
+        return np.concatenate([np.sin(o), np.cos(o)], axis=1)
+    return torch.from_numpy(np.concatenate([one(gw), one(gh)], axis=1)).float()
 
 
 def unet_param_specs(cfg, layers_per_block=2):
@@ -196,11 +252,28 @@ def init_param(name, shape, device="cpu"):
     return r * (gain / fan_in ** 0.5)
 
 
-def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None):
-    """name -> fp32 tensor for 'unet.*' and 'vae.*' (random init; there are no checkpoints offline)."""
-    ucfg = unet_cfg or UNET_CONFIGS[version]
+def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None, dit_cfg=None):
+    """name -> fp32 tensor for 'unet.*' (or 'transformer.*') and 'vae.*' (random init; no checkpoints offline)."""
     vcfg = vae_cfg or VAE_CONFIGS[version]
     sd = {}
+    dcfg = dit_cfg or (DIT_CONFIGS.get(version) if unet_cfg is None else None)
+    if dcfg is not None:
+        C = dcfg["heads"] * dcfg["head_dim"]
+        grid = dcfg["sample_size"] // dcfg["patch"]
+        for n, s in dit_param_specs(dcfg):
+            key = "transformer." + n
+            if n == "pos_embed.pos_embed":
+                sd[key] = sincos_pos_embed_2d(C, grid, grid, dcfg["interpolation_scale"])[None].to(device)
+            elif n.endswith("scale_shift_table"):
+                g = torch.Generator(device=device)
+                g.manual_seed(zlib.crc32(key.encode()))
+                sd[key] = torch.randn(*s, generator=g, device=device) / C ** 0.5   # diffusers init: randn / sqrt(dim)
+            else:
+                sd[key] = init_param(key, s, device)
+        for n, s in vae_param_specs(vcfg):
+            sd["vae." + n] = init_param("vae." + n, s, device)
+        return sd
+    ucfg = unet_cfg or UNET_CONFIGS[version]
     for n, s in unet_param_specs(ucfg):
         sd["unet." + n] = init_param("unet." + n, s, device)
     for n, s in vae_param_specs(vcfg):
@@ -241,12 +314,22 @@ def _vae_arch(cfg):
     return a
 
 
+def _dit_arch(cfg):
+    a = DitArch()
+    a.in_channels, a.out_channels, a.patch_size = cfg["in_ch"], cfg["out_ch"], cfg["patch"]
+    a.num_layers, a.num_heads, a.head_dim = cfg["layers"], cfg["heads"], cfg["head_dim"]
+    a.caption_channels = cfg["caption_dim"]
+    a.norm_eps = cfg["eps"]
+    return a
+
+
 class B200Pipe:
     """What `FeatureExtractor` holds in place of a diffusers pipeline on the B200 path."""
 
-    def __init__(self, version, unet_cfg, vae_cfg, device):
+    def __init__(self, version, unet_cfg, vae_cfg, device, dit_cfg=None):
         self.version = version
         self.unet_cfg = unet_cfg
+        self.dit_cfg = dit_cfg
         self.vae_cfg = vae_cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -255,8 +338,14 @@ class B200Pipe:
         self.lib = _lib.load()
         self.handle = ctypes.c_void_p()
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        ua, va = _unet_arch(unet_cfg), _vae_arch(vae_cfg)
-        check(self.lib.gdf_create(ctypes.byref(ua), ctypes.byref(va), self.dev_index, ctypes.byref(self.handle)))
+        va = _vae_arch(vae_cfg)
+        if dit_cfg is not None:
+            da = _dit_arch(dit_cfg)
+            check(self.lib.gdf_create_dit(ctypes.byref(da), ctypes.byref(va), self.dev_index,
+                                          ctypes.byref(self.handle)))
+        else:
+            ua = _unet_arch(unet_cfg)
+            check(self.lib.gdf_create(ctypes.byref(ua), ctypes.byref(va), self.dev_index, ctypes.byref(self.handle)))
         self._finalized = False
 
     def load_state_dict(self, sd, chunk=256):
@@ -295,7 +384,7 @@ class B200Pipe:
 
 
 def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename=None, device="cuda",
-                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None):
+                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None):
     """Mirror of feature/components/models.py:10 for the B200 path.
 
     There is no network and no checkpoint on disk, so unless `state_dict` (diffusers-named fp32 tensors with
@@ -307,6 +396,15 @@ def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename
         raise NotImplementedError("LoRA loading is outside the B200 hot path (SURVEY.md 2.1 OUT OF SCOPE)")
     if version in _NOT_BUILT:
         raise NotImplementedError("version '%s' is not built on the B200 path yet (UNet families only)" % version)
+    if dit_cfg is not None or (version in DIT_CONFIGS and unet_cfg is None):
+        dcfg = dit_cfg or DIT_CONFIGS[version]
+        vcfg = vae_cfg or VAE_CONFIGS[version]
+        pipe = B200Pipe(version, None, vcfg, device, dit_cfg=dcfg)
+        if state_dict is None:
+            state_dict = synthetic_state_dict(version, weight_device or "cpu", None, vcfg, dcfg)
+        pipe.load_state_dict(state_dict)
+        pipe.finalize()
+        return pipe
     if version not in UNET_CONFIGS and unet_cfg is None:
         raise NotImplementedError                      # models.py:173-174
     ucfg = unet_cfg or UNET_CONFIGS[version]

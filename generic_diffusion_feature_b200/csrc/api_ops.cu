@@ -103,6 +103,15 @@ int gdf_op_attention(const void* q, int ldq, const void* k, int ldk, const void*
                                 v_f16, static_cast<cudaStream_t>(stream)));
 }
 
+int gdf_op_attention_bias(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                          int B, int heads, int Nq, int Nk, int head_dim, float scale, const void* key_bias,
+                          void* stream) {
+  GDF_LAUNCH(launch_attention_generic(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
+                                      static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, B, heads, Nq, Nk,
+                                      head_dim, scale, static_cast<cudaStream_t>(stream),
+                                      static_cast<const float*>(key_bias)));
+}
+
 int gdf_op_softmax_rows(void* s, int64_t rows, int cols, int ld, void* stream) {
   GDF_LAUNCH(launch_softmax_rows(static_cast<bf16*>(s), rows, cols, ld, static_cast<cudaStream_t>(stream)));
 }

@@ -41,7 +41,7 @@ template <int DP>
 __global__ void __launch_bounds__(kGaThreads, 1)
 attention_generic_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk,
                          const bf16* __restrict__ V, int ldv, bf16* __restrict__ O, int ldo, int Nq, int Nk, int D,
-                         float scale_log2) {
+                         float scale_log2, const float* __restrict__ key_bias) {
   using Cfg = GaCfg<DP>;
   constexpr int RS = Cfg::kRS;
   extern __shared__ __align__(128) uint8_t ga_smem[];
@@ -55,6 +55,7 @@ attention_generic_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
   const bf16* Kb = K + ((long long)b * Nk) * ldk + h * D;
   const bf16* Vb = V + ((long long)b * Nk) * ldv + h * D;
   const int real_chunks = D / 8;
+  const float* kb = key_bias ? key_bias + (long long)b * Nk : nullptr;
 
   for (int i = tid; i < kGaBM * Cfg::kChunks; i += kGaThreads) {
     const int r = i / Cfg::kChunks, c = i % Cfg::kChunks;
@@ -128,6 +129,7 @@ attention_generic_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
         const int col = kv0 + nb * 8 + (lane & 3) * 2 + (j & 1);
         float v = s_acc[nb][j] * scale_log2;
         if (col >= Nk) v = -INFINITY;
+        else if (kb) v = fmaf(__ldg(kb + col), 1.4426950408889634f, v);
         s_acc[nb][j] = v;
         mx[j >> 1] = fmaxf(mx[j >> 1], v);
       }
@@ -202,7 +204,8 @@ attention_generic_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
 
 template <int DP>
 static cudaError_t launch_ga(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
-                             int B, int heads, int Nq, int Nk, int D, float scale, cudaStream_t stream) {
+                             int B, int heads, int Nq, int Nk, int D, float scale, cudaStream_t stream,
+                             const float* key_bias) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_generic_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -212,17 +215,17 @@ static cudaError_t launch_ga(const bf16* Q, int ldq, const bf16* K, int ldk, con
   }
   dim3 grid((Nq + kGaBM - 1) / kGaBM, heads, B);
   attention_generic_kernel<DP><<<grid, kGaThreads, GaCfg<DP>::kSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
-                                                                                D, scale * 1.4426950408889634f);
+                                                                                D, scale * 1.4426950408889634f, key_bias);
   return cudaGetLastError();
 }
 
 cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O,
                                      int ldo, int B, int heads, int Nq, int Nk, int D, float scale,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const float* key_bias) {
   if (D % 8 != 0 || D > 160 || (ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
-  if (D <= 48) return launch_ga<48>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream);
-  if (D <= 80) return launch_ga<80>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream);
-  return launch_ga<160>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream);
+  if (D <= 48) return launch_ga<48>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
+  if (D <= 80) return launch_ga<80>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
+  return launch_ga<160>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
 }
 
 }  // namespace gdf

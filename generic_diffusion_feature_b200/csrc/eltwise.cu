@@ -214,4 +214,91 @@ cudaError_t launch_small_linear(const float* x, const float* W, const float* b, 
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- PixArt DiT helpers
+// PatchEmbed im2col (Conv2d k = s = p, [diffusers embeddings.PatchEmbed]; reference use: transformer_2d.py:541-569):
+// latent NHWC bf16 [B, L, L, Cin] -> A[B*(L/p)^2, k_pad] with k = (py*p + px)*Cin + c, zero padded.
+__global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ A, int B, int L, int p, int Cin,
+                                int k_pad) {
+  const int g = L / p;
+  const long long total = (long long)B * g * g * k_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % k_pad);
+    long long m = i / k_pad;
+    const int gx = (int)(m % g);
+    m /= g;
+    const int gy = (int)(m % g);
+    const int b = (int)(m / g);
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (k < p * p * Cin) {
+      const int c = k % Cin, pp = k / Cin;
+      const int py = pp / p, px = pp % p;
+      v = x[(((long long)b * L + gy * p + py) * L + gx * p + px) * Cin + c];
+    }
+    A[i] = v;
+  }
+}
+cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream) {
+  if (L % p != 0 || p * p * Cin > k_pad) return cudaErrorInvalidValue;
+  const long long total = (long long)B * (L / p) * (L / p) * k_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  patchify_kernel<<<blocks, 256, 0, stream>>>(x, A, B, L, p, Cin, k_pad);
+  return cudaGetLastError();
+}
+// fp32 [N, C] table -> bf16 [B, N, C] (position embedding replicated over the batch: residual operand of the
+// patch-embedding GEMM)
+__global__ void replicate_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, int B) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * B;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i % n]);
+}
+cudaError_t launch_replicate_rows_bf16(const float* src, bf16* dst, long long n, int B, cudaStream_t stream) {
+  replicate_rows_bf16_kernel<<<148 * 8, 256, 0, stream>>>(src, dst, n, B);
+  return cudaGetLastError();
+}
+// AdaLN-single modulation vectors (attention.py:498-500): out[j][b][c] = table[j][c] + t[b][j*C + c], j < J
+__global__ void adaln_mod_kernel(const float* __restrict__ table, const float* __restrict__ t, float* __restrict__ out,
+                                 int B, int J, int C, int t_ld) {
+  const int total = J * B * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, b = (i / C) % B, j = i / (C * B);
+    out[i] = table[j * C + c] + t[(long long)b * t_ld + (t_ld == C ? 0 : j * C) + c];
+  }
+}
+cudaError_t launch_adaln_mod(const float* table, const float* t, float* out, int B, int J, int C, int t_ld,
+                             cudaStream_t stream) {
+  const int total = J * B * C;
+  adaln_mod_kernel<<<(total + 255) / 256, 256, 0, stream>>>(table, t, out, B, J, C, t_ld);
+  return cudaGetLastError();
+}
+// unpatchify ([pixart_transformer_2d.py forward tail]: reshape (n,h,w,p,q,c) -> einsum nhwpqc->nchpwq):
+// x fp32 [B*g*g, p*p*oc] (column = (py*p + px)*oc + c) -> out fp32 NCHW (B, oc, g*p, g*p)
+__global__ void unpatchify_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int g, int p, int oc) {
+  const int S = g * p;
+  const long long total = (long long)B * oc * S * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % S);
+    long long r = i / S;
+    const int Y = (int)(r % S);
+    r /= S;
+    const int c = (int)(r % oc), b = (int)(r / oc);
+    const int gy = Y / p, py = Y % p, gx = X / p, px = X % p;
+    out[i] = x[(((long long)b * g + gy) * g + gx) * (p * p * oc) + (py * p + px) * oc + c];
+  }
+}
+cudaError_t launch_unpatchify(const float* x, float* out, int B, int g, int p, int oc, cudaStream_t stream) {
+  unpatchify_kernel<<<148 * 4, 256, 0, stream>>>(x, out, B, g, p, oc);
+  return cudaGetLastError();
+}
+// encoder_attention_mask (1 = keep) -> additive key bias (1 - m) * -10000 ([pixart_transformer_2d.py forward head])
+__global__ void mask_to_bias_kernel(const float* __restrict__ m, float* __restrict__ bias, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bias[i] = (1.f - m[i]) * -10000.f;
+}
+cudaError_t launch_mask_to_bias(const float* mask, float* bias, int n, cudaStream_t stream) {
+  mask_to_bias_kernel<<<(n + 255) / 256, 256, 0, stream>>>(mask, bias, n);
+  return cudaGetLastError();
+}
+
 }  // namespace gdf

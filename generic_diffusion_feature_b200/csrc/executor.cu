@@ -10,6 +10,7 @@
 //   transformer_2d.py:403-530, attention.py:469-592,1249-1258, attention_processor.py:3244-3331,
 //   downsampling.py:132-152, upsampling.py:142-195                                  -> op list below
 //   components/feature_extractor.py:31-76,92-288 (store + id grammar)                -> capture slots
+#include <cstring>
 #include <functional>
 #include <map>
 #include <memory>
@@ -190,6 +191,10 @@ using namespace gdf;
 struct gdf_handle_s {
   gdf_unet_arch ua;
   gdf_vae_arch va;
+  gdf_dit_arch da;
+  bool is_dit = false;
+  float* key_bias = nullptr;     // [B, ctx_len] additive cross-attention bias (DiT), valid when has_key_bias
+  bool has_key_bias = false;
   int device = 0;
   std::unordered_map<std::string, RawW> raw;
   std::unordered_map<std::string, void*> packed;
@@ -513,6 +518,30 @@ class Builder {
     ops->tag(kKindLayerNorm, 0.0, "layernorm M=" + std::to_string(M) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_layernorm(x, y, gm, bt, M, C, eps, nullptr, nullptr, 0, rc.stream));
+      return 0;
+    });
+  }
+  // LayerNorm without affine + AdaLN-single modulation y = LN(x) * (1 + scale[b]) + shift[b] (attention.py:498-503)
+  void layernorm_mod(const bf16* x, bf16* y, long long M, int C, float eps, const float* scale, const float* shift,
+                     int rows_per_batch) {
+    if (dry || err) return;
+    ops->tag(kKindLayerNorm, 0.0, "layernorm-mod M=" + std::to_string(M) + " C=" + std::to_string(C));
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_layernorm(x, y, nullptr, nullptr, M, C, eps, scale, shift, rows_per_batch, rc.stream));
+      return 0;
+    });
+  }
+  // generic-head-dim attention with the handle's optional key bias (PixArt masked cross-attention)
+  void attention_bias(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int B,
+                      int heads, int Nq, int Nk, float scale, int head_dim, bool use_key_bias) {
+    if (dry || err) return;
+    gdf_handle_s* hh = h;
+    ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * head_dim,
+             "attention heads=" + std::to_string(heads) + " d=" + std::to_string(head_dim) + " Nq=" +
+                 std::to_string(Nq) + " Nk=" + std::to_string(Nk));
+    ops->push_back([=](const RunCtx& rc) -> int {
+      const float* kb = (use_key_bias && hh->has_key_bias) ? hh->key_bias : nullptr;
+      OP_CUDA(launch_attention_generic(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, head_dim, scale, rc.stream, kb));
       return 0;
     });
   }
@@ -1097,6 +1126,291 @@ static int build_unet(Builder& b) {
   return b.err;
 }
 
+// ----------------------------------------------------------------------------------------- PixArt DiT
+// [diffusers PixArtTransformer2DModel.forward, un-vendored] around the reference's vendored BasicTransformerBlock
+// (attention.py:469-592, norm_type 'ada_norm_single'); capture sites = feature_extractor.py:259-286.
+static int build_dit(Builder& b) {
+  gdf_handle_s* h = b.h;
+  const gdf_dit_arch& a = h->da;
+  const int B = h->B, p = a.patch_size, heads = a.num_heads, hd = a.head_dim;
+  const int C = heads * hd, g = h->L / p, N = g * g, Lc = h->ctx_len;
+  const long long M = (long long)B * N, Mc = (long long)B * Lc;
+  const float eps = a.norm_eps;
+  const float scale = 1.f / sqrtf((float)hd);
+  const std::string T = "transformer.";
+  b.ops = &h->unet_ops;
+  h->unet_in_cap = -1;
+  if (C % 64 != 0 || hd % 8 != 0 || hd > 160 || p * p * a.in_channels > 64 || a.caption_channels % 8 != 0)
+    return b.set_err(fail(GDF_ERR_UNSUPPORTED, "DiT: hidden size %d / head_dim %d / patch %d unsupported", C, hd, p));
+
+  // ---- conditioning: adaln_single(t) -> t6 [B, 6C], embedded timestep [B, C] (fp32)
+  float* tsin = b.fbuf((long long)B * 256);
+  float* e1 = b.fbuf((long long)B * C);
+  float* emb = b.fbuf((long long)B * C);
+  float* t6 = b.fbuf((long long)B * 6 * C);
+  if (!b.dry) {
+    float* t_dev = h->t_dev;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_timestep_embedding(t_dev, tsin, B, 256, rc.stream));
+      return 0;
+    });
+  }
+  b.small_linear(tsin, T + "adaln_single.emb.timestep_embedder.linear_1", e1, B, 256, C, false, true);
+  b.small_linear(e1, T + "adaln_single.emb.timestep_embedder.linear_2", emb, B, C, C, false, false);
+  b.small_linear(emb, T + "adaln_single.linear", t6, B, C, 6 * C, true, false);
+
+  // ---- caption projection: Linear -> GELU(tanh) -> Linear on [B*Lc, caption_channels]
+  bf16* cp1 = b.buf(Mc, C);
+  bf16* cproj = b.buf(Mc, C);
+  {
+    Epilogue e;
+    e.bias = b.f32(T + "caption_projection.linear_1.bias");
+    e.act = kActGeluTanh;
+    e.out = cp1;
+    e.ld_out = C;
+    b.linear(h->ctx_bf16, Mc, a.caption_channels, a.caption_channels, b.lin(T + "caption_projection.linear_1.weight"), C,
+             e);
+    Epilogue e2;
+    e2.bias = b.f32(T + "caption_projection.linear_2.bias");
+    e2.out = cproj;
+    e2.ld_out = C;
+    b.linear(cp1, Mc, C, C, b.lin(T + "caption_projection.linear_2.weight"), C, e2);
+  }
+  b.rel(cp1);
+
+  // ---- patch embedding + position table: hs = conv(latent) + pos_embed
+  bf16* hs = b.buf(M, C);
+  {
+    const RawW* pe = b.raw(T + "pos_embed.pos_embed");
+    bf16* pos = nullptr;
+    if (pe && !b.dry) {
+      if (pe->numel != (int64_t)N * C)
+        return b.set_err(fail(GDF_ERR_SHAPE, "pos_embed holds %lld values, this plan needs %d x %d (img_size %d)",
+                              (long long)pe->numel, N, C, h->img));
+      pos = b.buf(M, C);
+      if (pos) {
+        cudaError_t ce = launch_replicate_rows_bf16(pe->ptr, pos, (long long)N * C, B, 0);
+        if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+        if (ce != cudaSuccess) return b.set_err(fail(GDF_ERR_CUDA, "pos table: %s", cudaGetErrorString(ce)));
+      }
+    }
+    bf16* col = b.buf(M, 64);
+    if (!b.dry) {
+      bf16* lat = h->latent_nhwc;
+      const int L = h->L, cin = a.in_channels;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_patchify(lat, col, B, L, p, cin, 64, rc.stream));
+        return 0;
+      });
+    }
+    int npad = 0;
+    const bf16* w = b.conv_w(T + "pos_embed.proj.weight", &npad, 64);
+    Epilogue e;
+    e.bias = b.f32_pad(T + "pos_embed.proj.bias", npad);
+    e.n_out = C;
+    e.residual = pos;
+    e.ld_res = C;
+    e.out = hs;
+    e.ld_out = C;
+    b.linear(col, M, 64, 64, w, npad, e);
+    b.rel(col);
+    // `pos` stays allocated for the lifetime of the plan (read by every replay)
+  }
+
+  // ---- transformer blocks
+  float* mod = b.fbuf((long long)6 * B * C);   // [6][B][C]: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+  const long long plane = (long long)B * C;
+  for (int i = 0; i < a.num_layers; ++i) {
+    const std::string wp = T + "transformer_blocks." + std::to_string(i);
+    const std::string fid = "vit-block" + std::to_string(i);
+    const float* table = b.f32(wp + ".scale_shift_table");
+    if (!b.dry) {
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_adaln_mod(table, t6, mod, B, 6, C, 6 * C, rc.stream));
+        return 0;
+      });
+    }
+    // self attention
+    bf16* n1 = b.buf(M, C);
+    b.layernorm_mod(hs, n1, M, C, eps, mod + 1 * plane, mod + 0 * plane, N);
+    const bf16* wqkv = b.rows_bf16(wp + ".attn1#qkv", {wp + ".attn1.to_q.weight", wp + ".attn1.to_k.weight",
+                                                       wp + ".attn1.to_v.weight"}, nullptr);
+    const float* bqkv = nullptr;
+    {
+      const std::string key = wp + ".attn1#qkv_bias";
+      auto it = h->packed.find(key);
+      if (it != h->packed.end()) bqkv = static_cast<const float*>(it->second);
+      else {
+        const float* bq = b.f32(wp + ".attn1.to_q.bias");
+        const float* bk = b.f32(wp + ".attn1.to_k.bias");
+        const float* bv = b.f32(wp + ".attn1.to_v.bias");
+        float* d = static_cast<float*>(b.dev_alloc((size_t)3 * C * 4));
+        if (d && bq && bk && bv) {
+          cudaMemcpy(d, bq, (size_t)C * 4, cudaMemcpyDeviceToDevice);
+          cudaMemcpy(d + C, bk, (size_t)C * 4, cudaMemcpyDeviceToDevice);
+          cudaMemcpy(d + 2 * C, bv, (size_t)C * 4, cudaMemcpyDeviceToDevice);
+        }
+        h->packed[key] = d;
+        bqkv = d;
+      }
+    }
+    bf16* qkv = b.buf(M, 3 * C);
+    {
+      Epilogue e;
+      e.bias = bqkv;
+      e.out = qkv;
+      e.ld_out = 3 * C;
+      Caps caps;
+      caps.add(b.site(fid + "-self-q", C, g, g), 0, C);
+      caps.add(b.site(fid + "-self-k", C, g, g), C, 2 * C);
+      caps.add(b.site(fid + "-self-v", C, g, g), 2 * C, 3 * C);
+      b.linear(n1, M, C, C, wqkv, 3 * C, e, caps);
+    }
+    b.rel(n1);
+    bf16* ao = b.buf(M, C);
+    b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, hd, false);
+    b.rel(qkv);
+    bf16* hs1 = b.buf(M, C);
+    {
+      Epilogue e;
+      e.bias = b.f32(wp + ".attn1.to_out.0.bias");
+      e.col_scale = mod + 2 * plane;   // gate_msa
+      e.rows_per_batch = N;
+      e.residual = hs;
+      e.ld_res = C;
+      e.out = hs1;
+      e.ld_out = C;
+      b.linear(ao, M, C, C, b.lin(wp + ".attn1.to_out.0.weight"), C, e);
+    }
+    b.rel(ao);
+    b.rel(hs);
+    // cross attention on the un-normalised hidden states (attention.py:539-542)
+    bf16* q2 = b.buf(M, C);
+    {
+      Epilogue e;
+      e.bias = b.f32(wp + ".attn2.to_q.bias");
+      e.out = q2;
+      e.ld_out = C;
+      Caps caps;
+      caps.add(b.site(fid + "-cross-q", C, g, g), 0, C);
+      b.linear(hs1, M, C, C, b.lin(wp + ".attn2.to_q.weight"), C, e, caps);
+    }
+    const bf16* wkv = b.rows_bf16(wp + ".attn2#kv", {wp + ".attn2.to_k.weight", wp + ".attn2.to_v.weight"}, nullptr);
+    const float* bkv = nullptr;
+    {
+      const std::string key = wp + ".attn2#kv_bias";
+      auto it = h->packed.find(key);
+      if (it != h->packed.end()) bkv = static_cast<const float*>(it->second);
+      else {
+        const float* bk = b.f32(wp + ".attn2.to_k.bias");
+        const float* bv = b.f32(wp + ".attn2.to_v.bias");
+        float* d = static_cast<float*>(b.dev_alloc((size_t)2 * C * 4));
+        if (d && bk && bv) {
+          cudaMemcpy(d, bk, (size_t)C * 4, cudaMemcpyDeviceToDevice);
+          cudaMemcpy(d + C, bv, (size_t)C * 4, cudaMemcpyDeviceToDevice);
+        }
+        h->packed[key] = d;
+        bkv = d;
+      }
+    }
+    bf16* kv = b.buf(Mc, 2 * C);
+    {
+      Epilogue e;
+      e.bias = bkv;
+      e.out = kv;
+      e.ld_out = 2 * C;
+      b.linear(cproj, Mc, C, C, wkv, 2 * C, e);
+    }
+    bf16* ao2 = b.buf(M, C);
+    b.attention_bias(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, Lc, scale, hd, true);
+    b.rel(q2);
+    b.rel(kv);
+    bf16* hs2 = b.buf(M, C);
+    {
+      Epilogue e;
+      e.bias = b.f32(wp + ".attn2.to_out.0.bias");
+      e.residual = hs1;
+      e.ld_res = C;
+      e.out = hs2;
+      e.ld_out = C;
+      b.linear(ao2, M, C, C, b.lin(wp + ".attn2.to_out.0.weight"), C, e);
+    }
+    b.rel(ao2);
+    b.rel(hs1);
+    // feed-forward: norm2 + mlp modulation, GELU(tanh) (attention.py:570-583, 1249-1258)
+    bf16* n2 = b.buf(M, C);
+    b.layernorm_mod(hs2, n2, M, C, eps, mod + 4 * plane, mod + 3 * plane, N);
+    const int inner = 4 * C;
+    bf16* ffi = b.buf(M, inner);
+    {
+      Epilogue e;
+      e.act = kActGeluTanh;
+      e.bias = b.f32(wp + ".ff.net.0.proj.bias");
+      e.out = ffi;
+      e.ld_out = inner;
+      Caps caps;
+      caps.add(b.site(fid + "-ffn-inner", inner, g, g), 0, inner);
+      b.linear(n2, M, C, C, b.lin(wp + ".ff.net.0.proj.weight"), inner, e, caps);
+    }
+    b.rel(n2);
+    bf16* hs3 = b.buf(M, C);
+    {
+      Epilogue e;
+      e.bias = b.f32(wp + ".ff.net.2.bias");
+      e.col_scale = mod + 5 * plane;   // gate_mlp
+      e.rows_per_batch = N;
+      e.residual = hs2;
+      e.ld_res = C;
+      e.out = hs3;
+      e.ld_out = C;
+      Caps caps;
+      caps.add(b.site(fid + "-out", C, g, g), 0, C);
+      b.linear(ffi, M, inner, inner, b.lin(wp + ".ff.net.2.weight"), C, e, caps);
+    }
+    b.rel(ffi);
+    b.rel(hs2);
+    hs = hs3;
+  }
+  b.rel(cproj);
+
+  // ---- output: norm_out + (scale_shift_table + embedded_timestep) modulation -> proj_out -> unpatchify
+  {
+    float* mod2 = b.fbuf((long long)2 * B * C);   // [2][B][C]: shift, scale
+    const float* table = b.f32(T + "scale_shift_table");
+    if (!b.dry) {
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_adaln_mod(table, emb, mod2, B, 2, C, C, rc.stream));
+        return 0;
+      });
+    }
+    bf16* nf = b.buf(M, C);
+    b.layernorm_mod(hs, nf, M, C, eps, mod2 + plane, mod2, N);
+    b.rel(hs);
+    const int pout = p * p * a.out_channels;
+    const int npad = (pout + 15) / 16 * 16;
+    std::vector<int> idx(npad);
+    for (int r = 0; r < npad; ++r) idx[r] = r < pout ? r : -1;
+    const bf16* w = b.rows_bf16(T + "proj_out#pad", {T + "proj_out.weight"}, &idx);
+    float* o = b.fbuf(M * npad);
+    Epilogue e;
+    e.bias = b.f32_pad(T + "proj_out.bias", npad);
+    e.n_out = pout;
+    e.out_f32 = o;
+    e.ld_out_f32 = npad;
+    b.linear(nf, M, C, C, w, npad, e);
+    b.rel(nf);
+    if (!b.dry) {
+      const int oc = a.out_channels;
+      if (npad != pout) return b.set_err(fail(GDF_ERR_UNSUPPORTED, "DiT: patch^2 * out_channels must be a multiple of 16"));
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        if (rc.noise_pred_out) OP_CUDA(launch_unpatchify(o, rc.noise_pred_out, B, g, p, oc, rc.stream));
+        return 0;
+      });
+    }
+  }
+  return b.err;
+}
+
 // ----------------------------------------------------------------------------------------- VAE encoder
 static int build_vae(Builder& b) {
   gdf_handle_s* h = b.h;
@@ -1330,8 +1644,9 @@ static void free_plan(gdf_handle_s* h) {
   h->arena_bytes = 0;
   h->planned = false;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc);
-  h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr;
+  fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc); fr(h->key_bias);
+  h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr; h->key_bias = nullptr;
+  h->has_key_bias = false;
 }
 
 static int run_ops(gdf_handle_s* h, OpList& ops, const RunCtx& rc) {
@@ -1378,6 +1693,24 @@ int gdf_create(const gdf_unet_arch* unet, const gdf_vae_arch* vae, int device, g
   h->ua = *unet;
   h->va = *vae;
   h->device = device;
+  *out = h;
+  return GDF_OK;
+}
+
+int gdf_create_dit(const gdf_dit_arch* dit, const gdf_vae_arch* vae, int device, gdf_handle* out) {
+  if (!dit || !vae || !out) return fail(GDF_ERR_INVALID, "gdf_create_dit: null argument");
+  if (dit->num_layers < 1 || dit->num_heads < 1 || dit->patch_size < 1 || vae->num_levels > GDF_MAX_LEVELS)
+    return fail(GDF_ERR_INVALID, "gdf_create_dit: bad architecture");
+  GDF_CUDA(cudaSetDevice(device));
+  gdf_handle_s* h = new gdf_handle_s();
+  memset(&h->ua, 0, sizeof(h->ua));
+  h->da = *dit;
+  h->is_dit = true;
+  h->ua.in_channels = dit->in_channels;              // shared latent plumbing (gdf_encode_*, q_sample)
+  h->ua.cross_attention_dim = dit->caption_channels; // width of the fp32 -> bf16 context staging buffer
+  h->va = *vae;
+  h->device = device;
+  h->ctx_len = 300;
   *out = h;
   return GDF_OK;
 }
@@ -1432,7 +1765,7 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   Builder b(h, true);
   std::vector<Site> keep_sites = h->sites;
   int r = build_vae(b);
-  if (!r) r = build_unet(b);
+  if (!r) r = h->is_dit ? build_dit(b) : build_unet(b);
   h->sites = keep_sites;
   h->B = B0;
   h->img = img0;
@@ -1473,7 +1806,8 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
   Builder b(h, false);
   b.gn_ws = static_cast<float*>(h->pool.acquire(gn_workspace_floats(batch, 64) * 4));
   // UNet first: registers the capture sites (incl. unet-in, written by the q_sample kernel of the VAE pass)
-  int r = build_unet(b);
+  if (h->is_dit) GDF_CUDA(cudaMalloc(&h->key_bias, (size_t)batch * h->ctx_len * 4));
+  int r = h->is_dit ? build_dit(b) : build_unet(b);
   if (!r) r = build_vae(b);
   if (r) {
     free_plan(h);
@@ -1534,6 +1868,7 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
   if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: no plan");
   if (ctx_len != h->ctx_len)
     return fail(GDF_ERR_SHAPE, "gdf_denoise_capture: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
+  if (h->is_dit) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: this handle holds a DiT, use gdf_denoise_capture_dit");
   if (!ctx_dev || !arena_dev) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: null input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RunCtx rc;
@@ -1549,6 +1884,28 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
   if (h->unet_in_cap >= 0)  // unet-in (unet_2d_condition.py:1169-1170): the scaled latent, fp16 token-major
     GDF_CUDA(launch_cast_bf16_to_f16(h->latent_nhwc, reinterpret_cast<__half*>(rc.arena + h->unet_in_cap),
                                      (long long)h->B * h->L * h->L * h->ua.in_channels, st));
+  GDF_TRY(run_ops(h, h->unet_ops, rc));
+  return GDF_OK;
+}
+
+int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* ctx_mask_dev,
+                            void* arena_dev, void* noise_pred_out_dev, void* stream) {
+  if (!h || !h->planned || !h->is_dit) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_dit: no DiT plan");
+  if (ctx_len != h->ctx_len)
+    return fail(GDF_ERR_SHAPE, "gdf_denoise_capture_dit: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
+  if (!ctx_dev || !arena_dev) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_dit: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RunCtx rc;
+  rc.stream = st;
+  rc.arena = static_cast<char*>(arena_dev);
+  rc.noise_pred_out = static_cast<float*>(noise_pred_out_dev);
+  fill_f32_kernel<<<(h->B + 255) / 256, 256, 0, st>>>(h->t_dev, timestep, h->B);
+  GDF_CUDA(cudaGetLastError());
+  GDF_CUDA(launch_cast_f32_to_bf16(static_cast<const float*>(ctx_dev), h->ctx_bf16,
+                                   (long long)h->B * h->ctx_len * h->da.caption_channels, st));
+  h->has_key_bias = ctx_mask_dev != nullptr;
+  if (ctx_mask_dev)
+    GDF_CUDA(launch_mask_to_bias(static_cast<const float*>(ctx_mask_dev), h->key_bias, h->B * h->ctx_len, st));
   GDF_TRY(run_ops(h, h->unet_ops, rc));
   return GDF_OK;
 }

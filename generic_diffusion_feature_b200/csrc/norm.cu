@@ -97,23 +97,33 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, 
   }
 }
 
-// Pass 1b: one block per image reduces the per-chunk partials in double precision -> (mean, rstd) per group.
+// Pass 1b: one block per image, one warp per group: lanes stride over the per-chunk partials, double-precision
+// shuffle reduction -> (mean, rstd) per group.
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int HW, int C,
                                           int G, int nchunks, float eps) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
-  double s = 0.0, q = 0.0;
-  const float* src = partial + ((long long)b * nchunks * G + g) * 2;
-  for (int c = 0; c < nchunks; ++c) {
-    s += (double)src[(long long)c * G * 2];
-    q += (double)src[(long long)c * G * 2 + 1];
+  const int b = blockIdx.x, lane = threadIdx.x & 31;
+  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
+    double s = 0.0, q = 0.0;
+    const float2* src = reinterpret_cast<const float2*>(partial) + ((long long)b * nchunks * G + g);
+    for (int c = lane; c < nchunks; c += 32) {
+      const float2 v = __ldg(src + (long long)c * G);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double n = (double)HW * (C / G);
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[(b * G + g) * 2] = (float)mean;
+      stats[(b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
-  const double n = (double)HW * (C / G);
-  const double mean = s / n;
-  double var = q / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[(b * G + g) * 2] = (float)mean;
-  stats[(b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // Pass 2: normalise, affine, optional SiLU.
@@ -148,9 +158,7 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
       sh[j] = __ldg(beta + c) - s_mean[g] * a;
     }
     const long long base = ((long long)b * HW) * C + slot * 8;
-#pragma unroll 4
-    for (int p = p0 + lane_p; p < p1; p += m.lanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)p * C));
+    auto emit = [&](const uint4& u, int p) {
       float v[8];
       float2 f;
       f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
@@ -159,7 +167,7 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
       f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float t = v[j] * sc[j] + sh[j];
+        const float t = fmaf(v[j], sc[j], sh[j]);
         v[j] = silu ? silu_f(t) : t;
       }
       uint4 o;
@@ -168,7 +176,16 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
       o.z = pack_bf16x2(v[4], v[5]);
       o.w = pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4*>(y + base + (long long)p * C) = o;
+    };
+    int p = p0 + lane_p;
+    for (; p + 3 * m.lanes < p1; p += 4 * m.lanes) {   // four independent 128-bit loads in flight per thread
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)p * C));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)(p + m.lanes) * C));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)(p + 2 * m.lanes) * C));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(x + base + (long long)(p + 3 * m.lanes) * C));
+      emit(u0, p); emit(u1, p + m.lanes); emit(u2, p + 2 * m.lanes); emit(u3, p + 3 * m.lanes);
     }
+    for (; p < p1; p += m.lanes) emit(__ldg(reinterpret_cast<const uint4*>(x + base + (long long)p * C)), p);
   }
 }
 
@@ -183,7 +200,7 @@ cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const f
   dim3 grid(nchunks, B);
   float* stats = workspace + (size_t)B * kGnMaxChunks * G * 2;
   groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, workspace, HW, C, G, nchunks);
-  groupnorm_finalize_kernel<<<B, 64, 0, stream>>>(workspace, stats, HW, C, G, nchunks, eps);
+  groupnorm_finalize_kernel<<<B, 1024, 0, stream>>>(workspace, stats, HW, C, G, nchunks, eps);
   groupnorm_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, y, gamma, beta, stats, HW, C, G, nchunks, silu ? 1 : 0);
   return cudaGetLastError();
 }

@@ -77,9 +77,10 @@ cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, c
                                int B, int heads, int Nq, int Nk, float scale, int v_f16, cudaStream_t stream);
 bool attention_uses_tcgen05(int Nk);
 // head dims other than 64 (multiple of 8, <= 160): mma.sync kernel templated on the padded head dim
+// key_bias (optional): fp32 [B, Nk] added to the scaled scores (PixArt's (1 - mask) * -10000 cross-attention bias)
 cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O,
                                      int ldo, int B, int heads, int Nq, int Nk, int D, float scale,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const float* key_bias = nullptr);
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
@@ -107,6 +108,15 @@ cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim
 // small fp32 GEMV-style linear for the conditioning MLPs: y[B, N] = act(x[B, K]) W[N, K]^T + b
 cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
                                 int act_in_silu, int act_out_silu, cudaStream_t stream);
+
+// PixArt DiT helpers (eltwise.cu)
+cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream);
+cudaError_t launch_replicate_rows_bf16(const float* src, bf16* dst, long long n, int B, cudaStream_t stream);
+// out[j][b][c] = table[j][c] + t[b][j*C + c] (t_ld = J*C) or + t[b][c] (t_ld = C)
+cudaError_t launch_adaln_mod(const float* table, const float* t, float* out, int B, int J, int C, int t_ld,
+                             cudaStream_t stream);
+cudaError_t launch_unpatchify(const float* x, float* out, int B, int g, int p, int oc, cudaStream_t stream);
+cudaError_t launch_mask_to_bias(const float* mask, float* bias, int n, cudaStream_t stream);
 
 // ---- feature stack + correspondence (stack.cu)
 struct ResizeSrc {

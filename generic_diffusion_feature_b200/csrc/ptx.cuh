@@ -313,7 +313,15 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_
 }
 
 // ---------------------------------------------------------------- utilities
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) with two MUFU ops (ex2 + rcp, both ~1 ulp-class approximations) instead of an IEEE division
+__device__ __forceinline__ float silu_f(float x) {
+  return x * rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f));
+}
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16/fp16 output rounding): 1 rcp + 1 ex2 + 6 fma
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);
@@ -328,7 +336,9 @@ __device__ __forceinline__ float fast_erf(float x) {
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + fast_erf(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+  // 0.5 x (1 + tanh(u)) = x * sigmoid(2u): ex2 + rcp
+  const float u = k0 * (x + k1 * x * x * x);
+  return x * rcp_approx(1.f + ex2_approx(u * (-2.f * 1.4426950408889634f)));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -12,8 +12,10 @@ Differences a user can observe (all documented in INTEGRATION.md):
     token-major, feature_extractor.py:46-48); values and indexing are identical, `.contiguous()` restores NCHW;
   * `extract(..., noise=(eps_vae, eps_q))` optionally injects the two Gaussian draws the reference makes
     un-seeded (pipeline_pixart_sigma.py:644,671) so that results are reproducible;
-  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion and the DiT families
-    raise NotImplementedError (out of the hot path).
+  * the PixArt versions take prompts = (embeds, mask, neg_embeds, neg_mask) like the reference
+    (diffusion_feature.py:277-283) and, unlike it (B = 1 only, attention.py:498-500), any batch size;
+  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan,
+    IF and Flux raise NotImplementedError.
 """
 import ctypes
 
@@ -63,6 +65,7 @@ class FeatureExtractor(nn.Module):
         self.control = control
         self.attention = attention
         self._plan = None
+        self._plan_ctx_len = None
         self._ids = selected_ids(self.feature_store, pipe)
 
     # ------------------------------------------------------------------------------------------ images
@@ -94,6 +97,13 @@ class FeatureExtractor(nn.Module):
                 prompt_str = f.read()
         import zlib
         g = torch.Generator().manual_seed(zlib.crc32(prompt_str.encode()))
+        if getattr(self.pipe, "dit_cfg", None):
+            # PixArt: (prompt_embeds, prompt_attention_mask, negative_embeds, negative_mask), T5 length 300 for
+            # Sigma (diffusion_feature.py:193-205); the stand-in mask keeps every token
+            cd = self.pipe.dit_cfg["caption_dim"]
+            emb = torch.randn(1, 300, cd, generator=g)
+            neg = torch.randn(1, 300, cd, generator=g)
+            return emb, torch.ones(1, 300), neg, torch.ones(1, 300)
         ctx_dim = self.pipe.unet_cfg["ctx_dim"]
         emb = torch.randn(1, 77, ctx_dim, generator=g)
         neg = torch.randn(1, 77, ctx_dim, generator=g)
@@ -107,9 +117,12 @@ class FeatureExtractor(nn.Module):
         return None   # no text encoder is resident on the B200 path
 
     # ------------------------------------------------------------------------------------------ extract
-    def _ensure_plan(self, batch_size):
-        if self._plan is None or self._plan.batch != batch_size or self._plan.img_size != self.img_size:
+    def _ensure_plan(self, batch_size, ctx_len):
+        if (self._plan is None or self._plan.batch != batch_size or self._plan.img_size != self.img_size
+                or self._plan_ctx_len != ctx_len):
+            check(self.pipe.lib.gdf_set_ctx_len(self.pipe.handle, ctx_len))
             self._plan = FeaturePlan(self.pipe, self._ids, batch_size, self.img_size)
+            self._plan_ctx_len = ctx_len
         return self._plan
 
     @torch.no_grad()
@@ -134,7 +147,15 @@ class FeatureExtractor(nn.Module):
         pipe = self.pipe
         dev = pipe.device
         self.feature_store.reset()
-        prompt_embeds, _neg, pooled, _npooled = prompts
+        is_dit = getattr(pipe, "dit_cfg", None) is not None
+        ctx_mask = None
+        if is_dit:
+            prompt_embeds, ctx_mask, _neg, _neg_mask = prompts      # diffusion_feature.py:277-283
+            pooled = None
+            if ctx_mask is not None and ctx_mask.shape[0] == 1:
+                ctx_mask = ctx_mask.repeat(batch_size, 1)
+        else:
+            prompt_embeds, _neg, pooled, _npooled = prompts
         prompt_embeds = prompt_embeds.repeat(batch_size, 1, 1) if prompt_embeds.shape[0] == 1 else prompt_embeds
         if pooled is not None and pooled.shape[0] == 1:
             pooled = pooled.repeat(batch_size, 1)
@@ -149,7 +170,7 @@ class FeatureExtractor(nn.Module):
         image = image.contiguous()
         if image.shape[0] != batch_size:
             raise ValueError("got %d images for batch_size %d" % (image.shape[0], batch_size))
-        plan = self._ensure_plan(batch_size)
+        plan = self._ensure_plan(batch_size, int(prompt_embeds.shape[1]))
         L = self.img_size // 8
         if noise is None:
             eps_vae = torch.randn(batch_size, 4, L, L, device=dev)
@@ -173,14 +194,20 @@ class FeatureExtractor(nn.Module):
             else:
                 check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb,
                                            qs, None, st))
-            check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
-                                          _lib.ptr(time_ids), _lib.ptr(arena), None, st))
+            if is_dit:
+                mask_d = ctx_mask.to(dev, torch.float32).contiguous() if ctx_mask is not None else None
+                check(lib.gdf_denoise_capture_dit(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(mask_d),
+                                                  _lib.ptr(arena), None, st))
+            else:
+                mask_d = None
+                check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
+                                              _lib.ptr(time_ids), _lib.ptr(arena), None, st))
         feats = plan.views(arena)
         if self.feature_store.accept_all:
             feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
         self.feature_store.feats = feats
         # keep inputs alive until the stream has consumed them
-        self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena)
+        self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena, mask_d)
         return self.feature_store.stored_feats
 
     def set_background_extraction(self, idxs):

@@ -104,6 +104,15 @@ def attention(q, k, v, B, heads, Nq, Nk, scale, head_dim=64, v_f16=False):
     return o
 
 
+def attention_bias(q, k, v, B, heads, Nq, Nk, scale, head_dim, key_bias=None):
+    """Any head_dim (multiple of 8, <= 160), bf16 q/k/v, optional additive fp32 key bias [B, Nk]."""
+    lib = _lib.load()
+    o = torch.zeros(B * Nq, heads * head_dim, dtype=torch.bfloat16, device=q.device)
+    check(lib.gdf_op_attention_bias(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o),
+                                    o.stride(0), B, heads, Nq, Nk, head_dim, scale, ptr(key_bias), stream_ptr()))
+    return o
+
+
 def softmax_rows_(s):
     lib = _lib.load()
     rows, cols = s.shape

@@ -11,6 +11,9 @@ code; their published semantics for the configs models.py selects (SURVEY.md row
   2-1       : EulerDiscrete built from a PNDM config (models.py:38) -> spacing 'linspace' -> [999 .. 0]
   1-5       : PNDM skip_prk_steps, steps_offset 1 -> [1000, 999, 999, 998, ..., 1]
               add_noise sqrt(abar_t) z + sqrt(1 - abar_t) eps, scale_model_input identity
+  pixart-*  : DPMSolverMultistep (order 1 for get_timesteps), beta_schedule 'linear' 1e-4 -> 0.02, spacing
+              'linspace' -> round(linspace(0, 999, 1001))[::-1][:-1]; add_noise alpha_t z + sigma_t eps with
+              alpha_t = sqrt(abar_t), sigma_t = sqrt(1 - abar_t); scale_model_input identity
 """
 import math
 
@@ -42,4 +45,10 @@ def resolve(version, t):
         a = math.sqrt(float(ac[min(ts, 999)]))
         b = math.sqrt(1.0 - float(ac[min(ts, 999)]))
         return float(ts), a, b, 1.0
+    if version.startswith("pixart"):
+        seq = np.linspace(0, 999, 1001).round()[::-1][:-1]
+        ts = int(seq[min(t_start, len(seq) - 1)])
+        betas = np.linspace(0.0001, 0.02, 1000, dtype=np.float32)
+        ac_lin = np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32)
+        return float(ts), math.sqrt(float(ac_lin[ts])), math.sqrt(1.0 - float(ac_lin[ts])), 1.0
     raise NotImplementedError(version)

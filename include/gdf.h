@@ -77,8 +77,26 @@ typedef struct gdf_vae_arch {
   float scaling_factor;               /* 0.18215 / 0.13025 */
 } gdf_vae_arch;
 
+/* PixArt-style DiT denoiser (models.py:71-117 'pixart-sigma' / 'pixart-sigma-512' / 'pixart-alpha'; [diffusers
+ * PixArtTransformer2DModel config, un-vendored]; block arithmetic = the reference's vendored
+ * BasicTransformerBlock with norm_type 'ada_norm_single', feature/diffusers/models/attention.py:469-592). */
+typedef struct gdf_dit_arch {
+  int in_channels;                    /* 4 */
+  int out_channels;                   /* 8 (learned sigma) */
+  int patch_size;                     /* 2 */
+  int num_layers;                     /* 28 */
+  int num_heads;                      /* 16 */
+  int head_dim;                       /* 72 */
+  int caption_channels;               /* 4096 (T5) */
+  float norm_eps;                     /* 1e-6 */
+} gdf_dit_arch;
+
 /* replaces get_diffusion_model (feature/components/models.py:10): the handle owns packed bf16 weights */
 int gdf_create(const gdf_unet_arch* unet, const gdf_vae_arch* vae, int device, gdf_handle* out);
+/* same, DiT denoiser ("transformer.*" parameter names); gdf_load_weights / gdf_finalize_weights / gdf_plan /
+ * gdf_encode_noise / gdf_encode_latents are shared, the forward is gdf_denoise_capture_dit. Feature ids:
+ * vit-block{i}-{self-q,self-k,self-v,cross-q,ffn-inner,out} (feature_extractor.py:259-286). */
+int gdf_create_dit(const gdf_dit_arch* dit, const gdf_vae_arch* vae, int device, gdf_handle* out);
 int gdf_destroy(gdf_handle h);
 
 /* Weights by diffusers parameter name ("unet.down_blocks.0.resnets.0.conv1.weight", "vae.encoder.conv_in.weight",
@@ -136,6 +154,13 @@ int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_
 int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* pooled_dev,
                         const void* add_time_ids_dev, void* arena_dev, void* noise_pred_out_dev, void* stream);
 
+/* One DiT forward with capture (replaces pipe.transformer(...) at diffusion_feature.py:467-474).
+ *   ctx_dev : fp32 (B, ctx_len, caption_channels) caption embeddings (T5), ctx_len as set by gdf_set_ctx_len
+ *   ctx_mask_dev : fp32 (B, ctx_len), 1 = attend, 0 = masked (bias -10000 like the reference), or NULL = all ones
+ *   noise_pred_out_dev : optional fp32 (B, out_channels, h, w) un-patchified model output */
+int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* ctx_mask_dev,
+                            void* arena_dev, void* noise_pred_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ op level
  * Each hot kernel behind a plain entry point: used by the parity tests, by bench.py's roofline probe and by the
  * Python feature-stack / correspondence helpers. */
@@ -187,6 +212,10 @@ int gdf_op_layernorm(const void* x_dev, void* y_dev, const void* gamma_dev, cons
  * kernel) or fp16 bit patterns (v_f16 = 1, tcgen05/TMEM kernel, needs Nk >= 128). */
 int gdf_op_attention(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv, void* o_dev,
                      int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale, int v_f16, void* stream);
+/* any head_dim (multiple of 8, <= 160), bf16 v, optional additive key bias fp32 (B, Nk): PixArt masked cross-attention */
+int gdf_op_attention_bias(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv,
+                          void* o_dev, int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale,
+                          const void* key_bias_dev, void* stream);
 int gdf_op_softmax_rows(void* s_dev, int64_t rows, int cols, int ld, void* stream);
 int gdf_op_upsample_nearest2x(const void* x_dev, void* y_dev, int B, int H, int W, int C, void* stream);
 int gdf_op_im2col_small(const void* src_nchw_f32_dev, const void* src_nhwc_bf16_dev, void* a_dev, int B, int H,

@@ -417,6 +417,200 @@ class UNet2DConditionModel(nn.Module):
         return h
 
 
+# ------------------------------------------------------------------------------------------ PixArt DiT
+DIT_CONFIGS = {
+    # [PixArt-alpha/PixArt-Sigma-XL-2-{1024,512}-MS transformer/config.json, from memory; SURVEY.md row a16]
+    "pixart-sigma": dict(layers=28, heads=16, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=4096,
+                         sample_size=128, interpolation_scale=2.0, eps=1e-6),
+    "pixart-sigma-512": dict(layers=28, heads=16, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=4096,
+                             sample_size=64, interpolation_scale=1.0, eps=1e-6),
+}
+
+
+def sincos_pos_embed_2d(dim, grid, base_size, interpolation_scale):
+    """[diffusers 0.32.2 embeddings.get_2d_sincos_pos_embed, un-vendored]: grid positions
+    arange(grid) / (grid / base_size) / interpolation_scale; first half of the channels encodes the x (width)
+    coordinate, second half y (np.meshgrid(grid_w, grid_h) puts w first); each half = [sin | cos] over
+    omega_k = 10000^(-k / (dim/4)). float64 like numpy, returned fp32 (grid*grid, dim)."""
+    pos = torch.arange(grid, dtype=torch.float32).double() / (grid / base_size) / interpolation_scale
+    gw = pos[None, :].expand(grid, grid).reshape(-1)      # x varies fastest
+    gh = pos[:, None].expand(grid, grid).reshape(-1)
+    quarter = dim // 4
+    omega = 1.0 / 10000 ** (torch.arange(quarter, dtype=torch.float64) / quarter)
+
+    def one(p):
+        o = p[:, None] * omega[None]
+        return torch.cat([torch.sin(o), torch.cos(o)], dim=1)
+    return torch.cat([one(gw), one(gh)], dim=1).float()
+
+
+class PatchEmbed(nn.Module):
+    """[diffusers embeddings.PatchEmbed, un-vendored; equivalent use at transformer_2d.py:541-569]:
+    Conv2d(k = s = patch) -> flatten -> + fixed sin-cos table (a persistent buffer named pos_embed)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        dim = cfg["heads"] * cfg["head_dim"]
+        grid = cfg["sample_size"] // cfg["patch"]
+        self.proj = nn.Conv2d(cfg["in_ch"], dim, cfg["patch"], stride=cfg["patch"])
+        self.register_buffer("pos_embed", sincos_pos_embed_2d(dim, grid, grid, cfg["interpolation_scale"])[None])
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2) + self.pos_embed
+
+
+class _TimestepEmb(nn.Module):
+    """[PixArtAlphaCombinedTimestepSizeEmbeddings without additional conditions]: Timesteps(256, flip, shift 0)
+    -> TimestepEmbedding(256, dim)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.timestep_embedder = TimestepEmbedding(256, dim)
+
+    def forward(self, t):
+        return self.timestep_embedder(timestep_embedding(t, 256))
+
+
+class AdaLayerNormSingle(nn.Module):
+    """[diffusers normalization.AdaLayerNormSingle, un-vendored]: (Linear(SiLU(emb)) -> 6*dim, emb)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.emb = _TimestepEmb(dim)
+        self.linear = nn.Linear(dim, 6 * dim)
+
+    def forward(self, t):
+        e = self.emb(t)
+        return self.linear(F.silu(e)), e
+
+
+class CaptionProjection(nn.Module):
+    """[diffusers embeddings.PixArtAlphaTextProjection, act gelu_tanh]."""
+
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+    def forward(self, c):
+        return self.linear_2(F.gelu(self.linear_1(c), approximate="tanh"))
+
+
+class MaskedAttention(Attention):
+    """Attention (attention_processor.py:3244-3331) with bias on q/k/v and an additive key mask
+    (attention_mask prepared as (1 - mask) * -10000 by the PixArt transformer)."""
+
+    def forward(self, x, ctx=None, key_bias=None):
+        B, N, C = x.shape
+        ctx = x if ctx is None else ctx
+        q, k, v = self.to_q(x), self.to_k(ctx), self.to_v(ctx)
+        _gather(self, q, "q")
+        _gather(self, k, "k")
+        _gather(self, v, "v")
+        d = C // self.heads
+        q = q.view(B, -1, self.heads, d).transpose(1, 2)
+        k = k.view(B, -1, self.heads, d).transpose(1, 2)
+        v = v.view(B, -1, self.heads, d).transpose(1, 2)
+        m = None if key_bias is None else key_bias[:, None, None, :]
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=m)
+        o = o.transpose(1, 2).reshape(B, -1, C)
+        return self.to_out[0](o)
+
+
+class GELUProj(nn.Module):
+    """[diffusers activations.GELU(approximate='tanh'), un-vendored]."""
+
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner)
+
+    def forward(self, x):
+        return F.gelu(self.proj(x), approximate="tanh")
+
+
+class FeedForwardGelu(nn.Module):
+    """attention.py:1209-1258 with activation_fn='gelu-approximate'; `inner` gathered after net[0]."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GELUProj(dim, dim * 4), nn.Identity(), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        for i, m in enumerate(self.net):
+            x = m(x)
+            if i == 0:
+                _gather(self, x, "inner")
+        return x
+
+
+class AdaSingleTransformerBlock(nn.Module):
+    """feature/diffusers/models/attention.py:469-592 with norm_type='ada_norm_single' (:498-503 modulation,
+    :523-524 gate, :539-542 no norm before cross-attention, :570-583 norm2 + mlp modulation + gate)."""
+
+    def __init__(self, dim, heads, eps):
+        super().__init__()
+        self.scale_shift_table = nn.Parameter(torch.zeros(6, dim))
+        self.norm1 = nn.LayerNorm(dim, eps=eps, elementwise_affine=False)
+        self.attn1 = MaskedAttention(dim, heads, bias=True)
+        self.norm2 = nn.LayerNorm(dim, eps=eps, elementwise_affine=False)
+        self.attn2 = MaskedAttention(dim, heads, dim, bias=True)
+        self.ff = FeedForwardGelu(dim)
+
+    def forward(self, x, ctx, key_bias, t6):
+        B = x.shape[0]
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = (self.scale_shift_table[None] + t6.reshape(B, 6, -1)).chunk(6, dim=1)
+        x = g_a * self.attn1(self.norm1(x) * (1 + sc_a) + sh_a) + x
+        x = self.attn2(x, ctx, key_bias) + x
+        x = g_m * self.ff(self.norm2(x) * (1 + sc_m) + sh_m) + x
+        _gather(self, x, "out")
+        return x
+
+
+class PixArtTransformer2DModel(nn.Module):
+    """[diffusers 0.32.2 models/transformers/pixart_transformer_2d.py, un-vendored; the equivalent patch path is
+    visible in the reference at transformers/transformer_2d.py:497-515,541-569]. Parameter names equal diffusers'.
+    Called by the reference at diffusion_feature.py:467-474 with added_cond_kwargs resolution/aspect_ratio None."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        dim = cfg["heads"] * cfg["head_dim"]
+        self.pos_embed = PatchEmbed(cfg)
+        self.adaln_single = AdaLayerNormSingle(dim)
+        self.caption_projection = CaptionProjection(cfg["caption_dim"], dim)
+        self.transformer_blocks = nn.ModuleList([AdaSingleTransformerBlock(dim, cfg["heads"], cfg["eps"])
+                                                 for _ in range(cfg["layers"])])
+        self.norm_out = nn.LayerNorm(dim, eps=cfg["eps"], elementwise_affine=False)
+        self.scale_shift_table = nn.Parameter(torch.zeros(2, dim))
+        self.proj_out = nn.Linear(dim, cfg["patch"] * cfg["patch"] * cfg["out_ch"])
+
+    def forward(self, sample, timestep, ctx, ctx_mask=None):
+        B, _, H, W = sample.shape
+        p, oc = self.cfg["patch"], self.cfg["out_ch"]
+        key_bias = None if ctx_mask is None else (1 - ctx_mask.to(sample.dtype)) * -10000.0
+        x = self.pos_embed(sample)
+        t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(B)
+        t6, emb = self.adaln_single(t)
+        c = self.caption_projection(ctx)
+        for blk in self.transformer_blocks:
+            x = blk(x, c, key_bias, t6)
+        shift, scale = (self.scale_shift_table[None] + emb[:, None]).chunk(2, dim=1)
+        x = self.proj_out(self.norm_out(x) * (1 + scale) + shift)
+        h, w = H // p, W // p
+        x = x.reshape(B, h, w, p, p, oc)
+        return torch.einsum("nhwpqc->nchpwq", x).reshape(B, oc, h * p, w * p)
+
+
+def attach_gatherers_dit(model, store):
+    """prepare_feature_extractor, `hasattr(pipe, 'transformer')` branch (feature_extractor.py:259-286)."""
+    for i, blk in enumerate(model.transformer_blocks):
+        bid = "vit-block%d" % i
+        blk.feature_gatherer = FeatureGatherer(bid, store)
+        blk.attn1.feature_gatherer = FeatureGatherer(bid + "-self", store)
+        blk.attn2.feature_gatherer = FeatureGatherer(bid + "-cross", store)
+        blk.ff.feature_gatherer = FeatureGatherer(bid + "-ffn", store)
+
+
 # ------------------------------------------------------------------------------------------ VAE encoder
 class VaeAttention(nn.Module):
     """[diffusers Attention(512, heads=1, dim_head=512, norm_num_groups=32, residual_connection=True, bias=True)]
@@ -525,6 +719,17 @@ def resolve_timestep(version, t):
         a = float(ac[int(ts)] ** 0.5)
         b = float((1 - ac[int(ts)]) ** 0.5)
         return ts, a, b, 1.0
+    if version.startswith("pixart"):
+        # [PixArt scheduler_config.json, from memory: DPMSolverMultistepScheduler, beta_schedule 'linear'
+        # 1e-4 -> 0.02, timestep_spacing 'linspace', order 1]: timesteps = round(linspace(0, 999, 1001))[::-1][:-1];
+        # add_noise = sqrt(abar) z + sqrt(1 - abar) eps (alpha_t / sigma_t of sigma = sqrt((1 - abar) / abar)),
+        # scale_model_input = identity. PARITY UNPINNED (un-vendored scheduler).
+        import numpy as np
+        seq = np.linspace(0, 999, 1001).round()[::-1][:-1]
+        ts = float(seq[min(t_start, len(seq) - 1)])
+        betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float32)
+        ac_lin = torch.cumprod(1.0 - betas, dim=0)
+        return ts, float(ac_lin[int(ts)] ** 0.5), float((1 - ac_lin[int(ts)]) ** 0.5), 1.0
     raise NotImplementedError(version)
 
 
@@ -557,6 +762,21 @@ def extract(version, unet, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50,
         kw["text_embeds"] = pooled.repeat(B, 1) if pooled.shape[0] == 1 else pooled
         kw["time_ids"] = add_time_ids(img_size or image.shape[-1]).repeat(B, 1)
     noise_pred = unet(x, ts, ctx_b, **kw)
+    return store.stored_feats, latents, noise_pred
+
+
+@torch.no_grad()
+def extract_dit(version, model, vae, store, image, ctx, ctx_mask, eps_vae, eps_q, t=50):
+    """FeatureExtractor.extract for the PixArt versions (diffusion_feature.py:277-283,467-474): prompts =
+    (embeds, mask, neg_embeds, neg_mask), no repeat over the batch in the reference (it only works at B = 1
+    because `timestep` has one entry, attention.py:498-500); here embeds / mask broadcast over B."""
+    store.reset()
+    B = image.shape[0]
+    ts, a, b, s = resolve_timestep(version, t)
+    latents = prepare_latents(vae, image, eps_vae, eps_q, a, b)
+    ctx_b = ctx.expand(B, -1, -1) if ctx.shape[0] == 1 else ctx
+    mask_b = None if ctx_mask is None else (ctx_mask.expand(B, -1) if ctx_mask.shape[0] == 1 else ctx_mask)
+    noise_pred = model(latents * s, ts, ctx_b, mask_b)
     return store.stored_feats, latents, noise_pred
 
 

@@ -19,6 +19,10 @@ TINY_21 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0
 # SD-1.5 topology: 1x1-conv proj_in/out, 8 heads per level -> head dims 8 / 16 / 32 / 32 (generic attention kernel)
 TINY_15 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0, 1, 1, 1), depth=(1, 1, 1, 1),
                heads=(8, 8, 8, 8), ctx_dim=128, linear_proj=False, add_time_dim=0, add_in=0, eps=1e-5)
+# PixArt-Sigma topology at reduced size: the real head_dim (72 -> padded-head-dim attention kernel), hidden 576,
+# patch 2 on a 16x16 latent (128x128 images) -> 64 tokens, caption width 256
+TINY_DIT = dict(layers=2, heads=8, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=256, sample_size=16,
+                interpolation_scale=2.0, eps=1e-6)
 TINY_VAE = dict(block_out=(64, 64, 128, 128), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025)
 
 
@@ -45,6 +49,28 @@ def build_oracle(unet_cfg, vae_cfg, sd):
     unet.load_state_dict(usd, strict=True)
     vae.load_state_dict(vsd, strict=True)
     return unet.eval(), vae.eval()
+
+
+def build_oracle_dit(dit_cfg, vae_cfg, sd):
+    """Oracle PixArt transformer + VAE from a 'transformer.*' / 'vae.*' state dict (fp32, CPU)."""
+    model = O.PixArtTransformer2DModel(dit_cfg)
+    vae = O.Vae(vae_cfg["scaling_factor"], block_out=vae_cfg["block_out"], layers=vae_cfg["layers"],
+                latent=vae_cfg["latent"], eps=vae_cfg["eps"])
+    tsd = {k[len("transformer."):]: v.float().cpu() for k, v in sd.items() if k.startswith("transformer.")}
+    vsd = {k[len("vae."):]: v.float().cpu() for k, v in sd.items() if k.startswith("vae.")}
+    model.load_state_dict(tsd, strict=True)
+    vae.load_state_dict(vsd, strict=True)
+    return model.eval(), vae.eval()
+
+
+def make_dit_inputs(batch, img, caption_dim, ctx_len=24, masked_tail=5):
+    """Images / noise as make_inputs; caption embeddings N(0,1) seed 1235 (1, ctx_len, caption_dim) and an
+    attention mask whose last `masked_tail` tokens are padding (0), like a tokenised short prompt."""
+    image, ctx, _, eps_vae, eps_q = make_inputs(batch, img, caption_dim, None, ctx_len)
+    mask = torch.ones(1, ctx_len)
+    if masked_tail:
+        mask[:, ctx_len - masked_tail:] = 0
+    return image, ctx, mask, eps_vae, eps_q
 
 
 def compare_maps(got, want):

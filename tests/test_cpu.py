@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import O, ROOT, TINY_21, TINY_VAE, TINY_XL, build_oracle, make_inputs
+from common import O, ROOT, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, make_inputs
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -43,6 +43,44 @@ def test_oracle_matches_reference_vendored_unet(fixture, version, cfg):
         assert got.shape == ref.shape, k
         tol = 2e-3 * max(1.0, ref.abs().max().item())      # fp16 rounding of the stored fixture
         assert (got - ref).abs().max().item() <= tol, k
+
+
+def test_oracle_matches_reference_vendored_dit_blocks():
+    """tests/golden/dit_tiny_pixart.pt: the reference's vendored BasicTransformerBlock (ada_norm_single) stack +
+    its real prepare_feature_extractor PixArt branch (tools/make_golden.py); the oracle reproduces every map."""
+    from generic_diffusion_feature_b200.components.feature_extractor import _dit_feature_ids
+    gold = torch.load(os.path.join(GOLD, "dit_tiny_pixart.pt"), weights_only=False)
+    assert gold["ids"] == _dit_feature_ids(TINY_DIT)
+    sd = _models().synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, TINY_DIT)
+    model, _ = build_oracle_dit(TINY_DIT, TINY_VAE, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers_dit(model, store)
+    with torch.no_grad():
+        out = model(gold["x"], gold["timestep"], gold["ctx"], gold["mask"])
+    assert list(store.feats.keys()) == gold["ids"]
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+
+
+def test_dit_param_specs_and_pos_embed_match_oracle():
+    m = _models()
+    for ver in ("pixart-sigma", "pixart-sigma-512"):
+        cfg = m.DIT_CONFIGS[ver]
+        assert cfg == O.DIT_CONFIGS[ver]
+        with torch.device("meta"):
+            model = O.PixArtTransformer2DModel(cfg)
+        want = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        assert dict(m.dit_param_specs(cfg)) == want
+    n = sum(int(np.prod(s)) for k, s in m.dit_param_specs(m.DIT_CONFIGS["pixart-sigma"]) if "pos_embed.pos_embed" not in k)
+    assert 0.60e9 < n < 0.62e9              # PixArt-Sigma-XL/2: 0.61 B parameters
+    a = m.sincos_pos_embed_2d(64, 8, 8, 2.0)
+    b = O.sincos_pos_embed_2d(64, 8, 8, 2.0)
+    assert a.shape == (64, 64) and (a - b).abs().max().item() < 1e-6
+    # first half encodes x (fastest-varying token index), second half y
+    assert (a[0, :32] - a[8, :32]).abs().max().item() < 1e-7 and (a[0, 32:] - a[1, 32:]).abs().max().item() < 1e-7
 
 
 def test_oracle_correspondence_matches_reference():
@@ -140,13 +178,17 @@ def test_synthetic_weights_are_deterministic_by_name():
 
 
 @pytest.mark.parametrize("version,t,want_ts", [("xl", 50, 50.0), ("2-1", 50, 49.0), ("1-5", 50, 51.0),
-                                               ("xl", 250, 250.0), ("1-5", 1, 2.0)])
+                                               ("xl", 250, 250.0), ("1-5", 1, 2.0), ("pixart-sigma", 50, 50.0),
+                                               ("pixart-sigma-512", 261, 261.0)])
 def test_scheduler_resolution(version, t, want_ts):
     from generic_diffusion_feature_b200 import schedulers
     ts, a, b, s = schedulers.resolve(version, t)
     ots, oa, ob, os_ = O.resolve_timestep(version, t)
     assert ts == want_ts == ots
     assert abs(a - oa) < 1e-6 and abs(b - ob) < 1e-5 and abs(s - os_) < 1e-6
+    if version.startswith("pixart"):
+        assert s == 1.0 and abs(a * a + b * b - 1.0) < 1e-5     # variance-preserving q_sample, linear betas
+        return
     # both forms are the same q_sample: (a*z + b*eps)*s = sqrt(abar) z + sqrt(1-abar) eps
     abar = float(O.alphas_cumprod()[int(ts)])
     assert abs(a * s - abar ** 0.5) < 1e-5 and abs(b * s - (1 - abar) ** 0.5) < 1e-5
@@ -212,16 +254,16 @@ def test_struct_layouts_match_header():
     import subprocess
     import tempfile
     from generic_diffusion_feature_b200 import _lib
-    src = ('#include <stdio.h>\n#include "gdf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(gdf_epilogue),'
+    src = ('#include <stdio.h>\n#include "gdf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gdf_epilogue),'
            'sizeof(gdf_capture_seg), sizeof(gdf_unet_arch), sizeof(gdf_vae_arch), sizeof(gdf_slot),'
-           'sizeof(gdf_resize_src));return 0;}')
+           'sizeof(gdf_resize_src), sizeof(gdf_dit_arch));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o",
                                os.path.join(d, "p")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
     got = [ctypes.sizeof(c) for c in (_lib.Epilogue, _lib.CaptureSeg, _lib.UNetArch, _lib.VaeArch, _lib.Slot,
-                                      _lib.ResizeSrc)]
+                                      _lib.ResizeSrc, _lib.DitArch)]
     assert got == sizes
 
 

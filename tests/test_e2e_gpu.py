@@ -6,7 +6,8 @@ max-relative error (max |diff| / max |ref|) is reported and bounded at 5e-2 for 
 import pytest
 import torch
 
-from common import O, TINY_15, TINY_21, TINY_VAE, TINY_XL, build_oracle, compare_maps, make_inputs
+from common import (O, TINY_15, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, compare_maps,
+                    make_dit_inputs, make_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -65,6 +66,70 @@ def test_tiny_21_full_set(cuda_dev):
 def test_tiny_15_full_set(cuda_dev):
     """SD-1.5 topology: conv proj_in/out, PNDM timestep (t=50 -> 51), head dims != 64."""
     _run_case("1-5", TINY_15, batch=2, img=128)
+
+
+def _run_dit_case(batch, img, masked_tail, dcfg=TINY_DIT, ctx_len=24):
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _dit_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, dcfg)
+    image, ctx, mask, eps_vae, eps_q = make_dit_inputs(batch, img, dcfg["caption_dim"], ctx_len, masked_tail)
+    ids = _dit_feature_ids(dcfg)
+    layer = {i: True for i in ids}
+    model, vae = build_oracle_dit(dcfg, TINY_VAE, sd)
+    store = O.FeatureStore(layer)
+    O.attach_gatherers_dit(model, store)
+    want, _, _ = O.extract_dit("pixart-sigma", model, vae, store, image, ctx, mask, eps_vae, eps_q, t=50)
+    pipe = models.get_diffusion_model("pixart-sigma", "float16", device="cuda:0", state_dict=sd, dit_cfg=dcfg,
+                                      vae_cfg=TINY_VAE)
+    fe = FeatureExtractor(layer, "pixart-sigma", "cuda:0", img_size=img, external_model=pipe)
+    got = fe.extract((ctx, mask, ctx, mask), batch, image.cuda(), image_type="tensors", t=50, noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == list(want.keys()) == ids
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "DiT maps out of tolerance (id, cos, rel, maxrel): %s" % bad[:8]
+    return rows
+
+
+def test_tiny_pixart_full_set(cuda_dev):
+    """BASELINE.json configs[3] topology (PixArt-Sigma DiT: per-block attention q/k/v, cross-q, FFN inner, block
+    output) at reduced size, batch 2 (the reference itself only supports B = 1), padded caption mask."""
+    rows = _run_dit_case(batch=2, img=128, masked_tail=5)
+    assert len(rows) == 6 * TINY_DIT["layers"]
+
+
+def test_tiny_pixart_no_mask_batch1(cuda_dev):
+    _run_dit_case(batch=1, img=128, masked_tail=0)
+
+
+def test_cuda_matches_reference_vendored_dit_golden(cuda_dev):
+    """CUDA DiT path vs the fixture produced by the REFERENCE's vendored ada_norm_single transformer blocks and its
+    own FeatureStore (tools/make_golden.py); latents through the 4-channel branch of prepare_latents, zero noise."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "dit_tiny_pixart.pt"), weights_only=False)
+    sd = models.synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, TINY_DIT)
+    pipe = models.get_diffusion_model("pixart-sigma", "float16", device="cuda:0", state_dict=sd, dit_cfg=TINY_DIT,
+                                      vae_cfg=TINY_VAE)
+    img = 8 * gold["x"].shape[-1]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, "pixart-sigma", "cuda:0", img_size=img, external_model=pipe)
+    ts, a, b, s = schedulers.resolve("pixart-sigma", 50)
+    assert ts == gold["timestep"]
+    lat = gold["x"] / (a * s)
+    zero = torch.zeros_like(gold["x"])
+    got = fe.extract((gold["ctx"], gold["mask"], gold["ctx"], gold["mask"]), 1, lat.cuda(), image_type="tensors", t=50,
+                     noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"]
+    rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
 
 
 def test_unknown_id_and_unbuilt_features(cuda_dev):

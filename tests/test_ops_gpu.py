@@ -250,6 +250,28 @@ def test_attention_other_head_dims(cuda_dev, D, heads, Nq, Nk):
     check_close(o, want, what="attention d=%d" % D)
 
 
+@pytest.mark.parametrize("D,heads,Nq,Nk", [(72, 16, 512, 300), (72, 8, 64, 24), (64, 4, 200, 77)])
+def test_attention_key_bias(cuda_dev, D, heads, Nq, Nk):
+    """PixArt masked cross-attention: additive (1 - mask) * -10000 key bias (ragged valid length per batch)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(29)
+    B, C = 2, heads * D
+    q = _rand_bf16(g, B * Nq, C)
+    kv = _rand_bf16(g, B * Nk, 2 * C)
+    k, v = kv[:, :C], kv[:, C:]
+    mask = torch.ones(B, Nk, device="cuda")
+    mask[0, Nk // 3:] = 0
+    mask[1, Nk - 1:] = 0
+    bias = (1 - mask) * -10000.0
+    o = ops.attention_bias(q, k, v, B, heads, Nq, Nk, D ** -0.5, D, bias)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Nq, heads, D).transpose(1, 2)
+    kf = k.float().reshape(B, Nk, heads, D).transpose(1, 2)
+    vf = v.float().reshape(B, Nk, heads, D).transpose(1, 2)
+    want = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=bias[:, None, None, :])
+    check_close(o, want.transpose(1, 2).reshape(B * Nq, C), what="attention key bias d=%d" % D)
+
+
 def test_attention_peaked_softmax(cuda_dev):
     """Large score range (peaked rows) through the half2-exp path of the tcgen05 kernel."""
     ops = _ops()

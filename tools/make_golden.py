@@ -28,9 +28,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import ref_shim  # noqa: E402
-from common import O, TINY_21, TINY_VAE, TINY_XL, build_oracle, make_inputs  # noqa: E402
+from common import (O, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, make_dit_inputs,  # noqa: E402
+                    make_inputs)
 from generic_diffusion_feature_b200.components import models  # noqa: E402
-from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids  # noqa: E402
+from generic_diffusion_feature_b200.components.feature_extractor import _dit_feature_ids, _unet_feature_ids  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -79,6 +80,79 @@ def golden_unet(version, cfg, name):
     torch.save({"version": version, "ids": ids, "x": x, "ctx": ctx, "pooled": pooled, "timestep": 50.0,
                 "noise_pred": out, "feats": {k: v.to(torch.float16) for k, v in feats.items()},
                 "generator": "tools/make_golden.py via tools/ref_shim.py (reference vendored modules)"},
+               os.path.join(OUT, name))
+
+
+def golden_dit(name="dit_tiny_pixart.pt"):
+    """PixArt path: the reference's vendored BasicTransformerBlock (attention.py:469-592, norm_type
+    'ada_norm_single', attention_bias, gelu-approximate FeedForward) + vendored Attention / AttnProcessor2_0 +
+    the reference's real prepare_feature_extractor (PixArt branch, feature_extractor.py:259-286) / FeatureStore.
+    The outer model (PatchEmbed, AdaLayerNormSingle, caption projection, output head) is un-vendored in the
+    reference and comes from the oracle's restatement -> those pieces stay PARITY UNPINNED."""
+    import torch.nn as nn
+    root = ref_shim.install()
+    cfg = TINY_DIT
+    C = cfg["heads"] * cfg["head_dim"]
+    sd = models.synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, cfg)
+    omodel, _ = build_oracle_dit(cfg, TINY_VAE, sd)
+
+    class RefDit(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.outer = omodel
+            self.transformer_blocks = nn.ModuleList([
+                root.attention.BasicTransformerBlock(C, cfg["heads"], cfg["head_dim"], cross_attention_dim=C,
+                                                     activation_fn="gelu-approximate", attention_bias=True,
+                                                     norm_type="ada_norm_single", norm_elementwise_affine=False,
+                                                     norm_eps=cfg["eps"]) for _ in range(cfg["layers"])])
+
+        def forward(self, sample, timestep, ctx, mask):
+            o = self.outer
+            B = sample.shape[0]
+            bias = ((1 - mask) * -10000.0)[:, None, :]            # [pixart_transformer_2d.py forward head]
+            x = o.pos_embed(sample)
+            t6, emb = o.adaln_single(torch.full((B,), float(timestep)))
+            c = o.caption_projection(ctx)
+            for blk in self.transformer_blocks:
+                x = blk(x, encoder_hidden_states=c, encoder_attention_mask=bias, timestep=t6)
+            shift, scale = (o.scale_shift_table[None] + emb[:, None]).chunk(2, dim=1)
+            x = o.proj_out(o.norm_out(x) * (1 + scale) + shift)
+            g, p, oc = sample.shape[-1] // cfg["patch"], cfg["patch"], cfg["out_ch"]
+            x = x.reshape(B, g, g, p, p, oc)
+            return torch.einsum("nhwpqc->nchpwq", x).reshape(B, oc, g * p, g * p)
+
+    ref = RefDit().eval()
+    for i, blk in enumerate(ref.transformer_blocks):
+        blk.load_state_dict({k[len("transformer.transformer_blocks.%d." % i):]: v for k, v in sd.items()
+                             if k.startswith("transformer.transformer_blocks.%d." % i)}, strict=True)
+    rfe = ref_shim.load_reference_feature_extractor()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.transformer = ref
+    ids = _dit_feature_ids(cfg)
+    store = rfe.prepare_feature_extractor("pixart-sigma", pipe, {i: True for i in ids}, 1, True)
+    g = torch.Generator().manual_seed(4321)
+    L = cfg["sample_size"]
+    x = torch.randn(1, 4, L, L, generator=g)
+    _, ctx, mask, _, _ = make_dit_inputs(1, 8 * L, cfg["caption_dim"])
+    ctx_b, mask_b = ctx, mask
+    with torch.no_grad():
+        out = ref(x, 50.0, ctx_b, mask_b)
+    feats = store.stored_feats
+    assert list(feats.keys()) == ids, list(feats.keys())[:8]
+    ostore = O.FeatureStore({i: True for i in ids})
+    O.attach_gatherers_dit(omodel, ostore)
+    with torch.no_grad():
+        oout = omodel(x, 50.0, ctx_b, mask_b)
+    worst = max((feats[k] - ostore.feats[k]).abs().max().item() for k in ids)
+    print("%s: %d maps from the reference's vendored blocks; oracle max |diff| %.2e (out %.2e)"
+          % (name, len(ids), worst, (out - oout).abs().max().item()))
+    assert worst < 1e-3
+    torch.save({"ids": ids, "x": x, "ctx": ctx, "mask": mask, "timestep": 50.0, "noise_pred": out,
+                "feats": {k: v.to(torch.float16) for k, v in feats.items()},
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference vendored transformer blocks)"},
                os.path.join(OUT, name))
 
 
@@ -141,5 +215,6 @@ if __name__ == "__main__":
     golden_ids()
     golden_unet("xl", TINY_XL, "unet_tiny_xl.pt")
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
+    golden_dit()
     golden_correspondence()
     golden_extract()
