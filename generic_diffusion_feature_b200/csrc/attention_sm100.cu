@@ -91,7 +91,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
 
   if (warp == 0) {
     // ================================================= TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * kFaTile);
       tma_load_3d(smem, &map_q, q_full, h * 64, q0, b);
       tma_load_3d(smem + kFaTile, &map_q, q_full, h * 64, q0 + 128, b);
@@ -100,12 +100,12 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
     uint32_t ph = 0;
     for (int j = 0; j < n; ++j) {
       mbar_wait(&k_empty[s], ph ^ 1);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[s], kFaTile);
         tma_load_3d(smem + kFaOffK + s * kFaTile, &map_k, &k_full[s], h * 64, j * 128, b);
       }
       mbar_wait(&v_empty[s], ph ^ 1);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[s], kFaTile);
         tma_load_3d(smem + kFaOffV + s * kFaTile, &map_v, &v_full[s], h * 64, j * 128, b);
       }
@@ -140,7 +140,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: single active lane known to the compiler -> plain uniform-register operands
       issue_s(0, 0);
       issue_s(1, 0);
       umma_commit(&k_empty[0]);
@@ -155,9 +155,11 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       for (int t = 0; t < 2; ++t) {
         if (next_s[t] < n) {
           const int js = next_s[t], slot = js % kFaRing;
-          if (mbar_try_wait(&s_free[t], (js - 1) & 1) && mbar_try_wait(&k_full[slot], (js / kFaRing) & 1)) {
+          // warp-uniform decision (a completed phase observed by any lane is complete for all)
+          if (__any_sync(0xffffffffu, mbar_try_wait(&s_free[t], (js - 1) & 1) &&
+                                          mbar_try_wait(&k_full[slot], (js / kFaRing) & 1))) {
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               issue_s(t, slot);
               if (s_issued[slot] == 1) umma_commit(&k_empty[slot]);   // both query tiles have consumed K(js)
             }
@@ -168,9 +170,10 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
         }
         if (next_pv[t] < n) {
           const int jp = next_pv[t], slot = jp % kFaRing;
-          if (mbar_try_wait(&p_full[t], jp & 1) && mbar_try_wait(&v_full[slot], (jp / kFaRing) & 1)) {
+          if (__any_sync(0xffffffffu, mbar_try_wait(&p_full[t], jp & 1) &&
+                                          mbar_try_wait(&v_full[slot], (jp / kFaRing) & 1))) {
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               issue_pv(t, slot);
               if (pv_issued[slot] == 1) umma_commit(&v_empty[slot]);
             }

@@ -189,7 +189,9 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
                                                 const float* v /*32*/, int col, const StoreCoord& sc) {
   (void)toggle;
   uint8_t* buf = stg_warp;              // generic path: one buffer, fully drained around every store
-  if (lane == 0) bulk_wait_read<0>();
+  // elect.sync picks the same leader lane for the same member mask every time (PTX ISA), so issue / commit / wait
+  // stay on one thread; and the compiler knows a single lane is active -> no uniform-register waterfall loops
+  if (elect_one()) bulk_wait_read<0>();
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -206,7 +208,7 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one()) {
     if (sc.conv) tma_store_4d(map, buf, col, sc.c1, sc.c2, sc.c3);
     else tma_store_3d(map, buf, col, sc.c1, sc.c2);
     bulk_commit();
@@ -281,13 +283,13 @@ __device__ __forceinline__ void store_round(const CUtensorMap* map_a, int col_a,
                                             bool two, uint8_t* stg_warp, int& toggle, int lane, const int (&swz)[4],
                                             const float* v0, const float* v1, const StoreCoord& sc) {
   uint8_t* buf = stg_warp + toggle * 4096;
-  if (lane == 0) bulk_wait_read<1>();
+  if (elect_one()) bulk_wait_read<1>();
   __syncwarp();
   stage_chunk<kF16>(buf, swz, v0);
   if (two) stage_chunk<kF16>(buf + 2048, swz, v1);
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one()) {
     issue_store(map_a, buf, col_a, sc);
     if (two) issue_store(map_a, buf + 2048, col_a + 32, sc);
     if (map_b) {
@@ -402,7 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler knows a single lane is active -> plain uniform-register moves
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_tx_bytes);
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + kStageBytesA;
@@ -449,7 +451,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
             const uint64_t da = umma_desc_kmajor_sw128(a_addr);
             const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
@@ -711,7 +713,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
-    if (lane == 0) bulk_wait<0>();   // all bulk stores of this warp have completed before the CTA retires
+    __syncwarp();
+    if (elect_one()) bulk_wait<0>();   // all bulk stores of this warp have completed before the CTA retires
   }
 
   tc_fence_before();
