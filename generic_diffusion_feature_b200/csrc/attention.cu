@@ -56,6 +56,8 @@ attention64_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__
   uint8_t* sQ = att_smem;
   uint8_t* sK = att_smem + kAttBM * kAttD * 2;
   uint8_t* sV = sK + 2 * kAttBN * kAttD * 2;
+  pdl_wait();
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kAttBM;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -243,9 +245,8 @@ cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, c
     return cudaSuccess;
   }
   dim3 grid((Nq + kAttBM - 1) / kAttBM, heads, B);
-  attention64_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
-                                                            scale * 1.4426950408889634f);
-  return cudaGetLastError();
+  return launch_pdl(attention64_kernel, grid, dim3(kAttThreads), kAttSmem, stream, Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
+                    scale * 1.4426950408889634f);
 }
 
 // ------------------------------------------------------------------------------------------ row softmax

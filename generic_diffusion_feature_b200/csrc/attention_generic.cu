@@ -48,6 +48,8 @@ attention_generic_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __rest
   uint8_t* sQ = ga_smem;
   uint8_t* sK = ga_smem + kGaBM * RS;
   uint8_t* sV = sK + 2 * kGaBN * RS;
+  pdl_wait();
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * kGaBM;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -214,9 +216,8 @@ static cudaError_t launch_ga(const bf16* Q, int ldq, const bf16* K, int ldk, con
     attr_set = true;
   }
   dim3 grid((Nq + kGaBM - 1) / kGaBM, heads, B);
-  attention_generic_kernel<DP><<<grid, kGaThreads, GaCfg<DP>::kSmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk,
-                                                                                D, scale * 1.4426950408889634f, key_bias);
-  return cudaGetLastError();
+  return launch_pdl(attention_generic_kernel<DP>, grid, dim3(kGaThreads), (size_t)GaCfg<DP>::kSmem, stream, Q, ldq, K, ldk,
+                    V, ldv, O, ldo, Nq, Nk, D, scale * 1.4426950408889634f, key_bias);
 }
 
 cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O,

@@ -85,6 +85,8 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail; Q/K/V are only read from here on
+  pdl_trigger();
 
   // register rebalancing: the producer / MMA / allocator warpgroup needs few registers, the softmax warpgroups many
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -365,8 +367,7 @@ int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, c
   p.O = O;
   p.ldo = ldo;
   dim3 grid((Nq + 255) / 256, heads, B);
-  attention64_tcgen05_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(mq, mk, mv, p);
-  GDF_CUDA(cudaGetLastError());
+  GDF_CUDA(launch_pdl(attention64_tcgen05_kernel, grid, dim3(kFaThreads), (size_t)kFaSmem, stream, mq, mk, mv, p));
   return GDF_OK;
 }
 

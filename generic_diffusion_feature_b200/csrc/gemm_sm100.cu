@@ -370,6 +370,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlaps the previous kernel's tail; operands / destinations only from here on
+  pdl_trigger();
 
   // work unit = CG vertically adjacent 128-row tiles x one block_n column tile
   const int num_m_units = (p.num_m_tiles + CG - 1) / CG;
@@ -776,9 +778,9 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   if (total_units <= 0) return cudaSuccess;
   if (cg == 1) {
     const int grid = total_units < g_num_sms ? total_units : g_num_sms;
-    if (p.act == kActGeglu) gemm_tcgen05_kernel<1, true><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
-    else gemm_tcgen05_kernel<1, false><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(maps, p);
-    return cudaGetLastError();
+    if (p.act == kActGeglu)
+      return launch_pdl(gemm_tcgen05_kernel<1, true>, dim3(grid), dim3(kGemmThreads), (size_t)kGemmSmemBytes, stream, maps, p);
+    return launch_pdl(gemm_tcgen05_kernel<1, false>, dim3(grid), dim3(kGemmThreads), (size_t)kGemmSmemBytes, stream, maps, p);
   }
   if (g_pair_ctas < 2) return cudaErrorInvalidConfiguration;
   const int grid = 2 * total_units < g_pair_ctas ? 2 * total_units : g_pair_ctas;
@@ -787,13 +789,15 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = kGemmSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (p.act == kActGeglu) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, maps, p);
 }

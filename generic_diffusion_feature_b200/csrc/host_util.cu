@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <mutex>
 
@@ -68,6 +69,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                 rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
   }
   return GDF_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDF_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
 }
 
 }  // namespace gdf

@@ -35,6 +35,8 @@ size_t gn_workspace_floats(int B, int G) { return (size_t)B * kGnMaxChunks * G *
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int nchunks) {
   __shared__ float s_sum[64], s_sq[64];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, chunk = blockIdx.x;
   const GnMap m = gn_map(C);
   const int cpg = C / G;
@@ -101,6 +103,8 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, 
 // shuffle reduction -> (mean, rstd) per group.
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int HW, int C,
                                           int G, int nchunks, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x, lane = threadIdx.x & 31;
   for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
     double s = 0.0, q = 0.0;
@@ -132,6 +136,8 @@ groupnorm_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const f
                        const float* __restrict__ beta, const float* __restrict__ partial, int HW, int C, int G,
                        int nchunks, int silu) {
   __shared__ float s_mean[64], s_rstd[64];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, chunk = blockIdx.x;
   const GnMap m = gn_map(C);
   const int cpg = C / G;
@@ -199,10 +205,13 @@ cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const f
   if (nchunks < 1) nchunks = 1;
   dim3 grid(nchunks, B);
   float* stats = workspace + (size_t)B * kGnMaxChunks * G * 2;
-  groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, workspace, HW, C, G, nchunks);
-  groupnorm_finalize_kernel<<<B, 1024, 0, stream>>>(workspace, stats, HW, C, G, nchunks, eps);
-  groupnorm_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, y, gamma, beta, stats, HW, C, G, nchunks, silu ? 1 : 0);
-  return cudaGetLastError();
+  cudaError_t e = launch_pdl(groupnorm_stats_kernel, grid, dim3(kGnThreads), 0, stream, x, workspace, HW, C, G, nchunks);
+  if (e != cudaSuccess) return e;
+  e = launch_pdl(groupnorm_finalize_kernel, dim3(B), dim3(1024), 0, stream, (const float*)workspace, stats, HW, C, G,
+                 nchunks, eps);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(groupnorm_apply_kernel, grid, dim3(kGnThreads), 0, stream, x, y, gamma, beta, (const float*)stats, HW,
+                    C, G, nchunks, silu ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
@@ -213,6 +222,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long long M, int C, float eps, const float* __restrict__ mod_scale,
                  const float* __restrict__ mod_shift, int rows_per_batch) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -294,13 +305,17 @@ cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const f
   const int rpb = rows_per_batch > 0 ? rows_per_batch : 1;
   const int nv = C / 8;
   if (nv <= 64)
-    layernorm_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+    return launch_pdl(layernorm_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y, gamma, beta, M, C, eps,
+                      mod_scale, mod_shift, rpb);
   else if (nv <= 96)
-    layernorm_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+    return launch_pdl(layernorm_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y, gamma, beta, M, C, eps,
+                      mod_scale, mod_shift, rpb);
   else if (nv <= 160)
-    layernorm_kernel<5><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+    return launch_pdl(layernorm_kernel<5>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y, gamma, beta, M, C, eps,
+                      mod_scale, mod_shift, rpb);
   else if (nv <= 384)
-    layernorm_kernel<12><<<(unsigned)blocks, 256, 0, stream>>>(x, y, gamma, beta, M, C, eps, mod_scale, mod_shift, rpb);
+    return launch_pdl(layernorm_kernel<12>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y, gamma, beta, M, C, eps,
+                      mod_scale, mod_shift, rpb);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
