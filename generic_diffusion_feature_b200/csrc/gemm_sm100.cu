@@ -328,13 +328,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_rows = p.block_n / CG;                         // B rows staged by this CTA
   const int stage_bytes = kStageBytesA + b_rows * kBlockK * 2;
-  uint8_t* stg = smem + kPipeBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes + kStagingBytes);
+  uint8_t* stg = smem;                                      // [epilogue warp][4][32 rows][64 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagingBytes);
+  uint8_t* res_stg = smem + kStagingBytes + kBarrierBytes;  // [epilogue warp][2 halves][32 rows][64 B] (res_tma only)
+  smem += kStagingBytes + kBarrierBytes + (p.res_tma ? kResBytes : 0);   // operand ring
   uint64_t* full_bar = bars;                                 // [kMaxStages]  (CG = 2: the leader's are used)
   uint64_t* empty_bar = bars + kMaxStages;                   // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kAccStages]
   uint64_t* tempty_bar = bars + 2 * kMaxStages + kAccStages; // [kAccStages]  (CG = 2: the leader's are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages);
+  uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kAccStages + 1;   // [kEpilogueWarps] residual round landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -345,6 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     if (p.tma_store && p.out) tma_prefetch_desc(&maps.out);
+    if (p.res_tma) tma_prefetch_desc(&maps.res);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -355,6 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CG * kEpilogueWarps);
     }
+    for (int i = 0; i < kEpilogueWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -494,6 +499,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     int swz[4];   // byte offsets of this lane's four 16 B pieces in a [32 rows][64 B] SWIZZLE_64B staging buffer
 #pragma unroll
     for (int c = 0; c < 4; ++c) swz[c] = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+    // residual through TMA (res_tma): one 64-column round per warp in flight, fetched while the MMAs of the tile (or
+    // the stores of the previous round) run; per-thread row-strided global loads made the epilogue latency bound
+    const bool res_tma = !kGeglu && p.res_tma != 0;
+    uint8_t* res_buf = res_stg + e * 4096;
+    uint64_t* my_res_bar = &res_bar[e];
+    uint32_t res_ph = 0;
+    bool res_pending = false;
     for (int t = unit0; t < total_units; t += unit_step) {
       TileCoord tc;
       {
@@ -540,7 +552,32 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const float* rbb = (p.row_batch_bias && row_ok) ? p.row_batch_bias + (long long)bidx * p.N : nullptr;
       const float* csrow = (!kGeglu && p.col_scale && row_ok) ? p.col_scale + (long long)bidx * ncols_out : nullptr;
       // (GEGLU launches carry no residual / column gate on the lean path: checked on the host)
-      const __nv_bfloat16* resrow = (!kGeglu && p.residual && row_ok) ? p.residual + row * p.ld_res : nullptr;
+      const __nv_bfloat16* resrow = (!kGeglu && p.residual && row_ok && !res_tma) ? p.residual + row * p.ld_res : nullptr;
+      // a round of the lean path = 64 accumulator columns starting at c (32 at the ragged end of the tile)
+      auto lean_round = [&](int c) -> bool {
+        if (!p.fast_epi || c >= out_tile_w) return false;
+        const int oc = tc.n_tile * out_tile_w + c;
+        if (oc >= ncols_out) return false;
+        const bool tw2 = (c + 32 < out_tile_w) && (oc + 32 < ncols_out);
+        const int wc = tw2 ? 64 : 32;
+        return oc + wc <= ncols_out && tc.n_tile * p.block_n + c + (kGeglu ? out_tile_w : 0) + wc <= p.N;
+      };
+      auto res_issue = [&](int c) {   // both 32-column halves; out-of-range rows / columns arrive as zeros
+        const int oc = tc.n_tile * out_tile_w + c;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(my_res_bar, 4096);
+          if (sc.conv) {
+            tma_load_4d(res_buf, &maps.res, my_res_bar, oc, sc.c1, sc.c2, sc.c3);
+            tma_load_4d(res_buf + 2048, &maps.res, my_res_bar, oc + 32, sc.c1, sc.c2, sc.c3);
+          } else {
+            tma_load_3d(res_buf, &maps.res, my_res_bar, oc, sc.c1, sc.c2);
+            tma_load_3d(res_buf + 2048, &maps.res, my_res_bar, oc + 32, sc.c1, sc.c2);
+          }
+        }
+        __syncwarp();
+        res_pending = true;
+      };
+      if (res_tma && !res_pending && lean_round(cset * 64)) res_issue(cset * 64);   // lands during the main loop
       ResidualRegs rr[2];
 #pragma unroll
       for (int q = 0; q < 4; ++q) rr[0].u[q] = rr[1].u[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -571,6 +608,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             if (two) residual_prefetch(rr[1], resrow + ocol0 + 32);
           }
           have_res = false;
+          if (res_tma) {
+            if (!res_pending) res_issue(c);
+            mbar_wait(my_res_bar, res_ph);
+            res_ph ^= 1;
+            res_pending = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              rr[0].u[q] = *reinterpret_cast<const uint4*>(res_buf + swz[q]);
+              rr[1].u[q] = *reinterpret_cast<const uint4*>(res_buf + 2048 + swz[q]);
+            }
+            __syncwarp();                                   // every lane has read the buffer: it may be refilled
+            if (lean_round(c + 128)) res_issue(c + 128);    // next round of this tile, behind this round's stores
+          }
           tmem_ld_wait();
           float v[2][32];   // aliases raw: the accumulator registers are converted in place
 #pragma unroll
@@ -615,7 +665,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           for (int hh = 0; hh < 2; ++hh) {
             if (hh == 1 && !two) break;
             if (csrow) mul_f32x32(csrow + ocol0 + hh * 32, v[hh]);
-            if (resrow) residual_add(rr[hh], v[hh]);
+            if (resrow || res_tma) residual_add(rr[hh], v[hh]);
             if (p.out_scale != 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] *= p.out_scale;

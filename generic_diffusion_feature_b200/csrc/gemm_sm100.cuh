@@ -18,9 +18,14 @@ constexpr int kAccStages = 2;
 constexpr int kEpilogueWarps = 8;   // 4 TMEM lane quadrants x 2 interleaved column sets
 constexpr int kGemmThreads = 128 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int kStageBytesA = kBlockM * kBlockK * 2;          // 16 KB
-constexpr int kPipeBytes = 160 * 1024;                       // operand ring: num_stages * (16 KB + block_n / cta_group * 128 B)
 constexpr int kStagingBytes = kEpilogueWarps * 4 * 2048;     // epilogue: per warp 4 x [32 rows][64 B] TMA-store buffers
-constexpr int kGemmSmemBytes = kPipeBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int kBarrierBytes = 1024;                          // mbarriers + TMEM slot
+constexpr int kResBytes = kEpilogueWarps * 2 * 2048;         // epilogue: per warp one 64-column residual round (TMA load)
+// shared memory: [store staging | barriers | region], region = operand ring (160 KB), or, for launches that fetch the
+// residual through TMA, residual staging (32 KB) + operand ring (128 KB)
+constexpr int kRegionBytes = 160 * 1024;
+constexpr int kGemmSmemBytes = kStagingBytes + kBarrierBytes + kRegionBytes + 1024 /*align slack*/;
+static_assert(kGemmSmemBytes <= 232448, "dynamic shared memory of the GEMM kernel exceeds 227 KB");
 
 enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2 };
 enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3 };
@@ -35,7 +40,7 @@ struct GemmParams {
   int M, N, K;          // N counts accumulator columns (for GEGLU: 2x the output width)
   int n_out;            // valid output columns (<= N, or <= N/2 for GEGLU); padding columns are dropped
   int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
-  int num_stages;       // operand ring depth: kPipeBytes / (16 KB + block_n / cta_group * 128 B), <= kMaxStages
+  int num_stages;       // operand ring depth: ring bytes / (16 KB + block_n / cta_group * 128 B), <= kMaxStages
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
@@ -47,6 +52,7 @@ struct GemmParams {
   // ---- epilogue
   int tma_store;               // 1: bf16/fp16 destinations go through smem staging + TMA bulk stores
   int fast_epi;                // 1: tma_store and every fp32 / residual operand is 16-byte aligned (lean epilogue path)
+  int res_tma;                 // 1: the lean path fetches the residual through TMA (maps.res) into smem, one round ahead
   float alpha;                 // accumulator scale (1.0 default)
   const float* bias;           // [N] column bias (already permuted for GEGLU) or null
   const float* bias_m;         // [M] row bias (transposed products) or null
@@ -67,7 +73,7 @@ struct GemmParams {
 
 // Tensor maps of one launch: operands + the six possible 16-bit destinations (TMA-store path).
 struct GemmMaps {
-  CUtensorMap a, b, out, out2, cap_pre, cap[3];
+  CUtensorMap a, b, out, out2, cap_pre, cap[3], res;
 };
 
 }  // namespace gdf

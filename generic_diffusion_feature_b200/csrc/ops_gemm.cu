@@ -51,7 +51,11 @@ static int choose_cta_group(int block_n, int num_m_tiles) {
 
 static void finish_tiling(GemmParams& p) {
   p.cta_group = choose_cta_group(p.block_n, p.num_m_tiles);
-  p.num_stages = kPipeBytes / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
+}
+// ring depth once the epilogue mode (residual staging or not) is known
+static void finish_stages(GemmParams& p) {
+  const int ring = kRegionBytes - (p.res_tma ? kResBytes : 0);
+  p.num_stages = ring / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (env_int("GDF_MAX_STAGES", 0) > 0 && p.num_stages > env_int("GDF_MAX_STAGES", 0))
     p.num_stages = env_int("GDF_MAX_STAGES", 0);   // tuning knob
@@ -90,6 +94,8 @@ static int setup_stores(GemmLaunch* g) {
   if (env_int("GDF_TMA_STORE", 1) == 0) ok = false;   // tuning knob
   p.tma_store = ok ? 1 : 0;
   p.fast_epi = 0;
+  p.res_tma = 0;
+  finish_stages(p);
   if (!ok) return GDF_OK;
   {
     bool f = env_int("GDF_FAST_EPI", 1) != 0;
@@ -99,6 +105,12 @@ static int setup_stores(GemmLaunch* g) {
     if (p.residual && (!aligned16(p.residual) || p.ld_res % 8 != 0)) f = false;
     if (p.act == kActGeglu && (p.residual || p.col_scale)) f = false;   // lean GEGLU path has neither
     p.fast_epi = f ? 1 : 0;
+  }
+  if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0) {
+    // same geometry as the store maps: [32 rows][32 columns] boxes, SWIZZLE_64B, rows / columns out of range read 0
+    GDF_TRY(make_store_map(&g->maps.res, p, p.residual, p.n_out, p.ld_res, 0));
+    p.res_tma = 1;
+    finish_stages(p);
   }
   if (p.out) GDF_TRY(make_store_map(&g->maps.out, p, p.out, p.n_out, p.ld_out, p.out_batch_stride));
   if (p.out2) GDF_TRY(make_store_map(&g->maps.out2, p, p.out2, p.n_out, p.ld_out2, 0));
