@@ -1,0 +1,167 @@
+"""BASELINE.json `configs` at their full sizes (the bench line is configs[1]; these are the parity-test cases):
+  configs[0]  SD-1.5 UNet 512x512, batch 1, conventional up-block activations (config_15_legacy.json)
+  configs[2]  SD-2.1 768x768 multi-timestep ensemble + resize+concat to the 1/8-resolution feature stack
+  configs[3]  PixArt-Sigma DiT 1024x1024 per-block attention / FFN capture
+  configs[4]  SPair-shaped correspondence on SDXL `practical` features of an image pair (4096 query points)
+Each runs the CUDA path through the reference-facing API and compares with the CPU oracle on the box's host cores
+(same synthetic weights / inputs / injected noise): per-map cosine >= 0.999, max-relative error <= 5e-2; arg-max
+agreement >= 99.5 % with the remaining points required to be near-ties.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import O, ROOT, build_oracle, build_oracle_dit, compare_maps, make_dit_inputs, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999
+MAXREL_MAX = 5e-2
+
+
+def _ref_cfg(name):
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "reference_ids.json")))[name]
+
+
+def _check(rows, what):
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "%s: maps out of tolerance (id, cos, rel, maxrel): %s" % (what, bad[:8])
+
+
+def test_config0_sd15_512_legacy(cuda_dev):
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    torch.set_num_threads(os.cpu_count())
+    layer = _ref_cfg("config_15_legacy.json")          # the reference's own JSON (4 maps, 3520 channels)
+    ucfg, vcfg = models.UNET_CONFIGS["1-5"], models.VAE_CONFIGS["1-5"]
+    sd = models.synthetic_state_dict("1-5", "cuda:0")
+    image, ctx, _, ev, eq = make_inputs(1, 512, 768)
+    pipe = models.get_diffusion_model("1-5", "float16", device="cuda:0", state_dict=sd)
+    fe = FeatureExtractor(layer, "1-5", "cuda:0", img_size=512, external_model=pipe)
+    got = fe.extract((ctx, ctx, None, None), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    torch.cuda.synchronize()
+    got = {k: v.float().cpu() for k, v in got.items()}
+    assert sum(v.shape[1] for v in got.values()) == 3520
+    unet, vae = build_oracle(ucfg, vcfg, {k: v.cpu() for k, v in sd.items()})
+    store = O.FeatureStore(layer)
+    O.attach_gatherers(unet, store)
+    want, _, _ = O.extract("1-5", unet, vae, store, image, ctx, None, ev, eq, t=50, img_size=512)
+    assert list(got.keys()) == list(want.keys())
+    _check(compare_maps(got, want), "SD-1.5 512 legacy")
+
+
+def test_config2_sd21_768_multi_timestep_stack(cuda_dev):
+    """3 x extract at t in {50, 150, 250} of the full 165-id set (the reference re-encodes per timestep),
+    every map checked; then the `-out` maps of each timestep are resized to 96x96 and concatenated
+    (aggregation_network.py:62-66) and the stack is compared with F.interpolate + cat of the oracle's maps."""
+    from generic_diffusion_feature_b200 import correspondence as C
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    torch.set_num_threads(os.cpu_count())
+    ucfg, vcfg = models.UNET_CONFIGS["2-1"], models.VAE_CONFIGS["2-1"]
+    ids = _unet_feature_ids(ucfg)
+    assert len(ids) == 165
+    layer = {i: True for i in ids}
+    stack_ids = [i for i in ids if i.endswith("res-out") or i.endswith("vit-out")]
+    sd = models.synthetic_state_dict("2-1", "cuda:0")
+    image, ctx, _, ev, eq = make_inputs(1, 768, 1024)
+    pipe = models.get_diffusion_model("2-1", "float16", device="cuda:0", state_dict=sd)
+    fe = FeatureExtractor(layer, "2-1", "cuda:0", img_size=768, external_model=pipe)
+    unet, vae = build_oracle(ucfg, vcfg, {k: v.cpu() for k, v in sd.items()})
+    store = O.FeatureStore(layer)
+    O.attach_gatherers(unet, store)
+    got_stacks, want_stacks = [], []
+    for t in (50, 150, 250):
+        got = fe.extract((ctx, ctx, None, None), 1, image.cuda(), image_type="tensors", t=t, noise=(ev, eq))
+        got_stacks.append(C.build_stack([got[i] for i in stack_ids], (96, 96), layout="nchw"))
+        torch.cuda.synchronize()
+        got = {k: v.float().cpu() for k, v in got.items()}
+        want, _, _ = O.extract("2-1", unet, vae, store, image, ctx, None, ev, eq, t=t, img_size=768)
+        assert list(got.keys()) == list(want.keys()) == ids
+        _check(compare_maps(got, want), "SD-2.1 768 t=%d" % t)
+        want_stacks.append(O.resize_concat([want[i] for i in stack_ids], (96, 96)))
+    got_stack = torch.cat(got_stacks, dim=1).float().cpu()
+    want_stack = torch.cat(want_stacks, dim=1)
+    assert got_stack.shape == want_stack.shape and got_stack.shape[2:] == (96, 96)
+    cos = F.cosine_similarity(got_stack.flatten(), want_stack.flatten(), dim=0).item()
+    assert cos >= COS_MIN, cos
+    # per-pixel feature vectors (what the downstream heads consume) agree too
+    pcos = F.cosine_similarity(got_stack[0].flatten(1), want_stack[0].flatten(1), dim=0)
+    assert pcos.min().item() >= COS_MIN, pcos.min().item()
+
+
+def test_config3_pixart_sigma_1024_full_set(cuda_dev):
+    """PixArt-Sigma-XL/2 at 1024x1024 (28 blocks, hidden 1152, 16 heads x 72, 4096 tokens, 300 caption tokens with a
+    padded tail), all 168 maps, batch 1 (the reference's own limit)."""
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _dit_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    torch.set_num_threads(os.cpu_count())
+    dcfg, vcfg = models.DIT_CONFIGS["pixart-sigma"], models.VAE_CONFIGS["pixart-sigma"]
+    ids = _dit_feature_ids(dcfg)
+    assert len(ids) == 168
+    layer = {i: True for i in ids}
+    sd = models.synthetic_state_dict("pixart-sigma", "cuda:0")
+    image, ctx, mask, ev, eq = make_dit_inputs(1, 1024, dcfg["caption_dim"], ctx_len=300, masked_tail=280)
+    pipe = models.get_diffusion_model("pixart-sigma", "float16", device="cuda:0", state_dict=sd)
+    fe = FeatureExtractor(layer, "pixart-sigma", "cuda:0", img_size=1024, external_model=pipe)
+    got = fe.extract((ctx, mask, ctx, mask), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    torch.cuda.synchronize()
+    got = {k: v.float().cpu() for k, v in got.items()}
+    sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    del sd, fe, pipe
+    model, vae = build_oracle_dit(dcfg, vcfg, sd_cpu)
+    store = O.FeatureStore(layer)
+    O.attach_gatherers_dit(model, store)
+    want, _, _ = O.extract_dit("pixart-sigma", model, vae, store, image, ctx, mask, ev, eq, t=50)
+    assert list(got.keys()) == list(want.keys()) == ids
+    assert got["vit-block0-ffn-inner"].shape == (1, 4608, 64, 64)
+    _check(compare_maps(got, want), "PixArt-Sigma 1024")
+
+
+def test_config4_sdxl_pair_correspondence_4096(cuda_dev):
+    """SDXL `practical` features (config_xl_practical.json, 3840 channels) of a synthetic image pair -> stacks at
+    128x128 -> find_nn_source_correspondences with load_size 512 and 4096 query points; compared with the oracle's
+    restatement of correspondence_utils.py:113-138 evaluated on the SAME fp16 stacks (chunked over the queries)."""
+    from generic_diffusion_feature_b200 import correspondence as C
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    torch.set_num_threads(os.cpu_count())
+    layer = _ref_cfg("config_xl_practical.json")
+    sd = models.synthetic_state_dict("xl", "cuda:0")
+    image, ctx, pooled, ev, eq = make_inputs(2, 1024, 2048, 1280)
+    # second image = smoothly warped copy of the first so that correspondences are meaningful
+    image[1] = torch.roll(image[0], shifts=(24, -16), dims=(1, 2)) * 0.9 + 0.1 * image[1]
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd)
+    fe = FeatureExtractor(layer, "xl", "cuda:0", img_size=1024, external_model=pipe)
+    feats = fe.extract((ctx, ctx, pooled, pooled), 2, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    assert sum(v.shape[1] for v in feats.values()) == 3840
+    stack = C.build_stack(feats, (128, 128), layout="nhwc")          # [2, 16384, 3840] fp16
+    pts = np.random.RandomState(1239).uniform(0, 511, size=(4096, 2))
+    _, p2 = C.find_nn_source_correspondences(stack[0:1], stack[1:2], pts, None, (512, 512))
+    torch.cuda.synchronize()
+    p2 = p2.cpu()
+    # oracle on the same stacks, 512 queries at a time (the full sims matrix is 4096 x 262144)
+    s = stack.float().cpu().view(2, 128, 128, 3840).permute(0, 3, 1, 2)
+    f1 = F.interpolate(s[0:1], (512, 512), mode="bilinear").view(3840, -1).t()
+    f2 = F.interpolate(s[1:2], (512, 512), mode="bilinear").view(3840, -1).t()
+    f2 = f2 / torch.linalg.norm(f2, dim=-1, keepdim=True)
+    idx = torch.from_numpy(O.points_to_idxs(pts, (512, 512))).long()
+    agree, near = 0, 0
+    for c0 in range(0, 4096, 512):
+        q = f1[idx[c0:c0 + 512]]
+        q = q / torch.linalg.norm(q, dim=-1, keepdim=True)
+        sims = q @ f2.t()
+        best = sims.argmax(dim=-1)
+        ours = p2[c0:c0 + 512, 0] * 512 + p2[c0:c0 + 512, 1]
+        same = best == ours
+        agree += int(same.sum())
+        gap = sims.max(dim=-1).values - sims.gather(1, ours[:, None])[:, 0]
+        near += int(((~same) & (gap < 2e-3)).sum())       # fp16-resolution near-ties
+    assert agree / 4096 >= 0.995, agree / 4096
+    assert agree + near == 4096, "disagreeing points that are not near-ties: %d" % (4096 - agree - near)
