@@ -34,6 +34,12 @@ struct FaParams {
   int ldo;
 };
 
+// V = 1: two passes over S in TMEM, fp32 output accumulator in registers (kept for A/B timing: GDF_FA_V1=1).
+// V = 2: S read from TMEM once (128 registers, S_t released to the tensor core right away so that S_t(j+1) runs under
+//        softmax(j)), output accumulator left in TMEM (P V accumulates over the KV tiles), running maximum updated
+//        lazily: O / l are rescaled only when the block maximum exceeds the one in use by more than 2^8 (P <= 256 in
+//        fp16), which after the first tiles is rare -> no per-tile read-modify of the accumulator.
+template <int V, int kPolyMod>
 __global__ void __launch_bounds__(kFaThreads, 1)
 attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                            const __grid_constant__ CUtensorMap map_v, const FaParams p) {
@@ -129,13 +135,13 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + t * 128, da + 2 * k, db + 2 * k, idesc_s, k != 0);
       umma_commit(&s_full[t]);
     };
-    auto issue_pv = [&](int t, int slot) {  // PV_t = P_t V into TMEM columns [256 + t*64, +64), fresh accumulator
+    auto issue_pv = [&](int t, int slot, bool first) {  // PV_t (+)= P_t V into TMEM columns [256 + t*64, +64)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         // A: P block (k / 4) of 16 KB, 32 B step inside the swizzle row; B: 16 kv rows = 2048 B per step
         const uint64_t da = umma_desc_kmajor_sw128(p_addr + t * 2 * kFaTile + (k >> 2) * kFaTile) + 2 * (k & 3);
         const uint64_t db = umma_desc_mnmajor_sw128(v_addr + slot * kFaTile + k * 2048, 8192);
-        umma_f16_ss(tmem_base + 256 + t * 64, da, db, idesc_pv, k != 0);
+        umma_f16_ss(tmem_base + 256 + t * 64, da, db, idesc_pv, (k != 0 || (V == 2 && !first)) ? 1u : 0u);
       }
       umma_commit(&pv_full[t]);
     };
@@ -176,7 +182,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
                                           mbar_try_wait(&v_full[slot], (jp / kFaRing) & 1))) {
             tc_fence_after();
             if (elect_one()) {
-              issue_pv(t, slot);
+              issue_pv(t, slot, jp == 0);
               if (pv_issued[slot] == 1) umma_commit(&v_empty[slot]);
             }
             pv_issued[slot] ^= 1;
@@ -197,6 +203,125 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
     const uint32_t t_s = tmem_base + (uint32_t(quad * 32) << 16) + t * 128;
     const uint32_t t_pv = tmem_base + (uint32_t(quad * 32) << 16) + 256 + t * 64;
     uint8_t* p_base = smem + kFaOffP + t * 2 * kFaTile;
+    if constexpr (V == 2) {
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = smem_u32(p_base) + r * 128;   // this thread's 128 B row of the P blocks (SW128 K-major)
+    const uint32_t p_swz = (r & 7) << 4;
+    const float thresh = 8.f / p.scale_log2;   // lazy rescale: keep the maximum in use while P = 2^(..) stays <= 2^8
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1) while this tile's softmax runs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      const int kv0 = j * 128;
+      if (kv0 + 128 > p.Nk) {   // ragged last tile: keys beyond Nk (zero-filled by TMA) are masked out
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (kv0 + i >= p.Nk) s[i] = 0xff800000u;   // -inf
+      }
+      // ---- row maximum (4 independent chains, 3-input max)
+      float mx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx[c] = __uint_as_float(s[c * 32]);
+#pragma unroll
+        for (int i = 1; i < 31; i += 2)
+          mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])));
+        mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 32 + 31]));
+      }
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      // P_t(j-1) V has been consumed from smem / accumulated in TMEM before P_t(j) is written or O_t is rescaled
+      if (j > 0) {
+        mbar_wait(&pv_full[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, m_blk > m_run + thresh)) {   // warp-uniform (TMEM accesses are warp-collective)
+        const float m_new = fmaxf(m_run, m_blk);
+        const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // first tile: exp2(-inf) = 0
+        l_run *= alpha;
+        m_run = m_new;
+        if (j > 0) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_pv + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_pv + hh * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_m = -m_run * p.scale_log2;
+      // ---- P = exp2(S*scale - m*scale) -> fp16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum in half2 trees
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ph2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1]), p.scale_log2, neg_m);
+          // every kPolyMod-th pair takes the polynomial (FMA pipe) instead of MUFU
+          if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == kPolyMod - 1) ph2[i] = pack_f16x2(ex2_poly(x0), ex2_poly(x1));
+          else ph2[i] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
+        }
+        uint32_t a0 = hadd2_u32(hadd2_u32(ph2[0], ph2[1]), hadd2_u32(ph2[2], ph2[3]));
+        uint32_t a1 = hadd2_u32(hadd2_u32(ph2[4], ph2[5]), hadd2_u32(ph2[6], ph2[7]));
+        uint32_t a2 = hadd2_u32(hadd2_u32(ph2[8], ph2[9]), hadd2_u32(ph2[10], ph2[11]));
+        uint32_t a3 = hadd2_u32(hadd2_u32(ph2[12], ph2[13]), hadd2_u32(ph2[14], ph2[15]));
+        rs += (half2_sum_f32(a0) + half2_sum_f32(a1)) + (half2_sum_f32(a2) + half2_sum_f32(a3));
+        const uint32_t blk = p_row + (c >> 1) * kFaTile;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
+          st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
+        }
+      }
+      l_run += rs;
+      // ---- publish P_t(j): smem writes visible to the tensor core (async proxy), TMEM accesses retired
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- output: O_t / l from TMEM (each thread writes its 128-byte output row)
+    mbar_wait(&pv_full[t], (n - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    uint32_t oa[32], ob[32];
+    tmem_ld_32x32(t_pv, oa);
+    tmem_ld_32x32(t_pv + 32, ob);
+    tmem_ld_wait();
+    if (qrow < p.Nq) {
+      bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * 64;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
+        reinterpret_cast<uint4*>(dst)[q] = u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(ob[q * 8 + 0]) * inv, __uint_as_float(ob[q * 8 + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(ob[q * 8 + 2]) * inv, __uint_as_float(ob[q * 8 + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(ob[q * 8 + 4]) * inv, __uint_as_float(ob[q * 8 + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(ob[q * 8 + 6]) * inv, __uint_as_float(ob[q * 8 + 7]) * inv);
+        reinterpret_cast<uint4*>(dst)[4 + q] = u;
+      }
+    }
+    } else {
     float o_acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
@@ -326,6 +451,7 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
         reinterpret_cast<uint4*>(dst)[q] = u;
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -339,10 +465,18 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
 // Host: tensor maps over the strided Q / K / V views (cols, rows-per-batch, batch), box 64 x 128 x 1.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    GDF_CUDA(cudaFuncSetAttribute(attention64_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
-    attr_set = true;
+  typedef void (*FaKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaParams);
+  static FaKernel kern = nullptr;
+  if (!kern) {
+    const char* e1 = getenv("GDF_FA_V1");
+    const char* ep = getenv("GDF_FA_POLY");
+    const int poly = ep ? atoi(ep) : 0;
+    if (e1 && e1[0] == '1') kern = attention64_tcgen05_kernel<1, 0>;
+    else if (poly == 4) kern = attention64_tcgen05_kernel<2, 4>;
+    else if (poly == 3) kern = attention64_tcgen05_kernel<2, 3>;
+    else if (poly == 2) kern = attention64_tcgen05_kernel<2, 2>;
+    else kern = attention64_tcgen05_kernel<2, 0>;
+    GDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
   }
   CUtensorMap mq, mk, mv;
   const uint32_t box[3] = {64, 128, 1};
@@ -367,7 +501,7 @@ int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, c
   p.O = O;
   p.ldo = ldo;
   dim3 grid((Nq + 255) / 256, heads, B);
-  GDF_CUDA(launch_pdl(attention64_tcgen05_kernel, grid, dim3(kFaThreads), (size_t)kFaSmem, stream, mq, mk, mv, p));
+  GDF_CUDA(launch_pdl(kern, grid, dim3(kFaThreads), (size_t)kFaSmem, stream, mq, mk, mv, p));
   return GDF_OK;
 }
 

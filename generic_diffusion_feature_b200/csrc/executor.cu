@@ -249,6 +249,13 @@ class Builder {
   int err = 0;
   OpList* ops = nullptr;
   float* gn_ws = nullptr;
+  // UNet: the cross-attention K/V of every transformer block depend only on the context, so they come from ONE
+  // batched projection at the head of the op list (weights of all blocks row-concatenated) instead of one small
+  // M = B * ctx_len GEMM per block; each block reads its [K | V] column slice of kv_all (pitch kv_ld).
+  bool kv_batched = false;
+  std::vector<std::string> kv_names;
+  bf16* kv_all = nullptr;
+  int kv_ld = 0, kv_col = 0;
 
   int set_err(int e) {
     if (!err) err = e;
@@ -432,7 +439,7 @@ class Builder {
       e.cap[i].ld = caps.c1[i] - caps.c0[i];
     }
   }
-  void push_gemm(GemmLaunch& g, const Caps& caps) {
+  void push_gemm(GemmLaunch& g, const Caps& caps, int at = -1) {   // at >= 0: replaces the placeholder op at that index
     GemmParams& p = g.p;
     {
       char lbl[160];
@@ -451,7 +458,7 @@ class Builder {
     const GemmLaunch gl = g;
     const Caps c = caps;
     const bool has_caps = (c.pre >= 0) || (c.n > 0);
-    ops->push_back([gl, c, cache, has_caps](const RunCtx& rc) -> int {
+    Op fn = [gl, c, cache, has_caps](const RunCtx& rc) -> int {
       if (!has_caps) {
         OP_CUDA(launch_gemm(gl, rc.stream));
         return 0;
@@ -472,11 +479,20 @@ class Builder {
       }
       OP_CUDA(launch_gemm(cache->g[slot], rc.stream));
       return 0;
-    });
+    };
+    if (at < 0) {
+      ops->push_back(std::move(fn));
+    } else {
+      ops->fns[at] = std::move(fn);
+      ops->kinds[at] = ops->cur_kind;
+      ops->flops[at] = ops->cur_flops;
+      ops->labels[at] = ops->cur_label;
+      ops->tag(kKindOther, 0.0);
+    }
   }
   void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e0,
               const Caps& caps = Caps(), int batch = 1, long long abs = 0, long long wbs = 0, int ldw = 0,
-              int block_n = 0) {
+              int block_n = 0, int at = -1) {
     if (dry || err) return;
     Epilogue e = e0;
     apply_caps(e, caps, e.n_out > 0 ? e.n_out : (e.act == kActGeglu ? N / 2 : N));
@@ -485,7 +501,7 @@ class Builder {
       set_err(r);
       return;
     }
-    push_gemm(g, caps);
+    push_gemm(g, caps, at);
   }
   void conv3(const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int Npad, int stride, int pad_lo,
              const Epilogue& e0, const Caps& caps = Caps()) {
@@ -704,18 +720,26 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
   }
   b.rel(n2);
   const long long Mc = (long long)B * h->ctx_len;
-  const bf16* wkv = b.rows_bf16(wp + ".attn2#kv", {wp + ".attn2.to_k.weight", wp + ".attn2.to_v.weight"}, nullptr);
-  bf16* kv = b.buf(Mc, 2 * C);
-  {
+  bf16* kv = nullptr;
+  int ldkv = 2 * C;
+  if (b.kv_batched) {
+    b.kv_names.push_back(wp + ".attn2.to_k.weight");
+    b.kv_names.push_back(wp + ".attn2.to_v.weight");
+    kv = b.kv_all ? b.kv_all + b.kv_col : nullptr;
+    ldkv = b.kv_ld;
+    b.kv_col += 2 * C;
+  } else {
+    const bf16* wkv = b.rows_bf16(wp + ".attn2#kv", {wp + ".attn2.to_k.weight", wp + ".attn2.to_v.weight"}, nullptr);
+    kv = b.buf(Mc, 2 * C);
     Epilogue e;
     e.out = kv;
     e.ld_out = 2 * C;
     b.linear(h->ctx_bf16, Mc, ctx_dim, ctx_dim, wkv, 2 * C, e);
   }
   bf16* ao2 = b.buf(M, C);
-  b.attention(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, h->ctx_len, scale, 0, hd);
+  b.attention(q2, C, kv, ldkv, kv + C, ldkv, ao2, C, B, heads, N, h->ctx_len, scale, 0, hd);
   b.rel(q2);
-  b.rel(kv);
+  if (!b.kv_batched) b.rel(kv);
   bf16* hs2 = b.buf(M, C);
   {
     Epilogue e;
@@ -907,6 +931,28 @@ static int build_unet(Builder& b) {
     }
   }
 
+  // ---- cross-attention K/V of all transformer blocks: one placeholder op here, filled in once every block has
+  // registered its to_k / to_v weights (attention_processor.py:3283-3284; the context is the same for every block)
+  int kv_op = -1;
+  {
+    long long kv_cols = 0;
+    for (int i = 0; i < nl; ++i) {
+      if (a.down_has_attn[i]) kv_cols += (long long)lpb * a.transformer_depth[i] * 2 * a.block_out_channels[i];
+      const int li = nl - 1 - i;
+      if (a.up_has_attn[i]) kv_cols += (long long)(lpb + 1) * a.transformer_depth[li] * 2 * a.block_out_channels[li];
+    }
+    kv_cols += (long long)a.transformer_depth[nl - 1] * 2 * a.block_out_channels[nl - 1];   // mid block
+    b.kv_batched = true;
+    b.kv_names.clear();
+    b.kv_col = 0;
+    b.kv_ld = (int)kv_cols;
+    b.kv_all = b.buf((long long)B * h->ctx_len, (int)kv_cols);
+    if (!b.dry) {
+      kv_op = (int)b.ops->size();
+      b.ops->push_back([](const RunCtx&) -> int { return 0; });
+    }
+  }
+
   // ---- conv_in (unet_2d_condition.py:1169-1173): latent NHWC [B, L*L, 4] -> im2col(K=36->64) -> GEMM
   int sidx = 0;  // next skip to produce
   int hw = h->L;
@@ -1091,6 +1137,21 @@ static int build_unet(Builder& b) {
         }
       }
     }
+  }
+
+  // ---- fill in the batched context projection (all blocks have registered their weights by now)
+  {
+    if (b.kv_col != b.kv_ld && !b.err)
+      return b.set_err(fail(GDF_ERR_SHAPE, "cross-attention K/V columns: planned %d, emitted %d", b.kv_ld, b.kv_col));
+    const bf16* wkv_all = b.rows_bf16("unet#cross_kv_all", b.kv_names, nullptr);
+    if (!b.dry && !b.err) {
+      Epilogue e;
+      e.out = b.kv_all;
+      e.ld_out = b.kv_ld;
+      b.linear(h->ctx_bf16, (long long)B * h->ctx_len, a.cross_attention_dim, a.cross_attention_dim, wkv_all, b.kv_ld, e,
+               Caps(), 1, 0, 0, 0, 0, kv_op);
+    }
+    b.kv_batched = false;
   }
 
   // ---- conv_norm_out + SiLU + conv_out (unet_2d_condition.py:1304-1310)

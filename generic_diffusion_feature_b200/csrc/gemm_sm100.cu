@@ -46,7 +46,8 @@ __device__ __forceinline__ void store16_f16(__half* dst, const float* v) {
 // ---------------------------------------------------------------------------------- shared epilogue math
 // Loads 32 accumulator columns starting at TMEM column `c` of this tile and applies alpha, biases, activation.
 __device__ __forceinline__ void load_activate32(const GemmParams& p, uint32_t taddr, int c, int out_tile_w,
-                                                int n_tile, float bm, bool row_ok, int bidx, float* v) {
+                                                int n_tile, float bm, bool row_ok, int bidx, float ln_a, float ln_b,
+                                                float* v) {
   uint32_t raw[32];
   tmem_ld_32x32(taddr + c, raw);
   tmem_ld_wait();
@@ -54,6 +55,7 @@ __device__ __forceinline__ void load_activate32(const GemmParams& p, uint32_t ta
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x = __uint_as_float(raw[j]) * p.alpha + bm;
+    if (p.ln_sums) x = (acol0 + j < p.N) ? fmaf(ln_b, __ldg(p.ln_u + acol0 + j), x * ln_a) : 0.f;   // folded LayerNorm
     if (p.bias && acol0 + j < p.N) x += __ldg(p.bias + acol0 + j);
     v[j] = x;
   }
@@ -71,6 +73,7 @@ __device__ __forceinline__ void load_activate32(const GemmParams& p, uint32_t ta
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float g = __uint_as_float(graw[j]) * p.alpha;
+      if (p.ln_sums) g = (gcol0 + j < p.N) ? fmaf(ln_b, __ldg(p.ln_u + gcol0 + j), g * ln_a) : 0.f;
       if (p.bias && gcol0 + j < p.N) g += __ldg(p.bias + gcol0 + j);
       v[j] *= gelu_erf_f(g);
     }
@@ -233,6 +236,14 @@ __device__ __forceinline__ void add_f32x32(const float* src, float* v) {
   for (int q = 0; q < 8; ++q) {
     const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
     v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+  }
+}
+__device__ __forceinline__ void fma_f32x32(const float* src, float s, float* v) {   // v += s * src
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+    v[q * 4 + 0] = fmaf(s, f.x, v[q * 4 + 0]); v[q * 4 + 1] = fmaf(s, f.y, v[q * 4 + 1]);
+    v[q * 4 + 2] = fmaf(s, f.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(s, f.w, v[q * 4 + 3]);
   }
 }
 __device__ __forceinline__ void mul_f32x32(const float* src, float* v) {
@@ -547,6 +558,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const int bidx = (p.rows_per_batch > 0 && row_ok) ? (int)(row / p.rows_per_batch) : 0;
       const long long out_batch_off = (long long)tc.bz * p.out_batch_stride;
       const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + row) : 0.f;
+      // folded LayerNorm of the A rows: value = ln_a * acc + ln_b * u[col] + bias[col]
+      float ln_a = 1.f, ln_b = 0.f;
+      if (p.ln_sums && row_ok) {
+        const float2 sq = __ldg(reinterpret_cast<const float2*>(p.ln_sums) + row);
+        const float mean = sq.x * p.ln_inv_c;
+        const float var = fmaxf(fmaf(sq.y, p.ln_inv_c, -mean * mean), 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -ln_a * mean;
+      }
+      float rs_sum = 0.f, rs_sq = 0.f;   // row statistics of this thread's final values (row_sums)
 
       // per-row operand bases of the lean path (null rows of a padding tile read nothing)
       const float* rbb = (p.row_batch_bias && row_ok) ? p.row_batch_bias + (long long)bidx * p.N : nullptr;
@@ -626,7 +647,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hh == 1 && !two) break;
-            if (p.alpha == 1.f) {
+            if (p.ln_sums) {   // (alpha == 1, no row bias: checked on the host)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) * ln_a;
+              fma_f32x32(p.ln_u + acol0 + hh * 32, ln_b, v[hh]);
+            } else if (p.alpha == 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) + bm;
             } else {
@@ -647,7 +672,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               if (hh == 1 && !two) break;
               float g[32];   // aliases graw[hh]
 #pragma unroll
-              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * p.alpha;
+              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * (p.ln_sums ? ln_a : p.alpha);
+              if (p.ln_sums) fma_f32x32(p.ln_u + gcol0 + hh * 32, ln_b, g);
               if (p.bias) add_f32x32(p.bias + gcol0 + hh * 32, g);
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] *= gelu_erf_lean(g[j]);
@@ -669,6 +695,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             if (p.out_scale != 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] *= p.out_scale;
+            }
+            if (p.row_sums) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { rs_sum += v[hh][j]; rs_sq = fmaf(v[hh][j], v[hh][j], rs_sq); }
             }
           }
           if (resrow) {   // the residual registers are free again: fetch the next full round while this one is stored
@@ -731,11 +761,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         if (ocol0 >= ncols_out) break;
         const int lim = min(ncols_out, ocol0 + 32);
         float v[32];
-        load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, v);
+        load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, ln_a, ln_b, v);
         if (p.tma_store) {
           // registers -> swizzled smem -> one TMA bulk store per destination (rows / columns clipped by the map)
           if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
           gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
+          if (p.row_sums) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ocol0 + j < lim) { rs_sum += v[j]; rs_sq = fmaf(v[j], v[j], rs_sq); }
+          }
           if (p.out) {
             if (ocol0 >= p.out_f16_from) stage_and_store<true>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
             else stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
@@ -754,8 +789,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             for (int j = 0; j < 32; ++j) vpre[j] = v[j];
           }
           gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
+          if (p.row_sums) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ocol0 + j < lim) { rs_sum += v[j]; rs_sq = fmaf(v[j], v[j], rs_sq); }
+          }
           if (row_ok) direct_store32(p, vpre, v, row, ocol0, lim, out_batch_off, false);
         }
+      }
+      if (p.row_sums && row_ok) {   // this warp's column share of the row; the other column set / n-tiles add theirs
+        atomicAdd(p.row_sums + 2 * row, rs_sum);
+        atomicAdd(p.row_sums + 2 * row + 1, rs_sq);
       }
       tc_fence_before();
       __syncwarp();

@@ -69,6 +69,12 @@ struct GemmParams {
   __half* cap_pre; int ld_cap_pre;             // fp16 capture before residual add ("increment")
   CaptureSeg cap[3];                           // fp16 captures of the final value
   int num_cap;
+  // ---- LayerNorm folded into the GEMM that consumes it (attention.py:497,525,566): A holds the un-normalised rows,
+  // the weights carry gamma, bias carries beta . W^T:  value = rstd[row] * (acc - mean[row] * ln_u[col]) + bias[col]
+  const float* ln_sums;        // [M][2] (sum, sum of squares) of the A rows, written by the producer's row_sums; or null
+  const float* ln_u;           // [N] row sums of the (gamma-folded, bf16-rounded) weight matrix
+  float ln_inv_c, ln_eps;      // 1 / row width, epsilon
+  float* row_sums;             // [M][2]: this launch adds (sum, sum of squares) of its final output rows, or null
 };
 
 // Tensor maps of one launch: operands + the six possible 16-bit destinations (TMA-store path).

@@ -32,6 +32,10 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   __half* cap_pre = nullptr; int ld_cap_pre = 0;
   CaptureSeg cap[3] = {};
   int num_cap = 0;
+  const float* ln_sums = nullptr;   // folded LayerNorm of the A rows (see GemmParams)
+  const float* ln_u = nullptr;
+  float ln_eps = 1e-5f;
+  float* row_sums = nullptr;        // (sum, sum sq) of the final output rows for a LayerNorm folded into the consumer
   bool in_f16 = false;              // operands are fp16 instead of bf16
   bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };

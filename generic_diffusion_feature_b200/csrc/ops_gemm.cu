@@ -104,6 +104,7 @@ static int setup_stores(GemmLaunch* g) {
     if (p.col_scale && (!aligned16(p.col_scale) || p.n_out % 4 != 0)) f = false;
     if (p.residual && (!aligned16(p.residual) || p.ld_res % 8 != 0)) f = false;
     if (p.act == kActGeglu && (p.residual || p.col_scale)) f = false;   // lean GEGLU path has neither
+    if (p.ln_sums && (!aligned16(p.ln_u) || p.alpha != 1.f || p.bias_m)) f = false;
     p.fast_epi = f ? 1 : 0;
   }
   if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0) {
@@ -156,6 +157,11 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.ld_cap_pre = e.ld_cap_pre;
   p.num_cap = e.num_cap;
   for (int i = 0; i < 3; ++i) p.cap[i] = e.cap[i];
+  p.ln_sums = e.ln_sums;
+  p.ln_u = e.ln_u;
+  p.ln_inv_c = 1.f / (float)p.K;
+  p.ln_eps = e.ln_eps;
+  p.row_sums = e.row_sums;
 }
 
 int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, const bf16* W, int N, int ldw,

@@ -251,6 +251,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM, same shape as tmem_ld_32x32 (thread t writes row (lane base + t), 32 consecutive columns)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (=128 B),
 // 8-row swizzle atoms 1024 B apart (SBO). Start address may be advanced by k*32 B inside the atom.
@@ -281,6 +294,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// packed fp32 pair FMA (one issue slot for two lanes of work): {x0, x1} * {m, m} + {a, a}
+__device__ __forceinline__ void ffma2(float& x0, float& x1, float s0, float s1, float m, float a) {
+  uint64_t d, sv, mv, av;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(sv) : "f"(s0), "f"(s1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(mv) : "f"(m));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(sv), "l"(mv), "l"(av));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+}
+// 2^x on the FMA / ALU pipes (takes load off the 16-lane MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5],
+// degree-3 minimax polynomial of 2^f (max relative error 7.5e-5, below fp16 resolution), n added to the exponent field.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;             // 1.5 * 2^23: the low mantissa bits of t hold n (two's complement)
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.0551716685f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 // two exponentials per MUFU op: 2^x on a packed half2 (inputs <= 0 after max subtraction; fp16 range is ample)
 __device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
   uint32_t h, y;
