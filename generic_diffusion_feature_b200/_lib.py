@@ -48,6 +48,8 @@ class Epilogue(ctypes.Structure):
         ("out_f32_dev", c_void_p), ("ld_out_f32", c_int),
         ("cap_pre_dev", c_void_p), ("ld_cap_pre", c_int),
         ("cap", CaptureSeg * 3), ("num_cap", c_int),
+        ("ln_sums_dev", c_void_p), ("ln_u_dev", c_void_p), ("ln_eps", c_float), ("row_sums_dev", c_void_p),
+        ("gn_sums_dev", c_void_p), ("gn_cpg", c_int), ("gn_groups", c_int), ("gn_rows_per_img", c_int64),
     ]
 
 

@@ -35,6 +35,14 @@ static Epilogue to_epilogue(const gdf_epilogue* ep) {
     e.cap[i].col_end = ep->cap[i].col_end;
     e.cap[i].ld = ep->cap[i].ld;
   }
+  e.ln_sums = static_cast<const float*>(ep->ln_sums_dev);
+  e.ln_u = static_cast<const float*>(ep->ln_u_dev);
+  e.ln_eps = ep->ln_eps;
+  e.row_sums = static_cast<float*>(ep->row_sums_dev);
+  e.gn_sums = static_cast<float*>(ep->gn_sums_dev);
+  e.gn_cpg = ep->gn_cpg;
+  e.gn_groups = ep->gn_groups;
+  e.gn_rows_per_img = ep->gn_rows_per_img;
   return e;
 }
 

@@ -39,7 +39,11 @@ struct FaParams {
 //        softmax(j)), output accumulator left in TMEM (P V accumulates over the KV tiles), running maximum updated
 //        lazily: O / l are rescaled only when the block maximum exceeds the one in use by more than 2^8 (P <= 256 in
 //        fp16), which after the first tiles is rare -> no per-tile read-modify of the accumulator.
-template <int V, int kPolyMod>
+// kPingPong: the two softmax groups (one warp of each per SM sub-partition) take turns in the exponential phase
+//        through a pair of named barriers, so that one group's MUFU-bound phase runs against the other's TMEM loads /
+//        row maxima / barrier round trips instead of against its exponentials (both groups in the MUFU phase at once
+//        halve each other's rate and leave the remaining phases uncovered).
+template <int V, int kPolyMod, bool kPingPong>
 __global__ void __launch_bounds__(kFaThreads, 1)
 attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                            const __grid_constant__ CUtensorMap map_v, const FaParams p) {
@@ -205,15 +209,16 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
     uint8_t* p_base = smem + kFaOffP + t * 2 * kFaTile;
     if constexpr (V == 2) {
     float m_run = -INFINITY, l_run = 0.f;
+    if (kPingPong && t == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");   // group 0 goes first
     const uint32_t p_row = smem_u32(p_base) + r * 128;   // this thread's 128 B row of the P blocks (SW128 K-major)
     const uint32_t p_swz = (r & 7) << 4;
     const float thresh = 8.f / p.scale_log2;   // lazy rescale: keep the maximum in use while P = 2^(..) stays <= 2^8
     for (int j = 0; j < n; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t s[128];
+      float sf[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sf[c * 32]));
       tmem_ld_wait();
       // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1) while this tile's softmax runs
       tc_fence_before();
@@ -223,17 +228,16 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
       if (kv0 + 128 > p.Nk) {   // ragged last tile: keys beyond Nk (zero-filled by TMA) are masked out
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (kv0 + i >= p.Nk) s[i] = 0xff800000u;   // -inf
+          if (kv0 + i >= p.Nk) sf[i] = -INFINITY;
       }
       // ---- row maximum (4 independent chains, 3-input max)
       float mx[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        mx[c] = __uint_as_float(s[c * 32]);
+        mx[c] = sf[c * 32];
 #pragma unroll
-        for (int i = 1; i < 31; i += 2)
-          mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])));
-        mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 32 + 31]));
+        for (int i = 1; i < 31; i += 2) mx[c] = fmaxf(mx[c], fmaxf(sf[c * 32 + i], sf[c * 32 + i + 1]));
+        mx[c] = fmaxf(mx[c], sf[c * 32 + 31]);
       }
       const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       // P_t(j-1) V has been consumed from smem / accumulated in TMEM before P_t(j) is written or O_t is rescaled
@@ -260,18 +264,40 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
         }
       }
       const float neg_m = -m_run * p.scale_log2;
-      // ---- P = exp2(S*scale - m*scale) -> fp16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum in half2 trees
+      if (kPingPong) {   // wait for the other group to leave its exponential phase (group 1 hands over first)
+        if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      // ---- P = exp2(S*scale - m*scale) -> fp16 -> smem (K-major SW128, 2 blocks of 64 kv), row sum in half2 trees.
+      // Hand-scheduled with volatile asm (program order is kept): the 32 exponentials of chunk c+1 are issued
+      // between the packs of chunk c, so a pack never waits on a MUFU issued just before it (the compiler's own
+      // schedule put every F2FP right behind its two MUFUs: one MUFU latency per pair, XU 60 % busy).
       float rs = 0.f;
+      auto scale_chunk = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          ffma2(sf[c * 32 + 2 * i], sf[c * 32 + 2 * i + 1], sf[c * 32 + 2 * i], sf[c * 32 + 2 * i + 1], p.scale_log2, neg_m);
+      };
+      auto exp_pair = [&](int c, int i) {   // in place
+        if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == kPolyMod - 1) {
+          sf[c * 32 + 2 * i] = ex2_poly(sf[c * 32 + 2 * i]);
+          sf[c * 32 + 2 * i + 1] = ex2_poly(sf[c * 32 + 2 * i + 1]);
+        } else {
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(sf[c * 32 + 2 * i]));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(sf[c * 32 + 2 * i + 1]));
+        }
+      };
+      scale_chunk(0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) exp_pair(0, i);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if (c < 3) scale_chunk(c + 1);
         uint32_t ph2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float x0, x1;
-          ffma2(x0, x1, __uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1]), p.scale_log2, neg_m);
-          // every kPolyMod-th pair takes the polynomial (FMA pipe) instead of MUFU
-          if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == kPolyMod - 1) ph2[i] = pack_f16x2(ex2_poly(x0), ex2_poly(x1));
-          else ph2[i] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
+          if (c < 3) exp_pair(c + 1, i);
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph2[i]) : "f"(sf[c * 32 + 2 * i + 1]), "f"(sf[c * 32 + 2 * i]));
         }
         uint32_t a0 = hadd2_u32(hadd2_u32(ph2[0], ph2[1]), hadd2_u32(ph2[2], ph2[3]));
         uint32_t a1 = hadd2_u32(hadd2_u32(ph2[4], ph2[5]), hadd2_u32(ph2[6], ph2[7]));
@@ -284,6 +310,10 @@ attention64_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
           const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
           st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
         }
+      }
+      if (kPingPong) {
+        if (t == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        else if (j + 1 < n) asm volatile("bar.arrive 1, 256;" ::: "memory");
       }
       l_run += rs;
       // ---- publish P_t(j): smem writes visible to the tensor core (async proxy), TMEM accesses retired
@@ -471,11 +501,12 @@ int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, c
     const char* e1 = getenv("GDF_FA_V1");
     const char* ep = getenv("GDF_FA_POLY");
     const int poly = ep ? atoi(ep) : 0;
-    if (e1 && e1[0] == '1') kern = attention64_tcgen05_kernel<1, 0>;
-    else if (poly == 4) kern = attention64_tcgen05_kernel<2, 4>;
-    else if (poly == 3) kern = attention64_tcgen05_kernel<2, 3>;
-    else if (poly == 2) kern = attention64_tcgen05_kernel<2, 2>;
-    else kern = attention64_tcgen05_kernel<2, 0>;
+    const char* epp = getenv("GDF_FA_PP");
+    const bool pp = epp && epp[0] == '1';   // measured slower (612 vs 551 us at N = 4096): off unless asked for
+    if (e1 && e1[0] == '1') kern = attention64_tcgen05_kernel<1, 0, false>;
+    else if (poly == 4) kern = pp ? attention64_tcgen05_kernel<2, 4, true> : attention64_tcgen05_kernel<2, 4, false>;
+    else if (pp) kern = attention64_tcgen05_kernel<2, 0, true>;
+    else kern = attention64_tcgen05_kernel<2, 0, false>;
     GDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
   }
   CUtensorMap mq, mk, mv;

@@ -93,6 +93,41 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int K, const int
     dst[i] = __float2bfloat16_rn(sr >= 0 ? src[(long long)sr * K + k] : 0.f);
   }
 }
+// LayerNorm folded into a projection: dst[r, k] = bf16(src[idx[r], k] * gamma[k])
+__global__ void pack_rows_scaled_kernel(const float* __restrict__ src, int K, const int* __restrict__ row_idx, int R_out,
+                                        const float* __restrict__ gamma, bf16* __restrict__ dst) {
+  const long long total = (long long)R_out * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K), k = (int)(i % K);
+    const int sr = row_idx ? row_idx[r] : r;
+    dst[i] = __float2bfloat16_rn(sr >= 0 ? src[(long long)sr * K + k] * gamma[k] : 0.f);
+  }
+}
+// ... and its per-row constants: u[r] = sum_k dst[r, k] (the bf16 values the tensor core multiplies),
+// c[r] = bias[idx[r]] + sum_k src[idx[r], k] * beta[k]. One warp per row.
+__global__ void ln_fold_consts_kernel(const float* __restrict__ src, const bf16* __restrict__ dst, int K,
+                                      const int* __restrict__ row_idx, int R_out, const float* __restrict__ beta,
+                                      const float* __restrict__ bias, float* __restrict__ u, float* __restrict__ c) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R_out) return;
+  const int sr = row_idx ? row_idx[r] : r;
+  float su = 0.f, sc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    su += __bfloat162float(dst[(long long)r * K + k]);
+    if (sr >= 0) sc += src[(long long)sr * K + k] * beta[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if (lane == 0) {
+    u[r] = su;
+    c[r] = sc + ((bias && sr >= 0) ? bias[sr] : 0.f);
+  }
+}
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n,
                                   float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,6 +287,53 @@ class Builder {
   // UNet: the cross-attention K/V of every transformer block depend only on the context, so they come from ONE
   // batched projection at the head of the op list (weights of all blocks row-concatenated) instead of one small
   // M = B * ctx_len GEMM per block; each block reads its [K | V] column slice of kv_all (pitch kv_ld).
+  // UNet transformer blocks: LayerNorm folded into the projection that consumes it (GDF_LN_FOLD=0 disables). The
+  // producer of the residual stream adds per-row (sum, sum sq) into a slice of ln_slab (zeroed once per forward).
+  bool ln_fold = false;
+  float* ln_slab = nullptr;
+  long long ln_off = 0, ln_total = 0;
+  float* ln_rows(long long M) {
+    float* p = ln_slab ? ln_slab + ln_off : nullptr;
+    ln_off += 2 * M;
+    return p;
+  }
+  // GroupNorm statistics produced by the epilogue of the GEMM that writes the tensor (GDF_GN_FUSE=0 disables):
+  // slices of gn_slab, [B][G][2] fp32 each, zeroed by one memset at the head of the op list.
+  float* gn_slab = nullptr;
+  int gn_used = 0, gn_cap = 0;
+  bool gn_fuse = false;
+  bool gn_fusable(int C, int G, long long HW) const {
+    const int cpg = G > 0 ? C / G : 0;
+    return gn_fuse && (cpg == 4 || cpg == 8 || cpg == 16) && C % 64 == 0 && HW % 128 == 0;
+  }
+  float* gn_slot(int B, int G) {   // null when the slab is exhausted (callers fall back to the statistics kernel)
+    if (gn_used >= gn_cap) return nullptr;
+    float* p = gn_slab ? gn_slab + (size_t)gn_used * B * G * 2 : nullptr;
+    ++gn_used;
+    return dry ? reinterpret_cast<float*>(uintptr_t(16)) : p;
+  }
+  void gn_begin(int B, int G, int max_slots) {   // call once per op list, before the first producer
+    const char* ev = getenv("GDF_GN_FUSE");
+    gn_fuse = !(ev && ev[0] == '0');
+    gn_used = 0;
+    gn_cap = gn_fuse ? max_slots : 0;
+    gn_slab = gn_fuse ? fbuf((long long)max_slots * B * G * 2) : nullptr;
+    if (gn_fuse && !dry) {
+      float* slab = gn_slab;
+      const size_t bytes = (size_t)max_slots * B * G * 2 * 4;
+      ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(cudaMemsetAsync(slab, 0, bytes, rc.stream));
+        return 0;
+      });
+    }
+  }
+  static void want_gn_stats(Epilogue& e, float* sums, int C, int G, long long HW) {
+    if (!sums) return;
+    e.gn_sums = sums;
+    e.gn_cpg = C / G;
+    e.gn_groups = G;
+    e.gn_rows_per_img = HW;
+  }
   bool kv_batched = false;
   std::vector<std::string> kv_names;
   bf16* kv_all = nullptr;
@@ -343,6 +425,74 @@ class Builder {
     if (idx_dev) cudaFree(idx_dev);
     h->packed[key] = dst;
     return dst;
+  }
+  // rows_bf16 with LayerNorm (gamma, beta) folded in: weight columns scaled by gamma; u / c per output row (see
+  // ln_fold_consts_kernel). bias_name may be empty.
+  struct LnW { const bf16* w = nullptr; const float* u = nullptr; const float* c = nullptr; };
+  LnW rows_bf16_ln(const std::string& key, const std::vector<std::string>& names, const std::vector<int>* idx,
+                   const std::string& norm_prefix, const std::string& bias_name) {
+    LnW out;
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) {
+      out.w = static_cast<const bf16*>(it->second);
+      out.u = static_cast<const float*>(h->packed[key + "#u"]);
+      out.c = static_cast<const float*>(h->packed[key + "#c"]);
+      return out;
+    }
+    const float* gamma = f32(norm_prefix + ".weight");
+    const float* beta = f32(norm_prefix + ".bias");
+    const float* bias = bias_name.empty() ? nullptr : f32(bias_name);
+    if (!gamma || !beta || (!bias_name.empty() && !bias)) return out;
+    int K = -1;
+    int64_t R = 0;
+    for (auto& n : names) {
+      const RawW* r = raw(n);
+      if (!r) return out;
+      const int64_t k = r->numel / r->shape[0];
+      if (K < 0) K = (int)k;
+      if (k != K) {
+        set_err(fail(GDF_ERR_SHAPE, "rows_bf16_ln %s: inner size mismatch", key.c_str()));
+        return out;
+      }
+      R += r->shape[0];
+    }
+    float* stack = nullptr;
+    const float* src = nullptr;
+    if (names.size() == 1) {
+      src = raw(names[0])->ptr;
+    } else {
+      cudaMalloc(&stack, (size_t)R * K * 4);
+      int64_t off = 0;
+      for (auto& n : names) {
+        const RawW* r = raw(n);
+        cudaMemcpy(stack + off, r->ptr, (size_t)r->numel * 4, cudaMemcpyDeviceToDevice);
+        off += r->numel;
+      }
+      src = stack;
+    }
+    const int R_out = idx ? (int)idx->size() : (int)R;
+    int* idx_dev = nullptr;
+    if (idx) {
+      cudaMalloc(&idx_dev, idx->size() * 4);
+      cudaMemcpy(idx_dev, idx->data(), idx->size() * 4, cudaMemcpyHostToDevice);
+    }
+    bf16* dst = static_cast<bf16*>(dev_alloc((size_t)R_out * K * 2));
+    float* u = static_cast<float*>(dev_alloc((size_t)R_out * 4));
+    float* c = static_cast<float*>(dev_alloc((size_t)R_out * 4));
+    if (dst && u && c) {
+      pack_rows_scaled_kernel<<<1024, 256>>>(src, K, idx_dev, R_out, gamma, dst);
+      ln_fold_consts_kernel<<<(R_out + 7) / 8, 256>>>(src, dst, K, idx_dev, R_out, beta, bias, u, c);
+      cudaDeviceSynchronize();
+    }
+    if (stack) cudaFree(stack);
+    if (idx_dev) cudaFree(idx_dev);
+    h->packed[key] = dst;
+    h->packed[key + "#u"] = u;
+    h->packed[key + "#c"] = c;
+    out.w = dst;
+    out.u = u;
+    out.c = c;
+    return out;
   }
   const bf16* lin(const std::string& name) { return rows_bf16(name + "#bf16", {name}, nullptr); }
   const float* f32_gather(const std::string& key, const std::string& name, const std::vector<int>& idx) {
@@ -527,6 +677,19 @@ class Builder {
       return 0;
     });
   }
+  // GroupNorm whose statistics were accumulated by the producer's epilogue into `sums`
+  void groupnorm_from_sums(const bf16* x, bf16* y, const std::string& prefix, int B, int HW, int C, int G, float eps,
+                           bool silu, const float* sums) {
+    const float* gm = f32(prefix + ".weight");
+    const float* bt = f32(prefix + ".bias");
+    if (dry || err) return;
+    float* ws = gn_ws;
+    ops->tag(kKindGroupNorm, 0.0, "groupnorm(fused stats) HW=" + std::to_string(HW) + " C=" + std::to_string(C));
+    ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_groupnorm_from_sums(x, y, gm, bt, B, HW, C, G, eps, silu, sums, ws, rc.stream));
+      return 0;
+    });
+  }
   void layernorm(const bf16* x, bf16* y, const std::string& prefix, long long M, int C, float eps) {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
@@ -594,17 +757,21 @@ class Builder {
 };
 
 // ----------------------------------------------------------------------------------------- layers
-struct Dest {      // where a layer's output goes
+struct Dest {      // where a layer's output goes (gn_sums: statistics requested for the GroupNorm that consumes it)
   bf16* out = nullptr; int ld = 0;    // primary (may be a slice of a skip-concat buffer)
   bf16* out2 = nullptr; int ld2 = 0;  // optional second copy (skip-concat slice on the down path)
+  float* gn_sums = nullptr;
 };
 
 // ResnetBlock2D (resnet.py:320-379). x: [B*H*W, Cin] contiguous. temb: fp32 [B, temb_ch] or null (VAE).
 static void emit_resnet(Builder& b, const std::string& wp, const std::string& fid, const bf16* x, int B, int H, int W,
-                        int Cin, int Cout, const float* emb, int temb_ch, int groups, float eps, const Dest& d) {
+                        int Cin, int Cout, const float* emb, int temb_ch, int groups, float eps, const Dest& d,
+                        const float* x_sums = nullptr) {
+  // x_sums: GroupNorm statistics of x left by its producer's epilogue (null: norm1 runs its own statistics pass)
   const long long M = (long long)B * H * W;
   bf16* t1 = b.buf(M, Cin);
-  b.groupnorm(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true);
+  if (x_sums) b.groupnorm_from_sums(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true, x_sums);
+  else b.groupnorm(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true);
   float* tproj = nullptr;
   if (emb) {
     tproj = b.fbuf((long long)B * Cout);
@@ -613,6 +780,7 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
   int npad = 0;
   const bf16* w1 = b.conv_w(wp + ".conv1.weight", &npad);
   bf16* t2 = b.buf(M, Cout);
+  float* sums2 = (npad == Cout && b.gn_fusable(Cout, groups, (long long)H * W)) ? b.gn_slot(B, groups) : nullptr;
   {
     Epilogue e;
     e.bias = b.f32_pad(wp + ".conv1.bias", npad);
@@ -621,11 +789,13 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
     e.n_out = Cout;
     e.out = t2;
     e.ld_out = Cout;
+    Builder::want_gn_stats(e, sums2, Cout, groups, (long long)H * W);
     b.conv3(t1, B, H, W, Cin, w1, npad, 1, 1, e);
   }
   b.rel(t1);
   bf16* t3 = b.buf(M, Cout);
-  b.groupnorm(t2, t3, wp + ".norm2", B, H * W, Cout, groups, eps, true);
+  if (sums2) b.groupnorm_from_sums(t2, t3, wp + ".norm2", B, H * W, Cout, groups, eps, true, sums2);
+  else b.groupnorm(t2, t3, wp + ".norm2", B, H * W, Cout, groups, eps, true);
   b.rel(t2);
   const bf16* res = x;
   bf16* sc = nullptr;
@@ -652,6 +822,7 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
     e.ld_out = d.ld;
     e.out2 = d.out2;
     e.ld_out2 = d.ld2;
+    Builder::want_gn_stats(e, d.gn_sums, Cout, groups, (long long)H * W);
     Caps caps;
     if (!fid.empty()) {
       caps.pre = b.site(fid + "-increment", Cout, H, W);
@@ -666,21 +837,41 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
 }
 
 // BasicTransformerBlock (attention.py:469-592) on hs [M, C]; returns the new hidden-state buffer.
+// sums_in: row statistics of hs (written by its producer), sums_out: where the block's last GEMM adds the statistics of
+// its output for the next block's norm1 (null: not needed). Both null when the LayerNorms are not folded.
 static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& fid, bf16* hs, int B, int N, int C,
-                         int heads, int ctx_dim, int hw) {
+                         int heads, int ctx_dim, int hw, const float* sums_in = nullptr, float* sums_out = nullptr) {
   gdf_handle_s* h = b.h;
   const long long M = (long long)B * N;
   const float scale = 1.f / sqrtf((float)(C / heads));
   // ---- self attention
   const int hd = C / heads;
   const bool self_tc = (hd == 64) && attention_uses_tcgen05(N);
-  bf16* n1 = b.buf(M, C);
-  b.layernorm(hs, n1, wp + ".norm1", M, C, 1e-5f);
-  const bf16* wqkv = b.rows_bf16(wp + ".attn1#qkv", {wp + ".attn1.to_q.weight", wp + ".attn1.to_k.weight",
-                                                     wp + ".attn1.to_v.weight"}, nullptr);
+  const bool fold = b.ln_fold;
+  float* sums1 = fold ? b.ln_rows(M) : nullptr;   // statistics of hs1 / hs2 (inputs of norm2 / norm3)
+  float* sums2 = fold ? b.ln_rows(M) : nullptr;
+  const std::vector<std::string> qkv_names = {wp + ".attn1.to_q.weight", wp + ".attn1.to_k.weight",
+                                              wp + ".attn1.to_v.weight"};
+  bf16* n1 = nullptr;
+  const bf16* wqkv = nullptr;
+  Builder::LnW lw1;
+  if (fold) {
+    lw1 = b.rows_bf16_ln(wp + ".attn1#qkv_ln", qkv_names, nullptr, wp + ".norm1", "");
+    wqkv = lw1.w;
+  } else {
+    n1 = b.buf(M, C);
+    b.layernorm(hs, n1, wp + ".norm1", M, C, 1e-5f);
+    wqkv = b.rows_bf16(wp + ".attn1#qkv", qkv_names, nullptr);
+  }
   bf16* qkv = b.buf(M, 3 * C);
   {
     Epilogue e;
+    if (fold) {
+      e.bias = lw1.c;
+      e.ln_sums = sums_in;
+      e.ln_u = lw1.u;
+      e.ln_eps = 1e-5f;
+    }
     e.out = qkv;
     e.ld_out = 3 * C;
     if (self_tc) e.out_f16_from = 2 * C;   // V columns in fp16 for the fp16 P.V product of the tcgen05 kernel
@@ -688,9 +879,9 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     caps.add(b.site(fid + "-self-q", C, hw, hw), 0, C);
     caps.add(b.site(fid + "-self-k", C, hw, hw), C, 2 * C);
     caps.add(b.site(fid + "-self-v", C, hw, hw), 2 * C, 3 * C);
-    b.linear(n1, M, C, C, wqkv, 3 * C, e, caps);
+    b.linear(fold ? hs : n1, M, C, C, wqkv, 3 * C, e, caps);
   }
-  b.rel(n1);
+  if (n1) b.rel(n1);
   bf16* ao = b.buf(M, C);
   b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, self_tc ? 1 : 0, hd);
   b.rel(qkv);
@@ -702,23 +893,39 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     e.ld_res = C;
     e.out = hs1;
     e.ld_out = C;
+    e.row_sums = sums1;
     b.linear(ao, M, C, C, b.lin(wp + ".attn1.to_out.0.weight"), C, e);
   }
   b.rel(ao);
   b.rel(hs);
   // ---- cross attention (context K/V: B*ctx_len rows; reference drops cross-k / cross-v, feature_extractor.py:38)
-  bf16* n2 = b.buf(M, C);
-  b.layernorm(hs1, n2, wp + ".norm2", M, C, 1e-5f);
+  bf16* n2 = nullptr;
+  const bf16* wq2 = nullptr;
+  Builder::LnW lw2;
+  if (fold) {
+    lw2 = b.rows_bf16_ln(wp + ".attn2#q_ln", {wp + ".attn2.to_q.weight"}, nullptr, wp + ".norm2", "");
+    wq2 = lw2.w;
+  } else {
+    n2 = b.buf(M, C);
+    b.layernorm(hs1, n2, wp + ".norm2", M, C, 1e-5f);
+    wq2 = b.lin(wp + ".attn2.to_q.weight");
+  }
   bf16* q2 = b.buf(M, C);
   {
     Epilogue e;
+    if (fold) {
+      e.bias = lw2.c;
+      e.ln_sums = sums1;
+      e.ln_u = lw2.u;
+      e.ln_eps = 1e-5f;
+    }
     e.out = q2;
     e.ld_out = C;
     Caps caps;
     caps.add(b.site(fid + "-cross-q", C, hw, hw), 0, C);
-    b.linear(n2, M, C, C, b.lin(wp + ".attn2.to_q.weight"), C, e, caps);
+    b.linear(fold ? hs1 : n2, M, C, C, wq2, C, e, caps);
   }
-  b.rel(n2);
+  if (n2) b.rel(n2);
   const long long Mc = (long long)B * h->ctx_len;
   bf16* kv = nullptr;
   int ldkv = 2 * C;
@@ -748,13 +955,17 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     e.ld_res = C;
     e.out = hs2;
     e.ld_out = C;
+    e.row_sums = sums2;
     b.linear(ao2, M, C, C, b.lin(wp + ".attn2.to_out.0.weight"), C, e);
   }
   b.rel(ao2);
   b.rel(hs1);
   // ---- feed-forward (GEGLU), attention.py:1249-1258
-  bf16* n3 = b.buf(M, C);
-  b.layernorm(hs2, n3, wp + ".norm3", M, C, 1e-5f);
+  bf16* n3 = nullptr;
+  if (!fold) {
+    n3 = b.buf(M, C);
+    b.layernorm(hs2, n3, wp + ".norm3", M, C, 1e-5f);
+  }
   const int inner = 4 * C;
   const int bn = 256, half = bn / 2;
   std::vector<int> idx;
@@ -763,20 +974,35 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     for (int j = 0; j < half; ++j) idx.push_back(t * half + j);
     for (int j = 0; j < half; ++j) idx.push_back(inner + t * half + j);
   }
-  const bf16* w1 = b.rows_bf16(wp + ".ff#geglu", {wp + ".ff.net.0.proj.weight"}, &idx);
-  const float* b1 = b.f32_gather(wp + ".ff#geglu_bias", wp + ".ff.net.0.proj.bias", idx);
+  const bf16* w1 = nullptr;
+  const float* b1 = nullptr;
+  Builder::LnW lw3;
+  if (fold) {
+    lw3 = b.rows_bf16_ln(wp + ".ff#geglu_ln", {wp + ".ff.net.0.proj.weight"}, &idx, wp + ".norm3",
+                         wp + ".ff.net.0.proj.bias");
+    w1 = lw3.w;
+    b1 = lw3.c;
+  } else {
+    w1 = b.rows_bf16(wp + ".ff#geglu", {wp + ".ff.net.0.proj.weight"}, &idx);
+    b1 = b.f32_gather(wp + ".ff#geglu_bias", wp + ".ff.net.0.proj.bias", idx);
+  }
   bf16* ffi = b.buf(M, inner);
   {
     Epilogue e;
+    if (fold) {
+      e.ln_sums = sums2;
+      e.ln_u = lw3.u;
+      e.ln_eps = 1e-5f;
+    }
     e.act = kActGeglu;
     e.bias = b1;
     e.out = ffi;
     e.ld_out = inner;
     Caps caps;
     caps.add(b.site(fid + "-ffn-inner", inner, hw, hw), 0, inner);
-    b.linear(n3, M, C, C, w1, 2 * inner, e, caps, 1, 0, 0, 0, bn);
+    b.linear(fold ? hs2 : n3, M, C, C, w1, 2 * inner, e, caps, 1, 0, 0, 0, bn);
   }
-  b.rel(n3);
+  if (n3) b.rel(n3);
   bf16* hs3 = b.buf(M, C);
   {
     Epilogue e;
@@ -785,6 +1011,7 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     e.ld_res = C;
     e.out = hs3;
     e.ld_out = C;
+    e.row_sums = sums_out;
     Caps caps;
     caps.add(b.site(fid + "-out", C, hw, hw), 0, C);
     b.linear(ffi, M, inner, inner, b.lin(wp + ".ff.net.2.weight"), C, e, caps);
@@ -802,18 +1029,24 @@ static void emit_vit(Builder& b, const std::string& wp, const std::string& fid, 
   bf16* t = b.buf(M, C);
   b.groupnorm(x, t, wp + ".norm", B, N, C, groups, 1e-6f, false);
   bf16* hs = b.buf(M, C);
+  // folded LayerNorms: row statistics of the current block input, added by the GEMM that produces it
+  float* sums = b.ln_fold ? b.ln_rows(M) : nullptr;
   {
     // Linear (use_linear_projection) or 1x1 conv: the same [C, C] contraction in NHWC
     Epilogue e;
     e.bias = b.f32(wp + ".proj_in.bias");
     e.out = hs;
     e.ld_out = C;
+    e.row_sums = sums;
     b.linear(t, M, C, C, b.lin(wp + ".proj_in.weight"), C, e);
   }
   b.rel(t);
-  for (int k = 0; k < depth; ++k)
+  for (int k = 0; k < depth; ++k) {
+    float* sums_next = (b.ln_fold && k + 1 < depth) ? b.ln_rows(M) : nullptr;
     hs = emit_tblock(b, wp + ".transformer_blocks." + std::to_string(k), fid + "-block" + std::to_string(k), hs, B, N,
-                     C, heads, ctx_dim, hw);
+                     C, heads, ctx_dim, hw, sums, sums_next);
+    sums = sums_next;
+  }
   {
     Epilogue e;
     e.bias = b.f32(wp + ".proj_out.bias");
@@ -845,6 +1078,8 @@ static int build_unet(Builder& b) {
   const int temb_ch = a.block_out_channels[0] * 4;
   const std::string U = "unet.";
   b.ops = &h->unet_ops;
+  b.gn_fuse = false;   // fused GroupNorm statistics: VAE only (UNet groups of 10 / 20 / 40 channels are not supported)
+  b.gn_cap = 0;
 
   // ---- skip bookkeeping: channels/resolution of every skip in push order, consumers in pop order
   std::vector<Skip> skips;
@@ -942,6 +1177,33 @@ static int build_unet(Builder& b) {
       if (a.up_has_attn[i]) kv_cols += (long long)(lpb + 1) * a.transformer_depth[li] * 2 * a.block_out_channels[li];
     }
     kv_cols += (long long)a.transformer_depth[nl - 1] * 2 * a.block_out_channels[nl - 1];   // mid block
+    // folded LayerNorms: 3 statistics slices [B * hw^2][2] per transformer block (block input, hs1, hs2)
+    long long ln_floats = 0;
+    for (int i = 0; i < nl; ++i) {
+      const long long Mi = (long long)B * (h->L >> i) * (h->L >> i);
+      if (a.down_has_attn[i]) ln_floats += (long long)lpb * a.transformer_depth[i] * 3 * 2 * Mi;
+      const int li = nl - 1 - i;
+      const long long Mu = (long long)B * (h->L >> li) * (h->L >> li);
+      if (a.up_has_attn[i]) ln_floats += (long long)(lpb + 1) * a.transformer_depth[li] * 3 * 2 * Mu;
+    }
+    ln_floats += (long long)a.transformer_depth[nl - 1] * 3 * 2 * B * (h->L >> (nl - 1)) * (h->L >> (nl - 1));
+    {
+      // Off by default: measured on B200 (profiles/r01_ln_fold_ab.md) the three consumer GEMMs of a block (K = C,
+      // epilogue-latency bound) lose more (+6.3 ms / step) than the 210 LayerNorm launches cost (4.5 ms / step).
+      const char* ev = getenv("GDF_LN_FOLD");
+      b.ln_fold = ev && ev[0] == '1';
+    }
+    b.ln_off = 0;
+    b.ln_total = ln_floats;
+    b.ln_slab = b.ln_fold ? b.fbuf(ln_floats) : nullptr;
+    if (b.ln_fold && !b.dry) {
+      float* slab = b.ln_slab;
+      const size_t bytes = (size_t)ln_floats * 4;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(cudaMemsetAsync(slab, 0, bytes, rc.stream));
+        return 0;
+      });
+    }
     b.kv_batched = true;
     b.kv_names.clear();
     b.kv_col = 0;
@@ -1152,6 +1414,10 @@ static int build_unet(Builder& b) {
                Caps(), 1, 0, 0, 0, 0, kv_op);
     }
     b.kv_batched = false;
+    if (b.ln_fold && b.ln_off != b.ln_total && !b.err)
+      return b.set_err(fail(GDF_ERR_SHAPE, "LayerNorm statistics slab: planned %lld floats, used %lld", b.ln_total,
+                            b.ln_off));
+    b.ln_fold = false;
   }
 
   // ---- conv_norm_out + SiLU + conv_out (unet_2d_condition.py:1304-1310)
@@ -1200,6 +1466,8 @@ static int build_dit(Builder& b) {
   const float scale = 1.f / sqrtf((float)hd);
   const std::string T = "transformer.";
   b.ops = &h->unet_ops;
+  b.gn_fuse = false;
+  b.gn_cap = 0;
   h->unet_in_cap = -1;
   if (C % 64 != 0 || hd % 8 != 0 || hd > 160 || p * p * a.in_channels > 64 || a.caption_channels % 8 != 0)
     return b.set_err(fail(GDF_ERR_UNSUPPORTED, "DiT: hidden size %d / head_dim %d / patch %d unsupported", C, hd, p));
@@ -1482,6 +1750,9 @@ static int build_vae(Builder& b) {
   b.ops = &h->vae_ops;
   int hw = h->img;
   int ch = a.block_out_channels[0];
+  b.gn_begin(B, G, 64);
+  // statistics of `cur` for the GroupNorm that reads it next (null: that GroupNorm runs its own statistics pass)
+  float* cur_sums = b.gn_fusable(ch, G, (long long)hw * hw) ? b.gn_slot(B, G) : nullptr;
   // conv_in: image fp32 NCHW -> im2col (K = 27 -> 64) -> GEMM
   bf16* cur = b.buf((long long)B * hw * hw, ch);
   {
@@ -1500,6 +1771,7 @@ static int build_vae(Builder& b) {
     e.n_out = ch;
     e.out = cur;
     e.ld_out = ch;
+    Builder::want_gn_stats(e, cur_sums, ch, G, (long long)hw * hw);
     b.linear(col, (long long)B * hw * hw, 64, 64, w, npad, e);
     b.rel(col);
   }
@@ -1510,10 +1782,14 @@ static int build_vae(Builder& b) {
       Dest d;
       d.out = o;
       d.ld = cout;
+      // the output feeds a GroupNorm (next resnet / mid block) unless a downsampling conv follows
+      const bool last_of_level = (j == a.layers_per_block - 1) && (i != a.num_levels - 1);
+      d.gn_sums = (!last_of_level && b.gn_fusable(cout, G, (long long)hw * hw)) ? b.gn_slot(B, G) : nullptr;
       emit_resnet(b, V + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), "", cur, B, hw, hw, ch,
-                  cout, nullptr, 0, G, eps, d);
+                  cout, nullptr, 0, G, eps, d, cur_sums);
       b.rel(cur);
       cur = o;
+      cur_sums = d.gn_sums;
       ch = cout;
     }
     if (i != a.num_levels - 1) {  // Downsample2D(padding=0): F.pad (0,1,0,1) + conv s2 (downsampling.py:141-147)
@@ -1527,6 +1803,8 @@ static int build_vae(Builder& b) {
       e.n_out = ch;
       e.out = o;
       e.ld_out = ch;
+      cur_sums = (npad == ch && b.gn_fusable(ch, G, (long long)ho * ho)) ? b.gn_slot(B, G) : nullptr;
+      Builder::want_gn_stats(e, cur_sums, ch, G, (long long)ho * ho);
       b.conv3(cur, B, hw, hw, ch, w, npad, 2, 0, e);
       b.rel(cur);
       cur = o;
@@ -1540,11 +1818,13 @@ static int build_vae(Builder& b) {
     Dest d;
     d.out = r0;
     d.ld = ch;
-    emit_resnet(b, V + "mid_block.resnets.0", "", cur, B, hw, hw, ch, ch, nullptr, 0, G, eps, d);
+    d.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+    emit_resnet(b, V + "mid_block.resnets.0", "", cur, B, hw, hw, ch, ch, nullptr, 0, G, eps, d, cur_sums);
     b.rel(cur);
     const std::string ap = V + "mid_block.attentions.0";
     bf16* hn = b.buf(M, ch);
-    b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
+    if (d.gn_sums) b.groupnorm_from_sums(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false, d.gn_sums);
+    else b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
     // Q | K fused projection
     const bf16* wqk = b.rows_bf16(ap + "#qk", {ap + ".to_q.weight", ap + ".to_k.weight"}, nullptr);
     std::vector<int> ident;
@@ -1613,6 +1893,8 @@ static int build_vae(Builder& b) {
       e.ld_res = ch;
       e.out = ao;
       e.ld_out = ch;
+      cur_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+      Builder::want_gn_stats(e, cur_sums, ch, G, (long long)N);
       b.linear(o, M, ch, ch, b.lin(ap + ".to_out.0.weight"), ch, e);
     }
     b.rel(o);
@@ -1622,13 +1904,16 @@ static int build_vae(Builder& b) {
     Dest d1;
     d1.out = r1;
     d1.ld = ch;
-    emit_resnet(b, V + "mid_block.resnets.1", "", ao, B, hw, hw, ch, ch, nullptr, 0, G, eps, d1);
+    d1.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+    emit_resnet(b, V + "mid_block.resnets.1", "", ao, B, hw, hw, ch, ch, nullptr, 0, G, eps, d1, cur_sums);
     b.rel(ao);
     cur = r1;
+    cur_sums = d1.gn_sums;
   }
   // conv_norm_out + SiLU + (conv_out . quant_conv folded into one 3x3 conv) -> fp32 moments [M, 8]
   bf16* t = b.buf(M, ch);
-  b.groupnorm(cur, t, V + "conv_norm_out", B, N, ch, G, eps, true);
+  if (cur_sums) b.groupnorm_from_sums(cur, t, V + "conv_norm_out", B, N, ch, G, eps, true, cur_sums);
+  else b.groupnorm(cur, t, V + "conv_norm_out", B, N, ch, G, eps, true);
   b.rel(cur);
   const int nm = 2 * a.latent_channels;
   {

@@ -267,6 +267,30 @@ __device__ __forceinline__ float gelu_erf_lean(float g) {
   return g * (g >= 0.f ? 1.f - h : h);
 }
 
+// GEGLU on a pair of columns, packed fp32 math: v *= g * Phi(g), Phi(g) = 0.5 + sgn(g) * (0.5 - h(|g|)) with the same
+// erfc tail as gelu_erf_lean. ~10 issue slots per element instead of ~25 (the IEEE __frcp_rn alone cost a branch and
+// a slow-path call per element); this epilogue is co-critical with the MMAs of the K = C GEGLU projection.
+__device__ __forceinline__ void geglu_pair(float& v0, float& v1, float g0, float g1) {
+  const f32x2 ag = f2_make(fabsf(g0), fabsf(g1));
+  float d0, d1;
+  f2_get(f2_fma(f2_splat(0.3275911f * 0.70710678f), ag, f2_splat(1.f)), d0, d1);
+  const f32x2 t = f2_make(rcp_approx(d0), rcp_approx(d1));
+  f32x2 q = f2_fma(f2_splat(0.5f * 1.061405429f), t, f2_splat(0.5f * -1.453152027f));
+  q = f2_fma(q, t, f2_splat(0.5f * 1.421413741f));
+  q = f2_fma(q, t, f2_splat(0.5f * -0.284496736f));
+  q = f2_fma(q, t, f2_splat(0.5f * 0.254829592f));
+  const f32x2 g = f2_make(g0, g1);
+  float x0, x1;
+  f2_get(f2_mul(f2_mul(g, f2_splat(-0.5f * 1.4426950408889634f)), g), x0, x1);
+  const f32x2 h = f2_mul(f2_mul(q, t), f2_make(ex2_approx(x0), ex2_approx(x1)));
+  float e0, e1;
+  f2_get(f2_fma(h, f2_splat(-1.f), f2_splat(0.5f)), e0, e1);   // 0.5 - h >= 0
+  e0 = __uint_as_float(__float_as_uint(e0) ^ (__float_as_uint(g0) & 0x80000000u));
+  e1 = __uint_as_float(__float_as_uint(e1) ^ (__float_as_uint(g1) & 0x80000000u));
+  const f32x2 phi = f2_add(f2_make(e0, e1), f2_splat(0.5f));
+  f2_get(f2_mul(f2_mul(f2_make(v0, v1), g), phi), v0, v1);
+}
+
 template <bool kF16>
 __device__ __forceinline__ void stage_chunk(uint8_t* buf, const int (&swz)[4], const float* v) {
 #pragma unroll
@@ -326,6 +350,59 @@ __device__ __forceinline__ void residual_add(const ResidualRegs& r, float* v) {
     f = unpack_bf16x2(r.u[q].z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
     f = unpack_bf16x2(r.u[q].w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
   }
+}
+
+// ---------------------------------------------------------------------------------- fused GroupNorm statistics
+// Transposing butterfly: N values per lane are summed over the 32 lanes (= 32 rows of the tile); every halving step
+// exchanges half of the values, so N values cost N - 1 + (5 - log2 N) shuffles and lane l ends with value l >> (5 - log2 N).
+template <int N, int O>
+struct GnRed {
+  static __device__ __forceinline__ void run(float* a, int lane) {
+    if constexpr (N > 1) {
+      constexpr int H = N / 2;
+      const bool up = (lane & O) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float send = up ? a[i] : a[i + H];
+        const float keep = up ? a[i + H] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      if constexpr (O > 1) GnRed<H, O / 2>::run(a, lane);
+    } else {
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], O);
+      if constexpr (O > 1) GnRed<1, O / 2>::run(a, lane);
+    }
+  }
+};
+template <int kCpgLog2>
+__device__ __forceinline__ void gn_accumulate_t(const float* v, float* dst, bool ok, int lane) {
+  constexpr int kCpg = 1 << kCpgLog2;
+  constexpr int kNg = 32 / kCpg;       // groups inside 32 columns
+  constexpr int kNv = 2 * kNg;
+  float a[kNv];
+#pragma unroll
+  for (int k = 0; k < kNg; ++k) {
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCpg; ++j) {
+      sm += v[k * kCpg + j];
+      sq = fmaf(v[k * kCpg + j], v[k * kCpg + j], sq);
+    }
+    a[2 * k] = ok ? sm : 0.f;
+    a[2 * k + 1] = ok ? sq : 0.f;
+  }
+  GnRed<kNv, 16>::run(a, lane);
+  constexpr int kLanesPerValue = 32 / kNv;
+  if (ok && (lane & (kLanesPerValue - 1)) == 0) atomicAdd(dst + lane / kLanesPerValue, a[0]);
+}
+// v: the 32 final values of this thread's row in columns [col0, col0 + 32) (all inside n_out)
+__device__ __forceinline__ void gn_accumulate(const GemmParams& p, const float* v, int col0, long long row, bool row_ok,
+                                              int lane) {
+  const long long img = row_ok ? row / p.gn_rows_per_img : 0;
+  float* dst = p.gn_sums + (img * p.gn_groups + (col0 >> p.gn_cpg_log2)) * 2;
+  if (p.gn_cpg_log2 == 2) gn_accumulate_t<2>(v, dst, row_ok, lane);
+  else if (p.gn_cpg_log2 == 3) gn_accumulate_t<3>(v, dst, row_ok, lane);
+  else gn_accumulate_t<4>(v, dst, row_ok, lane);
 }
 
 // CG = 1: one CTA per 128 x block_n tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x block_n
@@ -676,7 +753,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               if (p.ln_sums) fma_f32x32(p.ln_u + gcol0 + hh * 32, ln_b, g);
               if (p.bias) add_f32x32(p.bias + gcol0 + hh * 32, g);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[hh][j] *= gelu_erf_lean(g[j]);
+              for (int j = 0; j < 32; j += 2) geglu_pair(v[hh][j], v[hh][j + 1], g[j], g[j + 1]);
             }
           } else if (p.act == kActGeluTanh) {
 #pragma unroll
@@ -700,6 +777,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) { rs_sum += v[hh][j]; rs_sq = fmaf(v[hh][j], v[hh][j], rs_sq); }
             }
+            if (p.gn_sums) gn_accumulate(p, v[hh], ocol0 + hh * 32, row, row_ok, lane);
           }
           if (resrow) {   // the residual registers are free again: fetch the next full round while this one is stored
             const int nc = c + 128, nocol0 = ocol0 + 128;

@@ -75,6 +75,12 @@ struct GemmParams {
   const float* ln_u;           // [N] row sums of the (gamma-folded, bf16-rounded) weight matrix
   float ln_inv_c, ln_eps;      // 1 / row width, epsilon
   float* row_sums;             // [M][2]: this launch adds (sum, sum of squares) of its final output rows, or null
+  // ---- GroupNorm statistics of the final output, for the GroupNorm that consumes it (resnet.py:327,351): per
+  // (image, group) (sum, sum of squares) added with atomics. Groups of 4 / 8 / 16 channels; every 128-row tile lies
+  // inside one image (checked on the host); lean epilogue path only.
+  float* gn_sums;              // [images][gn_groups][2] or null
+  int gn_cpg_log2, gn_groups;
+  long long gn_rows_per_img;
 };
 
 // Tensor maps of one launch: operands + the six possible 16-bit destinations (TMA-store path).

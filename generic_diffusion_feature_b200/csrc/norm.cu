@@ -214,6 +214,38 @@ cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const f
                     C, G, nchunks, silu ? 1 : 0);
 }
 
+// Statistics accumulated by the producing GEMM's epilogue (GemmParams::gn_sums): (sum, sum sq) per (image, group)
+// -> (mean, rstd); replaces groupnorm_stats_kernel + groupnorm_finalize_kernel (one full read of x less).
+__global__ void groupnorm_finalize_sums_kernel(const float* __restrict__ sums, float* __restrict__ stats, int n_bg,
+                                               double inv_n, float eps) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bg) return;
+  const double mean = (double)sums[2 * i] * inv_n;
+  double var = (double)sums[2 * i + 1] * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+cudaError_t launch_groupnorm_from_sums(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW,
+                                       int C, int G, float eps, bool silu, const float* sums, float* workspace,
+                                       cudaStream_t stream) {
+  if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > kGnThreads * kGnMaxSlots) return cudaErrorInvalidValue;
+  int nchunks = (148 * 4 + B - 1) / B;
+  if (nchunks > (HW + 31) / 32) nchunks = (HW + 31) / 32;
+  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
+  if (nchunks < 1) nchunks = 1;
+  float* stats = workspace + (size_t)B * kGnMaxChunks * G * 2;
+  const int n_bg = B * G;
+  cudaError_t e = launch_pdl(groupnorm_finalize_sums_kernel, dim3((n_bg + 127) / 128), dim3(128), 0, stream, sums, stats,
+                             n_bg, 1.0 / ((double)HW * (C / G)), eps);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(groupnorm_apply_kernel, dim3(nchunks, B), dim3(kGnThreads), 0, stream, x, y, gamma, beta,
+                    (const float*)stats, HW, C, G, nchunks, silu ? 1 : 0);
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm
 // One warp per token row; the row lives in registers between the statistics and the normalisation (one global
 // read, one write). kV = 128-bit vectors per lane (C <= 256 * kV).

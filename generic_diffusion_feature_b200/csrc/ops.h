@@ -36,6 +36,9 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   const float* ln_u = nullptr;
   float ln_eps = 1e-5f;
   float* row_sums = nullptr;        // (sum, sum sq) of the final output rows for a LayerNorm folded into the consumer
+  float* gn_sums = nullptr;         // fused GroupNorm statistics of the output (see GemmParams); groups of gn_cpg
+  int gn_cpg = 0, gn_groups = 0;    //   channels (4 / 8 / 16), gn_rows_per_img rows (pixels) per image
+  long long gn_rows_per_img = 0;
   bool in_f16 = false;              // operands are fp16 instead of bf16
   bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };
@@ -67,6 +70,10 @@ int gemm_num_sms();
 size_t gn_workspace_floats(int B, int G);
 cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
                              float eps, bool silu, float* workspace, cudaStream_t stream);
+// GroupNorm whose (sum, sum sq) per (image, group) were accumulated by the producing GEMM (Epilogue::gn_sums)
+cudaError_t launch_groupnorm_from_sums(const bf16* x, bf16* y, const float* gamma, const float* beta, int B, int HW,
+                                       int C, int G, float eps, bool silu, const float* sums, float* workspace,
+                                       cudaStream_t stream);
 // LayerNorm over rows of x[M, C] (ld = C) with optional affine and optional per-sample modulation
 // y = LN(x) * (1 + scale[b]) + shift[b] (PixArt AdaLN-single), rows_per_batch rows per sample.
 cudaError_t launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* beta, long long M, int C,

@@ -162,6 +162,21 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.ln_inv_c = 1.f / (float)p.K;
   p.ln_eps = e.ln_eps;
   p.row_sums = e.row_sums;
+  p.gn_sums = e.gn_sums;
+  p.gn_cpg_log2 = e.gn_cpg == 4 ? 2 : e.gn_cpg == 8 ? 3 : 4;
+  p.gn_groups = e.gn_groups;
+  p.gn_rows_per_img = e.gn_rows_per_img > 0 ? e.gn_rows_per_img : 1;
+}
+
+// fused GroupNorm statistics need the lean epilogue on every column and 128-row tiles that stay inside one image
+static int check_gn_stats(const GemmParams& p, const Epilogue& e) {
+  if (!e.gn_sums) return GDF_OK;
+  const bool cpg_ok = e.gn_cpg == 4 || e.gn_cpg == 8 || e.gn_cpg == 16;
+  const bool tile_ok = (p.a_mode == kALinear) ? (e.gn_rows_per_img % kBlockM == 0) : (p.tb == 1);
+  if (!cpg_ok || !tile_ok || !p.fast_epi || p.n_out % 32 != 0 || p.act == kActGeglu || p.batch != 1)
+    return fail(GDF_ERR_UNSUPPORTED, "fused GroupNorm statistics: unsupported launch (cpg %d, n_out %d, fast_epi %d)",
+                e.gn_cpg, p.n_out, p.fast_epi);
+  return GDF_OK;
 }
 
 int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, const bf16* W, int N, int ldw,
@@ -203,6 +218,7 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
     GDF_TRY(make_tmap_bf16(&g->maps.b, W, 3, dims, str, box));
   }
   GDF_TRY(setup_stores(g));
+  GDF_TRY(check_gn_stats(p, e));
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
 
@@ -262,6 +278,7 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
     GDF_TRY(make_tmap_bf16(&g->maps.b, Wp, 3, dims, str, box));
   }
   GDF_TRY(setup_stores(g));
+  GDF_TRY(check_gn_stats(p, e));
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
 

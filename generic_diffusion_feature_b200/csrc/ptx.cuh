@@ -306,6 +306,32 @@ __device__ __forceinline__ void ffma2(float& x0, float& x1, float s0, float s1, 
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(sv), "l"(mv), "l"(av));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
 }
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work)
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 f2_make(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float a) { return f2_make(a, a); }
+__device__ __forceinline__ void f2_get(f32x2 x, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
 // 2^x on the FMA / ALU pipes (takes load off the 16-lane MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5],
 // degree-3 minimax polynomial of 2^f (max relative error 7.5e-5, below fp16 resolution), n added to the exponent field.
 __device__ __forceinline__ float ex2_poly(float x) {

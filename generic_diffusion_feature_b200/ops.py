@@ -11,7 +11,8 @@ ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3
 
 def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_per_batch=0, act=ACT_NONE,
                   col_scale=None, residual=None, out_scale=1.0, alpha=1.0, out2=None, out_f32=None, cap_pre=None,
-                  caps=(), n_out=0, out_batch_stride=0, out_f16_from=0):
+                  caps=(), n_out=0, out_batch_stride=0, out_f16_from=0, ln_sums=None, ln_u=None, ln_eps=1e-5,
+                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0):
     e = Epilogue()
     e.alpha = alpha
     e.n_out = n_out
@@ -42,6 +43,14 @@ def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_pe
     e.num_cap = len(caps)
     for i, (t, c0, c1) in enumerate(caps):
         e.cap[i] = CaptureSeg(ptr(t), c0, c1, t.stride(-2))
+    e.ln_sums_dev = ptr(ln_sums)      # folded LayerNorm of the A rows (fp32 [M, 2] sums written by a producer's row_sums)
+    e.ln_u_dev = ptr(ln_u)
+    e.ln_eps = ln_eps
+    e.row_sums_dev = ptr(row_sums)
+    e.gn_sums_dev = ptr(gn_sums)      # fused GroupNorm statistics of the output: fp32 [images, groups, 2], ADDED to
+    e.gn_cpg = gn_cpg
+    e.gn_groups = gn_groups
+    e.gn_rows_per_img = gn_rows_per_img
     return e
 
 

@@ -187,6 +187,17 @@ typedef struct gdf_epilogue {
   void* out_f32_dev; int ld_out_f32;
   void* cap_pre_dev; int ld_cap_pre;                     /* fp16, before residual */
   gdf_capture_seg cap[3]; int num_cap;                   /* fp16, final value */
+  /* LayerNorm folded into the consuming projection (attention.py:497,525,566): A holds the un-normalised rows, the
+   * weight carries gamma, bias carries beta.W^T: value = rstd[row] * (acc - mean[row] * ln_u[col]) + bias[col] */
+  const void* ln_sums_dev;        /* fp32 [M][2] (sum, sum of squares) of the A rows, or NULL */
+  const void* ln_u_dev;           /* fp32 [N] row sums of the gamma-folded bf16 weight */
+  float ln_eps;
+  void* row_sums_dev;             /* fp32 [M][2]: the launch ADDS (sum, sum sq) of its final output rows, or NULL */
+  /* GroupNorm statistics of the output for the GroupNorm that consumes it (resnet.py:327,351): the launch ADDS
+   * (sum, sum sq) per (image, group); groups of gn_cpg = 4 / 8 / 16 channels, gn_rows_per_img % 128 == 0 */
+  void* gn_sums_dev;              /* fp32 [images][gn_groups][2] or NULL */
+  int gn_cpg, gn_groups;
+  int64_t gn_rows_per_img;
 } gdf_epilogue;
 
 /* C[M,N] = A[M,K] W[N,K]^T (+ fused epilogue); batch > 1: A/out strided by *_batch_stride elements,

@@ -54,6 +54,53 @@ def test_linear_bias(cuda_dev, M, N, K):
     check_close(out, a.float() @ w.float().T + bias, what="linear %dx%dx%d" % (M, N, K))
 
 
+@pytest.mark.parametrize("M,C,N,geglu", [(1000, 640, 1920, False), (8192, 1280, 1280, False), (700, 320, 2560, True),
+                                         (300, 1280, 10240, True)])
+def test_linear_layernorm_fold(cuda_dev, M, C, N, geglu):
+    """LayerNorm folded into the consuming projection (attention.py:497,525,566): the producer GEMM adds per-row
+    (sum, sum sq) of its output (row_sums), the consumer runs on the un-normalised rows with gamma folded into the
+    weight and applies rstd * (acc - mean * u) + (bias + beta.W^T) in its epilogue. Reference: F.layer_norm + matmul."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(40)
+    # producer: x = a @ w0^T + b0 + res  (bf16), statistics of x into sums
+    a = _rand_bf16(g, M, 320)
+    w0 = _rand_bf16(g, C, 320, scale=320 ** -0.5)
+    b0 = torch.randn(C, generator=g, device="cuda")
+    res = _rand_bf16(g, M, C) + 0.5   # non-zero row mean
+    x = torch.zeros(M, C, dtype=torch.bfloat16, device="cuda")
+    sums = torch.zeros(M, 2, device="cuda")
+    ops.linear(a, w0, ops.make_epilogue(out=x, bias=b0, residual=res, row_sums=sums))
+    torch.cuda.synchronize()
+    xf = a.float() @ w0.float().T + b0 + res.float()
+    assert torch.allclose(sums[:, 0], xf.sum(1), rtol=1e-3, atol=1e-2), "row sums"
+    assert torch.allclose(sums[:, 1], (xf * xf).sum(1), rtol=1e-3, atol=1e-2), "row sums of squares"
+    # consumer
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(C, generator=g, device="cuda")
+    W = torch.randn(N, C, generator=g, device="cuda") * C ** -0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    Wg = (W * gamma).to(torch.bfloat16)
+    u = Wg.float().sum(1).contiguous()
+    c = (bias + W @ beta).contiguous()
+    n_out = N // 2 if geglu else N
+    if geglu:   # value / gate rows interleaved per 256-column tile (128 + 128), as the executor packs them
+        idx = []
+        for t in range(n_out // 128):
+            idx += list(range(t * 128, t * 128 + 128)) + list(range(n_out + t * 128, n_out + t * 128 + 128))
+        idx = torch.tensor(idx, device="cuda")
+        Wg_k, u_k, c_k = Wg[idx].contiguous(), u[idx].contiguous(), c[idx].contiguous()
+    else:
+        Wg_k, u_k, c_k = Wg, u, c
+    out = torch.zeros(M, n_out, dtype=torch.bfloat16, device="cuda")
+    ep = ops.make_epilogue(out=out, bias=c_k, act=ops.ACT_GEGLU if geglu else ops.ACT_NONE, ln_sums=sums, ln_u=u_k,
+                           ln_eps=1e-5)
+    ops.linear(x, Wg_k, ep, block_n=256 if geglu else 0)
+    torch.cuda.synchronize()
+    y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ W.T + bias
+    want = y[:, :n_out] * F.gelu(y[:, n_out:]) if geglu else y
+    check_close(out, want, what="LN-folded linear M%d C%d N%d geglu=%d" % (M, C, N, geglu))
+
+
 def test_linear_full_epilogue(cuda_dev):
     """bias + per-sample row bias + residual + out_scale + pre/post captures + second destination + fp32 out."""
     ops = _ops()
@@ -403,3 +450,29 @@ def test_correspondence_vs_oracle(cuda_dev, C, hw, load, n):
     _, p2 = Cm.find_nn_source_correspondences(f1.cuda(), f2.cuda(), pts, None, (load, load))
     torch.cuda.synchronize()
     _check_corr(p2, f1, f2, pts, (load, load))
+
+
+@pytest.mark.parametrize("C,G,HW,B", [(128, 32, 4096, 2), (256, 32, 1024, 3), (512, 32, 256, 2)])
+def test_conv_fused_groupnorm_stats(cuda_dev, C, G, HW, B):
+    """GroupNorm statistics accumulated by the producing conv's epilogue (gn_sums) == statistics of its output."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(41)
+    H = W = int(math.isqrt(HW))
+    x = _rand_bf16(g, B, H, W, 64)
+    w = torch.randn(C, 64, 3, 3, generator=g, device="cuda") * (9 * 64) ** -0.5
+    bias = torch.randn(C, generator=g, device="cuda")
+    res = _rand_bf16(g, B * HW, C)
+    wp = ops.pack_conv_weight(w)
+    out = torch.zeros(B * HW, C, dtype=torch.bfloat16, device="cuda")
+    sums = torch.zeros(B, G, 2, device="cuda")
+    ep = ops.make_epilogue(out=out, bias=bias, residual=res, gn_sums=sums, gn_cpg=C // G, gn_groups=G, gn_rows_per_img=HW)
+    ops.conv3x3(x, wp, ep)
+    torch.cuda.synchronize()
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    want = want.permute(0, 2, 3, 1).reshape(B * HW, C) + res.float()
+    check_close(out, want, what="conv with fused GN stats")
+    wg = want.reshape(B, HW, G, C // G)
+    s_want = wg.sum(dim=(1, 3))
+    q_want = (wg * wg).sum(dim=(1, 3))
+    assert torch.allclose(sums[..., 0], s_want, rtol=2e-3, atol=0.5), (sums[..., 0] - s_want).abs().max()
+    assert torch.allclose(sums[..., 1], q_want, rtol=2e-3, atol=0.5), (sums[..., 1] - q_want).abs().max()
