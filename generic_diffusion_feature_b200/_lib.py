@@ -21,7 +21,7 @@ GDF_MAX_LEVELS = 4
 # every symbol include/gdf.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
-    "gdf_create", "gdf_create_dit", "gdf_denoise_capture_dit", "gdf_op_attention_bias", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
+    "gdf_create", "gdf_create_dit", "gdf_denoise_capture_dit", "gdf_create_flux", "gdf_denoise_capture_flux", "gdf_op_attention_bias", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
     "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
@@ -73,7 +73,7 @@ class VaeArch(ctypes.Structure):
     _fields_ = [
         ("in_channels", c_int), ("latent_channels", c_int), ("num_levels", c_int),
         ("block_out_channels", c_int * GDF_MAX_LEVELS), ("layers_per_block", c_int),
-        ("norm_num_groups", c_int), ("norm_eps", c_float), ("scaling_factor", c_float),
+        ("norm_num_groups", c_int), ("norm_eps", c_float), ("scaling_factor", c_float), ("shift_factor", c_float),
     ]
 
 
@@ -81,6 +81,14 @@ class DitArch(ctypes.Structure):
     _fields_ = [
         ("in_channels", c_int), ("out_channels", c_int), ("patch_size", c_int), ("num_layers", c_int),
         ("num_heads", c_int), ("head_dim", c_int), ("caption_channels", c_int), ("norm_eps", c_float),
+    ]
+
+
+class FluxArch(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("num_layers", c_int), ("num_single_layers", c_int), ("num_heads", c_int),
+        ("head_dim", c_int), ("joint_attention_dim", c_int), ("pooled_projection_dim", c_int),
+        ("guidance_embeds", c_int),
     ]
 
 
@@ -134,6 +142,8 @@ def load():
         lib.gdf_create.argtypes = [ctypes.POINTER(UNetArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
         lib.gdf_create_dit.argtypes = [ctypes.POINTER(DitArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
         lib.gdf_denoise_capture_dit.argtypes = [P, c_float, P, c_int, P, P, P, P]
+        lib.gdf_create_flux.argtypes = [ctypes.POINTER(FluxArch), ctypes.POINTER(VaeArch), c_int, ctypes.POINTER(P)]
+        lib.gdf_denoise_capture_flux.argtypes = [P, c_float, c_float, P, c_int, P, P, P, P, P, P]
         lib.gdf_destroy.argtypes = [P]
         lib.gdf_load_weights.argtypes = [P, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(P),
                                          ctypes.POINTER(c_int64), ctypes.POINTER(c_int), c_int, P]

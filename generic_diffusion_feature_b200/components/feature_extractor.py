@@ -63,6 +63,21 @@ def _dit_feature_ids(cfg):
     return ids
 
 
+def _flux_feature_ids(cfg):
+    """Ids of the Flux branch of prepare_feature_extractor (feature_extractor.py:98-123) in execution order:
+    double blocks q, k, v, attn-out (attention_processor.py:2280-2283, 2355-2356), norm-out (transformer_flux.py:
+    200-201), ffn-inner (attention.py:1249-1258), out (:210-211); single blocks (numbered after the double
+    blocks) q, k, v, attn-out (attention_processor.py:2285-2289, 2358-2360), out (transformer_flux.py:107-108)."""
+    ids = []
+    for k in range(cfg["layers"]):
+        for tag in ("q", "k", "v", "attn-out", "norm-out", "ffn-inner", "out"):
+            ids.append("vit-block%d-%s" % (k, tag))
+    for k in range(cfg["layers"], cfg["layers"] + cfg["single_layers"]):
+        for tag in ("q", "k", "v", "attn-out", "out"):
+            ids.append("vit-block%d-%s" % (k, tag))
+    return ids
+
+
 class FeatureStore:
     """Mirror of the reference FeatureStore (feature_extractor.py:8-80) backed by the arena plan."""
 
@@ -148,6 +163,8 @@ def selected_ids(feature_store, pipe):
     """Ids to plan: enabled JSON keys in file order, or every id of the architecture when accept_all
     (feature_extractor.py:10-15,36). `map` ids need the attention-probability path and raise."""
     if feature_store.accept_all:
+        if getattr(pipe, "flux_cfg", None):
+            return _flux_feature_ids(pipe.flux_cfg)
         return _dit_feature_ids(pipe.dit_cfg) if getattr(pipe, "dit_cfg", None) else _unet_feature_ids(pipe.unet_cfg)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:

@@ -14,7 +14,7 @@ import zlib
 import torch
 
 from .. import _lib
-from .._lib import DitArch, UNetArch, VaeArch, check
+from .._lib import DitArch, FluxArch, UNetArch, VaeArch, check
 
 # SURVEY.md Appendix B (diffusers configs of the checkpoints models.py:18-70 names)
 UNET_CONFIGS = {
@@ -41,7 +41,83 @@ DIT_CONFIGS = {
 }
 VAE_CONFIGS["pixart-sigma"] = VAE_CONFIGS["xl"]          # PixArt-Sigma ships the SDXL VAE
 VAE_CONFIGS["pixart-sigma-512"] = VAE_CONFIGS["xl"]
-_NOT_BUILT = ("pixart-alpha", "if", "hunyuan", "flux")
+# [black-forest-labs/FLUX.1-dev transformer/config.json = the FluxTransformer2DModel defaults the reference vendors at
+# transformers/transformer_flux.py:253-266 + guidance_embeds true; vae/config.json, from memory: 16 latent channels,
+# no quant_conv, scaling_factor 0.3611, shift_factor 0.1159]
+FLUX_CONFIGS = {
+    "flux": dict(layers=19, single_layers=38, heads=24, head_dim=128, in_ch=64, joint_dim=4096, pooled_dim=768,
+                 guidance_embeds=True, axes_dims_rope=(16, 56, 56), ctx_len=512),
+}
+VAE_CONFIGS["flux"] = dict(block_out=(128, 256, 512, 512), layers=2, latent=16, eps=1e-6, scaling_factor=0.3611,
+                           shift_factor=0.1159, quant_conv=False)
+_NOT_BUILT = ("pixart-alpha", "if", "hunyuan")
+
+
+def flux_param_specs(cfg):
+    """(name, shape) of every FluxTransformer2DModel parameter (transformer_flux.py:253-325; Attention ctor
+    attention_processor.py:105-297 with qk_norm='rms_norm', added_kv_proj_dim / pre_only), diffusers naming."""
+    C = cfg["heads"] * cfg["head_dim"]
+    hd = cfg["head_dim"]
+    out = []
+
+    def lin(n, o, i):
+        out.append((n + ".weight", (o, i)))
+        out.append((n + ".bias", (o,)))
+
+    lin("x_embedder", C, cfg["in_ch"])
+    lin("context_embedder", C, cfg["joint_dim"])
+    embs = ["timestep_embedder"] + (["guidance_embedder"] if cfg["guidance_embeds"] else [])
+    for e in embs:
+        lin("time_text_embed.%s.linear_1" % e, C, 256)
+        lin("time_text_embed.%s.linear_2" % e, C, C)
+    lin("time_text_embed.text_embedder.linear_1", C, cfg["pooled_dim"])
+    lin("time_text_embed.text_embedder.linear_2", C, C)
+    for k in range(cfg["layers"]):
+        b = "transformer_blocks.%d" % k
+        lin(b + ".norm1.linear", 6 * C, C)
+        lin(b + ".norm1_context.linear", 6 * C, C)
+        for pn in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
+            lin("%s.attn.%s" % (b, pn), C, C)
+        for nn_ in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+            out.append(("%s.attn.%s.weight" % (b, nn_), (hd,)))
+        for f in ("ff", "ff_context"):
+            lin("%s.%s.net.0.proj" % (b, f), 4 * C, C)
+            lin("%s.%s.net.2" % (b, f), C, 4 * C)
+    for k in range(cfg["single_layers"]):
+        b = "single_transformer_blocks.%d" % k
+        lin(b + ".norm.linear", 3 * C, C)
+        lin(b + ".proj_mlp", 4 * C, C)
+        lin(b + ".proj_out", C, 5 * C)
+        for pn in ("to_q", "to_k", "to_v"):
+            lin("%s.attn.%s" % (b, pn), C, C)
+        for nn_ in ("norm_q", "norm_k"):
+            out.append(("%s.attn.%s.weight" % (b, nn_), (hd,)))
+    lin("norm_out.linear", 2 * C, C)
+    lin("proj_out", cfg["in_ch"], C)
+    return out
+
+
+def flux_rope_tables(cfg, ctx_len, grid):
+    """cos / sin tables [ctx_len + grid*grid, head_dim] of FluxPosEmbed for ids = cat(txt_ids (zeros),
+    img_ids (0, y, x)) (pipeline_flux_img2img.py:483-494, transformer_flux.py:481-482). [diffusers embeddings.
+    FluxPosEmbed / get_1d_rotary_pos_embed(use_real=True, repeat_interleave_real=True, freqs_dtype=float64),
+    un-vendored]: per axis, freqs = pos * theta^(-2i/d); cos / sin repeat-interleaved by 2; axes concatenated."""
+    import numpy as np
+    S = ctx_len + grid * grid
+    ids = np.zeros((S, 3), dtype=np.float64)
+    yy, xx = np.meshgrid(np.arange(grid), np.arange(grid), indexing="ij")
+    ids[ctx_len:, 1] = yy.reshape(-1)
+    ids[ctx_len:, 2] = xx.reshape(-1)
+    cos, sin = [], []
+    for a, d in enumerate(cfg["axes_dims_rope"]):
+        freqs = 1.0 / (10000.0 ** (np.arange(0, d, 2, dtype=np.float64)[: d // 2] / d))
+        ang = np.outer(ids[:, a], freqs)
+        cos.append(np.repeat(np.cos(ang), 2, axis=1))
+        sin.append(np.repeat(np.sin(ang), 2, axis=1))
+    cos = torch.from_numpy(np.concatenate(cos, axis=1)).float()
+    sin = torch.from_numpy(np.concatenate(sin, axis=1)).float()
+    assert cos.shape[1] == cfg["head_dim"], "axes_dims_rope must sum to head_dim"
+    return cos, sin
 
 
 def dit_param_specs(cfg):
@@ -224,7 +300,8 @@ def vae_param_specs(cfg):
     resnet("encoder.mid_block.resnets.1", ch, ch)
     norm("encoder.conv_norm_out", ch)
     conv("encoder.conv_out", 2 * cfg["latent"], ch, 3)
-    conv("quant_conv", 2 * cfg["latent"], 2 * cfg["latent"], 1)
+    if cfg.get("quant_conv", True):
+        conv("quant_conv", 2 * cfg["latent"], 2 * cfg["latent"], 1)
     return out
 
 
@@ -240,7 +317,7 @@ def init_param(name, shape, device="cpu"):
     g = torch.Generator(device=device)
     g.manual_seed(zlib.crc32(name.encode()))
     r = torch.randn(*shape, generator=g, device=device, dtype=torch.float32)
-    is_norm = ".norm" in name or "group_norm" in name or "conv_norm_out" in name
+    is_norm = (".norm" in name or "group_norm" in name or "conv_norm_out" in name) and ".linear." not in name
     if name.endswith(".bias"):
         return 0.02 * r
     if is_norm:
@@ -252,10 +329,17 @@ def init_param(name, shape, device="cpu"):
     return r * (gain / fan_in ** 0.5)
 
 
-def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None, dit_cfg=None):
+def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None, dit_cfg=None, flux_cfg=None):
     """name -> fp32 tensor for 'unet.*' (or 'transformer.*') and 'vae.*' (random init; no checkpoints offline)."""
     vcfg = vae_cfg or VAE_CONFIGS[version]
     sd = {}
+    fcfg = flux_cfg or (FLUX_CONFIGS.get(version) if (unet_cfg is None and dit_cfg is None) else None)
+    if fcfg is not None:
+        for n, s in flux_param_specs(fcfg):
+            sd["transformer." + n] = init_param("transformer." + n, s, device)
+        for n, s in vae_param_specs(vcfg):
+            sd["vae." + n] = init_param("vae." + n, s, device)
+        return sd
     dcfg = dit_cfg or (DIT_CONFIGS.get(version) if unet_cfg is None else None)
     if dcfg is not None:
         C = dcfg["heads"] * dcfg["head_dim"]
@@ -311,6 +395,7 @@ def _vae_arch(cfg):
     a.norm_num_groups = 32
     a.norm_eps = cfg["eps"]
     a.scaling_factor = cfg["scaling_factor"]
+    a.shift_factor = cfg.get("shift_factor", 0.0)
     return a
 
 
@@ -323,13 +408,23 @@ def _dit_arch(cfg):
     return a
 
 
+def _flux_arch(cfg):
+    a = FluxArch()
+    a.in_channels, a.num_layers, a.num_single_layers = cfg["in_ch"], cfg["layers"], cfg["single_layers"]
+    a.num_heads, a.head_dim = cfg["heads"], cfg["head_dim"]
+    a.joint_attention_dim, a.pooled_projection_dim = cfg["joint_dim"], cfg["pooled_dim"]
+    a.guidance_embeds = int(cfg["guidance_embeds"])
+    return a
+
+
 class B200Pipe:
     """What `FeatureExtractor` holds in place of a diffusers pipeline on the B200 path."""
 
-    def __init__(self, version, unet_cfg, vae_cfg, device, dit_cfg=None):
+    def __init__(self, version, unet_cfg, vae_cfg, device, dit_cfg=None, flux_cfg=None):
         self.version = version
         self.unet_cfg = unet_cfg
         self.dit_cfg = dit_cfg
+        self.flux_cfg = flux_cfg
         self.vae_cfg = vae_cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -339,7 +434,11 @@ class B200Pipe:
         self.handle = ctypes.c_void_p()
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         va = _vae_arch(vae_cfg)
-        if dit_cfg is not None:
+        if flux_cfg is not None:
+            fa = _flux_arch(flux_cfg)
+            check(self.lib.gdf_create_flux(ctypes.byref(fa), ctypes.byref(va), self.dev_index,
+                                           ctypes.byref(self.handle)))
+        elif dit_cfg is not None:
             da = _dit_arch(dit_cfg)
             check(self.lib.gdf_create_dit(ctypes.byref(da), ctypes.byref(va), self.dev_index,
                                           ctypes.byref(self.handle)))
@@ -350,6 +449,12 @@ class B200Pipe:
 
     def load_state_dict(self, sd, chunk=256):
         """sd: name -> tensor ('unet.*', 'vae.*'), any float dtype / device; uploaded as fp32."""
+        if not self.vae_cfg.get("quant_conv", True) and "vae.quant_conv.weight" not in sd:
+            # Flux VAE (use_quant_conv False): the executor folds conv_out . quant_conv, so feed it the identity
+            nm = 2 * self.vae_cfg["latent"]
+            sd = dict(sd)
+            sd["vae.quant_conv.weight"] = torch.eye(nm).reshape(nm, nm, 1, 1)
+            sd["vae.quant_conv.bias"] = torch.zeros(nm)
         names = list(sd.keys())
         with torch.cuda.device(self.dev_index):
             for s in range(0, len(names), chunk):
@@ -384,7 +489,7 @@ class B200Pipe:
 
 
 def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename=None, device="cuda",
-                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None):
+                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None, flux_cfg=None):
     """Mirror of feature/components/models.py:10 for the B200 path.
 
     There is no network and no checkpoint on disk, so unless `state_dict` (diffusers-named fp32 tensors with
@@ -396,6 +501,15 @@ def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename
         raise NotImplementedError("LoRA loading is outside the B200 hot path (SURVEY.md 2.1 OUT OF SCOPE)")
     if version in _NOT_BUILT:
         raise NotImplementedError("version '%s' is not built on the B200 path yet (UNet families only)" % version)
+    if flux_cfg is not None or (version in FLUX_CONFIGS and unet_cfg is None and dit_cfg is None):
+        fcfg = flux_cfg or FLUX_CONFIGS[version]
+        vcfg = vae_cfg or VAE_CONFIGS[version]
+        pipe = B200Pipe(version, None, vcfg, device, flux_cfg=fcfg)
+        if state_dict is None:
+            state_dict = synthetic_state_dict(version, weight_device or "cpu", None, vcfg, None, fcfg)
+        pipe.load_state_dict(state_dict)
+        pipe.finalize()
+        return pipe
     if dit_cfg is not None or (version in DIT_CONFIGS and unet_cfg is None):
         dcfg = dit_cfg or DIT_CONFIGS[version]
         vcfg = vae_cfg or VAE_CONFIGS[version]

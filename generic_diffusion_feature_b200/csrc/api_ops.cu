@@ -139,9 +139,9 @@ int gdf_op_qsample(const void* moments, const void* eps_vae, const void* eps_q, 
                    float sqrt_1m_ab, float input_scale, void* latent_nhwc, void* cap_unet_in, void* latents_nchw,
                    int B, int HW, void* stream) {
   GDF_LAUNCH(launch_qsample(static_cast<const float*>(moments), static_cast<const float*>(eps_vae),
-                            static_cast<const float*>(eps_q), scaling_factor, sqrt_ab, sqrt_1m_ab, input_scale,
+                            static_cast<const float*>(eps_q), scaling_factor, 0.f, sqrt_ab, sqrt_1m_ab, input_scale,
                             static_cast<bf16*>(latent_nhwc), static_cast<__half*>(cap_unet_in),
-                            static_cast<float*>(latents_nchw), B, HW, static_cast<cudaStream_t>(stream)));
+                            static_cast<float*>(latents_nchw), B, HW, 4, static_cast<cudaStream_t>(stream)));
 }
 
 int gdf_op_cast_f32_to_bf16(const void* x, void* y, int64_t n, void* stream) {

@@ -226,6 +226,7 @@ cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int 
   if (D % 8 != 0 || D > 160 || (ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
   if (D <= 48) return launch_ga<48>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
   if (D <= 80) return launch_ga<80>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
+  if (D <= 128) return launch_ga<128>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);   // Flux
   return launch_ga<160>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
 }
 

@@ -79,40 +79,42 @@ cudaError_t launch_im2col_small(const float* src_nchw_f32, const bf16* src_nhwc_
 }
 
 // ---------------------------------------------------------------- posterior sample + q_sample
-// z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps_vae) * scaling_factor      (DiagonalGaussianDistribution.sample)
+// z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps_vae - shift_factor) * scaling_factor   (DiagonalGaussianDistribution
+// .sample; shift_factor != 0 only for the Flux VAE, pipeline_flux_img2img.py _encode_vae_image)
 // x_t = sqrt_ab * z + sqrt_1m_ab * eps_q                                      (scheduler.add_noise)
 // model input = x_t * input_scale                                            (scheduler.scale_model_input)
 __global__ void qsample_kernel(const float* __restrict__ moments, const float* __restrict__ eps_vae,
-                               const float* __restrict__ eps_q, float sf, float sqrt_ab, float sqrt_1m_ab,
+                               const float* __restrict__ eps_q, float sf, float shift, float sqrt_ab, float sqrt_1m_ab,
                                float input_scale, bf16* __restrict__ latent, __half* __restrict__ cap,
-                               float* __restrict__ latents_nchw, int B, int HW) {
+                               float* __restrict__ latents_nchw, int B, int HW, int LC) {
   const long long total = (long long)B * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
     const int p = (int)(i % HW);
-    const float* mo = moments + i * 8;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    const float* mo = moments + i * 2 * LC;
+    for (int c = 0; c < LC; ++c) {
       const float mean = mo[c];
-      const float logvar = fminf(fmaxf(mo[4 + c], -30.f), 20.f);
-      const long long ni = ((long long)b * 4 + c) * HW + p;
-      const float z = (mean + expf(0.5f * logvar) * eps_vae[ni]) * sf;
+      const float logvar = fminf(fmaxf(mo[LC + c], -30.f), 20.f);
+      const long long ni = ((long long)b * LC + c) * HW + p;
+      const float z = (mean + expf(0.5f * logvar) * eps_vae[ni] - shift) * sf;
       const float xt = sqrt_ab * z + sqrt_1m_ab * eps_q[ni];
       const float xin = xt * input_scale;
       if (latents_nchw) latents_nchw[ni] = xt;
-      latent[i * 4 + c] = __float2bfloat16_rn(xin);
-      if (cap) cap[i * 4 + c] = __float2half_rn(xin);
+      latent[i * LC + c] = __float2bfloat16_rn(xin);
+      if (cap) cap[i * LC + c] = __float2half_rn(xin);
     }
   }
 }
 cudaError_t launch_qsample(const float* moments, const float* eps_vae, const float* eps_q, float scaling_factor,
-                           float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc, __half* cap_unet_in,
-                           float* latents_nchw_f32, int B, int HW, cudaStream_t stream) {
+                           float shift_factor, float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc,
+                           __half* cap_unet_in, float* latents_nchw_f32, int B, int HW, int latent_channels,
+                           cudaStream_t stream) {
   const long long total = (long long)B * HW;
   const int blocks = (int)((total + 255) / 256);
-  qsample_kernel<<<blocks, 256, 0, stream>>>(moments, eps_vae, eps_q, scaling_factor, sqrt_ab, sqrt_1m_ab,
-                                             input_scale, latent_nhwc, cap_unet_in, latents_nchw_f32, B, HW);
+  qsample_kernel<<<blocks, 256, 0, stream>>>(moments, eps_vae, eps_q, scaling_factor, shift_factor, sqrt_ab,
+                                             sqrt_1m_ab, input_scale, latent_nhwc, cap_unet_in, latents_nchw_f32, B,
+                                             HW, latent_channels);
   return cudaGetLastError();
 }
 
@@ -217,8 +219,9 @@ cudaError_t launch_small_linear(const float* x, const float* W, const float* b, 
 // ---------------------------------------------------------------- PixArt DiT helpers
 // PatchEmbed im2col (Conv2d k = s = p, [diffusers embeddings.PatchEmbed]; reference use: transformer_2d.py:541-569):
 // latent NHWC bf16 [B, L, L, Cin] -> A[B*(L/p)^2, k_pad] with k = (py*p + px)*Cin + c, zero padded.
+// chan_major = 1: k = c*p*p + py*p + px (FluxImg2ImgPipeline._pack_latents: view(B,C,h/2,2,w/2,2).permute(0,2,4,1,3,5))
 __global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ A, int B, int L, int p, int Cin,
-                                int k_pad) {
+                                int k_pad, int chan_major) {
   const int g = L / p;
   const long long total = (long long)B * g * g * k_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -231,18 +234,19 @@ __global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ A
     const int b = (int)(m / g);
     bf16 v = __float2bfloat16_rn(0.f);
     if (k < p * p * Cin) {
-      const int c = k % Cin, pp = k / Cin;
+      const int c = chan_major ? k / (p * p) : k % Cin, pp = chan_major ? k % (p * p) : k / Cin;
       const int py = pp / p, px = pp % p;
       v = x[(((long long)b * L + gy * p + py) * L + gx * p + px) * Cin + c];
     }
     A[i] = v;
   }
 }
-cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream) {
+cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream,
+                            int chan_major) {
   if (L % p != 0 || p * p * Cin > k_pad) return cudaErrorInvalidValue;
   const long long total = (long long)B * (L / p) * (L / p) * k_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  patchify_kernel<<<blocks, 256, 0, stream>>>(x, A, B, L, p, Cin, k_pad);
+  patchify_kernel<<<blocks, 256, 0, stream>>>(x, A, B, L, p, Cin, k_pad, chan_major);
   return cudaGetLastError();
 }
 // fp32 [N, C] table -> bf16 [B, N, C] (position embedding replicated over the batch: residual operand of the
@@ -298,6 +302,108 @@ __global__ void mask_to_bias_kernel(const float* __restrict__ m, float* __restri
 }
 cudaError_t launch_mask_to_bias(const float* mask, float* bias, int n, cudaStream_t stream) {
   mask_to_bias_kernel<<<(n + 255) / 256, 256, 0, stream>>>(mask, bias, n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- Flux MMDiT helpers
+// RMS qk-norm + rotary embedding, in place on the fused QKV projection (FluxAttnProcessor2_0,
+// attention_processor.py:2298-2301, 2319-2322 norm_q / norm_k / norm_added_q / norm_added_k and :2330-2334
+// apply_rotary_emb; [diffusers normalization.RMSNorm, embeddings.apply_rotary_emb use_real_unbind_dim=-1, un-vendored]):
+//   y = x * rsqrt(mean(x^2) + eps) * w            over the head_dim of one (token, head)
+//   o[2i] = y[2i] cos[2i] - y[2i+1] sin[2i] ;  o[2i+1] = y[2i+1] cos[2i+1] + y[2i] sin[2i+1]
+// qkv: bf16 [rows, ld], q in columns [0, heads*hd), k in [k_off, k_off + heads*hd). Rows < rows_a use (wq_a, wk_a)
+// (the text stream's norm_added_* of a double block), the others (wq_b, wk_b). cos / sin: fp32 [rows, hd].
+// One warp per (row, head, q|k); lanes own (even, odd) pairs, so the rotation needs no shuffles.
+__global__ void qk_rmsnorm_rope_kernel(bf16* __restrict__ qkv, int ld, int rows, int heads, int hd, int k_off,
+                                       const float* __restrict__ wq_a, const float* __restrict__ wk_a,
+                                       const float* __restrict__ wq_b, const float* __restrict__ wk_b, int rows_a,
+                                       const float* __restrict__ cos_t, const float* __restrict__ sin_t, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)rows * heads * 2) return;
+  const int which = (int)(wid & 1);
+  const int head = (int)((wid >> 1) % heads);
+  const int row = (int)((wid >> 1) / heads);
+  bf16* x = qkv + (long long)row * ld + (which ? k_off : 0) + head * hd;
+  const float* w = row < rows_a ? (which ? wk_a : wq_a) : (which ? wk_b : wq_b);
+  const int pairs = hd >> 1;
+  float2 v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = lane + 32 * j;
+    v[j] = make_float2(0.f, 0.f);
+    if (p < pairs) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(x + 2 * p);
+      v[j] = __bfloat1622float2(t);
+      ss = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, ss));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  const float r = rsqrtf(ss / (float)hd + eps);
+  const float* cr = cos_t ? cos_t + (long long)row * hd : nullptr;
+  const float* sr = sin_t ? sin_t + (long long)row * hd : nullptr;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = lane + 32 * j;
+    if (p < pairs) {
+      const float y0 = v[j].x * r * (w ? w[2 * p] : 1.f), y1 = v[j].y * r * (w ? w[2 * p + 1] : 1.f);
+      float o0 = y0, o1 = y1;
+      if (cr) {
+        o0 = y0 * cr[2 * p] - y1 * sr[2 * p];
+        o1 = y1 * cr[2 * p + 1] + y0 * sr[2 * p + 1];
+      }
+      *reinterpret_cast<__nv_bfloat162*>(x + 2 * p) = __floats2bfloat162_rn(o0, o1);
+    }
+  }
+}
+cudaError_t launch_qk_rmsnorm_rope(bf16* qkv, int ld, int rows, int heads, int hd, int k_off, const float* wq_a,
+                                   const float* wk_a, const float* wq_b, const float* wk_b, int rows_a,
+                                   const float* cos_t, const float* sin_t, float eps, cudaStream_t stream) {
+  if (hd % 2 != 0 || hd > 256 || ld % 2 != 0 || k_off % 2 != 0) return cudaErrorInvalidValue;
+  const long long warps = (long long)rows * heads * 2;
+  const int wpb = 8;
+  qk_rmsnorm_rope_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      qkv, ld, rows, heads, hd, k_off, wq_a, wk_a, wq_b, wk_b, rows_a, cos_t, sin_t, eps);
+  return cudaGetLastError();
+}
+
+// bf16 [rows, cols] block with row pitch ld_src -> fp16 with pitch ld_dst (captures of tensors that no GEMM epilogue
+// produces: Flux `norm-out` / `out` = the modulated LayerNorm output, transformer_flux.py:200-211, and the single
+// blocks' `attn-out` = the attention output's image rows, attention_processor.py:2358-2360). cols, pitches % 8 == 0.
+__global__ void copy_rows_bf16_f16_kernel(const bf16* __restrict__ src, int ld_src, __half* __restrict__ dst, int ld_dst,
+                                          long long rows, int cols) {
+  const int cv = cols >> 3;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int c = (int)(i % cv) << 3;
+    const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld_src + c);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    uint4 o;
+    __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h2[q] = __float22half2_rn(__bfloat1622float2(b2[q]));
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = o;
+  }
+}
+cudaError_t launch_copy_rows_bf16_f16(const bf16* src, int ld_src, __half* dst, int ld_dst, long long rows, int cols,
+                                      cudaStream_t stream) {
+  if (cols % 8 != 0 || ld_src % 8 != 0 || ld_dst % 8 != 0) return cudaErrorInvalidValue;
+  copy_rows_bf16_f16_kernel<<<grid_for(rows * (cols >> 3)), 256, 0, stream>>>(src, ld_src, dst, ld_dst, rows, cols);
+  return cudaGetLastError();
+}
+
+// dst = a + b (+ c): the three conditioning embeddings of CombinedTimestepGuidanceTextProjEmbeddings
+__global__ void sum3_f32_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ c, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
+cudaError_t launch_sum3_f32(float* dst, const float* a, const float* b, const float* c, int n, cudaStream_t stream) {
+  sum3_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dst, a, b, c, n);
   return cudaGetLastError();
 }
 

@@ -227,7 +227,12 @@ struct gdf_handle_s {
   gdf_unet_arch ua;
   gdf_vae_arch va;
   gdf_dit_arch da;
+  gdf_flux_arch fa;
   bool is_dit = false;
+  bool is_flux = false;
+  const float* rope_cos = nullptr;   // [ctx_len + N_img, head_dim] fp32, borrowed per call (Flux)
+  const float* rope_sin = nullptr;
+  float* g_dev = nullptr;            // [B] guidance * 1000 (Flux)
   float* key_bias = nullptr;     // [B, ctx_len] additive cross-attention bias (DiT), valid when has_key_bias
   bool has_key_bias = false;
   int device = 0;
@@ -495,6 +500,28 @@ class Builder {
     return out;
   }
   const bf16* lin(const std::string& name) { return rows_bf16(name + "#bf16", {name}, nullptr); }
+  // fp32 vectors concatenated (biases of row-concatenated projections)
+  const float* f32_cat(const std::string& key, const std::vector<std::string>& names) {
+    auto it = h->packed.find(key);
+    if (it != h->packed.end()) return static_cast<const float*>(it->second);
+    int64_t total = 0;
+    for (auto& n : names) {
+      const RawW* r = raw(n);
+      if (!r) return nullptr;
+      total += r->numel;
+    }
+    float* d = static_cast<float*>(dev_alloc((size_t)total * 4));
+    if (d) {
+      int64_t off = 0;
+      for (auto& n : names) {
+        const RawW* r = raw(n);
+        cudaMemcpy(d + off, r->ptr, (size_t)r->numel * 4, cudaMemcpyDeviceToDevice);
+        off += r->numel;
+      }
+    }
+    h->packed[key] = d;
+    return d;
+  }
   const float* f32_gather(const std::string& key, const std::string& name, const std::vector<int>& idx) {
     auto it = h->packed.find(key);
     if (it != h->packed.end()) return static_cast<const float*>(it->second);
@@ -1740,6 +1767,370 @@ static int build_dit(Builder& b) {
   return b.err;
 }
 
+// ----------------------------------------------------------------------------------------- Flux MMDiT
+// FluxTransformer2DModel.forward (transformer_flux.py:414-604) with every gather call site of the reference's Flux
+// branch (feature_extractor.py:98-123): FluxAttnProcessor2_0 q / k / v / attn-out (attention_processor.py:2280-2289,
+// 2355-2361), FluxTransformerBlock norm-out / out (transformer_flux.py:200-211; both store norm_hidden_states - a
+// quirk of the reference that is kept), FeedForward inner (attention.py:1249-1258), FluxSingleTransformerBlock out
+// (:107-108, image rows only).
+// The op list is emitted sample by sample: the token sequence of one image is the concatenation [text | image]
+// (S = ctx_len + N rows of one joint buffer), so every projection is a plain row-range GEMM, the text and image
+// streams of a double block are two launches with their own weights on the two row ranges, and capture slots
+// (image rows only) are addressed by a per-sample offset. Weights (24 GB bf16 at full size) are re-read per sample,
+// which costs < 3 % of a sample's tensor-pipe time.
+static int build_flux(Builder& b) {
+  gdf_handle_s* h = b.h;
+  const gdf_flux_arch& a = h->fa;
+  const int B = h->B, heads = a.num_heads, hd = a.head_dim;
+  const int C = heads * hd, g = h->L / 2, N = g * g, Lt = h->ctx_len, S = Lt + N;
+  const int J = a.joint_attention_dim, P = a.pooled_projection_dim, cin = a.in_channels, lc = cin / 4;
+  const float eps = 1e-6f;
+  const float scale = 1.f / sqrtf((float)hd);
+  const std::string T = "transformer.";
+  b.ops = &h->unet_ops;
+  b.gn_fuse = false;
+  b.gn_cap = 0;
+  h->unet_in_cap = -1;
+  if (C % 64 != 0 || hd % 8 != 0 || hd > 160 || cin % 8 != 0 || cin != 4 * h->va.latent_channels || J % 8 != 0 ||
+      Lt % 8 != 0)
+    return b.set_err(fail(GDF_ERR_UNSUPPORTED, "Flux: hidden %d / head_dim %d / in_channels %d / ctx %d x %d unsupported",
+                          C, hd, cin, Lt, J));
+
+  // ---- conditioning (all B rows at once, fp32): temb = time(sigma * 1000) + guidance(g * 1000) + text(pooled)
+  // [diffusers embeddings.CombinedTimestepGuidanceTextProjEmbeddings, un-vendored; called at transformer_flux.py:463-467]
+  float* tsin = b.fbuf((long long)B * 256);
+  float* gsin = b.fbuf((long long)B * 256);
+  float* e1 = b.fbuf((long long)B * C);
+  float* et = b.fbuf((long long)B * C);
+  float* eg = b.fbuf((long long)B * C);
+  float* ep = b.fbuf((long long)B * C);
+  float* temb = b.fbuf((long long)B * C);
+  float* pool_in = b.fbuf((long long)B * P);
+  if (!b.dry) {
+    float* t_dev = h->t_dev;
+    float* g_dev = h->g_dev;
+    const bool guid = a.guidance_embeds != 0;
+    gdf_handle_s* hh = h;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_timestep_embedding(t_dev, tsin, B, 256, rc.stream));
+      if (guid) OP_CUDA(launch_timestep_embedding(g_dev, gsin, B, 256, rc.stream));
+      OP_CUDA(cudaMemcpyAsync(pool_in, hh->pooled, (size_t)B * P * 4, cudaMemcpyDeviceToDevice, rc.stream));
+      return 0;
+    });
+  }
+  b.small_linear(tsin, T + "time_text_embed.timestep_embedder.linear_1", e1, B, 256, C, false, true);
+  b.small_linear(e1, T + "time_text_embed.timestep_embedder.linear_2", et, B, C, C, false, false);
+  if (a.guidance_embeds) {
+    b.small_linear(gsin, T + "time_text_embed.guidance_embedder.linear_1", e1, B, 256, C, false, true);
+    b.small_linear(e1, T + "time_text_embed.guidance_embedder.linear_2", eg, B, C, C, false, false);
+  }
+  b.small_linear(pool_in, T + "time_text_embed.text_embedder.linear_1", e1, B, P, C, false, true);
+  b.small_linear(e1, T + "time_text_embed.text_embedder.linear_2", ep, B, C, C, false, false);
+  if (!b.dry) {
+    const bool guid = a.guidance_embeds != 0;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_sum3_f32(temb, et, ep, guid ? eg : nullptr, B * C, rc.stream));
+      return 0;
+    });
+  }
+  // modulation vectors of every block: Linear(SiLU(temb)) [diffusers normalization.AdaLayerNormZero (6C: shift_msa,
+  // scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), AdaLayerNormZeroSingle (3C: shift, scale, gate),
+  // AdaLayerNormContinuous (2C: scale, shift), un-vendored]
+  std::vector<float*> mod_img(a.num_layers), mod_txt(a.num_layers), mod_s(a.num_single_layers);
+  for (int i = 0; i < a.num_layers; ++i) {
+    const std::string wp = T + "transformer_blocks." + std::to_string(i);
+    mod_img[i] = b.fbuf((long long)B * 6 * C);
+    mod_txt[i] = b.fbuf((long long)B * 6 * C);
+    b.small_linear(temb, wp + ".norm1.linear", mod_img[i], B, C, 6 * C, true, false);
+    b.small_linear(temb, wp + ".norm1_context.linear", mod_txt[i], B, C, 6 * C, true, false);
+  }
+  for (int i = 0; i < a.num_single_layers; ++i) {
+    mod_s[i] = b.fbuf((long long)B * 3 * C);
+    b.small_linear(temb, T + "single_transformer_blocks." + std::to_string(i) + ".norm.linear", mod_s[i], B, C, 3 * C,
+                   true, false);
+  }
+  float* mod_f = b.fbuf((long long)B * 2 * C);
+  b.small_linear(temb, T + "norm_out.linear", mod_f, B, C, 2 * C, true, false);
+
+  // ---- packed latents: (B, lc, L, L) -> (B, N, 4 lc), column = c * 4 + py * 2 + px (_pack_latents)
+  bf16* col = b.buf((long long)B * N, cin);
+  if (!b.dry) {
+    bf16* lat = h->latent_nhwc;
+    const int L = h->L;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_patchify(lat, col, B, L, 2, lc, cin, rc.stream, 1));
+      return 0;
+    });
+  }
+
+  // capture slots: registered once (execution order of sample 0), addressed per sample
+  std::unordered_map<std::string, int64_t> slot_of;
+  auto slot = [&](const std::string& id, int Cc, int s) -> int64_t {
+    auto it = slot_of.find(id);
+    int64_t base;
+    if (it == slot_of.end()) {
+      base = b.site(id, Cc, g, g);
+      slot_of[id] = base;
+    } else {
+      base = it->second;
+    }
+    return base < 0 ? -1 : base + (int64_t)s * N * Cc * 2;
+  };
+  // fp16 copy of bf16 rows into a capture slot (tensors no GEMM epilogue produces)
+  auto capture_rows = [&](const bf16* src, int ld_src, int64_t off, int Cc) {
+    if (b.dry || b.err || off < 0) return;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_copy_rows_bf16_f16(src, ld_src, reinterpret_cast<__half*>(rc.arena + off), Cc, N, Cc, rc.stream));
+      return 0;
+    });
+  };
+  auto qk_norm_rope = [&](bf16* qkv, const float* wq_a, const float* wk_a, const float* wq_b, const float* wk_b,
+                          int rows_a) {
+    if (b.dry || b.err) return;
+    gdf_handle_s* hh = h;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      OP_CUDA(launch_qk_rmsnorm_rope(qkv, 3 * C, S, heads, hd, C, wq_a, wk_a, wq_b, wk_b, rows_a, hh->rope_cos,
+                                     hh->rope_sin, eps, rc.stream));
+      return 0;
+    });
+  };
+
+  for (int s = 0; s < B; ++s) {
+    // ---- embedders: joint hidden state [S, C] = [context_embedder(ctx) | x_embedder(packed latents)]
+    bf16* hs = b.buf(S, C);
+    {
+      Epilogue e;
+      e.bias = b.f32(T + "context_embedder.bias");
+      e.out = hs;
+      e.ld_out = C;
+      b.linear(h->ctx_bf16 + (long long)s * Lt * J, Lt, J, J, b.lin(T + "context_embedder.weight"), C, e);
+      Epilogue e2;
+      e2.bias = b.f32(T + "x_embedder.bias");
+      e2.out = hs + (long long)Lt * C;
+      e2.ld_out = C;
+      b.linear(col + (long long)s * N * cin, N, cin, cin, b.lin(T + "x_embedder.weight"), C, e2);
+    }
+
+    // ---- double-stream blocks
+    for (int i = 0; i < a.num_layers; ++i) {
+      const std::string wp = T + "transformer_blocks." + std::to_string(i);
+      const std::string fid = "vit-block" + std::to_string(i);
+      const float* mi = mod_img[i] + (long long)s * 6 * C;
+      const float* mt = mod_txt[i] + (long long)s * 6 * C;
+      bf16* hs_t = hs;
+      bf16* hs_i = hs + (long long)Lt * C;
+      bf16* nj = b.buf(S, C);
+      b.layernorm_mod(hs_t, nj, Lt, C, eps, mt + C, mt, Lt);
+      b.layernorm_mod(hs_i, nj + (long long)Lt * C, N, C, eps, mi + C, mi, N);
+      const bf16* wqkv_i = b.rows_bf16(wp + ".attn#qkv", {wp + ".attn.to_q.weight", wp + ".attn.to_k.weight",
+                                                          wp + ".attn.to_v.weight"}, nullptr);
+      const float* bqkv_i = b.f32_cat(wp + ".attn#qkv_bias", {wp + ".attn.to_q.bias", wp + ".attn.to_k.bias",
+                                                              wp + ".attn.to_v.bias"});
+      const bf16* wqkv_t = b.rows_bf16(wp + ".attn#add_qkv", {wp + ".attn.add_q_proj.weight",
+                                                              wp + ".attn.add_k_proj.weight",
+                                                              wp + ".attn.add_v_proj.weight"}, nullptr);
+      const float* bqkv_t = b.f32_cat(wp + ".attn#add_qkv_bias", {wp + ".attn.add_q_proj.bias",
+                                                                  wp + ".attn.add_k_proj.bias",
+                                                                  wp + ".attn.add_v_proj.bias"});
+      bf16* qkv = b.buf(S, 3 * C);
+      {
+        Epilogue e;
+        e.bias = bqkv_t;
+        e.out = qkv;
+        e.ld_out = 3 * C;
+        b.linear(nj, Lt, C, C, wqkv_t, 3 * C, e);
+        Epilogue e2;
+        e2.bias = bqkv_i;
+        e2.out = qkv + (long long)Lt * 3 * C;
+        e2.ld_out = 3 * C;
+        Caps caps;
+        caps.add(slot(fid + "-q", C, s), 0, C);
+        caps.add(slot(fid + "-k", C, s), C, 2 * C);
+        caps.add(slot(fid + "-v", C, s), 2 * C, 3 * C);
+        b.linear(nj + (long long)Lt * C, N, C, C, wqkv_i, 3 * C, e2, caps);
+      }
+      b.rel(nj);
+      qk_norm_rope(qkv, b.f32(wp + ".attn.norm_added_q.weight"), b.f32(wp + ".attn.norm_added_k.weight"),
+                   b.f32(wp + ".attn.norm_q.weight"), b.f32(wp + ".attn.norm_k.weight"), Lt);
+      bf16* ao = b.buf(S, C);
+      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, 1, heads, S, S, scale, hd, false);
+      b.rel(qkv);
+      bf16* hs2 = b.buf(S, C);
+      {
+        Epilogue e;   // image stream: hs + gate_msa * to_out(attn); attn-out captured before the gate
+        e.bias = b.f32(wp + ".attn.to_out.0.bias");
+        e.col_scale = mi + 2 * C;
+        e.rows_per_batch = N;
+        e.residual = hs_i;
+        e.ld_res = C;
+        e.out = hs2 + (long long)Lt * C;
+        e.ld_out = C;
+        Caps caps;
+        caps.pre = slot(fid + "-attn-out", C, s);
+        b.linear(ao + (long long)Lt * C, N, C, C, b.lin(wp + ".attn.to_out.0.weight"), C, e, caps);
+        Epilogue e2;  // text stream
+        e2.bias = b.f32(wp + ".attn.to_add_out.bias");
+        e2.col_scale = mt + 2 * C;
+        e2.rows_per_batch = Lt;
+        e2.residual = hs_t;
+        e2.ld_res = C;
+        e2.out = hs2;
+        e2.ld_out = C;
+        b.linear(ao, Lt, C, C, b.lin(wp + ".attn.to_add_out.weight"), C, e2);
+      }
+      b.rel(ao);
+      b.rel(hs);
+      bf16* n2 = b.buf(S, C);
+      b.layernorm_mod(hs2 + (long long)Lt * C, n2 + (long long)Lt * C, N, C, eps, mi + 4 * C, mi + 3 * C, N);
+      b.layernorm_mod(hs2, n2, Lt, C, eps, mt + 4 * C, mt + 3 * C, Lt);
+      capture_rows(n2 + (long long)Lt * C, C, slot(fid + "-norm-out", C, s), C);
+      const int inner = 4 * C;
+      bf16* ffi = b.buf(S, inner);
+      {
+        Epilogue e;
+        e.act = kActGeluTanh;
+        e.bias = b.f32(wp + ".ff.net.0.proj.bias");
+        e.out = ffi + (long long)Lt * inner;
+        e.ld_out = inner;
+        Caps caps;
+        caps.add(slot(fid + "-ffn-inner", inner, s), 0, inner);
+        b.linear(n2 + (long long)Lt * C, N, C, C, b.lin(wp + ".ff.net.0.proj.weight"), inner, e, caps);
+        Epilogue e2;
+        e2.act = kActGeluTanh;
+        e2.bias = b.f32(wp + ".ff_context.net.0.proj.bias");
+        e2.out = ffi;
+        e2.ld_out = inner;
+        b.linear(n2, Lt, C, C, b.lin(wp + ".ff_context.net.0.proj.weight"), inner, e2);
+      }
+      capture_rows(n2 + (long long)Lt * C, C, slot(fid + "-out", C, s), C);   // transformer_flux.py:210-211
+      b.rel(n2);
+      bf16* hs3 = b.buf(S, C);
+      {
+        Epilogue e;
+        e.bias = b.f32(wp + ".ff.net.2.bias");
+        e.col_scale = mi + 5 * C;
+        e.rows_per_batch = N;
+        e.residual = hs2 + (long long)Lt * C;
+        e.ld_res = C;
+        e.out = hs3 + (long long)Lt * C;
+        e.ld_out = C;
+        b.linear(ffi + (long long)Lt * inner, N, inner, inner, b.lin(wp + ".ff.net.2.weight"), C, e);
+        Epilogue e2;
+        e2.bias = b.f32(wp + ".ff_context.net.2.bias");
+        e2.col_scale = mt + 5 * C;
+        e2.rows_per_batch = Lt;
+        e2.residual = hs2;
+        e2.ld_res = C;
+        e2.out = hs3;
+        e2.ld_out = C;
+        b.linear(ffi, Lt, inner, inner, b.lin(wp + ".ff_context.net.2.weight"), C, e2);
+      }
+      b.rel(ffi);
+      b.rel(hs2);
+      hs = hs3;
+    }
+
+    // ---- single-stream blocks on the joint sequence (transformer_flux.py:539-541 cat([text, image]))
+    for (int i = 0; i < a.num_single_layers; ++i) {
+      const std::string wp = T + "single_transformer_blocks." + std::to_string(i);
+      const std::string fid = "vit-block" + std::to_string(a.num_layers + i);
+      const float* ms = mod_s[i] + (long long)s * 3 * C;
+      bf16* nj = b.buf(S, C);
+      b.layernorm_mod(hs, nj, S, C, eps, ms + C, ms, S);
+      const bf16* wqkv = b.rows_bf16(wp + ".attn#qkv", {wp + ".attn.to_q.weight", wp + ".attn.to_k.weight",
+                                                        wp + ".attn.to_v.weight"}, nullptr);
+      const float* bqkv = b.f32_cat(wp + ".attn#qkv_bias", {wp + ".attn.to_q.bias", wp + ".attn.to_k.bias",
+                                                            wp + ".attn.to_v.bias"});
+      bf16* qkv = b.buf(S, 3 * C);
+      bf16* cat = b.buf(S, 5 * C);   // [attention output | GELU(proj_mlp)] = the operand of proj_out
+      {
+        Epilogue e;
+        e.bias = bqkv;
+        e.out = qkv;
+        e.ld_out = 3 * C;
+        b.linear(nj, Lt, C, C, wqkv, 3 * C, e);
+        Epilogue e2;
+        e2.bias = bqkv;
+        e2.out = qkv + (long long)Lt * 3 * C;
+        e2.ld_out = 3 * C;
+        Caps caps;
+        caps.add(slot(fid + "-q", C, s), 0, C);
+        caps.add(slot(fid + "-k", C, s), C, 2 * C);
+        caps.add(slot(fid + "-v", C, s), 2 * C, 3 * C);
+        b.linear(nj + (long long)Lt * C, N, C, C, wqkv, 3 * C, e2, caps);
+        Epilogue e3;
+        e3.act = kActGeluTanh;
+        e3.bias = b.f32(wp + ".proj_mlp.bias");
+        e3.out = cat + C;
+        e3.ld_out = 5 * C;
+        b.linear(nj, S, C, C, b.lin(wp + ".proj_mlp.weight"), 4 * C, e3);
+      }
+      b.rel(nj);
+      const float* nq = b.f32(wp + ".attn.norm_q.weight");
+      const float* nk = b.f32(wp + ".attn.norm_k.weight");
+      qk_norm_rope(qkv, nq, nk, nq, nk, 0);
+      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, cat, 5 * C, 1, heads, S, S, scale, hd, false);
+      b.rel(qkv);
+      capture_rows(cat + (long long)Lt * 5 * C, 5 * C, slot(fid + "-attn-out", C, s), C);
+      bf16* hs2 = b.buf(S, C);
+      {
+        const bf16* wo = b.lin(wp + ".proj_out.weight");
+        Epilogue e;
+        e.bias = b.f32(wp + ".proj_out.bias");
+        e.col_scale = ms + 2 * C;
+        e.rows_per_batch = Lt;
+        e.residual = hs;
+        e.ld_res = C;
+        e.out = hs2;
+        e.ld_out = C;
+        b.linear(cat, Lt, 5 * C, 5 * C, wo, C, e);
+        Epilogue e2 = e;
+        e2.rows_per_batch = N;
+        e2.residual = hs + (long long)Lt * C;
+        e2.out = hs2 + (long long)Lt * C;
+        Caps caps;
+        caps.add(slot(fid + "-out", C, s), 0, C);
+        b.linear(cat + (long long)Lt * 5 * C, N, 5 * C, 5 * C, wo, C, e2, caps);
+      }
+      b.rel(cat);
+      b.rel(hs);
+      hs = hs2;
+    }
+
+    // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image rows
+    {
+      const float* mf = mod_f + (long long)s * 2 * C;
+      bf16* nf = b.buf(N, C);
+      b.layernorm_mod(hs + (long long)Lt * C, nf, N, C, eps, mf, mf + C, N);
+      b.rel(hs);
+      const int pout = cin;
+      const int npad = (pout + 15) / 16 * 16;
+      std::vector<int> idx(npad);
+      for (int r = 0; r < npad; ++r) idx[r] = r < pout ? r : -1;
+      const bf16* w = b.rows_bf16(T + "proj_out#pad", {T + "proj_out.weight"}, &idx);
+      float* o = b.fbuf((long long)N * npad);
+      Epilogue e;
+      e.bias = b.f32_pad(T + "proj_out.bias", npad);
+      e.n_out = pout;
+      e.out_f32 = o;
+      e.ld_out_f32 = npad;
+      b.linear(nf, N, C, C, w, npad, e);
+      b.rel(nf);
+      if (!b.dry) {
+        b.ops->push_back([=](const RunCtx& rc) -> int {
+          if (rc.noise_pred_out)
+            OP_CUDA(cudaMemcpy2DAsync(rc.noise_pred_out + (long long)s * N * pout, (size_t)pout * 4, o, (size_t)npad * 4,
+                                      (size_t)pout * 4, N, cudaMemcpyDeviceToDevice, rc.stream));
+          return 0;
+        });
+      }
+      b.rel(o);
+    }
+  }
+  b.rel(col);
+  return b.err;
+}
+
 // ----------------------------------------------------------------------------------------- VAE encoder
 static int build_vae(Builder& b) {
   gdf_handle_s* h = b.h;
@@ -1967,12 +2358,13 @@ static int build_vae(Builder& b) {
     b.rel(t);
     if (!b.dry) {
       gdf_handle_s* hh = h;
-      const float sf = a.scaling_factor;
+      const float sf = a.scaling_factor, shf = a.shift_factor;
+      const int lc = a.latent_channels;
       b.ops->push_back([=](const RunCtx& rc) -> int {
         __half* cap = (hh->unet_in_cap >= 0 && rc.arena) ? reinterpret_cast<__half*>(rc.arena + hh->unet_in_cap)
                                                           : nullptr;
-        OP_CUDA(launch_qsample(moments, rc.eps_vae, rc.eps_q, sf, rc.qa, rc.qb, rc.qs, hh->latent_nhwc, cap,
-                               rc.latents_out, B, N, rc.stream));
+        OP_CUDA(launch_qsample(moments, rc.eps_vae, rc.eps_q, sf, shf, rc.qa, rc.qb, rc.qs, hh->latent_nhwc, cap,
+                               rc.latents_out, B, N, lc, rc.stream));
         return 0;
       });
     }
@@ -1990,7 +2382,8 @@ static void free_plan(gdf_handle_s* h) {
   h->arena_bytes = 0;
   h->planned = false;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc); fr(h->key_bias);
+  fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc); fr(h->key_bias); fr(h->g_dev);
+  h->g_dev = nullptr;
   h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr; h->key_bias = nullptr;
   h->has_key_bias = false;
 }
@@ -2061,6 +2454,26 @@ int gdf_create_dit(const gdf_dit_arch* dit, const gdf_vae_arch* vae, int device,
   return GDF_OK;
 }
 
+int gdf_create_flux(const gdf_flux_arch* flux, const gdf_vae_arch* vae, int device, gdf_handle* out) {
+  if (!flux || !vae || !out) return fail(GDF_ERR_INVALID, "gdf_create_flux: null argument");
+  if (flux->num_layers < 0 || flux->num_single_layers < 0 || flux->num_heads < 1 || flux->in_channels < 4 ||
+      vae->num_levels > GDF_MAX_LEVELS)
+    return fail(GDF_ERR_INVALID, "gdf_create_flux: bad architecture");
+  GDF_CUDA(cudaSetDevice(device));
+  gdf_handle_s* h = new gdf_handle_s();
+  memset(&h->ua, 0, sizeof(h->ua));
+  memset(&h->da, 0, sizeof(h->da));
+  h->fa = *flux;
+  h->is_flux = true;
+  h->ua.in_channels = flux->in_channels / 4;             // latent channels (shared latent plumbing, q_sample)
+  h->ua.cross_attention_dim = flux->joint_attention_dim; // width of the fp32 -> bf16 context staging buffer
+  h->va = *vae;
+  h->device = device;
+  h->ctx_len = 512;
+  *out = h;
+  return GDF_OK;
+}
+
 int gdf_destroy(gdf_handle h) {
   if (!h) return GDF_OK;
   cudaSetDevice(h->device);
@@ -2111,7 +2524,7 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   Builder b(h, true);
   std::vector<Site> keep_sites = h->sites;
   int r = build_vae(b);
-  if (!r) r = h->is_dit ? build_dit(b) : build_unet(b);
+  if (!r) r = h->is_flux ? build_flux(b) : h->is_dit ? build_dit(b) : build_unet(b);
   h->sites = keep_sites;
   h->B = B0;
   h->img = img0;
@@ -2153,7 +2566,8 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
   b.gn_ws = static_cast<float*>(h->pool.acquire(gn_workspace_floats(batch, 64) * 4));
   // UNet first: registers the capture sites (incl. unet-in, written by the q_sample kernel of the VAE pass)
   if (h->is_dit) GDF_CUDA(cudaMalloc(&h->key_bias, (size_t)batch * h->ctx_len * 4));
-  int r = h->is_dit ? build_dit(b) : build_unet(b);
+  if (h->is_flux) GDF_CUDA(cudaMalloc(&h->g_dev, (size_t)batch * 4));
+  int r = h->is_flux ? build_flux(b) : h->is_dit ? build_dit(b) : build_unet(b);
   if (!r) r = build_vae(b);
   if (r) {
     free_plan(h);
@@ -2215,6 +2629,7 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
   if (ctx_len != h->ctx_len)
     return fail(GDF_ERR_SHAPE, "gdf_denoise_capture: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
   if (h->is_dit) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: this handle holds a DiT, use gdf_denoise_capture_dit");
+  if (h->is_flux) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: this handle holds Flux, use gdf_denoise_capture_flux");
   if (!ctx_dev || !arena_dev) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: null input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RunCtx rc;
@@ -2252,6 +2667,32 @@ int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, i
   h->has_key_bias = ctx_mask_dev != nullptr;
   if (ctx_mask_dev)
     GDF_CUDA(launch_mask_to_bias(static_cast<const float*>(ctx_mask_dev), h->key_bias, h->B * h->ctx_len, st));
+  GDF_TRY(run_ops(h, h->unet_ops, rc));
+  return GDF_OK;
+}
+
+int gdf_denoise_capture_flux(gdf_handle h, float sigma, float guidance, const void* ctx_dev, int ctx_len,
+                             const void* pooled_dev, const void* rope_cos_dev, const void* rope_sin_dev,
+                             void* arena_dev, void* noise_pred_out_dev, void* stream) {
+  if (!h || !h->planned || !h->is_flux) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_flux: no Flux plan");
+  if (ctx_len != h->ctx_len)
+    return fail(GDF_ERR_SHAPE, "gdf_denoise_capture_flux: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
+  if (!ctx_dev || !pooled_dev || !rope_cos_dev || !rope_sin_dev || !arena_dev)
+    return fail(GDF_ERR_INVALID, "gdf_denoise_capture_flux: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RunCtx rc;
+  rc.stream = st;
+  rc.arena = static_cast<char*>(arena_dev);
+  rc.noise_pred_out = static_cast<float*>(noise_pred_out_dev);
+  h->pooled = static_cast<const float*>(pooled_dev);
+  h->rope_cos = static_cast<const float*>(rope_cos_dev);
+  h->rope_sin = static_cast<const float*>(rope_sin_dev);
+  // transformer_flux.py:455-459: timestep = timestep * 1000, guidance = guidance * 1000
+  fill_f32_kernel<<<(h->B + 255) / 256, 256, 0, st>>>(h->t_dev, sigma * 1000.f, h->B);
+  fill_f32_kernel<<<(h->B + 255) / 256, 256, 0, st>>>(h->g_dev, guidance * 1000.f, h->B);
+  GDF_CUDA(cudaGetLastError());
+  GDF_CUDA(launch_cast_f32_to_bf16(static_cast<const float*>(ctx_dev), h->ctx_bf16,
+                                   (long long)h->B * h->ctx_len * h->fa.joint_attention_dim, st));
   GDF_TRY(run_ops(h, h->unet_ops, rc));
   return GDF_OK;
 }

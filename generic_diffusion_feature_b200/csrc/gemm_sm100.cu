@@ -15,6 +15,24 @@ namespace gdf {
 struct TileCoord {
   int m_tile, n_tile, bz;
 };
+// Work unit t of the persistent loop -> (m unit, n tile, batch). The CTAs (or CTA pairs) resident at one time work
+// on consecutive units. n_fastest: the n-tiles of one m unit run side by side, so the A rows are fetched from DRAM
+// once and shared through L2 while the (small, L2-resident) weight matrix is streamed by every wave; m-fastest: the
+// resident CTAs share one weight tile and sweep A once per n-tile, which re-reads A from DRAM whenever M x K exceeds
+// L2 (measured 224 MB instead of 118 MB per launch for M=8192, N=1280, K=5120, profiles/r01_launches_ncu_s7.csv).
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int t, int num_m_units, int& mu, int& n_tile, int& bz) {
+  if (p.n_fastest) {
+    n_tile = t % p.num_n_tiles;
+    const int r0 = t / p.num_n_tiles;
+    mu = r0 % num_m_units;
+    bz = r0 / num_m_units;
+  } else {
+    mu = t % num_m_units;
+    const int r0 = t / num_m_units;
+    n_tile = r0 % p.num_n_tiles;
+    bz = r0 / p.num_n_tiles;
+  }
+}
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
   TileCoord c;
   c.m_tile = t % p.num_m_tiles;
@@ -375,7 +393,7 @@ struct GnRed {
   }
 };
 template <int kCpgLog2>
-__device__ __forceinline__ void gn_accumulate_t(const float* v, float* dst, bool ok, int lane) {
+__device__ __forceinline__ float gn_reduce_t(const float* v, bool ok, int lane) {
   constexpr int kCpg = 1 << kCpgLog2;
   constexpr int kNg = 32 / kCpg;       // groups inside 32 columns
   constexpr int kNv = 2 * kNg;
@@ -392,17 +410,22 @@ __device__ __forceinline__ void gn_accumulate_t(const float* v, float* dst, bool
     a[2 * k + 1] = ok ? sq : 0.f;
   }
   GnRed<kNv, 16>::run(a, lane);
-  constexpr int kLanesPerValue = 32 / kNv;
-  if (ok && (lane & (kLanesPerValue - 1)) == 0) atomicAdd(dst + lane / kLanesPerValue, a[0]);
+  return a[0];   // lane l holds value (l / (32 / kNv)) of the warp's 32 rows: (sum, sum sq) per group, interleaved
 }
-// v: the 32 final values of this thread's row in columns [col0, col0 + 32) (all inside n_out)
-__device__ __forceinline__ void gn_accumulate(const GemmParams& p, const float* v, int col0, long long row, bool row_ok,
-                                              int lane) {
-  const long long img = row_ok ? row / p.gn_rows_per_img : 0;
-  float* dst = p.gn_sums + (img * p.gn_groups + (col0 >> p.gn_cpg_log2)) * 2;
-  if (p.gn_cpg_log2 == 2) gn_accumulate_t<2>(v, dst, row_ok, lane);
-  else if (p.gn_cpg_log2 == 3) gn_accumulate_t<3>(v, dst, row_ok, lane);
-  else gn_accumulate_t<4>(v, dst, row_ok, lane);
+// v: the 32 final values of this thread's row in columns [col0, col0 + 32) (all inside n_out). Returns this lane's share
+// of the warp-reduced statistics; the caller keeps a running sum over the tiles of one (image, n-tile) and issues the
+// atomics once per run (gn_flush) - one atomic per value and tile made the 65536-tile VAE launches atomic-bound
+// (conv_in 1.26 -> 2.17 ms with statistics in the epilogue).
+__device__ __forceinline__ float gn_reduce(const GemmParams& p, const float* v, bool row_ok, int lane) {
+  if (p.gn_cpg_log2 == 2) return gn_reduce_t<2>(v, row_ok, lane);
+  if (p.gn_cpg_log2 == 3) return gn_reduce_t<3>(v, row_ok, lane);
+  return gn_reduce_t<4>(v, row_ok, lane);
+}
+__device__ __forceinline__ void gn_flush(const GemmParams& p, float val, long long img, int col0, int lane) {
+  const int nv = 2 * (32 >> p.gn_cpg_log2);
+  const int lanes_per_value = 32 / nv;
+  if ((lane & (lanes_per_value - 1)) == 0)
+    atomicAdd(p.gn_sums + (img * p.gn_groups + (col0 >> p.gn_cpg_log2)) * 2 + lane / lanes_per_value, val);
 }
 
 // CG = 1: one CTA per 128 x block_n tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x block_n
@@ -481,10 +504,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     int s = 0;
     uint32_t ph = 0;
     for (int t = unit0; t < total_units; t += unit_step) {
-      const int mu = t % num_m_units;
-      const int r0 = t / num_m_units;
-      const int n_tile = r0 % p.num_n_tiles;
-      const int bz = r0 / p.num_n_tiles;
+      int mu, n_tile, bz;
+      decode_unit(p, t, num_m_units, mu, n_tile, bz);
       const int m_tile = mu * CG + (int)cta_rank;
       int x0 = 0, y0 = 0, b0 = 0;
       if (p.a_mode != kALinear) {
@@ -594,13 +615,28 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     uint64_t* my_res_bar = &res_bar[e];
     uint32_t res_ph = 0;
     bool res_pending = false;
+    // GroupNorm statistics (gn_sums): running per-lane sums of this warp's columns over the tiles of one
+    // (image, n-tile) run, [round c < 128 | c >= 128][32-column half]; flushed with atomics when the run ends
+    float gn_run0[2] = {0.f, 0.f}, gn_run1[2] = {0.f, 0.f};
+    int gn_key = -1;
+    auto gn_flush_run = [&]() {
+      const long long img = gn_key / p.num_n_tiles;
+      const int col_base = (int)(gn_key % p.num_n_tiles) * out_tile_w + cset * 64;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (col_base + hh * 32 + 32 <= ncols_out && cset * 64 + hh * 32 < out_tile_w)
+          gn_flush(p, gn_run0[hh], img, col_base + hh * 32, lane);
+        if (col_base + 128 + hh * 32 + 32 <= ncols_out && cset * 64 + 128 + hh * 32 < out_tile_w)
+          gn_flush(p, gn_run1[hh], img, col_base + 128 + hh * 32, lane);
+        gn_run0[hh] = 0.f;
+        gn_run1[hh] = 0.f;
+      }
+    };
     for (int t = unit0; t < total_units; t += unit_step) {
       TileCoord tc;
       {
-        const int mu = t % num_m_units;
-        const int r0 = t / num_m_units;
-        tc.n_tile = r0 % p.num_n_tiles;
-        tc.bz = r0 / p.num_n_tiles;
+        int mu;
+        decode_unit(p, t, num_m_units, mu, tc.n_tile, tc.bz);
         tc.m_tile = mu * CG + (int)cta_rank;
       }
       // ---- row of this thread, origin of this warp's 32-row slice
@@ -633,6 +669,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         sc.c3 = bt * p.tb + (w0 / p.tw) / p.th;
       }
       const int bidx = (p.rows_per_batch > 0 && row_ok) ? (int)(row / p.rows_per_batch) : 0;
+      if (p.gn_sums) {   // (row validity and the image are uniform over a tile: checked on the host)
+        const int key = row_ok ? (int)(row / p.gn_rows_per_img) * p.num_n_tiles + tc.n_tile : -1;
+        if (key != gn_key) {
+          if (gn_key >= 0) gn_flush_run();
+          gn_key = key;
+        }
+      }
       const long long out_batch_off = (long long)tc.bz * p.out_batch_stride;
       const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + row) : 0.f;
       // folded LayerNorm of the A rows: value = ln_a * acc + ln_b * u[col] + bias[col]
@@ -777,7 +820,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) { rs_sum += v[hh][j]; rs_sq = fmaf(v[hh][j], v[hh][j], rs_sq); }
             }
-            if (p.gn_sums) gn_accumulate(p, v[hh], ocol0 + hh * 32, row, row_ok, lane);
+            if (p.gn_sums) {
+              const float part = gn_reduce(p, v[hh], row_ok, lane);
+              if (c < 128) gn_run0[hh] += part; else gn_run1[hh] += part;
+            }
           }
           if (resrow) {   // the residual registers are free again: fetch the next full round while this one is stored
             const int nc = c + 128, nocol0 = ocol0 + 128;
@@ -887,6 +933,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
+    if (p.gn_sums && gn_key >= 0) gn_flush_run();
     __syncwarp();
     if (elect_one()) bulk_wait<0>();   // all bulk stores of this warp have completed before the CTA retires
   }

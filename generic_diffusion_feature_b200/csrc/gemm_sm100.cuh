@@ -44,6 +44,7 @@ struct GemmParams {
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
+  int n_fastest;        // 1: consecutive work units walk the n-tiles of one m unit first (see decode_unit)
   int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)
   int a_batched;        // 1: A has a batch dimension, 0: shared across the batch
   int b_batched;        // 1: B has a batch dimension, 0: shared

@@ -106,9 +106,11 @@ cudaError_t launch_im2col_small(const float* src_nchw_f32, const bf16* src_nhwc_
                                 int Cin, cudaStream_t stream);
 // Posterior sample + scaling + q_sample + scale_model_input (reference: pipeline_pixart_sigma.py:644-673,
 // diffusion_feature.py:406). moments: NHWC fp32 [B, HW, 8] (mean 0..3, logvar 4..7); eps_*: NCHW fp32 (B,4,h,w).
+// latent_channels = LC (4; 16 for the Flux VAE): moments [B, HW, 2*LC]; shift_factor is subtracted before scaling (Flux).
 cudaError_t launch_qsample(const float* moments, const float* eps_vae, const float* eps_q, float scaling_factor,
-                           float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc, __half* cap_unet_in,
-                           float* latents_nchw_f32, int B, int HW, cudaStream_t stream);
+                           float shift_factor, float sqrt_ab, float sqrt_1m_ab, float input_scale, bf16* latent_nhwc,
+                           __half* cap_unet_in, float* latents_nchw_f32, int B, int HW, int latent_channels,
+                           cudaStream_t stream);
 cudaError_t launch_cast_f32_to_bf16(const float* x, bf16* y, long long n, cudaStream_t stream);
 cudaError_t launch_cast_bf16_to_f16(const bf16* x, __half* y, long long n, cudaStream_t stream);
 // fp32 OIHW conv weight -> bf16 [O_pad][kh*kw*I] (k = (ky*kw+kx)*I + c), rows >= O zero.
@@ -121,7 +123,15 @@ cudaError_t launch_small_linear(const float* x, const float* W, const float* b, 
                                 int act_in_silu, int act_out_silu, cudaStream_t stream);
 
 // PixArt DiT helpers (eltwise.cu)
-cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream);
+cudaError_t launch_patchify(const bf16* x, bf16* A, int B, int L, int p, int Cin, int k_pad, cudaStream_t stream,
+                            int chan_major = 0);
+// Flux MMDiT helpers (eltwise.cu)
+cudaError_t launch_qk_rmsnorm_rope(bf16* qkv, int ld, int rows, int heads, int hd, int k_off, const float* wq_a,
+                                   const float* wk_a, const float* wq_b, const float* wk_b, int rows_a,
+                                   const float* cos_t, const float* sin_t, float eps, cudaStream_t stream);
+cudaError_t launch_copy_rows_bf16_f16(const bf16* src, int ld_src, __half* dst, int ld_dst, long long rows, int cols,
+                                      cudaStream_t stream);
+cudaError_t launch_sum3_f32(float* dst, const float* a, const float* b, const float* c, int n, cudaStream_t stream);
 cudaError_t launch_replicate_rows_bf16(const float* src, bf16* dst, long long n, int B, cudaStream_t stream);
 // out[j][b][c] = table[j][c] + t[b][j*C + c] (t_ld = J*C) or + t[b][c] (t_ld = C)
 cudaError_t launch_adaln_mod(const float* table, const float* t, float* out, int B, int J, int C, int t_ld,

@@ -51,6 +51,9 @@ static int choose_cta_group(int block_n, int num_m_tiles) {
 
 static void finish_tiling(GemmParams& p) {
   p.cta_group = choose_cta_group(p.block_n, p.num_m_tiles);
+  // n-fastest rasterisation whenever the whole weight matrix stays L2-resident (every layer of the path: <= 26 MB)
+  const long long w_bytes = (long long)p.N * p.K * 2;
+  p.n_fastest = (p.num_n_tiles > 1 && w_bytes <= (48ll << 20) && env_int("GDF_RASTER_N", 1) != 0) ? 1 : 0;
 }
 // ring depth once the epilogue mode (residual staging or not) is known
 static void finish_stages(GemmParams& p) {

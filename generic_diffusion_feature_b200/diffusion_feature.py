@@ -14,8 +14,11 @@ Differences a user can observe (all documented in INTEGRATION.md):
     un-seeded (pipeline_pixart_sigma.py:644,671) so that results are reproducible;
   * the PixArt versions take prompts = (embeds, mask, neg_embeds, neg_mask) like the reference
     (diffusion_feature.py:277-283) and, unlike it (B = 1 only, attention.py:498-500), any batch size;
-  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan,
-    IF and Flux raise NotImplementedError.
+  * version 'flux' (diffusion_feature.py:246-253 calls the whole FluxImg2ImgPipeline with strength = t/1000 and
+    guidance_scale 1): prompts = (t5_embeds (1|B, 512, 4096), pooled_clip (1|B, 768)) as returned by encode_prompt
+    here (the reference passes raw strings to the pipeline); noise = (eps_vae, eps_q) with 16 latent channels;
+  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
+    and IF raise NotImplementedError.
 """
 import ctypes
 
@@ -97,6 +100,10 @@ class FeatureExtractor(nn.Module):
                 prompt_str = f.read()
         import zlib
         g = torch.Generator().manual_seed(zlib.crc32(prompt_str.encode()))
+        if getattr(self.pipe, "flux_cfg", None):
+            # Flux: T5 sequence (max_sequence_length 512) + CLIP pooled vector (pipeline_flux_img2img.py encode_prompt)
+            fc = self.pipe.flux_cfg
+            return torch.randn(1, fc["ctx_len"], fc["joint_dim"], generator=g), torch.randn(1, fc["pooled_dim"], generator=g)
         if getattr(self.pipe, "dit_cfg", None):
             # PixArt: (prompt_embeds, prompt_attention_mask, negative_embeds, negative_mask), T5 length 300 for
             # Sigma (diffusion_feature.py:193-205); the stand-in mask keeps every token
@@ -148,8 +155,11 @@ class FeatureExtractor(nn.Module):
         dev = pipe.device
         self.feature_store.reset()
         is_dit = getattr(pipe, "dit_cfg", None) is not None
+        is_flux = getattr(pipe, "flux_cfg", None) is not None
         ctx_mask = None
-        if is_dit:
+        if is_flux:
+            prompt_embeds, pooled = prompts[0], prompts[1]
+        elif is_dit:
             prompt_embeds, ctx_mask, _neg, _neg_mask = prompts      # diffusion_feature.py:277-283
             pooled = None
             if ctx_mask is not None and ctx_mask.shape[0] == 1:
@@ -159,12 +169,13 @@ class FeatureExtractor(nn.Module):
         prompt_embeds = prompt_embeds.repeat(batch_size, 1, 1) if prompt_embeds.shape[0] == 1 else prompt_embeds
         if pooled is not None and pooled.shape[0] == 1:
             pooled = pooled.repeat(batch_size, 1)
-        timestep, qa, qb, qs = schedulers.resolve(self.version, t)
+        timestep, qa, qb, qs = schedulers.resolve("flux" if is_flux else self.version, t, self.img_size)
         # 6. prepare image (diffusion_feature.py:357-364)
         if image_type == 'image':
             image = torch.concat([self.preprocess_image(r) for r in image], dim=0)
         image = image.to(dev, torch.float32, non_blocking=True)
-        is_latents = image.shape[1] == 4      # prepare_latents: 4-channel input is taken as latents (:623-624)
+        lat_ch = pipe.vae_cfg["latent"]
+        is_latents = image.shape[1] == lat_ch  # prepare_latents: latent-channel input is taken as latents (:623-624)
         if not is_latents and image.shape[-2:] != (self.img_size, self.img_size):
             image = F.interpolate(image, (self.img_size, self.img_size), mode='bilinear')
         image = image.contiguous()
@@ -173,8 +184,8 @@ class FeatureExtractor(nn.Module):
         plan = self._ensure_plan(batch_size, int(prompt_embeds.shape[1]))
         L = self.img_size // 8
         if noise is None:
-            eps_vae = torch.randn(batch_size, 4, L, L, device=dev)
-            eps_q = torch.randn(batch_size, 4, L, L, device=dev)
+            eps_vae = torch.randn(batch_size, lat_ch, L, L, device=dev)
+            eps_q = torch.randn(batch_size, lat_ch, L, L, device=dev)
         else:
             eps_vae = noise[0].to(dev, torch.float32).contiguous()
             eps_q = noise[1].to(dev, torch.float32).contiguous()
@@ -194,7 +205,18 @@ class FeatureExtractor(nn.Module):
             else:
                 check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb,
                                            qs, None, st))
-            if is_dit:
+            if is_flux:
+                mask_d = None
+                key = (ctx.shape[1], L // 2)
+                if getattr(self, "_rope_key", None) != key:
+                    from .components.models import flux_rope_tables
+                    cos, sin = flux_rope_tables(pipe.flux_cfg, ctx.shape[1], L // 2)
+                    self._rope = (cos.to(dev).contiguous(), sin.to(dev).contiguous())
+                    self._rope_key = key
+                check(lib.gdf_denoise_capture_flux(pipe.handle, timestep, 1.0, _lib.ptr(ctx), ctx.shape[1],
+                                                   _lib.ptr(pooled_d), _lib.ptr(self._rope[0]), _lib.ptr(self._rope[1]),
+                                                   _lib.ptr(arena), None, st))
+            elif is_dit:
                 mask_d = ctx_mask.to(dev, torch.float32).contiguous() if ctx_mask is not None else None
                 check(lib.gdf_denoise_capture_dit(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(mask_d),
                                                   _lib.ptr(arena), None, st))

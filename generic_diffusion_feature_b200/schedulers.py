@@ -14,6 +14,13 @@ code; their published semantics for the configs models.py selects (SURVEY.md row
   pixart-*  : DPMSolverMultistep (order 1 for get_timesteps), beta_schedule 'linear' 1e-4 -> 0.02, spacing
               'linspace' -> round(linspace(0, 999, 1001))[::-1][:-1]; add_noise alpha_t z + sigma_t eps with
               alpha_t = sqrt(abar_t), sigma_t = sqrt(1 - abar_t); scale_model_input identity
+  flux      : the reference calls the whole img2img pipeline (diffusion_feature.py:246-253) with strength = t/1000,
+              guidance_scale 1 and the pipeline's default 28 steps: sigmas = linspace(1, 1/28, 28)
+              (pipeline_flux_img2img.py:745), FlowMatchEulerDiscrete with dynamic shifting sigma' = e^mu /
+              (e^mu + (1/sigma - 1)), mu = calculate_shift(image_seq_len) (:75-85 with the FLUX.1-dev scheduler
+              config base_shift 0.5, max_shift 1.15, seq 256..4096); get_timesteps (:416-425) keeps
+              timesteps[int(28 - 28*strength):]; prepare_latents (:565) scale_noise = sigma' eps + (1 - sigma') z;
+              the transformer is fed timestep / 1000 = sigma' (:812-815)
 """
 import math
 
@@ -25,8 +32,29 @@ def alphas_cumprod(beta_start=0.00085, beta_end=0.012, n=1000):
     return np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32)
 
 
-def resolve(version, t):
+def resolve_flux(t, img_size, num_inference_steps=28, base_shift=0.5, max_shift=1.15, base_seq=256, max_seq=4096):
+    """-> (sigma, a, b, 1.0) of the first step the reference's Flux img2img call runs (see module docstring)."""
+    strength = t / 1000
+    init = min(num_inference_steps * strength, num_inference_steps)
+    t_start = int(max(num_inference_steps - init, 0))
+    if num_inference_steps - t_start < 1:
+        raise ValueError("After adjusting the num_inference_steps by strength parameter: %s, the number of pipeline"
+                         "steps is %d which is < 1 and not appropriate for this pipeline."
+                         % (strength, num_inference_steps - t_start))     # pipeline_flux_img2img.py:768-772
+    sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
+    seq_len = (img_size // 8 // 2) ** 2
+    m = (max_shift - base_shift) / (max_seq - base_seq)
+    mu = seq_len * m + (base_shift - m * base_seq)
+    s = float(sigmas[t_start])
+    sigma = math.exp(mu) / (math.exp(mu) + (1.0 / s - 1.0))
+    sigma = float(np.float32(sigma))
+    return sigma, 1.0 - sigma, sigma, 1.0
+
+
+def resolve(version, t, img_size=None):
     """-> (timestep, a, b, input_scale): x_t = a*z + b*eps, model input = x_t * input_scale."""
+    if version == "flux":
+        return resolve_flux(t, img_size or 1024)
     init_timestep = min(int(1000 * (t / 1000)), 1000)
     t_start = max(1000 - init_timestep, 0)
     ac = alphas_cumprod()

@@ -74,7 +74,8 @@ typedef struct gdf_vae_arch {
   int layers_per_block;               /* 2 */
   int norm_num_groups;                /* 32 */
   float norm_eps;                     /* 1e-6 */
-  float scaling_factor;               /* 0.18215 / 0.13025 */
+  float scaling_factor;               /* 0.18215 / 0.13025 / 0.3611 (Flux) */
+  float shift_factor;                 /* 0 / 0.1159 (Flux): z = (sample - shift_factor) * scaling_factor */
 } gdf_vae_arch;
 
 /* PixArt-style DiT denoiser (models.py:71-117 'pixart-sigma' / 'pixart-sigma-512' / 'pixart-alpha'; [diffusers
@@ -97,6 +98,26 @@ int gdf_create(const gdf_unet_arch* unet, const gdf_vae_arch* vae, int device, g
  * gdf_encode_noise / gdf_encode_latents are shared, the forward is gdf_denoise_capture_dit. Feature ids:
  * vit-block{i}-{self-q,self-k,self-v,cross-q,ffn-inner,out} (feature_extractor.py:259-286). */
 int gdf_create_dit(const gdf_dit_arch* dit, const gdf_vae_arch* vae, int device, gdf_handle* out);
+
+/* Flux MMDiT denoiser (models.py:150-172 'flux' = FLUX.1-dev; FluxTransformer2DModel defaults at
+ * feature/diffusers/models/transformers/transformer_flux.py:253-266; block arithmetic = the reference's vendored
+ * FluxTransformerBlock :116-226, FluxSingleTransformerBlock :46-112 and FluxAttnProcessor2_0,
+ * attention_processor.py:2259-2362). */
+typedef struct gdf_flux_arch {
+  int in_channels;                    /* 64 = 16 latent channels x (2 x 2) packed pixels */
+  int num_layers;                     /* 19 double-stream (image + text) blocks */
+  int num_single_layers;              /* 38 single-stream blocks */
+  int num_heads;                      /* 24 */
+  int head_dim;                       /* 128 */
+  int joint_attention_dim;            /* 4096 (T5) */
+  int pooled_projection_dim;          /* 768 (CLIP pooled) */
+  int guidance_embeds;                /* 1 for FLUX.1-dev */
+} gdf_flux_arch;
+/* "transformer.*" parameter names; shared calls as for gdf_create_dit, the forward is gdf_denoise_capture_flux.
+ * Feature ids (feature_extractor.py:98-123): vit-block{i}-{q,k,v,attn-out,norm-out,ffn-inner,out} for the double
+ * blocks i < num_layers, vit-block{i}-{q,k,v,attn-out,out} for the single blocks numbered after them; image
+ * tokens only, (B, 3072, h/16, w/16). */
+int gdf_create_flux(const gdf_flux_arch* flux, const gdf_vae_arch* vae, int device, gdf_handle* out);
 int gdf_destroy(gdf_handle h);
 
 /* Weights by diffusers parameter name ("unet.down_blocks.0.resnets.0.conv1.weight", "vae.encoder.conv_in.weight",
@@ -160,6 +181,20 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
  *   noise_pred_out_dev : optional fp32 (B, out_channels, h, w) un-patchified model output */
 int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* ctx_mask_dev,
                             void* arena_dev, void* noise_pred_out_dev, void* stream);
+
+/* One Flux forward with capture (replaces self.transformer(...) at pipeline_flux_img2img.py:812-822; the reference
+ * returns right after it, :841).
+ *   sigma : the flow-match sigma of the resolved step = the pipeline's `timestep / 1000` (also the q_sample mix
+ *           x_t = sigma * eps + (1 - sigma) * z done by gdf_encode_noise with sqrt_alpha_bar = 1 - sigma,
+ *           sqrt_one_minus_alpha_bar = sigma)
+ *   guidance : guidance_scale (1.0 in the reference's call, diffusion_feature.py:246-253); ignored without guidance_embeds
+ *   ctx_dev : fp32 (B, ctx_len, joint_attention_dim) T5 embeddings; pooled_dev : fp32 (B, pooled_projection_dim)
+ *   rope_cos_dev / rope_sin_dev : fp32 (ctx_len + (h/16)*(w/16), head_dim) rotary tables of FluxPosEmbed for
+ *           ids = cat(txt_ids, img_ids) (computed by the host, transformer_flux.py:481-482)
+ *   noise_pred_out_dev : optional fp32 (B, (h/16)*(w/16), in_channels) packed model output */
+int gdf_denoise_capture_flux(gdf_handle h, float sigma, float guidance, const void* ctx_dev, int ctx_len,
+                             const void* pooled_dev, const void* rope_cos_dev, const void* rope_sin_dev,
+                             void* arena_dev, void* noise_pred_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ op level
  * Each hot kernel behind a plain entry point: used by the parity tests, by bench.py's roofline probe and by the

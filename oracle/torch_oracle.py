@@ -611,6 +611,297 @@ def attach_gatherers_dit(model, store):
         blk.ff.feature_gatherer = FeatureGatherer(bid + "-ffn", store)
 
 
+# ------------------------------------------------------------------------------------------ Flux MMDiT
+class RMSNorm(nn.Module):
+    """[diffusers normalization.RMSNorm, un-vendored; built by Attention(qk_norm='rms_norm'),
+    attention_processor.py:205-207, 278-280]: x * rsqrt(mean(x^2) + eps) * weight."""
+
+    def __init__(self, dim, eps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float().pow(2).mean(-1, keepdim=True)
+        return x * torch.rsqrt(v + self.eps) * self.weight
+
+
+def flux_rope(ids, axes_dim, theta=10000.0):
+    """[diffusers embeddings.FluxPosEmbed + get_1d_rotary_pos_embed(use_real=True, repeat_interleave_real=True,
+    freqs_dtype=float64), un-vendored; called at transformer_flux.py:481-482]: (cos, sin), each [S, sum(axes_dim)]."""
+    cos, sin = [], []
+    pos = ids.double()
+    for i, d in enumerate(axes_dim):
+        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64)[: d // 2] / d))
+        ang = torch.outer(pos[:, i], freqs)
+        cos.append(ang.cos().repeat_interleave(2, dim=1).float())
+        sin.append(ang.sin().repeat_interleave(2, dim=1).float())
+    return torch.cat(cos, dim=-1), torch.cat(sin, dim=-1)
+
+
+def apply_rotary_emb(x, rope):
+    """[diffusers embeddings.apply_rotary_emb, use_real=True, use_real_unbind_dim=-1, un-vendored; called at
+    attention_processor.py:2330-2334]: x [B, H, S, D]."""
+    cos, sin = rope
+    cos, sin = cos[None, None], sin[None, None]
+    xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+    return (x.float() * cos + rot.float() * sin).to(x.dtype)
+
+
+class FluxAttention(nn.Module):
+    """Attention ctor (attention_processor.py:105-297) as built by the Flux blocks (bias, qk_norm='rms_norm' eps 1e-6;
+    double blocks: added_kv_proj_dim = dim, context_pre_only False; single blocks: pre_only) + FluxAttnProcessor2_0
+    (:2259-2362) including its gather call sites (:2280-2289 q / k / v, :2355-2360 attn-out)."""
+
+    def __init__(self, dim, heads, joint):
+        super().__init__()
+        self.heads = heads
+        d = dim // heads
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.norm_q, self.norm_k = RMSNorm(d, 1e-6), RMSNorm(d, 1e-6)
+        self.joint = joint
+        if joint:
+            self.add_q_proj, self.add_k_proj, self.add_v_proj = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+            self.norm_added_q, self.norm_added_k = RMSNorm(d, 1e-6), RMSNorm(d, 1e-6)
+            self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Identity()])
+            self.to_add_out = nn.Linear(dim, dim)
+
+    def forward(self, x, ctx=None, rope=None):
+        B = x.shape[0]
+        q, k, v = self.to_q(x), self.to_k(x), self.to_v(x)
+        if ctx is not None:
+            _gather(self, q, "q")
+            _gather(self, k, "k")
+            _gather(self, v, "v")
+        else:
+            tl = self.text_len
+            _gather(self, q[:, tl:, :], "q")
+            _gather(self, k[:, tl:, :], "k")
+            _gather(self, v[:, tl:, :], "v")
+        d = k.shape[-1] // self.heads
+        sp = lambda t: t.view(B, -1, self.heads, d).transpose(1, 2)
+        q, k, v = self.norm_q(sp(q)), self.norm_k(sp(k)), sp(v)
+        if ctx is not None:
+            cq = self.norm_added_q(sp(self.add_q_proj(ctx)))
+            ck = self.norm_added_k(sp(self.add_k_proj(ctx)))
+            cv = sp(self.add_v_proj(ctx))
+            q, k, v = torch.cat([cq, q], dim=2), torch.cat([ck, k], dim=2), torch.cat([cv, v], dim=2)
+        if rope is not None:
+            q, k = apply_rotary_emb(q, rope), apply_rotary_emb(k, rope)
+        o = F.scaled_dot_product_attention(q, k, v)
+        o = o.transpose(1, 2).reshape(B, -1, self.heads * d)
+        if ctx is not None:
+            co, o = o[:, : ctx.shape[1]], o[:, ctx.shape[1]:]
+            o = self.to_out[1](self.to_out[0](o))
+            co = self.to_add_out(co)
+            _gather(self, o, "attn-out")
+            return o, co
+        _gather(self, o[:, self.text_len:, :], "attn-out")
+        return o
+
+
+class _AdaLNLinear(nn.Module):
+    """Shared shape of [diffusers normalization.AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous,
+    un-vendored]: emb = Linear(SiLU(conditioning)) -> n chunks; LayerNorm without affine, eps 1e-6."""
+
+    def __init__(self, dim, n):
+        super().__init__()
+        self.linear = nn.Linear(dim, n * dim)
+        self.n = n
+        self.dim = dim
+
+    def chunks(self, emb):
+        return self.linear(F.silu(emb)).chunk(self.n, dim=1)
+
+    def ln(self, x):
+        return F.layer_norm(x, (self.dim,), eps=1e-6)
+
+
+class FluxTransformerBlock(nn.Module):
+    """transformer_flux.py:116-226 (double-stream block). AdaLayerNormZero: (shift_msa, scale_msa, gate_msa, shift_mlp,
+    scale_mlp, gate_mlp) = chunk(6); x = LN(x) * (1 + scale_msa) + shift_msa."""
+
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.norm1 = _AdaLNLinear(dim, 6)
+        self.norm1_context = _AdaLNLinear(dim, 6)
+        self.attn = FluxAttention(dim, heads, joint=True)
+        self.ff = FeedForwardGelu(dim)
+        self.ff_context = FeedForwardGelu(dim)
+        self.dim = dim
+
+    def forward(self, x, c, temb, rope):
+        sh, sc, g_msa, sh_mlp, sc_mlp, g_mlp = self.norm1.chunks(temb)
+        csh, csc, cg_msa, csh_mlp, csc_mlp, cg_mlp = self.norm1_context.chunks(temb)
+        nx = self.norm1.ln(x) * (1 + sc[:, None]) + sh[:, None]
+        nc = self.norm1_context.ln(c) * (1 + csc[:, None]) + csh[:, None]
+        ao, co = self.attn(nx, nc, rope)
+        x = x + g_msa.unsqueeze(1) * ao                                             # :192-193
+        nx = self.norm1.ln(x) * (1 + sc_mlp[:, None]) + sh_mlp[:, None]             # :195-196 (norm2, no affine)
+        _gather(self, nx, "norm-out")                                               # :200-201
+        x = x + g_mlp.unsqueeze(1) * self.ff(nx)                                    # :203-206
+        _gather(self, nx, "out")                                                    # :210-211 stores norm_hidden_states
+        c = c + cg_msa.unsqueeze(1) * co                                            # :215-216
+        ncc = self.norm1_context.ln(c) * (1 + csc_mlp[:, None]) + csh_mlp[:, None]  # :218-219
+        c = c + cg_mlp.unsqueeze(1) * self.ff_context(ncc)                          # :221-222
+        return c, x
+
+
+class FluxSingleTransformerBlock(nn.Module):
+    """transformer_flux.py:46-112. AdaLayerNormZeroSingle: (shift, scale, gate) = chunk(3)."""
+
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.norm = _AdaLNLinear(dim, 3)
+        self.proj_mlp = nn.Linear(dim, 4 * dim)
+        self.proj_out = nn.Linear(5 * dim, dim)
+        self.attn = FluxAttention(dim, heads, joint=False)
+
+    def forward(self, x, temb, rope):
+        sh, sc, gate = self.norm.chunks(temb)
+        nx = self.norm.ln(x) * (1 + sc[:, None]) + sh[:, None]
+        mlp = F.gelu(self.proj_mlp(nx), approximate="tanh")
+        ao = self.attn(nx, None, rope)
+        x = x + gate.unsqueeze(1) * self.proj_out(torch.cat([ao, mlp], dim=2))
+        _gather(self, x[:, self.attn.text_len:, :], "out")                          # :107-108
+        return x
+
+
+class _TextProj(nn.Module):
+    """[diffusers embeddings.PixArtAlphaTextProjection(act_fn='silu'), un-vendored]."""
+
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+class _FluxTimeTextEmbed(nn.Module):
+    """[diffusers embeddings.CombinedTimestepGuidanceTextProjEmbeddings / CombinedTimestepTextProjEmbeddings,
+    un-vendored; built at transformer_flux.py:284-289]: time + (guidance) + pooled-text embeddings, summed."""
+
+    def __init__(self, dim, pooled_dim, guidance):
+        super().__init__()
+        self.timestep_embedder = TimestepEmbedding(256, dim)
+        if guidance:
+            self.guidance_embedder = TimestepEmbedding(256, dim)
+        self.text_embedder = _TextProj(pooled_dim, dim)
+        self.guidance = guidance
+
+    def forward(self, t, g, pooled):
+        e = self.timestep_embedder(timestep_embedding(t, 256))
+        if self.guidance:
+            e = e + self.guidance_embedder(timestep_embedding(g, 256))
+        return e + self.text_embedder(pooled)
+
+
+class FluxTransformer2DModel(nn.Module):
+    """transformer_flux.py:253-325 (ctor) and :414-604 (forward), parameter names equal diffusers'."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        dim = cfg["heads"] * cfg["head_dim"]
+        self.time_text_embed = _FluxTimeTextEmbed(dim, cfg["pooled_dim"], cfg["guidance_embeds"])
+        self.context_embedder = nn.Linear(cfg["joint_dim"], dim)
+        self.x_embedder = nn.Linear(cfg["in_ch"], dim)
+        self.transformer_blocks = nn.ModuleList([FluxTransformerBlock(dim, cfg["heads"]) for _ in range(cfg["layers"])])
+        self.single_transformer_blocks = nn.ModuleList([FluxSingleTransformerBlock(dim, cfg["heads"])
+                                                        for _ in range(cfg["single_layers"])])
+        self.norm_out = _AdaLNLinear(dim, 2)
+        self.proj_out = nn.Linear(dim, cfg["in_ch"])
+
+    def forward(self, hidden_states, ctx, pooled, timestep, img_ids, txt_ids, guidance=None):
+        B = hidden_states.shape[0]
+        x = self.x_embedder(hidden_states)
+        t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(B) * 1000          # :455
+        g = None if guidance is None else torch.as_tensor(guidance, dtype=torch.float32).reshape(-1).expand(B) * 1000
+        temb = self.time_text_embed(t, g, pooled)
+        c = self.context_embedder(ctx)
+        rope = flux_rope(torch.cat((txt_ids, img_ids), dim=0), self.cfg["axes_dims_rope"])
+        for blk in self.transformer_blocks:
+            c, x = blk(x, c, temb, rope)
+        x = torch.cat([c, x], dim=1)                                                            # :539
+        tl = c.shape[1]
+        for blk in self.single_transformer_blocks:
+            blk.attn.text_len = tl                                                              # :544-545
+            x = blk(x, temb, rope)
+        x = x[:, tl:]
+        scale, shift = self.norm_out.chunks(temb)     # AdaLayerNormContinuous: scale, shift = chunk(emb, 2)
+        x = self.norm_out.ln(x) * (1 + scale[:, None]) + shift[:, None]
+        return self.proj_out(x)
+
+
+def attach_gatherers_flux(model, store):
+    """prepare_feature_extractor, `version == 'flux'` branch (feature_extractor.py:98-123)."""
+    i = -1
+    for i, blk in enumerate(model.transformer_blocks):
+        bid = "vit-block%d" % i
+        blk.feature_gatherer = FeatureGatherer(bid, store)
+        blk.attn.feature_gatherer = FeatureGatherer(bid, store)
+        blk.ff.feature_gatherer = FeatureGatherer(bid + "-ffn", store)
+    for blk in model.single_transformer_blocks:
+        i += 1
+        bid = "vit-block%d" % i
+        blk.feature_gatherer = FeatureGatherer(bid, store)
+        blk.attn.feature_gatherer = FeatureGatherer(bid, store)
+
+
+def flux_latent_image_ids(h, w):
+    """pipeline_flux_img2img.py:483-494."""
+    ids = torch.zeros(h, w, 3)
+    ids[..., 1] = ids[..., 1] + torch.arange(h)[:, None]
+    ids[..., 2] = ids[..., 2] + torch.arange(w)[None, :]
+    return ids.reshape(h * w, 3)
+
+
+def flux_pack_latents(lat):
+    """pipeline_flux_img2img.py:498-503."""
+    B, C, H, W = lat.shape
+    lat = lat.view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return lat.reshape(B, (H // 2) * (W // 2), C * 4)
+
+
+def resolve_flux_sigma(t, img_size, steps=28, base_shift=0.5, max_shift=1.15, base_seq=256, max_seq=4096):
+    """pipeline_flux_img2img.py:745-766 + get_timesteps :416-425 + [FlowMatchEulerDiscreteScheduler.set_timesteps with
+    use_dynamic_shifting, un-vendored]: the sigma of the first step the reference's call runs (strength = t / 1000,
+    28 steps). PARITY UNPINNED (un-vendored scheduler / FLUX.1-dev scheduler_config.json from memory)."""
+    import numpy as np
+    strength = t / 1000
+    t_start = int(max(steps - min(steps * strength, steps), 0))
+    s = float(np.linspace(1.0, 1 / steps, steps)[t_start])
+    seq = (img_size // 8 // 2) ** 2
+    m = (max_shift - base_shift) / (max_seq - base_seq)
+    mu = seq * m + (base_shift - m * base_seq)
+    return float(np.float32(math.exp(mu) / (math.exp(mu) + (1 / s - 1))))
+
+
+@torch.no_grad()
+def extract_flux(model, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50, guidance=1.0):
+    """The reference's Flux path (diffusion_feature.py:246-253 -> FluxImg2ImgPipeline.__call__, pipeline_flux_img2img.py
+    :700-841, returning after the first transformer call): VAE encode, (z - shift) * scale (:411), scale_noise with
+    the resolved sigma (:565), pack (:566), one transformer forward with timestep = sigma (:812-822)."""
+    store.reset()
+    B, _, H, W = image.shape
+    sigma = resolve_flux_sigma(t, H)
+    m = vae.moments(image.float())
+    mean, logvar = m.chunk(2, dim=1)
+    logvar = logvar.clamp(-30.0, 20.0)
+    z = (mean + torch.exp(0.5 * logvar) * eps_vae - vae.shift_factor) * vae.scaling_factor
+    latents = sigma * eps_q + (1.0 - sigma) * z                     # FlowMatchEulerDiscreteScheduler.scale_noise
+    h, w = H // 16, W // 16
+    packed = flux_pack_latents(latents)
+    ctx_b = ctx.expand(B, -1, -1) if ctx.shape[0] == 1 else ctx
+    pooled_b = pooled.expand(B, -1) if pooled.shape[0] == 1 else pooled
+    g = guidance if model.cfg["guidance_embeds"] else None
+    out = model(packed, ctx_b, pooled_b, sigma, flux_latent_image_ids(h, w), torch.zeros(ctx.shape[1], 3), g)
+    return store.stored_feats, latents, out
+
+
 # ------------------------------------------------------------------------------------------ VAE encoder
 class VaeAttention(nn.Module):
     """[diffusers Attention(512, heads=1, dim_head=512, norm_num_groups=32, residual_connection=True, bias=True)]
@@ -682,14 +973,19 @@ class VaeEncoder(nn.Module):
 
 
 class Vae(nn.Module):
-    def __init__(self, scaling_factor, **kw):
+    def __init__(self, scaling_factor, shift_factor=0.0, quant_conv=True, **kw):
         super().__init__()
         self.encoder = VaeEncoder(**kw)
-        self.quant_conv = nn.Conv2d(8, 8, 1)
+        lat = kw.get("latent", 4)
+        if quant_conv:                      # Flux's AutoencoderKL has use_quant_conv False
+            self.quant_conv = nn.Conv2d(2 * lat, 2 * lat, 1)
+        self.has_quant = quant_conv
         self.scaling_factor = scaling_factor
+        self.shift_factor = shift_factor
 
     def moments(self, x):
-        return self.quant_conv(self.encoder(x))
+        m = self.encoder(x)
+        return self.quant_conv(m) if self.has_quant else m
 
 
 # ------------------------------------------------------------------------------------------ scheduler math

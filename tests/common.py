@@ -24,6 +24,13 @@ TINY_15 = dict(block_out=(64, 128, 256, 256), down_attn=(1, 1, 1, 0), up_attn=(0
 TINY_DIT = dict(layers=2, heads=8, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=256, sample_size=16,
                 interpolation_scale=2.0, eps=1e-6)
 TINY_VAE = dict(block_out=(64, 64, 128, 128), layers=2, latent=4, eps=1e-6, scaling_factor=0.13025)
+# Flux topology at reduced size with the real head_dim and rotary axes: 2 double + 2 single MMDiT blocks, hidden 256
+# (2 heads x 128), 16 latent channels packed 2x2 -> 64 input channels, 16 text tokens of width 64, pooled width 32;
+# 128x128 images -> 8x8 = 64 image tokens
+TINY_FLUX = dict(layers=2, single_layers=2, heads=2, head_dim=128, in_ch=64, joint_dim=64, pooled_dim=32,
+                 guidance_embeds=True, axes_dims_rope=(16, 56, 56), ctx_len=16)
+TINY_VAE_FLUX = dict(block_out=(64, 64, 128, 128), layers=2, latent=16, eps=1e-6, scaling_factor=0.3611,
+                     shift_factor=0.1159, quant_conv=False)
 
 
 def make_inputs(batch, img, ctx_dim, pooled_dim=None, ctx_len=77):
@@ -61,6 +68,31 @@ def build_oracle_dit(dit_cfg, vae_cfg, sd):
     model.load_state_dict(tsd, strict=True)
     vae.load_state_dict(vsd, strict=True)
     return model.eval(), vae.eval()
+
+
+def build_oracle_flux(flux_cfg, vae_cfg, sd):
+    """Oracle Flux transformer + VAE from a 'transformer.*' / 'vae.*' state dict (fp32, CPU)."""
+    model = O.FluxTransformer2DModel(flux_cfg)
+    vae = O.Vae(vae_cfg["scaling_factor"], vae_cfg.get("shift_factor", 0.0), vae_cfg.get("quant_conv", True),
+                block_out=vae_cfg["block_out"], layers=vae_cfg["layers"], latent=vae_cfg["latent"], eps=vae_cfg["eps"])
+    tsd = {k[len("transformer."):]: v.float().cpu() for k, v in sd.items() if k.startswith("transformer.")}
+    vsd = {k[len("vae."):]: v.float().cpu() for k, v in sd.items() if k.startswith("vae.")}
+    model.load_state_dict(tsd, strict=True)
+    vae.load_state_dict(vsd, strict=True)
+    return model.eval(), vae.eval()
+
+
+def make_flux_inputs(batch, img, flux_cfg, latent=16):
+    """Images as make_inputs; T5-like context (1, ctx_len, joint_dim) seed 1235, pooled (1, pooled_dim) seed 1236,
+    eps_vae / eps_q with `latent` channels (seeds 1237 / 1238)."""
+    g = lambda s: torch.Generator().manual_seed(s)
+    image = torch.rand(batch, 3, img, img, generator=g(1234)) * 2 - 1
+    ctx = torch.randn(1, flux_cfg["ctx_len"], flux_cfg["joint_dim"], generator=g(1235))
+    pooled = torch.randn(1, flux_cfg["pooled_dim"], generator=g(1236))
+    L = img // 8
+    eps_vae = torch.randn(batch, latent, L, L, generator=g(1237))
+    eps_q = torch.randn(batch, latent, L, L, generator=g(1238))
+    return image, ctx, pooled, eps_vae, eps_q
 
 
 def make_dit_inputs(batch, img, caption_dim, ctx_len=24, masked_tail=5):

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from common import O, ROOT, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, make_inputs
+from common import (O, ROOT, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle, build_oracle_dit,
+                    build_oracle_flux, make_inputs)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -63,6 +64,59 @@ def test_oracle_matches_reference_vendored_dit_blocks():
         ref = gold["feats"][k].float()
         tol = 2e-3 * max(1.0, ref.abs().max().item())
         assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+
+
+def test_oracle_matches_reference_vendored_flux():
+    """tests/golden/flux_tiny.pt: the reference's vendored FluxTransformer2DModel (transformer_flux.py ctor + forward,
+    double / single blocks, FluxAttnProcessor2_0) + its real prepare_feature_extractor Flux branch
+    (tools/make_golden.py); the oracle reproduces every map and the id order."""
+    from generic_diffusion_feature_b200.components.feature_extractor import _flux_feature_ids
+    gold = torch.load(os.path.join(GOLD, "flux_tiny.pt"), weights_only=False)
+    assert gold["ids"] == _flux_feature_ids(TINY_FLUX)
+    sd = _models().synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, TINY_FLUX)
+    model, _ = build_oracle_flux(TINY_FLUX, TINY_VAE_FLUX, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers_flux(model, store)
+    L = gold["latents"].shape[-1]
+    with torch.no_grad():
+        out = model(O.flux_pack_latents(gold["latents"]), gold["ctx"], gold["pooled"], gold["sigma"],
+                    O.flux_latent_image_ids(L // 2, L // 2), torch.zeros(gold["ctx"].shape[1], 3), gold["guidance"])
+    assert list(store.feats.keys()) == gold["ids"]
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+    # quirk kept from the reference (transformer_flux.py:200-211): `out` of a double block stores norm_hidden_states
+    assert torch.equal(store.feats["vit-block0-out"], store.feats["vit-block0-norm-out"])
+
+
+def test_flux_host_logic_matches_oracle():
+    """Parameter naming, rotary tables, the resolved flow-match sigma and the id grammar of the host side agree with
+    the oracle's restatement (FluxTransformer2DModel state_dict, FluxPosEmbed, pipeline_flux_img2img.py:745-766)."""
+    m = _models()
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components.feature_extractor import _flux_feature_ids
+    for cfg in (TINY_FLUX, dict(m.FLUX_CONFIGS["flux"], layers=1, single_layers=1)):
+        want = {k: tuple(v.shape) for k, v in O.FluxTransformer2DModel(cfg).state_dict().items()} \
+            if cfg is TINY_FLUX else None
+        if want is not None:
+            assert dict(m.flux_param_specs(cfg)) == want
+    full = m.FLUX_CONFIGS["flux"]
+    n = sum(int(np.prod(s)) for _, s in m.flux_param_specs(full))
+    assert 11.8e9 < n < 12.0e9                       # FLUX.1-dev: 11.9 B transformer parameters
+    ids = _flux_feature_ids(full)
+    assert len(ids) == 19 * 7 + 38 * 5 and ids[0] == "vit-block0-q" and ids[-1] == "vit-block56-out"
+    cos, sin = m.flux_rope_tables(TINY_FLUX, TINY_FLUX["ctx_len"], 8)
+    ids3 = torch.cat([torch.zeros(TINY_FLUX["ctx_len"], 3), O.flux_latent_image_ids(8, 8)], dim=0)
+    ocos, osin = O.flux_rope(ids3, TINY_FLUX["axes_dims_rope"])
+    assert torch.equal(cos, ocos) and torch.equal(sin, osin)
+    for img in (128, 512, 1024):
+        assert schedulers.resolve("flux", 50, img)[0] == O.resolve_flux_sigma(50, img)
+    sig, a, b, s = schedulers.resolve("flux", 50, 1024)
+    assert abs(sig - 0.19545) < 1e-4 and abs(a + b - 1.0) < 1e-7 and s == 1.0
+    with pytest.raises(ValueError):
+        schedulers.resolve("flux", 0, 1024)          # strength 0 leaves no step (pipeline_flux_img2img.py:768-772)
 
 
 def test_dit_param_specs_and_pos_embed_match_oracle():
@@ -254,16 +308,16 @@ def test_struct_layouts_match_header():
     import subprocess
     import tempfile
     from generic_diffusion_feature_b200 import _lib
-    src = ('#include <stdio.h>\n#include "gdf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gdf_epilogue),'
+    src = ('#include <stdio.h>\n#include "gdf.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gdf_epilogue),'
            'sizeof(gdf_capture_seg), sizeof(gdf_unet_arch), sizeof(gdf_vae_arch), sizeof(gdf_slot),'
-           'sizeof(gdf_resize_src), sizeof(gdf_dit_arch));return 0;}')
+           'sizeof(gdf_resize_src), sizeof(gdf_dit_arch), sizeof(gdf_flux_arch));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o",
                                os.path.join(d, "p")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
     got = [ctypes.sizeof(c) for c in (_lib.Epilogue, _lib.CaptureSeg, _lib.UNetArch, _lib.VaeArch, _lib.Slot,
-                                      _lib.ResizeSrc, _lib.DitArch)]
+                                      _lib.ResizeSrc, _lib.DitArch, _lib.FluxArch)]
     assert got == sizes
 
 

@@ -6,8 +6,8 @@ max-relative error (max |diff| / max |ref|) is reported and bounded at 5e-2 for 
 import pytest
 import torch
 
-from common import (O, TINY_15, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, compare_maps,
-                    make_dit_inputs, make_inputs)
+from common import (O, TINY_15, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,
+                    build_oracle_dit, build_oracle_flux, compare_maps, make_dit_inputs, make_flux_inputs, make_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -125,6 +125,75 @@ def test_cuda_matches_reference_vendored_dit_golden(cuda_dev):
     zero = torch.zeros_like(gold["x"])
     got = fe.extract((gold["ctx"], gold["mask"], gold["ctx"], gold["mask"]), 1, lat.cuda(), image_type="tensors", t=50,
                      noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"]
+    rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+
+
+def _run_flux_case(batch, img, fcfg=TINY_FLUX, vcfg=TINY_VAE_FLUX, subset=None):
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _flux_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict("flux", "cpu", None, vcfg, None, fcfg)
+    image, ctx, pooled, eps_vae, eps_q = make_flux_inputs(batch, img, fcfg, vcfg["latent"])
+    ids = _flux_feature_ids(fcfg)
+    if subset:
+        ids = [i for i in ids if subset(i)]
+    layer = {i: True for i in ids}
+    model, vae = build_oracle_flux(fcfg, vcfg, sd)
+    store = O.FeatureStore(layer)
+    O.attach_gatherers_flux(model, store)
+    want, _, _ = O.extract_flux(model, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50)
+    pipe = models.get_diffusion_model("flux", "float16", device="cuda:0", state_dict=sd, flux_cfg=fcfg, vae_cfg=vcfg)
+    fe = FeatureExtractor(layer, "flux", "cuda:0", img_size=img, external_model=pipe)
+    got = fe.extract((ctx, pooled), batch, image.cuda(), image_type="tensors", t=50, noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == list(want.keys()) == ids
+    for v in got.values():
+        assert v.dtype == torch.float16 and v.is_cuda
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "Flux maps out of tolerance (id, cos, rel, maxrel): %s" % bad[:8]
+    return rows
+
+
+def test_tiny_flux_full_set(cuda_dev):
+    """Flux MMDiT (double + single stream blocks, RMS qk-norm, rotary embedding, joint text+image
+    attention, flow-match scale_noise, 16-channel VAE with shift factor) at reduced size with the real head_dim 128,
+    batch 2: q / k / v / attn-out / norm-out / ffn-inner / out of every block vs the oracle."""
+    rows = _run_flux_case(batch=2, img=128)
+    assert len(rows) == 7 * TINY_FLUX["layers"] + 5 * TINY_FLUX["single_layers"]
+
+
+def test_tiny_flux_subset_img256_batch1(cuda_dev):
+    """Sparse selection (only single-block outputs and one attn-out), 256x256 images -> 256 image tokens."""
+    rows = _run_flux_case(batch=1, img=256, subset=lambda i: i.endswith("-out") and ("block3" in i or "block0-attn" in i))
+    assert len(rows) == 3
+
+
+def test_cuda_matches_reference_vendored_flux_golden(cuda_dev):
+    """CUDA Flux path vs the fixture produced by the REFERENCE's vendored FluxTransformer2DModel and its own
+    FeatureStore (tools/make_golden.py); latents through the latent-channel branch of prepare_latents, zero noise."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "flux_tiny.pt"), weights_only=False)
+    sd = models.synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, TINY_FLUX)
+    pipe = models.get_diffusion_model("flux", "float16", device="cuda:0", state_dict=sd, flux_cfg=TINY_FLUX,
+                                      vae_cfg=TINY_VAE_FLUX)
+    img = 8 * gold["latents"].shape[-1]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, "flux", "cuda:0", img_size=img, external_model=pipe)
+    sigma, a, b, s = schedulers.resolve("flux", 50, img)
+    assert sigma == gold["sigma"]
+    lat = gold["latents"] / (a * s)
+    zero = torch.zeros_like(gold["latents"])
+    got = fe.extract((gold["ctx"], gold["pooled"]), 1, lat.cuda(), image_type="tensors", t=50, noise=(zero, zero))
     torch.cuda.synchronize()
     assert list(got.keys()) == gold["ids"]
     rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})

@@ -9,6 +9,11 @@ Fixtures (small, committed; regenerate with this script):
       (feature/components/feature_extractor.py, train_unet=True so nothing is cast) on the reduced-width
       topologies of tests/common.py, synthetic weights by name, seeded inputs. Stored: every feature map (fp16),
       the noise prediction, and the inputs. The oracle and the CUDA path are both checked against these.
+  flux_tiny.pt
+      Output of the reference's vendored FluxTransformer2DModel (feature/diffusers/models/transformers/
+      transformer_flux.py: ctor, forward, both block classes) + vendored Attention / FluxAttnProcessor2_0 / FeedForward
+      + the reference's real prepare_feature_extractor (Flux branch) / FeatureStore on the reduced topology
+      TINY_FLUX; the un-vendored normalisation / embedding helpers come from tools/ref_shim.py.
   correspondence.pt
       Output of the reference's correspondence_utils.find_nn_source_correspondences / points_to_idxs
       (correspondence/correspondence/correspondence_utils.py:113-146) on seeded feature stacks and query points.
@@ -28,10 +33,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import ref_shim  # noqa: E402
-from common import (O, TINY_21, TINY_DIT, TINY_VAE, TINY_XL, build_oracle, build_oracle_dit, make_dit_inputs,  # noqa: E402
-                    make_inputs)
+from common import (O, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,  # noqa: E402
+                    build_oracle_dit, build_oracle_flux, make_dit_inputs, make_flux_inputs, make_inputs)
 from generic_diffusion_feature_b200.components import models  # noqa: E402
-from generic_diffusion_feature_b200.components.feature_extractor import _dit_feature_ids, _unet_feature_ids  # noqa: E402
+from generic_diffusion_feature_b200.components.feature_extractor import (_dit_feature_ids, _flux_feature_ids,  # noqa: E402
+                                                                        _unet_feature_ids)
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -156,6 +162,49 @@ def golden_dit(name="dit_tiny_pixart.pt"):
                os.path.join(OUT, name))
 
 
+def golden_flux(name="flux_tiny.pt"):
+    cfg = TINY_FLUX
+    sd = models.synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, cfg)
+    ref = ref_shim.build_reference_flux(cfg)
+    ref.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
+    ref.eval()
+    rfe = ref_shim.load_reference_feature_extractor()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.transformer = ref
+    ids = _flux_feature_ids(cfg)
+    store = rfe.prepare_feature_extractor("flux", pipe, {i: True for i in ids}, 1, True)
+    img = 128
+    L = img // 8
+    g = torch.Generator().manual_seed(4321)
+    lat = torch.randn(1, cfg["in_ch"] // 4, L, L, generator=g)     # x_t (already noised latents)
+    x = O.flux_pack_latents(lat)
+    _, ctx, pooled, _, _ = make_flux_inputs(1, img, cfg)
+    sigma = O.resolve_flux_sigma(50, img)
+    img_ids, txt_ids = O.flux_latent_image_ids(L // 2, L // 2), torch.zeros(cfg["ctx_len"], 3)
+    with torch.no_grad():
+        out = ref(hidden_states=x, encoder_hidden_states=ctx, pooled_projections=pooled,
+                  timestep=torch.tensor([sigma]), img_ids=img_ids, txt_ids=txt_ids, guidance=torch.tensor([1.0]),
+                  return_dict=False)[0]
+    feats = store.stored_feats
+    assert list(feats.keys()) == ids, list(feats.keys())[:8]
+    omodel, _ = build_oracle_flux(cfg, TINY_VAE_FLUX, sd)
+    ostore = O.FeatureStore({i: True for i in ids})
+    O.attach_gatherers_flux(omodel, ostore)
+    with torch.no_grad():
+        oout = omodel(x, ctx, pooled, sigma, img_ids, txt_ids, 1.0)
+    worst = max((feats[k] - ostore.feats[k]).abs().max().item() for k in ids)
+    print("%s: %d maps from the reference's vendored Flux transformer; oracle max |diff| %.2e (out %.2e)"
+          % (name, len(ids), worst, (out - oout).abs().max().item()))
+    assert worst < 1e-3
+    torch.save({"ids": ids, "latents": lat, "ctx": ctx, "pooled": pooled, "sigma": sigma, "guidance": 1.0,
+                "noise_pred": out, "feats": {k: v.to(torch.float16) for k, v in feats.items()},
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference vendored transformer_flux.py)"},
+               os.path.join(OUT, name))
+
+
 def golden_correspondence():
     cu = ref_shim.load_reference_correspondence_utils()
     g = torch.Generator().manual_seed(99)
@@ -216,5 +265,6 @@ if __name__ == "__main__":
     golden_unet("xl", TINY_XL, "unet_tiny_xl.pt")
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
     golden_dit()
+    golden_flux()
     golden_correspondence()
     golden_extract()

@@ -364,6 +364,158 @@ def install():
     return root
 
 
+def install_flux():
+    """Adds what the reference's vendored transformers/transformer_flux.py imports and loads it FROM ITS SOURCE FILE.
+    Vendored (pinned): FluxTransformer2DModel (ctor + forward), FluxTransformerBlock, FluxSingleTransformerBlock,
+    Attention ctor + FluxAttnProcessor2_0, FeedForward. Un-vendored, restated here from the published diffusers 0.32.2
+    semantics (NOT pinned): normalization.{RMSNorm, AdaLayerNormZero, AdaLayerNormZeroSingle, AdaLayerNormContinuous},
+    embeddings.{FluxPosEmbed, apply_rotary_emb, CombinedTimestep(Guidance)TextProjEmbeddings,
+    PixArtAlphaTextProjection}."""
+    root = install()
+    if PKG + ".models.transformers.transformer_flux" in sys.modules:
+        return root
+    nm = sys.modules[PKG + ".models.normalization"]
+    emb = sys.modules[PKG + ".models.embeddings"]
+    ld = sys.modules[PKG + ".loaders"]
+    ld.FluxTransformer2DLoadersMixin = type("FluxTransformer2DLoadersMixin", (), {})
+    ld.FromOriginalModelMixin = sys.modules[PKG + ".loaders.single_file_model"].FromOriginalModelMixin
+
+    class RMSNorm(nn.Module):
+        def __init__(self, dim, eps, elementwise_affine=True, bias=False):
+            super().__init__()
+            self.eps = eps
+            self.weight = nn.Parameter(torch.ones(dim)) if elementwise_affine else None
+
+        def forward(self, hidden_states):
+            input_dtype = hidden_states.dtype
+            variance = hidden_states.to(torch.float32).pow(2).mean(-1, keepdim=True)
+            hidden_states = hidden_states * torch.rsqrt(variance + self.eps)
+            if self.weight is not None:
+                hidden_states = hidden_states * self.weight
+            return hidden_states.to(input_dtype)
+
+    class AdaLayerNormZero(nn.Module):
+        def __init__(self, embedding_dim, num_embeddings=None, norm_type="layer_norm", bias=True):
+            super().__init__()
+            self.emb = None
+            self.silu = nn.SiLU()
+            self.linear = nn.Linear(embedding_dim, 6 * embedding_dim, bias=bias)
+            self.norm = nn.LayerNorm(embedding_dim, elementwise_affine=False, eps=1e-6)
+
+        def forward(self, x, timestep=None, class_labels=None, hidden_dtype=None, emb=None):
+            emb = self.linear(self.silu(emb))
+            shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
+            x = self.norm(x) * (1 + scale_msa[:, None]) + shift_msa[:, None]
+            return x, gate_msa, shift_mlp, scale_mlp, gate_mlp
+
+    class AdaLayerNormZeroSingle(nn.Module):
+        def __init__(self, embedding_dim, norm_type="layer_norm", bias=True):
+            super().__init__()
+            self.silu = nn.SiLU()
+            self.linear = nn.Linear(embedding_dim, 3 * embedding_dim, bias=bias)
+            self.norm = nn.LayerNorm(embedding_dim, elementwise_affine=False, eps=1e-6)
+
+        def forward(self, x, emb=None):
+            emb = self.linear(self.silu(emb))
+            shift_msa, scale_msa, gate_msa = emb.chunk(3, dim=1)
+            x = self.norm(x) * (1 + scale_msa[:, None]) + shift_msa[:, None]
+            return x, gate_msa
+
+    class AdaLayerNormContinuous(nn.Module):
+        def __init__(self, embedding_dim, conditioning_embedding_dim, elementwise_affine=True, eps=1e-5, bias=True,
+                     norm_type="layer_norm"):
+            super().__init__()
+            self.silu = nn.SiLU()
+            self.linear = nn.Linear(conditioning_embedding_dim, embedding_dim * 2, bias=bias)
+            self.norm = nn.LayerNorm(embedding_dim, eps, elementwise_affine, bias)
+
+        def forward(self, x, conditioning_embedding):
+            emb = self.linear(self.silu(conditioning_embedding).to(x.dtype))
+            scale, shift = torch.chunk(emb, 2, dim=1)
+            return self.norm(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+
+    nm.RMSNorm, nm.AdaLayerNormZero, nm.AdaLayerNormZeroSingle = RMSNorm, AdaLayerNormZero, AdaLayerNormZeroSingle
+    nm.AdaLayerNormContinuous = AdaLayerNormContinuous
+
+    def get_1d_rotary_pos_embed(dim, pos, theta=10000.0):
+        freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.float64)[: (dim // 2)] / dim))
+        freqs = torch.outer(pos, freqs)
+        return freqs.cos().repeat_interleave(2, dim=1).float(), freqs.sin().repeat_interleave(2, dim=1).float()
+
+    class FluxPosEmbed(nn.Module):
+        def __init__(self, theta, axes_dim):
+            super().__init__()
+            self.theta, self.axes_dim = theta, axes_dim
+
+        def forward(self, ids):
+            cos_out, sin_out = [], []
+            pos = ids.float().double()
+            for i in range(ids.shape[-1]):
+                c, s_ = get_1d_rotary_pos_embed(self.axes_dim[i], pos[:, i], self.theta)
+                cos_out.append(c)
+                sin_out.append(s_)
+            return torch.cat(cos_out, dim=-1), torch.cat(sin_out, dim=-1)
+
+    def apply_rotary_emb(x, freqs_cis, use_real=True, use_real_unbind_dim=-1):
+        cos, sin = freqs_cis
+        cos, sin = cos[None, None], sin[None, None]
+        x_real, x_imag = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+        x_rotated = torch.stack([-x_imag, x_real], dim=-1).flatten(3)
+        return (x.float() * cos + x_rotated.float() * sin).to(x.dtype)
+
+    class PixArtAlphaTextProjection(nn.Module):
+        def __init__(self, in_features, hidden_size, out_features=None, act_fn="gelu_tanh"):
+            super().__init__()
+            self.linear_1 = nn.Linear(in_features, hidden_size)
+            self.act_1 = {"gelu_tanh": nn.GELU(approximate="tanh"), "silu": nn.SiLU()}[act_fn]
+            self.linear_2 = nn.Linear(hidden_size, out_features or hidden_size)
+
+        def forward(self, caption):
+            return self.linear_2(self.act_1(self.linear_1(caption)))
+
+    class CombinedTimestepTextProjEmbeddings(nn.Module):
+        def __init__(self, embedding_dim, pooled_projection_dim):
+            super().__init__()
+            self.time_proj = emb.Timesteps(num_channels=256, flip_sin_to_cos=True, downscale_freq_shift=0)
+            self.timestep_embedder = emb.TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+            self.text_embedder = PixArtAlphaTextProjection(pooled_projection_dim, embedding_dim, act_fn="silu")
+
+        def forward(self, timestep, pooled_projection):
+            t = self.timestep_embedder(self.time_proj(timestep).to(dtype=pooled_projection.dtype))
+            return t + self.text_embedder(pooled_projection)
+
+    class CombinedTimestepGuidanceTextProjEmbeddings(nn.Module):
+        def __init__(self, embedding_dim, pooled_projection_dim):
+            super().__init__()
+            self.time_proj = emb.Timesteps(num_channels=256, flip_sin_to_cos=True, downscale_freq_shift=0)
+            self.timestep_embedder = emb.TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+            self.guidance_embedder = emb.TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+            self.text_embedder = PixArtAlphaTextProjection(pooled_projection_dim, embedding_dim, act_fn="silu")
+
+        def forward(self, timestep, guidance, pooled_projection):
+            t = self.timestep_embedder(self.time_proj(timestep).to(dtype=pooled_projection.dtype))
+            g = self.guidance_embedder(self.time_proj(guidance).to(dtype=pooled_projection.dtype))
+            return t + g + self.text_embedder(pooled_projection)
+
+    emb.FluxPosEmbed, emb.apply_rotary_emb = FluxPosEmbed, apply_rotary_emb
+    emb.PixArtAlphaTextProjection = PixArtAlphaTextProjection
+    emb.CombinedTimestepTextProjEmbeddings = CombinedTimestepTextProjEmbeddings
+    emb.CombinedTimestepGuidanceTextProjEmbeddings = CombinedTimestepGuidanceTextProjEmbeddings
+    root.transformer_flux = _load_ref(PKG + ".models.transformers.transformer_flux",
+                                      "models/transformers/transformer_flux.py")
+    return root
+
+
+def build_reference_flux(cfg):
+    """The reference's (vendored) FluxTransformer2DModel for one of the oracle-style config dicts."""
+    root = install_flux()
+    return root.transformer_flux.FluxTransformer2DModel(
+        patch_size=1, in_channels=cfg["in_ch"], num_layers=cfg["layers"], num_single_layers=cfg["single_layers"],
+        attention_head_dim=cfg["head_dim"], num_attention_heads=cfg["heads"], joint_attention_dim=cfg["joint_dim"],
+        pooled_projection_dim=cfg["pooled_dim"], guidance_embeds=cfg["guidance_embeds"],
+        axes_dims_rope=tuple(cfg["axes_dims_rope"]))
+
+
 def build_reference_unet(cfg):
     """The reference's (vendored) UNet2DConditionModel for one of the oracle-style config dicts."""
     root = install()
