@@ -21,16 +21,18 @@ struct TileCoord {
 // resident CTAs share one weight tile and sweep A once per n-tile, which re-reads A from DRAM whenever M x K exceeds
 // L2 (measured 224 MB instead of 118 MB per launch for M=8192, N=1280, K=5120, profiles/r01_launches_ncu_s7.csv).
 __device__ __forceinline__ void decode_unit(const GemmParams& p, int t, int num_m_units, int& mu, int& n_tile, int& bz) {
+  // (integer division is ~35 instructions here: skipped for single-n-tile / unbatched launches)
   if (p.n_fastest) {
-    n_tile = t % p.num_n_tiles;
-    const int r0 = t / p.num_n_tiles;
-    mu = r0 % num_m_units;
-    bz = r0 / num_m_units;
+    const int q = (p.num_n_tiles == 1) ? t : t / p.num_n_tiles;
+    n_tile = t - q * p.num_n_tiles;
+    if (p.batch == 1) { mu = q; bz = 0; }
+    else { bz = q / num_m_units; mu = q - bz * num_m_units; }
   } else {
-    mu = t % num_m_units;
-    const int r0 = t / num_m_units;
-    n_tile = r0 % p.num_n_tiles;
-    bz = r0 / p.num_n_tiles;
+    const int q = (p.batch == 1 && p.num_n_tiles == 1) ? 0 : t / num_m_units;
+    mu = t - q * num_m_units;
+    if (p.batch == 1) { n_tile = q; bz = 0; }
+    else if (p.num_n_tiles == 1) { n_tile = 0; bz = q; }
+    else { bz = q / p.num_n_tiles; n_tile = q - bz * p.num_n_tiles; }
   }
 }
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
@@ -501,96 +503,120 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
   if (warp == 0) {
     // ===================================================== TMA producer (every CTA loads its own A rows / B half)
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = unit0; t < total_units; t += unit_step) {
-      int mu, n_tile, bz;
-      decode_unit(p, t, num_m_units, mu, n_tile, bz);
-      const int m_tile = mu * CG + (int)cta_rank;
-      int x0 = 0, y0 = 0, b0 = 0;
-      if (p.a_mode != kALinear) {
-        const int xt = m_tile % p.tiles_x;
-        const int r = m_tile / p.tiles_x;
-        const int yt = r % p.tiles_y;
-        const int bt = r / p.tiles_y;
-        x0 = xt * p.tw;
-        y0 = yt * p.th;
-        b0 = bt * p.tb;           // >= B_img for the padding tile of an odd tile count: TMA zero-fills
-      }
-      const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (elect_one()) {   // elect.sync: the compiler knows a single lane is active -> plain uniform-register moves
+    // ONE elected thread runs the whole loop (no per-k-block elect / reconvergence / warp sync) with incremental
+    // coordinates (no division per k-block): an ncu source-level capture of the 1024^2 x 128-channel VAE convolution
+    // showed this warp, not the tensor pipe, pacing the kernel (~760 clk per k-block against 256 clk of MMA work;
+    // MMA issuer 56 % of its samples waiting on full_bar, producer 18 % on empty_bar; profiles/r01_ncu_gemm_roles.md).
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int cinb = p.cin_blocks;
+      for (int t = unit0; t < total_units; t += unit_step) {
+        int mu, n_tile, bz;
+        decode_unit(p, t, num_m_units, mu, n_tile, bz);
+        const int m_tile = mu * CG + (int)cta_rank;
+        const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
+        const int bz_b = p.b_batched ? bz : 0;
+        // one pipeline stage: wait for the slot, announce the bytes (leader), then the caller issues A; B follows
+        auto begin_stage = [&]() -> uint8_t* {
+          mbar_wait(&empty_bar[s], ph ^ 1);
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_tx_bytes);
-          uint8_t* a_dst = smem + s * stage_bytes;
-          uint8_t* b_dst = a_dst + kStageBytesA;
-          if (p.a_mode == kALinear) {
-            if (CG == 2) tma_load_3d_pair(a_dst, &maps.a, &full_bar[s], kb * kBlockK, m_tile * kBlockM, p.a_batched ? bz : 0);
-            else tma_load_3d(a_dst, &maps.a, &full_bar[s], kb * kBlockK, m_tile * kBlockM, p.a_batched ? bz : 0);
+          return smem + s * stage_bytes;
+        };
+        auto end_stage = [&](uint8_t* a_dst, int k0) {
+          if (CG == 2) tma_load_3d_pair(a_dst + kStageBytesA, &maps.b, &full_bar[s], k0, b_row0, bz_b);
+          else tma_load_3d(a_dst + kStageBytesA, &maps.b, &full_bar[s], k0, b_row0, bz_b);
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        };
+        if (p.a_mode == kALinear) {
+          const int m0 = m_tile * kBlockM;
+          const int bz_a = p.a_batched ? bz : 0;
+          for (int kb = 0, k0 = 0; kb < p.num_k_blocks; ++kb, k0 += kBlockK) {
+            uint8_t* a_dst = begin_stage();
+            if (CG == 2) tma_load_3d_pair(a_dst, &maps.a, &full_bar[s], k0, m0, bz_a);
+            else tma_load_3d(a_dst, &maps.a, &full_bar[s], k0, m0, bz_a);
+            end_stage(a_dst, k0);
+          }
+        } else {
+          const int r = m_tile / p.tiles_x;
+          const int xt = m_tile - r * p.tiles_x;
+          const int bt = r / p.tiles_y;
+          const int yt = r - bt * p.tiles_y;
+          const int x0 = xt * p.tw;
+          const int y0 = yt * p.th;
+          const int b0 = bt * p.tb;           // >= B_img for the padding tile of an odd tile count: TMA zero-fills
+          int k0 = 0;                         // K offset of the weight tile = (tap * cin_blocks + cb) * 64
+          if (p.a_mode == kAConvS1) {
+            for (int ky = 0; ky < 3; ++ky) {
+              for (int kx = 0; kx < 3; ++kx) {
+                for (int cb = 0, c0 = 0; cb < cinb; ++cb, c0 += kBlockK, k0 += kBlockK) {
+                  uint8_t* a_dst = begin_stage();
+                  if (CG == 2) tma_load_4d_pair(a_dst, &maps.a, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, b0);
+                  else tma_load_4d(a_dst, &maps.a, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, b0);
+                  end_stage(a_dst, k0);
+                }
+              }
+            }
           } else {
-            const int tap = kb / p.cin_blocks;
-            const int cb = kb - tap * p.cin_blocks;
-            const int ky = tap / 3, kx = tap - 3 * ky;
-            if (p.a_mode == kAConvS1) {
-              if (CG == 2) tma_load_4d_pair(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
-              else tma_load_4d(a_dst, &maps.a, &full_bar[s], cb * kBlockK, x0 + kx - 1, y0 + ky - 1, b0);
-            } else {
-              // stride-2: input viewed as (B, H, 2, W, 2*Cin) with H, W the OUTPUT extents;
-              // input row 2*oy + ky - pad_lo -> parity (t & 1), half-row oy + (t >> 1)
-              const int ty = ky - p.pad_lo, tx = kx - p.pad_lo;
+            // stride-2: input viewed as (B, H, 2, W, 2*Cin) with H, W the OUTPUT extents;
+            // input row 2*oy + ky - pad_lo -> parity (t & 1), half-row oy + (t >> 1)
+            for (int ky = 0; ky < 3; ++ky) {
+              const int ty = ky - p.pad_lo;
               const int ypar = ty & 1, yoff = ty >> 1;
-              const int xpar = tx & 1, xoff = tx >> 1;
-              const int c0 = xpar * p.cin_blocks * kBlockK + cb * kBlockK;
-              if (CG == 2) tma_load_5d_pair(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
-              else tma_load_5d(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
+              for (int kx = 0; kx < 3; ++kx) {
+                const int tx = kx - p.pad_lo;
+                const int xpar = tx & 1, xoff = tx >> 1;
+                for (int cb = 0, c0 = xpar * cinb * kBlockK; cb < cinb; ++cb, c0 += kBlockK, k0 += kBlockK) {
+                  uint8_t* a_dst = begin_stage();
+                  if (CG == 2) tma_load_5d_pair(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
+                  else tma_load_5d(a_dst, &maps.a, &full_bar[s], c0, x0 + xoff, ypar, y0 + yoff, b0);
+                  end_stage(a_dst, k0);
+                }
+              }
             }
           }
-          if (CG == 2) tma_load_3d_pair(b_dst, &maps.b, &full_bar[s], kb * kBlockK, b_row0, p.b_batched ? bz : 0);
-          else tma_load_3d(b_dst, &maps.b, &full_bar[s], kb * kBlockK, b_row0, p.b_batched ? bz : 0);
         }
-        __syncwarp();
-        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (leader CTA only when CG = 2)
-    if (cta_rank == 0) {
+    // ===================================================== MMA issuer (leader CTA only when CG = 2), one elected thread
+    if (cta_rank == 0 && elect_one()) {
       const uint32_t idesc = p.in_f16 ? umma_idesc_f16(CG * kBlockM, p.block_n) : umma_idesc_bf16(CG * kBlockM, p.block_n);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      const int last_kb = p.num_k_blocks - 1;
       for (int t = unit0; t < total_units; t += unit_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * kMaxBlockN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = 0; kb <= last_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-            const uint64_t da = umma_desc_kmajor_sw128(a_addr);
-            const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t da = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t db = umma_desc_kmajor_sw128(a_addr + kStageBytesA);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            if (CG == 2) {
-              umma_commit_pair(&empty_bar[s], 3);       // frees this stage in both CTAs
-              if (kb == p.num_k_blocks - 1) umma_commit_pair(&tfull_bar[as], 3);
-            } else {
-              umma_commit(&empty_bar[s]);
-              if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
-            }
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          __syncwarp();
+          if (CG == 2) {
+            umma_commit_pair(&empty_bar[s], 3);       // frees this stage in both CTAs
+            if (kb == last_kb) umma_commit_pair(&tfull_bar[as], 3);
+          } else {
+            umma_commit(&empty_bar[s]);
+            if (kb == last_kb) umma_commit(&tfull_bar[as]);
+          }
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
         if (++as == kAccStages) { as = 0; aph ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column sets
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -651,22 +677,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         sc.c2 = tc.bz;
         sc.c3 = 0;
       } else {
-        const int xt = tc.m_tile % p.tiles_x;
         const int r = tc.m_tile / p.tiles_x;
-        const int yt = r % p.tiles_y;
+        const int xt = tc.m_tile - r * p.tiles_x;
         const int bt = r / p.tiles_y;
-        const int tx = r_in_tile % p.tw;
-        const int r2 = r_in_tile / p.tw;
-        const int ty = r2 % p.th;
-        const int tbi = r2 / p.th;
+        const int yt = r - bt * p.tiles_y;
+        // tw, th, tb are powers of two (gcd with 128): shifts / masks instead of divisions
+        const int tx = r_in_tile & (p.tw - 1);
+        const int r2 = r_in_tile >> p.tw_log2;
+        const int ty = r2 & (p.th - 1);
+        const int tbi = r2 >> p.th_log2;
         const int b = bt * p.tb + tbi;
         row = ((long long)b * p.H + (yt * p.th + ty)) * p.W + (xt * p.tw + tx);
         row_ok = b < p.B_img;
         const int w0 = ew * 32;   // first row of the warp slice, decomposed the same way
         sc.conv = true;
-        sc.c1 = xt * p.tw + (w0 % p.tw);
-        sc.c2 = yt * p.th + ((w0 / p.tw) % p.th);
-        sc.c3 = bt * p.tb + (w0 / p.tw) / p.th;
+        sc.c1 = xt * p.tw + (w0 & (p.tw - 1));
+        sc.c2 = yt * p.th + ((w0 >> p.tw_log2) & (p.th - 1));
+        sc.c3 = bt * p.tb + ((w0 >> p.tw_log2) >> p.th_log2);
       }
       const int bidx = (p.rows_per_batch > 0 && row_ok) ? (int)(row / p.rows_per_batch) : 0;
       if (p.gn_sums) {   // (row validity and the image are uniform over a tile: checked on the host)

@@ -50,6 +50,7 @@ struct GemmParams {
   int b_batched;        // 1: B has a batch dimension, 0: shared
   // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows
   int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;
+  int tw_log2, th_log2;        // tw, th, tb are powers of two (gcd with 128)
   // ---- epilogue
   int tma_store;               // 1: bf16/fp16 destinations go through smem staging + TMA bulk stores
   int fast_epi;                // 1: tma_store and every fp32 / residual operand is 16-byte aligned (lean epilogue path)

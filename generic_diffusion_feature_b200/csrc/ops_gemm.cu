@@ -257,6 +257,9 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
   p.tw = tw;
   p.th = th;
   p.tb = tb;
+  for (p.tw_log2 = 0; (1 << p.tw_log2) < tw; ++p.tw_log2) {}
+  for (p.th_log2 = 0; (1 << p.th_log2) < th; ++p.th_log2) {}
+  if ((1 << p.tw_log2) != tw || (1 << p.th_log2) != th) return fail(GDF_ERR_SHAPE, "build_conv3x3: tile %d x %d", tw, th);
   p.cin_blocks = Cin / kBlockK;
   p.pad_lo = pad_lo;
   fill_epilogue(p, e);
