@@ -19,22 +19,44 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-// Tile width: the kernel is operand-load bound (L2 -> smem bytes per MMA cycle ~ (128 + bn) / bn), so the widest
-// tile that does not waste columns wins; narrower tiles only for narrow N (measured, profiles/r01_probe_gemm.txt).
+// Tile width. Two effects compete: wide tiles need fewer operand bytes per MMA cycle (L2 -> smem ~ (128 + bn/2) / bn
+// per CTA of a pair) and amortise the per-tile epilogue / handshake cost, narrow tiles can cut the padding columns of
+// the last n-tile and, for the small launches of the transformer blocks (M = 8192: 32 row units), the idle tail of
+// the last wave: N = 1280 is 160 work units at bn = 256 = 2.16 waves of the 74 resident CTA pairs (3 waves of 256
+// columns), but 192 units at bn = 224 (3 waves of 224) or 256 units at bn = 160 (4 waves of 160).
+// Cost model: waves x (bn + kTileFixedCols), kTileFixedCols = per-tile fixed cost in column equivalents.
+// GDF_WAVE_POLICY=0 restores the padding-only rule (A/B timing).
 int choose_block_n(int N, bool geglu, int num_m_tiles) {
-  (void)num_m_tiles;
   const int forced = env_int("GDF_BLOCK_N", 0);   // tuning knob
   if (forced > 0 && forced % 16 == 0 && forced <= kMaxBlockN && (!geglu || forced % 64 == 0)) return forced;
   if (geglu) return N >= 256 ? 256 : 128;
   if (N <= 256) return ((N + 15) / 16) * 16;
-  int best = 256, best_waste = ((N + 255) / 256) * 256 - N;
-  const int cands[3] = {224, 192, 160};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    const int waste = ((N + bn - 1) / bn) * bn - N;
-    if (waste * 8 < best_waste * 8 - N) {   // accept a narrower tile only if it saves > 1/8 of N in padded columns
+  if (env_int("GDF_WAVE_POLICY", 1) == 0 || num_m_tiles <= 0) {
+    int best = 256, best_waste = ((N + 255) / 256) * 256 - N;
+    const int cands[3] = {224, 192, 160};
+    for (int i = 0; i < 3; ++i) {
+      const int bn = cands[i];
+      const int waste = ((N + bn - 1) / bn) * bn - N;
+      if (waste * 8 < best_waste * 8 - N) {   // accept a narrower tile only if it saves > 1/8 of N in padded columns
+        best = bn;
+        best_waste = waste;
+      }
+    }
+    return best;
+  }
+  const int kTileFixedCols = 48;
+  const int cg = num_m_tiles >= 2 ? 2 : 1;
+  const long long m_units = (num_m_tiles + cg - 1) / cg;
+  const long long resident = 148 / cg;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 128; bn -= 32) {   // multiples of 32: whole rounds of the lean epilogue path
+    const long long units = m_units * ((N + bn - 1) / bn);
+    const long long waves = (units + resident - 1) / resident;
+    const long long cost = waves * (bn + kTileFixedCols);
+    if (best_cost < 0 || cost * 100 < best_cost * 97) {   // a narrower tile has to win by > 3 %
       best = bn;
-      best_waste = waste;
+      best_cost = cost;
     }
   }
   return best;

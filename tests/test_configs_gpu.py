@@ -15,7 +15,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from common import O, ROOT, build_oracle, build_oracle_dit, compare_maps, make_dit_inputs, make_inputs
+from common import (O, ROOT, build_oracle, build_oracle_dit, build_oracle_flux, compare_maps, make_dit_inputs,
+                    make_flux_inputs, make_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -165,3 +166,32 @@ def test_config4_sdxl_pair_correspondence_4096(cuda_dev):
         near += int(((~same) & (gap < 2e-3)).sum())       # fp16-resolution near-ties
     assert agree / 4096 >= 0.995, agree / 4096
     assert agree + near == 4096, "disagreeing points that are not near-ties: %d" % (4096 - agree - near)
+
+
+def test_flux_full_width_1024(cuda_dev):
+    """SURVEY.md 8(a17) at the real tensor shapes: FLUX.1-dev width (24 heads x 128 = 3072 channels, 4096-wide T5
+    context of 512 tokens, 768-wide pooled vector, guidance embedding, rotary axes 16/56/56) on a 1024x1024 image
+    (4096 image tokens, joint sequence 4608), depth reduced to 2 double + 2 single blocks so that the fp32 CPU oracle
+    finishes in about a minute; the full-size VAE encoder with 16 latent channels. Every captured map vs the oracle."""
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _flux_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    torch.set_num_threads(os.cpu_count())
+    fcfg = dict(models.FLUX_CONFIGS["flux"], layers=2, single_layers=2)
+    vcfg = models.VAE_CONFIGS["flux"]
+    sd = models.synthetic_state_dict("flux", "cuda:0", None, vcfg, None, fcfg)
+    image, ctx, pooled, ev, eq = make_flux_inputs(1, 1024, fcfg, vcfg["latent"])
+    ids = _flux_feature_ids(fcfg)
+    layer = {i: True for i in ids}
+    pipe = models.get_diffusion_model("flux", "float16", device="cuda:0", state_dict=sd, flux_cfg=fcfg, vae_cfg=vcfg)
+    fe = FeatureExtractor(layer, "flux", "cuda:0", img_size=1024, external_model=pipe)
+    got = fe.extract((ctx, pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    torch.cuda.synchronize()
+    got = {k: v.float().cpu() for k, v in got.items()}
+    assert list(got.keys()) == ids and got["vit-block0-q"].shape == (1, 3072, 64, 64)
+    assert got["vit-block0-ffn-inner"].shape == (1, 12288, 64, 64)
+    model, vae = build_oracle_flux(fcfg, vcfg, {k: v.cpu() for k, v in sd.items()})
+    store = O.FeatureStore(layer)
+    O.attach_gatherers_flux(model, store)
+    want, _, _ = O.extract_flux(model, vae, store, image, ctx, pooled, ev, eq, t=50)
+    _check(compare_maps(got, want), "Flux full width 1024")
