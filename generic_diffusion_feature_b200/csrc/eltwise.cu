@@ -185,34 +185,78 @@ cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim
   return cudaGetLastError();
 }
 
-// y[b, n] = (silu_in ? silu(x) : x)[b, :] . W[n, :] + bias[n]; one warp per output element.
+// y[b, n] = (silu_in ? silu(x) : x)[b, :] . W[n, :] + bias[n]; one warp per output COLUMN n, all B rows at once (the
+// weight row is streamed once with 128-bit loads and reused for every batch row; B <= 8 per pass). These GEMVs are
+// pure weight streaming: 57 Flux modulation projections read 12.9 GB of fp32 weights per forward.
+template <int kB>
 __global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                    const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
+                                    const float* __restrict__ bias, float* __restrict__ y, int B0, int B, int K, int N,
                                     int act_in_silu, int act_out_silu) {
   const int lane = threadIdx.x & 31;
-  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= (long long)B * N) return;
-  const int b = (int)(o / N), n = (int)(o % N);
-  const float* xr = x + (long long)b * K;
-  const float* wr = W + (long long)n * K;
-  float acc = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float xv = xr[k];
-    if (act_in_silu) xv = xv / (1.f + expf(-xv));
-    acc += xv * __ldg(wr + k);
+  const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float* wr = W + n * K;
+  float acc[kB];
+#pragma unroll
+  for (int b = 0; b < kB; ++b) acc[b] = 0.f;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        if (B0 + b < B) {
+          float4 xv = *reinterpret_cast<const float4*>(x + (long long)(B0 + b) * K + k);
+          if (act_in_silu) {
+            xv.x = xv.x / (1.f + expf(-xv.x)); xv.y = xv.y / (1.f + expf(-xv.y));
+            xv.z = xv.z / (1.f + expf(-xv.z)); xv.w = xv.w / (1.f + expf(-xv.w));
+          }
+          acc[b] += xv.x * w4.x + xv.y * w4.y + xv.z * w4.z + xv.w * w4.w;
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        if (B0 + b < B) {
+          float xv = x[(long long)(B0 + b) * K + k];
+          if (act_in_silu) xv = xv / (1.f + expf(-xv));
+          acc[b] += xv * wv;
+        }
+      }
+    }
   }
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  for (int b = 0; b < kB; ++b) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], s);
+  }
   if (lane == 0) {
-    float r = acc + (bias ? bias[n] : 0.f);
-    if (act_out_silu) r = r / (1.f + expf(-r));
-    y[o] = r;
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      if (B0 + b < B) {
+        float r = acc[b] + (bias ? bias[n] : 0.f);
+        if (act_out_silu) r = r / (1.f + expf(-r));
+        y[(long long)(B0 + b) * N + n] = r;
+      }
+    }
   }
 }
 cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
                                 int act_in_silu, int act_out_silu, cudaStream_t stream) {
-  const long long outs = (long long)B * N;
-  small_linear_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, stream>>>(x, W, b, y, B, K, N, act_in_silu, act_out_silu);
+  const unsigned blocks = (unsigned)((N + 7) / 8);
+  for (int b0 = 0; b0 < B; b0 += 8) {   // 8 batch rows per pass over the weights
+    const int nb = B - b0;
+    if (nb == 1)
+      small_linear_kernel<1><<<blocks, 256, 0, stream>>>(x, W, b, y, b0, B, K, N, act_in_silu, act_out_silu);
+    else if (nb == 2)
+      small_linear_kernel<2><<<blocks, 256, 0, stream>>>(x, W, b, y, b0, B, K, N, act_in_silu, act_out_silu);
+    else if (nb <= 4)
+      small_linear_kernel<4><<<blocks, 256, 0, stream>>>(x, W, b, y, b0, B, K, N, act_in_silu, act_out_silu);
+    else
+      small_linear_kernel<8><<<blocks, 256, 0, stream>>>(x, W, b, y, b0, B, K, N, act_in_silu, act_out_silu);
+  }
   return cudaGetLastError();
 }
 

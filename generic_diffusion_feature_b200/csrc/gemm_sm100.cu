@@ -434,7 +434,17 @@ __device__ __forceinline__ void gn_flush(const GemmParams& p, float val, long lo
 // tile with tcgen05.mma.cta_group::2 — each CTA stages its own 128 A rows and HALF of the B rows, the leader (even)
 // CTA issues the MMAs for both, and each CTA's TMEM receives its own 128 accumulator rows.  Operand bytes pulled
 // from L2 per MMA cycle drop from (128 + bn) to (128 + bn / 2) rows, which is what bounds this kernel.
-template <int CG, bool kGeglu>
+#define EPF(field, level, fixed_value) (kLevel >= (level) ? (fixed_value) : p.field)
+// kLevel: compile-time promises about the epilogue (checked by launch_gemm). The general epilogue (level 0) is ~17.6 k
+// SASS instructions of mostly untaken branches; on the epilogue-bound launches instruction-fetch stalls
+// (`stall_no_inst`) were the top stall reason of the epilogue warps (24 % of all samples of the 128-channel VAE
+// convolution, profiles/r01_ncu_gemm_roles.md).
+//   level 1 "lean":   full tiles through the TMA-store path only (no ragged / direct-store path), no folded LayerNorm,
+//                     no row statistics, no row bias, alpha = out_scale = 1, no fp32 destination, activation fixed
+//                     by kGeglu (GEGLU or none). Captures, cap_pre, out2, column gate, per-sample row bias, residual
+//                     and GroupNorm statistics stay run-time options.
+//   level 2 "simple": additionally one bf16 destination only: [bias] [+ residual] [+ GroupNorm statistics] (VAE).
+template <int CG, bool kGeglu, int kLevel = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -447,10 +457,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   smem += kStagingBytes + kBarrierBytes + (p.res_tma ? kResBytes : 0);   // operand ring
   uint64_t* full_bar = bars;                                 // [kMaxStages]  (CG = 2: the leader's are used)
   uint64_t* empty_bar = bars + kMaxStages;                   // [kMaxStages]
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kAccStages]
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + kAccStages; // [kAccStages]  (CG = 2: the leader's are used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages);
-  uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kAccStages + 1;   // [kEpilogueWarps] residual round landed
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kMaxAccStages]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAccStages; // [kMaxAccStages]  (CG = 2: the leader's are used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages);
+  uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages + 1;   // [kEpilogueWarps] residual round landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -468,7 +478,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CG * kEpilogueWarps);
     }
@@ -497,6 +507,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int unit0 = blockIdx.x / CG;
   const int unit_step = gridDim.x / CG;
   const uint32_t stage_tx_bytes = (CG * kBlockM + p.block_n) * kBlockK * 2;   // bytes landing per stage, all CTAs
+  // accumulator ring in TMEM (512 columns): 2 stages of 256 columns, or 4 stages of 128 for tiles <= 128 columns wide -
+  // those launches (VAE 128-channel convolutions) have an epilogue about as long as their main loop, and with two
+  // stages MMA(i + 2) -> epilogue(i + 2) -> MMA(i + 4) serialises through every handshake latency
+  const int acc_stages = p.acc_stages;
+  const uint32_t acc_stride = 512u / (uint32_t)acc_stages;
 
   // register rebalancing: producer / MMA / allocator warpgroup needs few registers, the two epilogue warpgroups many
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -591,7 +606,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       for (int t = unit0; t < total_units; t += unit_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * kMaxBlockN;
+        const uint32_t tmem_acc = tmem_base + as * acc_stride;
         for (int kb = 0; kb <= last_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -613,7 +628,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
-        if (++as == kAccStages) { as = 0; aph ^= 1; }
+        if (++as == acc_stages) { as = 0; aph ^= 1; }
       }
     }
     __syncwarp();
@@ -704,11 +719,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
       }
       const long long out_batch_off = (long long)tc.bz * p.out_batch_stride;
-      const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + row) : 0.f;
+      const float bm = (EPF(bias_m, 1, nullptr) && row_ok) ? __ldg(EPF(bias_m, 1, nullptr) + row) : 0.f;
       // folded LayerNorm of the A rows: value = ln_a * acc + ln_b * u[col] + bias[col]
       float ln_a = 1.f, ln_b = 0.f;
-      if (p.ln_sums && row_ok) {
-        const float2 sq = __ldg(reinterpret_cast<const float2*>(p.ln_sums) + row);
+      if (EPF(ln_sums, 1, nullptr) && row_ok) {
+        const float2 sq = __ldg(reinterpret_cast<const float2*>(EPF(ln_sums, 1, nullptr)) + row);
         const float mean = sq.x * p.ln_inv_c;
         const float var = fmaxf(fmaf(sq.y, p.ln_inv_c, -mean * mean), 0.f);
         ln_a = rsqrtf(var + p.ln_eps);
@@ -717,13 +732,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       float rs_sum = 0.f, rs_sq = 0.f;   // row statistics of this thread's final values (row_sums)
 
       // per-row operand bases of the lean path (null rows of a padding tile read nothing)
-      const float* rbb = (p.row_batch_bias && row_ok) ? p.row_batch_bias + (long long)bidx * p.N : nullptr;
-      const float* csrow = (!kGeglu && p.col_scale && row_ok) ? p.col_scale + (long long)bidx * ncols_out : nullptr;
+      const float* rbb = (EPF(row_batch_bias, 2, nullptr) && row_ok) ? EPF(row_batch_bias, 2, nullptr) + (long long)bidx * p.N : nullptr;
+      const float* csrow = (!kGeglu && EPF(col_scale, 2, nullptr) && row_ok) ? EPF(col_scale, 2, nullptr) + (long long)bidx * ncols_out : nullptr;
       // (GEGLU launches carry no residual / column gate on the lean path: checked on the host)
       const __nv_bfloat16* resrow = (!kGeglu && p.residual && row_ok && !res_tma) ? p.residual + row * p.ld_res : nullptr;
       // a round of the lean path = 64 accumulator columns starting at c (32 at the ragged end of the tile)
       auto lean_round = [&](int c) -> bool {
-        if (!p.fast_epi || c >= out_tile_w) return false;
+        if (!EPF(fast_epi, 1, 1) || c >= out_tile_w) return false;
         const int oc = tc.n_tile * out_tile_w + c;
         if (oc >= ncols_out) return false;
         const bool tw2 = (c + 32 < out_tile_w) && (oc + 32 < ncols_out);
@@ -752,13 +767,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kMaxBlockN;
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * acc_stride;
 
       // ---- lean path: rounds of 64 columns (two 32-column halves), TMEM loads / bias vectors / residual prefetch
       // in flight together, one fence + one elected TMA issue per destination and round
       bool have_res = false;
       int c_done = cset * 64;    // first column this warp still has to handle on the generic path
-      if (p.fast_epi) {
+      if (EPF(fast_epi, 1, 1)) {
         for (int c = cset * 64; c < out_tile_w; c += 128) {
           const int ocol0 = tc.n_tile * out_tile_w + c;
           if (ocol0 >= ncols_out) { c_done = out_tile_w; break; }
@@ -794,16 +809,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hh == 1 && !two) break;
-            if (p.ln_sums) {   // (alpha == 1, no row bias: checked on the host)
+            if (EPF(ln_sums, 1, nullptr)) {   // (alpha == 1, no row bias: checked on the host)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) * ln_a;
               fma_f32x32(p.ln_u + acol0 + hh * 32, ln_b, v[hh]);
-            } else if (p.alpha == 1.f) {
+            } else if (EPF(alpha, 1, 1.f) == 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) + bm;
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[hh][j] = fmaf(__uint_as_float(raw[hh][j]), p.alpha, bm);
+              for (int j = 0; j < 32; ++j) v[hh][j] = fmaf(__uint_as_float(raw[hh][j]), EPF(alpha, 1, 1.f), bm);
             }
             if (p.bias) add_f32x32(p.bias + acol0 + hh * 32, v[hh]);
             if (rbb) add_f32x32(rbb + acol0 + hh * 32, v[hh]);
@@ -819,31 +834,31 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               if (hh == 1 && !two) break;
               float g[32];   // aliases graw[hh]
 #pragma unroll
-              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * (p.ln_sums ? ln_a : p.alpha);
-              if (p.ln_sums) fma_f32x32(p.ln_u + gcol0 + hh * 32, ln_b, g);
+              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * (EPF(ln_sums, 1, nullptr) ? ln_a : EPF(alpha, 1, 1.f));
+              if (EPF(ln_sums, 1, nullptr)) fma_f32x32(p.ln_u + gcol0 + hh * 32, ln_b, g);
               if (p.bias) add_f32x32(p.bias + gcol0 + hh * 32, g);
 #pragma unroll
               for (int j = 0; j < 32; j += 2) geglu_pair(v[hh][j], v[hh][j + 1], g[j], g[j + 1]);
             }
-          } else if (p.act == kActGeluTanh) {
+          } else if (EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone)) == kActGeluTanh) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[0][j] = gelu_tanh_f(v[0][j]); v[1][j] = gelu_tanh_f(v[1][j]); }
-          } else if (p.act == kActSilu) {
+          } else if (EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone)) == kActSilu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[0][j] = silu_f(v[0][j]); v[1][j] = silu_f(v[1][j]); }
           }
-          if (p.cap_pre)
+          if (EPF(cap_pre, 2, nullptr))
             store_round<true>(&maps.cap_pre, ocol0, nullptr, 0, two, stg_warp, toggle, lane, swz, v[0], v[1], sc);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hh == 1 && !two) break;
             if (csrow) mul_f32x32(csrow + ocol0 + hh * 32, v[hh]);
             if (resrow || res_tma) residual_add(rr[hh], v[hh]);
-            if (p.out_scale != 1.f) {
+            if (EPF(out_scale, 1, 1.f) != 1.f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[hh][j] *= p.out_scale;
+              for (int j = 0; j < 32; ++j) v[hh][j] *= EPF(out_scale, 1, 1.f);
             }
-            if (p.row_sums) {
+            if (EPF(row_sums, 1, nullptr)) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) { rs_sum += v[hh][j]; rs_sq = fmaf(v[hh][j], v[hh][j], rs_sq); }
             }
@@ -863,22 +878,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // destinations of the final value; a dtype / capture-segment boundary in the middle of the round
           // (all boundaries are multiples of 32 columns) splits it into two single-half rounds
           auto emit = [&](int col, bool tw, const float* va, const float* vb) {
-            if (p.out && col >= p.out_f16_from) {
+            if (p.out && col >= EPF(out_f16_from, 2, (1 << 30))) {
               store_round<true>(&maps.out, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
-              if (p.out2) store_round<false>(&maps.out2, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
+              if (EPF(out2, 2, nullptr)) store_round<false>(&maps.out2, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
             } else if (p.out) {
-              store_round<false>(&maps.out, col, p.out2 ? &maps.out2 : nullptr, col, tw, stg_warp, toggle, lane, swz, va,
+              store_round<false>(&maps.out, col, EPF(out2, 2, nullptr) ? &maps.out2 : nullptr, col, tw, stg_warp, toggle, lane, swz, va,
                                  vb, sc);
-            } else if (p.out2) {
+            } else if (EPF(out2, 2, nullptr)) {
               store_round<false>(&maps.out2, col, nullptr, 0, tw, stg_warp, toggle, lane, swz, va, vb, sc);
             }
-            if (p.num_cap > 0) {
+            if (EPF(num_cap, 2, 0) > 0) {
               const CUtensorMap* m0 = nullptr;
               const CUtensorMap* m1 = nullptr;
               int c0 = 0, c1 = 0;
 #pragma unroll
               for (int s = 0; s < 3; ++s) {
-                if (s < p.num_cap && p.cap[s].ptr && col >= p.cap[s].col_begin && col < p.cap[s].col_end) {
+                if (s < EPF(num_cap, 2, 0) && p.cap[s].ptr && col >= p.cap[s].col_begin && col < p.cap[s].col_end) {
                   if (!m0) { m0 = &maps.cap[s]; c0 = col - p.cap[s].col_begin; }
                   else if (!m1) { m1 = &maps.cap[s]; c1 = col - p.cap[s].col_begin; }
                 }
@@ -889,17 +904,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           bool split = false;
           if (two) {
             const int mid = ocol0 + 32;
-            split = (p.out && p.out_f16_from == mid);
+            split = (p.out && EPF(out_f16_from, 2, (1 << 30)) == mid);
 #pragma unroll
             for (int s = 0; s < 3; ++s)
-              if (s < p.num_cap && p.cap[s].ptr && (p.cap[s].col_begin == mid || p.cap[s].col_end == mid)) split = true;
+              if (s < EPF(num_cap, 2, 0) && p.cap[s].ptr && (p.cap[s].col_begin == mid || p.cap[s].col_end == mid)) split = true;
           }
           if (!split) emit(ocol0, two, v[0], v[1]);
           else {
             emit(ocol0, false, v[0], v[0]);
             emit(ocol0 + 32, false, v[1], v[1]);
           }
-          if (p.out_f32 && row_ok) {
+          if (EPF(out_f32, 1, nullptr) && row_ok) {
             direct_store32(p, v[0], v[0], row, ocol0, ocol0 + 32, out_batch_off, true);
             if (two) direct_store32(p, v[1], v[1], row, ocol0 + 32, ocol0 + 64, out_batch_off, true);
           }
@@ -907,40 +922,41 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       // ---- generic path: whatever the lean path left (ragged tiles, unaligned operands, no TMA store), 32 columns
       // at a time; this warp owns the 64-column groups with (group index & 1) == cset
+      if (kLevel == 0)
       for (int c = c_done; c < out_tile_w; c += ((c & 32) ? 96 : 32)) {
         const int ocol0 = tc.n_tile * out_tile_w + c;
         if (ocol0 >= ncols_out) break;
         const int lim = min(ncols_out, ocol0 + 32);
         float v[32];
         load_activate32(p, taddr, c, out_tile_w, tc.n_tile, bm, row_ok, bidx, ln_a, ln_b, v);
-        if (p.tma_store) {
+        if (EPF(tma_store, 1, 1)) {
           // registers -> swizzled smem -> one TMA bulk store per destination (rows / columns clipped by the map)
-          if (p.cap_pre) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
+          if (EPF(cap_pre, 2, nullptr)) stage_and_store<true>(&maps.cap_pre, stg_warp, toggle, lane, v, ocol0, sc);
           gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
-          if (p.row_sums) {
+          if (EPF(row_sums, 1, nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (ocol0 + j < lim) { rs_sum += v[j]; rs_sq = fmaf(v[j], v[j], rs_sq); }
           }
           if (p.out) {
-            if (ocol0 >= p.out_f16_from) stage_and_store<true>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
+            if (ocol0 >= EPF(out_f16_from, 2, (1 << 30))) stage_and_store<true>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
             else stage_and_store<false>(&maps.out, stg_warp, toggle, lane, v, ocol0, sc);
           }
-          if (p.out2) stage_and_store<false>(&maps.out2, stg_warp, toggle, lane, v, ocol0, sc);
+          if (EPF(out2, 2, nullptr)) stage_and_store<false>(&maps.out2, stg_warp, toggle, lane, v, ocol0, sc);
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            if (s < p.num_cap && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end)
+            if (s < EPF(num_cap, 2, 0) && p.cap[s].ptr && ocol0 >= p.cap[s].col_begin && ocol0 < p.cap[s].col_end)
               stage_and_store<true>(&maps.cap[s], stg_warp, toggle, lane, v, ocol0 - p.cap[s].col_begin, sc);
           }
-          if (p.out_f32 && row_ok) direct_store32(p, v, v, row, ocol0, lim, out_batch_off, true);
+          if (EPF(out_f32, 1, nullptr) && row_ok) direct_store32(p, v, v, row, ocol0, lim, out_batch_off, true);
         } else {
           float vpre[32];
-          if (p.cap_pre) {
+          if (EPF(cap_pre, 2, nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) vpre[j] = v[j];
           }
           gate_residual32(p, v, row, bidx, ocol0, ncols_out, lim, row_ok);
-          if (p.row_sums) {
+          if (EPF(row_sums, 1, nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (ocol0 + j < lim) { rs_sum += v[j]; rs_sq = fmaf(v[j], v[j], rs_sq); }
@@ -948,9 +964,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (row_ok) direct_store32(p, vpre, v, row, ocol0, lim, out_batch_off, false);
         }
       }
-      if (p.row_sums && row_ok) {   // this warp's column share of the row; the other column set / n-tiles add theirs
-        atomicAdd(p.row_sums + 2 * row, rs_sum);
-        atomicAdd(p.row_sums + 2 * row + 1, rs_sq);
+      if (EPF(row_sums, 1, nullptr) && row_ok) {   // this warp's column share of the row; the other column set / n-tiles add theirs
+        atomicAdd(EPF(row_sums, 1, nullptr) + 2 * row, rs_sum);
+        atomicAdd(EPF(row_sums, 1, nullptr) + 2 * row + 1, rs_sq);
       }
       tc_fence_before();
       __syncwarp();
@@ -958,7 +974,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA issuer waits for both
         else mbar_arrive(&tempty_bar[as]);
       }
-      if (++as == kAccStages) { as = 0; aph ^= 1; }
+      if (++as == acc_stages) { as = 0; aph ^= 1; }
     }
     if (p.gn_sums && gn_key >= 0) gn_flush_run();
     __syncwarp();
@@ -989,6 +1005,12 @@ static cudaError_t gemm_init_once() {
   e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return e;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1044,7 +1066,21 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  if (p.act == kActGeglu) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
+  // specialised epilogues (see kLevel): GDF_EPI_LEVEL=0 forces the general kernel, =1 stops at "lean" (A/B timing)
+  static const int max_level = getenv("GDF_EPI_LEVEL") ? atoi(getenv("GDF_EPI_LEVEL")) : 2;
+  const bool geglu = p.act == kActGeglu;
+  const int out_w = geglu ? p.block_n / 2 : p.block_n;
+  const bool lean = max_level >= 1 && (geglu || p.act == kActNone) && !p.ln_sums && !p.row_sums && !p.bias_m &&
+                    p.alpha == 1.f && p.out_scale == 1.f && !p.out_f32 && p.fast_epi && p.tma_store &&
+                    p.N % p.block_n == 0 && out_w % 32 == 0 && p.n_out == (geglu ? p.N / 2 : p.N);
+  if (geglu) {
+    if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true, 1>, maps, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
+  }
+  const bool simple = lean && max_level >= 2 && !p.col_scale && !p.row_batch_bias && !p.out2 && !p.cap_pre &&
+                      p.num_cap == 0 && p.out && p.out_f16_from >= (1 << 30);
+  if (simple) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 2>, maps, p);
+  if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 1>, maps, p);
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, maps, p);
 }
 

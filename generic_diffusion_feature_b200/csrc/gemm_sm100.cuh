@@ -14,7 +14,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one swizzle row
 constexpr int kMaxBlockN = 256;
 constexpr int kMaxStages = 8;
-constexpr int kAccStages = 2;
+constexpr int kMaxAccStages = 4;    // TMEM accumulator ring: 2 x 256 columns, or 4 x 128 (block_n <= 128)
 constexpr int kEpilogueWarps = 8;   // 4 TMEM lane quadrants x 2 interleaved column sets
 constexpr int kGemmThreads = 128 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int kStageBytesA = kBlockM * kBlockK * 2;          // 16 KB
@@ -44,6 +44,7 @@ struct GemmParams {
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
+  int acc_stages;       // 2 or 4 (see kMaxAccStages)
   int n_fastest;        // 1: consecutive work units walk the n-tiles of one m unit first (see decode_unit)
   int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)
   int a_batched;        // 1: A has a batch dimension, 0: shared across the batch

@@ -50,13 +50,18 @@ int choose_block_n(int N, bool geglu, int num_m_tiles) {
   const long long resident = 148 / cg;
   int best = 256;
   long long best_cost = -1;
-  for (int bn = 256; bn >= 128; bn -= 32) {   // multiples of 32: whole rounds of the lean epilogue path
-    const long long units = m_units * ((N + bn - 1) / bn);
-    const long long waves = (units + resident - 1) / resident;
-    const long long cost = waves * (bn + kTileFixedCols);
-    if (best_cost < 0 || cost * 100 < best_cost * 97) {   // a narrower tile has to win by > 3 %
-      best = bn;
-      best_cost = cost;
+  // widths that divide N first: only launches without a ragged last tile qualify for the specialised ("lean" /
+  // "simple") epilogue instantiations, which are worth more than the last few per cent of wave packing
+  for (int pass = 0; pass < 2 && best_cost < 0; ++pass) {
+    for (int bn = 256; bn >= 128; bn -= 32) {   // multiples of 32: whole rounds of the lean epilogue path
+      if (pass == 0 && N % bn != 0) continue;
+      const long long units = m_units * ((N + bn - 1) / bn);
+      const long long waves = (units + resident - 1) / resident;
+      const long long cost = waves * (bn + kTileFixedCols);
+      if (best_cost < 0 || cost * 100 < best_cost * 97) {   // a narrower tile has to win by > 3 %
+        best = bn;
+        best_cost = cost;
+      }
     }
   }
   return best;
@@ -75,6 +80,7 @@ static void finish_tiling(GemmParams& p) {
   p.cta_group = choose_cta_group(p.block_n, p.num_m_tiles);
   // n-fastest rasterisation whenever the whole weight matrix stays L2-resident (every layer of the path: <= 26 MB)
   const long long w_bytes = (long long)p.N * p.K * 2;
+  p.acc_stages = (p.block_n <= 128 && env_int("GDF_ACC4", 1) != 0) ? 4 : 2;
   p.n_fastest = (p.num_n_tiles > 1 && w_bytes <= (48ll << 20) && env_int("GDF_RASTER_N", 1) != 0) ? 1 : 0;
 }
 // ring depth once the epilogue mode (residual staging or not) is known
