@@ -36,6 +36,18 @@ FLOP_PER_IMAGE = 11.640e12      # UNet 6.761 + VAE encoder 4.879
 IMG = 1024
 
 
+def read_gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this same command
+    (profiles/r01_gemm_traffic.json, written by tools/ncu_launch_summary.py --traffic-json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -242,8 +254,13 @@ def run_ours(args, rank, world, local):
         sustained, burst, hbm, how = read_peaks()
         gemm_tflops = flv[0] / (msv[0] * 1e-3) / 1e12 if msv[0] > 0 else 0.0
         tot_ms = sum(msv)
+        traffic = read_gemm_traffic()
         roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": sustained, "unit": "TFLOP/s",
-                "frac": gemm_tflops / sustained, "traffic": None, "peak_source": how + " (sustained bf16)",
+                "frac": gemm_tflops / sustained,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None,
+                "algorithmic_flop_per_launch": flv[0] / max(lnv[0], 1),
+                "peak_source": how + " (sustained bf16)",
                 "kernel": "gemm_tcgen05_kernel",
                 "avg_launch_us": 1e3 * msv[0] / max(lnv[0], 1),
                 "share_of_step": msv[0] / tot_ms if tot_ms > 0 else None,

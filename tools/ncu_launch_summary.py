@@ -29,3 +29,13 @@ for k, a in sorted(agg.items(), key=lambda x: -x[1]["t"]):
     print("| %s | %d | %.3f | %.3f | %.2f | %.2f | %.1f |" % (k, a["n"], a["t"], a["t"] / tot, a["rd"] / 1e9, a["wr"] / 1e9,
                                                           (a["rd"] + a["wr"]) / 1e6 / max(a["n"], 1)))
 print("\nTotal %.1f ms over %d launches (cold-cache, serialised: compare shares, not absolutes)." % (tot, sum(a["n"] for a in agg.values())))
+
+if "--traffic-json" in sys.argv:
+    import json
+    out = sys.argv[sys.argv.index("--traffic-json") + 1]
+    g = [a for k, a in agg.items() if "gemm_tcgen05_kernel" in k]
+    n = sum(a["n"] for a in g)
+    json.dump({"kernel": "gemm_tcgen05_kernel (all instantiations)", "launches": n,
+               "dram_bytes_per_launch": (sum(a["rd"] + a["wr"] for a in g) / max(n, 1)),
+               "dram_read_gb_per_step": sum(a["rd"] for a in g) / 1e9, "dram_write_gb_per_step": sum(a["wr"] for a in g) / 1e9,
+               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, " + sys.argv[1]}, open(out, "w"))
