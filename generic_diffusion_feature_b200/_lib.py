@@ -27,7 +27,7 @@ EXPORTS = [
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
     "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
-    "gdf_op_resize_concat", "gdf_correspond_workspace_floats", "gdf_correspond",
+    "gdf_op_resize_concat", "gdf_op_avgpool_nhwc", "gdf_correspond_workspace_floats", "gdf_correspond",
 ]
 
 
@@ -135,6 +135,7 @@ def load():
     lib.gdf_op_qsample.argtypes = [P, P, P, c_float, c_float, c_float, c_float, P, P, P, c_int, c_int, P]
     lib.gdf_op_cast_f32_to_bf16.argtypes = [P, P, c_int64, P]
     lib.gdf_op_resize_concat.argtypes = [ctypes.POINTER(ResizeSrc), c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+    lib.gdf_op_avgpool_nhwc.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     lib.gdf_correspond_workspace_floats.restype = c_int64
     lib.gdf_correspond_workspace_floats.argtypes = [c_int, c_int, c_int]
     lib.gdf_correspond.argtypes = [P, P, c_int, c_int, c_int, P, c_int, P, P, P]

@@ -108,6 +108,34 @@ class FeatureStore:
         return self.feats
 
 
+def pool_views(lib, feats, ratio):
+    """feature_resize (feature_extractor.py:51-53): every captured map -> F.adaptive_avg_pool2d(feat, (h // r, w // r)),
+    by gdf_op_avgpool_nhwc on the token-major fp16 storage; the pooled maps live in one new buffer and are returned as
+    (B, C, h // r, w // r) views in the same order. (The reference pools in model dtype before the fp16 cast; here the
+    fp16 capture is pooled with fp32 sums - one extra rounding.)"""
+    if ratio <= 1 or not feats:
+        return feats
+    total = 0
+    plan = []
+    for k, v in feats.items():
+        B, C, H, W = v.shape
+        OH, OW = H // ratio, W // ratio
+        if OH < 1 or OW < 1:
+            raise ValueError("feature_resize %d is larger than map '%s' (%d x %d)" % (ratio, k, H, W))
+        plan.append((k, v, B, C, H, W, OH, OW, total))
+        total += (B * OH * OW * C * 2 + 255) // 256 * 256
+    dev = next(iter(feats.values())).device
+    buf = torch.empty(total, dtype=torch.uint8, device=dev)
+    out = {}
+    for k, v, B, C, H, W, OH, OW, off in plan:
+        src = v.permute(0, 2, 3, 1)                       # the arena storage: (B, H, W, C) contiguous
+        assert src.is_contiguous() and v.dtype == torch.float16
+        dst = buf[off:off + B * OH * OW * C * 2].view(torch.float16).view(B, OH, OW, C)
+        check(lib.gdf_op_avgpool_nhwc(_lib.ptr(src), _lib.ptr(dst), B, H, W, C, OH, OW, _lib.stream_ptr()))
+        out[k] = dst.permute(0, 3, 1, 2)
+    return out
+
+
 class FeaturePlan:
     """Compiled selection: ids -> arena slots for one (batch, img_size)."""
 
@@ -153,9 +181,8 @@ def prepare_feature_extractor(version, pipe, config, resize_ratio, train_unet):
             config = json.load(f)
     if train_unet:
         raise NotImplementedError("train_unet needs autograd through the kernels (SURVEY.md 8f, not built)")
-    if resize_ratio != 1:
-        raise NotImplementedError("feature_resize > 1 (adaptive_avg_pool2d, feature_extractor.py:51-53) is not "
-                                  "built on the B200 path yet")
+    if not isinstance(resize_ratio, int) or resize_ratio < 1:
+        raise ValueError("feature_resize must be a positive integer")
     return FeatureStore(config, resize_ratio, train_unet)
 
 

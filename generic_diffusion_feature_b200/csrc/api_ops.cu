@@ -165,6 +165,11 @@ int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, i
                                   static_cast<cudaStream_t>(stream)));
 }
 
+int gdf_op_avgpool_nhwc(const void* x, void* y, int B, int H, int W, int C, int OH, int OW, void* stream) {
+  GDF_LAUNCH(launch_adaptive_avgpool_nhwc(static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C, OH, OW,
+                                          static_cast<cudaStream_t>(stream)));
+}
+
 int64_t gdf_correspond_workspace_floats(int n, int hw, int C) { return (int64_t)corr_workspace_floats(n, hw, C); }
 
 int gdf_correspond(const void* stack_src, const void* stack_tgt, int C, int hw, int load_hw, const void* query_yx,

@@ -440,10 +440,10 @@ __device__ __forceinline__ void gn_flush(const GemmParams& p, float val, long lo
 // (`stall_no_inst`) were the top stall reason of the epilogue warps (24 % of all samples of the 128-channel VAE
 // convolution, profiles/r01_ncu_gemm_roles.md).
 //   level 1 "lean":   full tiles through the TMA-store path only (no ragged / direct-store path), no folded LayerNorm,
-//                     no row statistics, no row bias, alpha = out_scale = 1, no fp32 destination, activation fixed
+//                     no row statistics, no row bias, out_scale = 1, no fp32 destination, activation fixed
 //                     by kGeglu (GEGLU or none). Captures, cap_pre, out2, column gate, per-sample row bias, residual
 //                     and GroupNorm statistics stay run-time options.
-//   level 2 "simple": additionally one bf16 destination only: [bias] [+ residual] [+ GroupNorm statistics] (VAE).
+//   level 2 "simple": additionally alpha = 1 and one bf16 destination only: [bias] [+ residual] [+ GroupNorm statistics] (VAE).
 template <int CG, bool kGeglu, int kLevel = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
@@ -813,12 +813,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) * ln_a;
               fma_f32x32(p.ln_u + acol0 + hh * 32, ln_b, v[hh]);
-            } else if (EPF(alpha, 1, 1.f) == 1.f) {
+            } else if (EPF(alpha, 2, 1.f) == 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[hh][j] = __uint_as_float(raw[hh][j]) + bm;
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[hh][j] = fmaf(__uint_as_float(raw[hh][j]), EPF(alpha, 1, 1.f), bm);
+              for (int j = 0; j < 32; ++j) v[hh][j] = fmaf(__uint_as_float(raw[hh][j]), EPF(alpha, 2, 1.f), bm);
             }
             if (p.bias) add_f32x32(p.bias + acol0 + hh * 32, v[hh]);
             if (rbb) add_f32x32(rbb + acol0 + hh * 32, v[hh]);
@@ -834,7 +834,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               if (hh == 1 && !two) break;
               float g[32];   // aliases graw[hh]
 #pragma unroll
-              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * (EPF(ln_sums, 1, nullptr) ? ln_a : EPF(alpha, 1, 1.f));
+              for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[hh][j]) * (EPF(ln_sums, 1, nullptr) ? ln_a : EPF(alpha, 2, 1.f));
               if (EPF(ln_sums, 1, nullptr)) fma_f32x32(p.ln_u + gcol0 + hh * 32, ln_b, g);
               if (p.bias) add_f32x32(p.bias + gcol0 + hh * 32, g);
 #pragma unroll
@@ -1071,13 +1071,13 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   const bool geglu = p.act == kActGeglu;
   const int out_w = geglu ? p.block_n / 2 : p.block_n;
   const bool lean = max_level >= 1 && (geglu || p.act == kActNone) && !p.ln_sums && !p.row_sums && !p.bias_m &&
-                    p.alpha == 1.f && p.out_scale == 1.f && !p.out_f32 && p.fast_epi && p.tma_store &&
+                    p.out_scale == 1.f && !p.out_f32 && p.fast_epi && p.tma_store &&
                     p.N % p.block_n == 0 && out_w % 32 == 0 && p.n_out == (geglu ? p.N / 2 : p.N);
   if (geglu) {
     if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true, 1>, maps, p);
     return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
   }
-  const bool simple = lean && max_level >= 2 && !p.col_scale && !p.row_batch_bias && !p.out2 && !p.cap_pre &&
+  const bool simple = lean && max_level >= 2 && p.alpha == 1.f && !p.col_scale && !p.row_batch_bias && !p.out2 && !p.cap_pre &&
                       p.num_cap == 0 && p.out && p.out_f16_from >= (1 << 30);
   if (simple) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 2>, maps, p);
   if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 1>, maps, p);

@@ -139,6 +139,10 @@ cudaError_t launch_adaln_mod(const float* table, const float* t, float* out, int
 cudaError_t launch_unpatchify(const float* x, float* out, int B, int g, int p, int oc, cudaStream_t stream);
 cudaError_t launch_mask_to_bias(const float* mask, float* bias, int n, cudaStream_t stream);
 
+// ---- feature_resize: adaptive average pooling of a captured fp16 NHWC map (stack.cu)
+cudaError_t launch_adaptive_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int OH, int OW,
+                                         cudaStream_t stream);
+
 // ---- feature stack + correspondence (stack.cu)
 struct ResizeSrc {
   const __half* ptr;  // fp16 NHWC map [B, h*w, C]

@@ -361,4 +361,52 @@ int launch_correspond(const __half* stack1, const __half* stack2, int C, int hw,
   return GDF_OK;
 }
 
+// ---------------------------------------------------------------- feature_resize (FeatureStore.store, feature_extractor.py:
+// 51-53): F.adaptive_avg_pool2d(feat, (h // r, w // r)) on a captured fp16 NHWC map. Window of output cell i along an
+// axis of length H: [floor(i * H / OH), ceil((i + 1) * H / OH)) (ATen adaptive pooling). 8 channels per thread, fp32 sums.
+__global__ void adaptive_avgpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W,
+                                             int C, int OH, int OW) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * OH * OW * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long r = i / cv;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const int y0 = (oy * H) / OH, y1 = ((oy + 1) * H + OH - 1) / OH;
+    const int x0 = (ox * W) / OW, x1 = ((ox + 1) * W + OW - 1) / OW;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int yy = y0; yy < y1; ++yy) {
+      for (int xx = x0; xx < x1; ++xx) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + yy) * W + xx) * C + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(h2[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+    const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(acc[2 * q] * inv, acc[2 * q + 1] * inv);
+    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + c) = o;
+  }
+}
+cudaError_t launch_adaptive_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int OH, int OW,
+                                         cudaStream_t stream) {
+  if (C % 8 != 0 || OH < 1 || OW < 1 || OH > H || OW > W) return cudaErrorInvalidValue;
+  const long long total = (long long)B * OH * OW * (C >> 3);
+  const long long blocks = (total + 255) / 256;
+  adaptive_avgpool_nhwc_kernel<<<(unsigned)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32), 256, 0, stream>>>(
+      x, y, B, H, W, C, OH, OW);
+  return cudaGetLastError();
+}
+
 }  // namespace gdf

@@ -17,7 +17,7 @@ Differences a user can observe (all documented in INTEGRATION.md):
   * version 'flux' (diffusion_feature.py:246-253 calls the whole FluxImg2ImgPipeline with strength = t/1000 and
     guidance_scale 1): prompts = (t5_embeds (1|B, 512, 4096), pooled_clip (1|B, 768)) as returned by encode_prompt
     here (the reference passes raw strings to the pipeline); noise = (eps_vae, eps_q) with 16 latent channels;
-  * control / attention / train_unet / feature_resize / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
+  * control / attention / train_unet / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
     and IF raise NotImplementedError.
 """
 import ctypes
@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 from . import _lib, schedulers
 from ._lib import check
-from .components.feature_extractor import FeaturePlan, prepare_feature_extractor, selected_ids
+from .components.feature_extractor import FeaturePlan, pool_views, prepare_feature_extractor, selected_ids
 from .components.models import get_diffusion_model
 
 
@@ -225,6 +225,9 @@ class FeatureExtractor(nn.Module):
                 check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
                                               _lib.ptr(time_ids), _lib.ptr(arena), None, st))
         feats = plan.views(arena)
+        if self.feature_store.resize_ratio > 1:                  # feature_extractor.py:51-53
+            with torch.cuda.device(pipe.dev_index):
+                feats = pool_views(lib, feats, self.feature_store.resize_ratio)
         if self.feature_store.accept_all:
             feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
         self.feature_store.feats = feats

@@ -29,10 +29,11 @@ class FeatureStore:
     """feature/components/feature_extractor.py:8-80 with train_unet=True semantics (no fp16 / cuda cast), so
     the oracle returns fp32 maps. Filtering, cross-k/v drop, (b (h w) c -> b c h w) and insertion order kept."""
 
-    def __init__(self, to_store):
+    def __init__(self, to_store, resize_ratio=1):
         self.to_store = dict(to_store) if to_store else {}
         self.accept_all = not to_store
         self.feats = {}
+        self.resize_ratio = resize_ratio
 
     def reset(self):
         self.feats = {}
@@ -44,6 +45,8 @@ class FeatureStore:
             if feat.dim() == 3:                                  # :46-48
                 size = int(math.sqrt(feat.shape[1]))
                 feat = feat.reshape(feat.shape[0], size, size, feat.shape[2]).permute(0, 3, 1, 2)
+            if self.resize_ratio > 1:                            # :51-53
+                feat = F.adaptive_avg_pool2d(feat, (feat.shape[2] // self.resize_ratio, feat.shape[3] // self.resize_ratio))
             self.feats[feat_id] = feat.detach().clone()          # TF.normalize(mean=0,std=1) is an identity clone :56
 
     @property

@@ -119,6 +119,19 @@ def test_flux_host_logic_matches_oracle():
         schedulers.resolve("flux", 0, 1024)          # strength 0 leaves no step (pipeline_flux_img2img.py:768-772)
 
 
+def test_oracle_feature_resize_matches_reference_store():
+    """tests/golden/feature_store_resize.pt: the reference's real FeatureStore.store with resize_ratio 2 and 3
+    (feature_extractor.py:51-53, adaptive_avg_pool2d; 3 does not divide the 16 x 16 maps)."""
+    gold = torch.load(os.path.join(GOLD, "feature_store_resize.pt"), weights_only=False)
+    for r in (2, 3):
+        st = O.FeatureStore({"a": True, "b": True}, r)
+        st.store(gold["conv"], "a")
+        st.store(gold["vit"], "b")
+        for k in ("a", "b"):
+            assert st.feats[k].shape == gold["r%d" % r][k].shape == (2, gold["conv"].shape[1] if k == "a" else 128, 16 // r, 16 // r)
+            assert torch.allclose(st.feats[k], gold["r%d" % r][k], atol=1e-6)
+
+
 def test_dit_param_specs_and_pos_embed_match_oracle():
     m = _models()
     for ver in ("pixart-sigma", "pixart-sigma-512"):

@@ -201,6 +201,31 @@ def test_cuda_matches_reference_vendored_flux_golden(cuda_dev):
     assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
 
 
+def test_tiny_xl_feature_resize(cuda_dev):
+    """FeatureExtractor(..., feature_resize=2): every captured map average-pooled 2 x 2 (feature_extractor.py:51-53),
+    vs the oracle's FeatureStore with the same ratio."""
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    image, ctx, pooled, eps_vae, eps_q = make_inputs(2, 128, TINY_XL["ctx_dim"], 64)
+    ids = [i for i in _unet_feature_ids(TINY_XL) if i.endswith("-out") or "self-q" in i]
+    layer = {i: True for i in ids}
+    unet, vae = build_oracle(TINY_XL, TINY_VAE, sd)
+    store = O.FeatureStore(layer, resize_ratio=2)
+    O.attach_gatherers(unet, store)
+    want, _, _ = O.extract("xl", unet, vae, store, image, ctx, pooled, eps_vae, eps_q, t=50, img_size=128)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    fe = FeatureExtractor(layer, "xl", "cuda:0", img_size=128, feature_resize=2, external_model=pipe)
+    got = fe.extract((ctx, ctx, pooled, pooled), 2, image.cuda(), image_type="tensors", t=50, noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == list(want.keys())
+    assert got["unet-out"].shape == (2, 4, 8, 8)
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "pooled maps out of tolerance: %s" % bad[:8]
+
+
 def test_unknown_id_and_unbuilt_features(cuda_dev):
     from generic_diffusion_feature_b200._lib import GdfError
     from generic_diffusion_feature_b200.components import models

@@ -476,3 +476,25 @@ def test_conv_fused_groupnorm_stats(cuda_dev, C, G, HW, B):
     q_want = (wg * wg).sum(dim=(1, 3))
     assert torch.allclose(sums[..., 0], s_want, rtol=2e-3, atol=0.5), (sums[..., 0] - s_want).abs().max()
     assert torch.allclose(sums[..., 1], q_want, rtol=2e-3, atol=0.5), (sums[..., 1] - q_want).abs().max()
+
+
+@pytest.mark.parametrize("ratio", [2, 3])
+def test_feature_resize_pool_vs_reference_store(cuda_dev, ratio):
+    """gdf_op_avgpool_nhwc (through pool_views) vs the fixture written by the reference's real FeatureStore.store with
+    resize_ratio 2 / 3 (feature_extractor.py:51-53); inputs rounded to fp16 first, as the arena holds them."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import _lib
+    from generic_diffusion_feature_b200.components.feature_extractor import pool_views
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "feature_store_resize.pt"), weights_only=False)
+    conv = gold["conv"].half().cuda()                                   # (B, C, h, w)
+    vit = gold["vit"].half().cuda()                                     # (B, N, C) token-major
+    feats = {"a": conv.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2),
+             "b": vit.view(2, 16, 16, 128).permute(0, 3, 1, 2)}
+    got = pool_views(_lib.load(), feats, ratio)
+    torch.cuda.synchronize()
+    assert list(got.keys()) == ["a", "b"]
+    for k in ("a", "b"):
+        want = gold["r%d" % ratio][k]
+        assert got[k].shape == want.shape and got[k].dtype == torch.float16
+        assert (got[k].float().cpu() - want).abs().max().item() < 4e-3

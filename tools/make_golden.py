@@ -205,6 +205,30 @@ def golden_flux(name="flux_tiny.pt"):
                os.path.join(OUT, name))
 
 
+def golden_store_resize(name="feature_store_resize.pt"):
+    """feature_resize: the reference's REAL FeatureStore.store (feature/components/feature_extractor.py:31-76,
+    adaptive_avg_pool2d at :51-53) on seeded conv-style (B,C,h,w) and ViT-style (B,N,C) activations, ratios 2 and 3
+    (3 does not divide 16: uneven adaptive windows)."""
+    rfe = ref_shim.load_reference_feature_extractor()
+    g = torch.Generator().manual_seed(77)
+    conv = torch.randn(2, 64, 16, 16, generator=g)
+    vit = torch.randn(2, 256, 128, generator=g)
+    out = {"conv": conv, "vit": vit}
+    for r in (2, 3):
+        st = rfe.FeatureStore({"a": True, "b": True}, r, True)
+        st.store(conv, "a")
+        st.store(vit, "b")
+        out["r%d" % r] = {k: v.clone() for k, v in st.stored_feats.items()}
+        ost = O.FeatureStore({"a": True, "b": True}, r)
+        ost.store(conv, "a")
+        ost.store(vit, "b")
+        for k in ("a", "b"):
+            assert torch.allclose(ost.feats[k], out["r%d" % r][k], atol=1e-6), (r, k)
+    out["generator"] = "tools/make_golden.py (reference FeatureStore.store)"
+    torch.save(out, os.path.join(OUT, name))
+    print("%s: reference FeatureStore.store with resize_ratio 2 / 3; oracle identical" % name)
+
+
 def golden_correspondence():
     cu = ref_shim.load_reference_correspondence_utils()
     g = torch.Generator().manual_seed(99)
@@ -266,5 +290,6 @@ if __name__ == "__main__":
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
     golden_dit()
     golden_flux()
+    golden_store_resize()
     golden_correspondence()
     golden_extract()
