@@ -243,10 +243,40 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
     }
   }
 }
+// one warp per output ELEMENT (b, n): most parallelism, weights re-read per batch row (fine while they sit in L2)
+__global__ void small_linear_elem_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                         const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
+                                         int act_in_silu, int act_out_silu) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (long long)B * N) return;
+  const int b = (int)(o / N), n = (int)(o % N);
+  const float* xr = x + (long long)b * K;
+  const float* wr = W + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = xr[k];
+    if (act_in_silu) xv = xv / (1.f + expf(-xv));
+    acc += xv * __ldg(wr + k);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float r = acc + (bias ? bias[n] : 0.f);
+    if (act_out_silu) r = r / (1.f + expf(-r));
+    y[o] = r;
+  }
+}
 cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
                                 int act_in_silu, int act_out_silu, cudaStream_t stream) {
+  if ((long long)N * K * 4 <= (32ll << 20)) {   // L2-resident weights (time / text embedding MLPs): favour parallelism
+    const long long outs = (long long)B * N;
+    small_linear_elem_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, stream>>>(x, W, b, y, B, K, N, act_in_silu,
+                                                                            act_out_silu);
+    return cudaGetLastError();
+  }
   const unsigned blocks = (unsigned)((N + 7) / 8);
-  for (int b0 = 0; b0 < B; b0 += 8) {   // 8 batch rows per pass over the weights
+  for (int b0 = 0; b0 < B; b0 += 8) {   // weight streaming (Flux modulation projections): 8 batch rows per pass
     const int nb = B - b0;
     if (nb == 1)
       small_linear_kernel<1><<<blocks, 256, 0, stream>>>(x, W, b, y, b0, B, K, N, act_in_silu, act_out_silu);

@@ -399,9 +399,36 @@ __global__ void adaptive_avgpool_nhwc_kernel(const __half* __restrict__ x, __hal
     *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + c) = o;
   }
 }
+// same, one channel per thread (maps whose channel count is not a multiple of 8: unet-in / unet-out, 4 channels)
+__global__ void adaptive_avgpool_nhwc_scalar_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H,
+                                                    int W, int C, int OH, int OW) {
+  const long long total = (long long)B * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const int y0 = (oy * H) / OH, y1 = ((oy + 1) * H + OH - 1) / OH;
+    const int x0 = (ox * W) / OW, x1 = ((ox + 1) * W + OW - 1) / OW;
+    float acc = 0.f;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) acc += __half2float(x[(((long long)b * H + yy) * W + xx) * C + c]);
+    y[i] = __float2half_rn(acc / (float)((y1 - y0) * (x1 - x0)));
+  }
+}
 cudaError_t launch_adaptive_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int OH, int OW,
                                          cudaStream_t stream) {
-  if (C % 8 != 0 || OH < 1 || OW < 1 || OH > H || OW > W) return cudaErrorInvalidValue;
+  if (OH < 1 || OW < 1 || OH > H || OW > W || C < 1) return cudaErrorInvalidValue;
+  if (C % 8 != 0) {
+    const long long tot = (long long)B * OH * OW * C;
+    const long long blk = (tot + 255) / 256;
+    adaptive_avgpool_nhwc_scalar_kernel<<<(unsigned)(blk < 148 * 32 ? (blk < 1 ? 1 : blk) : 148 * 32), 256, 0, stream>>>(
+        x, y, B, H, W, C, OH, OW);
+    return cudaGetLastError();
+  }
   const long long total = (long long)B * OH * OW * (C >> 3);
   const long long blocks = (total + 255) / 256;
   adaptive_avgpool_nhwc_kernel<<<(unsigned)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32), 256, 0, stream>>>(

@@ -280,7 +280,7 @@ int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, i
                          void* out_nchw_dev, void* sumsq_dev, void* stream);
 
 /* feature_resize (FeatureStore.store, feature/components/feature_extractor.py:51-53): F.adaptive_avg_pool2d of one
- * captured map, fp16 NHWC [B, H*W, C] -> [B, OH*OW, C] (OH = H // resize_ratio). C % 8 == 0. */
+ * captured map, fp16 NHWC [B, H*W, C] -> [B, OH*OW, C] (OH = H // resize_ratio). */
 int gdf_op_avgpool_nhwc(const void* x_dev, void* y_dev, int B, int H, int W, int C, int OH, int OW, void* stream);
 
 /* Correspondence (correspondence/correspondence/correspondence_utils.py:113-146 find_nn_source_correspondences):
