@@ -108,6 +108,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner through
+    NCCL_DEBUG_FILE = stdout when the box sets NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the
+    whole run and the JSON line is written to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,7 +186,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local):
@@ -297,7 +321,7 @@ def run_ours(args, rank, world, local):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -320,6 +344,7 @@ def main():
     ap.add_argument("--profile-csv", default=None, help="write the per-launch table of the profiling pass here")
     args = ap.parse_args()
     rank, world, local = dist_env()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
