@@ -337,8 +337,13 @@ template <bool kF16>
 __device__ __forceinline__ void store_round(const CUtensorMap* map_a, int col_a, const CUtensorMap* map_b, int col_b,
                                             bool two, uint8_t* stg_warp, int& toggle, int lane, const int (&swz)[4],
                                             const float* v0, const float* v1, const StoreCoord& sc) {
-  uint8_t* buf = stg_warp + toggle * 4096;
-  if (elect_one()) bulk_wait_read<1>();
+  // toggle: bit 0 = buffer pair in use, bit 1 set = this launch has ONE staging round per warp (32 KB of staging
+  // instead of 64 KB; the operand ring gets the difference): the previous round must have been read out entirely
+  uint8_t* buf = stg_warp + (toggle & 1) * 4096;
+  if (elect_one()) {
+    if (toggle & 2) bulk_wait_read<0>();
+    else bulk_wait_read<1>();
+  }
   __syncwarp();
   stage_chunk<kF16>(buf, swz, v0);
   if (two) stage_chunk<kF16>(buf + 2048, swz, v1);
@@ -353,7 +358,7 @@ __device__ __forceinline__ void store_round(const CUtensorMap* map_a, int col_a,
     }
     bulk_commit();
   }
-  toggle ^= 1;
+  if (!(toggle & 2)) toggle ^= 1;
 }
 
 struct ResidualRegs { uint4 u[4]; };
@@ -451,10 +456,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_rows = p.block_n / CG;                         // B rows staged by this CTA
   const int stage_bytes = kStageBytesA + b_rows * kBlockK * 2;
-  uint8_t* stg = smem;                                      // [epilogue warp][4][32 rows][64 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagingBytes);
-  uint8_t* res_stg = smem + kStagingBytes + kBarrierBytes;  // [epilogue warp][2 halves][32 rows][64 B] (res_tma only)
-  smem += kStagingBytes + kBarrierBytes + (p.res_tma ? kResBytes : 0);   // operand ring
+  uint8_t* stg = smem;                                      // [epilogue warp][2 * stg_rounds][32 rows][64 B]
+  const int stg_bytes = p.stg_rounds * (kStagingBytes / 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stg_bytes);
+  uint8_t* res_stg = smem + stg_bytes + kBarrierBytes;      // [epilogue warp][2 halves][32 rows][64 B] (res_tma only)
+  smem += stg_bytes + kBarrierBytes + (p.res_tma ? kResBytes : 0);   // operand ring (takes whatever staging leaves)
   uint64_t* full_bar = bars;                                 // [kMaxStages]  (CG = 2: the leader's are used)
   uint64_t* empty_bar = bars + kMaxStages;                   // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;               // [kMaxAccStages]
@@ -644,8 +650,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     constexpr bool geglu = kGeglu;   // host dispatch: p.act == kActGeglu
     const int ncols_out = p.n_out;
     const int out_tile_w = geglu ? p.block_n / 2 : p.block_n;
-    uint8_t* stg_warp = stg + e * 8192;   // 4 staging buffers of 2 KB per warp
-    int toggle = 0;
+    uint8_t* stg_warp = stg + e * (4096 * p.stg_rounds);   // 2 staging buffers of 2 KB per round and warp
+    int toggle = p.stg_rounds == 1 ? 2 : 0;
     int swz[4];   // byte offsets of this lane's four 16 B pieces in a [32 rows][64 B] SWIZZLE_64B staging buffer
 #pragma unroll
     for (int c = 0; c < 4; ++c) swz[c] = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);

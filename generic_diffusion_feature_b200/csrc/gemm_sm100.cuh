@@ -44,6 +44,7 @@ struct GemmParams {
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;
+  int stg_rounds;       // epilogue staging rounds in flight per warp: 2 (64 KB of staging) or 1 (32 KB, deeper ring)
   int acc_stages;       // 2 or 4 (see kMaxAccStages)
   int n_fastest;        // 1: consecutive work units walk the n-tiles of one m unit first (see decode_unit)
   int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)

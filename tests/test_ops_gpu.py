@@ -212,6 +212,43 @@ def test_conv3x3(cuda_dev, B, H, W, Cin, Cout, stride, pad_lo):
     check_close(got, want, what="conv3x3 B%d %dx%d %d->%d s%d p%d" % (B, H, W, Cin, Cout, stride, pad_lo))
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(1, 128, 320, 320), (2, 64, 640, 640), (1, 128, 960, 320)])
+def test_conv3x3_resnet_epilogue_long_k(cuda_dev, B, H, Cin, Cout):
+    """The second conv of a UNet resnet at its real shapes (K = 9 Cin >= 45 k-blocks: the deep-ring / single staging
+    round configuration): per-sample row bias (time embedding), residual, `increment` capture before the residual,
+    `out` capture after it, second bf16 destination (skip-concat slice) - every destination against torch."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = _rand_bf16(g, B, Cin, H, H)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, device="cuda") * (9 * Cin) ** -0.5
+    bias = torch.randn(Cout, generator=g, device="cuda")
+    rbb = torch.randn(B, Cout, generator=g, device="cuda")
+    res = _rand_bf16(g, B * H * H, Cout)
+    wq = w.to(torch.bfloat16).float()
+    pre = F.conv2d(x.float(), wq, bias, padding=1) + rbb[:, :, None, None]
+    pre = pre.permute(0, 2, 3, 1).reshape(B * H * H, Cout)
+    want = pre + res.float()
+    wp = ops.pack_conv_weight(w)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(B * H * H, Cout, dtype=torch.bfloat16, device="cuda")
+    cat = torch.zeros(B * H * H, Cout + 64, dtype=torch.bfloat16, device="cuda")
+    cap_pre = torch.zeros(B * H * H, Cout, dtype=torch.float16, device="cuda")
+    cap = torch.zeros(B * H * H, Cout, dtype=torch.float16, device="cuda")
+    ep = ops.make_epilogue(out=out, bias=bias, row_batch_bias=rbb, rows_per_batch=H * H, residual=res, out2=cat[:, 64:],
+                           cap_pre=cap_pre, caps=[(cap, 0, Cout)])
+    ops.conv3x3(x_nhwc, wp, ep)
+    torch.cuda.synchronize()
+    what = "resnet conv B%d %dx%d %d->%d" % (B, H, H, Cin, Cout)
+    check_close(cap_pre, pre, what=what + " increment capture")
+    check_close(out, want, what=what + " out")
+    check_close(cap, want, what=what + " out capture")
+    check_close(cat[:, 64:], want, what=what + " concat slice")
+    assert float(cat[:, :64].abs().max()) == 0.0
+    for name, t in (("out", out), ("out capture", cap)):      # sparse corruption hides in an L2 norm
+        worst = float((t.float() - want).abs().max() / want.abs().max())
+        assert worst < 3e-2, "%s %s: max-relative error %.3e" % (what, name, worst)
+
+
 @pytest.mark.parametrize("B,HW,C,silu", [(2, 64 * 64, 320, True), (3, 32 * 32, 1920, True), (2, 128 * 128, 128, True),
                                          (1, 16 * 16, 2560, False), (2, 1024, 960, True), (2, 77, 640, True)])
 def test_groupnorm(cuda_dev, B, HW, C, silu):
