@@ -118,3 +118,66 @@ def compare_maps(got, want):
         maxrel = ((gf - wf).abs().max() / (wf.abs().max() + 1e-12)).item()
         rows.append((k, cos, rel, maxrel))
     return rows
+
+
+# ------------------------------------------------------------------------------------------ CLI / on-disk format helpers
+# (shared by tools/make_golden.py, which runs the reference's own extract_feature.py on them, and tests/test_cpu.py)
+import numpy as np  # noqa: E402
+
+
+def cli_fixture_inputs(root):
+    """Six solid-colour PNGs in two folders (red channel = image index) + a prompt file; shared with tests/test_cpu.py."""
+    from PIL import Image
+    paths = []
+    for i in range(6):
+        d = os.path.join(root, "imgs", "cat" if i < 3 else "dog")
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, "im%d.png" % i)
+        Image.new("RGB", (40, 24), (10 * i + 5, 0, 0)).save(p)
+        paths.append(p)
+    with open(os.path.join(root, "prompt.txt"), "w") as f:
+        f.write("a photo")
+    return paths
+
+
+class FakeExtractor:
+    """Stands in for FeatureExtractor under the CLI: maps whose values depend only on the image (red channel)."""
+    LAYERS = (("up-level1-repeat1-vit-block0-self-q", 6, 8), ("mid-vit-out", 4, 4), ("unet-out", 2, 16))
+
+    def __init__(self, *a, **k):
+        self.feature_store = type("S", (), {"accept_all": False})()
+
+    def encode_prompt(self, p):
+        return p
+
+    def extract(self, prompts, n, images, t=None, **kw):
+        out = {}
+        for name, c, hw in self.LAYERS:
+            rows = []
+            for im in images:
+                idx = im.convert("RGB").getpixel((0, 0))[0]
+                g = torch.Generator().manual_seed(1000 + idx)
+                rows.append(torch.randn(c, hw, hw, generator=g))
+            out[name] = torch.stack(rows).to(torch.float16)
+        return out
+
+
+CLI_MODES = {
+    "default": ["--split", "val"],
+    "sample_first_original": ["--sample_name_first", "--use_original_filename"],
+    "aggregate_nested": ["--aggregate_output", "--use_original_filename", "--nested_input_dir"],
+}
+
+
+def tree_digest(root):
+    import hashlib
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            p = os.path.join(d, f)
+            a = np.load(p)
+            out[os.path.relpath(p, root)] = {"shape": list(a.shape), "dtype": str(a.dtype),
+                                             "sha1": hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()}
+    return out
+
+

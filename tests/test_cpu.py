@@ -132,6 +132,24 @@ def test_oracle_feature_resize_matches_reference_store():
             assert torch.allclose(st.feats[k], gold["r%d" % r][k], atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", ["default", "sample_first_original", "aggregate_nested"])
+def test_cli_on_disk_format_matches_reference(mode, tmp_path):
+    """tests/golden/cli_layouts.json holds the file trees (paths, shapes, dtypes, content hashes) the reference's OWN
+    extract_feature.py main() wrote for three flag combinations on a stand-in extractor (tools/make_golden.py);
+    generic_diffusion_feature_b200.extract_feature must write byte-identical arrays at identical paths."""
+    from common import CLI_MODES, FakeExtractor, cli_fixture_inputs, tree_digest
+    from generic_diffusion_feature_b200 import extract_feature as cli
+    gold = json.load(open(os.path.join(GOLD, "cli_layouts.json")))[mode]
+    root = str(tmp_path)
+    cli_fixture_inputs(root)
+    od = os.path.join(root, "out")
+    argv = ["--layer", "x.json", "--t", "50", "-b", "4", "--input_dir", os.path.join(root, "imgs", "*", "*.png"),
+            "--prompt_file", os.path.join(root, "prompt.txt"), "--output_dir", od, "--writer_threads", "3"] + CLI_MODES[mode]
+    n = cli.run(cli.build_parser().parse_args(argv), extractor=FakeExtractor())
+    assert n == 6
+    assert tree_digest(od) == gold
+
+
 def test_dit_param_specs_and_pos_embed_match_oracle():
     m = _models()
     for ver in ("pixart-sigma", "pixart-sigma-512"):

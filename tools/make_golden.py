@@ -33,7 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import ref_shim  # noqa: E402
-from common import (O, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,  # noqa: E402
+from common import (CLI_MODES, FakeExtractor, cli_fixture_inputs, tree_digest,  # noqa: E402
+                    O, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,  # noqa: E402
                     build_oracle_dit, build_oracle_flux, make_dit_inputs, make_flux_inputs, make_inputs)
 from generic_diffusion_feature_b200.components import models  # noqa: E402
 from generic_diffusion_feature_b200.components.feature_extractor import (_dit_feature_ids, _flux_feature_ids,  # noqa: E402
@@ -229,6 +230,40 @@ def golden_store_resize(name="feature_store_resize.pt"):
     print("%s: reference FeatureStore.store with resize_ratio 2 / 3; oracle identical" % name)
 
 
+def golden_cli(name="cli_layouts.json"):
+    """On-disk format: the reference's OWN extract_feature.py main() (argument parsing, naming, directory layout,
+    aggregation with F.interpolate + cat, np.save) executed on a stand-in FeatureExtractor; the file trees (paths,
+    shapes, dtypes, content hashes) of three flag combinations are the fixture."""
+    import importlib.util
+    import json
+    import tempfile
+    import types
+    fake_mod = types.ModuleType("diffusion_feature")
+    fake_mod.FeatureExtractor = FakeExtractor
+    sys.modules["diffusion_feature"] = fake_mod
+    spec = importlib.util.spec_from_file_location("ref_extract_feature", os.path.join(ref_shim.REF, "extract_feature.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        cli_fixture_inputs(root)
+        for mode, flags in CLI_MODES.items():
+            od = os.path.join(root, "out_" + mode)
+            argv = ["extract_feature.py", "--layer", "x.json", "--t", "50", "-b", "4", "--input_dir",
+                    os.path.join(root, "imgs", "*", "*.png"), "--prompt_file", os.path.join(root, "prompt.txt"),
+                    "--output_dir", od] + flags
+            old = sys.argv
+            sys.argv = argv
+            try:
+                ref.main()
+            finally:
+                sys.argv = old
+            out[mode] = tree_digest(od)
+    del sys.modules["diffusion_feature"]
+    json.dump(out, open(os.path.join(OUT, name), "w"), indent=0, sort_keys=True)
+    print("%s: %s files" % (name, {k: len(v) for k, v in out.items()}))
+
+
 def golden_correspondence():
     cu = ref_shim.load_reference_correspondence_utils()
     g = torch.Generator().manual_seed(99)
@@ -291,5 +326,6 @@ if __name__ == "__main__":
     golden_dit()
     golden_flux()
     golden_store_resize()
+    golden_cli()
     golden_correspondence()
     golden_extract()
