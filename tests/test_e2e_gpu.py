@@ -59,6 +59,11 @@ def test_tiny_xl_batch3_img256(cuda_dev):
               subset=lambda i: i.endswith("-out") or "cross-q" in i or "ffn-inner" in i)
 
 
+def test_tiny_xl_batch5(cuda_dev):
+    """Odd batch whose 4x4 / 8x8 maps pack several images into one 128-row GEMM tile with a partial last tile."""
+    _run_case("xl", TINY_XL, batch=5, img=128)
+
+
 def test_tiny_21_full_set(cuda_dev):
     _run_case("2-1", TINY_21, batch=2, img=128)
 
@@ -224,6 +229,56 @@ def test_tiny_xl_feature_resize(cuda_dev):
     rows = compare_maps(got, want)
     bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
     assert not bad, "pooled maps out of tolerance: %s" % bad[:8]
+
+
+def test_cli_extract_to_npy(cuda_dev, tmp_path):
+    """extract_feature CLI end to end on the GPU (reduced SDXL topology): PNG files -> prefetch thread -> extract ->
+    asynchronous pinned D2H -> writer pool; every .npy equals the map `extract` returns for the same image, in the
+    reference's layout <output_dir>/<layer>/<split><index>.npy (extract_feature.py:131-147)."""
+    import os
+    import numpy as np
+    from PIL import Image
+    from generic_diffusion_feature_b200 import extract_feature as cli
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "imgs"))
+    g = torch.Generator().manual_seed(3)
+    for i in range(5):
+        arr = (torch.rand(96, 128, 3, generator=g) * 255).to(torch.uint8).numpy()
+        Image.fromarray(arr).save(os.path.join(root, "imgs", "p%d.png" % i))
+    open(os.path.join(root, "prompt.txt"), "w").write("")
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    layer = {"mid-vit-out": True, "up-level1-repeat0-vit-block0-self-q": True, "unet-out": True}
+    fe = FeatureExtractor(layer, "xl", "cuda:0", img_size=128, external_model=pipe)
+    # the un-seeded noise draws of the reference (pipeline_pixart_sigma.py:644,671) are fixed here so that two calls agree
+    noise_for = lambda n: (torch.zeros(n, 4, 16, 16), torch.zeros(n, 4, 16, 16))
+    orig = fe.extract
+    fe.extract = lambda prompts, n, image, **kw: orig(prompts, n, image, noise=noise_for(n),
+                                                      **{k: v for k, v in kw.items() if k in ("t", "image_type")})
+    od = os.path.join(root, "out")
+    args = cli.build_parser().parse_args(["--layer", "unused", "--version", "xl", "--img_size", "128", "--t", "50", "-b", "2",
+                                          "--input_dir", os.path.join(root, "imgs", "*.png"), "--prompt_file",
+                                          os.path.join(root, "prompt.txt"), "--output_dir", od, "--split", "val"])
+    assert cli.run(args, extractor=fe) == 5
+    files = sorted(os.listdir(os.path.join(od, "mid-vit-out")))
+    assert files == ["val%d.npy" % i for i in range(5)] and sorted(os.listdir(od)) == sorted(layer.keys())
+    prompts = fe.encode_prompt("")
+    imgs = [Image.open(os.path.join(root, "imgs", "p%d.png" % i)) for i in range(5)]
+    for first in (0, 2, 4):                       # the CLI's own batch partition (-b 2)
+        part = imgs[first:first + 2]
+        want = {k: v.float().cpu().numpy() for k, v in orig(prompts, len(part), part, t=50, noise=noise_for(len(part))).items()}
+        for k in layer:
+            for j in range(len(part)):
+                a = np.load(os.path.join(od, k, "val%d.npy" % (first + j)))
+                w = want[k][j]
+                assert a.dtype == np.float16 and a.shape == w.shape
+                # two runs of the same image agree to bf16 rounding noise only (GroupNorm statistics are summed with
+                # atomics, so the last bits of mean / variance depend on the schedule): cosine, not bit equality
+                af, wf = a.astype(np.float64).ravel(), w.astype(np.float64).ravel()
+                cos = float(af @ wf / (np.linalg.norm(af) * np.linalg.norm(wf) + 1e-30))
+                assert cos >= COS_MIN, (k, first + j, cos)
 
 
 def test_unknown_id_and_unbuilt_features(cuda_dev):
