@@ -185,15 +185,17 @@ class HostStager:
         return {k: v.numpy() for k, v in views.items()}
 
 
-def prefetch_images(dataset, batch_size, img_size, depth=2):
-    """Generator of (first_index, [PIL images resized to img_size]) decoded by a background thread."""
+def prefetch_images(dataset, batch_size, img_size, depth=2, start=0, stop=None):
+    """Generator of (first_index, [PIL images resized to img_size]) decoded by a background thread, over the
+    [start, stop) shard of the dataset (indices stay global: they name the output files)."""
     from PIL import Image
     q = queue.Queue(maxsize=depth)
+    stop = len(dataset) if stop is None else stop
 
     def work():
-        for i in range(0, len(dataset), batch_size):
+        for i in range(start, stop, batch_size):
             imgs = [Image.open(dataset[j][0]).resize((img_size, img_size)).convert("RGB")
-                    for j in range(i, min(i + batch_size, len(dataset)))]
+                    for j in range(i, min(i + batch_size, stop))]
             q.put((i, imgs))
         q.put(None)
     threading.Thread(target=work, daemon=True).start()
@@ -204,8 +206,18 @@ def prefetch_images(dataset, batch_size, img_size, depth=2):
         yield item
 
 
+def shard_of_this_rank(n_items):
+    """Multi-GPU runs (one process per GPU, e.g. torchrun): every rank extracts its own contiguous shard of the input
+    list into the shared output tree - images are independent, so there is no collective (parallel.shard_range)."""
+    from .parallel import shard_range
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    return shard_range(n_items, rank, world) if world > 1 else (0, n_items)
+
+
 def run(args, extractor=None):
     from .diffusion_feature import FeatureExtractor
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.device == 'cuda':
+        args.device = 'cuda:%d' % int(os.environ.get("LOCAL_RANK", "0"))
     os.makedirs(args.output_dir, exist_ok=True)
     print(f'Run folder: {args.output_dir}')
     if args.show_all_layers:
@@ -224,7 +236,8 @@ def run(args, extractor=None):
     in_flight = None                           # (staged copy, first index, count) of the previous batch
     n_done = 0
     with torch.no_grad():
-        for first, imgs in prefetch_images(dataset, args.batch_size, args.img_size):
+        lo, hi = shard_of_this_rank(len(dataset))
+        for first, imgs in prefetch_images(dataset, args.batch_size, args.img_size, start=lo, stop=hi):
             features = df.extract(prompts, len(imgs), imgs, t=args.t, denoising_from=args.denoising_from,
                                   use_control=args.control is not None, use_ddim_inversion=args.use_ddim_inversion)
             if args.show_all_layers:             # debug mode of the reference (:100-108)

@@ -150,6 +150,26 @@ def test_cli_on_disk_format_matches_reference(mode, tmp_path):
     assert tree_digest(od) == gold
 
 
+def test_cli_two_rank_shards_write_the_same_tree(tmp_path, monkeypatch):
+    """Two ranks (RANK / WORLD_SIZE as torchrun sets them) each extract their contiguous shard into one output tree:
+    together they produce exactly the single-process tree of the reference (global indices name the files)."""
+    from common import CLI_MODES, FakeExtractor, cli_fixture_inputs, tree_digest
+    from generic_diffusion_feature_b200 import extract_feature as cli
+    gold = json.load(open(os.path.join(GOLD, "cli_layouts.json")))["default"]
+    root = str(tmp_path)
+    cli_fixture_inputs(root)
+    od = os.path.join(root, "out")
+    argv = ["--layer", "x.json", "--t", "50", "-b", "2", "--input_dir", os.path.join(root, "imgs", "*", "*.png"),
+            "--prompt_file", os.path.join(root, "prompt.txt"), "--output_dir", od, "--device", "cpu"] + CLI_MODES["default"]
+    counts = []
+    for rank in range(2):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("WORLD_SIZE", "2")
+        counts.append(cli.run(cli.build_parser().parse_args(argv), extractor=FakeExtractor()))
+    assert counts == [3, 3]
+    assert tree_digest(od) == gold
+
+
 def test_dit_param_specs_and_pos_embed_match_oracle():
     m = _models()
     for ver in ("pixart-sigma", "pixart-sigma-512"):
