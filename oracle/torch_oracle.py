@@ -185,9 +185,76 @@ class Attention(nn.Module):
         q = q.view(B, -1, self.heads, d).transpose(1, 2)
         k = k.view(B, -1, self.heads, d).transpose(1, 2)
         v = v.view(B, -1, self.heads, d).transpose(1, 2)
-        o = F.scaled_dot_product_attention(q, k, v)
+        proc = getattr(self, "attn_store_processor", None)
+        if proc is None:
+            o = F.scaled_dot_product_attention(q, k, v)
+        else:
+            # AttnStoreProcessor (feature/components/attention.py:165-263): explicit probabilities
+            # softmax(scale * Q K^T) (get_attention_scores, attention_processor.py:640-685), head-mean handed to the
+            # AttentionStore (:241-242), the (B, heads, Nq, Nk) tensor gathered as `map` (:243-244), then P V (:247)
+            attnstore, place = proc
+            probs = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, dim=-1)
+            if attnstore is not None:
+                attnstore(probs.mean(1), ctx is not x, place)
+            _gather(self, probs, "map")
+            o = probs @ v
         o = o.transpose(1, 2).reshape(B, -1, C)
         return self.to_out[0](o)
+
+
+class AttentionStore:
+    """feature/components/attention.py:102-161 (only what one forward uses): head-mean maps whose query count lies in
+    [min_size^2, max_size^2] are kept per "<place>_<cross|self>" category; aggregate_attention groups the maps of the
+    selected categories by size, (b (h w) c -> b c h w), and averages each group."""
+
+    KEYS = ("down_cross", "mid_cross", "up_cross", "down_self", "mid_self", "up_self")
+
+    def __init__(self, min_size=32, max_size=64):
+        self.min_size, self.max_size = min_size, max_size
+        self.reset()
+
+    def reset(self):
+        self.step_store = {k: [] for k in self.KEYS}
+
+    def __call__(self, attn, is_cross, place_in_unet):
+        key = "%s_%s" % (place_in_unet, "cross" if is_cross else "self")
+        if self.min_size ** 2 <= attn.shape[1] <= self.max_size ** 2:
+            self.step_store[key].append(attn.detach())
+        return attn
+
+    def aggregate_attention(self, attn_selector):
+        attns = {key: {} for key in attn_selector}
+        for k in attn_selector:
+            for a in self.step_store[k]:
+                size = int(math.sqrt(a.shape[1]))
+                r = a.reshape(a.shape[0], size, size, a.shape[2]).permute(0, 3, 1, 2)
+                attns[k].setdefault(size, []).append(r)
+            for size, a in attns[k].items():
+                attns[k][size] = torch.stack(a).mean(0)
+        return attns
+
+
+def register_attention_store(unet, img_size, processor_only=False):
+    """register_attention_store, UNet branch (feature/components/attention.py:531-566): every attention module of the
+    down / mid / up blocks gets the storing processor; AttentionStore(img_size // 32, img_size // 16)."""
+    store = None if processor_only else AttentionStore(img_size // 32, img_size // 16)
+    for place, blocks in (("down", unet.down_blocks), ("mid", [unet.mid_block]), ("up", unet.up_blocks)):
+        for blk in blocks:
+            for vit in (getattr(blk, "attentions", None) or []):
+                for tb in vit.transformer_blocks:
+                    tb.attn1.attn_store_processor = (store, place)
+                    tb.attn2.attn_store_processor = (store, place)
+    return store
+
+
+def aggregated_attention_feature(store, categories, img_size):
+    """diffusion_feature.py:488-500: every (category, size) mean map nearest-resized to (img/8, img/8), concatenated
+    on the channel axis (key index of the attention) -> the `attn` entry of the returned dict."""
+    all_attns = []
+    for category, maps in store.aggregate_attention(categories).items():
+        for size, attn in maps.items():
+            all_attns.append(F.interpolate(attn, size=(img_size // 8, img_size // 8)))
+    return torch.cat(all_attns, dim=-3)
 
 
 class GEGLU(nn.Module):

@@ -46,6 +46,31 @@ def test_oracle_matches_reference_vendored_unet(fixture, version, cfg):
         assert (got - ref).abs().max().item() <= tol, k
 
 
+def test_oracle_attention_maps_match_reference_processor():
+    """tests/golden/unet_tiny_xl_maps.pt (oracle side): the reference's real AttnStoreProcessor /
+    AttentionStore / register_attention_store on its vendored UNet - every `...-self-map` / `...-cross-map`
+    (B, heads, Nq, Nk), the id order with the maps interleaved, and the aggregated `attn` feature of
+    diffusion_feature.py:488-500."""
+    gold = torch.load(os.path.join(GOLD, "unet_tiny_xl_maps.pt"), weights_only=False)
+    sd = _models().synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    unet, _ = build_oracle(TINY_XL, TINY_VAE, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers(unet, store)
+    ast = O.register_attention_store(unet, gold["img"])
+    with torch.no_grad():
+        unet(gold["x"], gold["timestep"], gold["ctx"], text_embeds=gold["pooled"], time_ids=O.add_time_ids(gold["img"]))
+    assert list(store.feats.keys()) == gold["ids"] and len(gold["map_ids"]) == 34
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+    m = store.feats["mid-vit-block0-cross-map"]
+    assert m.dim() == 4 and m.shape[1] == TINY_XL["heads"][-1] and m.shape[-1] == 77
+    assert torch.allclose(m.sum(-1), torch.ones_like(m.sum(-1)), atol=1e-5)          # rows are probabilities
+    attn = O.aggregated_attention_feature(ast, gold["categories"], gold["img"])
+    assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
+
+
 def test_oracle_matches_reference_vendored_dit_blocks():
     """tests/golden/dit_tiny_pixart.pt: the reference's vendored BasicTransformerBlock (ada_norm_single) stack +
     its real prepare_feature_extractor PixArt branch (tools/make_golden.py); the oracle reproduces every map."""

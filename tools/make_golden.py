@@ -90,6 +90,69 @@ def golden_unet(version, cfg, name):
                os.path.join(OUT, name))
 
 
+def golden_unet_maps(name="unet_tiny_xl_maps.pt"):
+    """Attention-probability maps: the reference's REAL AttnStoreProcessor / AttentionStore /
+    register_attention_store (feature/components/attention.py:102-263, 531-566) installed on the vendored UNet, the
+    `...-self-map` / `...-cross-map` ids through the real FeatureStore, and the aggregated `attn` feature assembled
+    like diffusion_feature.py:488-500. The oracle must reproduce all of it."""
+    import torch.nn.functional as F
+    version, cfg, img = "xl", TINY_XL, 64
+    sd = models.synthetic_state_dict(version, "cpu", cfg, TINY_VAE)
+    ref_unet = ref_shim.build_reference_unet(cfg)
+    ref_unet.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("unet.")}, strict=True)
+    ref_unet.eval()
+    rfe = ref_shim.load_reference_feature_extractor()
+    rat = ref_shim.load_reference_attention_store()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.unet = ref_unet
+    base = _unet_feature_ids(cfg)
+    map_ids = []
+    for i in base:
+        if i.endswith("-self-q"):
+            map_ids.append(i[:-len("self-q")] + "self-map")
+        if i.endswith("-cross-q"):
+            map_ids.append(i[:-len("cross-q")] + "cross-map")
+    layer = {i: True for i in base + map_ids}
+    store = rfe.prepare_feature_extractor(version, pipe, layer, 1, True)
+    categories = ["up_cross", "down_self", "mid_cross"]
+    astore = rat.register_attention_store(version, pipe, img, True)
+    x, ctx, pooled = unet_inputs(cfg, L=img // 8)
+    tid = O.add_time_ids(img).repeat(x.shape[0], 1)
+    with torch.no_grad():
+        out = ref_unet(x, timestep=torch.tensor([50.0]), encoder_hidden_states=ctx, return_dict=False,
+                       added_cond_kwargs={"text_embeds": pooled, "time_ids": tid})[0]
+    feats = dict(store.stored_feats)
+    got_maps = [k for k in feats if k.endswith("-map")]
+    assert sorted(got_maps) == sorted(map_ids), (len(got_maps), len(map_ids))
+    all_attns = []
+    for category, maps in astore.aggregate_attention(categories).items():
+        for size, attn in maps.items():
+            all_attns.append(F.interpolate(attn, size=(img // 8, img // 8)))
+    attn_feat = torch.cat(all_attns, dim=-3)
+    # oracle
+    ounet, _ = build_oracle(cfg, TINY_VAE, sd)
+    ostore = O.FeatureStore(layer)
+    O.attach_gatherers(ounet, ostore)
+    oast = O.register_attention_store(ounet, img)
+    with torch.no_grad():
+        oout = ounet(x, 50.0, ctx, text_embeds=pooled, time_ids=tid)
+    assert list(ostore.feats.keys()) == list(feats.keys())
+    worst = max((feats[k] - ostore.feats[k]).abs().max().item() for k in feats)
+    oattn = O.aggregated_attention_feature(oast, categories, img)
+    print("%s: %d ids (%d maps) + aggregated attn %s from the reference's AttnStoreProcessor; oracle max |diff| %.2e "
+          "(attn %.2e, out %.2e)" % (name, len(feats), len(map_ids), tuple(attn_feat.shape), worst,
+                                     (attn_feat - oattn).abs().max().item(), (out - oout).abs().max().item()))
+    assert worst < 1e-4 and (attn_feat - oattn).abs().max().item() < 1e-5
+    torch.save({"ids": list(feats.keys()), "map_ids": map_ids, "categories": categories, "img": img, "x": x, "ctx": ctx,
+                "pooled": pooled, "timestep": 50.0, "attn": attn_feat,
+                "feats": {k: v.to(torch.float16) for k, v in feats.items()},
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference AttnStoreProcessor / AttentionStore)"},
+               os.path.join(OUT, name))
+
+
 def golden_dit(name="dit_tiny_pixart.pt"):
     """PixArt path: the reference's vendored BasicTransformerBlock (attention.py:469-592, norm_type
     'ada_norm_single', attention_bias, gelu-approximate FeedForward) + vendored Attention / AttnProcessor2_0 +
@@ -323,6 +386,7 @@ if __name__ == "__main__":
     golden_ids()
     golden_unet("xl", TINY_XL, "unet_tiny_xl.pt")
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
+    golden_unet_maps()
     golden_dit()
     golden_flux()
     golden_store_resize()

@@ -542,6 +542,23 @@ def load_reference_feature_extractor():
     return m
 
 
+def load_reference_attention_store():
+    """feature/components/attention.py (AttentionStore, AttnStoreProcessor, register_attention_store) executed from its
+    source file; its `from diffusers.models.attention_processor import ...` resolves to the vendored module loaded by
+    install()."""
+    root = install()
+    for alias, target in (("diffusers", PKG), ("diffusers.models", PKG + ".models"),
+                          ("diffusers.models.attention_processor", PKG + ".models.attention_processor")):
+        sys.modules.setdefault(alias, sys.modules[target])
+    if not hasattr(root.attention_processor, "AttnProcessor"):
+        raise RuntimeError("vendored attention_processor has no AttnProcessor")
+    path = os.path.join(REF, "feature", "components", "attention.py")
+    spec = importlib.util.spec_from_file_location("ref_components_attention", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 def load_reference_correspondence_utils():
     """correspondence/correspondence/correspondence_utils.py with a stub for its (unused here) matplotlib import."""
     for n in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors"):
