@@ -16,6 +16,45 @@ from .. import _lib
 from .._lib import Slot, check
 
 
+ATTN_MEAN_PREFIX = "#attnmean:"     # internal plan ids: head-mean attention probabilities of one attention module
+
+
+def attention_mean_ids(cfg, categories):
+    """Internal ids of the head-mean maps the reference's AttentionStore would receive for the selected categories
+    ('down_cross', 'up_self', ...; feature/components/attention.py:102-118, 531-566), execution order."""
+    ids = []
+    for i in _unet_feature_ids(cfg):
+        for kind in ("self", "cross"):
+            if i.endswith("-%s-q" % kind):
+                block = i[:-len("-%s-q" % kind)]
+                if "%s_%s" % (block.split("-")[0], kind) in categories:
+                    ids.append(ATTN_MEAN_PREFIX + block + "-" + kind)
+    return ids
+
+
+def aggregate_attention(means, categories, img_size):
+    """AttentionStore.aggregate_attention + the assembly of diffusion_feature.py:488-500 on the head-mean maps:
+    keep maps with (img/32)^2 <= Nq <= (img/16)^2 (attention.py:111-112, 541), group per category and size,
+    (b (h w) c -> b c h w), average each group, nearest-resize to (img/8, img/8), concatenate on the channel axis."""
+    import math
+    import torch.nn.functional as F
+    lo, hi = (img_size // 32) ** 2, (img_size // 16) ** 2
+    groups = {c: {} for c in categories}
+    for block, kind, t in means:
+        cat = "%s_%s" % (block.split("-")[0], kind)
+        if cat not in groups or not (lo <= t.shape[1] <= hi):
+            continue
+        size = int(math.sqrt(t.shape[1]))
+        r = t.reshape(t.shape[0], size, size, t.shape[2]).permute(0, 3, 1, 2)
+        groups[cat].setdefault(size, []).append(r)
+    parts = []
+    for cat in categories:
+        for size, maps in groups[cat].items():
+            m = torch.stack(maps).float().mean(0).to(torch.float16)
+            parts.append(F.interpolate(m, size=(img_size // 8, img_size // 8)))
+    return torch.cat(parts, dim=-3)
+
+
 def _unet_feature_ids(cfg, layers_per_block=2):
     """All non-`map` feature ids of a UNet in execution order (same grammar as feature_extractor.py:125-249;
     reproduces the 472 / 165 non-map ids of feature/configs/config_{xl,15}_full.json)."""
@@ -163,14 +202,30 @@ class FeaturePlan:
         out = []
         seen = set()
         for fid, off, C, H, W, order in self.slots:
-            if off < 0 or fid in seen:
+            if off < 0 or fid in seen or fid.startswith(ATTN_MEAN_PREFIX):
                 continue
             seen.add(fid)
             nbytes = self.batch * H * W * C * 2
-            t = arena[off:off + nbytes].view(torch.float16).view(self.batch, H, W, C).permute(0, 3, 1, 2)
+            if fid.endswith("-map"):
+                # attention probabilities: (B, heads, Nq, Nk) contiguous, exactly the 4-D tensor the reference stores
+                t = arena[off:off + nbytes].view(torch.float16).view(self.batch, C, H, W)
+            else:
+                t = arena[off:off + nbytes].view(torch.float16).view(self.batch, H, W, C).permute(0, 3, 1, 2)
             out.append((order, fid, t))
         out.sort(key=lambda x: x[0])
         return {fid: t for _, fid, t in out}
+
+    def attention_means(self, arena):
+        """Internal head-mean attention maps, execution order: [(block id, 'self'|'cross', (B, Nq, Nk) fp16)]."""
+        out = []
+        for fid, off, C, H, W, order in self.slots:
+            if off < 0 or not fid.startswith(ATTN_MEAN_PREFIX):
+                continue
+            block, kind = fid[len(ATTN_MEAN_PREFIX):].rsplit("-", 1)
+            t = arena[off:off + self.batch * H * W * 2].view(torch.float16).view(self.batch, H, W)
+            out.append((order, block, kind, t))
+        out.sort(key=lambda x: x[0])
+        return [(b, k, t) for _, b, k, t in out]
 
 
 def prepare_feature_extractor(version, pipe, config, resize_ratio, train_unet):
@@ -195,6 +250,8 @@ def selected_ids(feature_store, pipe):
         return _dit_feature_ids(pipe.dit_cfg) if getattr(pipe, "dit_cfg", None) else _unet_feature_ids(pipe.unet_cfg)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:
+        if "map" in k and getattr(pipe, "unet_cfg", None) is not None:
+            continue          # per-layer attention probabilities of the UNet families (slow path, like the reference)
         if "map" in k or k in ("vae-out", "attn"):
             raise NotImplementedError("feature id '%s' needs the attention-probability / vae-out path, which is "
                                       "not built on the B200 path yet (SURVEY.md 8f)" % k)

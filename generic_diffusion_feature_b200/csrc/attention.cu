@@ -311,4 +311,164 @@ cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaS
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- attention with the probability matrix as an output
+// Slow path of the reference (AttnStoreProcessor, feature/components/attention.py:165-263): P = softmax(scale Q K^T)
+// is materialised per head - it is the `...-self-map` / `...-cross-map` feature, (B, heads, Nq, Nk), and its head mean
+// feeds the AttentionStore - then O = P V. CUDA cores, fp32, two passes over the keys (row maximum / sum, then
+// probabilities + P V); one CTA = 16 query rows of one (batch, head), one thread = one key of a 128-key tile.
+constexpr int kApQT = 16, kApKT = 128;
+
+__device__ __forceinline__ void ap_scores(const float* __restrict__ q_s, const bf16* __restrict__ krow, int D, float* acc) {
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) acc[q] = 0.f;
+  for (int d = 0; d < D; d += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(krow + d);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float kf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(b2[i]);
+      kf[2 * i] = f.x;
+      kf[2 * i + 1] = f.y;
+    }
+#pragma unroll
+    for (int q = 0; q < kApQT; ++q) {
+      const float* qr = q_s + q * D + d;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[q] = fmaf(qr[i], kf[i], acc[q]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kApKT)
+attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk,
+                       const bf16* __restrict__ V, int ldv, int v_f16, bf16* __restrict__ O, int ldo,
+                       __half* __restrict__ P, int heads, int Nq, int Nk, int D, float scale) {
+  extern __shared__ float ap_smem[];
+  float* q_s = ap_smem;                       // [16][D] (pre-scaled queries)
+  float* p_s = ap_smem + kApQT * D;           // [16][128] probabilities of the current key tile / reduction scratch
+  __shared__ float m_s[kApQT], l_s[kApQT];
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * kApQT, h = blockIdx.y, b = blockIdx.z;
+  for (int i = tid; i < kApQT * D; i += kApKT) {
+    const int q = i / D, d = i - q * D, row = q0 + q;
+    q_s[i] = row < Nq ? __bfloat162float(Q[((long long)b * Nq + row) * ldq + h * D + d]) * scale : 0.f;
+  }
+  __syncthreads();
+  const bf16* Kb = K + (long long)b * Nk * ldk + h * D;
+  const bf16* Vb = V + (long long)b * Nk * ldv + h * D;
+  // ---- pass 1: per-thread running (max, sum) over this thread's keys, then a block reduction per query row
+  float m_t[kApQT], l_t[kApQT], acc[kApQT];
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) { m_t[q] = -INFINITY; l_t[q] = 0.f; }
+  for (int k0 = 0; k0 < Nk; k0 += kApKT) {
+    const int j = k0 + tid;
+    if (j < Nk) {
+      ap_scores(q_s, Kb + (long long)j * ldk, D, acc);
+#pragma unroll
+      for (int q = 0; q < kApQT; ++q) {
+        const float mn = fmaxf(m_t[q], acc[q]);
+        l_t[q] = l_t[q] * __expf(m_t[q] - mn) + __expf(acc[q] - mn);
+        m_t[q] = mn;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) p_s[q * kApKT + tid] = m_t[q];
+  __syncthreads();
+  if (tid < kApQT) {
+    float m = -INFINITY;
+    for (int i = 0; i < kApKT; ++i) m = fmaxf(m, p_s[tid * kApKT + i]);
+    m_s[tid] = m;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) p_s[q * kApKT + tid] = (l_t[q] > 0.f) ? l_t[q] * __expf(m_t[q] - m_s[q]) : 0.f;
+  __syncthreads();
+  if (tid < kApQT) {
+    float l = 0.f;
+    for (int i = 0; i < kApKT; ++i) l += p_s[tid * kApKT + i];
+    l_s[tid] = l;
+  }
+  __syncthreads();
+  // ---- pass 2: probabilities (written out) and O = P V; thread tid owns output dims tid and tid + 128
+  float o0[kApQT], o1[kApQT];
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) { o0[q] = 0.f; o1[q] = 0.f; }
+  const int d0 = tid, d1 = tid + kApKT;
+  for (int k0 = 0; k0 < Nk; k0 += kApKT) {
+    const int j = k0 + tid;
+    __syncthreads();                        // p_s of the previous tile has been consumed
+    if (j < Nk) {
+      ap_scores(q_s, Kb + (long long)j * ldk, D, acc);
+#pragma unroll
+      for (int q = 0; q < kApQT; ++q) {
+        const float pr = __expf(acc[q] - m_s[q]) / l_s[q];
+        p_s[q * kApKT + tid] = pr;
+        if (q0 + q < Nq) P[(((long long)b * heads + h) * Nq + q0 + q) * Nk + j] = __float2half_rn(pr);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kApQT; ++q) p_s[q * kApKT + tid] = 0.f;
+    }
+    __syncthreads();
+    const int nk = min(kApKT, Nk - k0);
+    for (int jj = 0; jj < nk; ++jj) {
+      const long long vo = (long long)(k0 + jj) * ldv;
+      float v0 = 0.f, v1 = 0.f;
+      if (v_f16) {
+        const __half* vh = reinterpret_cast<const __half*>(Vb);
+        if (d0 < D) v0 = __half2float(vh[vo + d0]);
+        if (d1 < D) v1 = __half2float(vh[vo + d1]);
+      } else {
+        if (d0 < D) v0 = __bfloat162float(Vb[vo + d0]);
+        if (d1 < D) v1 = __bfloat162float(Vb[vo + d1]);
+      }
+#pragma unroll
+      for (int q = 0; q < kApQT; ++q) {
+        const float pr = p_s[q * kApKT + jj];
+        o0[q] = fmaf(pr, v0, o0[q]);
+        o1[q] = fmaf(pr, v1, o1[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kApQT; ++q) {
+    const int row = q0 + q;
+    if (row < Nq) {
+      bf16* orow = O + ((long long)b * Nq + row) * ldo + h * D;
+      if (d0 < D) orow[d0] = __float2bfloat16_rn(o0[q]);
+      if (d1 < D) orow[d1] = __float2bfloat16_rn(o1[q]);
+    }
+  }
+}
+cudaError_t launch_attention_probs(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, int v_f16,
+                                   bf16* O, int ldo, __half* P, int B, int heads, int Nq, int Nk, int D, float scale,
+                                   cudaStream_t stream) {
+  if (D % 8 != 0 || D > 2 * kApKT || (ldq | ldk | ldv) % 8 != 0 || Nk < 1 || Nq < 1) return cudaErrorInvalidValue;
+  const dim3 grid((Nq + kApQT - 1) / kApQT, heads, B);
+  const size_t smem = (size_t)(kApQT * D + kApQT * kApKT) * sizeof(float);
+  attention_probs_kernel<<<grid, kApKT, smem, stream>>>(Q, ldq, K, ldk, V, ldv, v_f16, O, ldo, P, heads, Nq, Nk, D, scale);
+  return cudaGetLastError();
+}
+
+// head mean of a probability map: P fp16 [B, heads, n] -> mean fp16 [B, n] (AttnStoreProcessor: to_store.mean(1))
+__global__ void head_mean_kernel(const __half* __restrict__ P, __half* __restrict__ out, int heads, long long n,
+                                 long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n, r = i - b * n;
+    float s = 0.f;
+    for (int hh = 0; hh < heads; ++hh) s += __half2float(P[(b * heads + hh) * n + r]);
+    out[i] = __float2half_rn(s / (float)heads);
+  }
+}
+cudaError_t launch_head_mean(const __half* P, __half* out, int B, int heads, long long n, cudaStream_t stream) {
+  const long long total = (long long)B * n;
+  const long long blocks = (total + 255) / 256;
+  head_mean_kernel<<<(unsigned)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32), 256, 0, stream>>>(
+      P, out, heads, n, total);
+  return cudaGetLastError();
+}
+
 }  // namespace gdf

@@ -771,6 +771,33 @@ class Builder {
       return 0;
     });
   }
+  // Is this id (a feature id or an internal "#attnmean:<block>-<self|cross>" id) part of the current plan?
+  bool wants(const std::string& id) const { return !dry && h->requested.count(id) != 0; }
+  // Slow path with materialised probabilities (AttnStoreProcessor, feature/components/attention.py:165-263): the
+  // (B, heads, Nq, Nk) map goes to the `<block>-<kind>-map` slot (or a scratch buffer), its head mean to the internal
+  // `#attnmean:<block>-<kind>` slot that the host aggregates into the `attn` feature (diffusion_feature.py:488-500).
+  void attention_probs(const std::string& block_id, const char* kind, const bf16* q, int ldq, const bf16* k, int ldk,
+                       const bf16* v, int ldv, int v_f16, bf16* o, int ldo, int B, int heads, int Nq, int Nk, float scale,
+                       int head_dim) {
+    if (dry || err) return;
+    const int64_t map_off = site(block_id + "-" + kind + "-map", heads, Nq, Nk);
+    const int64_t mean_off = site("#attnmean:" + block_id + "-" + kind, 1, Nq, Nk);
+    __half* scratch = map_off < 0 ? reinterpret_cast<__half*>(buf((long long)B * heads * Nq, Nk)) : nullptr;
+    if (err) return;
+    ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * head_dim,
+             "attention-probs heads=" + std::to_string(heads) + " d=" + std::to_string(head_dim) + " Nq=" +
+                 std::to_string(Nq) + " Nk=" + std::to_string(Nk));
+    ops->push_back([=](const RunCtx& rc) -> int {
+      __half* P = map_off >= 0 ? reinterpret_cast<__half*>(rc.arena + map_off) : scratch;
+      OP_CUDA(launch_attention_probs(q, ldq, k, ldk, v, ldv, v_f16, o, ldo, P, B, heads, Nq, Nk, head_dim, scale,
+                                     rc.stream));
+      if (mean_off >= 0)
+        OP_CUDA(launch_head_mean(P, reinterpret_cast<__half*>(rc.arena + mean_off), B, heads, (long long)Nq * Nk,
+                                 rc.stream));
+      return 0;
+    });
+    if (scratch) rel(scratch);
+  }
   void small_linear(const float* x, const std::string& prefix, float* y, int B, int K, int N, bool silu_in,
                     bool silu_out) {
     const float* W = f32(prefix + ".weight");
@@ -873,7 +900,9 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
   const float scale = 1.f / sqrtf((float)(C / heads));
   // ---- self attention
   const int hd = C / heads;
-  const bool self_tc = (hd == 64) && attention_uses_tcgen05(N);
+  const bool probs_self = b.wants(fid + "-self-map") || b.wants("#attnmean:" + fid + "-self");
+  const bool probs_cross = b.wants(fid + "-cross-map") || b.wants("#attnmean:" + fid + "-cross");
+  const bool self_tc = !probs_self && (hd == 64) && attention_uses_tcgen05(N);
   const bool fold = b.ln_fold;
   float* sums1 = fold ? b.ln_rows(M) : nullptr;   // statistics of hs1 / hs2 (inputs of norm2 / norm3)
   float* sums2 = fold ? b.ln_rows(M) : nullptr;
@@ -910,7 +939,10 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
   }
   if (n1) b.rel(n1);
   bf16* ao = b.buf(M, C);
-  b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, self_tc ? 1 : 0, hd);
+  if (probs_self)
+    b.attention_probs(fid, "self", qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, 0, ao, C, B, heads, N, N, scale, hd);
+  else
+    b.attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, self_tc ? 1 : 0, hd);
   b.rel(qkv);
   bf16* hs1 = b.buf(M, C);
   {
@@ -971,7 +1003,10 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
     b.linear(h->ctx_bf16, Mc, ctx_dim, ctx_dim, wkv, 2 * C, e);
   }
   bf16* ao2 = b.buf(M, C);
-  b.attention(q2, C, kv, ldkv, kv + C, ldkv, ao2, C, B, heads, N, h->ctx_len, scale, 0, hd);
+  if (probs_cross)
+    b.attention_probs(fid, "cross", q2, C, kv, ldkv, kv + C, ldkv, 0, ao2, C, B, heads, N, h->ctx_len, scale, hd);
+  else
+    b.attention(q2, C, kv, ldkv, kv + C, ldkv, ao2, C, B, heads, N, h->ctx_len, scale, 0, hd);
   b.rel(q2);
   if (!b.kv_batched) b.rel(kv);
   bf16* hs2 = b.buf(M, C);
@@ -2551,8 +2586,11 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
   h->slots.assign(n_ids, gdf_slot{-1, 0, 0, 0, -1});
   for (int i = 0; i < n_ids; ++i) {
     const std::string id = feature_ids[i];
-    if (id.find("map") != std::string::npos || id == "vae-out" || id == "attn")
-      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps / vae-out are not built yet",
+    if (id == "vae-out" || id == "attn")
+      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': vae-out needs the VAE decoder / `attn` is assembled by the host "
+                  "from the #attnmean slots", id.c_str());
+    if (id.find("map") != std::string::npos && (h->is_dit || h->is_flux))
+      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps are built for the UNet families only",
                   id.c_str());
     h->requested[id] = i;
   }

@@ -17,7 +17,7 @@ Differences a user can observe (all documented in INTEGRATION.md):
   * version 'flux' (diffusion_feature.py:246-253 calls the whole FluxImg2ImgPipeline with strength = t/1000 and
     guidance_scale 1): prompts = (t5_embeds (1|B, 512, 4096), pooled_clip (1|B, 768)) as returned by encode_prompt
     here (the reference passes raw strings to the pipeline); noise = (eps_vae, eps_q) with 16 latent channels;
-  * control / attention / train_unet / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
+  * control / train_unet / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
     and IF raise NotImplementedError.
 """
 import ctypes
@@ -29,7 +29,8 @@ import torch.nn.functional as F
 
 from . import _lib, schedulers
 from ._lib import check
-from .components.feature_extractor import FeaturePlan, pool_views, prepare_feature_extractor, selected_ids
+from .components.feature_extractor import (FeaturePlan, aggregate_attention, attention_mean_ids, pool_views,
+                                           prepare_feature_extractor, selected_ids)
 from .components.models import get_diffusion_model
 
 
@@ -51,8 +52,6 @@ class FeatureExtractor(nn.Module):
         super().__init__()
         if control:
             raise NotImplementedError("ControlNet conditioning is outside the B200 hot path")
-        if attention:
-            raise NotImplementedError("aggregated attention maps are not built on the B200 path yet")
         if external_model:
             pipe = external_model            # diffusion_feature.py:46-47: the seam for pre-built pipes
         else:
@@ -70,6 +69,12 @@ class FeatureExtractor(nn.Module):
         self._plan = None
         self._plan_ctx_len = None
         self._ids = selected_ids(self.feature_store, pipe)
+        if attention:
+            # register_attention_store (diffusion_feature.py:67-68): the head-mean probabilities of every attention
+            # module of the selected categories become internal plan slots; `extract` aggregates them into `attn`
+            if getattr(pipe, "unet_cfg", None) is None:
+                raise NotImplementedError("aggregated attention maps are built for the UNet families only")
+            self._ids = list(self._ids) + attention_mean_ids(pipe.unet_cfg, list(attention))
 
     # ------------------------------------------------------------------------------------------ images
     def _preprocess_basic(self, x):
@@ -228,6 +233,8 @@ class FeatureExtractor(nn.Module):
         if self.feature_store.resize_ratio > 1:                  # feature_extractor.py:51-53
             with torch.cuda.device(pipe.dev_index):
                 feats = pool_views(lib, feats, self.feature_store.resize_ratio)
+        if self.attention:                                       # diffusion_feature.py:488-500
+            feats['attn'] = aggregate_attention(plan.attention_means(arena), list(self.attention), self.img_size)
         if self.feature_store.accept_all:
             feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
         self.feature_store.feats = feats

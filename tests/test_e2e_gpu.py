@@ -294,7 +294,7 @@ def test_unknown_id_and_unbuilt_features(cuda_dev):
     with pytest.raises(GdfError):
         fe.extract((ctx, ctx, pooled, pooled), 1, image, image_type="tensors")
     with pytest.raises(NotImplementedError):
-        FeatureExtractor({"mid-vit-block0-self-map": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
+        FeatureExtractor({"vae-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
     # cross-k / cross-v are accepted and silently dropped, like FeatureStore.store (feature_extractor.py:38-39)
     fe = FeatureExtractor({"mid-vit-block0-cross-k": True, "mid-vit-out": True}, "xl", "cuda:0", img_size=128,
                           external_model=pipe)
@@ -334,6 +334,47 @@ def test_cuda_matches_reference_vendored_unet_golden(cuda_dev, fixture, version,
     rows = compare_maps(got, {k: v.float() for k, v in gold["feats"].items()})
     bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
     assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+
+
+def test_cuda_attention_maps_match_reference_golden(cuda_dev):
+    """per-layer attention probabilities (`...-self-map` / `...-cross-map`, (B, heads, Nq, Nk)) and
+    the aggregated `attn` feature (FeatureExtractor(attention=[...])) vs the fixture written by the reference's REAL
+    AttnStoreProcessor / AttentionStore / register_attention_store on its vendored UNet (tools/make_golden.py)."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "unet_tiny_xl_maps.pt"), weights_only=False)
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    img = gold["img"]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, "xl", "cuda:0", img_size=img, attention=gold["categories"],
+                          external_model=pipe)
+    ts, a, b, s = schedulers.resolve("xl", 50)
+    lat = gold["x"] / (a * s)
+    zero = torch.zeros_like(gold["x"])
+    got = fe.extract((gold["ctx"], gold["ctx"], gold["pooled"], gold["pooled"]), 1, lat.cuda(), image_type="tensors",
+                     t=50, noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"] + ["attn"]
+    m = got["mid-vit-block0-cross-map"]
+    assert m.shape == (1, TINY_XL["heads"][-1], 4, 77) and m.dtype == torch.float16
+    assert (m.float().sum(-1) - 1).abs().max().item() < 5e-3
+    want = {k: v.float() for k, v in gold["feats"].items()}
+    want["attn"] = gold["attn"].float()
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+    # without `attention` and without map ids the fast (flash) path is used and gives the same activations
+    plain = [i for i in gold["ids"] if not i.endswith("-map")]
+    fe2 = FeatureExtractor({i: True for i in plain}, "xl", "cuda:0", img_size=img, external_model=pipe)
+    got2 = fe2.extract((gold["ctx"], gold["ctx"], gold["pooled"], gold["pooled"]), 1, lat.cuda(), image_type="tensors",
+                       t=50, noise=(zero, zero))
+    torch.cuda.synchronize()
+    rows = compare_maps(got2, {k: got[k].float().cpu() for k in plain})
+    assert min(r[1] for r in rows) >= COS_MIN
 
 
 def test_full_size_sdxl_1024_parity(cuda_dev):
