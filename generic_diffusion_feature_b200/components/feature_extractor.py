@@ -167,8 +167,16 @@ def pool_views(lib, feats, ratio):
     buf = torch.empty(total, dtype=torch.uint8, device=dev)
     out = {}
     for k, v, B, C, H, W, OH, OW, off in plan:
+        assert v.dtype == torch.float16
+        if v.is_contiguous() and C > 1:
+            # attention-probability map (B, heads, Nq, Nk), stored like the reference's 4-D tensor: pooled over its
+            # last two axes like any other 4-D feature (FeatureStore.store does not special-case it) - one channel
+            dst = buf[off:off + B * OH * OW * C * 2].view(torch.float16).view(B, C, OH, OW)
+            check(lib.gdf_op_avgpool_nhwc(_lib.ptr(v), _lib.ptr(dst), B * C, H, W, 1, OH, OW, _lib.stream_ptr()))
+            out[k] = dst
+            continue
         src = v.permute(0, 2, 3, 1)                       # the arena storage: (B, H, W, C) contiguous
-        assert src.is_contiguous() and v.dtype == torch.float16
+        assert src.is_contiguous()
         dst = buf[off:off + B * OH * OW * C * 2].view(torch.float16).view(B, OH, OW, C)
         check(lib.gdf_op_avgpool_nhwc(_lib.ptr(src), _lib.ptr(dst), B, H, W, C, OH, OW, _lib.stream_ptr()))
         out[k] = dst.permute(0, 3, 1, 2)

@@ -531,6 +531,11 @@ def test_feature_resize_pool_vs_reference_store(cuda_dev, ratio):
     got = pool_views(_lib.load(), feats, ratio)
     torch.cuda.synchronize()
     assert list(got.keys()) == ["a", "b"]
+    # a 4-D attention map (B, heads, Nq, Nk) is stored NCHW-contiguous and pooled over its last two axes
+    amap = torch.rand(2, 4, 16, 77, device="cuda").half()
+    pm = pool_views(_lib.load(), {"m-self-map": amap}, ratio)["m-self-map"]
+    want_m = F.adaptive_avg_pool2d(amap.float(), (16 // ratio, 77 // ratio))
+    assert pm.shape == want_m.shape and (pm.float() - want_m).abs().max().item() < 2e-3
     for k in ("a", "b"):
         want = gold["r%d" % ratio][k]
         assert got[k].shape == want.shape and got[k].dtype == torch.float16
