@@ -71,6 +71,35 @@ def test_oracle_attention_maps_match_reference_processor():
     assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
 
 
+def test_host_attention_aggregation_matches_reference():
+    """Host side of the aggregated `attn` feature (attention_mean_ids + aggregate_attention, the mirror of
+    register_attention_store / AttentionStore.aggregate_attention / diffusion_feature.py:488-500) fed with the oracle's
+    head-mean maps in plan order reproduces the reference fixture."""
+    from generic_diffusion_feature_b200.components.feature_extractor import (ATTN_MEAN_PREFIX, aggregate_attention,
+                                                                             attention_mean_ids)
+    gold = torch.load(os.path.join(GOLD, "unet_tiny_xl_maps.pt"), weights_only=False)
+    sd = _models().synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    unet, _ = build_oracle(TINY_XL, TINY_VAE, sd)
+    ast = O.register_attention_store(unet, gold["img"])
+    with torch.no_grad():
+        unet(gold["x"], gold["timestep"], gold["ctx"], text_embeds=gold["pooled"], time_ids=O.add_time_ids(gold["img"]))
+    ids = attention_mean_ids(TINY_XL, gold["categories"])
+    assert ids and all(i.startswith(ATTN_MEAN_PREFIX) for i in ids)
+    pools = {k: list(v) for k, v in ast.step_store.items()}
+    means = []
+    for i in ids:                                   # plan (= execution) order; the store keeps per-category lists
+        block, kind = i[len(ATTN_MEAN_PREFIX):].rsplit("-", 1)
+        means.append((block, kind, pools["%s_%s" % (block.split("-")[0], kind)].pop(0).to(torch.float16)))
+    attn = aggregate_attention(means, gold["categories"], gold["img"])
+    assert attn.shape == gold["attn"].shape and attn.dtype == torch.float16
+    assert (attn.float() - gold["attn"]).abs().max().item() < 2e-3
+    # every category the CLI accepts maps to at least one attention module of the SDXL UNet
+    full = _models().UNET_CONFIGS["xl"]
+    for cat in ("down_cross", "mid_cross", "up_cross", "down_self", "mid_self", "up_self"):
+        assert attention_mean_ids(full, [cat])
+    assert len(attention_mean_ids(full, ["down_cross", "mid_cross", "up_cross"])) == 70
+
+
 def test_oracle_matches_reference_vendored_dit_blocks():
     """tests/golden/dit_tiny_pixart.pt: the reference's vendored BasicTransformerBlock (ada_norm_single) stack +
     its real prepare_feature_extractor PixArt branch (tools/make_golden.py); the oracle reproduces every map."""
