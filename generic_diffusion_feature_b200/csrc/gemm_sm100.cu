@@ -449,7 +449,9 @@ __device__ __forceinline__ void gn_flush(const GemmParams& p, float val, long lo
 //                     by kGeglu (GEGLU or none). Captures, cap_pre, out2, column gate, per-sample row bias, residual
 //                     and GroupNorm statistics stay run-time options.
 //   level 2 "simple": additionally alpha = 1 and one bf16 destination only: [bias] [+ residual] [+ GroupNorm statistics] (VAE).
-template <int CG, bool kGeglu, int kLevel = 0>
+// kActRt (level 1 only): the element-wise activation (GELU-tanh / SiLU: PixArt, Flux FFNs) stays a run-time option; a
+// separate instantiation so that the activation code does not sit in the image of the launches that have none.
+template <int CG, bool kGeglu, int kLevel = 0, bool kActRt = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -846,10 +848,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) geglu_pair(v[hh][j], v[hh][j + 1], g[j], g[j + 1]);
             }
-          } else if (EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone)) == kActGeluTanh) {
+          } else if ((kActRt ? p.act : EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone))) == kActGeluTanh) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[0][j] = gelu_tanh_f(v[0][j]); v[1][j] = gelu_tanh_f(v[1][j]); }
-          } else if (EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone)) == kActSilu) {
+          } else if ((kActRt ? p.act : EPF(act, 1, (int)(kGeglu ? kActGeglu : kActNone))) == kActSilu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[0][j] = silu_f(v[0][j]); v[1][j] = silu_f(v[1][j]); }
           }
@@ -1018,6 +1020,8 @@ static cudaError_t gemm_init_once() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1076,13 +1080,15 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   static const int max_level = getenv("GDF_EPI_LEVEL") ? atoi(getenv("GDF_EPI_LEVEL")) : 2;
   const bool geglu = p.act == kActGeglu;
   const int out_w = geglu ? p.block_n / 2 : p.block_n;
-  const bool lean = max_level >= 1 && (geglu || p.act == kActNone) && !p.ln_sums && !p.row_sums && !p.bias_m &&
+  const bool act_rt = p.act == kActGeluTanh || p.act == kActSilu;
+  const bool lean = max_level >= 1 && (geglu || p.act == kActNone || act_rt) && !p.ln_sums && !p.row_sums && !p.bias_m &&
                     p.out_scale == 1.f && !p.out_f32 && p.fast_epi && p.tma_store &&
                     p.N % p.block_n == 0 && out_w % 32 == 0 && p.n_out == (geglu ? p.N / 2 : p.N);
   if (geglu) {
     if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true, 1>, maps, p);
     return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, true>, maps, p);
   }
+  if (lean && act_rt) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 1, true>, maps, p);
   const bool simple = lean && max_level >= 2 && p.alpha == 1.f && !p.col_scale && !p.row_batch_bias && !p.out2 && !p.cap_pre &&
                       p.num_cap == 0 && p.out && p.out_f16_from >= (1 << 30);
   if (simple) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 2>, maps, p);
