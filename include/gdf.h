@@ -130,7 +130,14 @@ int gdf_finalize_weights(gdf_handle h, void* stream);
 /* Feature plan: replaces prepare_feature_extractor (feature/components/feature_extractor.py:92-288).
  * ids are the reference's feature ids (feature/configs/*.json keys). For each accepted id the library returns
  * the arena slot: byte offset, channels, height, width. cross-k / cross-v are rejected exactly like
- * FeatureStore.store drops them (feature_extractor.py:38-39): offset = -1. Unknown ids -> GDF_ERR_INVALID. */
+ * FeatureStore.store drops them (feature_extractor.py:38-39): offset = -1. Unknown ids -> GDF_ERR_INVALID.
+ * Slot layout: fp16 token-major [B, height*width, channels], except
+ *   "<block>-self-map" / "<block>-cross-map" (UNet families; the reference's AttnStoreProcessor,
+ *       feature/components/attention.py:241-244): fp16 [B, heads, Nq, Nk] with channels = heads, height = Nq,
+ *       width = Nk; requesting one switches that attention module to the probability-materialising kernel;
+ *   "#attnmean:<block>-self" / "#attnmean:<block>-cross" (internal, not a reference id): the head mean of the same
+ *       probabilities, fp16 [B, Nq, Nk] (channels = 1) - what the reference's AttentionStore receives
+ *       (attention.py:241-242); the host aggregates these into the `attn` feature (diffusion_feature.py:488-500). */
 typedef struct gdf_slot {
   int64_t offset_bytes;               /* -1: id accepted by the grammar but never stored (cross-k/v) */
   int channels, height, width;
