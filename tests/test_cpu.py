@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import (O, ROOT, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle, build_oracle_dit,
+from common import (O, ROOT, TINY_15, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle, build_oracle_dit,
                     build_oracle_flux, make_inputs)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -22,7 +22,8 @@ def _models():
 
 
 # ------------------------------------------------------------------------------------------ oracle vs golden
-@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21)])
+@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21),
+                                                 ("unet_tiny_15.pt", "1-5", TINY_15)])
 def test_oracle_matches_reference_vendored_unet(fixture, version, cfg):
     """tests/golden/unet_tiny_*.pt were produced by the reference's vendored UNet2DConditionModel + its own
     FeatureStore (tools/make_golden.py); the oracle must reproduce every map (fixtures are fp16-rounded)."""

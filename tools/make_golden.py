@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import ref_shim  # noqa: E402
 from common import (CLI_MODES, FakeExtractor, cli_fixture_inputs, tree_digest,  # noqa: E402
-                    O, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,  # noqa: E402
+                    O, TINY_15, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle,  # noqa: E402
                     build_oracle_dit, build_oracle_flux, make_dit_inputs, make_flux_inputs, make_inputs)
 from generic_diffusion_feature_b200.components import models  # noqa: E402
 from generic_diffusion_feature_b200.components.feature_extractor import (_dit_feature_ids, _flux_feature_ids,  # noqa: E402
@@ -386,6 +386,7 @@ if __name__ == "__main__":
     golden_ids()
     golden_unet("xl", TINY_XL, "unet_tiny_xl.pt")
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
+    golden_unet("1-5", TINY_15, "unet_tiny_15.pt")       # conv proj_in / proj_out (use_linear_projection False), 8 heads
     golden_unet_maps()
     golden_dit()
     golden_flux()
