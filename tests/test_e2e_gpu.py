@@ -306,7 +306,8 @@ def test_unknown_id_and_unbuilt_features(cuda_dev):
         models.get_diffusion_model("no-such-version", "float16")
 
 
-@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21)])
+@pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21),
+                                                 ("unet_tiny_15.pt", "1-5", TINY_15)])
 def test_cuda_matches_reference_vendored_unet_golden(cuda_dev, fixture, version, cfg):
     """CUDA path vs the fixture produced by the REFERENCE's vendored UNet2DConditionModel + FeatureStore
     (tools/make_golden.py): latents are fed through the 4-channel branch of prepare_latents with zero noise."""
@@ -322,7 +323,9 @@ def test_cuda_matches_reference_vendored_unet_golden(cuda_dev, fixture, version,
                                       vae_cfg=TINY_VAE)
     img = 8 * gold["x"].shape[-1]
     fe = FeatureExtractor({i: True for i in gold["ids"]}, version, "cuda:0", img_size=img, external_model=pipe)
-    t_use = 51 if version == "2-1" else 50          # the 2-1 Euler list is [999..0]: t=51 resolves to timestep 50
+    # the fixtures were made at timestep 50: the 2-1 Euler list is [999..0] (t=51 resolves to 50), the 1-5 PNDM list
+    # is [1000, 999, 999, 998, ...] (t=49 resolves to 50)
+    t_use = {"2-1": 51, "1-5": 49}.get(version, 50)
     ts, a, b, s = schedulers.resolve(version, t_use)
     assert ts == gold["timestep"]
     lat = gold["x"] / (a * s)                         # model input = (a*lat + b*0) * s = x
