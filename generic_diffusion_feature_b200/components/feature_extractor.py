@@ -55,16 +55,19 @@ def aggregate_attention(means, categories, img_size):
     return torch.cat(parts, dim=-3)
 
 
-def _unet_feature_ids(cfg, layers_per_block=2):
-    """All non-`map` feature ids of a UNet in execution order (same grammar as feature_extractor.py:125-249;
-    reproduces the 472 / 165 non-map ids of feature/configs/config_{xl,15}_full.json)."""
+def _unet_feature_ids(cfg, layers_per_block=2, with_maps=False):
+    """Feature ids of a UNet in execution order (same grammar as feature_extractor.py:125-249): the 472 / 165 non-`map`
+    ids of feature/configs/config_{xl,15}_full.json, or with_maps=True all 612 / 213 of them, the attention-probability
+    maps interleaved where AttnStoreProcessor gathers them (after the module's q / k / v)."""
     ids = ["unet-in", "unet-after-conv-in"]
     bo = cfg["block_out"]
     n = len(bo)
+    tags = ("self-q", "self-k", "self-v", "self-map", "cross-q", "cross-map", "ffn-inner", "out") if with_maps else \
+        ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out")
 
     def vit(prefix, depth):
         for k in range(depth):
-            for tag in ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out"):
+            for tag in tags:
                 ids.append("%s-block%d-%s" % (prefix, k, tag))
         ids.append(prefix + "-out")
 
@@ -255,7 +258,11 @@ def selected_ids(feature_store, pipe):
     if feature_store.accept_all:
         if getattr(pipe, "flux_cfg", None):
             return _flux_feature_ids(pipe.flux_cfg)
-        return _dit_feature_ids(pipe.dit_cfg) if getattr(pipe, "dit_cfg", None) else _unet_feature_ids(pipe.unet_cfg)
+        if getattr(pipe, "dit_cfg", None):
+            return _dit_feature_ids(pipe.dit_cfg)
+        # an empty config makes the reference install its storing attention processors (diffusion_feature.py:74-77), so
+        # accept-all includes every `...-map` (this is how config_{xl,15}_full.json were produced, :502-514)
+        return _unet_feature_ids(pipe.unet_cfg, with_maps=True)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:
         if "map" in k and getattr(pipe, "unet_cfg", None) is not None:

@@ -275,6 +275,10 @@ def test_id_grammar_matches_reference_configs():
     m = _models()
     assert _unet_feature_ids(m.UNET_CONFIGS["xl"]) == ref["ids_xl"] and len(ref["ids_xl"]) == 472
     assert _unet_feature_ids(m.UNET_CONFIGS["1-5"]) == ref["ids_1-5"] and len(ref["ids_1-5"]) == 165
+    # with the attention-probability maps interleaved (what accept-all plans, like the reference's empty-config mode that
+    # produced these files): all 612 / 197 keys of config_{xl,15}_full.json in file (= execution) order
+    assert _unet_feature_ids(m.UNET_CONFIGS["xl"], with_maps=True) == ref["all_ids_xl"] and len(ref["all_ids_xl"]) == 612
+    assert _unet_feature_ids(m.UNET_CONFIGS["1-5"], with_maps=True) == ref["all_ids_1-5"] and len(ref["all_ids_1-5"]) == 197
     # every practical / legacy config id is a legal id of its architecture
     for f, ver in (("config_xl_practical.json", "xl"), ("config_xl_legacy.json", "xl"),
                    ("config_15_practical.json", "1-5"), ("config_15_legacy.json", "1-5")):

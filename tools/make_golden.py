@@ -370,6 +370,7 @@ def golden_ids():
         cfg = json.load(open(os.path.join(ref, "feature", "configs", f)))
         out["ids_" + key] = [k for k in cfg if "map" not in k]
         out["map_ids_" + key] = [k for k in cfg if "map" in k]
+        out["all_ids_" + key] = list(cfg)                  # file order = execution order, maps interleaved
     for f in ("config_xl_practical.json", "config_xl_legacy.json", "config_15_practical.json",
               "config_15_legacy.json"):
         out[f] = json.load(open(os.path.join(ref, "feature", "configs", f)))
