@@ -72,6 +72,33 @@ def test_oracle_attention_maps_match_reference_processor():
     assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
 
 
+def test_feature_plan_views_layouts():
+    """FeaturePlan.views / attention_means on a hand-made slot table (pure tensor views, no GPU): token-major maps come
+    back as (B, C, h, w) with channel stride 1, `...-map` slots as the contiguous (B, heads, Nq, Nk) tensor the
+    reference stores, internal `#attnmean:` slots only through attention_means, everything in execution order."""
+    from generic_diffusion_feature_b200.components.feature_extractor import ATTN_MEAN_PREFIX, FeaturePlan
+    plan = FeaturePlan.__new__(FeaturePlan)
+    plan.batch = 2
+    B = 2
+    # (id, offset, C, H, W, order): a 3-channel 2x2 map, a (heads=2, Nq=4, Nk=3) probability map, its head mean
+    n0, n1, n2 = B * 2 * 2 * 3, B * 2 * 4 * 3, B * 4 * 3
+    plan.slots = [("mid-vit-block0-self-map", 256, 2, 4, 3, 1), ("mid-vit-out", 0, 3, 2, 2, 3),
+                  (ATTN_MEAN_PREFIX + "mid-vit-block0-self", 512, 1, 4, 3, 2), ("mid-vit-block0-cross-k", -1, 0, 0, 0, -1)]
+    arena = torch.zeros(1024, dtype=torch.uint8)
+    arena[0:2 * n0].view(torch.float16)[:] = torch.arange(n0, dtype=torch.float16)
+    arena[256:256 + 2 * n1].view(torch.float16)[:] = torch.arange(n1, dtype=torch.float16) + 100
+    arena[512:512 + 2 * n2].view(torch.float16)[:] = torch.arange(n2, dtype=torch.float16) + 500
+    views = plan.views(arena)
+    assert list(views.keys()) == ["mid-vit-block0-self-map", "mid-vit-out"]            # execution order, internal ids hidden
+    v = views["mid-vit-out"]
+    assert v.shape == (2, 3, 2, 2) and v.stride(1) == 1 and v[1, 2, 1, 0].item() == float((1 * 4 + 2) * 3 + 2)
+    m = views["mid-vit-block0-self-map"]
+    assert m.shape == (2, 2, 4, 3) and m.is_contiguous() and m[1, 1, 3, 2].item() == 100.0 + n1 - 1
+    means = plan.attention_means(arena)
+    assert [(b, k) for b, k, _ in means] == [("mid-vit-block0", "self")]
+    assert means[0][2].shape == (2, 4, 3) and means[0][2][1, 3, 2].item() == 500.0 + n2 - 1
+
+
 def test_host_attention_aggregation_matches_reference():
     """Host side of the aggregated `attn` feature (attention_mean_ids + aggregate_attention, the mirror of
     register_attention_store / AttentionStore.aggregate_attention / diffusion_feature.py:488-500) fed with the oracle's
