@@ -30,38 +30,46 @@ import numpy as np
 import torch
 
 
-def build_parser():
-    parser = argparse.ArgumentParser()
-    # same settings as the diffusion feature package (reference extract_feature.py:18-30)
-    parser.add_argument('--layer', type=str, help="which layer's output to be used as features")
-    parser.add_argument('--version', type=str, default='xl', help='Model version')
-    parser.add_argument('--dtype', type=str, default='float16', choices=('float16', 'float32'),
-                        help='Model data type to use')
-    parser.add_argument('--offline_lora', type=str, default=None, help='path for pretrained lora weights')
-    parser.add_argument('--offline_lora_filename', type=str, default=None, help='name of lora file')
-    parser.add_argument('--feature_resize', type=int, default=1, help='resize ratio of width and height')
-    parser.add_argument('--control', type=str, nargs='+', default=None, help='type of control information to use')
-    parser.add_argument('--attention', type=str, nargs='+', default=None,
-                        choices=('down_cross', 'mid_cross', 'up_cross', 'down_self', 'mid_self', 'up_self'))
-    parser.add_argument('--img_size', type=int, default=1024)
-    # extraction settings (:31-35)
-    parser.add_argument('--batch_size', '-b', type=int, default=2)
-    parser.add_argument('--t', type=int, help='Timesteps to compute features')
-    parser.add_argument('--denoising_from', type=int, default=None, help='perform multiple denoising from a given t')
-    parser.add_argument('--use_ddim_inversion', action='store_true')
-    # io settings (:36-45)
-    parser.add_argument('--input_dir', type=str, default=None, help='glob of the input images')
-    parser.add_argument('--nested_input_dir', action='store_true')
-    parser.add_argument('--prompt_file', type=str, default='prompt.txt')
-    parser.add_argument('--output_dir', type=str, default='./output/')
-    parser.add_argument('--aggregate_output', action='store_true')
-    parser.add_argument('--use_original_filename', action='store_true')
-    parser.add_argument('--split', type=str, default='train')
-    parser.add_argument('--sample_name_first', action='store_true')
-    parser.add_argument('--show_all_layers', action='store_true')
+# flag table: (names, kwargs). Same flag names / defaults as the reference CLI (extract_feature.py:18-47) so that
+# existing command lines keep working; descriptions are ours.
+_FLAGS = [
+    # model / capture selection
+    (("--layer",), dict(type=str, help="JSON file (or nothing with --show_all_layers) naming the feature ids to keep")),
+    (("--version",), dict(type=str, default="xl", help="xl | pgv2 | 2-1 | 1-5 | pixart-sigma | pixart-sigma-512 | flux")),
+    (("--dtype",), dict(type=str, default="float16", choices=("float16", "float32"), help="accepted for compatibility")),
+    (("--offline_lora",), dict(type=str, default=None, help="not built on this path")),
+    (("--offline_lora_filename",), dict(type=str, default=None, help="not built on this path")),
+    (("--feature_resize",), dict(type=int, default=1, help="average-pool every stored map by this factor")),
+    (("--control",), dict(type=str, nargs="+", default=None, help="not built on this path")),
+    (("--attention",), dict(type=str, nargs="+", default=None,
+                            choices=("down_cross", "mid_cross", "up_cross", "down_self", "mid_self", "up_self"),
+                            help="attention categories aggregated into the `attn` feature")),
+    (("--img_size",), dict(type=int, default=1024, help="images are resized to img_size x img_size")),
+    # extraction
+    (("--batch_size", "-b"), dict(type=int, default=2, help="images per extract call")),
+    (("--t",), dict(type=int, help="q_sample timestep (0..1000)")),
+    (("--denoising_from",), dict(type=int, default=None, help="not built on this path")),
+    (("--use_ddim_inversion",), dict(action="store_true", help="not built on this path")),
+    # input / output
+    (("--input_dir",), dict(type=str, default=None, help="glob pattern of the input images")),
+    (("--nested_input_dir",), dict(action="store_true", help="prefix output names with the image's parent folder")),
+    (("--prompt_file",), dict(type=str, default="prompt.txt", help="text file holding the prompt")),
+    (("--output_dir",), dict(type=str, default="./output/", help="root of the .npy tree")),
+    (("--aggregate_output",), dict(action="store_true", help="one concatenated array per image")),
+    (("--use_original_filename",), dict(action="store_true", help="name outputs after the input files")),
+    (("--split",), dict(type=str, default="train", help="name prefix when not using original file names")),
+    (("--sample_name_first",), dict(action="store_true", help="<out>/<name>/<layer>.npy instead of <out>/<layer>/<name>.npy")),
+    (("--show_all_layers",), dict(action="store_true", help="print every available feature id and exit")),
     # B200-path extras
-    parser.add_argument('--writer_threads', type=int, default=8)
-    parser.add_argument('--device', type=str, default='cuda')
+    (("--writer_threads",), dict(type=int, default=8, help="threads writing .npy files")),
+    (("--device",), dict(type=str, default="cuda", help="cuda | cuda:N (torchrun picks cuda:LOCAL_RANK)")),
+]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="feature extraction to .npy files on the B200 path")
+    for names, kw in _FLAGS:
+        parser.add_argument(*names, **kw)
     return parser
 
 
