@@ -232,6 +232,19 @@ def test_cli_on_disk_format_matches_reference(mode, tmp_path):
     assert tree_digest(od) == gold
 
 
+def test_cli_nearest_resize_matches_torch_interpolate():
+    """The aggregated CLI output resizes with F.interpolate's default mode (`nearest`, extract_feature.py:122-124);
+    the writer threads do it in numpy - same index rule for integer and non-integer ratios, up and down."""
+    import torch.nn.functional as F
+    from generic_diffusion_feature_b200.extract_feature import nearest_resize_chw
+    g = torch.Generator().manual_seed(5)
+    for h, size in ((4, 16), (8, 8), (6, 16), (16, 6), (5, 7), (32, 128), (3, 128)):
+        a = torch.randn(3, h, h, generator=g)
+        want = F.interpolate(a[None], size)[0].numpy()
+        got = nearest_resize_chw(a.numpy(), size)
+        assert got.shape == want.shape and np.array_equal(got, want), (h, size)
+
+
 def test_cli_two_rank_shards_write_the_same_tree(tmp_path, monkeypatch):
     """Two ranks (RANK / WORLD_SIZE as torchrun sets them) each extract their contiguous shard into one output tree:
     together they produce exactly the single-process tree of the reference (global indices name the files)."""
