@@ -465,7 +465,7 @@ class UNet2DConditionModel(nn.Module):
         self.conv_norm_out = nn.GroupNorm(32, bo[0], eps=cfg["eps"])
         self.conv_out = nn.Conv2d(bo[0], 4, 3, padding=1)
 
-    def forward(self, sample, timestep, ctx, text_embeds=None, time_ids=None):
+    def forward(self, sample, timestep, ctx, text_embeds=None, time_ids=None, down_residuals=None, mid_residual=None):
         B = sample.shape[0]
         t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(B)
         emb = self.time_embedding(timestep_embedding(t, self.cfg["block_out"][0]))        # :1141-1142
@@ -479,7 +479,11 @@ class UNet2DConditionModel(nn.Module):
         for blk in self.down_blocks:
             h, s = blk(h, emb, ctx)
             skips += s
+        if down_residuals is not None:        # ControlNet: one residual per skip tensor (:1244-1252) ...
+            skips = [s + r for s, r in zip(skips, down_residuals)]
         h = self.mid_block(h, emb, ctx)
+        if mid_residual is not None:          # ... and one after the mid block (:1274-1275)
+            h = h + mid_residual
         for blk in self.up_blocks:
             h = blk(h, skips, emb, ctx)
         h = self.conv_out(F.silu(self.conv_norm_out(h)))                                  # :1304-1307

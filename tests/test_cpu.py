@@ -47,6 +47,22 @@ def test_oracle_matches_reference_vendored_unet(fixture, version, cfg):
         assert (got - ref).abs().max().item() <= tol, k
 
 
+def test_oracle_controlnet_residual_inputs_match_reference():
+    """tests/golden/unet_tiny_xl_control.pt (oracle side; the CUDA path does not take these inputs
+    yet): the reference's vendored UNet forward with down_block_additional_residuals / mid_block_additional_residual
+    (unet_2d_condition.py:1236-1275)."""
+    gold = torch.load(os.path.join(GOLD, "unet_tiny_xl_control.pt"), weights_only=False)
+    sd = _models().synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    unet, _ = build_oracle(TINY_XL, TINY_VAE, sd)
+    tid = O.add_time_ids(8 * gold["x"].shape[-1])
+    with torch.no_grad():
+        out = unet(gold["x"], gold["timestep"], gold["ctx"], text_embeds=gold["pooled"], time_ids=tid,
+                   down_residuals=gold["down"], mid_residual=gold["mid"])
+        plain = unet(gold["x"], gold["timestep"], gold["ctx"], text_embeds=gold["pooled"], time_ids=tid)
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    assert (plain - gold["noise_pred"]).abs().max().item() > 1e-2          # the residuals matter
+
+
 def test_oracle_attention_maps_match_reference_processor():
     """tests/golden/unet_tiny_xl_maps.pt (oracle side): the reference's real AttnStoreProcessor /
     AttentionStore / register_attention_store on its vendored UNet - every `...-self-map` / `...-cross-map`

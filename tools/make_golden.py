@@ -153,6 +153,58 @@ def golden_unet_maps(name="unet_tiny_xl_maps.pt"):
                os.path.join(OUT, name))
 
 
+def golden_unet_control(name="unet_tiny_xl_control.pt"):
+    """ControlNet residual inputs: the reference's vendored UNet2DConditionModel.forward with
+    down_block_additional_residuals / mid_block_additional_residual (unet_2d_condition.py:1236-1275) on seeded
+    residual tensors; a handful of maps that depend on them + the noise prediction."""
+    version, cfg = "xl", TINY_XL
+    sd = models.synthetic_state_dict(version, "cpu", cfg, TINY_VAE)
+    ref_unet = ref_shim.build_reference_unet(cfg)
+    ref_unet.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("unet.")}, strict=True)
+    ref_unet.eval()
+    rfe = ref_shim.load_reference_feature_extractor()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.unet = ref_unet
+    ids = [i for i in _unet_feature_ids(cfg) if i.startswith("up-") and i.endswith("-res-out")] + ["mid-vit-out", "unet-out"]
+    order = [i for i in _unet_feature_ids(cfg) if i in set(ids)]
+    store = rfe.prepare_feature_extractor(version, pipe, {i: True for i in order}, 1, True)
+    x, ctx, pooled = unet_inputs(cfg)
+    L = x.shape[-1]
+    tid = O.add_time_ids(8 * L).repeat(x.shape[0], 1)
+    # skip tensors of the oracle give the shapes: conv_in output + every resnet / downsampler output of the down path
+    ounet, _ = build_oracle(cfg, TINY_VAE, sd)
+    g = torch.Generator().manual_seed(99)
+    bo = cfg["block_out"]
+    shapes, res = [(bo[0], L)], L
+    for i, c in enumerate(bo):
+        shapes += [(c, res), (c, res)]
+        if i != len(bo) - 1:
+            res //= 2
+            shapes.append((c, res))
+    down = [0.3 * torch.randn(1, c, r, r, generator=g) for c, r in shapes]
+    mid = 0.3 * torch.randn(1, bo[-1], res, res, generator=g)
+    with torch.no_grad():
+        out = ref_unet(x, timestep=torch.tensor([50.0]), encoder_hidden_states=ctx, return_dict=False,
+                       added_cond_kwargs={"text_embeds": pooled, "time_ids": tid},
+                       down_block_additional_residuals=tuple(down), mid_block_additional_residual=mid)[0]
+        plain = ref_unet(x, timestep=torch.tensor([50.0]), encoder_hidden_states=ctx, return_dict=False,
+                         added_cond_kwargs={"text_embeds": pooled, "time_ids": tid})[0]
+    feats = dict(store.stored_feats)          # (second call overwrote nothing: reset between calls)
+    ostore = O.FeatureStore({i: True for i in order})
+    O.attach_gatherers(ounet, ostore)
+    with torch.no_grad():
+        oout = ounet(x, 50.0, ctx, text_embeds=pooled, time_ids=tid, down_residuals=down, mid_residual=mid)
+    print("%s: noise prediction moves by %.3f with the residuals; oracle max |diff| %.2e"
+          % (name, (out - plain).abs().max().item(), (out - oout).abs().max().item()))
+    assert (out - oout).abs().max().item() < 1e-4 and (out - plain).abs().max().item() > 1e-2
+    torch.save({"x": x, "ctx": ctx, "pooled": pooled, "timestep": 50.0, "down": down, "mid": mid, "noise_pred": out,
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference vendored UNet, ControlNet residuals)"},
+               os.path.join(OUT, name))
+
+
 def golden_dit(name="dit_tiny_pixart.pt"):
     """PixArt path: the reference's vendored BasicTransformerBlock (attention.py:469-592, norm_type
     'ada_norm_single', attention_bias, gelu-approximate FeedForward) + vendored Attention / AttnProcessor2_0 +
@@ -389,6 +441,7 @@ if __name__ == "__main__":
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
     golden_unet("1-5", TINY_15, "unet_tiny_15.pt")       # conv proj_in / proj_out (use_linear_projection False), 8 heads
     golden_unet_maps()
+    golden_unet_control()
     golden_dit()
     golden_flux()
     golden_store_resize()
