@@ -101,7 +101,13 @@ int gdf_op_layernorm(const void* x, void* y, const void* gamma, const void* beta
 int gdf_op_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
                      int heads, int Nq, int Nk, int head_dim, float scale, int v_f16, void* stream) {
   if (head_dim != 64) {
-    if (v_f16) return fail(GDF_ERR_UNSUPPORTED, "gdf_op_attention: fp16 V needs head_dim 64");
+    if (v_f16) {
+      if (!attention_tc_supports(head_dim))
+        return fail(GDF_ERR_UNSUPPORTED, "gdf_op_attention: fp16 V needs head_dim 40 / 64 / 72 / 80 / 128");
+      return launch_attention_tc(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
+                                 static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, B, heads, Nq, Nk, head_dim,
+                                 scale, 1, nullptr, static_cast<cudaStream_t>(stream));
+    }
     GDF_LAUNCH(launch_attention_generic(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
                                         static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, B, heads, Nq, Nk,
                                         head_dim, scale, static_cast<cudaStream_t>(stream)));

@@ -217,8 +217,18 @@ attention64_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__
   }
 }
 
+static bool attention_tc_enabled() {   // GDF_ATTN_TC=0: round-1 kernels (A/B timing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDF_ATTN_TC");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 bool attention_uses_tcgen05(int Nk) {
-  // long KV (self-attention): tcgen05 / TMEM kernel; short KV (text cross-attention, Nk = 77): mma.sync kernel
+  // long KV (self-attention): the QKV projection writes V as fp16 and P.V runs in fp16; short KV (text cross-attention,
+  // Nk = 77): V stays bf16 (one batched projection for all blocks) and P is rounded to bf16
   static int use_tc = -1;
   if (use_tc < 0) {
     const char* v = getenv("GDF_ATTN_TCGEN05");
@@ -229,13 +239,20 @@ bool attention_uses_tcgen05(int Nk) {
 
 cudaError_t launch_attention64(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, int v_f16, cudaStream_t stream) {
+  if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
+  if (attention_tc_enabled()) {
+    if (launch_attention_tc(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, 64, scale, v_f16, nullptr, stream) != 0) {
+      fprintf(stderr, "gdf: tcgen05 attention launch failed: %s\n", last_error().c_str());
+      return cudaErrorUnknown;
+    }
+    return cudaSuccess;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
   if (v_f16) {
     if (!attention_uses_tcgen05(Nk)) return cudaErrorInvalidValue;   // the mma.sync kernel takes bf16 V
     if (launch_attention64_tcgen05(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, scale, stream) != 0) {

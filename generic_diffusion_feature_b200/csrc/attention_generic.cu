@@ -2,6 +2,7 @@
 // kernel of attention.cu templated on the padded head dim DP (multiple of 16; columns [D, DP) are zero-filled in
 // shared memory, so they add nothing to QK^T and produce zero output columns that are never stored).
 // Reference call site: F.scaled_dot_product_attention, attention_processor.py:3311-3313.
+#include <stdlib.h>
 #include "ops.h"
 
 namespace gdf {
@@ -224,6 +225,22 @@ cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int 
                                      int ldo, int B, int heads, int Nq, int Nk, int D, float scale,
                                      cudaStream_t stream, const float* key_bias) {
   if (D % 8 != 0 || D > 160 || (ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1) return cudaErrorInvalidValue;
+  {
+    // tcgen05 / TMEM kernel for every head dim it is built for (GDF_ATTN_TC=0: the mma.sync kernels below, kept for
+    // head dim 160 = the 16x16 / 8x8-token levels of SD-1.5, and for A/B timing)
+    static int tc = -1;
+    if (tc < 0) {
+      const char* e = getenv("GDF_ATTN_TC");
+      tc = e ? atoi(e) : 1;
+    }
+    if (tc && attention_tc_supports(D)) {
+      if (launch_attention_tc(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, 0, key_bias, stream) != 0) {
+        fprintf(stderr, "gdf: tcgen05 attention launch failed: %s\n", last_error().c_str());
+        return cudaErrorUnknown;
+      }
+      return cudaSuccess;
+    }
+  }
   if (D <= 48) return launch_ga<48>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
   if (D <= 80) return launch_ga<80>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);
   if (D <= 128) return launch_ga<128>(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Nq, Nk, D, scale, stream, key_bias);   // Flux

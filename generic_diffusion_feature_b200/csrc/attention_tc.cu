@@ -1,0 +1,527 @@
+// Persistent flash attention forward on tcgen05 / TMEM / TMA for every head dim of the path (40, 64, 72, 80, 128)
+// and any key count (text cross-attention with 77 keys is one masked KV tile).
+// Reference call sites: F.scaled_dot_product_attention, feature/diffusers/models/attention_processor.py:3311-3313
+// (AttnProcessor2_0) and :2335-2336 (FluxAttnProcessor2_0).
+//
+// Grid = min(#work items, #SMs) CTAs; a work item = 256 queries (two tiles of 128 rows) of one (batch, head); CTA c
+// walks items c, c + grid, ... with ONE continuous tile pipeline (the barriers count KV tiles across items, so the
+// Q / K / V loads and the S product of the next item run under the last softmax tile and the output of the current one).
+//   warp 0     : TMA producer  (Q tiles per item; K and V tiles through two rings; 128B swizzle, 64-column blocks)
+//   warp 1     : MMA issuer    (S_t = Q_t K_j^T; O_t (+)= P_t V_j with V as MN-major operand; L_t (+)= P_t 1: the
+//                               softmax denominators come from the tensor core as a 16-column product with a tile of
+//                               ones instead of 128 additions per row and tile in the softmax warps)
+//   warp 2     : TMEM allocator (S_0, S_1 | O_0, L_0 | O_1, L_1)
+//   warps 4-11 : softmax       (2 groups x 4 warps, one group per query tile; thread = one query row: S read from TMEM
+//                               once, running maximum updated lazily (O / L rescaled in TMEM only when the block maximum
+//                               exceeds the one in use by more than 2^8), P = exp2(.) -> fp16 / bf16 -> smem in the
+//                               K-major SW128 layout; a template-selected share of the exponentials is evaluated by a
+//                               degree-3 polynomial on the FMA pipe (packed fp32 pairs) to take load off the MUFU)
+// Q / K / V are read in place from the token-major projection outputs (head h = columns [h*D, h*D + D)) through 4-D
+// tensor maps (d, head, token, batch) whose innermost extent is D: the 64-column boxes are zero-filled beyond D.
+#include <stdlib.h>
+#include "ops.h"
+
+namespace gdf {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcRing = 3;
+
+template <int DPAD, int KT>
+struct TcCfg {
+  static constexpr int NB = (DPAD + 63) / 64;        // 64-column blocks of the head dim
+  static constexpr int kQBlk = 128 * 128;            // one 64-column block of a 128-row Q tile (16 KB)
+  static constexpr int kQTile = NB * kQBlk;
+  static constexpr int kKvBlk = KT * 128;            // one 64-column block of a KT-row K / V tile
+  static constexpr int kKvTile = NB * kKvBlk;
+  static constexpr int kPBlk = 128 * 128;            // P: 128 rows x 64 keys (16 KB) per block, KT / 64 blocks
+  static constexpr int kPTile = (KT / 64) * kPBlk;
+  static constexpr int kOffK = 2 * kQTile;
+  static constexpr int kOffV = kOffK + kTcRing * kKvTile;
+  static constexpr int kOffP = kOffV + kTcRing * kKvTile;
+  static constexpr int kOffOnes = kOffP + 2 * kPTile;
+  static constexpr int kOffBar = kOffOnes + 2048;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  // TMEM columns: S_t at t * KT; O_t at 2 * KT + t * kStrideO (32-column aligned), L_t (16 columns) right behind O_t
+  static constexpr int kColO = 2 * KT;
+  static constexpr int kStrideO = (DPAD + 31) / 32 * 32 + 32;
+  static_assert(2 * KT + 2 * kStrideO <= 512, "TMEM budget");
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+struct TcParams {
+  int Nq, Nk, heads, B, D;
+  int n_kv;          // KV tiles per item
+  int nqb;           // 256-query blocks per (batch, head)
+  int num_items;
+  float scale_log2;
+  float inv_scale;   // 1 / softmax scale (key bias is added in the unscaled score domain)
+  const float* key_bias;   // optional fp32 [B, Nk], added to the scaled scores
+  bf16* O;
+  int ldo;
+};
+
+// kPoly8: of every 8 (even, odd) column pairs, this many are exponentiated on the FMA pipe. kPBf16: P (and V) in bf16.
+template <int DPAD, int KT, int kPoly8, bool kPBf16>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const TcParams p) {
+  using C = TcCfg<DPAD, KT>;
+  constexpr int NB = C::NB;
+  constexpr int NC = KT / 32;    // 32-column chunks of an S tile
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* q_full = bars;                  // [2] per query tile
+  uint64_t* q_empty = q_full + 2;           // [2]
+  uint64_t* k_full = q_empty + 2;           // [ring]
+  uint64_t* k_empty = k_full + kTcRing;
+  uint64_t* v_full = k_empty + kTcRing;
+  uint64_t* v_empty = v_full + kTcRing;
+  uint64_t* s_full = v_empty + kTcRing;     // [2]
+  uint64_t* s_free = s_full + 2;            // [2] S_t(g) fully read out of TMEM
+  uint64_t* p_full = s_free + 2;            // [2]
+  uint64_t* pv_full = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.n_kv;
+  const int my_items = (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int T = my_items * n;               // KV tiles this CTA walks per query tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kTcRing; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&q_empty[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == 3) {   // tile of ones (B operand of the denominator product): 16 rows x 128 B, any layout
+    const uint32_t one2 = kPBf16 ? 0x3F803F80u : 0x3C003C00u;
+    uint32_t* o = reinterpret_cast<uint32_t*>(smem + C::kOffOnes);
+    for (int i = lane; i < 512; i += 32) o[i] = one2;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail; Q/K/V are only read from here on
+  pdl_trigger();
+
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+
+  if (warp == 0) {
+    // ================================================= TMA producer (single elected thread)
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      int item = blockIdx.x;
+      for (int it = 0; it < my_items; ++it, item += gridDim.x) {
+        const int qb = item % p.nqb;
+        const int bh = item / p.nqb;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int q0 = qb * 256;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (it > 0) mbar_wait(&q_empty[t], (it - 1) & 1);
+          mbar_arrive_expect_tx(&q_full[t], C::kQTile);
+#pragma unroll
+          for (int kb = 0; kb < NB; ++kb)
+            tma_load_4d(smem + t * C::kQTile + kb * C::kQBlk, &map_q, &q_full[t], kb * 64, h, q0 + t * 128, b);
+        }
+        for (int j = 0; j < n; ++j) {
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], C::kKvTile);
+#pragma unroll
+          for (int kb = 0; kb < NB; ++kb)
+            tma_load_4d(smem + C::kOffK + s * C::kKvTile + kb * C::kKvBlk, &map_k, &k_full[s], kb * 64, h, j * KT, b);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], C::kKvTile);
+#pragma unroll
+          for (int kb = 0; kb < NB; ++kb)
+            tma_load_4d(smem + C::kOffV + s * C::kKvTile + kb * C::kKvBlk, &map_v, &v_full[s], kb * 64, h, j * KT, b);
+          if (++s == kTcRing) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(128, KT, 0);
+    const uint32_t idesc_pv = kPBf16 ? umma_idesc_bf16(128, DPAD, 1) : umma_idesc_f16(128, DPAD, 1);
+    const uint32_t idesc_l = kPBf16 ? umma_idesc_bf16(128, 16, 0) : umma_idesc_f16(128, 16, 0);
+    const uint32_t q_addr = smem_u32(smem);
+    const uint32_t k_addr = smem_u32(smem + C::kOffK);
+    const uint32_t v_addr = smem_u32(smem + C::kOffV);
+    const uint32_t p_addr = smem_u32(smem + C::kOffP);
+    const uint64_t d_ones = umma_desc_kmajor_sw128(smem_u32(smem + C::kOffOnes));
+    auto issue_s = [&](int t, int slot) {   // S_t = Q_t K^T into TMEM columns [t*KT, t*KT + KT)
+#pragma unroll
+      for (int ks = 0; ks < DPAD / 16; ++ks) {
+        const uint64_t da = umma_desc_kmajor_sw128(q_addr + t * C::kQTile + (ks >> 2) * C::kQBlk) + 2 * (ks & 3);
+        const uint64_t db = umma_desc_kmajor_sw128(k_addr + slot * C::kKvTile + (ks >> 2) * C::kKvBlk) + 2 * (ks & 3);
+        umma_f16_ss(tmem_base + t * KT, da, db, idesc_s, ks != 0);
+      }
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int t, int slot, bool first) {  // O_t (+)= P_t V, L_t (+)= P_t 1
+      const uint32_t t_o = tmem_base + C::kColO + t * C::kStrideO;
+#pragma unroll
+      for (int k = 0; k < KT / 16; ++k) {
+        // A: P block (k / 4) of 16 KB, 32 B step inside the swizzle row; B: 16 kv rows = 2048 B per step
+        const uint64_t da = umma_desc_kmajor_sw128(p_addr + t * C::kPTile + (k >> 2) * C::kPBlk) + 2 * (k & 3);
+        const uint64_t db = umma_desc_mnmajor_sw128(v_addr + slot * C::kKvTile + k * 2048, C::kKvBlk);
+        const uint32_t acc = (k != 0 || !first) ? 1u : 0u;
+        umma_f16_ss(t_o, da, db, idesc_pv, acc);
+        umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, acc);
+      }
+      umma_commit(&pv_full[t]);
+    };
+    // Event-driven issue: each query tile advances on its own barriers (S_t(g+1) once S_t(g) has been read out of
+    // TMEM, PV_t(g) once P_t(g) is in smem), so one group never waits for the other group's softmax. g counts the KV
+    // tiles of this CTA across its work items; js / jp is the tile index inside the current item.
+    int gs[2] = {0, 0}, js[2] = {0, 0}, its[2] = {0, 0};
+    int gp[2] = {0, 0}, jp[2] = {0, 0};
+    uint32_t s_half = 0, pv_half = 0;   // bit slot: one of the two query tiles has consumed the K / V tile in that slot
+    while (gp[0] < T || gp[1] < T) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (gs[t] < T) {
+          const int g = gs[t], slot = g % kTcRing;
+          bool ready = mbar_try_wait(&k_full[slot], (g / kTcRing) & 1);
+          if (ready && g > 0) ready = mbar_try_wait(&s_free[t], (g - 1) & 1);
+          if (ready && js[t] == 0) ready = mbar_try_wait(&q_full[t], its[t] & 1);
+          if (__any_sync(0xffffffffu, ready)) {   // a completed phase observed by any lane is complete for all
+            tc_fence_after();
+            if (elect_one()) {
+              issue_s(t, slot);
+              if ((s_half >> slot) & 1) umma_commit(&k_empty[slot]);   // both query tiles have consumed this K tile
+              if (js[t] == n - 1) umma_commit(&q_empty[t]);          // last S product of the item: Q_t may be reloaded
+            }
+            s_half ^= 1u << slot;
+            __syncwarp();
+            gs[t] = g + 1;
+            if (++js[t] == n) { js[t] = 0; ++its[t]; }
+          }
+        }
+        if (gp[t] < T) {
+          const int g = gp[t], slot = g % kTcRing;
+          bool ready = mbar_try_wait(&p_full[t], g & 1);
+          if (ready) ready = mbar_try_wait(&v_full[slot], (g / kTcRing) & 1);
+          if (__any_sync(0xffffffffu, ready)) {
+            tc_fence_after();
+            if (elect_one()) {
+              issue_pv(t, slot, jp[t] == 0);
+              if ((pv_half >> slot) & 1) umma_commit(&v_empty[slot]);
+            }
+            pv_half ^= 1u << slot;
+            __syncwarp();
+            gp[t] = g + 1;
+            if (++jp[t] == n) jp[t] = 0;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================= softmax + output
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int e = warp - 4;
+    const int t = e >> 2;        // query tile of this group
+    const int quad = e & 3;      // == warp % 4: TMEM lane quadrant
+    const int r = quad * 32 + lane;              // row inside the query tile
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + t * KT;
+    const uint32_t t_o = tmem_base + lane_off + C::kColO + t * C::kStrideO;
+    const uint32_t p_row = smem_u32(smem + C::kOffP + t * C::kPTile) + r * 128;   // this thread's 128 B row (SW128)
+    const uint32_t p_swz = (r & 7) << 4;
+    const float thresh = 8.f * p.inv_scale * 0.6931471805599453f;   // lazy rescale: P = 2^(..) stays <= 2^8
+    int g = 0;
+    int item = blockIdx.x;
+    for (int it = 0; it < my_items; ++it, item += gridDim.x) {
+      const int qb = item % p.nqb;
+      const int bh = item / p.nqb;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int qrow = qb * 256 + t * 128 + r;
+      float m_run = -INFINITY;
+      for (int j = 0; j < n; ++j, ++g) {
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        float sf[KT];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sf[c * 32]));
+        tmem_ld_wait();
+        // S_t(g) is in registers: the tensor core may overwrite it with S_t(g+1) while this tile's softmax runs
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        const int kv0 = j * KT;
+        if (p.key_bias) {   // additive key bias (PixArt masked cross-attention), unscaled score domain
+          const float* kb = p.key_bias + (long long)b * p.Nk + kv0;
+#pragma unroll
+          for (int i = 0; i < KT; ++i)
+            if (kv0 + i < p.Nk) sf[i] = fmaf(__ldg(kb + i), p.inv_scale, sf[i]);
+        }
+        if (kv0 + KT > p.Nk) {   // ragged last tile: keys beyond Nk (zero-filled by TMA) are masked out
+#pragma unroll
+          for (int i = 0; i < KT; ++i)
+            if (kv0 + i >= p.Nk) sf[i] = -INFINITY;
+        }
+        // ---- row maximum (independent chains per chunk, 3-input max)
+        float mx[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          mx[c] = sf[c * 32];
+#pragma unroll
+          for (int i = 1; i < 31; i += 2) mx[c] = fmaxf(mx[c], fmaxf(sf[c * 32 + i], sf[c * 32 + i + 1]));
+          mx[c] = fmaxf(mx[c], sf[c * 32 + 31]);
+        }
+        float m_blk = mx[0];
+#pragma unroll
+        for (int c = 1; c < NC; ++c) m_blk = fmaxf(m_blk, mx[c]);
+        // P_t(g-1) V has been consumed from smem / accumulated in TMEM before P_t(g) is written or O_t is rescaled
+        if (g > 0) {
+          mbar_wait(&pv_full[t], (g - 1) & 1);
+          tc_fence_after();
+        }
+        if (__any_sync(0xffffffffu, m_blk > m_run + thresh)) {   // warp-uniform (TMEM accesses are warp-collective)
+          const float m_new = fmaxf(m_run, m_blk);
+          const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // first tile: exp2(-inf) = 0
+          m_run = m_new;
+          if (j > 0) {   // O_t and L_t of this item are live in TMEM
+#pragma unroll
+            for (int hh = 0; hh < DPAD / 16; ++hh) {
+              uint32_t o[16];
+              tmem_ld_32x16(t_o + hh * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(t_o + hh * 16, o);
+            }
+            {
+              uint32_t l = tmem_ld_32x1(t_o + DPAD);
+              tmem_ld_wait();
+              uint32_t lv[16];
+              const uint32_t ls = __float_as_uint(__uint_as_float(l) * alpha);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) lv[i] = ls;
+              tmem_st_32x16(t_o + DPAD, lv);
+            }
+            tmem_st_wait();
+          }
+        }
+        const float neg_m = -m_run * p.scale_log2;
+        // ---- P = exp2(S*scale - m*scale) -> 16-bit -> smem (K-major SW128, KT/64 blocks of 64 keys).
+        // Chunk c+1 is scaled / exponentiated between the packs of chunk c so that a pack never waits on the MUFU
+        // issued just before it.
+        auto scale_chunk = [&](int c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            ffma2(sf[c * 32 + 2 * i], sf[c * 32 + 2 * i + 1], sf[c * 32 + 2 * i], sf[c * 32 + 2 * i + 1], p.scale_log2,
+                  neg_m);
+        };
+        auto exp_pair = [&](int c, int i) {   // in place
+          float& x0 = sf[c * 32 + 2 * i];
+          float& x1 = sf[c * 32 + 2 * i + 1];
+          if (kPoly8 > 0 && (i & 7) < kPoly8) {
+            // 2^x on the FMA pipe: x = n + f (round to nearest), degree-3 minimax polynomial of 2^f, n into the exponent
+            const f32x2 xc = f2_make(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+            const f32x2 tt = f2_add(xc, f2_splat(12582912.f));
+            const f32x2 ff = f2_add(xc, f2_fma(tt, f2_splat(-1.f), f2_splat(12582912.f)));   // x - (t - magic)
+            f32x2 pp = f2_fma(f2_splat(0.0551716685f), ff, f2_splat(0.2426111251f));
+            pp = f2_fma(pp, ff, f2_splat(0.6932609677f));
+            pp = f2_fma(pp, ff, f2_splat(0.9999280572f));
+            float p0, p1, t0, t1;
+            f2_get(pp, p0, p1);
+            f2_get(tt, t0, t1);
+            x0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+            x1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+          } else {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
+          }
+        };
+        scale_chunk(0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) exp_pair(0, i);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (c < NC - 1) scale_chunk(c + 1);
+          uint32_t ph2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (c < NC - 1) exp_pair(c + 1, i);
+            if (kPBf16)
+              asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ph2[i]) : "f"(sf[c * 32 + 2 * i + 1]), "f"(sf[c * 32 + 2 * i]));
+            else
+              asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph2[i]) : "f"(sf[c * 32 + 2 * i + 1]), "f"(sf[c * 32 + 2 * i]));
+          }
+          const uint32_t blk = p_row + (c >> 1) * C::kPBlk;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
+            st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
+          }
+        }
+        // ---- publish P_t(g): smem writes visible to the tensor core (async proxy), TMEM accesses retired
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- output of the item: O_t / L_t from TMEM (each thread writes its D-column output row)
+      mbar_wait(&pv_full[t], (g - 1) & 1);
+      tc_fence_after();
+      const uint32_t l_raw = tmem_ld_32x1(t_o + DPAD);
+      tmem_ld_wait();
+      const float inv = 1.f / __uint_as_float(l_raw);
+      bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * p.D;
+#pragma unroll
+      for (int hh = 0; hh < DPAD / 32; ++hh) {
+        uint32_t oa[32];
+        tmem_ld_32x32(t_o + hh * 32, oa);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (hh * 32 + q * 8 < p.D) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
+              reinterpret_cast<uint4*>(dst)[hh * 4 + q] = u;
+            }
+          }
+        }
+      }
+      if constexpr (DPAD % 32 != 0) {   // 16-column remainder (DPAD = 48, 80)
+        constexpr int hh0 = (DPAD / 32) * 32;
+        uint32_t oa[16];
+        tmem_ld_32x16(t_o + hh0, oa);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (hh0 + q * 8 < p.D) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
+              reinterpret_cast<uint4*>(dst)[hh0 / 8 + q] = u;
+            }
+          }
+        }
+      }
+      // the next item's first P V (accumulate = 0) is only issued after this warp has published P again: the TMEM
+      // loads above are retired (tcgen05.wait::ld) and ordered by the fence before that arrive
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+
+template <int DPAD, int KT>
+static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int* smem_out) {
+  *smem_out = TcCfg<DPAD, KT>::kSmem;
+  if constexpr (DPAD == 64) {   // the SDXL / SD-2.1 head dim: every polynomial share (GDF_FA_POLY8 = 0 / 2 / 3 / 4)
+    if (!p_bf16) {
+      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false>;
+      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false>;
+    }
+  }
+  if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true> : attention_tc_kernel<DPAD, KT, 0, true>;
+  return poly8 ? attention_tc_kernel<DPAD, KT, 3, false> : attention_tc_kernel<DPAD, KT, 0, false>;
+}
+
+bool attention_tc_supports(int D) { return D == 40 || D == 64 || D == 72 || D == 80 || D == 128; }
+
+// Host: 4-D tensor maps (d, head, token, batch) over the strided Q / K / V views, box 64 x 1 x rows x 1.
+// v_f16: V (and therefore P) in fp16 bit patterns; otherwise bf16.
+int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int B,
+                        int heads, int Nq, int Nk, int D, float scale, int v_f16, const float* key_bias,
+                        cudaStream_t stream) {
+  if (!attention_tc_supports(D)) return fail(GDF_ERR_UNSUPPORTED, "attention_tc: head dim %d", D);
+  if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1 || Nq < 1) return fail(GDF_ERR_INVALID, "attention_tc: bad strides");
+  static int poly8 = -1;
+  if (poly8 < 0) {
+    const char* ep = getenv("GDF_FA_POLY8");
+    poly8 = ep ? atoi(ep) : 3;
+  }
+  const int dpad = (D + 15) / 16 * 16;
+  const int kt = dpad <= 64 ? 128 : 64;
+  int smem = 0;
+  TcKernel kern = nullptr;
+  const bool pb = v_f16 == 0;
+  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, &smem);
+  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, &smem);
+  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, &smem);
+  else kern = pick_tc_kernel<128, 64>(poly8, pb, &smem);
+  {
+    // once per distinct kernel (cheap driver call; the set is small)
+    static TcKernel configured[64];
+    static int n_conf = 0;
+    bool seen = false;
+    for (int i = 0; i < n_conf; ++i) seen |= (configured[i] == kern);
+    if (!seen) {
+      GDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (n_conf < 64) configured[n_conf++] = kern;
+    }
+  }
+  CUtensorMap mq, mk, mv;
+  auto make = [&](CUtensorMap* m, const bf16* base, int ld, int N, int rows) -> int {
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)ld * 2, (uint64_t)N * ld * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)rows, 1};
+    return make_tmap_bf16(m, base, 4, dims, str, box);
+  };
+  GDF_TRY(make(&mq, Q, ldq, Nq, 128));
+  GDF_TRY(make(&mk, K, ldk, Nk, kt));
+  GDF_TRY(make(&mv, V, ldv, Nk, kt));
+  TcParams p;
+  p.Nq = Nq;
+  p.Nk = Nk;
+  p.heads = heads;
+  p.B = B;
+  p.D = D;
+  p.n_kv = (Nk + kt - 1) / kt;
+  p.nqb = (Nq + 255) / 256;
+  p.num_items = p.nqb * heads * B;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.inv_scale = 1.f / scale;
+  p.key_bias = key_bias;
+  p.O = O;
+  p.ldo = ldo;
+  const int sms = gemm_num_sms();
+  dim3 grid(p.num_items < sms ? p.num_items : sms);
+  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcThreads), (size_t)smem, stream, mq, mk, mv, p));
+  return GDF_OK;
+}
+
+}  // namespace gdf

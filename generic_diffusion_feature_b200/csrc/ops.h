@@ -101,6 +101,12 @@ cudaError_t launch_head_mean(const __half* P, __half* out, int B, int heads, lon
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
+// persistent tcgen05 / TMEM flash attention for head dims 40 / 64 / 72 / 80 / 128 and any key count (attention_tc.cu);
+// v_f16: V (and P) are fp16 bit patterns, otherwise bf16. key_bias: optional fp32 [B, Nk] added to the scaled scores.
+bool attention_tc_supports(int D);
+int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int B,
+                        int heads, int Nq, int Nk, int D, float scale, int v_f16, const float* key_bias,
+                        cudaStream_t stream);
 // Row softmax in place over bf16 S[rows, cols] (ld), fp32 math (VAE single-head attention).
 cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaStream_t stream);
 

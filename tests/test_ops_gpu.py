@@ -287,13 +287,13 @@ def test_layernorm(cuda_dev, M, C, mod):
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk", [(2, 4, 1024, 1024), (1, 10, 4096, 4096), (2, 5, 1024, 77), (1, 2, 200, 300),
-                                           (3, 1, 64, 64)])
+                                           (3, 1, 64, 64), (4, 10, 1024, 1024), (8, 20, 1024, 77), (2, 3, 576, 576)])
 @pytest.mark.parametrize("v_f16", [False, True])
 def test_attention64(cuda_dev, B, heads, Nq, Nk, v_f16):
-    """v_f16=False: mma.sync kernel (bf16 V); v_f16=True: tcgen05/TMEM kernel (fp16 V and P, needs Nk >= 128)."""
+    """Persistent tcgen05 / TMEM kernel: v_f16=False rounds P to bf16 (bf16 V, the text cross-attention path),
+    v_f16=True keeps P and V in fp16 (self-attention). (4, 10, 1024, 1024) = 160 work items and (8, 20, 1024, 77) = 640
+    exceed the SM count, so CTAs walk several items through one continuous tile pipeline."""
     ops = _ops()
-    if v_f16 and Nk < 128:
-        pytest.skip("the tcgen05 kernel serves self-attention (Nk >= 128)")
     g = torch.Generator(device="cuda").manual_seed(8)
     C = heads * 64
     # q/k/v as column slices of a fused projection output (exercises the row pitch)
@@ -316,16 +316,23 @@ def test_attention64(cuda_dev, B, heads, Nq, Nk, v_f16):
 
 
 @pytest.mark.parametrize("D,heads,Nq,Nk", [(40, 8, 1024, 1024), (80, 8, 256, 256), (160, 8, 200, 77), (72, 16, 512, 300),
-                                          (8, 8, 256, 256), (32, 4, 100, 100)])
-def test_attention_other_head_dims(cuda_dev, D, heads, Nq, Nk):
-    """SD-1.5 (40/80/160) and PixArt (72) head dims through the padded-head-dim kernel."""
+                                          (8, 8, 256, 256), (32, 4, 100, 100), (128, 24, 1100, 1100), (72, 16, 4096, 4096),
+                                          (128, 3, 300, 77)])
+@pytest.mark.parametrize("v_f16", [False, True])
+def test_attention_other_head_dims(cuda_dev, D, heads, Nq, Nk, v_f16):
+    """SD-1.5 (40/80), PixArt (72) and Flux (128) head dims through the tcgen05 kernel (64-column blocks zero-filled
+    beyond the head dim by TMA); 160 / 8 / 32 through the padded-head-dim mma.sync kernel."""
     ops = _ops()
+    if v_f16 and D not in (40, 72, 80, 128):
+        pytest.skip("fp16 V is a tcgen05-kernel option")
     g = torch.Generator(device="cuda").manual_seed(28)
     B, C = 2, heads * D
     q = _rand_bf16(g, B * Nq, C)
     kv = _rand_bf16(g, B * Nk, 2 * C)
     k, v = kv[:, :C], kv[:, C:]
-    o = ops.attention(q, k, v, B, heads, Nq, Nk, D ** -0.5, head_dim=D)
+    if v_f16:
+        v = v.float().half().contiguous()
+    o = ops.attention(q, k, v, B, heads, Nq, Nk, D ** -0.5, head_dim=D, v_f16=v_f16)
     torch.cuda.synchronize()
     qf = q.float().reshape(B, Nq, heads, D).transpose(1, 2)
     kf = k.float().reshape(B, Nk, heads, D).transpose(1, 2)
