@@ -205,6 +205,13 @@ class FeaturePlan:
                        slots[i].order) for i in range(n)]
         self.launches = int(lib.gdf_num_launches(pipe.handle))
         self.workspace_bytes = int(lib.gdf_workspace_bytes(pipe.handle))
+        # the handle holds ONE compiled plan: whoever plans next on the same pipe (a second extractor built with
+        # external_model=pipe) replaces it; `current()` tells the owner to plan again before replaying
+        self.generation = int(lib.gdf_plan_generation(pipe.handle))
+        self._pipe = pipe
+
+    def current(self):
+        return int(self._pipe.lib.gdf_plan_generation(self._pipe.handle)) == self.generation
 
     def views(self, arena):
         """dict id -> fp16 (B, C, h, w) view of the arena, insertion order = execution order (the reference's

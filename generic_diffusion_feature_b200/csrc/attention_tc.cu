@@ -56,6 +56,7 @@ struct TcParams {
   float scale_log2;
   float inv_scale;   // 1 / softmax scale (key bias is added in the unscaled score domain)
   const float* key_bias;   // optional fp32 [B, Nk], added to the scaled scores
+  int lmode;         // how the denominator product is issued (see issue_pv)
   bf16* O;
   int ldo;
 };
@@ -183,8 +184,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       umma_commit(&s_full[t]);
     };
+    const uint32_t idesc_pvl = kPBf16 ? umma_idesc_bf16(128, DPAD + 16, 1) : umma_idesc_f16(128, DPAD + 16, 1);
+    const uint32_t ones_addr = smem_u32(smem + C::kOffOnes);
     auto issue_pv = [&](int t, int slot, bool first) {  // O_t (+)= P_t V, L_t (+)= P_t 1
       const uint32_t t_o = tmem_base + C::kColO + t * C::kStrideO;
+      if (DPAD == 64 && p.lmode == 3) {
+        // one product of N = 80: the MN-major B operand takes its first 64 columns from the V tile and the next 16
+        // from the tile of ones, addressed through the leading-dimension byte offset of the descriptor
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr + t * C::kPTile + (k >> 2) * C::kPBlk) + 2 * (k & 3);
+          const uint32_t vb = v_addr + slot * C::kKvTile + k * 2048;
+          const uint64_t db = umma_desc_mnmajor_sw128(vb, ones_addr - vb);
+          umma_f16_ss(t_o, da, db, idesc_pvl, (k != 0 || !first) ? 1u : 0u);
+        }
+        umma_commit(&pv_full[t]);
+        return;
+      }
 #pragma unroll
       for (int k = 0; k < KT / 16; ++k) {
         // A: P block (k / 4) of 16 KB, 32 B step inside the swizzle row; B: 16 kv rows = 2048 B per step
@@ -192,7 +208,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint64_t db = umma_desc_mnmajor_sw128(v_addr + slot * C::kKvTile + k * 2048, C::kKvBlk);
         const uint32_t acc = (k != 0 || !first) ? 1u : 0u;
         umma_f16_ss(t_o, da, db, idesc_pv, acc);
-        umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, acc);
+        if (p.lmode == 0) umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, acc);
+      }
+      if (p.lmode == 1) {
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr + t * C::kPTile + (k >> 2) * C::kPBlk) + 2 * (k & 3);
+          umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, (k != 0 || !first) ? 1u : 0u);
+        }
       }
       umma_commit(&pv_full[t]);
     };
@@ -516,6 +539,14 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   p.scale_log2 = scale * 1.4426950408889634f;
   p.inv_scale = 1.f / scale;
   p.key_bias = key_bias;
+  {
+    static int lmode = -1;
+    if (lmode < 0) {
+      const char* e = getenv("GDF_FA_LMODE");
+      lmode = e ? atoi(e) : 0;
+    }
+    p.lmode = lmode;
+  }
   p.O = O;
   p.ldo = ldo;
   const int sms = gemm_num_sms();

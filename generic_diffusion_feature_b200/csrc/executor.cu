@@ -23,9 +23,10 @@
 namespace gdf {
 
 struct RawW {
-  float* ptr = nullptr;
+  float* ptr = nullptr;          // fp32 copy on the device; null once released (see gdf_finalize_weights)
   std::vector<int64_t> shape;
   int64_t numel = 0;
+  bool keep = false;             // read directly at run time / plan time (biases, norm affines, conditioning MLPs)
 };
 
 struct RunCtx {
@@ -239,6 +240,9 @@ struct gdf_handle_s {
   std::unordered_map<std::string, RawW> raw;
   std::unordered_map<std::string, void*> packed;
   std::vector<void*> owned;
+  std::unordered_map<const void*, std::pair<int64_t, int64_t>> mat_dims;   // packed matrix -> (rows, cols)
+  std::unordered_map<const void*, int64_t> vec_len;                        // fp32 vector -> elements
+  uint64_t plan_generation = 0;      // bumped by every successful gdf_plan (gdf_plan_generation)
   bool finalized = false;
   // plan
   bool planned = false;
@@ -366,9 +370,47 @@ class Builder {
     h->owned.push_back(p);
     return p;
   }
+  // fp32 tensor read in place at run time: stays resident after gdf_finalize_weights
   const float* f32(const std::string& name) {
-    const RawW* r = raw(name);
+    auto it = h->raw.find(name);
+    if (it == h->raw.end()) {
+      set_err(fail(GDF_ERR_MISSING_WEIGHT, "missing weight '%s'", name.c_str()));
+      return nullptr;
+    }
+    it->second.keep = true;
+    note_vec(it->second.ptr, it->second.numel);
+    return it->second.ptr;
+  }
+  // fp32 source of a packing step: fails when the tensor was released after finalisation
+  const float* src_ptr(const RawW* r, const std::string& name) {
+    if (r && !r->ptr) set_err(fail(GDF_ERR_INVALID, "weight '%s' was released by gdf_finalize_weights; load it again "
+                                   "before asking for a new packing", name.c_str()));
     return r ? r->ptr : nullptr;
+  }
+  // ---- shape registry: every packed matrix / fp32 vector handed to an op is remembered with its extents, and the op
+  // emitters check them against the extents the ARCHITECTURE asks for (a checkpoint / config mismatch becomes
+  // GDF_ERR_SHAPE at finalisation instead of an out-of-bounds read on the device).
+  void note_mat(const void* p, int64_t rows, int64_t cols) { if (p) h->mat_dims[p] = {rows, cols}; }
+  void note_vec(const void* p, int64_t n) { if (p) h->vec_len[p] = n; }
+  bool check_mat(const void* p, int64_t rows_needed, int64_t cols, const char* what) {
+    auto it = h->mat_dims.find(p);
+    if (it == h->mat_dims.end()) return true;   // activations / slices: not a registered weight
+    if (it->second.first < rows_needed || it->second.second != cols) {
+      set_err(fail(GDF_ERR_SHAPE, "%s: weight is [%lld, %lld], the architecture needs [>=%lld, %lld]", what,
+                   (long long)it->second.first, (long long)it->second.second, (long long)rows_needed, (long long)cols));
+      return false;
+    }
+    return true;
+  }
+  bool check_vec(const void* p, int64_t n_needed, const char* what) {
+    auto it = h->vec_len.find(p);
+    if (it == h->vec_len.end()) return true;
+    if (it->second < n_needed) {
+      set_err(fail(GDF_ERR_SHAPE, "%s: vector holds %lld values, the architecture needs %lld", what,
+                   (long long)it->second, (long long)n_needed));
+      return false;
+    }
+    return true;
   }
   // fp32 vector zero-padded to n_pad entries
   const float* f32_pad(const std::string& name, int n_pad) {
@@ -376,12 +418,18 @@ class Builder {
     auto it = h->packed.find(key);
     if (it != h->packed.end()) return static_cast<const float*>(it->second);
     const RawW* r = raw(name);
-    if (!r) return nullptr;
+    if (!r || !src_ptr(r, name)) return nullptr;
+    if (r->numel > n_pad) {
+      set_err(fail(GDF_ERR_SHAPE, "%s holds %lld values, the architecture needs at most %d", name.c_str(),
+                   (long long)r->numel, n_pad));
+      return nullptr;
+    }
     float* p = static_cast<float*>(dev_alloc((size_t)n_pad * 4));
     if (!p) return nullptr;
     cudaMemset(p, 0, (size_t)n_pad * 4);
     cudaMemcpy(p, r->ptr, (size_t)r->numel * 4, cudaMemcpyDeviceToDevice);
     h->packed[key] = p;
+    note_vec(p, r->numel);
     return p;
   }
   // rows of [R, K] fp32 matrices stacked and cast to bf16; idx (host) selects/permutes rows of the stack
@@ -392,7 +440,11 @@ class Builder {
     int64_t R = 0;
     for (auto& n : names) {
       const RawW* r = raw(n);
-      if (!r) return nullptr;
+      if (!r || !src_ptr(r, n)) return nullptr;
+      if (r->shape.empty() || r->shape[0] < 1) {
+        set_err(fail(GDF_ERR_SHAPE, "%s: not a matrix", n.c_str()));
+        return nullptr;
+      }
       const int64_t k = r->numel / r->shape[0];
       if (K < 0) K = (int)k;
       if (k != K) {
@@ -416,6 +468,14 @@ class Builder {
       src = stack;
     }
     const int R_out = idx ? (int)idx->size() : (int)R;
+    if (idx)
+      for (int v : *idx)
+        if (v >= R) {
+          if (stack) cudaFree(stack);
+          set_err(fail(GDF_ERR_SHAPE, "%s: the architecture addresses row %d of a %lld-row weight", key.c_str(), v,
+                       (long long)R));
+          return nullptr;
+        }
     int* idx_dev = nullptr;
     if (idx) {
       cudaMalloc(&idx_dev, idx->size() * 4);
@@ -429,6 +489,7 @@ class Builder {
     if (stack) cudaFree(stack);
     if (idx_dev) cudaFree(idx_dev);
     h->packed[key] = dst;
+    note_mat(dst, R_out, K);
     return dst;
   }
   // rows_bf16 with LayerNorm (gamma, beta) folded in: weight columns scaled by gamma; u / c per output row (see
@@ -452,7 +513,11 @@ class Builder {
     int64_t R = 0;
     for (auto& n : names) {
       const RawW* r = raw(n);
-      if (!r) return out;
+      if (!r || !src_ptr(r, n)) return out;
+      if (r->shape.empty() || r->shape[0] < 1) {
+        set_err(fail(GDF_ERR_SHAPE, "%s: not a matrix", n.c_str()));
+        return out;
+      }
       const int64_t k = r->numel / r->shape[0];
       if (K < 0) K = (int)k;
       if (k != K) {
@@ -476,6 +541,14 @@ class Builder {
       src = stack;
     }
     const int R_out = idx ? (int)idx->size() : (int)R;
+    if (idx)
+      for (int v : *idx)
+        if (v >= R) {
+          if (stack) cudaFree(stack);
+          set_err(fail(GDF_ERR_SHAPE, "%s: the architecture addresses row %d of a %lld-row weight", key.c_str(), v,
+                       (long long)R));
+          return out;
+        }
     int* idx_dev = nullptr;
     if (idx) {
       cudaMalloc(&idx_dev, idx->size() * 4);
@@ -494,6 +567,9 @@ class Builder {
     h->packed[key] = dst;
     h->packed[key + "#u"] = u;
     h->packed[key + "#c"] = c;
+    note_mat(dst, R_out, K);
+    note_vec(u, R_out);
+    note_vec(c, R_out);
     out.w = dst;
     out.u = u;
     out.c = c;
@@ -507,10 +583,11 @@ class Builder {
     int64_t total = 0;
     for (auto& n : names) {
       const RawW* r = raw(n);
-      if (!r) return nullptr;
+      if (!r || !src_ptr(r, n)) return nullptr;
       total += r->numel;
     }
     float* d = static_cast<float*>(dev_alloc((size_t)total * 4));
+    note_vec(d, total);
     if (d) {
       int64_t off = 0;
       for (auto& n : names) {
@@ -526,7 +603,13 @@ class Builder {
     auto it = h->packed.find(key);
     if (it != h->packed.end()) return static_cast<const float*>(it->second);
     const RawW* r = raw(name);
-    if (!r) return nullptr;
+    if (!r || !src_ptr(r, name)) return nullptr;
+    for (int v : idx)
+      if (v >= r->numel) {
+        set_err(fail(GDF_ERR_SHAPE, "%s: the architecture addresses element %d of %lld", name.c_str(), v,
+                     (long long)r->numel));
+        return nullptr;
+      }
     int* idx_dev = nullptr;
     cudaMalloc(&idx_dev, idx.size() * 4);
     cudaMemcpy(idx_dev, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
@@ -537,6 +620,7 @@ class Builder {
     }
     cudaFree(idx_dev);
     h->packed[key] = dst;
+    note_vec(dst, (int64_t)idx.size());
     return dst;
   }
   // conv weight OIHW -> bf16 [O_pad][k_pad]
@@ -554,12 +638,19 @@ class Builder {
     const std::string key = name + "#conv" + std::to_string(k_pad);
     auto it = h->packed.find(key);
     if (it != h->packed.end()) return static_cast<const bf16*>(it->second);
+    if (!src_ptr(r, name)) return nullptr;
+    if (k_pad < kh * kw * I) {
+      set_err(fail(GDF_ERR_SHAPE, "%s: %d x %d x %d taps do not fit the K = %d the architecture asks for", name.c_str(),
+                   kh, kw, I, k_pad));
+      return nullptr;
+    }
     bf16* dst = static_cast<bf16*>(dev_alloc((size_t)O_pad * k_pad * 2));
     if (dst) {
       launch_pack_conv_weight(r->ptr, dst, O, O_pad, I, kh, kw, k_pad, 0);
       cudaDeviceSynchronize();
     }
     h->packed[key] = dst;
+    note_mat(dst, O_pad, k_pad);
     return dst;
   }
 
@@ -670,7 +761,10 @@ class Builder {
   void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e0,
               const Caps& caps = Caps(), int batch = 1, long long abs = 0, long long wbs = 0, int ldw = 0,
               int block_n = 0, int at = -1) {
-    if (dry || err) return;
+    if (err) return;
+    if (!check_mat(W, N, ldw ? ldw : K, "linear weight")) return;
+    if (!check_vec(e0.bias, (e0.n_out > 0 && e0.act != kActGeglu) ? e0.n_out : N, "linear bias")) return;
+    if (dry) return;
     Epilogue e = e0;
     apply_caps(e, caps, e.n_out > 0 ? e.n_out : (e.act == kActGeglu ? N / 2 : N));
     GemmLaunch g;
@@ -682,7 +776,10 @@ class Builder {
   }
   void conv3(const bf16* X, int B, int Hin, int Win, int Cin, const bf16* Wp, int Npad, int stride, int pad_lo,
              const Epilogue& e0, const Caps& caps = Caps()) {
-    if (dry || err) return;
+    if (err) return;
+    if (!check_mat(Wp, Npad, 9LL * Cin, "conv3x3 weight")) return;
+    if (!check_vec(e0.bias, e0.n_out > 0 ? e0.n_out : Npad, "conv3x3 bias")) return;
+    if (dry) return;
     Epilogue e = e0;
     apply_caps(e, caps, e.n_out > 0 ? e.n_out : Npad);
     GemmLaunch g;
@@ -696,7 +793,8 @@ class Builder {
                  bool silu) {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
-    if (dry || err) return;
+    if (err || !check_vec(gm, C, "GroupNorm weight") || !check_vec(bt, C, "GroupNorm bias")) return;
+    if (dry) return;
     float* ws = gn_ws;
     ops->tag(kKindGroupNorm, 0.0, "groupnorm HW=" + std::to_string(HW) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
@@ -709,7 +807,8 @@ class Builder {
                            bool silu, const float* sums) {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
-    if (dry || err) return;
+    if (err || !check_vec(gm, C, "GroupNorm weight") || !check_vec(bt, C, "GroupNorm bias")) return;
+    if (dry) return;
     float* ws = gn_ws;
     ops->tag(kKindGroupNorm, 0.0, "groupnorm(fused stats) HW=" + std::to_string(HW) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
@@ -720,7 +819,8 @@ class Builder {
   void layernorm(const bf16* x, bf16* y, const std::string& prefix, long long M, int C, float eps) {
     const float* gm = f32(prefix + ".weight");
     const float* bt = f32(prefix + ".bias");
-    if (dry || err) return;
+    if (err || !check_vec(gm, C, "LayerNorm weight") || !check_vec(bt, C, "LayerNorm bias")) return;
+    if (dry) return;
     ops->tag(kKindLayerNorm, 0.0, "layernorm M=" + std::to_string(M) + " C=" + std::to_string(C));
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_layernorm(x, y, gm, bt, M, C, eps, nullptr, nullptr, 0, rc.stream));
@@ -802,7 +902,9 @@ class Builder {
                     bool silu_out) {
     const float* W = f32(prefix + ".weight");
     const float* b = f32(prefix + ".bias");
-    if (dry || err) return;
+    if (err || !check_vec(W, (int64_t)N * K, "conditioning MLP weight") || !check_vec(b, N, "conditioning MLP bias"))
+      return;
+    if (dry) return;
     ops->push_back([=](const RunCtx& rc) -> int {
       OP_CUDA(launch_small_linear(x, W, b, y, B, K, N, silu_in, silu_out, rc.stream));
       return 0;
@@ -2524,9 +2626,28 @@ int gdf_destroy(gdf_handle h) {
 int gdf_load_weights(gdf_handle h, const char* const* names, const void* const* ptrs_dev, const int64_t* shapes,
                      const int* ranks, int n, void* stream) {
   if (!h) return fail(GDF_ERR_INVALID, "null handle");
+  if (n > 0 && (!names || !ptrs_dev || !shapes || !ranks)) return fail(GDF_ERR_INVALID, "gdf_load_weights: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GDF_CUDA(cudaSetDevice(h->device));
+  // Everything derived from the weights held so far is dropped: the plan (its op list holds raw pointers to biases and
+  // norm affines), every packed bf16 / folded tensor (the cache is keyed by name and would silently keep the OLD
+  // values) and the shape registry. The caller re-finalises and re-plans.
+  if (h->planned || !h->packed.empty()) {
+    GDF_CUDA(cudaDeviceSynchronize());
+    free_plan(h);
+    for (void* p : h->owned) cudaFree(p);
+    h->owned.clear();
+    h->packed.clear();
+    h->mat_dims.clear();
+    h->vec_len.clear();
+    for (auto it = h->raw.begin(); it != h->raw.end();) {   // derived entries ("vae#folded_conv_out.*") lived in `owned`
+      if (it->first.find('#') != std::string::npos) it = h->raw.erase(it);
+      else ++it;
+    }
+  }
   const int64_t* sp = shapes;
   for (int i = 0; i < n; ++i) {
+    if (ranks[i] < 0 || ranks[i] > 8) return fail(GDF_ERR_SHAPE, "gdf_load_weights: '%s' has rank %d", names[i], ranks[i]);
     RawW w;
     w.numel = 1;
     for (int d = 0; d < ranks[i]; ++d) {
@@ -2538,7 +2659,7 @@ int gdf_load_weights(gdf_handle h, const char* const* names, const void* const* 
     GDF_CUDA(cudaMemcpyAsync(w.ptr, ptrs_dev[i], (size_t)w.numel * 4, cudaMemcpyDeviceToDevice, st));
     auto it = h->raw.find(names[i]);
     if (it != h->raw.end()) {
-      cudaFree(it->second.ptr);
+      if (it->second.ptr) cudaFree(it->second.ptr);
       h->raw.erase(it);
     }
     h->raw[names[i]] = w;
@@ -2566,6 +2687,17 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   h->L = L0;
   GDF_CUDA(cudaDeviceSynchronize());
   if (r) return r;
+  // The fp32 originals of the matrices are only needed for packing: release them (SDXL: ~10 GB, Flux: ~48 GB). What
+  // the op lists read in place (biases, norm affines, conditioning MLPs, position tables) was marked `keep` by the walk.
+  const char* keep_all = getenv("GDF_KEEP_FP32_WEIGHTS");
+  if (!(keep_all && keep_all[0] == '1')) {
+    for (auto& kv : h->raw) {
+      RawW& w = kv.second;
+      if (w.keep || !w.ptr || w.shape.size() < 2 || kv.first.find('#') != std::string::npos) continue;
+      cudaFree(w.ptr);
+      w.ptr = nullptr;
+    }
+  }
   h->finalized = true;
   return GDF_OK;
 }
@@ -2626,9 +2758,12 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
   }
   if (arena_bytes_out) *arena_bytes_out = h->arena_bytes > 0 ? h->arena_bytes : 256;
   h->planned = true;
+  ++h->plan_generation;
   h->gpu_launches = (int)(h->vae_ops.size() + h->unet_ops.size());
   return GDF_OK;
 }
+
+uint64_t gdf_plan_generation(gdf_handle h) { return (h && h->planned) ? h->plan_generation : 0; }
 
 int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_dev, const void* eps_q_dev,
                      float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,
@@ -2661,9 +2796,18 @@ int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_
   return GDF_OK;
 }
 
+static int check_arena(gdf_handle h, int64_t arena_bytes, const char* who) {
+  if (arena_bytes < h->arena_bytes)
+    return fail(GDF_ERR_SHAPE, "%s: the arena holds %lld bytes, the current plan (generation %llu) writes %lld", who,
+                (long long)arena_bytes, (unsigned long long)h->plan_generation, (long long)h->arena_bytes);
+  return GDF_OK;
+}
+
 int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* pooled_dev,
-                        const void* add_time_ids_dev, void* arena_dev, void* noise_pred_out_dev, void* stream) {
+                        const void* add_time_ids_dev, void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev,
+                        void* stream) {
   if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: no plan");
+  GDF_TRY(check_arena(h, arena_bytes, "gdf_denoise_capture"));
   if (ctx_len != h->ctx_len)
     return fail(GDF_ERR_SHAPE, "gdf_denoise_capture: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
   if (h->is_dit) return fail(GDF_ERR_INVALID, "gdf_denoise_capture: this handle holds a DiT, use gdf_denoise_capture_dit");
@@ -2688,8 +2832,9 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
 }
 
 int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* ctx_mask_dev,
-                            void* arena_dev, void* noise_pred_out_dev, void* stream) {
+                            void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev, void* stream) {
   if (!h || !h->planned || !h->is_dit) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_dit: no DiT plan");
+  GDF_TRY(check_arena(h, arena_bytes, "gdf_denoise_capture_dit"));
   if (ctx_len != h->ctx_len)
     return fail(GDF_ERR_SHAPE, "gdf_denoise_capture_dit: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
   if (!ctx_dev || !arena_dev) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_dit: null input");
@@ -2711,8 +2856,9 @@ int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, i
 
 int gdf_denoise_capture_flux(gdf_handle h, float sigma, float guidance, const void* ctx_dev, int ctx_len,
                              const void* pooled_dev, const void* rope_cos_dev, const void* rope_sin_dev,
-                             void* arena_dev, void* noise_pred_out_dev, void* stream) {
+                             void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev, void* stream) {
   if (!h || !h->planned || !h->is_flux) return fail(GDF_ERR_INVALID, "gdf_denoise_capture_flux: no Flux plan");
+  GDF_TRY(check_arena(h, arena_bytes, "gdf_denoise_capture_flux"));
   if (ctx_len != h->ctx_len)
     return fail(GDF_ERR_SHAPE, "gdf_denoise_capture_flux: ctx_len %d, plan was built for %d", ctx_len, h->ctx_len);
   if (!ctx_dev || !pooled_dev || !rope_cos_dev || !rope_sin_dev || !arena_dev)

@@ -131,7 +131,7 @@ class FeatureExtractor(nn.Module):
     # ------------------------------------------------------------------------------------------ extract
     def _ensure_plan(self, batch_size, ctx_len):
         if (self._plan is None or self._plan.batch != batch_size or self._plan.img_size != self.img_size
-                or self._plan_ctx_len != ctx_len):
+                or self._plan_ctx_len != ctx_len or not self._plan.current()):
             check(self.pipe.lib.gdf_set_ctx_len(self.pipe.handle, ctx_len))
             self._plan = FeaturePlan(self.pipe, self._ids, batch_size, self.img_size)
             self._plan_ctx_len = ctx_len
@@ -196,6 +196,31 @@ class FeatureExtractor(nn.Module):
             eps_q = noise[1].to(dev, torch.float32).contiguous()
         ctx = prompt_embeds.to(dev, torch.float32).contiguous()
         pooled_d = pooled.to(dev, torch.float32).contiguous() if pooled is not None else None
+        # the C ABI takes raw pointers: every extent is checked here against the architecture first
+        ctx_dim = (pipe.flux_cfg["joint_dim"] if is_flux else pipe.dit_cfg["caption_dim"] if is_dit
+                   else pipe.unet_cfg["ctx_dim"])
+        if ctx.dim() != 3 or ctx.shape[0] != batch_size or ctx.shape[2] != ctx_dim:
+            raise ValueError("prompt embeddings must be (%d | 1, L, %d) for version '%s', got %s"
+                             % (batch_size, ctx_dim, self.version, tuple(prompt_embeds.shape)))
+        pooled_dim = (pipe.flux_cfg["pooled_dim"] if is_flux else
+                      (pipe.unet_cfg["add_in"] - 6 * pipe.unet_cfg["add_time_dim"]) if (not is_dit and
+                                                                                        pipe.unet_cfg["add_time_dim"])
+                      else None)
+        if pooled_dim is not None:
+            if pooled_d is None or tuple(pooled_d.shape) != (batch_size, pooled_dim):
+                raise ValueError("pooled text embeddings must be (%d | 1, %d) for version '%s', got %s"
+                                 % (batch_size, pooled_dim, self.version,
+                                    None if pooled is None else tuple(pooled.shape)))
+        for name, e_ in (("eps_vae", eps_vae), ("eps_q", eps_q)):
+            if tuple(e_.shape) != (batch_size, lat_ch, L, L):
+                raise ValueError("noise[%s] must be (%d, %d, %d, %d), got %s"
+                                 % (name, batch_size, lat_ch, L, L, tuple(e_.shape)))
+        if is_latents and tuple(image.shape) != (batch_size, lat_ch, L, L):
+            raise ValueError("latent input must be (%d, %d, %d, %d), got %s"
+                             % (batch_size, lat_ch, L, L, tuple(image.shape)))
+        if ctx_mask is not None and tuple(ctx_mask.shape) != (batch_size, ctx.shape[1]):
+            raise ValueError("prompt attention mask must be (%d | 1, %d), got %s"
+                             % (batch_size, ctx.shape[1], tuple(ctx_mask.shape)))
         time_ids = None
         if self.version in ('xl', 'pgv2'):
             # _get_add_time_ids (diffusion_feature.py:534-571): original_size + crop (0,0) + target_size
@@ -220,15 +245,15 @@ class FeatureExtractor(nn.Module):
                     self._rope_key = key
                 check(lib.gdf_denoise_capture_flux(pipe.handle, timestep, 1.0, _lib.ptr(ctx), ctx.shape[1],
                                                    _lib.ptr(pooled_d), _lib.ptr(self._rope[0]), _lib.ptr(self._rope[1]),
-                                                   _lib.ptr(arena), None, st))
+                                                   _lib.ptr(arena), arena.numel(), None, st))
             elif is_dit:
                 mask_d = ctx_mask.to(dev, torch.float32).contiguous() if ctx_mask is not None else None
                 check(lib.gdf_denoise_capture_dit(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(mask_d),
-                                                  _lib.ptr(arena), None, st))
+                                                  _lib.ptr(arena), arena.numel(), None, st))
             else:
                 mask_d = None
                 check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
-                                              _lib.ptr(time_ids), _lib.ptr(arena), None, st))
+                                              _lib.ptr(time_ids), _lib.ptr(arena), arena.numel(), None, st))
         feats = plan.views(arena)
         if self.feature_store.resize_ratio > 1:                  # feature_extractor.py:51-53
             with torch.cuda.device(pipe.dev_index):

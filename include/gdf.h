@@ -36,7 +36,7 @@ extern "C" {
 #define GDF_ERR_MISSING_WEIGHT (-4)
 #define GDF_ERR_SHAPE (-5)
 
-#define GDF_ABI_VERSION 1
+#define GDF_ABI_VERSION 2
 
 typedef struct gdf_handle_s* gdf_handle;
 
@@ -125,6 +125,10 @@ int gdf_destroy(gdf_handle h);
  * Call repeatedly, then gdf_finalize_weights once (checks that every parameter the architecture needs arrived). */
 int gdf_load_weights(gdf_handle h, const char* const* names, const void* const* ptrs_dev, const int64_t* shapes,
                      const int* ranks, int n, void* stream);
+/* Packs the weights (bf16, K-major; conv taps; fused / folded matrices), checks every extent against the architecture
+ * (GDF_ERR_SHAPE / GDF_ERR_MISSING_WEIGHT name the offending parameter) and releases the fp32 originals of the
+ * matrices (GDF_KEEP_FP32_WEIGHTS=1 keeps them). Loading weights again after this drops the plan and every packed
+ * tensor: finalise and plan again. */
 int gdf_finalize_weights(gdf_handle h, void* stream);
 
 /* Feature plan: replaces prepare_feature_extractor (feature/components/feature_extractor.py:92-288).
@@ -145,6 +149,10 @@ typedef struct gdf_slot {
 } gdf_slot;
 int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch, int img_size, gdf_slot* slots_out,
              int64_t* arena_bytes_out);
+/* A handle holds ONE compiled plan. Every successful gdf_plan bumps this counter; callers that share a handle (two
+ * extractors on one pipe, diffusion_feature.py:46-47 `external_model`) compare it with the value they saw after their
+ * own gdf_plan and plan again when it moved. 0 = no plan. */
+uint64_t gdf_plan_generation(gdf_handle h);
 /* Encoder-hidden-state length the next plan is built for (default 77, CLIP). Invalidates the current plan. */
 int gdf_set_ctx_len(gdf_handle h, int ctx_len);
 /* Introspection of the current plan: kernels launched per (encode + denoise) pass, internal workspace bytes. */
@@ -178,16 +186,18 @@ int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_
  *   timestep : resolved scheduler timestep (float, e.g. 50.0)
  *   ctx_dev : fp32 (B, ctx_len, cross_attention_dim) encoder hidden states
  *   pooled_dev : fp32 (B, 1280) pooled text embeds or NULL; add_time_ids_dev : fp32 (B, 6) or NULL
- *   arena_dev : caller-owned arena of arena_bytes; noise_pred_out_dev : optional fp32 (B,4,h,w) */
+ *   arena_dev : caller-owned arena of arena_bytes (checked against the plan: GDF_ERR_SHAPE when too small);
+ *   noise_pred_out_dev : optional fp32 (B,4,h,w) */
 int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* pooled_dev,
-                        const void* add_time_ids_dev, void* arena_dev, void* noise_pred_out_dev, void* stream);
+                        const void* add_time_ids_dev, void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev,
+                        void* stream);
 
 /* One DiT forward with capture (replaces pipe.transformer(...) at diffusion_feature.py:467-474).
  *   ctx_dev : fp32 (B, ctx_len, caption_channels) caption embeddings (T5), ctx_len as set by gdf_set_ctx_len
  *   ctx_mask_dev : fp32 (B, ctx_len), 1 = attend, 0 = masked (bias -10000 like the reference), or NULL = all ones
  *   noise_pred_out_dev : optional fp32 (B, out_channels, h, w) un-patchified model output */
 int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, int ctx_len, const void* ctx_mask_dev,
-                            void* arena_dev, void* noise_pred_out_dev, void* stream);
+                            void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev, void* stream);
 
 /* One Flux forward with capture (replaces self.transformer(...) at pipeline_flux_img2img.py:812-822; the reference
  * returns right after it, :841).
@@ -201,7 +211,7 @@ int gdf_denoise_capture_dit(gdf_handle h, float timestep, const void* ctx_dev, i
  *   noise_pred_out_dev : optional fp32 (B, (h/16)*(w/16), in_channels) packed model output */
 int gdf_denoise_capture_flux(gdf_handle h, float sigma, float guidance, const void* ctx_dev, int ctx_len,
                              const void* pooled_dev, const void* rope_cos_dev, const void* rope_sin_dev,
-                             void* arena_dev, void* noise_pred_out_dev, void* stream);
+                             void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ op level
  * Each hot kernel behind a plain entry point: used by the parity tests, by bench.py's roofline probe and by the

@@ -8,10 +8,13 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from generic_diffusion_feature_b200 import ops
 
-tag = "old" if os.environ.get("GDF_ATTN_TC") == "0" else "tc/poly8=" + os.environ.get("GDF_FA_POLY8", "3")
+tag = "old" if os.environ.get("GDF_ATTN_TC") == "0" else "tc/poly8=%s/lmode=%s" % (
+    os.environ.get("GDF_FA_POLY8", "3"), os.environ.get("GDF_FA_LMODE", "0"))
 g = torch.Generator(device="cuda").manual_seed(0)
 shapes = [(8, 20, 1024, 1024, 64, True), (8, 10, 4096, 4096, 64, True), (2, 10, 576, 576, 64, True),
           (8, 20, 1024, 77, 64, False), (8, 10, 4096, 77, 64, False)]
+if os.environ.get("BENCH_ATTN_ONLY"):      # one shape (ncu captures): index into the list above
+    shapes = [shapes[int(os.environ["BENCH_ATTN_ONLY"])]]
 if os.environ.get("BENCH_ATTN_ALL"):
     shapes += [(8, 16, 4096, 4096, 72, False), (8, 16, 4096, 300, 72, False), (1, 24, 4608, 4608, 128, False),
                (8, 8, 4096, 4096, 40, False)]
