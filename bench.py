@@ -204,7 +204,7 @@ def run_ours(args, rank, world, local):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line of the contract
         dist.init_process_group("nccl", device_id=torch.device(dev))
     B = args.batch
-    pipe = get_diffusion_model("xl", "float16", device=dev, weight_device=dev)
+    pipe = get_diffusion_model("xl", "float16", device=dev, weight_device=dev, synthetic=True)
     fe = FeatureExtractor(full_xl_layer(), "xl", dev, img_size=IMG, external_model=pipe)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = torch.rand(B, 3, IMG, IMG, generator=g, device=dev) * 2 - 1

@@ -39,8 +39,14 @@ DIT_CONFIGS = {
     "pixart-sigma-512": dict(layers=28, heads=16, head_dim=72, in_ch=4, out_ch=8, patch=2, caption_dim=4096,
                              sample_size=64, interpolation_scale=1.0, eps=1e-6),
 }
+# [PixArt-alpha/PixArt-XL-2-512x512 transformer/config.json, from memory]: the same 28 x (16 x 72) AdaLN-single blocks as
+# Sigma-512 (sample_size 64, interpolation_scale 1, caption_channels 4096; no resolution / aspect-ratio conditioning at
+# 512: `use_additional_conditions` is sample_size == 128 only); prompts are 120 T5 tokens (diffusion_feature.py:195-205
+# passes whatever encode_prompt returned), the VAE is the SD one (sd-vae-ft-ema, scaling_factor 0.18215).
+DIT_CONFIGS["pixart-alpha"] = dict(DIT_CONFIGS["pixart-sigma-512"], prompt_len=120)
 VAE_CONFIGS["pixart-sigma"] = VAE_CONFIGS["xl"]          # PixArt-Sigma ships the SDXL VAE
 VAE_CONFIGS["pixart-sigma-512"] = VAE_CONFIGS["xl"]
+VAE_CONFIGS["pixart-alpha"] = VAE_CONFIGS["1-5"]
 # [black-forest-labs/FLUX.1-dev transformer/config.json = the FluxTransformer2DModel defaults the reference vendors at
 # transformers/transformer_flux.py:253-266 + guidance_embeds true; vae/config.json, from memory: 16 latent channels,
 # no quant_conv, scaling_factor 0.3611, shift_factor 0.1159]
@@ -50,7 +56,7 @@ FLUX_CONFIGS = {
 }
 VAE_CONFIGS["flux"] = dict(block_out=(128, 256, 512, 512), layers=2, latent=16, eps=1e-6, scaling_factor=0.3611,
                            shift_factor=0.1159, quant_conv=False)
-_NOT_BUILT = ("pixart-alpha", "if", "hunyuan")
+_NOT_BUILT = ("if", "hunyuan")
 
 
 def flux_param_specs(cfg):
@@ -417,6 +423,81 @@ def _flux_arch(cfg):
     return a
 
 
+def expected_shapes(unet_cfg=None, vae_cfg=None, dit_cfg=None, flux_cfg=None):
+    """name -> shape of every parameter the architecture reads (prefixed 'unet.' / 'transformer.' / 'vae.')."""
+    out = {}
+    if flux_cfg is not None:
+        out.update({"transformer." + n: tuple(s) for n, s in flux_param_specs(flux_cfg)})
+    elif dit_cfg is not None:
+        out.update({"transformer." + n: tuple(s) for n, s in dit_param_specs(dit_cfg)})
+    elif unet_cfg is not None:
+        out.update({"unet." + n: tuple(s) for n, s in unet_param_specs(unet_cfg)})
+    if vae_cfg is not None:
+        out.update({"vae." + n: tuple(s) for n, s in vae_param_specs(vae_cfg)})
+    return out
+
+
+# AutoencoderKL checkpoints written before diffusers 0.18 name the mid-block attention projections query / key /
+# value / proj_attn ([diffusers modeling_utils._convert_deprecated_attention_blocks]); some store them as 1x1 convs
+_VAE_ATTN_RENAMES = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+
+
+def _read_safetensors_dir(folder):
+    """Every tensor of `folder`/*.safetensors (single file or shards), as CPU tensors."""
+    import glob
+    import os
+    from safetensors import safe_open
+    files = sorted(glob.glob(os.path.join(folder, "*.safetensors")))
+    if not files:
+        raise FileNotFoundError("no .safetensors file in %s" % folder)
+    # prefer the full-precision file when fp16 variants sit next to it (diffusion_pytorch_model[.fp16].safetensors)
+    plain = [f for f in files if ".fp16." not in os.path.basename(f)]
+    out = {}
+    for f in (plain or files):
+        with safe_open(f, framework="pt", device="cpu") as sf:
+            for k in sf.keys():
+                out[k] = sf.get_tensor(k)
+    return out
+
+
+def load_diffusers_dir(model_dir, version):
+    """Read a diffusers-layout checkpoint directory (the layout `from_pretrained(...).save_pretrained(dir)` writes and
+    the hub snapshots models.py:18-172 downloads): <dir>/unet/*.safetensors (or <dir>/transformer/ for the DiT / Flux
+    families) and <dir>/vae/*.safetensors. Returns the name -> tensor dict `B200Pipe.load_state_dict` takes: parameter
+    names exactly as diffusers writes them, prefixed 'unet.' / 'transformer.' / 'vae.' (decoder tensors are dropped:
+    the extraction path only encodes)."""
+    import os
+    if not os.path.isdir(model_dir):
+        raise FileNotFoundError("model directory %s does not exist" % model_dir)
+    is_tr = version in DIT_CONFIGS or version in FLUX_CONFIGS
+    sub = "transformer" if is_tr else "unet"
+    sd = {}
+    for k, v in _read_safetensors_dir(os.path.join(model_dir, sub)).items():
+        sd[sub + "." + k] = v
+    for k, v in _read_safetensors_dir(os.path.join(model_dir, "vae")).items():
+        if not (k.startswith("encoder.") or k.startswith("quant_conv.")):
+            continue
+        for a, b in _VAE_ATTN_RENAMES.items():
+            k = k.replace(a, b)
+        if ".attentions." in k and k.endswith(".weight") and v.dim() == 4 and v.shape[-2:] == (1, 1):
+            v = v[:, :, 0, 0]
+        sd["vae." + k] = v
+    return sd
+
+
+def save_diffusers_dir(sd, model_dir):
+    """Inverse of load_diffusers_dir for a name -> tensor dict (used to stage synthetic checkpoints on disk)."""
+    import os
+    from safetensors.torch import save_file
+    groups = {}
+    for k, v in sd.items():
+        sub, name = k.split(".", 1)
+        groups.setdefault(sub, {})[name] = v.detach().cpu().contiguous()
+    for sub, tensors in groups.items():
+        os.makedirs(os.path.join(model_dir, sub), exist_ok=True)
+        save_file(tensors, os.path.join(model_dir, sub, "diffusion_pytorch_model.safetensors"))
+
+
 class B200Pipe:
     """What `FeatureExtractor` holds in place of a diffusers pipeline on the B200 path."""
 
@@ -448,7 +529,17 @@ class B200Pipe:
         self._finalized = False
 
     def load_state_dict(self, sd, chunk=256):
-        """sd: name -> tensor ('unet.*', 'vae.*'), any float dtype / device; uploaded as fp32."""
+        """sd: name -> tensor ('unet.*', 'vae.*'), any float dtype / device; uploaded as fp32. Every tensor the
+        architecture reads is checked against its expected shape first (a checkpoint / config mismatch raises here
+        instead of reaching the device); names the architecture does not know (decoder, EMA copies, ...) are skipped."""
+        want = expected_shapes(self.unet_cfg, self.vae_cfg, self.dit_cfg, self.flux_cfg)
+        bad = ["%s: checkpoint %s, architecture %s" % (n, tuple(sd[n].shape), want[n])
+               for n in want if n in sd and tuple(sd[n].shape) != tuple(want[n])
+               and not (n.endswith("pos_embed.pos_embed"))]      # position table: validated against img_size by gdf_plan
+        if bad:
+            raise _lib.GdfError("gdf error -5: weight shapes do not match the architecture of '%s':\n  %s"
+                                % (self.version, "\n  ".join(bad[:8]) + ("\n  ..." if len(bad) > 8 else "")))
+        sd = {n: t for n, t in sd.items() if n in want or n.startswith("vae.quant_conv.")}
         if not self.vae_cfg.get("quant_conv", True) and "vae.quant_conv.weight" not in sd:
             # Flux VAE (use_quant_conv False): the executor folds conv_out . quant_conv, so feed it the identity
             nm = 2 * self.vae_cfg["latent"]
@@ -489,43 +580,48 @@ class B200Pipe:
 
 
 def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename=None, device="cuda",
-                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None, flux_cfg=None):
+                        state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None, flux_cfg=None,
+                        model_dir=None, synthetic=False):
     """Mirror of feature/components/models.py:10 for the B200 path.
 
-    There is no network and no checkpoint on disk, so unless `state_dict` (diffusers-named fp32 tensors with
-    'unet.' / 'vae.' prefixes, e.g. read from safetensors by the caller) is given, deterministic synthetic
-    weights are generated by parameter name (`synthetic_state_dict`)."""
+    Where the reference calls `Pipeline.from_pretrained(model_id)` (hub download, models.py:18-172), the weights come
+    from, in this order:
+      1. `state_dict`  - name -> tensor with diffusers parameter names prefixed 'unet.' / 'transformer.' / 'vae.';
+      2. `model_dir`   - a diffusers-layout directory (<dir>/unet|transformer/*.safetensors + <dir>/vae/*.safetensors),
+                         or the environment variable GDF_MODEL_DIR (the directory itself, or GDF_MODEL_DIR/<version>);
+      3. `synthetic=True` (or GDF_SYNTHETIC=1) - deterministic random weights generated by parameter name
+                         (`synthetic_state_dict`): benchmarks and parity tests, never a silent default.
+    With none of the three the call raises: features of a random network are not what a caller of the reference's
+    factory expects to get."""
+    import os
     if dtype not in ("float32", "float16"):
         raise NotImplementedError                      # models.py:11-16
     if offline_lora is not None:
         raise NotImplementedError("LoRA loading is outside the B200 hot path (SURVEY.md 2.1 OUT OF SCOPE)")
     if version in _NOT_BUILT:
-        raise NotImplementedError("version '%s' is not built on the B200 path yet (UNet families only)" % version)
-    if flux_cfg is not None or (version in FLUX_CONFIGS and unet_cfg is None and dit_cfg is None):
-        fcfg = flux_cfg or FLUX_CONFIGS[version]
-        vcfg = vae_cfg or VAE_CONFIGS[version]
-        pipe = B200Pipe(version, None, vcfg, device, flux_cfg=fcfg)
-        if state_dict is None:
-            state_dict = synthetic_state_dict(version, weight_device or "cpu", None, vcfg, None, fcfg)
-        pipe.load_state_dict(state_dict)
-        pipe.finalize()
-        return pipe
-    if dit_cfg is not None or (version in DIT_CONFIGS and unet_cfg is None):
-        dcfg = dit_cfg or DIT_CONFIGS[version]
-        vcfg = vae_cfg or VAE_CONFIGS[version]
-        pipe = B200Pipe(version, None, vcfg, device, dit_cfg=dcfg)
-        if state_dict is None:
-            state_dict = synthetic_state_dict(version, weight_device or "cpu", None, vcfg, dcfg)
-        pipe.load_state_dict(state_dict)
-        pipe.finalize()
-        return pipe
-    if version not in UNET_CONFIGS and unet_cfg is None:
+        raise NotImplementedError("version '%s' is not built on the B200 path (SURVEY.md 8f)" % version)
+    is_flux = flux_cfg is not None or (version in FLUX_CONFIGS and unet_cfg is None and dit_cfg is None)
+    is_dit = not is_flux and (dit_cfg is not None or (version in DIT_CONFIGS and unet_cfg is None))
+    if not is_flux and not is_dit and version not in UNET_CONFIGS and unet_cfg is None:
         raise NotImplementedError                      # models.py:173-174
-    ucfg = unet_cfg or UNET_CONFIGS[version]
+    fcfg = (flux_cfg or FLUX_CONFIGS[version]) if is_flux else None
+    dcfg = (dit_cfg or DIT_CONFIGS[version]) if is_dit else None
+    ucfg = None if (is_flux or is_dit) else (unet_cfg or UNET_CONFIGS[version])
     vcfg = vae_cfg or VAE_CONFIGS[version]
-    pipe = B200Pipe(version, ucfg, vcfg, device)
     if state_dict is None:
-        state_dict = synthetic_state_dict(version, weight_device or "cpu", ucfg, vcfg)
+        env_dir = os.environ.get("GDF_MODEL_DIR")
+        if model_dir is None and env_dir:
+            model_dir = os.path.join(env_dir, version) if os.path.isdir(os.path.join(env_dir, version)) else env_dir
+        if model_dir is not None:
+            state_dict = load_diffusers_dir(model_dir, version)
+        elif synthetic or os.environ.get("GDF_SYNTHETIC") == "1":
+            state_dict = synthetic_state_dict(version, weight_device or "cpu", ucfg, vcfg, dcfg, fcfg)
+        else:
+            raise _lib.GdfError(
+                "get_diffusion_model('%s'): no weights. Pass state_dict=, model_dir= (or set GDF_MODEL_DIR) pointing at "
+                "a diffusers-layout checkpoint, or ask for random weights explicitly with synthetic=True / "
+                "GDF_SYNTHETIC=1 (there is no network for from_pretrained)" % version)
+    pipe = B200Pipe(version, ucfg, vcfg, device, dit_cfg=dcfg, flux_cfg=fcfg)
     pipe.load_state_dict(state_dict)
     pipe.finalize()
     return pipe

@@ -7,10 +7,10 @@
 // walks items c, c + grid, ... with ONE continuous tile pipeline (the barriers count KV tiles across items, so the
 // Q / K / V loads and the S product of the next item run under the last softmax tile and the output of the current one).
 //   warp 0     : TMA producer  (Q tiles per item; K and V tiles through two rings; 128B swizzle, 64-column blocks)
-//   warp 1     : MMA issuer    (S_t = Q_t K_j^T; O_t (+)= P_t V_j with V as MN-major operand; L_t (+)= P_t 1: the
+//   warps 1, 3 : MMA issuers, one per query tile (S_t = Q_t K_j^T; O_t (+)= P_t V_j with V as MN-major operand; L_t (+)= P_t 1: the
 //                               softmax denominators come from the tensor core as a 16-column product with a tile of
 //                               ones instead of 128 additions per row and tile in the softmax warps)
-//   warp 2     : TMEM allocator (S_0, S_1 | O_0, L_0 | O_1, L_1)
+//   warp 2     : TMEM allocator (S_0, S_1 | O_0, L_0 | O_1, L_1), fills the tile of ones
 //   warps 4-11 : softmax       (2 groups x 4 warps, one group per query tile; thread = one query row: S read from TMEM
 //                               once, running maximum updated lazily (O / L rescaled in TMEM only when the block maximum
 //                               exceeds the one in use by more than 2^8), P = exp2(.) -> fp16 / bf16 -> smem in the
@@ -87,7 +87,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.n_kv;
   const int my_items = (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int T = my_items * n;               // KV tiles this CTA walks per query tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -97,9 +96,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTcRing; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);   // released by the issuers of both query tiles
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
@@ -114,8 +113,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
-  }
-  if (warp == 3) {   // tile of ones (B operand of the denominator product): 16 rows x 128 B, any layout
+    // tile of ones (B operand of the denominator product): 16 rows x 128 B, any layout
     const uint32_t one2 = kPBf16 ? 0x3F803F80u : 0x3C003C00u;
     uint32_t* o = reinterpret_cast<uint32_t*>(smem + C::kOffOnes);
     for (int i = lane; i < 512; i += 32) o[i] = one2;
@@ -128,7 +126,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   pdl_wait();      // prologue above overlaps the previous kernel's tail; Q/K/V are only read from here on
   pdl_trigger();
 
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
 
   if (warp == 0) {
     // ================================================= TMA producer (single elected thread)
@@ -165,8 +163,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================================================= MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ================================================= MMA issuers
+    const int t = warp >> 1;
     const uint32_t idesc_s = umma_idesc_bf16(128, KT, 0);
     const uint32_t idesc_pv = kPBf16 ? umma_idesc_bf16(128, DPAD, 1) : umma_idesc_f16(128, DPAD, 1);
     const uint32_t idesc_l = kPBf16 ? umma_idesc_bf16(128, 16, 0) : umma_idesc_f16(128, 16, 0);
@@ -219,50 +218,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       umma_commit(&pv_full[t]);
     };
-    // Event-driven issue: each query tile advances on its own barriers (S_t(g+1) once S_t(g) has been read out of
-    // TMEM, PV_t(g) once P_t(g) is in smem), so one group never waits for the other group's softmax. g counts the KV
-    // tiles of this CTA across its work items; js / jp is the tile index inside the current item.
-    int gs[2] = {0, 0}, js[2] = {0, 0}, its[2] = {0, 0};
-    int gp[2] = {0, 0}, jp[2] = {0, 0};
-    uint32_t s_half = 0, pv_half = 0;   // bit slot: one of the two query tiles has consumed the K / V tile in that slot
-    while (gp[0] < T || gp[1] < T) {
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (gs[t] < T) {
-          const int g = gs[t], slot = g % kTcRing;
-          bool ready = mbar_try_wait(&k_full[slot], (g / kTcRing) & 1);
-          if (ready && g > 0) ready = mbar_try_wait(&s_free[t], (g - 1) & 1);
-          if (ready && js[t] == 0) ready = mbar_try_wait(&q_full[t], its[t] & 1);
-          if (__any_sync(0xffffffffu, ready)) {   // a completed phase observed by any lane is complete for all
-            tc_fence_after();
-            if (elect_one()) {
-              issue_s(t, slot);
-              if ((s_half >> slot) & 1) umma_commit(&k_empty[slot]);   // both query tiles have consumed this K tile
-              if (js[t] == n - 1) umma_commit(&q_empty[t]);          // last S product of the item: Q_t may be reloaded
-            }
-            s_half ^= 1u << slot;
-            __syncwarp();
-            gs[t] = g + 1;
-            if (++js[t] == n) { js[t] = 0; ++its[t]; }
-          }
+    // One issuer warp per query tile (warp 1: tile 0, warp 3: tile 1). Per tile the order of events is fixed -
+    // S(g+1) may go once the softmax group has read S(g) out of TMEM (early in its tile), P V(g) once P(g) is in smem
+    // (end of its tile) - so each issuer walks that sequence with BLOCKING barrier waits: no polling over the barriers
+    // of both tiles (mbarrier.try_wait suspends the warp for a hardware time slice when the phase is not complete,
+    // which made a polling issuer the pacing role of the kernel: ncu, profiles/r02_attention_tc.md). g counts the KV
+    // tiles of this CTA across its work items; K / V slots are released by both issuers (barrier count 2).
+    int g = 0;
+    bool prev_first = false;
+    for (int it = 0; it < my_items; ++it) {
+      for (int j = 0; j < n; ++j, ++g) {
+        const int slot = g % kTcRing;
+        mbar_wait(&k_full[slot], (g / kTcRing) & 1);
+        if (g > 0) mbar_wait(&s_free[t], (g - 1) & 1);
+        if (j == 0) mbar_wait(&q_full[t], it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s(t, slot);
+          umma_commit(&k_empty[slot]);
+          if (j == n - 1) umma_commit(&q_empty[t]);   // last S product of the item: Q_t may be reloaded
         }
-        if (gp[t] < T) {
-          const int g = gp[t], slot = g % kTcRing;
-          bool ready = mbar_try_wait(&p_full[t], g & 1);
-          if (ready) ready = mbar_try_wait(&v_full[slot], (g / kTcRing) & 1);
-          if (__any_sync(0xffffffffu, ready)) {
-            tc_fence_after();
-            if (elect_one()) {
-              issue_pv(t, slot, jp[t] == 0);
-              if ((pv_half >> slot) & 1) umma_commit(&v_empty[slot]);
-            }
-            pv_half ^= 1u << slot;
-            __syncwarp();
-            gp[t] = g + 1;
-            if (++jp[t] == n) jp[t] = 0;
+        __syncwarp();
+        if (g > 0) {
+          const int gp = g - 1, pslot = gp % kTcRing;
+          mbar_wait(&p_full[t], gp & 1);
+          mbar_wait(&v_full[pslot], (gp / kTcRing) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(t, pslot, prev_first);
+            umma_commit(&v_empty[pslot]);
           }
+          __syncwarp();
         }
+        prev_first = (j == 0);
       }
+    }
+    {
+      const int gp = g - 1, pslot = gp % kTcRing;
+      mbar_wait(&p_full[t], gp & 1);
+      mbar_wait(&v_full[pslot], (gp / kTcRing) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(t, pslot, prev_first);
+        umma_commit(&v_empty[pslot]);
+      }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ================================================= softmax + output

@@ -27,6 +27,7 @@ struct RawW {
   std::vector<int64_t> shape;
   int64_t numel = 0;
   bool keep = false;             // read directly at run time / plan time (biases, norm affines, conditioning MLPs)
+  bool packed_from = false;      // a bf16 / conv / folded packing was made from it (the only tensors ever released)
 };
 
 struct RunCtx {
@@ -378,11 +379,17 @@ class Builder {
       return nullptr;
     }
     it->second.keep = true;
+    if (!it->second.ptr) {
+      set_err(fail(GDF_ERR_INVALID, "weight '%s' was released by gdf_finalize_weights but is read in place by this plan; "
+                   "load the weights again (or set GDF_KEEP_FP32_WEIGHTS=1)", name.c_str()));
+      return nullptr;
+    }
     note_vec(it->second.ptr, it->second.numel);
     return it->second.ptr;
   }
   // fp32 source of a packing step: fails when the tensor was released after finalisation
   const float* src_ptr(const RawW* r, const std::string& name) {
+    if (r) const_cast<RawW*>(r)->packed_from = true;
     if (r && !r->ptr) set_err(fail(GDF_ERR_INVALID, "weight '%s' was released by gdf_finalize_weights; load it again "
                                    "before asking for a new packing", name.c_str()));
     return r ? r->ptr : nullptr;
@@ -929,7 +936,7 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
   if (x_sums) b.groupnorm_from_sums(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true, x_sums);
   else b.groupnorm(x, t1, wp + ".norm1", B, H * W, Cin, groups, eps, true);
   float* tproj = nullptr;
-  if (emb) {
+  if (temb_ch > 0) {   // (emb itself is null during the dry weight walk)
     tproj = b.fbuf((long long)B * Cout);
     b.small_linear(emb, wp + ".time_emb_proj", tproj, B, temb_ch, Cout, true, false);  // Linear(SiLU(temb))
   }
@@ -1675,6 +1682,7 @@ static int build_dit(Builder& b) {
   bf16* hs = b.buf(M, C);
   {
     const RawW* pe = b.raw(T + "pos_embed.pos_embed");
+    if (pe) const_cast<RawW*>(pe)->keep = true;   // replicated into the plan's position table at every gdf_plan
     bf16* pos = nullptr;
     if (pe && !b.dry) {
       if (pe->numel != (int64_t)N * C)
@@ -2693,7 +2701,8 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   if (!(keep_all && keep_all[0] == '1')) {
     for (auto& kv : h->raw) {
       RawW& w = kv.second;
-      if (w.keep || !w.ptr || w.shape.size() < 2 || kv.first.find('#') != std::string::npos) continue;
+      if (w.keep || !w.packed_from || !w.ptr || w.shape.size() < 2 || kv.first.find('#') != std::string::npos)
+        continue;
       cudaFree(w.ptr);
       w.ptr = nullptr;
     }

@@ -17,8 +17,9 @@ Differences a user can observe (all documented in INTEGRATION.md):
   * version 'flux' (diffusion_feature.py:246-253 calls the whole FluxImg2ImgPipeline with strength = t/1000 and
     guidance_scale 1): prompts = (t5_embeds (1|B, 512, 4096), pooled_clip (1|B, 768)) as returned by encode_prompt
     here (the reference passes raw strings to the pipeline); noise = (eps_vae, eps_q) with 16 latent channels;
-  * control / train_unet / denoising_from / DDIM inversion, PixArt-alpha, Hunyuan
-    and IF raise NotImplementedError.
+  * weights come from `external_model`, else from the diffusers-layout directory in GDF_MODEL_DIR[/<version>], else - only
+    with GDF_SYNTHETIC=1 - from the deterministic random initialisation; there is no silent default (models.py here);
+  * control / train_unet / denoising_from / DDIM inversion, Hunyuan and IF raise NotImplementedError.
 """
 import ctypes
 
@@ -103,7 +104,11 @@ class FeatureExtractor(nn.Module):
         if prompt_file:
             with open(prompt_file, 'r') as f:
                 prompt_str = f.read()
+        import warnings
         import zlib
+        warnings.warn("FeatureExtractor.encode_prompt on the B200 path returns STAND-IN embeddings (N(0,1), seeded by "
+                      "the prompt text): no text encoder is part of this path. Encode the prompt once with the "
+                      "reference and pass the embeddings to extract() for real conditioning.", stacklevel=2)
         g = torch.Generator().manual_seed(zlib.crc32(prompt_str.encode()))
         if getattr(self.pipe, "flux_cfg", None):
             # Flux: T5 sequence (max_sequence_length 512) + CLIP pooled vector (pipeline_flux_img2img.py encode_prompt)
@@ -113,9 +118,10 @@ class FeatureExtractor(nn.Module):
             # PixArt: (prompt_embeds, prompt_attention_mask, negative_embeds, negative_mask), T5 length 300 for
             # Sigma (diffusion_feature.py:193-205); the stand-in mask keeps every token
             cd = self.pipe.dit_cfg["caption_dim"]
-            emb = torch.randn(1, 300, cd, generator=g)
-            neg = torch.randn(1, 300, cd, generator=g)
-            return emb, torch.ones(1, 300), neg, torch.ones(1, 300)
+            n_tok = self.pipe.dit_cfg.get("prompt_len", 300)     # 120 T5 tokens for PixArt-alpha, 300 for Sigma
+            emb = torch.randn(1, n_tok, cd, generator=g)
+            neg = torch.randn(1, n_tok, cd, generator=g)
+            return emb, torch.ones(1, n_tok), neg, torch.ones(1, n_tok)
         ctx_dim = self.pipe.unet_cfg["ctx_dim"]
         emb = torch.randn(1, 77, ctx_dim, generator=g)
         neg = torch.randn(1, 77, ctx_dim, generator=g)

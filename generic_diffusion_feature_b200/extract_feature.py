@@ -36,7 +36,9 @@ _FLAGS = [
     # model / capture selection
     (("--layer",), dict(type=str, help="JSON file (or nothing with --show_all_layers) naming the feature ids to keep")),
     (("--version",), dict(type=str, default="xl", help="xl | pgv2 | 2-1 | 1-5 | pixart-sigma | pixart-sigma-512 | flux")),
-    (("--dtype",), dict(type=str, default="float16", choices=("float16", "float32"), help="accepted for compatibility")),
+    (("--dtype",), dict(type=str, default="float16", choices=("float16", "float32"),
+                        help="checked like the reference (models.py:11-16); the kernels compute in bf16 with fp32 "
+                             "accumulation and the stored maps are fp16 for either value (FeatureStore casts them too)")),
     (("--offline_lora",), dict(type=str, default=None, help="not built on this path")),
     (("--offline_lora_filename",), dict(type=str, default=None, help="not built on this path")),
     (("--feature_resize",), dict(type=int, default=1, help="average-pool every stored map by this factor")),
@@ -61,6 +63,16 @@ _FLAGS = [
     (("--sample_name_first",), dict(action="store_true", help="<out>/<name>/<layer>.npy instead of <out>/<layer>/<name>.npy")),
     (("--show_all_layers",), dict(action="store_true", help="print every available feature id and exit")),
     # B200-path extras
+    (("--checkpoint",), dict(type=str, default=None,
+                             help="diffusers-layout model directory (<dir>/unet|transformer + <dir>/vae, .safetensors); "
+                                  "default: $GDF_MODEL_DIR[/<version>]")),
+    (("--prompt_embeds",), dict(type=str, default=None,
+                                help=".pt / .safetensors file holding the encoded prompt (the tuple encode_prompt returns, or "
+                                     "a dict prompt_embeds / pooled_prompt_embeds / prompt_attention_mask); text encoders "
+                                     "are not part of this path")),
+    (("--synthetic",), dict(action="store_true",
+                            help="explicit opt-in: random-init weights and/or stand-in prompt embeddings when no "
+                                 "--checkpoint / --prompt_embeds is given (benchmarks, smoke tests)")),
     (("--writer_threads",), dict(type=int, default=8, help="threads writing .npy files")),
     (("--device",), dict(type=str, default="cuda", help="cuda | cuda:N (torchrun picks cuda:LOCAL_RANK)")),
 ]
@@ -201,17 +213,43 @@ def prefetch_images(dataset, batch_size, img_size, depth=2, start=0, stop=None):
     stop = len(dataset) if stop is None else stop
 
     def work():
-        for i in range(start, stop, batch_size):
-            imgs = [Image.open(dataset[j][0]).resize((img_size, img_size)).convert("RGB")
-                    for j in range(i, min(i + batch_size, stop))]
-            q.put((i, imgs))
-        q.put(None)
+        try:
+            for i in range(start, stop, batch_size):
+                imgs = [Image.open(dataset[j][0]).resize((img_size, img_size)).convert("RGB")
+                        for j in range(i, min(i + batch_size, stop))]
+                q.put((i, imgs))
+            q.put(None)
+        except BaseException as ex:  # noqa: BLE001 - a corrupt / missing file must reach the consumer, not hang it
+            q.put(ex)
     threading.Thread(target=work, daemon=True).start()
     while True:
         item = q.get()
         if item is None:
             return
+        if isinstance(item, BaseException):
+            raise RuntimeError("image prefetch failed: %r" % (item,)) from item
         yield item
+
+
+def load_prompt_embeds(path):
+    """The tuple `extract` takes as `prompts` (diffusion_feature.py:262-283), from a .pt (torch.save of the tuple
+    encode_prompt returned, or of a dict) or a .safetensors file with the keys prompt_embeds [, negative_prompt_embeds,
+    pooled_prompt_embeds, negative_pooled_prompt_embeds | prompt_attention_mask, negative_prompt_attention_mask]."""
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        d = load_file(path)
+    else:
+        d = torch.load(path, map_location="cpu")
+    if isinstance(d, (tuple, list)):
+        return tuple(d)
+    pe = d["prompt_embeds"]
+    if "prompt_attention_mask" in d:                       # PixArt
+        return (pe, d["prompt_attention_mask"], d.get("negative_prompt_embeds", pe),
+                d.get("negative_prompt_attention_mask", d["prompt_attention_mask"]))
+    if "pooled_prompt_embeds" in d and pe.shape[-1] == 4096:    # Flux: (T5 sequence, CLIP pooled)
+        return (pe, d["pooled_prompt_embeds"])
+    return (pe, d.get("negative_prompt_embeds", pe), d.get("pooled_prompt_embeds"),
+            d.get("negative_pooled_prompt_embeds", d.get("pooled_prompt_embeds")))
 
 
 def shard_of_this_rank(n_items):
@@ -230,6 +268,17 @@ def run(args, extractor=None):
     print(f'Run folder: {args.output_dir}')
     if args.show_all_layers:
         args.layer = None
+    if args.offline_lora or args.control:
+        raise NotImplementedError("--offline_lora / --control are not built on the B200 path (SURVEY.md 2.1)")
+    if extractor is None:
+        # weights: --checkpoint, else $GDF_MODEL_DIR, else an explicit --synthetic; never a silent random network
+        if getattr(args, "checkpoint", None):
+            os.environ["GDF_MODEL_DIR"] = args.checkpoint
+        elif getattr(args, "synthetic", False) and not os.environ.get("GDF_MODEL_DIR"):
+            os.environ["GDF_SYNTHETIC"] = "1"
+        elif not os.environ.get("GDF_MODEL_DIR"):
+            raise SystemExit("no weights: pass --checkpoint <diffusers model dir> (or set GDF_MODEL_DIR), or opt in to "
+                             "random-init weights with --synthetic")
     df = extractor or FeatureExtractor(args.layer, args.version, device=args.device, dtype=args.dtype,
                                        offline_lora=args.offline_lora, offline_lora_filename=args.offline_lora_filename,
                                        feature_resize=args.feature_resize, control=args.control,
@@ -238,7 +287,14 @@ def run(args, extractor=None):
     with open(args.prompt_file, 'r') as f:
         prompts = f.read()
         print('prompt:', prompts)
-    prompts = df.encode_prompt(prompts)       # (the B200 path takes embeddings for every version, Flux included)
+    if getattr(args, "prompt_embeds", None):
+        prompts = load_prompt_embeds(args.prompt_embeds)
+    elif getattr(args, "synthetic", False) or extractor is not None:
+        prompts = df.encode_prompt(prompts)   # stand-in embeddings seeded by the prompt text (warns)
+    else:
+        raise SystemExit("no prompt embeddings: text encoders are outside this path - pass --prompt_embeds <file> "
+                         "(encode the prompt once with the reference's FeatureExtractor.encode_prompt and torch.save "
+                         "the tuple), or opt in to stand-in embeddings with --synthetic")
     writer = NpyWriter(args, dataset, args.writer_threads)
     stager = None
     in_flight = None                           # (staged copy, first index, count) of the previous batch

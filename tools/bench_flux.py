@@ -21,7 +21,7 @@ dev = "cuda:0"
 fcfg = dict(models.FLUX_CONFIGS["flux"], layers=a.layers, single_layers=a.single)
 t0 = time.time()
 pipe = models.get_diffusion_model("flux", "float16", device=dev, weight_device=dev, flux_cfg=fcfg,
-                                  vae_cfg=models.VAE_CONFIGS["flux"])
+                                  vae_cfg=models.VAE_CONFIGS["flux"], synthetic=True)
 t_load = time.time() - t0
 ids = _flux_feature_ids(fcfg)
 fe = FeatureExtractor({i: True for i in ids}, "flux", dev, img_size=a.img, external_model=pipe)
