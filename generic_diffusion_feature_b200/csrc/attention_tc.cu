@@ -23,7 +23,7 @@
 
 namespace gdf {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcHelperThreads = 128;   // warps 0-3: TMA producer, MMA issuer tile 0, TMEM allocator, MMA issuer tile 1
 constexpr int kTcRing = 3;
 
 template <int DPAD, int KT>
@@ -39,7 +39,8 @@ struct TcCfg {
   static constexpr int kOffV = kOffK + kTcRing * kKvTile;
   static constexpr int kOffP = kOffV + kTcRing * kKvTile;
   static constexpr int kOffOnes = kOffP + 2 * kPTile;
-  static constexpr int kOffBar = kOffOnes + 2048;
+  static constexpr int kOffX = kOffOnes + 2048;      // row-maximum exchange between the two threads of a row (kSplit = 2)
+  static constexpr int kOffBar = kOffX + 4096;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   // TMEM columns: S_t at t * KT; O_t at 2 * KT + t * kStrideO (32-column aligned), L_t (16 columns) right behind O_t
   static constexpr int kColO = 2 * KT;
@@ -62,13 +63,18 @@ struct TcParams {
 };
 
 // kPoly8: of every 8 (even, odd) column pairs, this many are exponentiated on the FMA pipe. kPBf16: P (and V) in bf16.
-template <int DPAD, int KT, int kPoly8, bool kPBf16>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// kSplit: softmax threads per query row. 1: 8 softmax warps (thread = row, KT columns each). 2: 16 softmax warps, the two
+// threads of a row (same TMEM lane quadrant, different warps) take half of the tile's columns each and exchange their
+// partial row maxima through shared memory: four softmax warps per SM sub-partition instead of two keep the MUFU and
+// the issue slots busy across the TMEM-load / maximum / fence / barrier phases of the others.
+template <int DPAD, int KT, int kPoly8, bool kPBf16, int kSplit>
+__global__ void __launch_bounds__(kTcHelperThreads + 256 * kSplit, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const TcParams p) {
   using C = TcCfg<DPAD, KT>;
   constexpr int NB = C::NB;
-  constexpr int NC = KT / 32;    // 32-column chunks of an S tile
+  constexpr int HC = KT / kSplit;   // S columns per softmax thread
+  constexpr int NC = HC / 32;       // ... in 32-column chunks
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -104,8 +110,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&q_full[t], 1);
       mbar_init(&q_empty[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&s_free[t], 4 * kSplit);
+      mbar_init(&p_full[t], 4 * kSplit);
       mbar_init(&pv_full[t], 1);
     }
     fence_barrier_init();
@@ -126,7 +132,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   pdl_wait();      // prologue above overlaps the previous kernel's tail; Q/K/V are only read from here on
   pdl_trigger();
 
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  if (warp < 4) {
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
 
   if (warp == 0) {
     // ================================================= TMA producer (single elected thread)
@@ -266,16 +275,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
   } else if (warp >= 4) {
     // ================================================= softmax + output
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int e = warp - 4;
-    const int t = e >> 2;        // query tile of this group
-    const int quad = e & 3;      // == warp % 4: TMEM lane quadrant
-    const int r = quad * 32 + lane;              // row inside the query tile
+    const int quad = e & 3;            // == warp % 4: TMEM lane quadrant
+    const int t = (e >> 2) & 1;        // query tile of this group
+    const int hf = e >> 3;             // column half of the row (kSplit = 2), else 0
+    const int r = quad * 32 + lane;    // row inside the query tile
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + t * KT;
+    const uint32_t t_s = tmem_base + lane_off + t * KT + hf * HC;
     const uint32_t t_o = tmem_base + lane_off + C::kColO + t * C::kStrideO;
     const uint32_t p_row = smem_u32(smem + C::kOffP + t * C::kPTile) + r * 128;   // this thread's 128 B row (SW128)
     const uint32_t p_swz = (r & 7) << 4;
+    float* xchg = reinterpret_cast<float*>(smem + C::kOffX);   // [parity][tile][half][128 rows]
+    // O / L columns this thread rescales and writes out, in 16-column chunks (the second thread of a row also owns L)
+    constexpr int n16 = DPAD / 16;
+    const int ch0 = (kSplit == 1 || hf == 0) ? 0 : (n16 + 1) / 2;
+    const int ch1 = (kSplit == 1 || hf == 1) ? n16 : (n16 + 1) / 2;
+    const bool owns_l = (kSplit == 1) || hf == 1;
     const float thresh = 8.f * p.inv_scale * 0.6931471805599453f;   // lazy rescale: P = 2^(..) stays <= 2^8
     int g = 0;
     int item = blockIdx.x;
@@ -288,7 +305,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int j = 0; j < n; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
-        float sf[KT];
+        float sf[HC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sf[c * 32]));
         tmem_ld_wait();
@@ -296,16 +313,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
-        const int kv0 = j * KT;
+        const int kv0 = j * KT + hf * HC;   // first key of this thread's columns
         if (p.key_bias) {   // additive key bias (PixArt masked cross-attention), unscaled score domain
           const float* kb = p.key_bias + (long long)b * p.Nk + kv0;
 #pragma unroll
-          for (int i = 0; i < KT; ++i)
+          for (int i = 0; i < HC; ++i)
             if (kv0 + i < p.Nk) sf[i] = fmaf(__ldg(kb + i), p.inv_scale, sf[i]);
         }
-        if (kv0 + KT > p.Nk) {   // ragged last tile: keys beyond Nk (zero-filled by TMA) are masked out
+        if (kv0 + HC > p.Nk) {   // ragged last tile: keys beyond Nk (zero-filled by TMA) are masked out
 #pragma unroll
-          for (int i = 0; i < KT; ++i)
+          for (int i = 0; i < HC; ++i)
             if (kv0 + i >= p.Nk) sf[i] = -INFINITY;
         }
         // ---- row maximum (independent chains per chunk, 3-input max)
@@ -320,18 +337,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         float m_blk = mx[0];
 #pragma unroll
         for (int c = 1; c < NC; ++c) m_blk = fmaxf(m_blk, mx[c]);
+        if constexpr (kSplit == 2) {
+          // exchange with the thread that holds the other half of this row (warp e ^ 8): slot parity g & 1 - a thread
+          // is never more than one barrier ahead of its partner, so the slot written two tiles ago has been read
+          float* slot = xchg + (((g & 1) * 2 + t) * 2) * 128;
+          slot[hf * 128 + r] = m_blk;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quad) : "memory");
+          m_blk = fmaxf(m_blk, slot[(hf ^ 1) * 128 + r]);
+        }
         // P_t(g-1) V has been consumed from smem / accumulated in TMEM before P_t(g) is written or O_t is rescaled
         if (g > 0) {
           mbar_wait(&pv_full[t], (g - 1) & 1);
           tc_fence_after();
         }
-        if (__any_sync(0xffffffffu, m_blk > m_run + thresh)) {   // warp-uniform (TMEM accesses are warp-collective)
-          const float m_new = fmaxf(m_run, m_blk);
+        if (__any_sync(0xffffffffu, m_blk > m_run + thresh)) {   // warp-uniform (TMEM accesses are warp-collective); both
+          const float m_new = fmaxf(m_run, m_blk);               // threads of a row see the same maxima
           const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // first tile: exp2(-inf) = 0
           m_run = m_new;
           if (j > 0) {   // O_t and L_t of this item are live in TMEM
-#pragma unroll
-            for (int hh = 0; hh < DPAD / 16; ++hh) {
+            for (int hh = ch0; hh < ch1; ++hh) {
               uint32_t o[16];
               tmem_ld_32x16(t_o + hh * 16, o);
               tmem_ld_wait();
@@ -339,7 +363,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
               tmem_st_32x16(t_o + hh * 16, o);
             }
-            {
+            if (owns_l) {
               uint32_t l = tmem_ld_32x1(t_o + DPAD);
               tmem_ld_wait();
               uint32_t lv[16];
@@ -397,10 +421,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             else
               asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph2[i]) : "f"(sf[c * 32 + 2 * i + 1]), "f"(sf[c * 32 + 2 * i]));
           }
-          const uint32_t blk = p_row + (c >> 1) * C::kPBlk;
+          const int col0 = hf * HC + c * 32;                       // first tile column of this chunk
+          const uint32_t blk = p_row + (col0 >> 6) * C::kPBlk;     // P block of 64 keys
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int chunk = (c & 1) * 4 + q;   // 16 B chunk inside the 128 B row of this block
+            const int chunk = ((col0 & 63) >> 3) + q;   // 16 B chunk inside the 128 B row of this block
             st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
           }
         }
@@ -410,53 +435,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
-      // ---- output of the item: O_t / L_t from TMEM (each thread writes its D-column output row)
+      // ---- output of the item: O_t / L_t from TMEM (each thread writes its 16-column chunks of the output row)
       mbar_wait(&pv_full[t], (g - 1) & 1);
       tc_fence_after();
       const uint32_t l_raw = tmem_ld_32x1(t_o + DPAD);
       tmem_ld_wait();
       const float inv = 1.f / __uint_as_float(l_raw);
       bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * p.D;
-#pragma unroll
-      for (int hh = 0; hh < DPAD / 32; ++hh) {
-        uint32_t oa[32];
-        tmem_ld_32x32(t_o + hh * 32, oa);
-        tmem_ld_wait();
-        if (qrow < p.Nq) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (hh * 32 + q * 8 < p.D) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
-              u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
-              u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
-              u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
-              reinterpret_cast<uint4*>(dst)[hh * 4 + q] = u;
-            }
-          }
-        }
-      }
-      if constexpr (DPAD % 32 != 0) {   // 16-column remainder (DPAD = 48, 80)
-        constexpr int hh0 = (DPAD / 32) * 32;
+      for (int hh = ch0; hh < ch1; ++hh) {
         uint32_t oa[16];
-        tmem_ld_32x16(t_o + hh0, oa);
+        tmem_ld_32x16(t_o + hh * 16, oa);
         tmem_ld_wait();
         if (qrow < p.Nq) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            if (hh0 + q * 8 < p.D) {
+            if (hh * 16 + q * 8 < p.D) {
               uint4 u;
               u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
               u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
               u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
               u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
-              reinterpret_cast<uint4*>(dst)[hh0 / 8 + q] = u;
+              reinterpret_cast<uint4*>(dst)[hh * 2 + q] = u;
             }
           }
         }
       }
-      // the next item's first P V (accumulate = 0) is only issued after this warp has published P again: the TMEM
-      // loads above are retired (tcgen05.wait::ld) and ordered by the fence before that arrive
+      // the next item's first P V (accumulate = 0) is only issued after every softmax warp of the tile has published P
+      // again: the TMEM loads above are retired (tcgen05.wait::ld) and ordered by the fence before that arrive
     }
   }
 
@@ -470,17 +475,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
-template <int DPAD, int KT>
-static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int* smem_out) {
-  *smem_out = TcCfg<DPAD, KT>::kSmem;
+template <int DPAD, int KT, int kSplit>
+static TcKernel pick_tc_kernel2(int poly8, bool p_bf16) {
   if constexpr (DPAD == 64) {   // the SDXL / SD-2.1 head dim: every polynomial share (GDF_FA_POLY8 = 0 / 2 / 3 / 4)
     if (!p_bf16) {
-      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false>;
-      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false>;
+      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, kSplit>;
+      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, kSplit>;
     }
   }
-  if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true> : attention_tc_kernel<DPAD, KT, 0, true>;
-  return poly8 ? attention_tc_kernel<DPAD, KT, 3, false> : attention_tc_kernel<DPAD, KT, 0, false>;
+  if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true, kSplit> : attention_tc_kernel<DPAD, KT, 0, true, kSplit>;
+  return poly8 ? attention_tc_kernel<DPAD, KT, 3, false, kSplit> : attention_tc_kernel<DPAD, KT, 0, false, kSplit>;
+}
+template <int DPAD, int KT>
+static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int split, int* smem_out) {
+  *smem_out = TcCfg<DPAD, KT>::kSmem;
+  return split == 2 ? pick_tc_kernel2<DPAD, KT, 2>(poly8, p_bf16) : pick_tc_kernel2<DPAD, KT, 1>(poly8, p_bf16);
 }
 
 bool attention_tc_supports(int D) { return D == 40 || D == 64 || D == 72 || D == 80 || D == 128; }
@@ -492,20 +501,22 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
                         cudaStream_t stream) {
   if (!attention_tc_supports(D)) return fail(GDF_ERR_UNSUPPORTED, "attention_tc: head dim %d", D);
   if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1 || Nq < 1) return fail(GDF_ERR_INVALID, "attention_tc: bad strides");
-  static int poly8 = -1;
+  static int poly8 = -1, split = -1;
   if (poly8 < 0) {
     const char* ep = getenv("GDF_FA_POLY8");
-    poly8 = ep ? atoi(ep) : 3;
+    poly8 = ep ? atoi(ep) : 0;
+    const char* es = getenv("GDF_FA_SPLIT");
+    split = es ? atoi(es) : 2;
   }
   const int dpad = (D + 15) / 16 * 16;
   const int kt = dpad <= 64 ? 128 : 64;
   int smem = 0;
   TcKernel kern = nullptr;
   const bool pb = v_f16 == 0;
-  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, &smem);
-  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, &smem);
-  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, &smem);
-  else kern = pick_tc_kernel<128, 64>(poly8, pb, &smem);
+  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, split, &smem);
+  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, split, &smem);
+  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, split, &smem);
+  else kern = pick_tc_kernel<128, 64>(poly8, pb, split, &smem);
   {
     // once per distinct kernel (cheap driver call; the set is small)
     static TcKernel configured[64];
@@ -543,7 +554,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
     static int lmode = -1;
     if (lmode < 0) {
       const char* e = getenv("GDF_FA_LMODE");
-      lmode = e ? atoi(e) : 0;
+      lmode = e ? atoi(e) : 3;
     }
     p.lmode = lmode;
   }
@@ -551,7 +562,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   p.ldo = ldo;
   const int sms = gemm_num_sms();
   dim3 grid(p.num_items < sms ? p.num_items : sms);
-  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcThreads), (size_t)smem, stream, mq, mk, mv, p));
+  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcHelperThreads + 256 * (split == 2 ? 2 : 1)), (size_t)smem, stream, mq, mk, mv, p));
   return GDF_OK;
 }
 

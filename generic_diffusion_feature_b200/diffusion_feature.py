@@ -126,8 +126,10 @@ class FeatureExtractor(nn.Module):
         emb = torch.randn(1, 77, ctx_dim, generator=g)
         neg = torch.randn(1, 77, ctx_dim, generator=g)
         if self.version in ('xl', 'pgv2'):
-            pooled = torch.randn(1, 1280, generator=g)
-            npooled = torch.randn(1, 1280, generator=g)
+            uc = self.pipe.unet_cfg
+            pd = uc["add_in"] - 6 * uc["add_time_dim"]      # 1280 for SDXL (projection_dim of text_encoder_2)
+            pooled = torch.randn(1, pd, generator=g)
+            npooled = torch.randn(1, pd, generator=g)
             return emb, neg, pooled, npooled
         return emb, neg, None, None
 

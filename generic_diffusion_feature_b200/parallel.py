@@ -25,18 +25,35 @@ def max_over_ranks(value, device="cpu"):
 
 
 def gather_to_rank0(tensor, counts=None):
-    """Gather per-rank result rows (e.g. argmax indices of this rank's image pairs, shape [n_local, ...]) on rank 0.
-    `counts`: rows per rank (defaults to equal). Returns the concatenated tensor on rank 0, None elsewhere."""
+    """Gather per-rank result rows (argmax indices of this rank's image pairs, resized feature stacks, ...; shape
+    [n_local, ...]) on rank 0. `counts`: rows per rank (defaults to equal). Returns the concatenated tensor on rank 0,
+    None elsewhere.
+    Point-to-point: every non-root rank sends exactly its own rows to rank 0 (NCCL send / recv over NVLink, batched
+    into one group) - no padding and nothing delivered to ranks that do not need it (an all_gather would move
+    world x the bytes). Rank 0 receives straight into slices of the output tensor."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return tensor
     world, rank = dist.get_world_size(), dist.get_rank()
     if counts is None:
         counts = [tensor.shape[0]] * world
-    mx = max(counts)
-    pad = torch.zeros((mx,) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
-    pad[:tensor.shape[0]] = tensor
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
+    tensor = tensor.contiguous()
     if rank != 0:
+        if counts[rank] > 0:
+            dist.send(tensor[:counts[rank]], dst=0)
         return None
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    out = torch.empty((sum(counts),) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+    out[:counts[0]] = tensor[:counts[0]]
+    ops, off = [], counts[0]
+    for r in range(1, world):
+        if counts[r] > 0:
+            ops.append(dist.P2POp(dist.irecv, out[off:off + counts[r]], r))
+        off += counts[r]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
+
+
+def gather_bytes(counts, row_bytes):
+    """Bytes that cross the interconnect in gather_to_rank0 (everything but rank 0's own rows)."""
+    return sum(counts[1:]) * row_bytes

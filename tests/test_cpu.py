@@ -519,3 +519,65 @@ def test_two_rank_sharding_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert rows == list(range(7)) and mx == 11.0
+
+
+def test_checkpoint_dir_round_trip(tmp_path):
+    """get_diffusion_model's checkpoint source (reference: Pipeline.from_pretrained, models.py:18-172): a diffusers-layout
+    directory written by save_diffusers_dir reads back name-for-name and bit-for-bit through load_diffusers_dir; VAE
+    checkpoints in the pre-0.18 naming (query / key / value / proj_attn stored as 1x1 convs) are converted; decoder
+    tensors are dropped."""
+    m = _models()
+    from common import TINY_VAE, TINY_XL
+    sd = m.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    d = str(tmp_path / "ckpt")
+    m.save_diffusers_dir(sd, d)
+    back = m.load_diffusers_dir(d, "xl")
+    assert set(back) == set(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+    assert set(back) == set(m.expected_shapes(TINY_XL, TINY_VAE))
+    # old VAE naming + a decoder tensor
+    legacy = {}
+    for k, v in sd.items():
+        if not k.startswith("vae."):
+            continue
+        k2 = k[4:]
+        for new, old in ((".to_q.", ".query."), (".to_k.", ".key."), (".to_v.", ".value."), (".to_out.0.", ".proj_attn.")):
+            if new in k2:
+                k2 = k2.replace(new, old)
+                if k2.endswith(".weight"):
+                    v = v[:, :, None, None]
+        legacy[k2] = v.contiguous()
+    legacy["decoder.conv_in.weight"] = torch.zeros(4, 4, 3, 3)
+    from safetensors.torch import save_file
+    save_file(legacy, os.path.join(d, "vae", "diffusion_pytorch_model.safetensors"))
+    back = m.load_diffusers_dir(d, "xl")
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_no_silent_synthetic_weights(monkeypatch):
+    """Without state_dict / model_dir / GDF_MODEL_DIR / an explicit synthetic opt-in the factory raises (the reference
+    would download a checkpoint here; a random network must never be a silent default). Checked before any device use."""
+    m = _models()
+    from generic_diffusion_feature_b200._lib import GdfError
+    monkeypatch.delenv("GDF_MODEL_DIR", raising=False)
+    monkeypatch.delenv("GDF_SYNTHETIC", raising=False)
+    with pytest.raises(GdfError, match="no weights"):
+        m.get_diffusion_model("xl", "float16", device="cuda:0")
+    with pytest.raises(FileNotFoundError):
+        m.get_diffusion_model("xl", "float16", device="cuda:0", model_dir="/nonexistent/gdf-model-dir")
+    assert "pixart-alpha" in m.DIT_CONFIGS and m.VAE_CONFIGS["pixart-alpha"]["scaling_factor"] == 0.18215
+
+
+def test_cli_prefetch_error_reaches_the_consumer(tmp_path):
+    """A corrupt / missing input file must raise in the consumer, not leave it blocked on the queue."""
+    from generic_diffusion_feature_b200.extract_feature import prefetch_images
+    from PIL import Image
+    good = str(tmp_path / "a.png")
+    Image.new("RGB", (8, 8)).save(good)
+    bad = str(tmp_path / "b.png")
+    open(bad, "wb").write(b"not an image")
+    got = []
+    with pytest.raises(RuntimeError, match="image prefetch failed"):
+        for first, imgs in prefetch_images([(good, "a"), (bad, "b")], 1, 8):
+            got.append(first)
+    assert got == [0]

@@ -409,3 +409,98 @@ def test_full_size_sdxl_1024_parity(cuda_dev):
     rows = compare_maps(got, want)
     bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
     assert not bad, "full-size maps out of tolerance: %s" % bad[:8]
+
+
+@pytest.mark.gpu
+def test_two_extractors_share_one_pipe(cuda_dev):
+    """the compiled plan lives on the pipe handle. Two extractors built on one pipe (external_model) with
+    different selections alternate: each must notice that the other re-planned (gdf_plan_generation) and plan again
+    instead of replaying the other's op list into its own arena; a too-small arena is rejected by the C ABI."""
+    import ctypes
+    from generic_diffusion_feature_b200 import _lib
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    image, ctx, pooled, ev, eq = make_inputs(2, 128, TINY_XL["ctx_dim"], 64)
+    ids = _unet_feature_ids(TINY_XL)
+    fe_a = FeatureExtractor({i: True for i in ids}, "xl", "cuda:0", img_size=128, external_model=pipe)
+    fe_b = FeatureExtractor({"mid-vit-out": True, "unet-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
+    run = lambda fe: {k: v.float().cpu() for k, v in fe.extract((ctx, ctx, pooled, pooled), 2, image.cuda(),
+                                                                image_type="tensors", t=50, noise=(ev, eq)).items()}
+    a1 = run(fe_a)
+    b1 = run(fe_b)          # re-plans the shared handle
+    a2 = run(fe_a)          # must re-plan again (the cached FeaturePlan is stale)
+    b2 = run(fe_b)
+    assert list(a2.keys()) == ids and list(b2.keys()) == ["mid-vit-out", "unet-out"]
+    for k in ids:           # GroupNorm statistics use atomics: equal up to summation order
+        assert torch.allclose(a1[k], a2[k], rtol=2e-2, atol=2e-2), k
+    for k in b1:
+        assert torch.allclose(b1[k], b2[k], rtol=2e-2, atol=2e-2) and torch.allclose(b1[k], a1[k], rtol=2e-2, atol=2e-2)
+    # the ABI rejects an arena smaller than the current plan writes
+    small = torch.empty(16, dtype=torch.uint8, device="cuda:0")
+    rc = pipe.lib.gdf_denoise_capture(pipe.handle, 50.0, _lib.ptr(ctx.cuda().repeat(2, 1, 1).contiguous()), 77,
+                                      _lib.ptr(pooled.cuda().repeat(2, 1).contiguous()),
+                                      _lib.ptr(torch.zeros(2, 6, device="cuda:0")), _lib.ptr(small), small.numel(), None,
+                                      _lib.stream_ptr())
+    assert rc == -5 and b"arena" in pipe.lib.gdf_last_error()
+
+
+@pytest.mark.gpu
+def test_reloading_weights_replaces_every_packed_tensor(cuda_dev):
+    """gdf_load_weights on a planned handle drops the plan and the packed bf16 / conv / folded caches, so the
+    second state dict is the one that runs (the name-keyed cache used to keep the old values)."""
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd_a = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    sd_b = {k: (v * 1.25 if v.dim() >= 2 else v + 0.01) for k, v in sd_a.items()}
+    image, ctx, pooled, ev, eq = make_inputs(1, 128, TINY_XL["ctx_dim"], 64)
+    layer = {"mid-vit-out": True, "up-level1-repeat0-res-out": True, "unet-out": True}
+
+    def run(pipe):
+        fe = FeatureExtractor(layer, "xl", "cuda:0", img_size=128, external_model=pipe)
+        out = fe.extract((ctx, ctx, pooled, pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+        torch.cuda.synchronize()
+        return {k: v.float().cpu() for k, v in out.items()}
+
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd_a, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    got_a = run(pipe)
+    pipe.load_state_dict(sd_b)
+    pipe.finalize()
+    got_b = run(pipe)
+    fresh = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd_b, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    want_b = run(fresh)
+    for k in layer:
+        assert torch.allclose(got_b[k], want_b[k], rtol=2e-2, atol=2e-2), k
+        assert not torch.allclose(got_b[k], got_a[k], rtol=2e-2, atol=2e-2), k
+
+
+@pytest.mark.gpu
+def test_weight_and_input_shapes_are_checked(cuda_dev):
+    """a checkpoint / config mismatch and wrongly shaped conditioning raise instead of reaching the device."""
+    from generic_diffusion_feature_b200._lib import GdfError
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+    bad = dict(sd)
+    k = "unet.mid_block.attentions.0.transformer_blocks.0.attn1.to_q.weight"
+    bad[k] = torch.zeros(sd[k].shape[0] * 2, sd[k].shape[1])
+    with pytest.raises(GdfError, match="shapes do not match"):
+        models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=bad, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    missing = {n: v for n, v in sd.items() if n != "unet.conv_out.bias"}
+    with pytest.raises(GdfError, match="missing weight"):
+        models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=missing, unet_cfg=TINY_XL,
+                                   vae_cfg=TINY_VAE)
+    pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+    fe = FeatureExtractor({"unet-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
+    image, ctx, pooled, ev, eq = make_inputs(1, 128, TINY_XL["ctx_dim"], 64)
+    with pytest.raises(ValueError, match="prompt embeddings"):
+        fe.extract((ctx[..., :-8], ctx, pooled, pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    with pytest.raises(ValueError, match="pooled"):
+        fe.extract((ctx, ctx, pooled[:, :-1], pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev, eq))
+    with pytest.raises(ValueError, match="noise"):
+        fe.extract((ctx, ctx, pooled, pooled), 1, image.cuda(), image_type="tensors", t=50, noise=(ev[:, :, :-1], eq))
