@@ -65,9 +65,12 @@ struct TcParams {
 // kPoly8: of every 8 (even, odd) column pairs, this many are exponentiated on the FMA pipe. kPBf16: P (and V) in bf16.
 // kSplit: softmax threads per query row. 1: 8 softmax warps (thread = row, KT columns each). 2: 16 softmax warps, the two
 // threads of a row (same TMEM lane quadrant, different warps) take half of the tile's columns each and exchange their
-// partial row maxima through shared memory: four softmax warps per SM sub-partition instead of two keep the MUFU and
-// the issue slots busy across the TMEM-load / maximum / fence / barrier phases of the others.
-template <int DPAD, int KT, int kPoly8, bool kPBf16, int kSplit>
+// partial row maxima through shared memory: four softmax warps per SM sub-partition instead of two.
+// kPP (kSplit = 1): the two softmax groups take turns in the exponential phase through a pair of named barriers. Left
+// alone the groups run in lockstep (they wait on the same K / V tiles), so both are in their MUFU-bound phase at once
+// (each at half rate) and then both in their TMEM-load / maximum / fence phases (MUFU idle); alternating puts one
+// group's exponentials under the other's loads and barrier round trips.
+template <int DPAD, int KT, int kPoly8, bool kPBf16, int kSplit, bool kPP = false>
 __global__ void __launch_bounds__(kTcHelperThreads + 256 * kSplit, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const TcParams p) {
@@ -216,7 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint64_t db = umma_desc_mnmajor_sw128(v_addr + slot * C::kKvTile + k * 2048, C::kKvBlk);
         const uint32_t acc = (k != 0 || !first) ? 1u : 0u;
         umma_f16_ss(t_o, da, db, idesc_pv, acc);
-        if (p.lmode == 0) umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, acc);
+        if (p.lmode == 0 || p.lmode == 3) umma_f16_ss(t_o + DPAD, da, d_ones, idesc_l, acc);
       }
       if (p.lmode == 1) {
 #pragma unroll
@@ -296,6 +299,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float thresh = 8.f * p.inv_scale * 0.6931471805599453f;   // lazy rescale: P = 2^(..) stays <= 2^8
     int g = 0;
     int item = blockIdx.x;
+    const int g_last = my_items * n - 1;
+    if (kPP && t == 1) asm volatile("bar.arrive 9, 256;" ::: "memory");   // group 0 goes first
     for (int it = 0; it < my_items; ++it, item += gridDim.x) {
       const int qb = item % p.nqb;
       const int bh = item / p.nqb;
@@ -376,6 +381,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         const float neg_m = -m_run * p.scale_log2;
+        if (kPP) {   // wait for the other group to leave its exponential phase
+          if (t == 0) asm volatile("bar.sync 9, 256;" ::: "memory");
+          else asm volatile("bar.sync 10, 256;" ::: "memory");
+        }
         // ---- P = exp2(S*scale - m*scale) -> 16-bit -> smem (K-major SW128, KT/64 blocks of 64 keys).
         // Chunk c+1 is scaled / exponentiated between the packs of chunk c so that a pack never waits on the MUFU
         // issued just before it.
@@ -428,6 +437,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const int chunk = ((col0 & 63) >> 3) + q;   // 16 B chunk inside the 128 B row of this block
             st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
           }
+        }
+        if (kPP) {   // hand the exponential phase over
+          if (t == 0) asm volatile("bar.arrive 10, 256;" ::: "memory");
+          else if (g != g_last) asm volatile("bar.arrive 9, 256;" ::: "memory");
         }
         // ---- publish P_t(g): smem writes visible to the tensor core (async proxy), TMEM accesses retired
         fence_proxy_async_smem();
@@ -487,8 +500,16 @@ static TcKernel pick_tc_kernel2(int poly8, bool p_bf16) {
   return poly8 ? attention_tc_kernel<DPAD, KT, 3, false, kSplit> : attention_tc_kernel<DPAD, KT, 0, false, kSplit>;
 }
 template <int DPAD, int KT>
-static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int split, int* smem_out) {
+static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int split, int pp, int* smem_out) {
   *smem_out = TcCfg<DPAD, KT>::kSmem;
+  if constexpr (DPAD == 64) {
+    if (pp && split != 2 && !p_bf16) {
+      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, 1, true>;
+      if (poly8 == 3) return attention_tc_kernel<DPAD, KT, 3, false, 1, true>;
+      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, 1, true>;
+      return attention_tc_kernel<DPAD, KT, 0, false, 1, true>;
+    }
+  }
   return split == 2 ? pick_tc_kernel2<DPAD, KT, 2>(poly8, p_bf16) : pick_tc_kernel2<DPAD, KT, 1>(poly8, p_bf16);
 }
 
@@ -501,22 +522,24 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
                         cudaStream_t stream) {
   if (!attention_tc_supports(D)) return fail(GDF_ERR_UNSUPPORTED, "attention_tc: head dim %d", D);
   if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1 || Nq < 1) return fail(GDF_ERR_INVALID, "attention_tc: bad strides");
-  static int poly8 = -1, split = -1;
+  static int poly8 = -1, split = -1, pp = 0;
   if (poly8 < 0) {
     const char* ep = getenv("GDF_FA_POLY8");
     poly8 = ep ? atoi(ep) : 0;
     const char* es = getenv("GDF_FA_SPLIT");
-    split = es ? atoi(es) : 2;
+    split = es ? atoi(es) : 1;
+    const char* e2 = getenv("GDF_FA_PP");
+    pp = e2 ? atoi(e2) : 0;
   }
   const int dpad = (D + 15) / 16 * 16;
   const int kt = dpad <= 64 ? 128 : 64;
   int smem = 0;
   TcKernel kern = nullptr;
   const bool pb = v_f16 == 0;
-  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, split, &smem);
-  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, split, &smem);
-  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, split, &smem);
-  else kern = pick_tc_kernel<128, 64>(poly8, pb, split, &smem);
+  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, split, pp, &smem);
+  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, split, pp, &smem);
+  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, split, pp, &smem);
+  else kern = pick_tc_kernel<128, 64>(poly8, pb, split, pp, &smem);
   {
     // once per distinct kernel (cheap driver call; the set is small)
     static TcKernel configured[64];
