@@ -23,7 +23,7 @@ EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
     "gdf_create", "gdf_create_dit", "gdf_denoise_capture_dit", "gdf_create_flux", "gdf_denoise_capture_flux", "gdf_op_attention_bias", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
     "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
-    "gdf_plan_generation",
+    "gdf_plan_generation", "gdf_control_residual_shapes", "gdf_set_control_residuals",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
@@ -155,6 +155,8 @@ def load():
         lib.gdf_encode_noise.argtypes = [P, P, P, P, c_float, c_float, c_float, P, P]
         lib.gdf_encode_latents.argtypes = [P, P, P, c_float, c_float, c_float, P, P]
         lib.gdf_denoise_capture.argtypes = [P, c_float, P, c_int, P, P, P, c_int64, P, P]
+        lib.gdf_control_residual_shapes.argtypes = [P, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int]
+        lib.gdf_set_control_residuals.argtypes = [P, ctypes.POINTER(P), c_int, P]
         lib.gdf_plan_generation.argtypes = [P]
         lib.gdf_plan_generation.restype = ctypes.c_uint64
         lib.gdf_set_ctx_len.argtypes = [P, c_int]

@@ -159,6 +159,20 @@ __global__ void latents_qsample_kernel(const float* __restrict__ z, const float*
     latent_nhwc[((long long)bb * HW + p) * C + c] = __float2bfloat16_rn(xt * s);
   }
 }
+// ControlNet residual (fp32 NCHW (B, C, HW)) added into a bf16 NHWC tensor / column slice: dst[(b*HW + p)*ld + c] += r
+// (unet_2d_condition.py:1236-1247 down_block_additional_residuals, :1261-1275 mid_block_additional_residual)
+__global__ void add_residual_nchw_kernel(bf16* __restrict__ dst, int ld, const float* __restrict__ res, int B, int HW,
+                                         int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const int p = (int)(r % HW), b = (int)(r / HW);
+    bf16* d = dst + ((long long)b * HW + p) * ld + c;
+    *d = __float2bfloat16_rn(__bfloat162float(*d) + res[((long long)b * C + c) * HW + p]);
+  }
+}
 // moments/noise-pred style NHWC bf16/f32 [B, HW, C] -> NCHW fp32 (B, C, HW)
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
   const long long total = (long long)B * HW * C;
@@ -268,6 +282,11 @@ struct gdf_handle_s {
   bf16* latent_nhwc = nullptr;   // [B, L*L, 4] model input
   int64_t unet_in_cap = -1;
   int gpu_launches = 0;
+  // ControlNet residual inputs of the next UNet forward (borrowed device pointers, fp32 NCHW); n_ctrl = 0: none
+  std::vector<const float*> ctrl_down;
+  const float* ctrl_mid = nullptr;
+  int n_skips = 0;                   // skip tensors of the planned UNet (= expected number of down residuals)
+  std::vector<std::pair<int, int>> skip_shapes;   // (channels, side) per skip, push order
 };
 
 namespace gdf {
@@ -1501,6 +1520,34 @@ static int build_unet(Builder& b) {
     cur = nullptr;
   }
 
+  // ---- ControlNet residual inputs (unet_2d_condition.py:1236-1247, 1261-1275): every skip tensor and the mid-block
+  // output take an additive residual when the caller supplied them (gdf_set_control_residuals). The skips live as
+  // column slices of the up path's concat buffers and are complete by now; the captures of the down / mid path were
+  // written by the producers' epilogues before this point, like the reference's gather sites.
+  h->n_skips = (int)skips.size();
+  h->skip_shapes.clear();
+  for (auto& sk : skips) h->skip_shapes.push_back({sk.C, sk.hw});
+  if (!b.dry) {
+    gdf_handle_s* hh = h;
+    const std::vector<Skip> sk = skips;
+    bf16* mid_dst = upres[0].cbuf;
+    const int mid_ld = upres[0].cprev + upres[0].cskip, mid_c = ch, mid_hw = hw;
+    b.ops->tag(kKindOther, 0.0, "controlnet residual adds (no-op without residuals)");
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      if (hh->ctrl_down.empty() && !hh->ctrl_mid) return 0;
+      for (size_t i = 0; i < sk.size() && i < hh->ctrl_down.size(); ++i) {
+        if (!hh->ctrl_down[i] || !sk[i].cbuf) continue;
+        const int HW = sk[i].hw * sk[i].hw;
+        add_residual_nchw_kernel<<<1024, 256, 0, rc.stream>>>(sk[i].cbuf + sk[i].col, sk[i].ld, hh->ctrl_down[i], B, HW,
+                                                             sk[i].C);
+      }
+      if (hh->ctrl_mid)
+        add_residual_nchw_kernel<<<1024, 256, 0, rc.stream>>>(mid_dst, mid_ld, hh->ctrl_mid, B, mid_hw * mid_hw, mid_c);
+      OP_CUDA(cudaGetLastError());
+      return 0;
+    });
+  }
+
   // ---- up blocks
   size_t ur = 0;
   bf16* final_h = nullptr;
@@ -2526,6 +2573,9 @@ static void free_plan(gdf_handle_s* h) {
   h->requested.clear();
   h->arena_bytes = 0;
   h->planned = false;
+  h->ctrl_down.clear();
+  h->ctrl_mid = nullptr;
+  h->n_skips = 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc); fr(h->key_bias); fr(h->g_dev);
   h->g_dev = nullptr;
@@ -2773,6 +2823,26 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
 }
 
 uint64_t gdf_plan_generation(gdf_handle h) { return (h && h->planned) ? h->plan_generation : 0; }
+
+int gdf_control_residual_shapes(gdf_handle h, int* channels_out, int* sides_out, int max_n) {
+  if (!h || !h->planned || h->is_dit || h->is_flux) return fail(GDF_ERR_INVALID, "gdf_control_residual_shapes: no UNet plan");
+  for (int i = 0; i < h->n_skips && i < max_n; ++i) {
+    if (channels_out) channels_out[i] = h->skip_shapes[i].first;
+    if (sides_out) sides_out[i] = h->skip_shapes[i].second;
+  }
+  return h->n_skips;
+}
+
+int gdf_set_control_residuals(gdf_handle h, const void* const* down_dev, int n_down, const void* mid_dev) {
+  if (!h || !h->planned || h->is_dit || h->is_flux) return fail(GDF_ERR_INVALID, "gdf_set_control_residuals: no UNet plan");
+  if (n_down != 0 && n_down != h->n_skips)
+    return fail(GDF_ERR_SHAPE, "gdf_set_control_residuals: %d down residuals, this UNet has %d skip tensors", n_down,
+                h->n_skips);
+  h->ctrl_down.clear();
+  for (int i = 0; i < n_down; ++i) h->ctrl_down.push_back(static_cast<const float*>(down_dev[i]));
+  h->ctrl_mid = static_cast<const float*>(mid_dev);
+  return GDF_OK;
+}
 
 int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_dev, const void* eps_q_dev,
                      float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,

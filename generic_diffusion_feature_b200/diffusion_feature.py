@@ -52,7 +52,10 @@ class FeatureExtractor(nn.Module):
                  ):
         super().__init__()
         if control:
-            raise NotImplementedError("ControlNet conditioning is outside the B200 hot path")
+            # components/controlnet.py runs diffusers ControlNetModel checkpoints (+ cv2 / Midas preprocessors) to produce
+            # the residuals; that encoder network is not built here. Its OUTPUTS are taken: extract(control_residuals=...)
+            raise NotImplementedError("the ControlNet encoder (feature/components/controlnet.py) is not built on the B200 "
+                                      "path; pass its outputs to extract(..., control_residuals=(down, mid)) instead")
         if external_model:
             pipe = external_model            # diffusion_feature.py:46-47: the seam for pre-built pipes
         else:
@@ -156,12 +159,16 @@ class FeatureExtractor(nn.Module):
                 use_control=False,
                 use_ddim_inversion=False,
                 noise=None,   # extension: (eps_vae, eps_q), each (B,4,S/8,S/8)
+                control_residuals=None,   # extension: (down_block_res_samples, mid_block_res_sample) of a ControlNet
                 ):
         if denoising_from:
             raise NotImplementedError("denoising_from (multi-step denoise loop) is deprecated in the reference and "
                                       "not built here")
-        if use_control or use_ddim_inversion:
-            raise NotImplementedError("ControlNet / DDIM inversion are outside the B200 hot path")
+        if use_ddim_inversion:
+            raise NotImplementedError("DDIM inversion is outside the B200 hot path")
+        if use_control and control_residuals is None:
+            raise NotImplementedError("use_control needs the ControlNet outputs: pass control_residuals=(down, mid) "
+                                      "(unet_2d_condition.py:1236-1275); the ControlNet encoder itself is not built here")
         if self.feature_store.store_idx is not None:
             raise NotImplementedError("background extraction hooks a generation loop, which is not built here")
         pipe = self.pipe
@@ -260,6 +267,7 @@ class FeatureExtractor(nn.Module):
                                                   _lib.ptr(arena), arena.numel(), None, st))
             else:
                 mask_d = None
+                ctrl_keep = self._set_control_residuals(control_residuals, batch_size)
                 check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
                                               _lib.ptr(time_ids), _lib.ptr(arena), arena.numel(), None, st))
         feats = plan.views(arena)
@@ -272,8 +280,44 @@ class FeatureExtractor(nn.Module):
             feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
         self.feature_store.feats = feats
         # keep inputs alive until the stream has consumed them
-        self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena, mask_d)
+        self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena, mask_d,
+                           locals().get("ctrl_keep"))
         return self.feature_store.stored_feats
+
+    def _set_control_residuals(self, control_residuals, batch_size):
+        """ControlNet outputs -> gdf_set_control_residuals (UNet families): `down` = one (B, C_i, s_i, s_i) tensor per skip
+        in push order, `mid` = (B, C, s, s); None clears them. Shapes are checked against the planned UNet."""
+        pipe, lib = self.pipe, self.pipe.lib
+        if control_residuals is None:
+            check(lib.gdf_set_control_residuals(pipe.handle, None, 0, None))
+            return None
+        if getattr(pipe, "unet_cfg", None) is None:
+            raise NotImplementedError("control residuals are inputs of the UNet families")
+        down, mid = control_residuals
+        ch = (ctypes.c_int * 32)()
+        sd = (ctypes.c_int * 32)()
+        n = lib.gdf_control_residual_shapes(pipe.handle, ch, sd, 32)
+        if n < 0:
+            check(n)
+        if len(down) != n:
+            raise ValueError("got %d down residuals, this UNet has %d skip tensors" % (len(down), n))
+        dev = pipe.device
+        keep = []
+        for i, d_ in enumerate(down):
+            if tuple(d_.shape) != (batch_size, ch[i], sd[i], sd[i]):
+                raise ValueError("down residual %d must be %s, got %s" % (i, (batch_size, ch[i], sd[i], sd[i]),
+                                                                       tuple(d_.shape)))
+            keep.append(d_.to(dev, torch.float32).contiguous())
+        mid_d = None
+        if mid is not None:
+            if tuple(mid.shape) != (batch_size, ch[n - 1], sd[n - 1], sd[n - 1]):
+                raise ValueError("mid residual must be %s, got %s" % ((batch_size, ch[n - 1], sd[n - 1], sd[n - 1]),
+                                                                    tuple(mid.shape)))
+            mid_d = mid.to(dev, torch.float32).contiguous()
+            keep.append(mid_d)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in keep[:n]])
+        check(lib.gdf_set_control_residuals(pipe.handle, ptrs, n, _lib.ptr(mid_d)))
+        return keep
 
     def set_background_extraction(self, idxs):
         self.feature_store.store_idx = idxs

@@ -192,6 +192,16 @@ int gdf_denoise_capture(gdf_handle h, float timestep, const void* ctx_dev, int c
                         const void* add_time_ids_dev, void* arena_dev, int64_t arena_bytes, void* noise_pred_out_dev,
                         void* stream);
 
+/* ControlNet conditioning inputs of the UNet forward (feature/diffusers/models/unet/unet_2d_condition.py:1236-1247
+ * down_block_additional_residuals, :1261-1275 mid_block_additional_residual; produced in the reference by
+ * feature/components/controlnet.py). fp32 NCHW device tensors (B, C_i, s_i, s_i), borrowed until replaced: one per skip
+ * tensor in push order (conv_in output, then every resnet / transformer / downsampler output of the down path) and one
+ * for the mid-block output. They are added where the reference adds them; captured maps of the down / mid path are
+ * taken before the addition like the reference's gather sites. n_down = 0 and mid_dev = NULL clear them.
+ * gdf_control_residual_shapes returns the number of skips and fills (channels, side) per skip. */
+int gdf_control_residual_shapes(gdf_handle h, int* channels_out, int* sides_out, int max_n);
+int gdf_set_control_residuals(gdf_handle h, const void* const* down_dev, int n_down, const void* mid_dev);
+
 /* One DiT forward with capture (replaces pipe.transformer(...) at diffusion_feature.py:467-474).
  *   ctx_dev : fp32 (B, ctx_len, caption_channels) caption embeddings (T5), ctx_len as set by gdf_set_ctx_len
  *   ctx_mask_dev : fp32 (B, ctx_len), 1 = attend, 0 = masked (bias -10000 like the reference), or NULL = all ones
