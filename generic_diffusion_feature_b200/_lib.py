@@ -26,7 +26,7 @@ EXPORTS = [
     "gdf_plan_generation", "gdf_control_residual_shapes", "gdf_set_control_residuals",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
-    "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows",
+    "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows", "gdf_debug_attention_trace",
     "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
     "gdf_op_resize_concat", "gdf_op_avgpool_nhwc", "gdf_correspond_workspace_floats", "gdf_correspond",
 ]
@@ -131,6 +131,7 @@ def load():
     lib.gdf_op_attention_bias.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_float, P, P]
     lib.gdf_op_softmax_rows.argtypes = [P, c_int64, c_int, c_int, P]
+    lib.gdf_debug_attention_trace.argtypes = [P, c_int]
     lib.gdf_op_upsample_nearest2x.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.gdf_op_im2col_small.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P]
     lib.gdf_op_qsample.argtypes = [P, P, P, c_float, c_float, c_float, c_float, P, P, P, c_int, c_int, P]

@@ -1,5 +1,6 @@
 // C ABI, op level (include/gdf.h): thin extern "C" wrappers over ops.h.
 #include "../../include/gdf.h"
+#include <vector>
 #include "ops.h"
 
 using namespace gdf;
@@ -126,6 +127,13 @@ int gdf_op_attention_bias(const void* q, int ldq, const void* k, int ldk, const 
                                       static_cast<const float*>(key_bias)));
 }
 
+/* Debug: the next attention launches record a timeline of CTA 0 (role events stamped with the SM clock) into `buf`
+ * (u64[cap], zeroed by the caller; [0] = number of events). NULL turns it off. tools/attn_trace.py decodes it. */
+int gdf_debug_attention_trace(void* buf_dev, int cap) {
+  attention_tc_set_trace(buf_dev, cap);
+  return GDF_OK;
+}
+
 int gdf_op_softmax_rows(void* s, int64_t rows, int cols, int ld, void* stream) {
   GDF_LAUNCH(launch_softmax_rows(static_cast<bf16*>(s), rows, cols, ld, static_cast<cudaStream_t>(stream)));
 }
@@ -157,8 +165,8 @@ int gdf_op_cast_f32_to_bf16(const void* x, void* y, int64_t n, void* stream) {
 
 int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, int OW, int Ctot, void* out_nhwc,
                          void* out_nchw, void* sumsq, void* stream) {
-  if (n_src > 64) return fail(GDF_ERR_INVALID, "gdf_op_resize_concat: too many sources");
-  ResizeSrc rs[64];
+  if (n_src > 1024) return fail(GDF_ERR_INVALID, "gdf_op_resize_concat: too many sources (%d > 1024)", n_src);
+  std::vector<ResizeSrc> rs(n_src > 0 ? n_src : 1);
   for (int i = 0; i < n_src; ++i) {
     rs[i].ptr = static_cast<const __half*>(srcs[i].ptr_dev);
     rs[i].h = srcs[i].h;
@@ -166,7 +174,7 @@ int gdf_op_resize_concat(const gdf_resize_src* srcs, int n_src, int B, int OH, i
     rs[i].C = srcs[i].C;
     rs[i].c_off = srcs[i].c_off;
   }
-  GDF_LAUNCH(launch_resize_concat(rs, n_src, B, OH, OW, Ctot, static_cast<__half*>(out_nhwc),
+  GDF_LAUNCH(launch_resize_concat(rs.data(), n_src, B, OH, OW, Ctot, static_cast<__half*>(out_nhwc),
                                   static_cast<__half*>(out_nchw), static_cast<float*>(sumsq),
                                   static_cast<cudaStream_t>(stream)));
 }

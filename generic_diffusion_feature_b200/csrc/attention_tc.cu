@@ -58,6 +58,8 @@ struct TcParams {
   float inv_scale;   // 1 / softmax scale (key bias is added in the unscaled score domain)
   const float* key_bias;   // optional fp32 [B, Nk], added to the scaled scores
   int lmode;         // how the denominator product is issued (see issue_pv)
+  unsigned long long* trace;   // debug timeline of CTA 0 (gdf_debug_attention_trace): [0] = count, then (id << 40 | clock)
+  int trace_cap;
   bf16* O;
   int ldo;
 };
@@ -97,6 +99,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int n = p.n_kv;
   const int my_items = (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  // debug timeline (CTA 0, one lane per role): event id = kind << 16 | g, stamped with the SM clock
+  auto tr = [&](int kind, int gg) {
+    if (p.trace && blockIdx.x == 0 && lane == 0) {
+      const unsigned long long slot = atomicAdd(p.trace, 1ULL) + 1;
+      if (slot < (unsigned long long)p.trace_cap)
+        p.trace[slot] = ((unsigned long long)((kind << 16) | (gg & 0xffff)) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFULL);
+    }
+  };
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
@@ -143,6 +153,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 0) {
     // ================================================= TMA producer (single elected thread)
     if (elect_one()) {
+      auto trp = [&](int kind, int gg) {
+        if (p.trace && blockIdx.x == 0) {
+          const unsigned long long slot = atomicAdd(p.trace, 1ULL) + 1;
+          if (slot < (unsigned long long)p.trace_cap)
+            p.trace[slot] = ((unsigned long long)((kind << 16) | (gg & 0xffff)) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFULL);
+        }
+      };
       int s = 0;
       uint32_t ph = 0;
       int item = blockIdx.x;
@@ -154,6 +171,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (it > 0) mbar_wait(&q_empty[t], (it - 1) & 1);
+          trp(1 + t, it);   // 1 / 2: Q tile t of item `it` issued
           mbar_arrive_expect_tx(&q_full[t], C::kQTile);
 #pragma unroll
           for (int kb = 0; kb < NB; ++kb)
@@ -161,11 +179,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         for (int j = 0; j < n; ++j) {
           mbar_wait(&k_empty[s], ph ^ 1);
+          trp(3, it * n + j);   // 3: K tile issued
           mbar_arrive_expect_tx(&k_full[s], C::kKvTile);
 #pragma unroll
           for (int kb = 0; kb < NB; ++kb)
             tma_load_4d(smem + C::kOffK + s * C::kKvTile + kb * C::kKvBlk, &map_k, &k_full[s], kb * 64, h, j * KT, b);
           mbar_wait(&v_empty[s], ph ^ 1);
+          trp(4, it * n + j);   // 4: V tile issued
           mbar_arrive_expect_tx(&v_full[s], C::kKvTile);
 #pragma unroll
           for (int kb = 0; kb < NB; ++kb)
@@ -245,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if (g > 0) mbar_wait(&s_free[t], (g - 1) & 1);
         if (j == 0) mbar_wait(&q_full[t], it & 1);
         tc_fence_after();
+        tr(10 + t, g);   // 10 / 11: S_t(g) issued
         if (elect_one()) {
           issue_s(t, slot);
           umma_commit(&k_empty[slot]);
@@ -256,6 +277,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           mbar_wait(&p_full[t], gp & 1);
           mbar_wait(&v_full[pslot], (gp / kTcRing) & 1);
           tc_fence_after();
+          tr(12 + t, gp);   // 12 / 13: P V_t(gp) issued
           if (elect_one()) {
             issue_pv(t, pslot, prev_first);
             umma_commit(&v_empty[pslot]);
@@ -310,6 +332,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int j = 0; j < n; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
+        if (quad == 0 && hf == 0) tr(20 + t, g);   // 20 / 21: S_t(g) seen by the softmax group
         float sf[HC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sf[c * 32]));
@@ -351,10 +374,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           m_blk = fmaxf(m_blk, slot[(hf ^ 1) * 128 + r]);
         }
         // P_t(g-1) V has been consumed from smem / accumulated in TMEM before P_t(g) is written or O_t is rescaled
+        if (quad == 0 && hf == 0) tr(22 + t, g);   // 22 / 23: row maximum done
         if (g > 0) {
           mbar_wait(&pv_full[t], (g - 1) & 1);
           tc_fence_after();
         }
+        if (quad == 0 && hf == 0) tr(24 + t, g);   // 24 / 25: P V_t(g-1) complete (P buffer free)
         if (__any_sync(0xffffffffu, m_blk > m_run + thresh)) {   // warp-uniform (TMEM accesses are warp-collective); both
           const float m_new = fmaxf(m_run, m_blk);               // threads of a row see the same maxima
           const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // first tile: exp2(-inf) = 0
@@ -447,10 +472,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (quad == 0 && hf == 0) tr(26 + t, g);   // 26 / 27: P_t(g) published
       }
       // ---- output of the item: O_t / L_t from TMEM (each thread writes its 16-column chunks of the output row)
       mbar_wait(&pv_full[t], (g - 1) & 1);
       tc_fence_after();
+      if (quad == 0 && hf == 0) tr(28 + t, g - 1);   // 28 / 29: last P V of the item complete, output starts
       const uint32_t l_raw = tmem_ld_32x1(t_o + DPAD);
       tmem_ld_wait();
       const float inv = 1.f / __uint_as_float(l_raw);
@@ -473,6 +500,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
       }
+      if (quad == 0 && hf == 0) tr(30 + t, g - 1);   // 30 / 31: output of the item written
       // the next item's first P V (accumulate = 0) is only issued after every softmax warp of the tile has published P
       // again: the TMEM loads above are retired (tcgen05.wait::ld) and ordered by the fence before that arrive
     }
@@ -513,6 +541,13 @@ static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int split, int pp, int* s
   return split == 2 ? pick_tc_kernel2<DPAD, KT, 2>(poly8, p_bf16) : pick_tc_kernel2<DPAD, KT, 1>(poly8, p_bf16);
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0;
+void attention_tc_set_trace(void* buf, int cap) {
+  g_trace_buf = static_cast<unsigned long long*>(buf);
+  g_trace_cap = cap;
+}
+
 bool attention_tc_supports(int D) { return D == 40 || D == 64 || D == 72 || D == 80 || D == 128; }
 
 // Host: 4-D tensor maps (d, head, token, batch) over the strided Q / K / V views, box 64 x 1 x rows x 1.
@@ -529,7 +564,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
     const char* es = getenv("GDF_FA_SPLIT");
     split = es ? atoi(es) : 1;
     const char* e2 = getenv("GDF_FA_PP");
-    pp = e2 ? atoi(e2) : 0;
+    pp = e2 ? atoi(e2) : 1;
   }
   const int dpad = (D + 15) / 16 * 16;
   const int kt = dpad <= 64 ? 128 : 64;
@@ -573,6 +608,8 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   p.scale_log2 = scale * 1.4426950408889634f;
   p.inv_scale = 1.f / scale;
   p.key_bias = key_bias;
+  p.trace = g_trace_buf;
+  p.trace_cap = g_trace_cap;
   {
     static int lmode = -1;
     if (lmode < 0) {

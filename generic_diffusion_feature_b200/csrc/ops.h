@@ -104,6 +104,7 @@ int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, c
 // persistent tcgen05 / TMEM flash attention for head dims 40 / 64 / 72 / 80 / 128 and any key count (attention_tc.cu);
 // v_f16: V (and P) are fp16 bit patterns, otherwise bf16. key_bias: optional fp32 [B, Nk] added to the scaled scores.
 bool attention_tc_supports(int D);
+void attention_tc_set_trace(void* buf, int cap);   // debug: device buffer of `cap` u64 that CTA 0 of the next launches fills
 int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int B,
                         int heads, int Nq, int Nk, int D, float scale, int v_f16, const float* key_bias,
                         cudaStream_t stream);

@@ -3,6 +3,7 @@
 // Reference: F.interpolate(f, (128,128), mode='bilinear') + torch.cat in
 // correspondence/correspondence/aggregation_network.py:62-66. HBM-bound; NCHW output is transposed through
 // shared memory so both the reads (channel-contiguous) and the writes (pixel-contiguous) are coalesced.
+#include <stdlib.h>
 #include "ops.h"
 
 namespace gdf {
@@ -72,6 +73,106 @@ resize_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int c_of
   }
 }
 
+// NHWC -> NHWC for integer up-scaling factors S = OH / h = OW / w (1, 2, 4, 8: every map of the SDXL / SD-2.1 stacks):
+// one thread per (source cell, 8 channels). All output pixels whose bilinear taps are the four corners of that cell -
+// oy in [S*cy + S/2, S*cy + 3S/2), cy = -1 .. h-1 with clamped corners - are produced from ONE load of the corners:
+// the general kernel above re-reads them S*S times through L2 (4x16 B read per 16 B written), which capped it at a
+// quarter of the HBM write rate. Weights come from the same bilinear_tap arithmetic, so results are bit-identical.
+// The warp's lanes hold consecutive channel groups of one cell (the channel index space is padded to a multiple of 32),
+// so stores are 512 B contiguous per warp and the per-pixel squared norm (sumsq, optional) is a shuffle reduction +
+// one atomicAdd per (warp, pixel) instead of a second pass over the stack.
+template <int S>
+__global__ void __launch_bounds__(256)
+resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int c_off, int B, int Ctot,
+                        __half* __restrict__ out, float* __restrict__ sumsq) {
+  const int OH = h * S, OW = w * S;
+  const int C8 = C / 8, C8P = (C8 + 31) & ~31;
+  const int ch = (S == 1) ? h : h + 1, cw = (S == 1) ? w : w + 1;     // cells per axis
+  const long long total = (long long)B * ch * cw * C8P;
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8P);
+    long long r = i / C8P;
+    const int cxi = (int)(r % cw);
+    r /= cw;
+    const int cyi = (int)(r % ch);
+    const int b = (int)(r / ch);
+    const bool live = c8 < C8;
+    const int cy = (S == 1) ? cyi : cyi - 1, cx = (S == 1) ? cxi : cxi - 1;
+    const int r0 = cy < 0 ? 0 : cy, r1 = cy + 1 > h - 1 ? h - 1 : cy + 1;
+    const int q0 = cx < 0 ? 0 : cx, q1 = cx + 1 > w - 1 ? w - 1 : cx + 1;
+    uint4 v00 = make_uint4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
+    if (live) {
+      const uint4* sp = reinterpret_cast<const uint4*>(src + ((long long)b * h * w) * C) + c8;
+      v00 = __ldg(sp + ((long long)r0 * w + q0) * C8);
+      if (S > 1) {
+        v01 = __ldg(sp + ((long long)r0 * w + q1) * C8);
+        v10 = __ldg(sp + ((long long)r1 * w + q0) * C8);
+        v11 = __ldg(sp + ((long long)r1 * w + q1) * C8);
+      }
+    }
+    const int oy0 = (S == 1) ? cy : S * cy + S / 2, ox0 = (S == 1) ? cx : S * cx + S / 2;
+#pragma unroll
+    for (int dy = 0; dy < S; ++dy) {
+      const int oy = oy0 + dy;
+      if (oy < 0 || oy >= OH) continue;            // warp-uniform (one cell per warp)
+      const BilinearTap ty = bilinear_tap(oy, h, 1.f / (float)S);
+#pragma unroll
+      for (int dx = 0; dx < S; ++dx) {
+        const int ox = ox0 + dx;
+        if (ox < 0 || ox >= OW) continue;
+        float ss = 0.f;
+        if (live) {
+          uint4 u;
+          if (S == 1) {
+            u = v00;
+            if (sumsq) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                ss += f.x * f.x + f.y * f.y;
+              }
+            }
+          } else {
+            const BilinearTap tx = bilinear_tap(ox, w, 1.f / (float)S);
+            float o[8];
+            blend8(v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1, o);
+            u.x = pack_f16x2(o[0], o[1]);
+            u.y = pack_f16x2(o[2], o[3]);
+            u.z = pack_f16x2(o[4], o[5]);
+            u.w = pack_f16x2(o[6], o[7]);
+            if (sumsq) {   // norm of the ROUNDED values (what a second pass over the fp16 stack would read)
+              const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                ss += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * Ctot + c_off + c8 * 8) = u;
+        }
+        if (sumsq) {
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+          if (lane == 0) atomicAdd(sumsq + ((long long)b * OH + oy) * OW + ox, ss);
+        }
+      }
+    }
+  }
+}
+
+template <int S>
+static void launch_resize_cell(const ResizeSrc& s, int B, int Ctot, __half* out, float* sumsq, cudaStream_t stream) {
+  const int C8P = (s.C / 8 + 31) & ~31;
+  const long long total = (long long)B * (S == 1 ? s.h : s.h + 1) * (S == 1 ? s.w : s.w + 1) * C8P;
+  const long long blocks = (total + 255) / 256;
+  resize_cell_nhwc_kernel<S><<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), 256, 0, stream>>>(
+      s.ptr, s.h, s.w, s.C, s.c_off, B, Ctot, out, sumsq);
+}
+
 // NHWC -> NCHW through shared memory: block = 32 output pixels (one row segment) x 64 channels.
 __global__ void __launch_bounds__(256)
 resize_nchw_kernel(const __half* __restrict__ src, int h, int w, int C, int c_off, int B, int OH, int OW, int Ctot,
@@ -137,21 +238,46 @@ rownorm_kernel(const __half* __restrict__ x, long long rows, int C, float* __res
 cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, int OH, int OW, int Ctot,
                                  __half* out_nhwc, __half* out_nchw, float* sumsq, cudaStream_t stream) {
   if (Ctot % 8 != 0) return cudaErrorInvalidValue;
+  static int use_cell = -1;
+  if (use_cell < 0) {
+    const char* e = getenv("GDF_RESIZE_CELL");     // 0: the general kernel for every map (A/B timing)
+    use_cell = e ? atoi(e) : 1;
+  }
+  // per-pixel squared norms: accumulated by the cell kernels (atomicAdd) when every map takes that path, otherwise
+  // by one pass over the finished stack (rownorm_kernel)
+  bool all_cell = use_cell != 0 && out_nhwc != nullptr;
+  for (int i = 0; i < n_src && all_cell; ++i) {
+    const ResizeSrc& s = srcs_host[i];
+    const int sc = (s.h > 0 && OH % s.h == 0) ? OH / s.h : 0;
+    all_cell = (OW == s.w * sc) && (sc == 1 || sc == 2 || sc == 4 || sc == 8);
+  }
+  float* fused_sumsq = (sumsq && all_cell) ? sumsq : nullptr;
+  if (fused_sumsq) {
+    cudaError_t e = cudaMemsetAsync(sumsq, 0, (size_t)B * OH * OW * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+  }
   for (int i = 0; i < n_src; ++i) {
     const ResizeSrc& s = srcs_host[i];
     if (s.C % 8 != 0 || s.c_off % 8 != 0) return cudaErrorInvalidValue;
     if (out_nhwc) {
-      const long long total = (long long)B * OH * OW * (s.C / 8);
-      const long long blocks = (total + 255) / 256;
-      resize_nhwc_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, stream>>>(
-          s.ptr, s.h, s.w, s.C, s.c_off, B, OH, OW, Ctot, out_nhwc);
+      const int sc = (use_cell && s.h > 0 && OH % s.h == 0 && OW == s.w * (OH / s.h)) ? OH / s.h : 0;
+      if (sc == 1) launch_resize_cell<1>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 2) launch_resize_cell<2>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 4) launch_resize_cell<4>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 8) launch_resize_cell<8>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else {
+        const long long total = (long long)B * OH * OW * (s.C / 8);
+        const long long blocks = (total + 255) / 256;
+        resize_nhwc_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, stream>>>(
+            s.ptr, s.h, s.w, s.C, s.c_off, B, OH, OW, Ctot, out_nhwc);
+      }
     }
     if (out_nchw) {
       dim3 grid((unsigned)(((OW + 31) / 32) * OH * B), (unsigned)((s.C + 63) / 64));
       resize_nchw_kernel<<<grid, 256, 0, stream>>>(s.ptr, s.h, s.w, s.C, s.c_off, B, OH, OW, Ctot, out_nchw);
     }
   }
-  if (sumsq && out_nhwc) {
+  if (sumsq && out_nhwc && !fused_sumsq) {
     const long long rows = (long long)B * OH * OW;
     rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(out_nhwc, rows, Ctot, sumsq);
   }

@@ -290,6 +290,9 @@ int gdf_op_attention_bias(const void* q_dev, int ldq, const void* k_dev, int ldk
                           void* o_dev, int ldo, int B, int heads, int Nq, int Nk, int head_dim, float scale,
                           const void* key_bias_dev, void* stream);
 int gdf_op_softmax_rows(void* s_dev, int64_t rows, int cols, int ld, void* stream);
+/* Debug aid: CTA 0 of the following attention launches records (event id << 40 | SM clock) into buf_dev (u64[cap],
+ * zero it first; [0] = event count). NULL turns tracing off. Event ids: tools/attn_trace.py. */
+int gdf_debug_attention_trace(void* buf_dev, int cap);
 int gdf_op_upsample_nearest2x(const void* x_dev, void* y_dev, int B, int H, int W, int C, void* stream);
 int gdf_op_im2col_small(const void* src_nchw_f32_dev, const void* src_nhwc_bf16_dev, void* a_dev, int B, int H,
                         int W, int Cin, void* stream);

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from generic_diffusion_feature_b200 import ops
 
 tag = "old" if os.environ.get("GDF_ATTN_TC") == "0" else "tc/split=%s/pp=%s/poly8=%s/lmode=%s" % (
-    os.environ.get("GDF_FA_SPLIT", "1"), os.environ.get("GDF_FA_PP", "0"), os.environ.get("GDF_FA_POLY8", "0"),
+    os.environ.get("GDF_FA_SPLIT", "1"), os.environ.get("GDF_FA_PP", "1"), os.environ.get("GDF_FA_POLY8", "0"),
     os.environ.get("GDF_FA_LMODE", "3"))
 g = torch.Generator(device="cuda").manual_seed(0)
 shapes = [(8, 20, 1024, 1024, 64, True), (8, 10, 4096, 4096, 64, True), (2, 10, 576, 576, 64, True),
