@@ -377,6 +377,10 @@ class Workload:
         for f in feats.values():
             B, C, h, w = f.shape
             maps.append(f.permute(0, 2, 3, 1).reshape(B, h * w, C))     # the arena's token-major storage, no copy
+        # maps whose channel count is not a multiple of 8 (the 4-channel unet-in / unet-out) go last, so that every other
+        # map keeps 16-byte aligned channel offsets in the stack (a consumer reads the stack through its own id -> offset
+        # table either way; the reference concatenates in dict order, aggregation_network.py:62-66)
+        maps.sort(key=lambda m: m.shape[2] % 8 != 0)
         self.stack_bytes = sum(m.numel() * 2 for m in maps) + self.B * hw * hw * sum(m.shape[2] for m in maps) * 2
         return self._timed(self.stack_ms, lambda: ops.resize_concat(maps, (hw, hw), nhwc=(layout == "nhwc"),
                                                                     nchw=(layout == "nchw"), with_sumsq=sumsq))

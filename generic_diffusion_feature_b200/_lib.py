@@ -25,7 +25,7 @@ EXPORTS = [
     "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_plan_generation", "gdf_control_residual_shapes", "gdf_set_control_residuals",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
-    "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_groupnorm_workspace_floats",
+    "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_pack_conv_weight_f16", "gdf_op_conv_in", "gdf_op_groupnorm_workspace_floats",
     "gdf_op_groupnorm", "gdf_op_layernorm", "gdf_op_attention", "gdf_op_softmax_rows", "gdf_debug_attention_trace",
     "gdf_op_upsample_nearest2x", "gdf_op_im2col_small", "gdf_op_qsample", "gdf_op_cast_f32_to_bf16",
     "gdf_op_resize_concat", "gdf_op_avgpool_nhwc", "gdf_correspond_workspace_floats", "gdf_correspond",
@@ -51,6 +51,7 @@ class Epilogue(ctypes.Structure):
         ("cap", CaptureSeg * 3), ("num_cap", c_int),
         ("ln_sums_dev", c_void_p), ("ln_u_dev", c_void_p), ("ln_eps", c_float), ("row_sums_dev", c_void_p),
         ("gn_sums_dev", c_void_p), ("gn_cpg", c_int), ("gn_groups", c_int), ("gn_rows_per_img", c_int64),
+        ("in_f16", c_int),
     ]
 
 
@@ -124,6 +125,8 @@ def load():
     lib.gdf_op_conv3x3.argtypes = [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, ctypes.POINTER(Epilogue),
                                    c_int, P]
     lib.gdf_op_pack_conv_weight.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
+    lib.gdf_op_conv_in.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P]
+    lib.gdf_op_pack_conv_weight_f16.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     lib.gdf_op_groupnorm.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P]
     lib.gdf_op_layernorm.argtypes = [P, P, P, P, c_int64, c_int, c_float, P, P, c_int, P]
     lib.gdf_op_attention.argtypes = [P, c_int, P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -53,3 +53,32 @@ def find_nn_source_correspondences(img1_feats, img2_feats, source_points, output
     check(lib.gdf_correspond(ptr(s1), ptr(s2), C, hw, load_size[0], ptr(qyx), n, ptr(idx), ptr(ws), stream_ptr()))
     points2 = torch.stack([idx // load_size[0], idx % load_size[0]], dim=-1)
     return torch.from_numpy(np.asarray(source_points)), points2
+
+
+class AggregationHead:
+    """Forward of the reference's trainable output processor on the feature stack:
+    `AggregationNetwork.out = nn.Conv2d(dim, out_dim, 3, 1, 1, bias=False)` applied to the fp32-cast stack
+    (aggregation_network.py:22,97-99). Here the fp16 NHWC stack goes straight into the tcgen05 implicit-GEMM convolution
+    (fp16 operands, fp32 accumulation, fp32 output): no cast pass over the 126 MB / image stack.
+
+        head = AggregationHead(weight)           # weight: (out_dim, dim, 3, 3) fp32, the nn.Conv2d parameter
+        y = head(stack, (128, 128))              # stack: [B, H*W, dim] fp16 NHWC (build_stack) -> (B, out_dim, H, W) fp32
+    """
+
+    def __init__(self, weight, device=None):
+        if weight.dim() != 4 or tuple(weight.shape[2:]) != (3, 3):
+            raise ValueError("AggregationNetwork.out is a 3x3 convolution: weight must be (out_dim, dim, 3, 3)")
+        dev = torch.device(device) if device is not None else weight.device
+        self.out_dim, self.dim = int(weight.shape[0]), int(weight.shape[1])
+        if self.dim % 64 != 0:
+            raise ValueError("stack channels must be a multiple of 64 (got %d)" % self.dim)
+        self.w = ops.pack_conv_weight_f16(weight.to(dev))
+
+    def __call__(self, stack_nhwc, hw):
+        B, HW, C = stack_nhwc.shape
+        H, W = hw
+        assert HW == H * W and C == self.dim and stack_nhwc.dtype == torch.float16 and stack_nhwc.is_contiguous()
+        out = torch.empty(B * HW, self.out_dim, dtype=torch.float32, device=stack_nhwc.device)
+        ep = ops.make_epilogue(out_f32=out, n_out=self.out_dim, in_f16=True)
+        ops.conv3x3(stack_nhwc.view(B, H, W, C), self.w, ep)
+        return out.view(B, H, W, self.out_dim).permute(0, 3, 1, 2)

@@ -36,6 +36,7 @@ static Epilogue to_epilogue(const gdf_epilogue* ep) {
     e.cap[i].col_end = ep->cap[i].col_end;
     e.cap[i].ld = ep->cap[i].ld;
   }
+  e.in_f16 = ep->in_f16 != 0;
   e.ln_sums = static_cast<const float*>(ep->ln_sums_dev);
   e.ln_u = static_cast<const float*>(ep->ln_u_dev);
   e.ln_eps = ep->ln_eps;
@@ -74,6 +75,19 @@ int gdf_op_conv3x3(const void* x_dev, int B, int Hin, int Win, int Cin, const vo
   GDF_TRY(build_conv3x3(&g, static_cast<const bf16*>(x_dev), B, Hin, Win, Cin, static_cast<const bf16*>(w_packed_dev),
                         N, stride, pad_lo, to_epilogue(ep), block_n));
   GDF_LAUNCH(launch_gemm(g, static_cast<cudaStream_t>(stream)));
+}
+
+int gdf_op_conv_in(const void* img, const void* w_packed, const void* bias, void* out, int B, int H, int W, int N,
+                   void* gn_sums, int gn_cpg, int gn_groups, void* stream) {
+  return launch_conv_in_fused(static_cast<const float*>(img), static_cast<const bf16*>(w_packed),
+                              static_cast<const float*>(bias), static_cast<bf16*>(out), B, H, W, N,
+                              static_cast<float*>(gn_sums), gn_cpg, gn_groups, static_cast<cudaStream_t>(stream));
+}
+
+int gdf_op_pack_conv_weight_f16(const void* w, void* out, int O, int O_pad, int I, int kh, int kw, int k_pad,
+                                void* stream) {
+  GDF_LAUNCH(launch_pack_conv_weight_f16(static_cast<const float*>(w), static_cast<__half*>(out), O, O_pad, I, kh, kw,
+                                         k_pad, static_cast<cudaStream_t>(stream)));
 }
 
 int gdf_op_pack_conv_weight(const void* w, void* out, int O, int O_pad, int I, int kh, int kw, int k_pad,

@@ -39,8 +39,7 @@ struct TcCfg {
   static constexpr int kOffV = kOffK + kTcRing * kKvTile;
   static constexpr int kOffP = kOffV + kTcRing * kKvTile;
   static constexpr int kOffOnes = kOffP + 2 * kPTile;
-  static constexpr int kOffX = kOffOnes + 2048;      // row-maximum exchange between the two threads of a row (kSplit = 2)
-  static constexpr int kOffBar = kOffX + 4096;
+  static constexpr int kOffBar = kOffOnes + 2048;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   // TMEM columns: S_t at t * KT; O_t at 2 * KT + t * kStrideO (32-column aligned), L_t (16 columns) right behind O_t
   static constexpr int kColO = 2 * KT;
@@ -65,20 +64,19 @@ struct TcParams {
 };
 
 // kPoly8: of every 8 (even, odd) column pairs, this many are exponentiated on the FMA pipe. kPBf16: P (and V) in bf16.
-// kSplit: softmax threads per query row. 1: 8 softmax warps (thread = row, KT columns each). 2: 16 softmax warps, the two
-// threads of a row (same TMEM lane quadrant, different warps) take half of the tile's columns each and exchange their
-// partial row maxima through shared memory: four softmax warps per SM sub-partition instead of two.
-// kPP (kSplit = 1): the two softmax groups take turns in the exponential phase through a pair of named barriers. Left
+// (A variant with two threads per row - 16 softmax warps, each thread half of the tile's columns - measured 5-15 %
+// slower at every shape, profiles/r02_attention_tc.md, and is gone.)
+// kPP: the two softmax groups take turns in the exponential phase through a pair of named barriers. Left
 // alone the groups run in lockstep (they wait on the same K / V tiles), so both are in their MUFU-bound phase at once
 // (each at half rate) and then both in their TMEM-load / maximum / fence phases (MUFU idle); alternating puts one
 // group's exponentials under the other's loads and barrier round trips.
-template <int DPAD, int KT, int kPoly8, bool kPBf16, int kSplit, bool kPP = false>
-__global__ void __launch_bounds__(kTcHelperThreads + 256 * kSplit, 1)
+template <int DPAD, int KT, int kPoly8, bool kPBf16, bool kPP = false>
+__global__ void __launch_bounds__(kTcHelperThreads + 256, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const TcParams p) {
   using C = TcCfg<DPAD, KT>;
   constexpr int NB = C::NB;
-  constexpr int HC = KT / kSplit;   // S columns per softmax thread
+  constexpr int HC = KT;            // S columns per softmax thread (thread = one query row)
   constexpr int NC = HC / 32;       // ... in 32-column chunks
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -123,8 +121,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&q_full[t], 1);
       mbar_init(&q_empty[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4 * kSplit);
-      mbar_init(&p_full[t], 4 * kSplit);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&p_full[t], 4);
       mbar_init(&pv_full[t], 1);
     }
     fence_barrier_init();
@@ -145,10 +143,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   pdl_wait();      // prologue above overlaps the previous kernel's tail; Q/K/V are only read from here on
   pdl_trigger();
 
-  if (warp < 4) {
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  }
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
 
   if (warp == 0) {
     // ================================================= TMA producer (single elected thread)
@@ -300,29 +295,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
   } else if (warp >= 4) {
     // ================================================= softmax + output
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int e = warp - 4;
     const int quad = e & 3;            // == warp % 4: TMEM lane quadrant
     const int t = (e >> 2) & 1;        // query tile of this group
-    const int hf = e >> 3;             // column half of the row (kSplit = 2), else 0
+    constexpr int hf = 0;
     const int r = quad * 32 + lane;    // row inside the query tile
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_off + t * KT + hf * HC;
     const uint32_t t_o = tmem_base + lane_off + C::kColO + t * C::kStrideO;
     const uint32_t p_row = smem_u32(smem + C::kOffP + t * C::kPTile) + r * 128;   // this thread's 128 B row (SW128)
     const uint32_t p_swz = (r & 7) << 4;
-    float* xchg = reinterpret_cast<float*>(smem + C::kOffX);   // [parity][tile][half][128 rows]
-    // O / L columns this thread rescales and writes out, in 16-column chunks (the second thread of a row also owns L)
-    constexpr int n16 = DPAD / 16;
-    const int ch0 = (kSplit == 1 || hf == 0) ? 0 : (n16 + 1) / 2;
-    const int ch1 = (kSplit == 1 || hf == 1) ? n16 : (n16 + 1) / 2;
-    const bool owns_l = (kSplit == 1) || hf == 1;
+    constexpr int n16 = DPAD / 16;     // O columns in 16-column chunks
+    constexpr int ch0 = 0, ch1 = n16;
+    constexpr bool owns_l = true;
     const float thresh = 8.f * p.inv_scale * 0.6931471805599453f;   // lazy rescale: P = 2^(..) stays <= 2^8
     int g = 0;
     int item = blockIdx.x;
     const int g_last = my_items * n - 1;
-    if (kPP && t == 1) asm volatile("bar.arrive 9, 256;" ::: "memory");   // group 0 goes first
+    const bool pp_on = kPP && n > 1;   // one-tile items (text cross-attention) have nothing to put under the other group
+    if (pp_on && t == 1) asm volatile("bar.arrive 9, 256;" ::: "memory");   // group 0 goes first
     for (int it = 0; it < my_items; ++it, item += gridDim.x) {
       const int qb = item % p.nqb;
       const int bh = item / p.nqb;
@@ -365,14 +357,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         float m_blk = mx[0];
 #pragma unroll
         for (int c = 1; c < NC; ++c) m_blk = fmaxf(m_blk, mx[c]);
-        if constexpr (kSplit == 2) {
-          // exchange with the thread that holds the other half of this row (warp e ^ 8): slot parity g & 1 - a thread
-          // is never more than one barrier ahead of its partner, so the slot written two tiles ago has been read
-          float* slot = xchg + (((g & 1) * 2 + t) * 2) * 128;
-          slot[hf * 128 + r] = m_blk;
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quad) : "memory");
-          m_blk = fmaxf(m_blk, slot[(hf ^ 1) * 128 + r]);
-        }
         // P_t(g-1) V has been consumed from smem / accumulated in TMEM before P_t(g) is written or O_t is rescaled
         if (quad == 0 && hf == 0) tr(22 + t, g);   // 22 / 23: row maximum done
         if (g > 0) {
@@ -406,7 +390,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         const float neg_m = -m_run * p.scale_log2;
-        if (kPP) {   // wait for the other group to leave its exponential phase
+        if (pp_on) {   // wait for the other group to leave its exponential phase
           if (t == 0) asm volatile("bar.sync 9, 256;" ::: "memory");
           else asm volatile("bar.sync 10, 256;" ::: "memory");
         }
@@ -455,7 +439,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             else
               asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph2[i]) : "f"(sf[c * 32 + 2 * i + 1]), "f"(sf[c * 32 + 2 * i]));
           }
-          const int col0 = hf * HC + c * 32;                       // first tile column of this chunk
+          const int col0 = c * 32;                                 // first tile column of this chunk
           const uint32_t blk = p_row + (col0 >> 6) * C::kPBlk;     // P block of 64 keys
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -463,7 +447,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             st_shared_v4(blk + ((chunk << 4) ^ p_swz), ph2[q * 4 + 0], ph2[q * 4 + 1], ph2[q * 4 + 2], ph2[q * 4 + 3]);
           }
         }
-        if (kPP) {   // hand the exponential phase over
+        if (pp_on) {   // hand the exponential phase over
           if (t == 0) asm volatile("bar.arrive 10, 256;" ::: "memory");
           else if (g != g_last) asm volatile("bar.arrive 9, 256;" ::: "memory");
         }
@@ -478,23 +462,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(&pv_full[t], (g - 1) & 1);
       tc_fence_after();
       if (quad == 0 && hf == 0) tr(28 + t, g - 1);   // 28 / 29: last P V of the item complete, output starts
+      // every TMEM load of the row in flight before the single wait (one load + wait per 16 columns cost ~2000 clk)
       const uint32_t l_raw = tmem_ld_32x1(t_o + DPAD);
+      uint32_t oa[n16][16];
+#pragma unroll
+      for (int hh = 0; hh < n16; ++hh)
+        if (hh >= ch0 && hh < ch1) tmem_ld_32x16(t_o + hh * 16, oa[hh]);
       tmem_ld_wait();
       const float inv = 1.f / __uint_as_float(l_raw);
       bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * p.D;
-      for (int hh = ch0; hh < ch1; ++hh) {
-        uint32_t oa[16];
-        tmem_ld_32x16(t_o + hh * 16, oa);
-        tmem_ld_wait();
-        if (qrow < p.Nq) {
+      if (qrow < p.Nq) {
+#pragma unroll
+        for (int hh = 0; hh < n16; ++hh) {
+          if (hh < ch0 || hh >= ch1) continue;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (hh * 16 + q * 8 < p.D) {
               uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
-              u.y = pack_bf16x2(__uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
-              u.z = pack_bf16x2(__uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
-              u.w = pack_bf16x2(__uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
+              u.x = pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 0]) * inv, __uint_as_float(oa[hh][q * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 2]) * inv, __uint_as_float(oa[hh][q * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 4]) * inv, __uint_as_float(oa[hh][q * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 6]) * inv, __uint_as_float(oa[hh][q * 8 + 7]) * inv);
               reinterpret_cast<uint4*>(dst)[hh * 2 + q] = u;
             }
           }
@@ -516,29 +504,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
-template <int DPAD, int KT, int kSplit>
-static TcKernel pick_tc_kernel2(int poly8, bool p_bf16) {
+template <int DPAD, int KT>
+static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int pp, int* smem_out) {
+  *smem_out = TcCfg<DPAD, KT>::kSmem;
   if constexpr (DPAD == 64) {   // the SDXL / SD-2.1 head dim: every polynomial share (GDF_FA_POLY8 = 0 / 2 / 3 / 4)
     if (!p_bf16) {
-      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, kSplit>;
-      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, kSplit>;
+      if (pp) {
+        if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, true>;
+        if (poly8 == 3) return attention_tc_kernel<DPAD, KT, 3, false, true>;
+        if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, true>;
+        return attention_tc_kernel<DPAD, KT, 0, false, true>;
+      }
+      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, false>;
+      if (poly8 == 3) return attention_tc_kernel<DPAD, KT, 3, false, false>;
+      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, false>;
+      return attention_tc_kernel<DPAD, KT, 0, false, false>;
     }
   }
-  if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true, kSplit> : attention_tc_kernel<DPAD, KT, 0, true, kSplit>;
-  return poly8 ? attention_tc_kernel<DPAD, KT, 3, false, kSplit> : attention_tc_kernel<DPAD, KT, 0, false, kSplit>;
-}
-template <int DPAD, int KT>
-static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int split, int pp, int* smem_out) {
-  *smem_out = TcCfg<DPAD, KT>::kSmem;
-  if constexpr (DPAD == 64) {
-    if (pp && split != 2 && !p_bf16) {
-      if (poly8 == 2) return attention_tc_kernel<DPAD, KT, 2, false, 1, true>;
-      if (poly8 == 3) return attention_tc_kernel<DPAD, KT, 3, false, 1, true>;
-      if (poly8 == 4) return attention_tc_kernel<DPAD, KT, 4, false, 1, true>;
-      return attention_tc_kernel<DPAD, KT, 0, false, 1, true>;
-    }
+  if (pp) {
+    if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true, true> : attention_tc_kernel<DPAD, KT, 0, true, true>;
+    return poly8 ? attention_tc_kernel<DPAD, KT, 3, false, true> : attention_tc_kernel<DPAD, KT, 0, false, true>;
   }
-  return split == 2 ? pick_tc_kernel2<DPAD, KT, 2>(poly8, p_bf16) : pick_tc_kernel2<DPAD, KT, 1>(poly8, p_bf16);
+  if (p_bf16) return poly8 ? attention_tc_kernel<DPAD, KT, 3, true, false> : attention_tc_kernel<DPAD, KT, 0, true, false>;
+  return poly8 ? attention_tc_kernel<DPAD, KT, 3, false, false> : attention_tc_kernel<DPAD, KT, 0, false, false>;
 }
 
 static unsigned long long* g_trace_buf = nullptr;
@@ -557,12 +545,10 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
                         cudaStream_t stream) {
   if (!attention_tc_supports(D)) return fail(GDF_ERR_UNSUPPORTED, "attention_tc: head dim %d", D);
   if ((ldq | ldk | ldv | ldo) % 8 != 0 || Nk < 1 || Nq < 1) return fail(GDF_ERR_INVALID, "attention_tc: bad strides");
-  static int poly8 = -1, split = -1, pp = 0;
+  static int poly8 = -1, pp = 0;
   if (poly8 < 0) {
     const char* ep = getenv("GDF_FA_POLY8");
     poly8 = ep ? atoi(ep) : 0;
-    const char* es = getenv("GDF_FA_SPLIT");
-    split = es ? atoi(es) : 1;
     const char* e2 = getenv("GDF_FA_PP");
     pp = e2 ? atoi(e2) : 1;
   }
@@ -571,10 +557,10 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   int smem = 0;
   TcKernel kern = nullptr;
   const bool pb = v_f16 == 0;
-  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, split, pp, &smem);
-  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, split, pp, &smem);
-  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, split, pp, &smem);
-  else kern = pick_tc_kernel<128, 64>(poly8, pb, split, pp, &smem);
+  if (dpad == 48) kern = pick_tc_kernel<48, 128>(poly8, pb, pp, &smem);
+  else if (dpad == 64) kern = pick_tc_kernel<64, 128>(poly8, pb, pp, &smem);
+  else if (dpad == 80) kern = pick_tc_kernel<80, 64>(poly8, pb, pp, &smem);
+  else kern = pick_tc_kernel<128, 64>(poly8, pb, pp, &smem);
   {
     // once per distinct kernel (cheap driver call; the set is small)
     static TcKernel configured[64];
@@ -622,7 +608,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   p.ldo = ldo;
   const int sms = gemm_num_sms();
   dim3 grid(p.num_items < sms ? p.num_items : sms);
-  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcHelperThreads + 256 * (split == 2 ? 2 : 1)), (size_t)smem, stream, mq, mk, mv, p));
+  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcHelperThreads + 256), (size_t)smem, stream, mq, mk, mv, p));
   return GDF_OK;
 }
 

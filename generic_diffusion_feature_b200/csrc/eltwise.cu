@@ -1,5 +1,6 @@
 // Bandwidth-bound helpers around the GEMMs: q_sample, nearest upsample, tiny-Cin im2col, dtype casts,
 // weight packing and the conditioning-embedding math (sinusoids + small fp32 linears).
+#include <type_traits>
 #include "ops.h"
 
 namespace gdf {
@@ -142,7 +143,8 @@ cudaError_t launch_cast_bf16_to_f16(const bf16* x, __half* y, long long n, cudaS
 
 // ---------------------------------------------------------------- conv weight packing
 // w[O][I][kh][kw] fp32 -> out[O_pad][k_pad] bf16, k = (ky*kw+kx)*I + c, zero padding rows/cols.
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int O, int O_pad, int I,
+template <typename T>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int O_pad, int I,
                                         int kh, int kw, int k_pad) {
   const long long total = (long long)O_pad * k_pad;
   const int Kreal = kh * kw * I;
@@ -157,13 +159,21 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __res
       const int ky = tap / kw, kx = tap % kw;
       v = w[(((long long)o * I + c) * kh + ky) * kw + kx];
     }
-    out[i] = __float2bfloat16_rn(v);
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) out[i] = __float2half_rn(v);
+    else out[i] = __float2bfloat16_rn(v);
   }
 }
 cudaError_t launch_pack_conv_weight(const float* w_oihw, bf16* out, int O, int O_pad, int I, int kh, int kw, int k_pad,
                                     cudaStream_t stream) {
-  pack_conv_weight_kernel<<<grid_for((long long)O_pad * k_pad), 256, 0, stream>>>(w_oihw, out, O, O_pad, I, kh, kw,
-                                                                                k_pad);
+  pack_conv_weight_kernel<bf16><<<grid_for((long long)O_pad * k_pad), 256, 0, stream>>>(w_oihw, out, O, O_pad, I, kh,
+                                                                                      kw, k_pad);
+  return cudaGetLastError();
+}
+// same packing in fp16: weights of a convolution over an fp16 tensor (feature stacks; kind::f16 needs A and B of one type)
+cudaError_t launch_pack_conv_weight_f16(const float* w_oihw, __half* out, int O, int O_pad, int I, int kh, int kw,
+                                        int k_pad, cudaStream_t stream) {
+  pack_conv_weight_kernel<__half><<<grid_for((long long)O_pad * k_pad), 256, 0, stream>>>(w_oihw, out, O, O_pad, I, kh,
+                                                                                        kw, k_pad);
   return cudaGetLastError();
 }
 

@@ -2336,9 +2336,29 @@ static int build_vae(Builder& b) {
   b.gn_begin(B, G, 64);
   // statistics of `cur` for the GroupNorm that reads it next (null: that GroupNorm runs its own statistics pass)
   float* cur_sums = b.gn_fusable(ch, G, (long long)hw * hw) ? b.gn_slot(B, G) : nullptr;
-  // conv_in: image fp32 NCHW -> im2col (K = 27 -> 64) -> GEMM
+  // conv_in: image fp32 NCHW -> NHWC bf16. Fused kernel (conv_in_sm100.cu: the 27-tap operand is built in shared memory)
+  // when the shape allows; otherwise im2col (K = 27 -> 64) + GEMM. GDF_CONV_IN_FUSED=0 forces the latter (A/B timing).
   bf16* cur = b.buf((long long)B * hw * hw, ch);
+  bool fused_in = conv_in_fused_supported(a.in_channels, ch, hw);
   {
+    const char* ev = getenv("GDF_CONV_IN_FUSED");
+    if (ev && ev[0] == '0') fused_in = false;
+    if (cur_sums && !((ch / G) == 4 || (ch / G) == 8 || (ch / G) == 16)) fused_in = false;
+  }
+  if (fused_in) {
+    int npad = 0;
+    const bf16* w = b.conv_w(V + "conv_in.weight", &npad, 64);
+    const float* bias = b.f32_pad(V + "conv_in.bias", npad);
+    if (!b.err && !b.check_mat(w, ch, 64, "VAE conv_in weight")) return b.err;
+    if (!b.dry && !b.err) {
+      const int S = hw, cpg = ch / G;
+      float* sums = cur_sums;
+      b.ops->tag(kKindGemm, 2.0 * B * S * S * (double)ch * 27.0, "conv_in fused (image -> NHWC, K=27) N=" + std::to_string(ch));
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        return launch_conv_in_fused(rc.images, w, bias, cur, B, S, S, ch, sums, cpg, G, rc.stream);
+      });
+    }
+  } else {
     bf16* col = b.buf((long long)B * hw * hw, 64);
     if (!b.dry) {
       const int S = hw, cin = a.in_channels;

@@ -65,6 +65,11 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
 inline cudaError_t launch_gemm(const GemmLaunch& g, cudaStream_t s) { return launch_gemm(g.maps, g.p, s); }
 int gemm_num_sms();
 
+// ---- first VAE convolution fused from the fp32 NCHW image (conv_in_sm100.cu): no im2col operand in HBM
+bool conv_in_fused_supported(int Cin, int N, int W);
+int launch_conv_in_fused(const float* img, const bf16* w_packed, const float* bias, bf16* out, int B, int H, int W, int N,
+                         float* gn_sums, int gn_cpg, int gn_groups, cudaStream_t stream);
+
 // ---- normalisation (norm.cu)
 // GroupNorm(+SiLU) over NHWC bf16 x[B, HW, C] -> y[B, HW, C]; stats in fp32, workspace >= gn_workspace_floats().
 size_t gn_workspace_floats(int B, int G);
@@ -129,6 +134,8 @@ cudaError_t launch_cast_bf16_to_f16(const bf16* x, __half* y, long long n, cudaS
 // fp32 OIHW conv weight -> bf16 [O_pad][kh*kw*I] (k = (ky*kw+kx)*I + c), rows >= O zero.
 cudaError_t launch_pack_conv_weight(const float* w_oihw, bf16* out, int O, int O_pad, int I, int kh, int kw,
                                     int k_pad, cudaStream_t stream);
+cudaError_t launch_pack_conv_weight_f16(const float* w_oihw, __half* out, int O, int O_pad, int I, int kh, int kw,
+                                        int k_pad, cudaStream_t stream);
 // Sinusoidal timestep embedding (flip_sin_to_cos=True, freq_shift=0): out[n, dim] = [cos | sin].
 cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim, cudaStream_t stream);
 // small fp32 GEMV-style linear for the conditioning MLPs: y[B, N] = act(x[B, K]) W[N, K]^T + b

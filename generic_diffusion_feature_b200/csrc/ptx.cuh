@@ -103,6 +103,11 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
 }
 
 // TMA stores (shared -> global), bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)

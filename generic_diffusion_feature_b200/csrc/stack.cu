@@ -164,6 +164,29 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
   }
 }
 
+// any channel count / offset (latent-sized maps: unet-in / unet-out have 4 channels): one thread per output element
+__global__ void __launch_bounds__(256)
+resize_nhwc_scalar_kernel(const __half* __restrict__ src, int h, int w, int C, int c_off, int B, int OH, int OW, int Ctot,
+                          __half* __restrict__ out) {
+  const long long total = (long long)B * OH * OW * C;
+  const float sy = (float)h / (float)OH, sx = (float)w / (float)OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const BilinearTap ty = bilinear_tap(oy, h, sy), tx = bilinear_tap(ox, w, sx);
+    const __half* s = src + ((long long)b * h * w) * C + c;
+    const float a = __half2float(s[((long long)ty.i0 * w + tx.i0) * C]), bq = __half2float(s[((long long)ty.i0 * w + tx.i1) * C]);
+    const float cq = __half2float(s[((long long)ty.i1 * w + tx.i0) * C]), d = __half2float(s[((long long)ty.i1 * w + tx.i1) * C]);
+    out[(((long long)b * OH + oy) * OW + ox) * Ctot + c_off + c] =
+        __float2half_rn(ty.w0 * (tx.w0 * a + tx.w1 * bq) + ty.w1 * (tx.w0 * cq + tx.w1 * d));
+  }
+}
+
 template <int S>
 static void launch_resize_cell(const ResizeSrc& s, int B, int Ctot, __half* out, float* sumsq, cudaStream_t stream) {
   const int C8P = (s.C / 8 + 31) & ~31;
@@ -237,7 +260,6 @@ rownorm_kernel(const __half* __restrict__ x, long long rows, int C, float* __res
 
 cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, int OH, int OW, int Ctot,
                                  __half* out_nhwc, __half* out_nchw, float* sumsq, cudaStream_t stream) {
-  if (Ctot % 8 != 0) return cudaErrorInvalidValue;
   static int use_cell = -1;
   if (use_cell < 0) {
     const char* e = getenv("GDF_RESIZE_CELL");     // 0: the general kernel for every map (A/B timing)
@@ -249,7 +271,8 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
   for (int i = 0; i < n_src && all_cell; ++i) {
     const ResizeSrc& s = srcs_host[i];
     const int sc = (s.h > 0 && OH % s.h == 0) ? OH / s.h : 0;
-    all_cell = (OW == s.w * sc) && (sc == 1 || sc == 2 || sc == 4 || sc == 8);
+    all_cell = (OW == s.w * sc) && (sc == 1 || sc == 2 || sc == 4 || sc == 8) && s.C % 8 == 0 && s.c_off % 8 == 0 &&
+               Ctot % 8 == 0;
   }
   float* fused_sumsq = (sumsq && all_cell) ? sumsq : nullptr;
   if (fused_sumsq) {
@@ -258,7 +281,17 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
   }
   for (int i = 0; i < n_src; ++i) {
     const ResizeSrc& s = srcs_host[i];
-    if (s.C % 8 != 0 || s.c_off % 8 != 0) return cudaErrorInvalidValue;
+    if (s.C % 8 != 0 || s.c_off % 8 != 0 || Ctot % 8 != 0) {
+      // maps that cannot use 128-bit channel vectors (4-channel latents, or anything stacked behind them)
+      if (out_nchw) return cudaErrorInvalidValue;     // the reference-layout transpose kernel is vector-only
+      if (out_nhwc) {
+        const long long total = (long long)B * OH * OW * s.C;
+        const long long blocks = (total + 255) / 256;
+        resize_nhwc_scalar_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, stream>>>(
+            s.ptr, s.h, s.w, s.C, s.c_off, B, OH, OW, Ctot, out_nhwc);
+      }
+      continue;
+    }
     if (out_nhwc) {
       const int sc = (use_cell && s.h > 0 && OH % s.h == 0 && OW == s.w * (OH / s.h)) ? OH / s.h : 0;
       if (sc == 1) launch_resize_cell<1>(s, B, Ctot, out_nhwc, fused_sumsq, stream);

@@ -12,7 +12,7 @@ ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3
 def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_per_batch=0, act=ACT_NONE,
                   col_scale=None, residual=None, out_scale=1.0, alpha=1.0, out2=None, out_f32=None, cap_pre=None,
                   caps=(), n_out=0, out_batch_stride=0, out_f16_from=0, ln_sums=None, ln_u=None, ln_eps=1e-5,
-                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0):
+                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0, in_f16=False):
     e = Epilogue()
     e.alpha = alpha
     e.n_out = n_out
@@ -51,6 +51,7 @@ def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_pe
     e.gn_cpg = gn_cpg
     e.gn_groups = gn_groups
     e.gn_rows_per_img = gn_rows_per_img
+    e.in_f16 = int(in_f16)           # A and W are fp16 (feature stacks) instead of bf16
     return e
 
 
@@ -75,12 +76,38 @@ def pack_conv_weight(w_oihw, o_pad=None, k_pad=None):
     return out
 
 
+def pack_conv_weight_f16(w_oihw, o_pad=None, k_pad=None):
+    """fp16 packing for convolutions over fp16 tensors (make_epilogue(in_f16=True))."""
+    lib = _lib.load()
+    O, I, kh, kw = w_oihw.shape
+    o_pad = o_pad or ((O + 15) // 16) * 16
+    k_pad = k_pad or kh * kw * I
+    out = torch.empty(o_pad, k_pad, dtype=torch.float16, device=w_oihw.device)
+    check(lib.gdf_op_pack_conv_weight_f16(ptr(w_oihw.float().contiguous()), ptr(out), O, o_pad, I, kh, kw, k_pad,
+                                          stream_ptr()))
+    return out
+
+
 def conv3x3(x_nhwc, w_packed, ep, stride=1, pad_lo=1, block_n=0):
     lib = _lib.load()
     B, H, W, C = x_nhwc.shape
     assert x_nhwc.is_contiguous()
     check(lib.gdf_op_conv3x3(ptr(x_nhwc), B, H, W, C, ptr(w_packed), w_packed.shape[0], stride, pad_lo,
                              ctypes.byref(ep), block_n, stream_ptr()))
+
+
+def conv_in_fused(img_nchw_f32, w_oihw, bias, gn_groups=0):
+    """First VAE convolution fused from the image: (B,3,H,W) fp32 -> bf16 [B, H*W, N] (+ optional GroupNorm sums
+    fp32 [B, gn_groups, 2] of the output)."""
+    lib = _lib.load()
+    B, C, H, W = img_nchw_f32.shape
+    N = w_oihw.shape[0]
+    wp = pack_conv_weight(w_oihw, k_pad=64)
+    out = torch.empty(B, H * W, N, dtype=torch.bfloat16, device=img_nchw_f32.device)
+    sums = torch.zeros(B, gn_groups, 2, dtype=torch.float32, device=out.device) if gn_groups else None
+    check(lib.gdf_op_conv_in(ptr(img_nchw_f32.contiguous()), ptr(wp), ptr(bias.float().contiguous()), ptr(out), B, H, W, N,
+                             ptr(sums), (N // gn_groups) if gn_groups else 0, gn_groups, stream_ptr()))
+    return out, sums
 
 
 def groupnorm(x, gamma, beta, groups, eps, silu):

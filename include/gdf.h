@@ -260,6 +260,10 @@ typedef struct gdf_epilogue {
   void* gn_sums_dev;              /* fp32 [images][gn_groups][2] or NULL */
   int gn_cpg, gn_groups;
   int64_t gn_rows_per_img;
+  /* 1: A and W hold fp16 bit patterns instead of bf16 (operands of one 16-bit type: a convolution or projection over an
+   * fp16 feature stack - the downstream heads of aggregation_network.py:22,97-99 - with weights from
+   * gdf_op_pack_conv_weight_f16) */
+  int in_f16;
 } gdf_epilogue;
 
 /* C[M,N] = A[M,K] W[N,K]^T (+ fused epilogue); batch > 1: A/out strided by *_batch_stride elements,
@@ -273,6 +277,14 @@ int gdf_op_conv3x3(const void* x_dev, int B, int Hin, int Win, int Cin, const vo
                    int pad_lo, const gdf_epilogue* ep, int block_n, void* stream);
 int gdf_op_pack_conv_weight(const void* w_oihw_f32_dev, void* out_bf16_dev, int O, int O_pad, int I, int kh, int kw,
                             int k_pad, void* stream);
+/* First convolution of the VAE encoder fused from the image ([diffusers Encoder.conv_in], 3 -> N channels, 3x3, pad 1):
+ * img fp32 NCHW (B,3,H,W) -> out bf16 NHWC [B*H*W, N] (+ bias), the 27-tap operand is built in shared memory.
+ * w_packed: gdf_op_pack_conv_weight(..., k_pad = 64). N in {64, 128}, W % 128 == 0. gn_sums (optional): fp32
+ * [B][gn_groups][2], the launch ADDS (sum, sum sq) of its output per (image, group of gn_cpg = 4 / 8 / 16 channels). */
+int gdf_op_conv_in(const void* img_nchw_f32_dev, const void* w_packed_dev, const void* bias_dev, void* out_dev, int B,
+                   int H, int W, int N, void* gn_sums_dev, int gn_cpg, int gn_groups, void* stream);
+int gdf_op_pack_conv_weight_f16(const void* w_oihw_f32_dev, void* out_f16_dev, int O, int O_pad, int I, int kh, int kw,
+                                int k_pad, void* stream);
 /* GroupNorm(+SiLU) NHWC bf16 (resnet.py:327-328). workspace_dev: fp32, gdf_op_groupnorm_workspace_floats(B,G). */
 int64_t gdf_op_groupnorm_workspace_floats(int B, int G);
 int gdf_op_groupnorm(const void* x_dev, void* y_dev, const void* gamma_dev, const void* beta_dev, int B, int HW,

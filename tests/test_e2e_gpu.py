@@ -439,10 +439,14 @@ def test_two_extractors_share_one_pipe(cuda_dev):
     def same(x, y):         # GroupNorm statistics use atomics: equal up to summation order (bf16 rounding flips)
         return F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item() >= 0.9999 and \
             (x - y).abs().max().item() <= 0.05 * max(1.0, y.abs().max().item())
-    for k in ids:
-        assert same(a1[k], a2[k]), k
-    for k in b1:
-        assert same(b1[k], b2[k]) and same(b1[k], a1[k]), k
+    def stat(x, y):
+        return (F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item(),
+                (x - y).abs().max().item() / max(1.0, y.abs().max().item()))
+    bad = [(k,) + stat(a1[k], a2[k]) for k in ids if not same(a1[k], a2[k])]
+    assert not bad, "replanned extractor A differs from its first run (id, cos, maxdiff/absmax): %s" % bad[:6]
+    bad = [(k,) + stat(b1[k], b2[k]) for k in b1 if not same(b1[k], b2[k])]
+    bad += [(k + " vs A",) + stat(b1[k], a1[k]) for k in b1 if not same(b1[k], a1[k])]
+    assert not bad, "extractor B (id, cos, maxdiff/absmax): %s" % bad[:6]
     # the ABI rejects an arena smaller than the current plan writes
     small = torch.empty(16, dtype=torch.uint8, device="cuda:0")
     rc = pipe.lib.gdf_denoise_capture(pipe.handle, 50.0, _lib.ptr(ctx.cuda().repeat(2, 1, 1).contiguous()), 77,

@@ -547,3 +547,45 @@ def test_feature_resize_pool_vs_reference_store(cuda_dev, ratio):
         want = gold["r%d" % ratio][k]
         assert got[k].shape == want.shape and got[k].dtype == torch.float16
         assert (got[k].float().cpu() - want).abs().max().item() < 4e-3
+
+
+@pytest.mark.gpu
+def test_aggregation_head_conv_on_fp16_stack(cuda_dev):
+    """AggregationNetwork.out (3x3, bias-free, aggregation_network.py:22,97-99) on the fp16 stack
+    through the implicit-GEMM conv with fp16 operands vs F.conv2d in fp32 on the same stack values and weights rounded
+    to fp16 (tight), and vs unrounded fp32 weights (fp16 weight rounding only)."""
+    from generic_diffusion_feature_b200 import correspondence as C
+    g = torch.Generator(device="cuda").manual_seed(31)
+    B, H, dim, out_dim = 2, 32, 384, 192
+    stack = (torch.randn(B, H * H, dim, generator=g, device="cuda") * 0.5).half()
+    w = torch.randn(out_dim, dim, 3, 3, generator=g, device="cuda") / (9 * dim) ** 0.5
+    head = C.AggregationHead(w)
+    got = head(stack, (H, H))
+    torch.cuda.synchronize()
+    x = stack.float().view(B, H, H, dim).permute(0, 3, 1, 2)
+    want16 = F.conv2d(x, w.half().float(), padding=1)
+    want32 = F.conv2d(x, w, padding=1)
+    assert got.shape == want32.shape
+    assert rel_err(got, want16) < 2e-4
+    assert rel_err(got, want32) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,N,G", [(2, 128, 128, 128, 32), (1, 64, 256, 64, 0), (3, 96, 384, 128, 8)])
+def test_conv_in_fused(cuda_dev, B, H, W, N, G):
+    """VAE Encoder.conv_in fused from the fp32 NCHW image (the 27-tap operand is built in shared memory): vs F.conv2d on
+    bf16-rounded image / weights, and the GroupNorm sums it accumulates for the following GroupNorm."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(41)
+    img = torch.rand(B, 3, H, W, generator=g, device="cuda") * 2 - 1
+    w = torch.randn(N, 3, 3, 3, generator=g, device="cuda") / 27 ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda") * 0.1
+    out, sums = ops.conv_in_fused(img, w, bias, gn_groups=G)
+    torch.cuda.synchronize()
+    want = F.conv2d(img.bfloat16().float(), w.bfloat16().float(), bias, padding=1)       # (B, N, H, W) fp32
+    got = out.float().view(B, H, W, N).permute(0, 3, 1, 2)
+    check_close(got, want, what="conv_in fused")
+    if G:
+        wg = want.view(B, G, N // G, H * W)
+        ref = torch.stack([wg.sum(dim=(2, 3)), (wg * wg).sum(dim=(2, 3))], dim=-1)
+        assert rel_err(sums, ref) < 1e-3
