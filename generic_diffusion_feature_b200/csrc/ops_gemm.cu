@@ -207,6 +207,7 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.gn_cpg_log2 = e.gn_cpg == 4 ? 2 : e.gn_cpg == 8 ? 3 : 4;
   p.gn_groups = e.gn_groups;
   p.gn_rows_per_img = e.gn_rows_per_img > 0 ? e.gn_rows_per_img : 1;
+  p.in_f16 = e.in_f16 ? 1 : 0;   // both builders (the convolution path used to drop it)
 }
 
 // fused GroupNorm statistics need the lean epilogue on every column and 128-row tiles that stay inside one image
@@ -240,7 +241,6 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
   p.batch = batch;
   p.a_mode = kALinear;
-  p.in_f16 = e.in_f16 ? 1 : 0;
   p.a_batched = (batch > 1 && a_batch_stride != 0) ? 1 : 0;
   p.b_batched = (w_batch_stride != 0) ? 1 : 0;
   fill_epilogue(p, e);

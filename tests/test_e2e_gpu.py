@@ -436,8 +436,12 @@ def test_two_extractors_share_one_pipe(cuda_dev):
     a2 = run(fe_a)          # must re-plan again (the cached FeaturePlan is stale)
     b2 = run(fe_b)
     assert list(a2.keys()) == ids and list(b2.keys()) == ["mid-vit-out", "unet-out"]
-    def same(x, y):         # GroupNorm statistics use atomics: equal up to summation order (bf16 rounding flips)
-        return F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item() >= 0.9999 and \
+    def same(x, y):
+        # GroupNorm statistics use atomics, so two runs of ONE plan already differ: a flipped bf16 rounding spreads
+        # through the random-weight network until the difference sits at the bf16 noise floor (measured on this case,
+        # gpurun_out/r02_s8_probe_replan.txt: repeat of the same plan cos 0.99973-0.99996, re-planned 0.99975-0.99997,
+        # either against the oracle 0.9998-0.99997). A replayed foreign plan gives unrelated values (cos ~ 0).
+        return F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item() >= COS_MIN and \
             (x - y).abs().max().item() <= 0.05 * max(1.0, y.abs().max().item())
     def stat(x, y):
         return (F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item(),
