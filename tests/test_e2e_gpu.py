@@ -487,7 +487,8 @@ def test_reloading_weights_replaces_every_packed_tensor(cuda_dev):
     want_b = run(fresh)
     cos = lambda x, y: F.cosine_similarity(x.flatten(), y.flatten(), dim=0).item()
     for k in layer:
-        assert cos(got_b[k], want_b[k]) >= 0.9999, (k, cos(got_b[k], want_b[k]))
+        # two runs of one plan differ at the bf16 noise floor (GroupNorm statistics through atomics): 0.99983-0.99997
+        assert cos(got_b[k], want_b[k]) >= 0.9995, (k, cos(got_b[k], want_b[k]))
         assert cos(got_b[k], got_a[k]) < 0.999, (k, cos(got_b[k], got_a[k]))
 
 
