@@ -57,6 +57,7 @@ struct TcParams {
   float inv_scale;   // 1 / softmax scale (key bias is added in the unscaled score domain)
   const float* key_bias;   // optional fp32 [B, Nk], added to the scaled scores
   int lmode;         // how the denominator product is issued (see issue_pv)
+  int out_tma;       // 1: head dims <= 64 write the output through smem staging + TMA stores
   unsigned long long* trace;   // debug timeline of CTA 0 (gdf_debug_attention_trace): [0] = count, then (id << 40 | clock)
   int trace_cap;
   bf16* O;
@@ -73,7 +74,8 @@ struct TcParams {
 template <int DPAD, int KT, int kPoly8, bool kPBf16, bool kPP = false>
 __global__ void __launch_bounds__(kTcHelperThreads + 256, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                    const __grid_constant__ CUtensorMap map_v, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                    const TcParams p) {
   using C = TcCfg<DPAD, KT>;
   constexpr int NB = C::NB;
   constexpr int HC = KT;            // S columns per softmax thread (thread = one query row)
@@ -109,6 +111,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
+    tma_prefetch_desc(&map_o);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTcRing; ++i) {
@@ -309,6 +312,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     constexpr int n16 = DPAD / 16;     // O columns in 16-column chunks
     constexpr int ch0 = 0, ch1 = n16;
     constexpr bool owns_l = true;
+    constexpr bool kOutTmaOk = DPAD <= 64;   // output through smem staging + one TMA store per query tile
+    const bool kOutTma = kOutTmaOk && p.out_tma != 0;   // (GDF_FA_OUT_TMA=0: per-thread row stores, A/B timing)
     const float thresh = 8.f * p.inv_scale * 0.6931471805599453f;   // lazy rescale: P = 2^(..) stays <= 2^8
     int g = 0;
     int item = blockIdx.x;
@@ -390,6 +395,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         const float neg_m = -m_run * p.scale_log2;
+        if (kOutTma && j == 0 && it > 0) {   // the P buffer staged the previous item's output: TMA must have read it
+          if (quad == 0 && lane == 0) bulk_wait_read<0>();
+          if (t == 0) asm volatile("bar.sync 11, 128;" ::: "memory");
+          else asm volatile("bar.sync 12, 128;" ::: "memory");
+        }
         if (pp_on) {   // wait for the other group to leave its exponential phase
           if (t == 0) asm volatile("bar.sync 9, 256;" ::: "memory");
           else asm volatile("bar.sync 10, 256;" ::: "memory");
@@ -470,6 +480,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if (hh >= ch0 && hh < ch1) tmem_ld_32x16(t_o + hh * 16, oa[hh]);
       tmem_ld_wait();
       const float inv = 1.f / __uint_as_float(l_raw);
+      if (kOutTma) {
+        // head dims <= 64: the output row (<= 128 B) goes into this tile's P buffer (free: the last P V has completed)
+        // in the SW128 layout and leaves through ONE TMA store per tile - per-thread row stores (8 x 16 B, 32 rows per
+        // instruction) cost ~3100 clk per item on the critical path of the one-tile text cross-attention items
+        // (gpurun_out/r02_s6_trace_cross.txt). Rows >= Nq and columns >= D are clipped by the tensor map.
+#pragma unroll
+        for (int hh = 0; hh < n16; ++hh) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int chunk = hh * 2 + q;
+            st_shared_v4(p_row + ((chunk << 4) ^ p_swz),
+                         pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 0]) * inv, __uint_as_float(oa[hh][q * 8 + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 2]) * inv, __uint_as_float(oa[hh][q * 8 + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 4]) * inv, __uint_as_float(oa[hh][q * 8 + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(oa[hh][q * 8 + 6]) * inv, __uint_as_float(oa[hh][q * 8 + 7]) * inv));
+          }
+        }
+        fence_proxy_async_smem();
+        if (t == 0) asm volatile("bar.sync 11, 128;" ::: "memory");
+        else asm volatile("bar.sync 12, 128;" ::: "memory");
+        if (quad == 0 && lane == 0) {
+          tma_store_4d(&map_o, smem + C::kOffP + t * C::kPTile, 0, h, qb * 256 + t * 128, b);
+          bulk_commit();
+        }
+      } else {
       bf16* dst = p.O + ((long long)b * p.Nq + qrow) * p.ldo + h * p.D;
       if (qrow < p.Nq) {
 #pragma unroll
@@ -488,10 +523,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
       }
+      }
       if (quad == 0 && hf == 0) tr(30 + t, g - 1);   // 30 / 31: output of the item written
       // the next item's first P V (accumulate = 0) is only issued after every softmax warp of the tile has published P
       // again: the TMEM loads above are retired (tcgen05.wait::ld) and ordered by the fence before that arrive
     }
+    if (kOutTma && quad == 0 && lane == 0) bulk_wait<0>();   // output stores complete before the CTA (its smem) retires
   }
 
   tc_fence_before();
@@ -502,7 +539,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
 template <int DPAD, int KT>
 static TcKernel pick_tc_kernel(int poly8, bool p_bf16, int pp, int* smem_out) {
@@ -572,7 +609,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
       if (n_conf < 64) configured[n_conf++] = kern;
     }
   }
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   auto make = [&](CUtensorMap* m, const bf16* base, int ld, int N, int rows) -> int {
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)ld * 2, (uint64_t)N * ld * 2};
@@ -582,6 +619,7 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
   GDF_TRY(make(&mq, Q, ldq, Nq, 128));
   GDF_TRY(make(&mk, K, ldk, Nk, kt));
   GDF_TRY(make(&mv, V, ldv, Nk, kt));
+  GDF_TRY(make(&mo, O, ldo, Nq, 128));   // output store map (head dims <= 64; built for every launch, unused otherwise)
   TcParams p;
   p.Nq = Nq;
   p.Nk = Nk;
@@ -603,12 +641,18 @@ int launch_attention_tc(const bf16* Q, int ldq, const bf16* K, int ldk, const bf
       lmode = e ? atoi(e) : 3;
     }
     p.lmode = lmode;
+    static int out_tma = -1;
+    if (out_tma < 0) {
+      const char* e = getenv("GDF_FA_OUT_TMA");
+      out_tma = e ? atoi(e) : 1;
+    }
+    p.out_tma = out_tma;
   }
   p.O = O;
   p.ldo = ldo;
   const int sms = gemm_num_sms();
   dim3 grid(p.num_items < sms ? p.num_items : sms);
-  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcHelperThreads + 256), (size_t)smem, stream, mq, mk, mv, p));
+  GDF_CUDA(launch_pdl(kern, grid, dim3(kTcHelperThreads + 256), (size_t)smem, stream, mq, mk, mv, mo, p));
   return GDF_OK;
 }
 
