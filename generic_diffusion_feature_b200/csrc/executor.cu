@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ops.h"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3 (ranges behind GDF_NVTX=1)
 
 namespace gdf {
 
@@ -49,6 +50,8 @@ struct OpList {   // flat program: closures + bookkeeping for the profiling pass
   std::vector<int> kinds;
   std::vector<double> flops;
   std::vector<std::string> labels;
+  std::vector<std::string> scopes;   // block the op belongs to ("down-level1-repeat0-vit-block0", "vae", ...): NVTX ranges
+  std::string scope;                 // current block, set by the emit_* functions; sticks until the next one
   std::vector<float> last_ms;
   int cur_kind = kKindOther;
   double cur_flops = 0.0;
@@ -58,6 +61,7 @@ struct OpList {   // flat program: closures + bookkeeping for the profiling pass
     kinds.push_back(cur_kind);
     flops.push_back(cur_flops);
     labels.push_back(cur_label);
+    scopes.push_back(scope);
     last_ms.push_back(0.f);
     cur_kind = kKindOther;
     cur_flops = 0.0;
@@ -73,6 +77,8 @@ struct OpList {   // flat program: closures + bookkeeping for the profiling pass
     kinds.clear();
     flops.clear();
     labels.clear();
+    scopes.clear();
+    scope.clear();
     last_ms.clear();
   }
   size_t size() const { return fns.size(); }
@@ -949,6 +955,7 @@ struct Dest {      // where a layer's output goes (gn_sums: statistics requested
 static void emit_resnet(Builder& b, const std::string& wp, const std::string& fid, const bf16* x, int B, int H, int W,
                         int Cin, int Cout, const float* emb, int temb_ch, int groups, float eps, const Dest& d,
                         const float* x_sums = nullptr) {
+  if (b.ops) b.ops->scope = fid.empty() ? wp : fid;   // NVTX range of this block (GDF_NVTX=1)
   // x_sums: GroupNorm statistics of x left by its producer's epilogue (null: norm1 runs its own statistics pass)
   const long long M = (long long)B * H * W;
   bf16* t1 = b.buf(M, Cin);
@@ -1023,6 +1030,7 @@ static void emit_resnet(Builder& b, const std::string& wp, const std::string& fi
 // its output for the next block's norm1 (null: not needed). Both null when the LayerNorms are not folded.
 static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& fid, bf16* hs, int B, int N, int C,
                          int heads, int ctx_dim, int hw, const float* sums_in = nullptr, float* sums_out = nullptr) {
+  if (b.ops) b.ops->scope = fid.empty() ? wp : fid;
   gdf_handle_s* h = b.h;
   const long long M = (long long)B * N;
   const float scale = 1.f / sqrtf((float)(C / heads));
@@ -1214,6 +1222,7 @@ static bf16* emit_tblock(Builder& b, const std::string& wp, const std::string& f
 // Transformer2DModel (transformers/transformer_2d.py:403-530). x [B*hw*hw, C] contiguous (NHWC == token-major).
 static void emit_vit(Builder& b, const std::string& wp, const std::string& fid, const bf16* x, int B, int hw, int C,
                      int heads, int depth, int ctx_dim, int groups, const Dest& d) {
+  if (b.ops) b.ops->scope = fid.empty() ? wp : fid;
   const int N = hw * hw;
   const long long M = (long long)B * N;
   bf16* t = b.buf(M, C);
@@ -1237,6 +1246,7 @@ static void emit_vit(Builder& b, const std::string& wp, const std::string& fid, 
                      C, heads, ctx_dim, hw, sums, sums_next);
     sums = sums_next;
   }
+  if (b.ops) b.ops->scope = fid;
   {
     Epilogue e;
     e.bias = b.f32(wp + ".proj_out.bias");
@@ -1268,6 +1278,7 @@ static int build_unet(Builder& b) {
   const int temb_ch = a.block_out_channels[0] * 4;
   const std::string U = "unet.";
   b.ops = &h->unet_ops;
+  b.ops->scope = "denoiser-head";
   b.gn_fuse = false;   // fused GroupNorm statistics: VAE only (UNet groups of 10 / 20 / 40 channels are not supported)
   b.gn_cap = 0;
 
@@ -1684,6 +1695,7 @@ static int build_dit(Builder& b) {
   const float scale = 1.f / sqrtf((float)hd);
   const std::string T = "transformer.";
   b.ops = &h->unet_ops;
+  b.ops->scope = "denoiser-head";
   b.gn_fuse = false;
   b.gn_cap = 0;
   h->unet_in_cap = -1;
@@ -1771,6 +1783,7 @@ static int build_dit(Builder& b) {
   for (int i = 0; i < a.num_layers; ++i) {
     const std::string wp = T + "transformer_blocks." + std::to_string(i);
     const std::string fid = "vit-block" + std::to_string(i);
+    b.ops->scope = fid;
     const float* table = b.f32(wp + ".scale_shift_table");
     if (!b.dry) {
       b.ops->push_back([=](const RunCtx& rc) -> int {
@@ -1980,6 +1993,7 @@ static int build_flux(Builder& b) {
   const float scale = 1.f / sqrtf((float)hd);
   const std::string T = "transformer.";
   b.ops = &h->unet_ops;
+  b.ops->scope = "denoiser-head";
   b.gn_fuse = false;
   b.gn_cap = 0;
   h->unet_in_cap = -1;
@@ -2107,6 +2121,7 @@ static int build_flux(Builder& b) {
     for (int i = 0; i < a.num_layers; ++i) {
       const std::string wp = T + "transformer_blocks." + std::to_string(i);
       const std::string fid = "vit-block" + std::to_string(i);
+      b.ops->scope = fid;
       const float* mi = mod_img[i] + (long long)s * 6 * C;
       const float* mt = mod_txt[i] + (long long)s * 6 * C;
       bf16* hs_t = hs;
@@ -2226,6 +2241,7 @@ static int build_flux(Builder& b) {
     for (int i = 0; i < a.num_single_layers; ++i) {
       const std::string wp = T + "single_transformer_blocks." + std::to_string(i);
       const std::string fid = "vit-block" + std::to_string(a.num_layers + i);
+      b.ops->scope = fid;
       const float* ms = mod_s[i] + (long long)s * 3 * C;
       bf16* nj = b.buf(S, C);
       b.layernorm_mod(hs, nj, S, C, eps, ms + C, ms, S);
@@ -2331,6 +2347,7 @@ static int build_vae(Builder& b) {
   const float eps = a.norm_eps;
   const std::string V = "vae.encoder.";
   b.ops = &h->vae_ops;
+  b.ops->scope = "vae-encoder";
   int hw = h->img;
   int ch = a.block_out_channels[0];
   b.gn_begin(B, G, 64);
@@ -2603,8 +2620,33 @@ static void free_plan(gdf_handle_s* h) {
   h->has_key_bias = false;
 }
 
+// GDF_NVTX=1: one NVTX range per block of the network (resnet / transformer block / VAE stage, named by the feature-id
+// prefix the reference uses for that block) around the launches of its ops, and one per op (its label), so that an
+// Nsight Systems / ncu --nvtx timeline reads in the reference's vocabulary. Off by default: zero cost in the replay loop.
+static bool nvtx_enabled() {
+  static const bool on = [] { const char* e = getenv("GDF_NVTX"); return e && e[0] == '1'; }();
+  return on;
+}
+static int run_ops_nvtx(OpList& ops, const RunCtx& rc) {
+  const std::string* open_scope = nullptr;
+  int r = GDF_OK;
+  for (size_t i = 0; i < ops.size() && r == GDF_OK; ++i) {
+    if (!open_scope || *open_scope != ops.scopes[i]) {
+      if (open_scope) nvtxRangePop();
+      nvtxRangePushA(ops.scopes[i].empty() ? "gdf" : ops.scopes[i].c_str());
+      open_scope = &ops.scopes[i];
+    }
+    nvtxRangePushA(ops.labels[i].empty() ? "op" : ops.labels[i].c_str());
+    r = ops.fns[i](rc);
+    nvtxRangePop();
+  }
+  if (open_scope) nvtxRangePop();
+  return r;
+}
+
 static int run_ops(gdf_handle_s* h, OpList& ops, const RunCtx& rc) {
   if (!h->profile) {
+    if (nvtx_enabled()) return run_ops_nvtx(ops, rc);
     for (auto& op : ops.fns) GDF_TRY(op(rc));
     return GDF_OK;
   }

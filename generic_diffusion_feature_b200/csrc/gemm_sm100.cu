@@ -1,11 +1,15 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution kernel (see gemm_sm100.cuh).
 //
-// Roles (256 threads, 1 CTA per SM, TMEM 512 columns = 2 accumulator stages of 128 lanes x 256 fp32):
-//   warp 0  : TMA producer  (A tile 128x64 bf16, B tile block_n x 64 bf16, 128B swizzle, num_stages-deep ring)
-//   warp 1  : MMA issuer    (one elected lane issues tcgen05.mma 128 x block_n x 16, commits to mbarriers)
-//   warp 2  : TMEM allocator / deallocator
-//   warps 4-7: epilogue     (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue ->
-//                            swizzled smem staging -> TMA bulk stores; direct 128-bit stores as fallback)
+// Roles (384 threads = 12 warps, 1 CTA per SM; CTA pairs (cluster of 2, tcgen05 cta_group::2) whenever the tile allows;
+// TMEM 512 columns = 2 accumulator stages of 128 lanes x 256 fp32, or 4 x 128 for tiles <= 128 columns wide):
+//   warp 0    : TMA producer (one elected thread; A tile 128x64, B tile block_n / cta_group x 64, 128B swizzle,
+//               num_stages-deep ring, incremental tap / channel-block coordinates for the implicit-GEMM modes)
+//   warp 1    : MMA issuer   (one elected thread of the leader CTA issues tcgen05.mma 128|256 x block_n x 16 and
+//               commits to the mbarriers of both CTAs)
+//   warp 2    : TMEM allocator / deallocator;  warp 3: idle (holds the register budget the epilogue warps take over)
+//   warps 4-11: epilogue     (4 TMEM lane quadrants x 2 interleaved column sets: tcgen05.ld 32 lanes x 32 columns ->
+//               registers -> fused epilogue -> SWIZZLE_64B smem staging -> TMA bulk stores; direct 128-bit stores only
+//               for destinations TMA cannot address)
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static persistent tile loop.
 #include "gemm_sm100.cuh"
 #include "host_util.h"
@@ -120,7 +124,7 @@ __device__ __forceinline__ void gate_residual32(const GemmParams& p, float* v, l
     if (ocol0 + 32 <= lim && (p.ld_res % 8 == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + q);
+        uint4 u = ldg_stream_v4(reinterpret_cast<const uint4*>(r) + q);
         float2 f;
         f = unpack_bf16x2(u.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
         f = unpack_bf16x2(u.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
@@ -364,7 +368,7 @@ __device__ __forceinline__ void store_round(const CUtensorMap* map_a, int col_a,
 struct ResidualRegs { uint4 u[4]; };
 __device__ __forceinline__ void residual_prefetch(ResidualRegs& r, const __nv_bfloat16* src) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) r.u[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+  for (int q = 0; q < 4; ++q) r.u[q] = ldg_stream_v4(reinterpret_cast<const uint4*>(src) + q);
 }
 __device__ __forceinline__ void residual_add(const ResidualRegs& r, float* v) {
 #pragma unroll
@@ -457,7 +461,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_rows = p.block_n / CG;                         // B rows staged by this CTA
-  const int stage_bytes = kStageBytesA + b_rows * kBlockK * 2;
+  const int stage_bytes = (p.a_mode == kAConvS1Halo ? 0 : kStageBytesA) + b_rows * kBlockK * 2;
   uint8_t* stg = smem;                                      // [epilogue warp][2 * stg_rounds][32 rows][64 B]
   const int stg_bytes = p.stg_rounds * (kStagingBytes / 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stg_bytes);
@@ -469,6 +473,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAccStages; // [kMaxAccStages]  (CG = 2: the leader's are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages);
   uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages + 1;   // [kEpilogueWarps] residual round landed
+  uint64_t* hfull_bar = res_bar + kEpilogueWarps;                      // [kMaxHaloStages] halo tile landed (kAConvS1Halo)
+  uint64_t* hempty_bar = hfull_bar + kMaxHaloStages;                   // [kMaxHaloStages] its nine taps have been consumed
+  const bool halo = p.a_mode == kAConvS1Halo;
+  // halo mode: region = [halo ring: halo_stages x 36 KB][B ring: num_stages x b_rows x 128 B]
+  uint8_t* const b_ring = smem + (halo ? p.halo_stages * kHaloBytes : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -491,6 +500,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       mbar_init(&tempty_bar[i], CG * kEpilogueWarps);
     }
     for (int i = 0; i < kEpilogueWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kMaxHaloStages; ++i) {
+      mbar_init(&hfull_bar[i], 1);
+      mbar_init(&hempty_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -534,7 +547,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       int s = 0;
       uint32_t ph = 0;
       const int cinb = p.cin_blocks;
-      for (int t = unit0; t < total_units; t += unit_step) {
+      for (int t = unit0; !halo && t < total_units; t += unit_step) {
         int mu, n_tile, bz;
         decode_unit(p, t, num_m_units, mu, n_tile, bz);
         const int m_tile = mu * CG + (int)cta_rank;
@@ -600,6 +613,49 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
       }
+      if (halo) {
+        // Halo-tile convolution: one "block" = (work unit, 64-channel block) = one 36 KB halo box + nine B tiles (taps).
+        // The halo of block i + 1 is requested BEFORE the taps of block i, so that it has a whole block of MMA time
+        // (9 x 4 instructions) to arrive; the B ring is filled in tap order behind it.
+        const int cinb2 = p.cin_blocks;
+        int hs = 0;
+        uint32_t hph = 0;
+        auto issue_halo = [&](int t, int cb) {
+          int mu, n_tile, bz;
+          decode_unit(p, t, num_m_units, mu, n_tile, bz);
+          const int m_tile = mu * CG + (int)cta_rank;
+          const int r = m_tile / p.tiles_x;
+          const int xt = m_tile - r * p.tiles_x;
+          const int bt = r / p.tiles_y;
+          const int yt = r - bt * p.tiles_y;
+          mbar_wait(&hempty_bar[hs], hph ^ 1);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&hfull_bar[hs], (uint32_t)(CG * kHaloBytes));
+          uint8_t* dst = smem + hs * kHaloBytes;
+          if (CG == 2) tma_load_4d_pair(dst, &maps.a, &hfull_bar[hs], cb * kBlockK, xt * p.tw - 1, yt * p.th - 1, bt);
+          else tma_load_4d(dst, &maps.a, &hfull_bar[hs], cb * kBlockK, xt * p.tw - 1, yt * p.th - 1, bt);
+          if (++hs == p.halo_stages) { hs = 0; hph ^= 1; }
+        };
+        const uint32_t b_tx_bytes = (uint32_t)p.block_n * kBlockK * 2;
+        if (unit0 < total_units) issue_halo(unit0, 0);
+        for (int t = unit0; t < total_units; t += unit_step) {
+          int mu, n_tile, bz;
+          decode_unit(p, t, num_m_units, mu, n_tile, bz);
+          const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
+          for (int cb = 0; cb < cinb2; ++cb) {
+            if (cb + 1 < cinb2) issue_halo(t, cb + 1);
+            else if (t + unit_step < total_units) issue_halo(t + unit_step, 0);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], b_tx_bytes);
+              const int k0 = (tap * cinb2 + cb) * kBlockK;
+              uint8_t* b_dst = b_ring + s * stage_bytes;
+              if (CG == 2) tma_load_3d_pair(b_dst, &maps.b, &full_bar[s], k0, b_row0, 0);
+              else tma_load_3d(b_dst, &maps.b, &full_bar[s], k0, b_row0, 0);
+              if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -610,11 +666,49 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      int hs = 0;
+      uint32_t hph = 0;
       const int last_kb = p.num_k_blocks - 1;
       for (int t = unit0; t < total_units; t += unit_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * acc_stride;
+        if (halo) {
+          // nine taps per halo tile: tap (ky, kx) = the operand that starts (ky * 16 + kx) rows into the box, 8-row groups
+          // (one line of the 8-pixel-wide output tile) 2 KB apart; its swizzle phase is the row offset kx
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&hfull_bar[hs], hph);
+            tc_fence_after();
+            const uint32_t h_addr = smem_u32(smem + hs * kHaloBytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - 3 * ky;
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              const uint64_t da = umma_desc_kmajor_sw128_sbo(h_addr + (uint32_t)(ky * kHaloLinePx + kx) * 128u,
+                                                             kHaloLinePx * 128u, p.halo_base_off ? (uint32_t)kx : 0u);
+              const uint64_t db = umma_desc_kmajor_sw128(smem_u32(b_ring + s * stage_bytes));
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+              }
+              const bool last = (cb == p.cin_blocks - 1) && tap == 8;
+              if (CG == 2) {
+                umma_commit_pair(&empty_bar[s], 3);
+                if (tap == 8) umma_commit_pair(&hempty_bar[hs], 3);
+                if (last) umma_commit_pair(&tfull_bar[as], 3);
+              } else {
+                umma_commit(&empty_bar[s]);
+                if (tap == 8) umma_commit(&hempty_bar[hs]);
+                if (last) umma_commit(&tfull_bar[as]);
+              }
+              if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+            if (++hs == p.halo_stages) { hs = 0; hph ^= 1; }
+          }
+          if (++as == acc_stages) { as = 0; aph ^= 1; }
+          continue;
+        }
         for (int kb = 0; kb <= last_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();

@@ -27,7 +27,16 @@ constexpr int kRegionBytes = 160 * 1024;
 constexpr int kGemmSmemBytes = kStagingBytes + kBarrierBytes + kRegionBytes + 1024 /*align slack*/;
 static_assert(kGemmSmemBytes <= 232448, "dynamic shared memory of the GEMM kernel exceeds 227 KB");
 
-enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2 };
+enum GemmAMode : int { kALinear = 0, kAConvS1 = 1, kAConvS2 = 2, kAConvS1Halo = 3 };
+// kAConvS1Halo: stride-1 3x3 convolution whose nine taps read ONE halo tile per 64-channel block from shared memory.
+// Output tile = 16 lines x 8 pixels (128 rows); the producer loads the (18 lines x 16 pixels x 64 channels) box around
+// it once (36 KB, 128B swizzle, one pixel = one 128 B row, one line = 16 rows = 2 KB) and tap (ky, kx) is the UMMA operand
+// that starts (ky * 16 + kx) rows into the box with 8-row groups 2 KB apart: L2 -> smem traffic for A drops from
+// 9 x 16 KB to 36 KB per channel block (the kernel is bound by that traffic at tile widths <= 160).
+constexpr int kHaloLinePx = 16;                               // pixels per halo line in shared memory (10 used)
+constexpr int kHaloLines = 18;
+constexpr int kHaloBytes = kHaloLines * kHaloLinePx * 128;    // 36 KB per 64-channel block
+constexpr int kMaxHaloStages = 4;
 enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3 };
 
 struct CaptureSeg {   // fp16 side output of columns [col_begin, col_end) into a feature-arena slot
@@ -41,6 +50,8 @@ struct GemmParams {
   int n_out;            // valid output columns (<= N, or <= N/2 for GEGLU); padding columns are dropped
   int block_n;          // multiple of 16, <= 256 (multiple of 64 when act == GEGLU)
   int num_stages;       // operand ring depth: ring bytes / (16 KB + block_n / cta_group * 128 B), <= kMaxStages
+  int halo_stages;      // kAConvS1Halo: halo tiles in flight (the B tiles of the taps use num_stages)
+  int halo_base_off;    // kAConvS1Halo: 1 = descriptors carry the matrix base offset of their start row (A/B knob)
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;

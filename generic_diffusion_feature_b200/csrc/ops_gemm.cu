@@ -90,7 +90,16 @@ static void finish_stages(GemmParams& p) {
   // they run with one staging round per warp and give the 32 KB to the ring. GDF_STG1_MIN_KB tunes the threshold.
   p.stg_rounds = (p.num_k_blocks >= env_int("GDF_STG1_MIN_KB", 16)) ? 1 : 2;
   const int ring = kRegionBytes + (2 - p.stg_rounds) * (kStagingBytes / 2) - (p.res_tma ? kResBytes : 0);
-  p.num_stages = ring / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
+  if (p.a_mode == kAConvS1Halo) {
+    // three halo tiles (the producer asks for the halo of block i + 1 before the taps of block i, so the slot of block
+    // i - 2 must be free without waiting), the rest of the region is the ring of per-tap B tiles
+    const int b_stage = (p.block_n / p.cta_group) * kBlockK * 2;
+    p.halo_stages = 3;
+    if (ring - p.halo_stages * kHaloBytes < 3 * b_stage) p.halo_stages = 2;
+    p.num_stages = (ring - p.halo_stages * kHaloBytes) / b_stage;
+  } else {
+    p.num_stages = ring / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
+  }
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (env_int("GDF_MAX_STAGES", 0) > 0 && p.num_stages > env_int("GDF_MAX_STAGES", 0))
     p.num_stages = env_int("GDF_MAX_STAGES", 0);   // tuning knob
@@ -272,10 +281,21 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
   if (stride != 1 && stride != 2) return fail(GDF_ERR_UNSUPPORTED, "build_conv3x3: stride %d", stride);
   if (stride == 2 && ((Hin | Win) & 1)) return fail(GDF_ERR_SHAPE, "build_conv3x3: stride 2 needs even H, W");
   const int H = Hin / stride, W = Win / stride;  // output grid
-  const int tw = gcd_int(W, kBlockM);
-  const int th = gcd_int(H, kBlockM / tw);
+  // halo-tile mode (gemm_sm100.cuh kAConvS1Halo): 16 x 8 pixel output tiles, one 18 x 16 pixel box per channel block.
+  // GDF_CONV_HALO=0 keeps the tap-by-tap loads (A/B timing).
+  bool halo = stride == 1 && pad_lo == 1 && W % 8 == 0 && H % 16 == 0 && env_int("GDF_CONV_HALO", 1) != 0;
+  if (block_n <= 0) {
+    const int tw0 = halo ? 8 : gcd_int(W, kBlockM), th0 = halo ? 16 : gcd_int(H, kBlockM / tw0);
+    const int tb0 = kBlockM / (tw0 * th0);
+    block_n = choose_block_n(N, false, (W / tw0) * (H / th0) * ((B + tb0 - 1) / tb0));
+  }
+  // Measured per tile width on one box (gpurun_out/r02_s14_perop_{halo,nohalo}.csv, SDXL-1024 step): 128-column tiles
+  // +5..10 %, 256-column tiles +1..3 %, 160-column tiles (UNet convolutions with N = 320 / 640 / 1280) -5..8 % - those
+  // keep the tap-by-tap loads. GDF_CONV_HALO=2 forces the halo mode for every width.
+  if (halo && block_n > 128 && block_n < 256 && env_int("GDF_CONV_HALO", 1) != 2) halo = false;
+  const int tw = halo ? 8 : gcd_int(W, kBlockM);
+  const int th = halo ? 16 : gcd_int(H, kBlockM / tw);
   const int tb = kBlockM / (tw * th);
-  if (block_n <= 0) block_n = choose_block_n(N, false, (W / tw) * (H / th) * ((B + tb - 1) / tb));
   p.M = B * H * W;
   p.N = N;
   p.K = 9 * Cin;
@@ -287,7 +307,12 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
   p.num_n_tiles = (N + block_n - 1) / block_n;
   p.num_k_blocks = 9 * (Cin / kBlockK);
   p.batch = 1;
-  p.a_mode = (stride == 1) ? kAConvS1 : kAConvS2;
+  p.a_mode = (stride == 1) ? (halo ? kAConvS1Halo : kAConvS1) : kAConvS2;
+  // Measured on B200 (gpurun_out/r02_s13_conv_tests_bo{0,1}.txt): the 128B swizzle of a tcgen05 shared-memory operand
+  // is a function of the ABSOLUTE address bits [7,10), exactly like the TMA write that filled the box, so a tap that
+  // starts kx rows into a 1024 B pattern needs base offset 0; putting (start >> 7) & 7 into the descriptor's
+  // base-offset field is applied ON TOP and gives wrong products (7 of 12 convolution tests fail).
+  p.halo_base_off = env_int("GDF_HALO_BASEOFF", 0);
   p.b_batched = 0;
   p.B_img = B;
   p.H = H;
@@ -305,6 +330,11 @@ int build_conv3x3(GemmLaunch* g, const bf16* X, int B, int Hin, int Win, int Cin
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+    if (halo) {
+      box[1] = kHaloLinePx;   // 16 pixels per line (x0 - 1 ... x0 + 14; 10 are used): one line = 2 KB = two swizzle patterns
+      box[2] = kHaloLines;    // y0 - 1 ... y0 + 16
+      box[3] = 1;
+    }
     GDF_TRY(make_tmap_bf16(&g->maps.a, X, 4, dims, str, box));
   } else {
     // (B, Hout, 2, Wout, 2*Cin): innermost merges (x parity, channel)

@@ -296,6 +296,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major SW128 operand whose 8-row groups are `sbo_bytes` apart and whose first row may sit anywhere on a 128 B
+// boundary inside the 1024 B swizzle pattern (halo-tile convolution taps); base_off = (start address >> 7) & 7 goes
+// into the matrix-base-offset field [49,52).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_off & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // MN-major operand (e.g. V[kv][d] used as B[K=kv][N=d]): rows are K indices, 64 N-elements (128 B) per row,
 // 8-row groups 1024 B apart (SBO); LBO = stride between 64-element N blocks (single block here).
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -400,6 +414,17 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_
 }
 
 // ---------------------------------------------------------------- utilities
+// Streaming 128-bit read that does not allocate in L1: with 227 KB of the SM's 256 KB carved out as shared memory only
+// ~29 KB of L1 are left, and a read-once stream (the residual rows of a GEMM epilogue, 32 KB per tile) evicted the
+// bias / per-sample vectors that every tile re-reads (ncu: 25 % of the kernel's samples on the bias adds of the
+// 128-channel VAE convolution with residual, gpurun_out/r02_s15_conv128_lines.txt).
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr));
+  return v;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
