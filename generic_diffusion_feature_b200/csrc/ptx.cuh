@@ -414,14 +414,16 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_
 }
 
 // ---------------------------------------------------------------- utilities
-// Streaming 128-bit read that does not allocate in L1: with 227 KB of the SM's 256 KB carved out as shared memory only
-// ~29 KB of L1 are left, and a read-once stream (the residual rows of a GEMM epilogue, 32 KB per tile) evicted the
-// bias / per-sample vectors that every tile re-reads (ncu: 25 % of the kernel's samples on the bias adds of the
-// 128-channel VAE convolution with residual, gpurun_out/r02_s15_conv128_lines.txt).
-__device__ __forceinline__ uint4 ldg_stream_v4(const void* ptr) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+// 128-bit read of a small vector that every tile of a persistent kernel re-reads (bias, per-sample row bias): kept in
+// L1 with evict_last priority. With 227 KB of the SM's 256 KB carved out as shared memory only ~29 KB of L1 are left,
+// and the read-once residual rows of a GEMM epilogue (32 KB per tile) evicted those vectors: 25 % of the samples of
+// the 128-channel VAE convolution with residual sat on the bias adds (gpurun_out/r02_s15_conv128_lines.txt).
+// (Reading the residual rows with L1::no_allocate instead is far worse: the four 16 B loads of a thread's 64 B row
+// piece rely on L1 to be merged - 0.708 -> 0.924 ms for the same launch, gpurun_out/r02_s16_perop.csv.)
+__device__ __forceinline__ float4 ldg_keep_f4(const float4* ptr) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(ptr));
   return v;
 }
