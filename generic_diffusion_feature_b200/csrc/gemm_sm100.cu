@@ -615,8 +615,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       if (halo) {
         // Halo-tile convolution: one "block" = (work unit, 64-channel block) = one 36 KB halo box + nine B tiles (taps).
-        // The halo of block i + 1 is requested BEFORE the taps of block i, so that it has a whole block of MMA time
-        // (9 x 4 instructions) to arrive; the B ring is filled in tap order behind it.
+        // The halo of block i + 1 is requested during the taps of block i (see tap_next_halo), so that it has most of a
+        // block of MMA time (9 x 4 instructions) to arrive; the B ring is filled in tap order around it.
         const int cinb2 = p.cin_blocks;
         int hs = 0;
         uint32_t hph = 0;
@@ -636,15 +636,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (++hs == p.halo_stages) { hs = 0; hph ^= 1; }
         };
         const uint32_t b_tx_bytes = (uint32_t)p.block_n * kBlockK * 2;
+        // With two halo tiles the slot of block i + 1 is the one block i - 1 used: it is free once the MMA issuer has
+        // started block i, which the producer knows when it has been granted the B slot of tap `nstages` of block i
+        // (the ring is nstages deep). Asking earlier would park the producer on hempty with the B ring running dry.
+        const int tap_next_halo = p.halo_stages >= 3 ? 0 : (nstages < 8 ? nstages : 8);
         if (unit0 < total_units) issue_halo(unit0, 0);
         for (int t = unit0; t < total_units; t += unit_step) {
           int mu, n_tile, bz;
           decode_unit(p, t, num_m_units, mu, n_tile, bz);
           const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
           for (int cb = 0; cb < cinb2; ++cb) {
-            if (cb + 1 < cinb2) issue_halo(t, cb + 1);
-            else if (t + unit_step < total_units) issue_halo(t + unit_step, 0);
             for (int tap = 0; tap < 9; ++tap) {
+              if (tap == tap_next_halo) {
+                if (cb + 1 < cinb2) issue_halo(t, cb + 1);
+                else if (t + unit_step < total_units) issue_halo(t + unit_step, 0);
+              }
               mbar_wait(&empty_bar[s], ph ^ 1);
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], b_tx_bytes);
               const int k0 = (tap * cinb2 + cb) * kBlockK;
@@ -756,6 +762,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const bool res_tma = !kGeglu && p.res_tma != 0;
     uint8_t* res_buf = res_stg + e * 4096;
     uint64_t* my_res_bar = &res_bar[e];
+    uint32_t* res_sink = reinterpret_cast<uint32_t*>(bars + 64) + e;   // scratch word of this warp (see the residual reads)
     uint32_t res_ph = 0;
     bool res_pending = false;
     // GroupNorm statistics (gn_sums): running per-lane sums of this warp's columns over the tiles of one
@@ -915,7 +922,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               rr[0].u[q] = *reinterpret_cast<const uint4*>(res_buf + swz[q]);
               rr[1].u[q] = *reinterpret_cast<const uint4*>(res_buf + 2048 + swz[q]);
             }
-            __syncwarp();                                   // every lane has read the buffer: it may be refilled
+            // The buffer may only be handed back to TMA once the eight loads above have RETURNED, not merely issued:
+            // they queue behind this warp's outstanding global loads (bias / per-sample vectors), and a refill issued
+            // right after them (the residual is usually L2 resident) overtook them - the "sparse wrong values" defect
+            // of round 1: 16 B pieces of a round's residual read as the NEXT round's (zeros where that box lies
+            // beyond N), gpurun_out/r02_s23 probe. The xor chain reads one word of every load (scoreboard wait).
+            {
+              // (ptxas deletes a dead xor chain even inside asm volatile: the result is stored to a scratch word)
+              const uint32_t sink = rr[0].u[0].x ^ rr[0].u[1].x ^ rr[0].u[2].x ^ rr[0].u[3].x ^ rr[1].u[0].x ^
+                                    rr[1].u[1].x ^ rr[1].u[2].x ^ rr[1].u[3].x;
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(res_sink)), "r"(sink) : "memory");
+            }
+            __syncwarp();                                   // every lane HAS the buffer's contents: it may be refilled
             if (lean_round(c + 128)) res_issue(c + 128);    // next round of this tile, behind this round's stores
           }
           tmem_ld_wait();

@@ -91,10 +91,10 @@ static void finish_stages(GemmParams& p) {
   p.stg_rounds = (p.num_k_blocks >= env_int("GDF_STG1_MIN_KB", 16)) ? 1 : 2;
   const int ring = kRegionBytes + (2 - p.stg_rounds) * (kStagingBytes / 2) - (p.res_tma ? kResBytes : 0);
   if (p.a_mode == kAConvS1Halo) {
-    // three halo tiles (the producer asks for the halo of block i + 1 before the taps of block i, so the slot of block
-    // i - 2 must be free without waiting), the rest of the region is the ring of per-tap B tiles
+    // two halo tiles (the one in use + the next, requested part-way through the current block: gemm_sm100.cu
+    // tap_next_halo); the rest of the region is the ring of per-tap B tiles. GDF_HALO_STAGES=3 for A/B timing.
     const int b_stage = (p.block_n / p.cta_group) * kBlockK * 2;
-    p.halo_stages = 3;
+    p.halo_stages = env_int("GDF_HALO_STAGES", 2) == 3 ? 3 : 2;
     if (ring - p.halo_stages * kHaloBytes < 3 * b_stage) p.halo_stages = 2;
     p.num_stages = (ring - p.halo_stages * kHaloBytes) / b_stage;
   } else {
@@ -151,13 +151,13 @@ static int setup_stores(GemmLaunch* g) {
     if (p.ln_sums && (!aligned16(p.ln_u) || p.alpha != 1.f || p.bias_m)) f = false;
     p.fast_epi = f ? 1 : 0;
   }
-  // Residual through TMA only for the short-main-loop launches that keep two staging rounds: long main loops want the
-  // 32 KB as ring depth, and the combination "single staging round + residual TMA" produced sparse wrong values in
-  // the post-residual destinations of one shape (conv 128x128, 320 -> 320, caught by test_ops_gpu.py::
-  // test_conv3x3_resnet_epilogue_long_k) - not understood yet, so it is not used (GDF_RES_TMA_WITH_STG1=1 re-enables
-  // it for debugging).
-  if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0 &&
-      (p.stg_rounds == 2 || env_int("GDF_RES_TMA_WITH_STG1", 0) != 0)) {
+  // Residual through TMA (one 64-column round per warp in flight, fetched under the main loop) for every launch of the
+  // lean path: per-thread row loads after the accumulator wait put a DRAM round trip on every tile's critical path and
+  // evict the bias vectors from the ~29 KB of L1 left next to 227 KB of shared memory (128-channel VAE convolution with
+  // residual: 0.64 -> 0.57 ms, step +1.5 %). Round 1 kept it off for the single-staging-round launches because of
+  // sparse wrong values; that was a write-after-read race in the epilogue (see the comment at the buffer reads in
+  // gemm_sm100.cu), fixed in round 2. GDF_RES_TMA=0 restores the direct loads (A/B timing).
+  if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0) {
     // same geometry as the store maps: [32 rows][32 columns] boxes, SWIZZLE_64B, rows / columns out of range read 0
     GDF_TRY(make_store_map(&g->maps.res, p, p.residual, p.n_out, p.ld_res, 0));
     p.res_tma = 1;

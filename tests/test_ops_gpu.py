@@ -249,6 +249,31 @@ def test_conv3x3_resnet_epilogue_long_k(cuda_dev, B, H, Cin, Cout):
         assert worst < 3e-2, "%s %s: max-relative error %.3e" % (what, name, worst)
 
 
+def test_conv3x3_residual_tma_refill_race(cuda_dev):
+    """Round-1 defect, root-caused in round 2: the epilogue handed its residual staging buffer back to TMA while the
+    shared-memory loads of the current round were still queued behind outstanding global loads, so 16-byte pieces of a
+    round's residual were read as the NEXT round's (zeros where that box lies beyond N). About every second launch of
+    this shape (conv 64x64, 640 -> 640, residual, B = 2) showed 30-350 wrong elements; 12 launches, per-element check."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, C = 2, 64, 640
+    x = _rand_bf16(g, B, C, H, H)
+    w = torch.randn(C, C, 3, 3, generator=g, device="cuda") * (9 * C) ** -0.5
+    bias = torch.randn(C, generator=g, device="cuda")
+    res = _rand_bf16(g, B * H * H, C)
+    want = F.conv2d(x.float(), w.to(torch.bfloat16).float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * H, C)
+    want = want + res.float()
+    wp = ops.pack_conv_weight(w)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    tol = 0.02 * float(want.abs().max())
+    for rep in range(12):
+        out = torch.zeros(B * H * H, C, dtype=torch.bfloat16, device="cuda")
+        ops.conv3x3(x_nhwc, wp, ops.make_epilogue(out=out, bias=bias, residual=res))
+        torch.cuda.synchronize()
+        bad = int(((out.float() - want).abs() > tol).sum())
+        assert bad == 0, "launch %d: %d elements off by more than 2 %% of the largest value" % (rep, bad)
+
+
 @pytest.mark.parametrize("B,HW,C,silu", [(2, 64 * 64, 320, True), (3, 32 * 32, 1920, True), (2, 128 * 128, 128, True),
                                          (1, 16 * 16, 2560, False), (2, 1024, 960, True), (2, 77, 640, True)])
 def test_groupnorm(cuda_dev, B, HW, C, silu):
