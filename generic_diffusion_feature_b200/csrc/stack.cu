@@ -88,23 +88,25 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
   const int OH = h * S, OW = w * S;
   const int C8 = C / 8, C8P = (C8 + 31) & ~31;
   const int ch = (S == 1) ? h : h + 1, cw = (S == 1) ? w : w + 1;     // cells per axis
-  const long long total = (long long)B * ch * cw * C8P;
+  // 32-bit index arithmetic (the host checks total < 2^31): the four 64-bit divisions per cell of the first version
+  // were about as many instructions as the blends of an S = 2 cell
+  const unsigned total = (unsigned)B * ch * cw * C8P;
   const int lane = threadIdx.x & 31;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8P);
-    long long r = i / C8P;
-    const int cxi = (int)(r % cw);
-    r /= cw;
-    const int cyi = (int)(r % ch);
-    const int b = (int)(r / ch);
-    const bool live = c8 < C8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i / (unsigned)C8P;
+    const int c8x = (int)(i - q * (unsigned)C8P);
+    unsigned r = q;
+    const int cxi = (int)(r % (unsigned)cw);
+    r /= (unsigned)cw;
+    const int cyi = (int)(r % (unsigned)ch);
+    const int b = (int)(r / (unsigned)ch);
+    const bool live = c8x < C8;
     const int cy = (S == 1) ? cyi : cyi - 1, cx = (S == 1) ? cxi : cxi - 1;
     const int r0 = cy < 0 ? 0 : cy, r1 = cy + 1 > h - 1 ? h - 1 : cy + 1;
     const int q0 = cx < 0 ? 0 : cx, q1 = cx + 1 > w - 1 ? w - 1 : cx + 1;
     uint4 v00 = make_uint4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
     if (live) {
-      const uint4* sp = reinterpret_cast<const uint4*>(src + ((long long)b * h * w) * C) + c8;
+      const uint4* sp = reinterpret_cast<const uint4*>(src + ((long long)b * h * w) * C) + c8x;
       v00 = __ldg(sp + ((long long)r0 * w + q0) * C8);
       if (S > 1) {
         v01 = __ldg(sp + ((long long)r0 * w + q1) * C8);
@@ -113,6 +115,13 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
       }
     }
     const int oy0 = (S == 1) ? cy : S * cy + S / 2, ox0 = (S == 1) ? cx : S * cx + S / 2;
+    float txw0[S], txw1[S];                        // x taps of the S output columns of this cell (same for every dy)
+#pragma unroll
+    for (int dx = 0; dx < S; ++dx) {
+      const BilinearTap tx = bilinear_tap(ox0 + dx < 0 ? 0 : ox0 + dx, w, 1.f / (float)S);
+      txw0[dx] = tx.w0;
+      txw1[dx] = tx.w1;
+    }
 #pragma unroll
     for (int dy = 0; dy < S; ++dy) {
       const int oy = oy0 + dy;
@@ -136,9 +145,8 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
               }
             }
           } else {
-            const BilinearTap tx = bilinear_tap(ox, w, 1.f / (float)S);
             float o[8];
-            blend8(v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1, o);
+            blend8(v00, v01, v10, v11, ty.w0, ty.w1, txw0[dx], txw1[dx], o);
             u.x = pack_f16x2(o[0], o[1]);
             u.y = pack_f16x2(o[2], o[3]);
             u.z = pack_f16x2(o[4], o[5]);
@@ -152,7 +160,7 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
               }
             }
           }
-          *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * Ctot + c_off + c8 * 8) = u;
+          *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * Ctot + c_off + c8x * 8) = u;
         }
         if (sumsq) {
 #pragma unroll
@@ -160,6 +168,87 @@ resize_cell_nhwc_kernel(const __half* __restrict__ src, int h, int w, int C, int
           if (lane == 0) atomicAdd(sumsq + ((long long)b * OH + oy) * OW + ox, ss);
         }
       }
+    }
+  }
+}
+
+// NHWC -> NHWC, EVERY map of the stack in one launch: block = 8 x 8 output pixels x all channels. The per-map kernels
+// above write one map's channel slab of every pixel (512 B pieces 2 * Ctot bytes apart: 2.5-2.9 TB/s, the same as a
+// strided torch copy into the stack); here a block produces the whole 2 * Ctot byte row of its 64 pixels within a few
+// microseconds, so DRAM sees full-row writes. Warp w owns tile row w: for every map, for each of its 8 pixels the taps
+// are computed once (warp-uniform) and the lanes walk the map's channel vectors (32 x 16 B = 512 B per step); the four
+// corners of neighbouring output pixels are the same source pixels (scale factors 1 ... 8), so the corner loads hit L1
+// after the first touch. The per-pixel squared norm is a register sum per (warp, pixel) + one shuffle reduction at the
+// end: no atomics, no memset, no second pass. Any scale factor (general taps), C and c_off multiples of 8.
+constexpr int kMaxFusedSrc = 64;
+struct ResizeSrcDev {
+  const __half* ptr;
+  int h, w, C, c_off;
+  float sy, sx;
+};
+struct ResizeSrcList {
+  ResizeSrcDev s[kMaxFusedSrc];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+resize_concat_tile_kernel(const __grid_constant__ ResizeSrcList L, int B, int OH, int OW, int Ctot,
+                          __half* __restrict__ out, float* __restrict__ sumsq) {
+  const int tiles_x = (OW + 7) >> 3, tiles_y = (OH + 7) >> 3;
+  const int tx_ = blockIdx.x % tiles_x;
+  const int ty_ = (blockIdx.x / tiles_x) % tiles_y;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oy = ty_ * 8 + warp;
+  if (oy >= OH) return;
+  const int ox0 = tx_ * 8;
+  float ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+  __half* orow = out + (((long long)b * OH + oy) * OW + ox0) * Ctot;
+  for (int m = 0; m < L.n; ++m) {
+    const ResizeSrcDev& s = L.s[m];
+    const int C8 = s.C >> 3;
+    const BilinearTap ty = bilinear_tap(oy, s.h, s.sy);
+    const uint4* base = reinterpret_cast<const uint4*>(s.ptr + ((long long)b * s.h * s.w) * s.C);
+    const uint4* r0 = base + (long long)ty.i0 * s.w * C8;
+    const uint4* r1 = base + (long long)ty.i1 * s.w * C8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (ox0 + j >= OW) break;
+      const BilinearTap tx = bilinear_tap(ox0 + j, s.w, s.sx);
+      const uint4* p00 = r0 + (long long)tx.i0 * C8;
+      const uint4* p01 = r0 + (long long)tx.i1 * C8;
+      const uint4* p10 = r1 + (long long)tx.i0 * C8;
+      const uint4* p11 = r1 + (long long)tx.i1 * C8;
+      uint4* dst = reinterpret_cast<uint4*>(orow + (long long)j * Ctot + s.c_off);
+      for (int c8 = lane; c8 < C8; c8 += 32) {
+        const uint4 v00 = __ldg(p00 + c8), v01 = __ldg(p01 + c8), v10 = __ldg(p10 + c8), v11 = __ldg(p11 + c8);
+        float o[8];
+        blend8(v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1, o);
+        uint4 u;
+        u.x = pack_f16x2(o[0], o[1]);
+        u.y = pack_f16x2(o[2], o[3]);
+        u.z = pack_f16x2(o[4], o[5]);
+        u.w = pack_f16x2(o[6], o[7]);
+        if (sumsq) {   // norm of the ROUNDED values (what a second pass over the fp16 stack would read)
+          const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(hp[q]);
+            ss[j] += f.x * f.x + f.y * f.y;
+          }
+        }
+        dst[c8] = u;
+      }
+    }
+  }
+  if (sumsq) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = ss[j];
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+      if (lane == 0 && ox0 + j < OW) sumsq[((long long)b * OH + oy) * OW + ox0 + j] = v;
     }
   }
 }
@@ -188,32 +277,41 @@ resize_nhwc_scalar_kernel(const __half* __restrict__ src, int h, int w, int C, i
 }
 
 template <int S>
-static void launch_resize_cell(const ResizeSrc& s, int B, int Ctot, __half* out, float* sumsq, cudaStream_t stream) {
+static bool launch_resize_cell(const ResizeSrc& s, int B, int Ctot, __half* out, float* sumsq, cudaStream_t stream) {
   const int C8P = (s.C / 8 + 31) & ~31;
   const long long total = (long long)B * (S == 1 ? s.h : s.h + 1) * (S == 1 ? s.w : s.w + 1) * C8P;
+  if (total >= (1ll << 31)) return false;          // the kernel indexes cells with 32 bits
   const long long blocks = (total + 255) / 256;
   resize_cell_nhwc_kernel<S><<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), 256, 0, stream>>>(
       s.ptr, s.h, s.w, s.C, s.c_off, B, Ctot, out, sumsq);
+  return true;
 }
 
-// NHWC -> NCHW through shared memory: block = 32 output pixels (one row segment) x 64 channels.
+// NHWC -> NCHW through shared memory: block = 64 output pixels (one row segment) x 64 channels. Phase 1 blends
+// (pixel, 8 channels) items and scatters them into a [channel][pixel] tile whose 8-pixel groups are XOR-swizzled by the
+// channel vector index (conflict-free 2-byte scatter); phase 2 writes 8 pixels of one channel per thread as one 16 B
+// store: a warp covers 4 channels x 128 B contiguous (the first version wrote 64 B per warp row with 2-byte stores and
+// ran at 18 % of the HBM peak).
 __global__ void __launch_bounds__(256)
 resize_nchw_kernel(const __half* __restrict__ src, int h, int w, int C, int c_off, int B, int OH, int OW, int Ctot,
                    __half* __restrict__ out) {
-  __shared__ __half tile[64][32 + 2];
-  const int xblocks = (OW + 31) / 32;
+  __shared__ __align__(16) __half tile[64][64];
+  const int xblocks = (OW + 63) / 64;
   const int xb = blockIdx.x % xblocks;
   const int oy = (blockIdx.x / xblocks) % OH;
   const int b = blockIdx.x / (xblocks * OH);
   const int cb = blockIdx.y * 64;
   const float sy = (float)h / (float)OH, sx = (float)w / (float)OW;
   const int C8 = C / 8;
-  {  // 32 pixels x 8 channel-vectors = 256 work items
-    const int px = threadIdx.x >> 3, cv = threadIdx.x & 7;
-    const int ox = xb * 32 + px;
+  const BilinearTap ty = bilinear_tap(oy, h, sy);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // 64 pixels x 8 channel-vectors = 512 work items
+    const int item = threadIdx.x + k * 256;
+    const int px = item >> 3, cv = item & 7;
+    const int ox = xb * 64 + px;
     const int c8 = cb / 8 + cv;
     if (ox < OW && c8 < C8) {
-      const BilinearTap ty = bilinear_tap(oy, h, sy), tx = bilinear_tap(ox, w, sx);
+      const BilinearTap tx = bilinear_tap(ox, w, sx);
       const uint4* s = reinterpret_cast<const uint4*>(src + ((long long)b * h * w) * C) + c8;
       const uint4 v00 = __ldg(s + ((long long)ty.i0 * w + tx.i0) * C8);
       const uint4 v01 = __ldg(s + ((long long)ty.i0 * w + tx.i1) * C8);
@@ -221,17 +319,25 @@ resize_nchw_kernel(const __half* __restrict__ src, int h, int w, int C, int c_of
       const uint4 v11 = __ldg(s + ((long long)ty.i1 * w + tx.i1) * C8);
       float o[8];
       blend8(v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1, o);
+      const int col = (((px >> 3) ^ cv) << 3) | (px & 7);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tile[cv * 8 + j][px] = __float2half_rn(o[j]);
+      for (int j = 0; j < 8; ++j) tile[cv * 8 + j][col] = __float2half_rn(o[j]);
     }
   }
   __syncthreads();
-  {  // 64 channels x 32 pixels, pixel fastest
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int ch = i >> 5, px = i & 31;
-      const int ox = xb * 32 + px;
-      if (ox < OW && cb + ch < C)
-        out[(((long long)b * Ctot + c_off + cb + ch) * OH + oy) * OW + ox] = tile[ch][px];
+  const bool vec = (OW % 8 == 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // 64 channels x 8 pixel groups, pixel group fastest
+    const int item = threadIdx.x + k * 256;
+    const int ch = item >> 3, pg = item & 7;
+    const int ox = xb * 64 + pg * 8;
+    if (cb + ch >= C || ox >= OW) continue;
+    const __half* t = &tile[ch][(pg ^ (ch >> 3)) << 3];
+    __half* dst = out + (((long long)b * Ctot + c_off + cb + ch) * OH + oy) * OW + ox;
+    if (vec && ox + 8 <= OW) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(t);
+    } else {
+      for (int j = 0; j < 8 && ox + j < OW; ++j) dst[j] = t[j];
     }
   }
 }
@@ -272,7 +378,35 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
     const ResizeSrc& s = srcs_host[i];
     const int sc = (s.h > 0 && OH % s.h == 0) ? OH / s.h : 0;
     all_cell = (OW == s.w * sc) && (sc == 1 || sc == 2 || sc == 4 || sc == 8) && s.C % 8 == 0 && s.c_off % 8 == 0 &&
-               Ctot % 8 == 0;
+               Ctot % 8 == 0 && (long long)B * (s.h + 1) * (s.w + 1) * ((s.C / 8 + 31) & ~31) < (1ll << 31);
+  }
+  // every map vectorisable and at most kMaxFusedSrc of them: ONE launch for the NHWC stack (+ sumsq); GDF_RESIZE_FUSED=0
+  // keeps the per-map kernels (A/B timing)
+  static int use_fused = -1;
+  if (use_fused < 0) {
+    const char* e = getenv("GDF_RESIZE_FUSED");
+    use_fused = e ? atoi(e) : 1;
+  }
+  bool fused = use_fused != 0 && out_nhwc != nullptr && n_src <= kMaxFusedSrc && Ctot % 8 == 0;
+  for (int i = 0; i < n_src && fused; ++i)
+    fused = srcs_host[i].C % 8 == 0 && srcs_host[i].c_off % 8 == 0 && srcs_host[i].h > 0 && srcs_host[i].w > 0;
+  if (fused) {
+    ResizeSrcList L;
+    L.n = n_src;
+    for (int i = 0; i < n_src; ++i) {
+      const ResizeSrc& s = srcs_host[i];
+      L.s[i].ptr = s.ptr;
+      L.s[i].h = s.h;
+      L.s[i].w = s.w;
+      L.s[i].C = s.C;
+      L.s[i].c_off = s.c_off;
+      L.s[i].sy = (float)s.h / (float)OH;
+      L.s[i].sx = (float)s.w / (float)OW;
+    }
+    const unsigned blocks = (unsigned)(((OW + 7) / 8) * ((OH + 7) / 8) * B);
+    resize_concat_tile_kernel<<<blocks, 256, 0, stream>>>(L, B, OH, OW, Ctot, out_nhwc, sumsq);
+    out_nhwc = nullptr;    // done (sumsq too); the reference-layout output, if requested, follows below
+    sumsq = nullptr;
   }
   float* fused_sumsq = (sumsq && all_cell) ? sumsq : nullptr;
   if (fused_sumsq) {
@@ -294,11 +428,13 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
     }
     if (out_nhwc) {
       const int sc = (use_cell && s.h > 0 && OH % s.h == 0 && OW == s.w * (OH / s.h)) ? OH / s.h : 0;
-      if (sc == 1) launch_resize_cell<1>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
-      else if (sc == 2) launch_resize_cell<2>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
-      else if (sc == 4) launch_resize_cell<4>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
-      else if (sc == 8) launch_resize_cell<8>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
-      else {
+      bool done = false;
+      if (sc == 1) done = launch_resize_cell<1>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 2) done = launch_resize_cell<2>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 4) done = launch_resize_cell<4>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      else if (sc == 8) done = launch_resize_cell<8>(s, B, Ctot, out_nhwc, fused_sumsq, stream);
+      if (!done) {
+        if (fused_sumsq) return cudaErrorInvalidValue;   // (cannot happen: all_cell implies 32-bit cell counts below)
         const long long total = (long long)B * OH * OW * (s.C / 8);
         const long long blocks = (total + 255) / 256;
         resize_nhwc_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, stream>>>(
@@ -306,7 +442,7 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
       }
     }
     if (out_nchw) {
-      dim3 grid((unsigned)(((OW + 31) / 32) * OH * B), (unsigned)((s.C + 63) / 64));
+      dim3 grid((unsigned)(((OW + 63) / 64) * OH * B), (unsigned)((s.C + 63) / 64));
       resize_nchw_kernel<<<grid, 256, 0, stream>>>(s.ptr, s.h, s.w, s.C, s.c_off, B, OH, OW, Ctot, out_nchw);
     }
   }
