@@ -192,7 +192,7 @@ struct ResizeSrcList {
 };
 __global__ void __launch_bounds__(256)
 resize_concat_tile_kernel(const __grid_constant__ ResizeSrcList L, int B, int OH, int OW, int Ctot,
-                          __half* __restrict__ out, float* __restrict__ sumsq) {
+                          __half* __restrict__ out, float* __restrict__ sumsq, int sumsq_accumulate) {
   const int tiles_x = (OW + 7) >> 3, tiles_y = (OH + 7) >> 3;
   const int tx_ = blockIdx.x % tiles_x;
   const int ty_ = (blockIdx.x / tiles_x) % tiles_y;
@@ -248,7 +248,10 @@ resize_concat_tile_kernel(const __grid_constant__ ResizeSrcList L, int B, int OH
       float v = ss[j];
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-      if (lane == 0 && ox0 + j < OW) sumsq[((long long)b * OH + oy) * OW + ox0 + j] = v;
+      if (lane == 0 && ox0 + j < OW) {   // stacks of more than kMaxFusedSrc maps: later launches add their channels' share
+        float* d = sumsq + ((long long)b * OH + oy) * OW + ox0 + j;
+        *d = sumsq_accumulate ? *d + v : v;
+      }
     }
   }
 }
@@ -387,24 +390,26 @@ cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, i
     const char* e = getenv("GDF_RESIZE_FUSED");
     use_fused = e ? atoi(e) : 1;
   }
-  bool fused = use_fused != 0 && out_nhwc != nullptr && n_src <= kMaxFusedSrc && Ctot % 8 == 0;
+  bool fused = use_fused != 0 && out_nhwc != nullptr && Ctot % 8 == 0;
   for (int i = 0; i < n_src && fused; ++i)
     fused = srcs_host[i].C % 8 == 0 && srcs_host[i].c_off % 8 == 0 && srcs_host[i].h > 0 && srcs_host[i].w > 0;
   if (fused) {
-    ResizeSrcList L;
-    L.n = n_src;
-    for (int i = 0; i < n_src; ++i) {
-      const ResizeSrc& s = srcs_host[i];
-      L.s[i].ptr = s.ptr;
-      L.s[i].h = s.h;
-      L.s[i].w = s.w;
-      L.s[i].C = s.C;
-      L.s[i].c_off = s.c_off;
-      L.s[i].sy = (float)s.h / (float)OH;
-      L.s[i].sx = (float)s.w / (float)OW;
-    }
     const unsigned blocks = (unsigned)(((OW + 7) / 8) * ((OH + 7) / 8) * B);
-    resize_concat_tile_kernel<<<blocks, 256, 0, stream>>>(L, B, OH, OW, Ctot, out_nhwc, sumsq);
+    for (int i0 = 0; i0 < n_src; i0 += kMaxFusedSrc) {   // kMaxFusedSrc maps per launch (kernel-parameter space)
+      ResizeSrcList L;
+      L.n = n_src - i0 < kMaxFusedSrc ? n_src - i0 : kMaxFusedSrc;
+      for (int i = 0; i < L.n; ++i) {
+        const ResizeSrc& s = srcs_host[i0 + i];
+        L.s[i].ptr = s.ptr;
+        L.s[i].h = s.h;
+        L.s[i].w = s.w;
+        L.s[i].C = s.C;
+        L.s[i].c_off = s.c_off;
+        L.s[i].sy = (float)s.h / (float)OH;
+        L.s[i].sx = (float)s.w / (float)OW;
+      }
+      resize_concat_tile_kernel<<<blocks, 256, 0, stream>>>(L, B, OH, OW, Ctot, out_nhwc, sumsq, i0 > 0 ? 1 : 0);
+    }
     out_nhwc = nullptr;    // done (sumsq too); the reference-layout output, if requested, follows below
     sumsq = nullptr;
   }
