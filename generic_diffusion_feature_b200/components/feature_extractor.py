@@ -19,29 +19,38 @@ from .._lib import Slot, check
 ATTN_MEAN_PREFIX = "#attnmean:"     # internal plan ids: head-mean attention probabilities of one attention module
 
 
-def attention_mean_ids(cfg, categories):
+def _place_of(block):
+    """place_in_unet of an attention module: 'down' / 'mid' / 'up' for UNet blocks; every block of a transformer pipe
+    is registered with place 'up' (register_attention_store, feature/components/attention.py:567-593)."""
+    head = block.split("-")[0]
+    return "up" if head == "vit" else head
+
+
+def attention_mean_ids(cfg, categories, dit_cfg=None):
     """Internal ids of the head-mean maps the reference's AttentionStore would receive for the selected categories
-    ('down_cross', 'up_self', ...; feature/components/attention.py:102-118, 531-566), execution order."""
+    ('down_cross', 'up_self', ...; feature/components/attention.py:102-118, 531-593), execution order."""
     ids = []
-    for i in _unet_feature_ids(cfg):
+    base = _dit_feature_ids(dit_cfg) if dit_cfg is not None else _unet_feature_ids(cfg)
+    for i in base:
         for kind in ("self", "cross"):
             if i.endswith("-%s-q" % kind):
                 block = i[:-len("-%s-q" % kind)]
-                if "%s_%s" % (block.split("-")[0], kind) in categories:
+                if "%s_%s" % (_place_of(block), kind) in categories:
                     ids.append(ATTN_MEAN_PREFIX + block + "-" + kind)
     return ids
 
 
-def aggregate_attention(means, categories, img_size):
+def aggregate_attention(means, categories, img_size, transformer=False):
     """AttentionStore.aggregate_attention + the assembly of diffusion_feature.py:488-500 on the head-mean maps:
-    keep maps with (img/32)^2 <= Nq <= (img/16)^2 (attention.py:111-112, 541), group per category and size,
-    (b (h w) c -> b c h w), average each group, nearest-resize to (img/8, img/8), concatenate on the channel axis."""
+    keep maps with (img/32)^2 <= Nq <= (img/16)^2 (attention.py:111-112, 541; (img/8)^2 for transformer pipes, :568),
+    group per category and size, (b (h w) c -> b c h w), average each group, nearest-resize to (img/8, img/8),
+    concatenate on the channel axis."""
     import math
     import torch.nn.functional as F
-    lo, hi = (img_size // 32) ** 2, (img_size // 16) ** 2
+    lo, hi = (img_size // 32) ** 2, (img_size // (8 if transformer else 16)) ** 2
     groups = {c: {} for c in categories}
     for block, kind, t in means:
-        cat = "%s_%s" % (block.split("-")[0], kind)
+        cat = "%s_%s" % (_place_of(block), kind)
         if cat not in groups or not (lo <= t.shape[1] <= hi):
             continue
         size = int(math.sqrt(t.shape[1]))
@@ -95,12 +104,15 @@ def _unet_feature_ids(cfg, layers_per_block=2, with_maps=False):
     return ids
 
 
-def _dit_feature_ids(cfg):
+def _dit_feature_ids(cfg, with_maps=False):
     """Ids of the PixArt branch of prepare_feature_extractor (feature_extractor.py:259-286) that
-    FeatureStore.store keeps, in execution order: per block self-q/k/v, cross-q, ffn-inner, out."""
+    FeatureStore.store keeps, in execution order: per block self-q/k/v, cross-q, ffn-inner, out; with_maps=True adds the
+    attention-probability maps where AttnStoreProcessor gathers them (after the module's q / k / v)."""
     ids = []
+    tags = ("self-q", "self-k", "self-v", "self-map", "cross-q", "cross-map", "ffn-inner", "out") if with_maps else \
+        ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out")
     for k in range(cfg["layers"]):
-        for tag in ("self-q", "self-k", "self-v", "cross-q", "ffn-inner", "out"):
+        for tag in tags:
             ids.append("vit-block%d-%s" % (k, tag))
     return ids
 
@@ -266,14 +278,14 @@ def selected_ids(feature_store, pipe):
         if getattr(pipe, "flux_cfg", None):
             return _flux_feature_ids(pipe.flux_cfg)
         if getattr(pipe, "dit_cfg", None):
-            return _dit_feature_ids(pipe.dit_cfg)
+            return _dit_feature_ids(pipe.dit_cfg, with_maps=True)   # accept-all installs the storing processors too
         # an empty config makes the reference install its storing attention processors (diffusion_feature.py:74-77), so
         # accept-all includes every `...-map` (this is how config_{xl,15}_full.json were produced, :502-514)
         return _unet_feature_ids(pipe.unet_cfg, with_maps=True)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:
-        if "map" in k and getattr(pipe, "unet_cfg", None) is not None:
-            continue          # per-layer attention probabilities of the UNet families (slow path, like the reference)
+        if "map" in k and (getattr(pipe, "unet_cfg", None) is not None or getattr(pipe, "dit_cfg", None) is not None):
+            continue          # per-layer attention probabilities of the UNet / PixArt families (slow path, like the reference)
         if "map" in k or k in ("vae-out", "attn"):
             raise NotImplementedError("feature id '%s' needs the attention-probability / vae-out path, which is "
                                       "not built on the B200 path yet (SURVEY.md 8f)" % k)

@@ -360,7 +360,8 @@ __device__ __forceinline__ void ap_scores(const float* __restrict__ q_s, const b
 __global__ void __launch_bounds__(kApKT)
 attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk,
                        const bf16* __restrict__ V, int ldv, int v_f16, bf16* __restrict__ O, int ldo,
-                       __half* __restrict__ P, int heads, int Nq, int Nk, int D, float scale) {
+                       __half* __restrict__ P, int heads, int Nq, int Nk, int D, float scale,
+                       const float* __restrict__ key_bias) {
   extern __shared__ float ap_smem[];
   float* q_s = ap_smem;                       // [16][D] (pre-scaled queries)
   float* p_s = ap_smem + kApQT * D;           // [16][128] probabilities of the current key tile / reduction scratch
@@ -382,6 +383,11 @@ attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restri
     const int j = k0 + tid;
     if (j < Nk) {
       ap_scores(q_s, Kb + (long long)j * ldk, D, acc);
+      if (key_bias) {   // additive key mask in logit units (PixArt: (1 - mask) * -10000, attention.py:165-263 path)
+        const float kb = __ldg(key_bias + (long long)b * Nk + j);
+#pragma unroll
+        for (int q = 0; q < kApQT; ++q) acc[q] += kb;
+      }
 #pragma unroll
       for (int q = 0; q < kApQT; ++q) {
         const float mn = fmaxf(m_t[q], acc[q]);
@@ -418,6 +424,11 @@ attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restri
     __syncthreads();                        // p_s of the previous tile has been consumed
     if (j < Nk) {
       ap_scores(q_s, Kb + (long long)j * ldk, D, acc);
+      if (key_bias) {
+        const float kb = __ldg(key_bias + (long long)b * Nk + j);
+#pragma unroll
+        for (int q = 0; q < kApQT; ++q) acc[q] += kb;
+      }
 #pragma unroll
       for (int q = 0; q < kApQT; ++q) {
         const float pr = __expf(acc[q] - m_s[q]) / l_s[q];
@@ -461,11 +472,12 @@ attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restri
 }
 cudaError_t launch_attention_probs(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, int v_f16,
                                    bf16* O, int ldo, __half* P, int B, int heads, int Nq, int Nk, int D, float scale,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, const float* key_bias) {
   if (D % 8 != 0 || D > 2 * kApKT || (ldq | ldk | ldv) % 8 != 0 || Nk < 1 || Nq < 1) return cudaErrorInvalidValue;
   const dim3 grid((Nq + kApQT - 1) / kApQT, heads, B);
   const size_t smem = (size_t)(kApQT * D + kApQT * kApKT) * sizeof(float);
-  attention_probs_kernel<<<grid, kApKT, smem, stream>>>(Q, ldq, K, ldk, V, ldv, v_f16, O, ldo, P, heads, Nq, Nk, D, scale);
+  attention_probs_kernel<<<grid, kApKT, smem, stream>>>(Q, ldq, K, ldk, V, ldv, v_f16, O, ldo, P, heads, Nq, Nk, D, scale,
+                                                        key_bias);
   return cudaGetLastError();
 }
 

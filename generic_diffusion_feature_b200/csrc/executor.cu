@@ -910,8 +910,9 @@ class Builder {
   // `#attnmean:<block>-<kind>` slot that the host aggregates into the `attn` feature (diffusion_feature.py:488-500).
   void attention_probs(const std::string& block_id, const char* kind, const bf16* q, int ldq, const bf16* k, int ldk,
                        const bf16* v, int ldv, int v_f16, bf16* o, int ldo, int B, int heads, int Nq, int Nk, float scale,
-                       int head_dim) {
+                       int head_dim, bool use_key_bias = false) {
     if (dry || err) return;
+    gdf_handle_s* hh = h;
     const int64_t map_off = site(block_id + "-" + kind + "-map", heads, Nq, Nk);
     const int64_t mean_off = site("#attnmean:" + block_id + "-" + kind, 1, Nq, Nk);
     __half* scratch = map_off < 0 ? reinterpret_cast<__half*>(buf((long long)B * heads * Nq, Nk)) : nullptr;
@@ -921,8 +922,9 @@ class Builder {
                  std::to_string(Nq) + " Nk=" + std::to_string(Nk));
     ops->push_back([=](const RunCtx& rc) -> int {
       __half* P = map_off >= 0 ? reinterpret_cast<__half*>(rc.arena + map_off) : scratch;
+      const float* kb = (use_key_bias && hh->has_key_bias) ? hh->key_bias : nullptr;   // PixArt caption mask
       OP_CUDA(launch_attention_probs(q, ldq, k, ldk, v, ldv, v_f16, o, ldo, P, B, heads, Nq, Nk, head_dim, scale,
-                                     rc.stream));
+                                     rc.stream, kb));
       if (mean_off >= 0)
         OP_CUDA(launch_head_mean(P, reinterpret_cast<__half*>(rc.arena + mean_off), B, heads, (long long)Nq * Nk,
                                  rc.stream));
@@ -1829,7 +1831,12 @@ static int build_dit(Builder& b) {
     }
     b.rel(n1);
     bf16* ao = b.buf(M, C);
-    b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, hd, false);
+    // attention-probability maps (AttnStoreProcessor on attn1 / attn2 of every block, place 'up':
+    // feature/components/attention.py:583-593): the materialising kernel for the modules whose map is requested
+    if (b.wants(fid + "-self-map") || b.wants("#attnmean:" + fid + "-self"))
+      b.attention_probs(fid, "self", qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, 0, ao, C, B, heads, N, N, scale, hd);
+    else
+      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, B, heads, N, N, scale, hd, false);
     b.rel(qkv);
     bf16* hs1 = b.buf(M, C);
     {
@@ -1883,7 +1890,10 @@ static int build_dit(Builder& b) {
       b.linear(cproj, Mc, C, C, wkv, 2 * C, e);
     }
     bf16* ao2 = b.buf(M, C);
-    b.attention_bias(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, Lc, scale, hd, true);
+    if (b.wants(fid + "-cross-map") || b.wants("#attnmean:" + fid + "-cross"))
+      b.attention_probs(fid, "cross", q2, C, kv, 2 * C, kv + C, 2 * C, 0, ao2, C, B, heads, N, Lc, scale, hd, true);
+    else
+      b.attention_bias(q2, C, kv, 2 * C, kv + C, 2 * C, ao2, C, B, heads, N, Lc, scale, hd, true);
     b.rel(q2);
     b.rel(kv);
     bf16* hs2 = b.buf(M, C);
@@ -2842,8 +2852,9 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
     if (id == "vae-out" || id == "attn")
       return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': vae-out needs the VAE decoder / `attn` is assembled by the host "
                   "from the #attnmean slots", id.c_str());
-    if (id.find("map") != std::string::npos && (h->is_dit || h->is_flux))
-      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps are built for the UNet families only",
+    if ((id.find("map") != std::string::npos || id.rfind("#attnmean:", 0) == 0) && h->is_flux)
+      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps are built for the UNet and PixArt "
+                  "families (the Flux joint-attention maps of feature/components/attention.py:402-527 are not)",
                   id.c_str());
     h->requested[id] = i;
   }

@@ -586,7 +586,19 @@ class MaskedAttention(Attention):
         k = k.view(B, -1, self.heads, d).transpose(1, 2)
         v = v.view(B, -1, self.heads, d).transpose(1, 2)
         m = None if key_bias is None else key_bias[:, None, None, :]
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=m)
+        proc = getattr(self, "attn_store_processor", None)
+        if proc is None:
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=m)
+        else:
+            # AttnStoreProcessor on a PixArt block (feature/components/attention.py:165-263, registered by :583-593):
+            # get_attention_scores = softmax(mask + scale * Q K^T) (baddbmm with the prepared additive mask)
+            attnstore, place = proc
+            sc = q @ k.transpose(-1, -2) * d ** -0.5
+            probs = torch.softmax(sc if m is None else sc + m, dim=-1)
+            if attnstore is not None:
+                attnstore(probs.mean(1), ctx is not x, place)
+            _gather(self, probs, "map")
+            o = probs @ v
         o = o.transpose(1, 2).reshape(B, -1, C)
         return self.to_out[0](o)
 
@@ -673,6 +685,16 @@ class PixArtTransformer2DModel(nn.Module):
         h, w = H // p, W // p
         x = x.reshape(B, h, w, p, p, oc)
         return torch.einsum("nhwpqc->nchpwq", x).reshape(B, oc, h * p, w * p)
+
+
+def register_attention_store_dit(model, img_size, processor_only=False):
+    """register_attention_store, transformer branch (feature/components/attention.py:567-593): attn1 and attn2 of every
+    block get the storing processor with place 'up'; AttentionStore(img_size // 32, img_size // 8)."""
+    store = None if processor_only else AttentionStore(img_size // 32, img_size // 8)
+    for blk in model.transformer_blocks:
+        blk.attn1.attn_store_processor = (store, "up")
+        blk.attn2.attn_store_processor = (store, "up")
+    return store
 
 
 def attach_gatherers_dit(model, store):

@@ -88,6 +88,45 @@ def test_oracle_attention_maps_match_reference_processor():
     assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
 
 
+def test_oracle_pixart_attention_maps_match_reference_processor():
+    """tests/golden/dit_tiny_pixart_maps.pt (transformer pipes): the reference's real
+    AttnStoreProcessor / AttentionStore / register_attention_store (feature/components/attention.py:567-593: attn1 and
+    attn2 of every block, place 'up', AttentionStore(img // 32, img // 8)) on its vendored ada_norm_single blocks with a
+    caption mask that pads 5 tokens - every `vit-block{i}-self-map` / `-cross-map`, the id order, the aggregated `attn`
+    feature; and the host-side mirror (attention_mean_ids / aggregate_attention) fed with the oracle's head means."""
+    from generic_diffusion_feature_b200.components.feature_extractor import (ATTN_MEAN_PREFIX, _dit_feature_ids,
+                                                                             aggregate_attention, attention_mean_ids)
+    gold = torch.load(os.path.join(GOLD, "dit_tiny_pixart_maps.pt"), weights_only=False)
+    assert gold["ids"] == _dit_feature_ids(TINY_DIT, with_maps=True)
+    sd = _models().synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, TINY_DIT)
+    model, _ = build_oracle_dit(TINY_DIT, TINY_VAE, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers_dit(model, store)
+    ast = O.register_attention_store_dit(model, gold["img"])
+    with torch.no_grad():
+        out = model(gold["x"], gold["timestep"], gold["ctx"], gold["mask"])
+    assert list(store.feats.keys()) == gold["ids"] and len(gold["map_ids"]) == 2 * TINY_DIT["layers"]
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+    m = store.feats["vit-block0-cross-map"]
+    assert m.dim() == 4 and m.shape[1] == TINY_DIT["heads"]
+    assert torch.allclose(m.sum(-1), torch.ones_like(m.sum(-1)), atol=1e-5)
+    assert m[..., -5:].abs().max().item() == 0.0                      # padded caption tokens get probability 0
+    attn = O.aggregated_attention_feature(ast, gold["categories"], gold["img"])
+    assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    # host mirror: plan-order head means -> the same `attn`
+    mean_ids = attention_mean_ids(None, gold["categories"], dit_cfg=TINY_DIT)
+    assert mean_ids == [ATTN_MEAN_PREFIX + "vit-block%d-%s" % (i, k) for i in range(TINY_DIT["layers"])
+                        for k in ("self", "cross")]
+    means = [(i[len(ATTN_MEAN_PREFIX):].rsplit("-", 1)[0], i.rsplit("-", 1)[1],
+              store.feats[i[len(ATTN_MEAN_PREFIX):] + "-map"].mean(1)) for i in mean_ids]
+    host = aggregate_attention(means, gold["categories"], gold["img"], transformer=True)
+    assert host.shape == gold["attn"].shape and (host.float() - gold["attn"]).abs().max().item() < 2e-3
+
+
 def test_feature_plan_views_layouts():
     """FeaturePlan.views / attention_means on a hand-made slot table (pure tensor views, no GPU): token-major maps come
     back as (B, C, h, w) with channel stride 1, `...-map` slots as the contiguous (B, heads, Nq, Nk) tensor the

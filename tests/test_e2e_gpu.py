@@ -138,6 +138,49 @@ def test_cuda_matches_reference_vendored_dit_golden(cuda_dev):
     assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
 
 
+def test_cuda_pixart_attention_maps_match_reference_golden(cuda_dev):
+    """SURVEY.md 8f row 1 for the PixArt family: `vit-block{i}-self-map` / `-cross-map` ((B, heads, Nq, Nk), caption mask
+    with 5 padded tokens) and the aggregated `attn` feature vs the fixture written by the reference's REAL
+    AttnStoreProcessor / AttentionStore / register_attention_store (transformer branch) on its vendored blocks."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "dit_tiny_pixart_maps.pt"), weights_only=False)
+    sd = models.synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, TINY_DIT)
+    pipe = models.get_diffusion_model("pixart-sigma", "float16", device="cuda:0", state_dict=sd, dit_cfg=TINY_DIT,
+                                      vae_cfg=TINY_VAE)
+    img = gold["img"]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, "pixart-sigma", "cuda:0", img_size=img,
+                          attention=gold["categories"], external_model=pipe)
+    ts, a, b, s = schedulers.resolve("pixart-sigma", 50)
+    lat = gold["x"] / (a * s)
+    zero = torch.zeros_like(gold["x"])
+    got = fe.extract((gold["ctx"], gold["mask"], gold["ctx"], gold["mask"]), 1, lat.cuda(), image_type="tensors", t=50,
+                     noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"] + ["attn"]
+    m = got["vit-block0-cross-map"]
+    assert m.shape == gold["feats"]["vit-block0-cross-map"].shape and m.dtype == torch.float16
+    assert (m.float().sum(-1) - 1).abs().max().item() < 5e-3
+    assert m[..., -5:].abs().max().item() == 0.0                      # padded caption tokens
+    want = {k: v.float() for k, v in gold["feats"].items()}
+    want["attn"] = gold["attn"].float()
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+    # the flash path (no maps requested) gives the same activations
+    plain = [i for i in gold["ids"] if not i.endswith("-map")]
+    fe2 = FeatureExtractor({i: True for i in plain}, "pixart-sigma", "cuda:0", img_size=img, external_model=pipe)
+    got2 = fe2.extract((gold["ctx"], gold["mask"], gold["ctx"], gold["mask"]), 1, lat.cuda(), image_type="tensors", t=50,
+                       noise=(zero, zero))
+    torch.cuda.synchronize()
+    rows = compare_maps(got2, {k: got[k].float().cpu() for k in plain})
+    assert min(r[1] for r in rows) >= COS_MIN
+
+
 def _run_flux_case(batch, img, fcfg=TINY_FLUX, vcfg=TINY_VAE_FLUX, subset=None):
     from generic_diffusion_feature_b200.components import models
     from generic_diffusion_feature_b200.components.feature_extractor import _flux_feature_ids

@@ -205,15 +205,10 @@ def golden_unet_control(name="unet_tiny_xl_control.pt"):
                os.path.join(OUT, name))
 
 
-def golden_dit(name="dit_tiny_pixart.pt"):
-    """PixArt path: the reference's vendored BasicTransformerBlock (attention.py:469-592, norm_type
-    'ada_norm_single', attention_bias, gelu-approximate FeedForward) + vendored Attention / AttnProcessor2_0 +
-    the reference's real prepare_feature_extractor (PixArt branch, feature_extractor.py:259-286) / FeatureStore.
-    The outer model (PatchEmbed, AdaLayerNormSingle, caption projection, output head) is un-vendored in the
-    reference and comes from the oracle's restatement -> those pieces stay PARITY UNPINNED."""
+def _build_ref_dit(cfg):
+    """The reference's vendored BasicTransformerBlock stack inside the oracle's (un-vendored) outer PixArt model."""
     import torch.nn as nn
     root = ref_shim.install()
-    cfg = TINY_DIT
     C = cfg["heads"] * cfg["head_dim"]
     sd = models.synthetic_state_dict("pixart-sigma", "cpu", None, TINY_VAE, cfg)
     omodel, _ = build_oracle_dit(cfg, TINY_VAE, sd)
@@ -247,6 +242,76 @@ def golden_dit(name="dit_tiny_pixart.pt"):
     for i, blk in enumerate(ref.transformer_blocks):
         blk.load_state_dict({k[len("transformer.transformer_blocks.%d." % i):]: v for k, v in sd.items()
                              if k.startswith("transformer.transformer_blocks.%d." % i)}, strict=True)
+    return ref, omodel, sd
+
+
+def golden_dit_maps(name="dit_tiny_pixart_maps.pt"):
+    """Attention-probability maps of the PixArt family: the reference's REAL AttnStoreProcessor /
+    AttentionStore / register_attention_store (transformer branch, feature/components/attention.py:567-593: attn1 and
+    attn2 of every block, place 'up', AttentionStore(img // 32, img // 8)) installed on its vendored blocks, the
+    `vit-block{i}-self-map` / `-cross-map` ids through the real FeatureStore, a caption mask with padded tokens, and the
+    aggregated `attn` feature assembled like diffusion_feature.py:488-500."""
+    import torch.nn.functional as F
+    cfg = TINY_DIT
+    ref, omodel, sd = _build_ref_dit(cfg)
+    rfe = ref_shim.load_reference_feature_extractor()
+    rat = ref_shim.load_reference_attention_store()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.transformer = ref
+    ids = _dit_feature_ids(cfg, with_maps=True)
+    map_ids = [i for i in ids if i.endswith("-map")]
+    L = cfg["sample_size"]
+    img = 8 * L
+    store = rfe.prepare_feature_extractor("pixart-sigma", pipe, {i: True for i in ids}, 1, True)
+    astore = rat.register_attention_store("pixart-sigma", pipe, img, True)
+    categories = ["up_cross", "up_self"]
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(1, 4, L, L, generator=g)
+    _, ctx, mask, _, _ = make_dit_inputs(1, img, cfg["caption_dim"])
+    mask = mask.clone()
+    mask[:, -5:] = 0                                   # padded caption tokens: their probabilities must come out 0
+    with torch.no_grad():
+        out = ref(x, 50.0, ctx, mask)
+    feats = dict(store.stored_feats)
+    assert list(feats.keys()) == ids, list(feats.keys())[:10]
+    all_attns = []
+    for category, maps in astore.aggregate_attention(categories).items():
+        for size, attn in maps.items():
+            all_attns.append(F.interpolate(attn, size=(img // 8, img // 8)))
+    attn_feat = torch.cat(all_attns, dim=-3)
+    ostore = O.FeatureStore({i: True for i in ids})
+    O.attach_gatherers_dit(omodel, ostore)
+    oast = O.register_attention_store_dit(omodel, img)
+    with torch.no_grad():
+        oout = omodel(x, 50.0, ctx, mask)
+    assert list(ostore.feats.keys()) == ids
+    worst = max((feats[k] - ostore.feats[k]).abs().max().item() for k in ids)
+    oattn = O.aggregated_attention_feature(oast, categories, img)
+    print("%s: %d ids (%d maps) + aggregated attn %s from the reference's AttnStoreProcessor on its vendored PixArt "
+          "blocks; oracle max |diff| %.2e (attn %.2e, out %.2e)"
+          % (name, len(ids), len(map_ids), tuple(attn_feat.shape), worst, (attn_feat - oattn).abs().max().item(),
+             (out - oout).abs().max().item()))
+    assert worst < 1e-3 and (attn_feat - oattn).abs().max().item() < 1e-5
+    # drop the processors again (the oracle model object is shared with nothing else, but be explicit)
+    torch.save({"ids": ids, "map_ids": map_ids, "categories": categories, "img": img, "x": x, "ctx": ctx, "mask": mask,
+                "timestep": 50.0, "attn": attn_feat, "noise_pred": out,
+                "feats": {k: v.to(torch.float16) for k, v in feats.items()},
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference AttnStoreProcessor / AttentionStore "
+                             "on the vendored BasicTransformerBlock, norm_type ada_norm_single)"},
+               os.path.join(OUT, name))
+
+
+def golden_dit(name="dit_tiny_pixart.pt"):
+    """PixArt path: the reference's vendored BasicTransformerBlock (attention.py:469-592, norm_type
+    'ada_norm_single', attention_bias, gelu-approximate FeedForward) + vendored Attention / AttnProcessor2_0 +
+    the reference's real prepare_feature_extractor (PixArt branch, feature_extractor.py:259-286) / FeatureStore.
+    The outer model (PatchEmbed, AdaLayerNormSingle, caption projection, output head) is un-vendored in the
+    reference and comes from the oracle's restatement -> those pieces stay PARITY UNPINNED."""
+    cfg = TINY_DIT
+    ref, omodel, sd = _build_ref_dit(cfg)
     rfe = ref_shim.load_reference_feature_extractor()
 
     class Pipe:
@@ -441,6 +506,7 @@ if __name__ == "__main__":
     golden_unet("2-1", TINY_21, "unet_tiny_21.pt")
     golden_unet("1-5", TINY_15, "unet_tiny_15.pt")       # conv proj_in / proj_out (use_linear_projection False), 8 heads
     golden_unet_maps()
+    golden_dit_maps()
     golden_unet_control()
     golden_dit()
     golden_flux()
