@@ -26,10 +26,16 @@ def _place_of(block):
     return "up" if head == "vit" else head
 
 
-def attention_mean_ids(cfg, categories, dit_cfg=None):
+def attention_mean_ids(cfg, categories, dit_cfg=None, flux_cfg=None):
     """Internal ids of the head-mean maps the reference's AttentionStore would receive for the selected categories
-    ('down_cross', 'up_self', ...; feature/components/attention.py:102-118, 531-593), execution order."""
+    ('down_cross', 'up_self', ...; feature/components/attention.py:102-118, 531-603), execution order."""
     ids = []
+    if flux_cfg is not None:      # one joint attention per block: cross (text keys) first, then self (image keys)
+        for k in range(flux_cfg["layers"] + flux_cfg["single_layers"]):
+            for kind in ("cross", "self"):
+                if "up_%s" % kind in categories:
+                    ids.append(ATTN_MEAN_PREFIX + "vit-block%d-%s" % (k, kind))
+        return ids
     base = _dit_feature_ids(dit_cfg) if dit_cfg is not None else _unet_feature_ids(cfg)
     for i in base:
         for kind in ("self", "cross"):
@@ -117,17 +123,20 @@ def _dit_feature_ids(cfg, with_maps=False):
     return ids
 
 
-def _flux_feature_ids(cfg):
+def _flux_feature_ids(cfg, with_maps=False):
     """Ids of the Flux branch of prepare_feature_extractor (feature_extractor.py:98-123) in execution order:
     double blocks q, k, v, attn-out (attention_processor.py:2280-2283, 2355-2356), norm-out (transformer_flux.py:
     200-201), ffn-inner (attention.py:1249-1258), out (:210-211); single blocks (numbered after the double
     blocks) q, k, v, attn-out (attention_processor.py:2285-2289, 2358-2360), out (transformer_flux.py:107-108)."""
     ids = []
+    # with_maps: FluxAttnStoreProcessor gathers `cross-map` (image queries x text keys) then `self-map` (image x image)
+    # right after q / k / v (feature/components/attention.py:494-502)
+    maps = ("cross-map", "self-map") if with_maps else ()
     for k in range(cfg["layers"]):
-        for tag in ("q", "k", "v", "attn-out", "norm-out", "ffn-inner", "out"):
+        for tag in ("q", "k", "v") + maps + ("attn-out", "norm-out", "ffn-inner", "out"):
             ids.append("vit-block%d-%s" % (k, tag))
     for k in range(cfg["layers"], cfg["layers"] + cfg["single_layers"]):
-        for tag in ("q", "k", "v", "attn-out", "out"):
+        for tag in ("q", "k", "v") + maps + ("attn-out", "out"):
             ids.append("vit-block%d-%s" % (k, tag))
     return ids
 
@@ -276,7 +285,7 @@ def selected_ids(feature_store, pipe):
     (feature_extractor.py:10-15,36). `map` ids need the attention-probability path and raise."""
     if feature_store.accept_all:
         if getattr(pipe, "flux_cfg", None):
-            return _flux_feature_ids(pipe.flux_cfg)
+            return _flux_feature_ids(pipe.flux_cfg, with_maps=True)
         if getattr(pipe, "dit_cfg", None):
             return _dit_feature_ids(pipe.dit_cfg, with_maps=True)   # accept-all installs the storing processors too
         # an empty config makes the reference install its storing attention processors (diffusion_feature.py:74-77), so
@@ -284,9 +293,9 @@ def selected_ids(feature_store, pipe):
         return _unet_feature_ids(pipe.unet_cfg, with_maps=True)
     ids = [k for k, v in feature_store.to_store.items() if v]
     for k in ids:
-        if "map" in k and (getattr(pipe, "unet_cfg", None) is not None or getattr(pipe, "dit_cfg", None) is not None):
-            continue          # per-layer attention probabilities of the UNet / PixArt families (slow path, like the reference)
-        if "map" in k or k in ("vae-out", "attn"):
-            raise NotImplementedError("feature id '%s' needs the attention-probability / vae-out path, which is "
-                                      "not built on the B200 path yet (SURVEY.md 8f)" % k)
+        if "map" in k:
+            continue          # per-layer attention probabilities (slow materialising path, like the reference's)
+        if k in ("vae-out", "attn"):
+            raise NotImplementedError("feature id '%s': vae-out (scheduler.step + VAE decoder) is not built on the B200 "
+                                      "path; `attn` comes from FeatureExtractor(attention=[...])" % k)
     return ids

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kApKT)
 attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restrict__ K, int ldk,
                        const bf16* __restrict__ V, int ldv, int v_f16, bf16* __restrict__ O, int ldo,
                        __half* __restrict__ P, int heads, int Nq, int Nk, int D, float scale,
-                       const float* __restrict__ key_bias) {
+                       const float* __restrict__ key_bias, __half* __restrict__ P2, int split) {
   extern __shared__ float ap_smem[];
   float* q_s = ap_smem;                       // [16][D] (pre-scaled queries)
   float* p_s = ap_smem + kApQT * D;           // [16][128] probabilities of the current key tile / reduction scratch
@@ -433,7 +433,16 @@ attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restri
       for (int q = 0; q < kApQT; ++q) {
         const float pr = __expf(acc[q] - m_s[q]) / l_s[q];
         p_s[q * kApKT + tid] = pr;
-        if (q0 + q < Nq) P[(((long long)b * heads + h) * Nq + q0 + q) * Nk + j] = __float2half_rn(pr);
+        if (q0 + q < Nq) {
+          // keys >= split go to P (pitch Nk - split), keys < split to P2 (pitch split): the Flux joint attention stores
+          // image-query x text-key (`cross-map`) and image x image (`self-map`) separately; split = 0 elsewhere
+          const long long rowi = ((long long)b * heads + h) * Nq + q0 + q;
+          if (j >= split) {
+            if (P) P[rowi * (Nk - split) + (j - split)] = __float2half_rn(pr);
+          } else if (P2) {
+            P2[rowi * split + j] = __float2half_rn(pr);
+          }
+        }
       }
     } else {
 #pragma unroll
@@ -472,12 +481,12 @@ attention_probs_kernel(const bf16* __restrict__ Q, int ldq, const bf16* __restri
 }
 cudaError_t launch_attention_probs(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, int v_f16,
                                    bf16* O, int ldo, __half* P, int B, int heads, int Nq, int Nk, int D, float scale,
-                                   cudaStream_t stream, const float* key_bias) {
+                                   cudaStream_t stream, const float* key_bias, __half* P2, int split) {
   if (D % 8 != 0 || D > 2 * kApKT || (ldq | ldk | ldv) % 8 != 0 || Nk < 1 || Nq < 1) return cudaErrorInvalidValue;
   const dim3 grid((Nq + kApQT - 1) / kApQT, heads, B);
   const size_t smem = (size_t)(kApQT * D + kApQT * kApKT) * sizeof(float);
   attention_probs_kernel<<<grid, kApKT, smem, stream>>>(Q, ldq, K, ldk, V, ldv, v_f16, O, ldo, P, heads, Nq, Nk, D, scale,
-                                                        key_bias);
+                                                        key_bias, P2, split);
   return cudaGetLastError();
 }
 

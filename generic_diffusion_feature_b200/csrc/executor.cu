@@ -2100,6 +2100,57 @@ static int build_flux(Builder& b) {
       return 0;
     });
   };
+  // Joint attention of sample `s` over the [text | image] rows of qkv. With an attention-probability map (or its head
+  // mean for the aggregated `attn` feature) requested for this block - FluxAttnStoreProcessor,
+  // feature/components/attention.py:402-527 - the image-query rows run the materialising kernel, which writes
+  // P[:, :, image rows, text keys] (`cross-map`) and P[:, :, image rows, image keys] (`self-map`) separately; the text
+  // rows (whose probabilities the reference does not store) stay on the flash kernel.
+  std::unordered_map<std::string, int64_t> map_slot_of;
+  auto map_slot = [&](const std::string& id, int Nk_, int s) -> int64_t {
+    auto it = map_slot_of.find(id);
+    int64_t base;
+    if (it == map_slot_of.end()) {
+      base = b.site(id, id[0] == '#' ? 1 : heads, N, Nk_);
+      map_slot_of[id] = base;
+    } else {
+      base = it->second;
+    }
+    return base < 0 ? -1 : base + (int64_t)s * (id[0] == '#' ? 1 : heads) * N * Nk_ * 2;
+  };
+  auto joint_attention = [&](const std::string& fid, int s, bf16* qkv, bf16* out, int ld_out) {
+    const bool maps = b.wants(fid + "-cross-map") || b.wants(fid + "-self-map") ||
+                      b.wants("#attnmean:" + fid + "-cross") || b.wants("#attnmean:" + fid + "-self");
+    if (!maps) {
+      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, out, ld_out, 1, heads, S, S, scale, hd, false);
+      return;
+    }
+    if (b.dry || b.err) return;
+    // registration order = the reference's gather order: cross-map, self-map (then the internal head means)
+    const int64_t cross_off = map_slot(fid + "-cross-map", Lt, s);
+    const int64_t self_off = map_slot(fid + "-self-map", N, s);
+    const int64_t cmean_off = map_slot("#attnmean:" + fid + "-cross", Lt, s);
+    const int64_t smean_off = map_slot("#attnmean:" + fid + "-self", N, s);
+    __half* cross_scr = (cross_off < 0 && cmean_off >= 0) ? reinterpret_cast<__half*>(b.buf((long long)heads * N, Lt)) : nullptr;
+    __half* self_scr = (self_off < 0 && smean_off >= 0) ? reinterpret_cast<__half*>(b.buf((long long)heads * N, N)) : nullptr;
+    b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, out, ld_out, 1, heads, Lt, S, scale, hd, false);
+    b.ops->tag(kKindAttention, 4.0 * heads * (double)N * (double)S * hd,
+               "attention-probs (joint, image rows) heads=" + std::to_string(heads) + " d=" + std::to_string(hd));
+    const bf16* q_img = qkv + (long long)Lt * 3 * C;
+    bf16* o_img = out + (long long)Lt * ld_out;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      __half* Pc = cross_off >= 0 ? reinterpret_cast<__half*>(rc.arena + cross_off) : cross_scr;
+      __half* Ps = self_off >= 0 ? reinterpret_cast<__half*>(rc.arena + self_off) : self_scr;
+      OP_CUDA(launch_attention_probs(q_img, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, 0, o_img, ld_out, Ps, 1, heads, N, S,
+                                     hd, scale, rc.stream, nullptr, Pc, Lt));
+      if (cmean_off >= 0)
+        OP_CUDA(launch_head_mean(Pc, reinterpret_cast<__half*>(rc.arena + cmean_off), 1, heads, (long long)N * Lt, rc.stream));
+      if (smean_off >= 0)
+        OP_CUDA(launch_head_mean(Ps, reinterpret_cast<__half*>(rc.arena + smean_off), 1, heads, (long long)N * N, rc.stream));
+      return 0;
+    });
+    if (cross_scr) b.rel(reinterpret_cast<bf16*>(cross_scr));
+    if (self_scr) b.rel(reinterpret_cast<bf16*>(self_scr));
+  };
   auto qk_norm_rope = [&](bf16* qkv, const float* wq_a, const float* wk_a, const float* wq_b, const float* wk_b,
                           int rows_a) {
     if (b.dry || b.err) return;
@@ -2170,7 +2221,7 @@ static int build_flux(Builder& b) {
       qk_norm_rope(qkv, b.f32(wp + ".attn.norm_added_q.weight"), b.f32(wp + ".attn.norm_added_k.weight"),
                    b.f32(wp + ".attn.norm_q.weight"), b.f32(wp + ".attn.norm_k.weight"), Lt);
       bf16* ao = b.buf(S, C);
-      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, ao, C, 1, heads, S, S, scale, hd, false);
+      joint_attention(fid, s, qkv, ao, C);
       b.rel(qkv);
       bf16* hs2 = b.buf(S, C);
       {
@@ -2287,7 +2338,7 @@ static int build_flux(Builder& b) {
       const float* nq = b.f32(wp + ".attn.norm_q.weight");
       const float* nk = b.f32(wp + ".attn.norm_k.weight");
       qk_norm_rope(qkv, nq, nk, nq, nk, 0);
-      b.attention_bias(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, cat, 5 * C, 1, heads, S, S, scale, hd, false);
+      joint_attention(fid, s, qkv, cat, 5 * C);
       b.rel(qkv);
       capture_rows(cat + (long long)Lt * 5 * C, 5 * C, slot(fid + "-attn-out", C, s), C);
       bf16* hs2 = b.buf(S, C);
@@ -2852,10 +2903,6 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
     if (id == "vae-out" || id == "attn")
       return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': vae-out needs the VAE decoder / `attn` is assembled by the host "
                   "from the #attnmean slots", id.c_str());
-    if ((id.find("map") != std::string::npos || id.rfind("#attnmean:", 0) == 0) && h->is_flux)
-      return fail(GDF_ERR_UNSUPPORTED, "feature id '%s': attention-probability maps are built for the UNet and PixArt "
-                  "families (the Flux joint-attention maps of feature/components/attention.py:402-527 are not)",
-                  id.c_str());
     h->requested[id] = i;
   }
   const gdf_unet_arch& a = h->ua;

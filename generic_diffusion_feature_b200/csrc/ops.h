@@ -101,7 +101,8 @@ cudaError_t launch_attention_generic(const bf16* Q, int ldq, const bf16* K, int 
 // O = P V (the reference's AttnStoreProcessor slow path); v_f16: V holds fp16 bit patterns. head dim % 8 == 0, <= 256.
 cudaError_t launch_attention_probs(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, int v_f16,
                                    bf16* O, int ldo, __half* P, int B, int heads, int Nq, int Nk, int D, float scale,
-                                   cudaStream_t stream, const float* key_bias = nullptr);
+                                   cudaStream_t stream, const float* key_bias = nullptr, __half* P2 = nullptr,
+                                   int split = 0);
 cudaError_t launch_head_mean(const __half* P, __half* out, int B, int heads, long long n, cudaStream_t stream);
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,

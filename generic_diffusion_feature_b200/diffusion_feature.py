@@ -76,11 +76,9 @@ class FeatureExtractor(nn.Module):
         if attention:
             # register_attention_store (diffusion_feature.py:67-68): the head-mean probabilities of every attention
             # module of the selected categories become internal plan slots; `extract` aggregates them into `attn`
-            if getattr(pipe, "flux_cfg", None):
-                raise NotImplementedError("aggregated attention maps are built for the UNet and PixArt families (the Flux "
-                                          "joint-attention processor of feature/components/attention.py:402-527 is not)")
             self._ids = list(self._ids) + attention_mean_ids(getattr(pipe, "unet_cfg", None), list(attention),
-                                                             dit_cfg=getattr(pipe, "dit_cfg", None))
+                                                             dit_cfg=getattr(pipe, "dit_cfg", None),
+                                                             flux_cfg=getattr(pipe, "flux_cfg", None))
 
     # ------------------------------------------------------------------------------------------ images
     def _preprocess_basic(self, x):
@@ -278,7 +276,8 @@ class FeatureExtractor(nn.Module):
                 feats = pool_views(lib, feats, self.feature_store.resize_ratio)
         if self.attention:                                       # diffusion_feature.py:488-500
             feats['attn'] = aggregate_attention(plan.attention_means(arena), list(self.attention), self.img_size,
-                                                transformer=getattr(self.pipe, 'dit_cfg', None) is not None)
+                                                transformer=(getattr(self.pipe, 'dit_cfg', None) is not None or
+                                                             getattr(self.pipe, 'flux_cfg', None) is not None))
         if self.feature_store.accept_all:
             feats = {k: v.cpu() for k, v in feats.items()}   # feature_extractor.py:65-66
         self.feature_store.feats = feats

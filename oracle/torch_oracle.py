@@ -697,6 +697,15 @@ def register_attention_store_dit(model, img_size, processor_only=False):
     return store
 
 
+def register_attention_store_flux(model, img_size, processor_only=False):
+    """register_attention_store, Flux branch (feature/components/attention.py:567-603): the attention of every double
+    and single block gets FluxAttnStoreProcessor with place 'up'; AttentionStore(img_size // 32, img_size // 8)."""
+    store = None if processor_only else AttentionStore(img_size // 32, img_size // 8)
+    for blk in list(model.transformer_blocks) + list(model.single_transformer_blocks):
+        blk.attn.attn_store_processor = (store, "up")
+    return store
+
+
 def attach_gatherers_dit(model, store):
     """prepare_feature_extractor, `hasattr(pipe, 'transformer')` branch (feature_extractor.py:259-286)."""
     for i, blk in enumerate(model.transformer_blocks):
@@ -785,7 +794,23 @@ class FluxAttention(nn.Module):
             q, k, v = torch.cat([cq, q], dim=2), torch.cat([ck, k], dim=2), torch.cat([cv, v], dim=2)
         if rope is not None:
             q, k = apply_rotary_emb(q, rope), apply_rotary_emb(k, rope)
-        o = F.scaled_dot_product_attention(q, k, v)
+        proc = getattr(self, "attn_store_processor", None)
+        if proc is None:
+            o = F.scaled_dot_product_attention(q, k, v)
+        else:
+            # FluxAttnStoreProcessor (feature/components/attention.py:402-527): explicit softmax of the JOINT sequence
+            # (my_scaled_dot_product_attention, :264-292); the image-query rows are split into the text keys
+            # (`cross-map`) and the image keys (`self-map`), head means go to the AttentionStore (cross first), :494-502
+            attnstore, place = proc
+            tl = ctx.shape[1] if ctx is not None else self.text_len
+            probs = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, dim=-1)
+            cross, self_ = probs[:, :, tl:, :tl], probs[:, :, tl:, tl:]
+            if attnstore is not None:
+                attnstore(cross.mean(1), True, place)
+                attnstore(self_.mean(1), False, place)
+            _gather(self, cross, "cross-map")
+            _gather(self, self_, "self-map")
+            o = probs @ v
         o = o.transpose(1, 2).reshape(B, -1, self.heads * d)
         if ctx is not None:
             co, o = o[:, : ctx.shape[1]], o[:, ctx.shape[1]:]

@@ -228,6 +228,45 @@ def test_oracle_matches_reference_vendored_flux():
     assert torch.equal(store.feats["vit-block0-out"], store.feats["vit-block0-norm-out"])
 
 
+def test_oracle_flux_attention_maps_match_reference_processor():
+    """tests/golden/flux_tiny_maps.pt (MMDiT): the reference's real FluxAttnStoreProcessor /
+    AttentionStore / register_attention_store (feature/components/attention.py:402-527, 567-603) on its whole vendored
+    FluxTransformer2DModel - per block `cross-map` (image queries x text keys) and `self-map` (image x image), gathered
+    in that order right after q / k / v, and the aggregated `attn` feature; plus the host-side mirror."""
+    from generic_diffusion_feature_b200.components.feature_extractor import (ATTN_MEAN_PREFIX, _flux_feature_ids,
+                                                                             aggregate_attention, attention_mean_ids)
+    gold = torch.load(os.path.join(GOLD, "flux_tiny_maps.pt"), weights_only=False)
+    assert gold["ids"] == _flux_feature_ids(TINY_FLUX, with_maps=True)
+    sd = _models().synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, TINY_FLUX)
+    model, _ = build_oracle_flux(TINY_FLUX, TINY_VAE_FLUX, sd)
+    store = O.FeatureStore({i: True for i in gold["ids"]})
+    O.attach_gatherers_flux(model, store)
+    ast = O.register_attention_store_flux(model, gold["img"])
+    L = gold["latents"].shape[-1]
+    with torch.no_grad():
+        out = model(O.flux_pack_latents(gold["latents"]), gold["ctx"], gold["pooled"], gold["sigma"],
+                    O.flux_latent_image_ids(L // 2, L // 2), torch.zeros(gold["ctx"].shape[1], 3), gold["guidance"])
+    assert list(store.feats.keys()) == gold["ids"]
+    assert (out - gold["noise_pred"]).abs().max().item() < 1e-4
+    for k in gold["ids"]:
+        ref = gold["feats"][k].float()
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert store.feats[k].shape == ref.shape and (store.feats[k] - ref).abs().max().item() <= tol, k
+    n_img, n_txt = (L // 2) ** 2, TINY_FLUX["ctx_len"]
+    c, m = store.feats["vit-block0-cross-map"], store.feats["vit-block0-self-map"]
+    assert c.shape == (1, TINY_FLUX["heads"], n_img, n_txt) and m.shape == (1, TINY_FLUX["heads"], n_img, n_img)
+    assert torch.allclose(c.sum(-1) + m.sum(-1), torch.ones_like(c.sum(-1)), atol=1e-5)   # one softmax over both parts
+    attn = O.aggregated_attention_feature(ast, gold["categories"], gold["img"])
+    assert attn.shape == gold["attn"].shape and (attn - gold["attn"]).abs().max().item() < 1e-5
+    mean_ids = attention_mean_ids(None, gold["categories"], flux_cfg=TINY_FLUX)
+    nb = TINY_FLUX["layers"] + TINY_FLUX["single_layers"]
+    assert mean_ids == [ATTN_MEAN_PREFIX + "vit-block%d-%s" % (i, k) for i in range(nb) for k in ("cross", "self")]
+    means = [(i[len(ATTN_MEAN_PREFIX):].rsplit("-", 1)[0], i.rsplit("-", 1)[1],
+              store.feats[i[len(ATTN_MEAN_PREFIX):] + "-map"].mean(1)) for i in mean_ids]
+    host = aggregate_attention(means, gold["categories"], gold["img"], transformer=True)
+    assert host.shape == gold["attn"].shape and (host.float() - gold["attn"]).abs().max().item() < 2e-3
+
+
 def test_flux_host_logic_matches_oracle():
     """Parameter naming, rotary tables, the resolved flow-match sigma and the id grammar of the host side agree with
     the oracle's restatement (FluxTransformer2DModel state_dict, FluxPosEmbed, pipeline_flux_img2img.py:745-766)."""

@@ -250,6 +250,48 @@ def test_cuda_matches_reference_vendored_flux_golden(cuda_dev):
     assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
 
 
+def test_cuda_flux_attention_maps_match_reference_golden(cuda_dev):
+    """SURVEY.md 8f row 1 for the Flux family: per block `cross-map` (B, heads, N_img, N_txt) and `self-map`
+    (B, heads, N_img, N_img) of the joint attention and the aggregated `attn` feature vs the fixture written by the
+    reference's REAL FluxAttnStoreProcessor / AttentionStore on its vendored FluxTransformer2DModel."""
+    import os
+    from common import ROOT
+    from generic_diffusion_feature_b200 import schedulers
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "flux_tiny_maps.pt"), weights_only=False)
+    sd = models.synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, TINY_FLUX)
+    pipe = models.get_diffusion_model("flux", "float16", device="cuda:0", state_dict=sd, flux_cfg=TINY_FLUX,
+                                      vae_cfg=TINY_VAE_FLUX)
+    img = gold["img"]
+    fe = FeatureExtractor({i: True for i in gold["ids"]}, "flux", "cuda:0", img_size=img, attention=gold["categories"],
+                          external_model=pipe)
+    sigma, a, b, s = schedulers.resolve("flux", 50, img)
+    lat = gold["latents"] / (a * s)
+    zero = torch.zeros_like(gold["latents"])
+    got = fe.extract((gold["ctx"], gold["pooled"]), 1, lat.cuda(), image_type="tensors", t=50, noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got.keys()) == gold["ids"] + ["attn"]
+    c, m = got["vit-block0-cross-map"], got["vit-block0-self-map"]
+    assert c.shape == gold["feats"]["vit-block0-cross-map"].shape and m.shape == gold["feats"]["vit-block0-self-map"].shape
+    assert (c.float().sum(-1) + m.float().sum(-1) - 1).abs().max().item() < 5e-3
+    want = {k: v.float() for k, v in gold["feats"].items()}
+    want["attn"] = gold["attn"].float()
+    rows = compare_maps(got, want)
+    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    assert not bad, "vs reference golden (id, cos, rel, maxrel): %s" % bad[:8]
+    # only the aggregated feature (no per-layer map ids): internal scratch maps, same activations as the flash path
+    plain = [i for i in gold["ids"] if not i.endswith("-map")]
+    fe2 = FeatureExtractor({i: True for i in plain}, "flux", "cuda:0", img_size=img, attention=["up_cross"],
+                           external_model=pipe)
+    got2 = fe2.extract((gold["ctx"], gold["pooled"]), 1, lat.cuda(), image_type="tensors", t=50, noise=(zero, zero))
+    torch.cuda.synchronize()
+    assert list(got2.keys()) == plain + ["attn"] and got2["attn"].shape[1] == TINY_FLUX["ctx_len"]
+    rows = compare_maps({k: got2[k] for k in plain}, {k: got[k].float().cpu() for k in plain})
+    assert min(r[1] for r in rows) >= COS_MIN
+
+
 def test_tiny_xl_feature_resize(cuda_dev):
     """FeatureExtractor(..., feature_resize=2): every captured map average-pooled 2 x 2 (feature_extractor.py:51-53),
     vs the oracle's FeatureStore with the same ratio."""

@@ -386,6 +386,69 @@ def golden_flux(name="flux_tiny.pt"):
                os.path.join(OUT, name))
 
 
+def golden_flux_maps(name="flux_tiny_maps.pt"):
+    """Attention-probability maps of the Flux family: the reference's REAL FluxAttnStoreProcessor /
+    AttentionStore / register_attention_store (feature/components/attention.py:402-527, 567-603) installed on its whole
+    vendored FluxTransformer2DModel: per block `cross-map` (image queries x text keys) and `self-map` (image x image)
+    through the real FeatureStore + the aggregated `attn` feature (diffusion_feature.py:488-500)."""
+    import torch.nn.functional as F
+    cfg = TINY_FLUX
+    sd = models.synthetic_state_dict("flux", "cpu", None, TINY_VAE_FLUX, None, cfg)
+    ref = ref_shim.build_reference_flux(cfg)
+    ref.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
+    ref.eval()
+    rfe = ref_shim.load_reference_feature_extractor()
+    rat = ref_shim.load_reference_attention_store()
+
+    class Pipe:
+        pass
+    pipe = Pipe()
+    pipe.transformer = ref
+    ids = _flux_feature_ids(cfg, with_maps=True)
+    map_ids = [i for i in ids if i.endswith("-map")]
+    img = 128
+    store = rfe.prepare_feature_extractor("flux", pipe, {i: True for i in ids}, 1, True)
+    astore = rat.register_attention_store("flux", pipe, img, True)
+    categories = ["up_cross", "up_self"]
+    L = img // 8
+    g = torch.Generator().manual_seed(4321)
+    lat = torch.randn(1, cfg["in_ch"] // 4, L, L, generator=g)
+    x = O.flux_pack_latents(lat)
+    _, ctx, pooled, _, _ = make_flux_inputs(1, img, cfg)
+    sigma = O.resolve_flux_sigma(50, img)
+    img_ids, txt_ids = O.flux_latent_image_ids(L // 2, L // 2), torch.zeros(cfg["ctx_len"], 3)
+    with torch.no_grad():
+        out = ref(hidden_states=x, encoder_hidden_states=ctx, pooled_projections=pooled,
+                  timestep=torch.tensor([sigma]), img_ids=img_ids, txt_ids=txt_ids, guidance=torch.tensor([1.0]),
+                  return_dict=False)[0]
+    feats = dict(store.stored_feats)
+    assert list(feats.keys()) == ids, list(feats.keys())[:12]
+    all_attns = []
+    for category, maps in astore.aggregate_attention(categories).items():
+        for size, attn in maps.items():
+            all_attns.append(F.interpolate(attn, size=(img // 8, img // 8)))
+    attn_feat = torch.cat(all_attns, dim=-3)
+    omodel, _ = build_oracle_flux(cfg, TINY_VAE_FLUX, sd)
+    ostore = O.FeatureStore({i: True for i in ids})
+    O.attach_gatherers_flux(omodel, ostore)
+    oast = O.register_attention_store_flux(omodel, img)
+    with torch.no_grad():
+        oout = omodel(x, ctx, pooled, sigma, img_ids, txt_ids, 1.0)
+    assert list(ostore.feats.keys()) == ids
+    worst = max((feats[k] - ostore.feats[k]).abs().max().item() for k in ids)
+    oattn = O.aggregated_attention_feature(oast, categories, img)
+    print("%s: %d ids (%d maps) + aggregated attn %s from the reference's FluxAttnStoreProcessor; oracle max |diff| %.2e "
+          "(attn %.2e, out %.2e)" % (name, len(ids), len(map_ids), tuple(attn_feat.shape), worst,
+                                     (attn_feat - oattn).abs().max().item(), (out - oout).abs().max().item()))
+    assert worst < 1e-3 and (attn_feat - oattn).abs().max().item() < 1e-5
+    torch.save({"ids": ids, "map_ids": map_ids, "categories": categories, "img": img, "latents": lat, "ctx": ctx,
+                "pooled": pooled, "sigma": sigma, "guidance": 1.0, "attn": attn_feat, "noise_pred": out,
+                "feats": {k: v.to(torch.float16) for k, v in feats.items()},
+                "generator": "tools/make_golden.py via tools/ref_shim.py (reference FluxAttnStoreProcessor on the vendored "
+                             "transformer_flux.py)"},
+               os.path.join(OUT, name))
+
+
 def golden_store_resize(name="feature_store_resize.pt"):
     """feature_resize: the reference's REAL FeatureStore.store (feature/components/feature_extractor.py:31-76,
     adaptive_avg_pool2d at :51-53) on seeded conv-style (B,C,h,w) and ViT-style (B,N,C) activations, ratios 2 and 3
@@ -507,6 +570,7 @@ if __name__ == "__main__":
     golden_unet("1-5", TINY_15, "unet_tiny_15.pt")       # conv proj_in / proj_out (use_linear_projection False), 8 heads
     golden_unet_maps()
     golden_dit_maps()
+    golden_flux_maps()
     golden_unet_control()
     golden_dit()
     golden_flux()

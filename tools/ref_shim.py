@@ -548,8 +548,10 @@ def load_reference_attention_store():
     install()."""
     root = install()
     for alias, target in (("diffusers", PKG), ("diffusers.models", PKG + ".models"),
-                          ("diffusers.models.attention_processor", PKG + ".models.attention_processor")):
-        sys.modules.setdefault(alias, sys.modules[target])
+                          ("diffusers.models.attention_processor", PKG + ".models.attention_processor"),
+                          ("diffusers.models.embeddings", PKG + ".models.embeddings")):   # FluxAttnStoreProcessor: rotary
+        if target in sys.modules:
+            sys.modules.setdefault(alias, sys.modules[target])
     if not hasattr(root.attention_processor, "AttnProcessor"):
         raise RuntimeError("vendored attention_processor has no AttnProcessor")
     path = os.path.join(REF, "feature", "components", "attention.py")
