@@ -209,6 +209,10 @@ class BufPool {
       cudaGetLastError();
       return nullptr;
     }
+    // GDF_POISON_WORKSPACE=1 (debug): every new workspace buffer starts as 0xFF bytes (bf16 / fp16 / fp32 NaN), so a kernel
+    // that reads a buffer region nobody wrote in this forward shows up as NaN instead of as a silent run-to-run difference
+    static const bool poison = [] { const char* e = getenv("GDF_POISON_WORKSPACE"); return e && e[0] == '1'; }();
+    if (poison) cudaMemset(p, 0xFF, bytes);
     all_.push_back(p);
     size_of_[p] = bytes;
     total_ += bytes;
@@ -349,7 +353,7 @@ class Builder {
   }
   void gn_begin(int B, int G, int max_slots) {   // call once per op list, before the first producer
     const char* ev = getenv("GDF_GN_FUSE");
-    gn_fuse = !(ev && ev[0] == '0');
+    gn_fuse = !(ev && ev[0] == '0') && !deterministic_mode();   // epilogue statistics are float atomics
     gn_used = 0;
     gn_cap = gn_fuse ? max_slots : 0;
     gn_slab = gn_fuse ? fbuf((long long)max_slots * B * G * 2) : nullptr;
@@ -2508,15 +2512,13 @@ static int build_vae(Builder& b) {
     else b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
     // Q | K fused projection
     const bf16* wqk = b.rows_bf16(ap + "#qk", {ap + ".to_q.weight", ap + ".to_k.weight"}, nullptr);
-    std::vector<int> ident;
-    const float* bq = b.f32(ap + ".to_q.bias");
-    const float* bk = b.f32(ap + ".to_k.bias");
-    float* bqk = nullptr;
-    if (!b.dry) {
-      bqk = b.fbuf(2 * ch);
-      cudaMemcpy(bqk, bq, (size_t)ch * 4, cudaMemcpyDeviceToDevice);
-      cudaMemcpy(bqk + ch, bk, (size_t)ch * 4, cudaMemcpyDeviceToDevice);
-    }
+    // The concatenated q | k bias is a CONSTANT of the plan: it lives in weight storage (f32_cat), not in the activation
+    // pool. Round 1 filled a pool buffer at plan time and released it after the block: the pool handed it to a later
+    // layer, so from the second forward on (the first one still saw the plan-time contents) the VAE's mid-block
+    // attention added whatever activations that layer had left there instead of the bias. Found in round 2 through the
+    // bit-reproducibility probe (tools/probe_determinism_vae2.py: the latents changed for good after the first UNet
+    // forward); the error was small enough (logit shifts of one 512-wide head) to pass the cosine / max-relative bounds.
+    const float* bqk = b.f32_cat(ap + "#qk_bias", {ap + ".to_q.bias", ap + ".to_k.bias"});
     bf16* qk = b.buf(M, 2 * ch);
     {
       Epilogue e;
@@ -2580,7 +2582,6 @@ static int build_vae(Builder& b) {
     }
     b.rel(o);
     b.rel(r0);
-    b.rel(bqk);
     bf16* r1 = b.buf(M, ch);
     Dest d1;
     d1.out = r1;

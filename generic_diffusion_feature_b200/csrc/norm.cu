@@ -3,6 +3,7 @@
 // Reference arithmetic: torch.nn.GroupNorm + SiLU in feature/diffusers/models/resnet.py:327-328,351,363,
 // unet/unet_2d_condition.py:1305-1306, transformers/transformer_2d.py:484; nn.LayerNorm and the
 // ada_norm_single modulation in feature/diffusers/models/attention.py:498-503,539,565,570-572.
+#include <stdlib.h>
 #include "ops.h"
 
 namespace gdf {
@@ -27,6 +28,11 @@ __host__ __device__ inline GnMap gn_map(int C) {
     m.slots = (m.c8 + kGnThreads - 1) / kGnThreads;
   }
   return m;
+}
+
+bool deterministic_mode() {
+  static const bool on = [] { const char* e = getenv("GDF_DETERMINISTIC"); return e && e[0] == '1'; }();
+  return on;
 }
 
 size_t gn_workspace_floats(int B, int G) { return (size_t)B * kGnMaxChunks * G * 2 + (size_t)B * G * 2; }
@@ -96,6 +102,46 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partial, 
     float* dst = partial + (((long long)b * nchunks + chunk) * G + threadIdx.x) * 2;
     dst[0] = s_sum[threadIdx.x];
     dst[1] = s_sq[threadIdx.x];
+  }
+}
+
+// Deterministic variant of pass 1 (GDF_DETERMINISTIC=1): one block per (chunk, group, image), a fixed element -> thread
+// assignment and a fixed-order tree reduction in shared memory instead of shared-memory atomics, so that two runs give
+// bit-identical statistics (and therefore bit-identical features). Strided reads: slower, opt-in.
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_stats_det_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int nchunks) {
+  __shared__ float s_a[kGnThreads], s_b[kGnThreads];
+  pdl_wait();
+  pdl_trigger();
+  const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int cpg = C / G;
+  const int pix_per_chunk = (HW + nchunks - 1) / nchunks;
+  const int p0 = chunk * pix_per_chunk;
+  const int p1 = min(HW, p0 + pix_per_chunk);
+  const long long n = (long long)(p1 > p0 ? p1 - p0 : 0) * cpg;
+  const bf16* base = x + ((long long)b * HW) * C + g * cpg;
+  float sm = 0.f, sq = 0.f;
+  for (long long i = threadIdx.x; i < n; i += kGnThreads) {
+    const long long p = p0 + i / cpg;
+    const int c = (int)(i % cpg);
+    const float v = __bfloat162float(base[p * C + c]);
+    sm += v;
+    sq = fmaf(v, v, sq);
+  }
+  s_a[threadIdx.x] = sm;
+  s_b[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = kGnThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float* dst = partial + (((long long)b * nchunks + chunk) * G + g) * 2;
+    dst[0] = s_a[0];
+    dst[1] = s_b[0];
   }
 }
 
@@ -205,7 +251,12 @@ cudaError_t launch_groupnorm(const bf16* x, bf16* y, const float* gamma, const f
   if (nchunks < 1) nchunks = 1;
   dim3 grid(nchunks, B);
   float* stats = workspace + (size_t)B * kGnMaxChunks * G * 2;
-  cudaError_t e = launch_pdl(groupnorm_stats_kernel, grid, dim3(kGnThreads), 0, stream, x, workspace, HW, C, G, nchunks);
+  cudaError_t e;
+  if (deterministic_mode())
+    e = launch_pdl(groupnorm_stats_det_kernel, dim3(nchunks, G, B), dim3(kGnThreads), 0, stream, x, workspace, HW, C, G,
+                   nchunks);
+  else
+    e = launch_pdl(groupnorm_stats_kernel, grid, dim3(kGnThreads), 0, stream, x, workspace, HW, C, G, nchunks);
   if (e != cudaSuccess) return e;
   e = launch_pdl(groupnorm_finalize_kernel, dim3(B), dim3(1024), 0, stream, (const float*)workspace, stats, HW, C, G,
                  nchunks, eps);

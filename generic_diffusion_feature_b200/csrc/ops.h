@@ -172,6 +172,9 @@ struct ResizeSrc {
 // Bilinear (align_corners=False) resize of every map to (OH, OW) + channel concat. out_nhwc: [B, OH*OW, Ctot]
 // (fp16); out_nchw: [B, Ctot, OH, OW] (reference layout). sumsq (optional): [B, OH*OW] fp32 accumulated
 // squared L2 norm per pixel of the NHWC stack.
+// GDF_DETERMINISTIC=1: no floating-point atomics anywhere on the path (GroupNorm statistics by their own kernel with a
+// fixed-order reduction instead of the producing GEMM's epilogue): two runs give bit-identical features.
+bool deterministic_mode();
 cudaError_t launch_resize_concat(const ResizeSrc* srcs_host, int n_src, int B, int OH, int OW, int Ctot,
                                  __half* out_nhwc, __half* out_nchw, float* sumsq, cudaStream_t stream);
 

@@ -546,6 +546,41 @@ def test_two_extractors_share_one_pipe(cuda_dev):
 
 
 @pytest.mark.gpu
+def test_deterministic_mode_is_bit_reproducible(cuda_dev):
+    """GDF_DETERMINISTIC=1: GroupNorm statistics by a fixed-order reduction instead of float atomics in
+    the producing epilogue - two runs of the same extraction give bit-identical maps (the default mode differs at the
+    bf16 noise floor, see test_two_extractors_share_one_pipe). The flag is read once per process: run in a child."""
+    import os
+    import subprocess
+    import sys
+    from common import ROOT
+    code = r'''
+import sys, torch
+sys.path.insert(0, "tests")
+from common import TINY_XL, TINY_VAE, make_inputs
+from generic_diffusion_feature_b200.components import models
+from generic_diffusion_feature_b200.components.feature_extractor import _unet_feature_ids
+from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
+pipe = models.get_diffusion_model("xl", "float16", device="cuda:0", state_dict=sd, unet_cfg=TINY_XL, vae_cfg=TINY_VAE)
+image, ctx, pooled, ev, eq = make_inputs(2, 128, TINY_XL["ctx_dim"], 64)
+ids = _unet_feature_ids(TINY_XL)
+fe = FeatureExtractor({i: True for i in ids}, "xl", "cuda:0", img_size=128, external_model=pipe)
+run = lambda: {k: v.clone() for k, v in fe.extract((ctx, ctx, pooled, pooled), 2, image.cuda(), image_type="tensors",
+                                                   t=50, noise=(ev, eq)).items()}
+a, b, c = run(), run(), run()
+torch.cuda.synchronize()
+diff = [k for k in ids if not (torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]))]
+print("MAPS", len(ids), "DIFFERENT", len(diff), diff[:4])
+'''
+    env = dict(os.environ, GDF_DETERMINISTIC="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MAPS")][-1]
+    assert " DIFFERENT 0 " in line + " ", line
+
+
+@pytest.mark.gpu
 def test_reloading_weights_replaces_every_packed_tensor(cuda_dev):
     """ADVICE r1: gdf_load_weights on a planned handle drops the plan and the packed bf16 / conv / folded caches, so the
     second state dict is the one that runs (the name-keyed cache used to keep the old values)."""
