@@ -277,6 +277,56 @@ __global__ void small_linear_elem_kernel(const float* __restrict__ x, const floa
     y[o] = r;
   }
 }
+// Grouped GEMV: y_i[b, n] = bias_i[n] + sum_k act(x[b, k]) W_i[n, k] for a table of (W_i, bias_i, y_i, N_i) that all read
+// the same x (the time-embedding projections of every resnet of a UNet, resnet.py:354-355: Linear(SiLU(temb))). One
+// launch at the head of the op list instead of one cold fp32 GEMV per resnet inside the dependency chain: one warp per
+// output row of the concatenated problem, the B rows of x staged in shared memory, every weight row read once.
+__global__ void __launch_bounds__(256)
+grouped_small_linear_kernel(const GroupedLinearItem* __restrict__ items, int n_items, const float* __restrict__ x, int B,
+                            int K, int total_rows, int act_in_silu) {
+  extern __shared__ float gsl_x[];   // [B][K]
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    float v = x[i];
+    if (act_in_silu) v = v / (1.f + expf(-v));
+    gsl_x[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  int it = 0;
+  while (it + 1 < n_items && items[it + 1].row0 <= r) ++it;   // <= 64 groups: a linear scan of a table in L1
+  const GroupedLinearItem g = items[it];
+  const int n = r - g.row0;
+  const float* wr = g.W + (long long)n * K;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b0 + j < B) acc[j] = fmaf(w, gsl_x[(b0 + j) * K + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[j];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+      if (lane == 0 && b0 + j < B) g.y[(long long)(b0 + j) * g.N + n] = a + (g.bias ? g.bias[n] : 0.f);
+    }
+  }
+}
+cudaError_t launch_grouped_small_linear(const GroupedLinearItem* items_dev, int n_items, const float* x, int B, int K,
+                                        int total_rows, int act_in_silu, cudaStream_t stream) {
+  const size_t smem = (size_t)B * K * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;   // callers fall back to one launch per projection
+  grouped_small_linear_kernel<<<(unsigned)((total_rows + 7) / 8), 256, smem, stream>>>(items_dev, n_items, x, B, K,
+                                                                                      total_rows, act_in_silu);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
                                 int act_in_silu, int act_out_silu, cudaStream_t stream) {
   if ((long long)N * K * 4 <= (32ll << 20)) {   // L2-resident weights (time / text embedding MLPs): favour parallelism

@@ -140,6 +140,15 @@ cudaError_t launch_pack_conv_weight_f16(const float* w_oihw, __half* out, int O,
 // Sinusoidal timestep embedding (flip_sin_to_cos=True, freq_shift=0): out[n, dim] = [cos | sin].
 cudaError_t launch_timestep_embedding(const float* t, float* out, int n, int dim, cudaStream_t stream);
 // small fp32 GEMV-style linear for the conditioning MLPs: y[B, N] = act(x[B, K]) W[N, K]^T + b
+struct GroupedLinearItem {   // one projection of a grouped GEMV (launch_grouped_small_linear)
+  const float* W;            // [N, K] fp32
+  const float* bias;         // [N] or null
+  float* y;                  // [B, N]
+  int N;
+  int row0;                  // first row of this projection in the concatenated row space
+};
+cudaError_t launch_grouped_small_linear(const GroupedLinearItem* items_dev, int n_items, const float* x, int B, int K,
+                                        int total_rows, int act_in_silu, cudaStream_t stream);
 cudaError_t launch_small_linear(const float* x, const float* W, const float* b, float* y, int B, int K, int N,
                                 int act_in_silu, int act_out_silu, cudaStream_t stream);
 

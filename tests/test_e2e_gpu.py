@@ -14,6 +14,11 @@ pytestmark = pytest.mark.gpu
 
 COS_MIN = 0.999
 MAXREL_MAX = 5e-2
+# Full-size SDXL (real widths: long reductions average the bf16 rounding noise): measured over the 472 maps in rounds 1-2
+# minimum cosine 0.99989, worst max-relative 2.8e-2 -> bounds = measured + margin. The reduced-width test networks keep
+# the looser pair above (their 64 ... 256-channel reductions average less).
+FULL_COS_MIN = 0.9997
+FULL_MAXREL_MAX = 4e-2
 
 
 def _run_case(version, ucfg, batch, img, subset=None):
@@ -493,7 +498,21 @@ def test_full_size_sdxl_1024_parity(cuda_dev):
     O.attach_gatherers(unet, store)
     want, _, _ = O.extract("xl", unet, vae, store, image, ctx, pooled, ev, eq, t=50, img_size=1024)
     rows = compare_maps(got, want)
-    bad = [r for r in rows if r[1] < COS_MIN or r[3] > MAXREL_MAX]
+    # the distribution over the 472 maps goes on record ("report the per-map distribution and tighten to
+    # what is achieved + margin"): gpurun_out/r02_full_parity_sdxl1024_b1.json, copied to profiles/ at the end of a round
+    import json
+    import numpy as np
+    from common import ROOT
+    cosv, relv, mrv = (np.array([r[i] for r in rows]) for i in (1, 2, 3))
+    pct = lambda v: {p: float(np.percentile(v, p)) for p in (0, 1, 10, 50, 90, 99, 100)}
+    rec = {"maps": len(rows), "cosine_percentiles": pct(cosv), "rel_l2_percentiles": pct(relv),
+           "max_relative_percentiles": pct(mrv), "worst_cosine": min(rows, key=lambda r: r[1])[:2],
+           "worst_max_relative": max(rows, key=lambda r: r[3])[::3],
+           "bounds": {"cosine_min": FULL_COS_MIN, "max_relative_max": FULL_MAXREL_MAX}}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "r02_full_parity_sdxl1024_b1.json"), "w"), indent=1)
+    print("full-size parity:", rec)
+    bad = [r for r in rows if r[1] < FULL_COS_MIN or r[3] > FULL_MAXREL_MAX]
     assert not bad, "full-size maps out of tolerance: %s" % bad[:8]
 
 
