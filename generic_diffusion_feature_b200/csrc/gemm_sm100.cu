@@ -639,17 +639,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         // With two halo tiles the slot of block i + 1 is the one block i - 1 used: it is free once the MMA issuer has
         // started block i, which the producer knows when it has been granted the B slot of tap `nstages` of block i
         // (the ring is nstages deep). Asking earlier would park the producer on hempty with the B ring running dry.
-        const int tap_next_halo = p.halo_stages >= 3 ? 0 : (nstages < 8 ? nstages : 8);
-        if (unit0 < total_units) issue_halo(unit0, 0);
-        for (int t = unit0; t < total_units; t += unit_step) {
+        const int tap_next_halo = p.halo_stages >= 3 && !p.halo_dual ? 0 : (nstages < 8 ? nstages : 8);
+        // dual mode: a "block" covers the two tiles t and t + unit_step of this CTA (two halos per channel block, one set
+        // of nine B tiles); the epilogue still sees them as consecutive tiles in consecutive accumulator stages
+        const int t_stride = p.halo_dual ? 2 * unit_step : unit_step;
+        auto issue_block = [&](int t, int cb) {
+          issue_halo(t, cb);
+          if (p.halo_dual && t + unit_step < total_units) issue_halo(t + unit_step, cb);
+        };
+        if (unit0 < total_units) issue_block(unit0, 0);
+        for (int t = unit0; t < total_units; t += t_stride) {
           int mu, n_tile, bz;
           decode_unit(p, t, num_m_units, mu, n_tile, bz);
           const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
           for (int cb = 0; cb < cinb2; ++cb) {
             for (int tap = 0; tap < 9; ++tap) {
               if (tap == tap_next_halo) {
-                if (cb + 1 < cinb2) issue_halo(t, cb + 1);
-                else if (t + unit_step < total_units) issue_halo(t + unit_step, 0);
+                if (cb + 1 < cinb2) issue_block(t, cb + 1);
+                else if (t + t_stride < total_units) issue_block(t + t_stride, 0);
               }
               mbar_wait(&empty_bar[s], ph ^ 1);
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], b_tx_bytes);
@@ -675,6 +682,77 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       int hs = 0;
       uint32_t hph = 0;
       const int last_kb = p.num_k_blocks - 1;
+      if (halo && p.halo_dual) {
+        // two output tiles per B tile: tiles t and t + unit_step of this CTA, accumulators `as` and the next stage
+        for (int t = unit0; t < total_units; t += 2 * unit_step) {
+          const bool two = t + unit_step < total_units;
+          int as2 = as + 1;
+          uint32_t aph2 = aph;
+          if (as2 == acc_stages) { as2 = 0; aph2 ^= 1; }
+          mbar_wait(&tempty_bar[as], aph ^ 1);
+          if (two) mbar_wait(&tempty_bar[as2], aph2 ^ 1);
+          tc_fence_after();
+          const uint32_t acc0 = tmem_base + as * acc_stride, acc1 = tmem_base + as2 * acc_stride;
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            int hs2 = hs + 1;
+            uint32_t hph2 = hph;
+            if (hs2 == p.halo_stages) { hs2 = 0; hph2 ^= 1; }
+            mbar_wait(&hfull_bar[hs], hph);
+            if (two) mbar_wait(&hfull_bar[hs2], hph2);
+            tc_fence_after();
+            const uint32_t h0 = smem_u32(smem + hs * kHaloBytes), h1 = smem_u32(smem + hs2 * kHaloBytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - 3 * ky;
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              const uint32_t toff = (uint32_t)(ky * kHaloLinePx + kx) * 128u;
+              const uint64_t da0 = umma_desc_kmajor_sw128_sbo(h0 + toff, kHaloLinePx * 128u, 0u);
+              const uint64_t da1 = umma_desc_kmajor_sw128_sbo(h1 + toff, kHaloLinePx * 128u, 0u);
+              const uint64_t db = umma_desc_kmajor_sw128(smem_u32(b_ring + s * stage_bytes));
+              const uint32_t accum0 = (cb | tap) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if (CG == 2) umma_f16_ss_pair(acc0, da0 + 2 * k, db + 2 * k, idesc, (accum0 | (uint32_t)k) != 0 ? 1u : 0u);
+                else umma_f16_ss(acc0, da0 + 2 * k, db + 2 * k, idesc, (accum0 | (uint32_t)k) != 0 ? 1u : 0u);
+              }
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  if (CG == 2) umma_f16_ss_pair(acc1, da1 + 2 * k, db + 2 * k, idesc, (accum0 | (uint32_t)k) != 0 ? 1u : 0u);
+                  else umma_f16_ss(acc1, da1 + 2 * k, db + 2 * k, idesc, (accum0 | (uint32_t)k) != 0 ? 1u : 0u);
+                }
+              }
+              const bool last = (cb == p.cin_blocks - 1) && tap == 8;
+              if (CG == 2) {
+                umma_commit_pair(&empty_bar[s], 3);
+                if (tap == 8) {
+                  umma_commit_pair(&hempty_bar[hs], 3);
+                  if (two) umma_commit_pair(&hempty_bar[hs2], 3);
+                }
+                if (last) {
+                  umma_commit_pair(&tfull_bar[as], 3);
+                  if (two) umma_commit_pair(&tfull_bar[as2], 3);
+                }
+              } else {
+                umma_commit(&empty_bar[s]);
+                if (tap == 8) {
+                  umma_commit(&hempty_bar[hs]);
+                  if (two) umma_commit(&hempty_bar[hs2]);
+                }
+                if (last) {
+                  umma_commit(&tfull_bar[as]);
+                  if (two) umma_commit(&tfull_bar[as2]);
+                }
+              }
+              if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+            if (two) { hs = hs2; hph = hph2; }
+            if (++hs == p.halo_stages) { hs = 0; hph ^= 1; }
+          }
+          if (two) { as = as2; aph = aph2; }
+          if (++as == acc_stages) { as = 0; aph ^= 1; }
+        }
+      } else
       for (int t = unit0; t < total_units; t += unit_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();

@@ -52,6 +52,8 @@ struct GemmParams {
   int num_stages;       // operand ring depth: ring bytes / (16 KB + block_n / cta_group * 128 B), <= kMaxStages
   int halo_stages;      // kAConvS1Halo: halo tiles in flight (the B tiles of the taps use num_stages)
   int halo_base_off;    // kAConvS1Halo: 1 = descriptors carry the matrix base offset of their start row (A/B knob)
+  int halo_dual;        // kAConvS1Halo, single n-tile, block_n <= 128: every B (tap) tile feeds the MMAs of TWO output tiles
+                        // of this CTA (two halos, two TMEM accumulators): halves the weight traffic from L2 per tile
   int cta_group;        // 1: one CTA per 128 x block_n tile; 2: CTA pair per 256 x block_n tile (tcgen05 cta_group::2)
   int num_m_tiles, num_n_tiles, num_k_blocks, batch;
   int a_mode;

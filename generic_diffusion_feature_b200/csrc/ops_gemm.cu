@@ -96,6 +96,16 @@ static void finish_stages(GemmParams& p) {
     const int b_stage = (p.block_n / p.cta_group) * kBlockK * 2;
     p.halo_stages = env_int("GDF_HALO_STAGES", 2) == 3 ? 3 : 2;
     if (ring - p.halo_stages * kHaloBytes < 3 * b_stage) p.halo_stages = 2;
+    // Dual-tile mode (one n-tile of <= 128 columns, four accumulator stages): two halos per block -> four halo slots. The
+    // weight tiles of a 128-channel convolution are 2x the bytes of its halos per output tile (9 x 8 KB against 36 KB
+    // per channel block and CTA) and every tile re-reads them from L2; sharing each tap tile between two output tiles
+    // halves that. Needs >= 4 B stages next to the 144 KB of halos: not together with the residual staging (32 KB).
+    p.halo_dual = 0;
+    if (p.num_n_tiles == 1 && p.block_n <= 128 && p.acc_stages == 4 && env_int("GDF_HALO_DUAL", 1) != 0 &&
+        (ring - 4 * kHaloBytes) / b_stage >= 4) {
+      p.halo_dual = 1;
+      p.halo_stages = 4;
+    }
     p.num_stages = (ring - p.halo_stages * kHaloBytes) / b_stage;
   } else {
     p.num_stages = ring / (kStageBytesA + (p.block_n / p.cta_group) * kBlockK * 2);
@@ -157,7 +167,10 @@ static int setup_stores(GemmLaunch* g) {
   // residual: 0.64 -> 0.57 ms, step +1.5 %). Round 1 kept it off for the single-staging-round launches because of
   // sparse wrong values; that was a write-after-read race in the epilogue (see the comment at the buffer reads in
   // gemm_sm100.cu), fixed in round 2. GDF_RES_TMA=0 restores the direct loads (A/B timing).
-  if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0) {
+  // (dual-tile halo convolutions need the 32 KB of residual staging for their B ring: GDF_HALO_DUAL_RES=1 gives them the
+  // dual mode with direct residual loads instead of the single-tile mode with the residual through TMA)
+  const bool dual_wins = p.a_mode == kAConvS1Halo && p.halo_dual && env_int("GDF_HALO_DUAL_RES", 0) != 0;
+  if (p.fast_epi && p.residual && p.batch == 1 && p.act != kActGeglu && env_int("GDF_RES_TMA", 1) != 0 && !dual_wins) {
     // same geometry as the store maps: [32 rows][32 columns] boxes, SWIZZLE_64B, rows / columns out of range read 0
     GDF_TRY(make_store_map(&g->maps.res, p, p.residual, p.n_out, p.ld_res, 0));
     p.res_tma = 1;
