@@ -51,7 +51,7 @@ class Epilogue(ctypes.Structure):
         ("cap", CaptureSeg * 3), ("num_cap", c_int),
         ("ln_sums_dev", c_void_p), ("ln_u_dev", c_void_p), ("ln_eps", c_float), ("row_sums_dev", c_void_p),
         ("gn_sums_dev", c_void_p), ("gn_cpg", c_int), ("gn_groups", c_int), ("gn_rows_per_img", c_int64),
-        ("in_f16", c_int),
+        ("in_f16", c_int), ("res_f16", c_int),
     ]
 
 

@@ -37,6 +37,7 @@ static Epilogue to_epilogue(const gdf_epilogue* ep) {
     e.cap[i].ld = ep->cap[i].ld;
   }
   e.in_f16 = ep->in_f16 != 0;
+  e.res_f16 = ep->res_f16 != 0;
   e.ln_sums = static_cast<const float*>(ep->ln_sums_dev);
   e.ln_u = static_cast<const float*>(ep->ln_u_dev);
   e.ln_eps = ep->ln_eps;

@@ -107,6 +107,9 @@ __device__ __forceinline__ void load_activate32(const GemmParams& p, uint32_t ta
   } else if (p.act == kActSilu) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  } else if (p.act == kActRelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
 }
 
@@ -121,7 +124,25 @@ __device__ __forceinline__ void gate_residual32(const GemmParams& p, float* v, l
   }
   if (p.residual && row_ok) {
     const __nv_bfloat16* r = p.residual + row * p.ld_res + ocol0;
-    if (ocol0 + 32 <= lim && (p.ld_res % 8 == 0)) {
+    if (p.res_f16) {   // fp16 residual (captured feature maps added back by the downstream ResBlock heads)
+      const __half* rh = reinterpret_cast<const __half*>(r);
+      if (ocol0 + 32 <= lim && (p.ld_res % 8 == 0)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rh) + q);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            v[q * 8 + 2 * k] += f.x;
+            v[q * 8 + 2 * k + 1] += f.y;
+          }
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (ocol0 + j < lim) v[j] += __half2float(rh[j]);
+      }
+    } else if (ocol0 + 32 <= lim && (p.ld_res % 8 == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + q);

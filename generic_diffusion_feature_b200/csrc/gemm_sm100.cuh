@@ -37,7 +37,7 @@ constexpr int kHaloLinePx = 16;                               // pixels per halo
 constexpr int kHaloLines = 18;
 constexpr int kHaloBytes = kHaloLines * kHaloLinePx * 128;    // 36 KB per 64-channel block
 constexpr int kMaxHaloStages = 4;
-enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3 };
+enum GemmAct : int { kActNone = 0, kActGeglu = 1, kActGeluTanh = 2, kActSilu = 3, kActRelu = 4 };
 
 struct CaptureSeg {   // fp16 side output of columns [col_begin, col_end) into a feature-arena slot
   __half* ptr;        // slot base; element (row, col) goes to ptr[row * ld + (col - col_begin)]
@@ -78,6 +78,7 @@ struct GemmParams {
   int act;
   const float* col_scale;      // [M / rows_per_batch, Nout] per-sample column gate applied before residual, or null
   const __nv_bfloat16* residual; int ld_res;   // added after activation
+  int res_f16;                 // 1: residual holds fp16 bit patterns (general epilogue only: fast_epi is 0)
   float out_scale;             // multiplies (acc + residual), = 1/output_scale_factor
   __nv_bfloat16* out;  int ld_out;  long long out_batch_stride;
   int out_f16_from;            // columns >= this are written to `out` as fp16 instead of bf16 (V for fp16 P.V)

@@ -26,7 +26,7 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   const bf16* residual = nullptr; int ld_res = 0;
   float out_scale = 1.f;
   bf16* out = nullptr; int ld_out = 0; long long out_batch_stride = 0;
-  int out_f16_from = 0;       // > 0: columns >= this go to `out` as fp16 (multiple of 32)
+  int out_f16_from = 0;       // > 0: columns >= this go to `out` as fp16 (multiple of 32); < 0: all columns fp16
   bf16* out2 = nullptr; int ld_out2 = 0;
   float* out_f32 = nullptr; int ld_out_f32 = 0;
   __half* cap_pre = nullptr; int ld_cap_pre = 0;
@@ -40,6 +40,7 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   int gn_cpg = 0, gn_groups = 0;    //   channels (4 / 8 / 16), gn_rows_per_img rows (pixels) per image
   long long gn_rows_per_img = 0;
   bool in_f16 = false;              // operands are fp16 instead of bf16
+  bool res_f16 = false;             // residual holds fp16 (captured feature map) instead of bf16: general epilogue
   bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };
 

@@ -158,6 +158,7 @@ static int setup_stores(GemmLaunch* g) {
     if (p.col_scale && (!aligned16(p.col_scale) || p.n_out % 4 != 0)) f = false;
     if (p.residual && (!aligned16(p.residual) || p.ld_res % 8 != 0)) f = false;
     if (p.act == kActGeglu && (p.residual || p.col_scale)) f = false;   // lean GEGLU path has neither
+    if (p.res_f16 || p.act == kActRelu) f = false;   // fp16 residual / ReLU exist in the general epilogue only
     if (p.ln_sums && (!aligned16(p.ln_u) || p.alpha != 1.f || p.bias_m)) f = false;
     p.fast_epi = f ? 1 : 0;
   }
@@ -211,7 +212,7 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.out = e.out;
   p.ld_out = e.ld_out;
   p.out_batch_stride = e.out_batch_stride;
-  p.out_f16_from = e.out_f16_from > 0 ? e.out_f16_from : (1 << 30);
+  p.out_f16_from = e.out_f16_from > 0 ? e.out_f16_from : (e.out_f16_from < 0 ? 0 : (1 << 30));
   p.out2 = e.out2;
   p.ld_out2 = e.ld_out2;
   p.out_f32 = e.out_f32;
@@ -230,6 +231,7 @@ static void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.gn_groups = e.gn_groups;
   p.gn_rows_per_img = e.gn_rows_per_img > 0 ? e.gn_rows_per_img : 1;
   p.in_f16 = e.in_f16 ? 1 : 0;   // both builders (the convolution path used to drop it)
+  p.res_f16 = (e.res_f16 && e.residual) ? 1 : 0;
 }
 
 // fused GroupNorm statistics need the lean epilogue on every column and 128-row tiles that stay inside one image

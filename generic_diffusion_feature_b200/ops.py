@@ -6,13 +6,13 @@ import torch
 from . import _lib
 from ._lib import CaptureSeg, Epilogue, ResizeSrc, check, ptr, stream_ptr
 
-ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3
+ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU, ACT_RELU = 0, 1, 2, 3, 4
 
 
 def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_per_batch=0, act=ACT_NONE,
                   col_scale=None, residual=None, out_scale=1.0, alpha=1.0, out2=None, out_f32=None, cap_pre=None,
                   caps=(), n_out=0, out_batch_stride=0, out_f16_from=0, ln_sums=None, ln_u=None, ln_eps=1e-5,
-                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0, in_f16=False):
+                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0, in_f16=False, res_f16=False):
     e = Epilogue()
     e.alpha = alpha
     e.n_out = n_out
@@ -52,6 +52,7 @@ def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_pe
     e.gn_groups = gn_groups
     e.gn_rows_per_img = gn_rows_per_img
     e.in_f16 = int(in_f16)           # A and W are fp16 (feature stacks) instead of bf16
+    e.res_f16 = int(res_f16)         # residual is fp16 (a captured feature map) instead of bf16
     return e
 
 

@@ -239,12 +239,13 @@ typedef struct gdf_epilogue {
   const void* bias_m_dev;         /* fp32 [M] */
   const void* row_batch_bias_dev; /* fp32 [M/rows_per_batch, N] */
   int rows_per_batch;
-  int act;                /* 0 none, 1 GEGLU(erf), 2 GELU-tanh, 3 SiLU */
+  int act;                /* 0 none, 1 GEGLU(erf), 2 GELU-tanh, 3 SiLU, 4 ReLU */
   const void* col_scale_dev;      /* fp32 [M/rows_per_batch, n_out] */
   const void* residual_dev; int ld_res;    /* bf16 */
   float out_scale;        /* 0 is treated as 1 */
   void* out_dev; int ld_out; int64_t out_batch_stride;   /* bf16 */
-  int out_f16_from;       /* > 0: columns >= this are written to out as fp16 (V of a fused QKV projection) */
+  int out_f16_from;       /* > 0: columns >= this are written to out as fp16 (V of a fused QKV projection);
+                           * < 0: every column of out is fp16 (intermediate of an fp16-operand head) */
   void* out2_dev; int ld_out2;                           /* bf16 */
   void* out_f32_dev; int ld_out_f32;
   void* cap_pre_dev; int ld_cap_pre;                     /* fp16, before residual */
@@ -264,6 +265,9 @@ typedef struct gdf_epilogue {
    * fp16 feature stack - the downstream heads of aggregation_network.py:22,97-99 - with weights from
    * gdf_op_pack_conv_weight_f16) */
   int in_f16;
+  /* 1: residual_dev holds fp16 (a captured feature map: the ResBlock heads of
+   * segmentation/models/diffusion_segmentor.py:23-44 add their fp16 input back) instead of bf16 */
+  int res_f16;
 } gdf_epilogue;
 
 /* C[M,N] = A[M,K] W[N,K]^T (+ fused epilogue); batch > 1: A/out strided by *_batch_stride elements,

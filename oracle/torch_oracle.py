@@ -1225,3 +1225,31 @@ def find_nn_source_correspondences(f1, f2, source_points, load_size):
     n = int(math.sqrt(sims.shape[-1]))
     p2 = sims.argmax(dim=-1)
     return torch.stack([p2 // n, p2 % n], dim=-1)[0], sims[0]
+
+
+# ------------------------------------------------------------------------------------------ segmentation head
+def seg_layer_conv_name(layer, model_index=None):
+    """segmentation/models/diffusion_segmentor.py:188-192."""
+    name = layer.replace("-", "_")
+    return name if model_index is None else "%d_%s" % (model_index, name)
+
+
+def seg_resblock(x, sd, prefix, eps=1e-5):
+    """ResBlock.forward, segmentation/models/diffusion_segmentor.py:23-44, inference (eval-mode BatchNorm2d: running
+    statistics): x + BN2(conv2(relu(BN1(conv1(x))))). sd holds the module's own parameter names
+    (`<prefix>.conv1.0.weight`, `<prefix>.conv1.1.running_mean`, ...)."""
+    def conv_bn(h, c):
+        h = F.conv2d(h, sd["%s.%s.0.weight" % (prefix, c)], sd["%s.%s.0.bias" % (prefix, c)], stride=1, padding=1)
+        return F.batch_norm(h, sd["%s.%s.1.running_mean" % (prefix, c)], sd["%s.%s.1.running_var" % (prefix, c)],
+                            sd["%s.%s.1.weight" % (prefix, c)], sd["%s.%s.1.bias" % (prefix, c)], False, 0.0, eps)
+    return x + conv_bn(F.relu(conv_bn(x, "conv1")), "conv2")
+
+
+def seg_extract_feat(features, feature_layers, sd):
+    """DiffusionSegmentor.extract_feat, single-extractor branch, segmentation/models/diffusion_segmentor.py:232-246:
+    per level, a ResBlock per captured map on its fp32 cast, channel concat, one more ResBlock."""
+    outs = []
+    for level, res_level in enumerate(feature_layers):
+        per = [seg_resblock(features[layer[0]].float(), sd, seg_layer_conv_name(layer[0])) for layer in res_level]
+        outs.append(seg_resblock(torch.cat(per, dim=1), sd, seg_layer_conv_name("sum%d" % level)))
+    return outs

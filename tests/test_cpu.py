@@ -9,6 +9,7 @@ import re
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from common import (O, ROOT, TINY_15, TINY_21, TINY_DIT, TINY_FLUX, TINY_VAE, TINY_VAE_FLUX, TINY_XL, build_oracle, build_oracle_dit,
                     build_oracle_flux, make_inputs)
@@ -383,6 +384,31 @@ def test_oracle_correspondence_matches_reference():
     p2, _ = O.find_nn_source_correspondences(gold["f1"], gold["f2"], pts, tuple(gold["load_size"]))
     assert torch.equal(p2, gold["points2"])
     assert np.array_equal(O.points_to_idxs(pts, tuple(gold["load_size"])), gold["idx"].numpy())
+
+
+def test_oracle_segmentor_head_matches_reference():
+    """tests/golden/segmentor_head.pt: outputs of the reference's real ResBlock / MultiRes / DiffusionSegmentor.extract_feat
+    (segmentation/models/diffusion_segmentor.py, eval mode; tools/make_golden.py) vs the oracle restatement, and the
+    BatchNorm fold the CUDA head applies at load time vs the unfolded form."""
+    gold = torch.load(os.path.join(GOLD, "segmentor_head.pt"), weights_only=False)
+    sd = {k: v.float() for k, v in gold["state_dict"].items()}
+    outs = O.seg_extract_feat(gold["features"], gold["feature_layers"], sd)
+    for got, want in zip(outs, gold["outs"]):
+        assert got.shape == want.shape
+        assert (got - want.float()).abs().max().item() <= 2e-3 * want.float().abs().max().item()   # fixture is fp16-rounded
+    x = gold["features"]["up-level1-upsampler-out"].float()
+    y = x
+    for _ in range(gold["multires_n"]):
+        y = O.seg_resblock(y, sd, "up_level1_upsampler_out")
+    assert (y - gold["multires_out"].float()).abs().max().item() <= 2e-3 * y.abs().max().item()
+    # fold: conv(x, w * s) + (b - mean) * s + beta == BN(conv(x, w) + b)
+    p = "up_level1_upsampler_out.conv1"
+    s = sd[p + ".1.weight"] * torch.rsqrt(sd[p + ".1.running_var"] + 1e-5)
+    folded = F.conv2d(x, sd[p + ".0.weight"] * s[:, None, None, None], (sd[p + ".0.bias"] - sd[p + ".1.running_mean"]) * s
+                      + sd[p + ".1.bias"], padding=1)
+    plain = F.batch_norm(F.conv2d(x, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=1), sd[p + ".1.running_mean"],
+                         sd[p + ".1.running_var"], sd[p + ".1.weight"], sd[p + ".1.bias"], False, 0.0, 1e-5)
+    assert torch.allclose(folded, plain, atol=1e-4, rtol=1e-4)
 
 
 def test_oracle_whole_path_digest():

@@ -5,6 +5,7 @@ Tolerances are for bf16 inputs/outputs with fp32 accumulation: relative L2 error
 mantissa, rounding of the output alone is 2^-9 relative) and cosine similarity >= 0.9999.
 """
 import math
+import os
 
 import numpy as np
 
@@ -13,6 +14,7 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _ops():
@@ -593,6 +595,38 @@ def test_aggregation_head_conv_on_fp16_stack(cuda_dev):
     assert got.shape == want32.shape
     assert rel_err(got, want16) < 2e-4
     assert rel_err(got, want32) < 2e-3
+
+
+@pytest.mark.gpu
+def test_segmentor_feature_head_matches_reference(cuda_dev):
+    """DiffusionSegmentor.extract_feat's ResBlocks (segmentation/models/diffusion_segmentor.py:23-53,
+    232-246, eval mode) on fp16 maps through the fp16-operand tcgen05 convolution (ReLU epilogue, fp16 residual, channel
+    slices of the concat buffer) vs the outputs of the reference's REAL module (tests/golden/segmentor_head.pt, fp32
+    cuDNN-free CPU run) and vs the CPU oracle. fp16 operands + fp16 intermediates: tolerance 3e-3 of the map's range."""
+    from common import O
+    from generic_diffusion_feature_b200 import segmentation as S
+    gold = torch.load(os.path.join(GOLD, "segmentor_head.pt"), weights_only=False)
+    sd = {k: v.float() for k, v in gold["state_dict"].items()}
+    feats = {k: v.cuda() for k, v in gold["features"].items()}
+    head = S.SegmentorFeatureHead(gold["feature_layers"], sd)
+    outs = head(feats)
+    torch.cuda.synchronize()
+    o_outs = O.seg_extract_feat(gold["features"], gold["feature_layers"], sd)
+    assert len(outs) == len(gold["outs"])
+    for got, want, o in zip(outs, gold["outs"], o_outs):
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert rel_err(got.cpu(), want.float()) < 3e-3
+        assert rel_err(got.cpu(), o) < 3e-3
+    # MultiRes: ONE ResBlock applied n times (diffusion_segmentor.py:46-53)
+    pre = "up_level1_upsampler_out."
+    mr = S.MultiRes({"m.res.0." + k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, "m", gold["multires_n"])
+    x = feats["up-level1-upsampler-out"].permute(0, 2, 3, 1).contiguous()
+    y = mr(x).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), gold["multires_out"].float()) < 5e-3
+    with pytest.raises(ValueError):
+        S.ResBlock({k.replace(pre, "q."): v[:32, :32] if v.dim() == 4 else v[:32] for k, v in sd.items()
+                    if k.startswith(pre)}, "q")
 
 
 @pytest.mark.gpu

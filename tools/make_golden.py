@@ -525,6 +525,70 @@ def golden_correspondence():
                 "idx": torch.from_numpy(idx)}, os.path.join(OUT, "correspondence.pt"))
 
 
+def golden_segmentor(name="segmentor_head.pt"):
+    """Real ResBlock / DiffusionSegmentor.extract_feat of segmentation/models/diffusion_segmentor.py (single-extractor
+    branch, eval mode) on seeded fp16 maps. The reference initialises every ResBlock parameter to zero (an identity at
+    the start of training), so seeded weights and BatchNorm running statistics stand in for a trained head."""
+    seg = ref_shim.load_reference_segmentor()
+    feature_layers = [[("up-level0-upsampler-out", 64)],
+                      [("up-level1-upsampler-out", 64), ("up-level2-repeat2-res-out", 64)]]
+    sizes = [16, 32]
+    g = torch.Generator().manual_seed(2718)
+    B = 2
+    feats = {}
+    for level, res in enumerate(feature_layers):
+        for lname, c in res:
+            feats[lname] = torch.randn(B, c, sizes[level], sizes[level], generator=g).to(torch.float16)
+
+    class _FE:
+        def extract(self, **kw):
+            assert kw["image_type"] == "tensors" and kw["t"] == 50
+            return feats
+
+    m = object.__new__(seg.DiffusionSegmentor)
+    torch.nn.Module.__init__(m)
+    m.multiple_diffusion = False
+    m.t = 50
+    m.feature_layers = feature_layers
+    m.prompt_embeds = None
+    m.feature_extractor = _FE()
+    for rank, res in enumerate(feature_layers):
+        for lname, c in res:
+            setattr(m, m.layer_conv_name(lname), seg.ResBlock(c))
+        setattr(m, m.layer_conv_name("sum%d" % rank), seg.ResBlock(sum(c for _, c in res)))
+    for n, p in m.named_parameters():
+        with torch.no_grad():
+            if n.endswith(".0.weight"):     # fp16-representable, stored as fp16 (fixture size)
+                p.copy_((torch.randn(p.shape, generator=g) * (0.7 / (9 * p.shape[1]) ** 0.5)).half().float())
+            elif n.endswith(".1.weight"):
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    for n, b in m.named_buffers():
+        if n.endswith("running_mean"):
+            b.copy_(0.1 * torch.randn(b.shape, generator=g))
+        elif n.endswith("running_var"):
+            b.copy_(0.5 + torch.rand(b.shape, generator=g))
+    m.eval()
+    with torch.no_grad():
+        outs = m.extract_feat(torch.zeros(B, 3, 8, 8), is_test=True)
+    sd = {k: v.clone() for k, v in m.state_dict().items() if "num_batches_tracked" not in k}
+    o_outs = O.seg_extract_feat(feats, feature_layers, sd)
+    for a, b in zip(outs, o_outs):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), "oracle segmentor head differs from the reference's"
+    # MultiRes (diffusion_segmentor.py:46-53): one shared ResBlock applied n times
+    mr = seg.MultiRes(64, 3)
+    mr.load_state_dict({"res.%d.%s" % (i, k[len("up_level1_upsampler_out."):]): v for i in range(3)
+                        for k, v in sd.items() if k.startswith("up_level1_upsampler_out.")}, strict=False)
+    mr.eval()
+    with torch.no_grad():
+        mr_out = mr(feats["up-level1-upsampler-out"].float())
+    sd = {k: (v.half() if k.endswith(".0.weight") else v) for k, v in sd.items()}
+    torch.save({"feature_layers": feature_layers, "features": feats, "state_dict": sd,
+                "outs": [o.half() for o in outs], "multires_n": 3, "multires_out": mr_out.half()}, os.path.join(OUT, name))
+    print("%s: %d levels %s, oracle == reference" % (name, len(outs), [tuple(o.shape) for o in outs]))
+
+
 def golden_extract():
     sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)
     unet, vae = build_oracle(TINY_XL, TINY_VAE, sd)
@@ -577,4 +641,5 @@ if __name__ == "__main__":
     golden_store_resize()
     golden_cli()
     golden_correspondence()
+    golden_segmentor()
     golden_extract()

@@ -575,3 +575,46 @@ def load_reference_correspondence_utils():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
+
+
+def load_reference_segmentor():
+    """segmentation/models/diffusion_segmentor.py (ResBlock, MultiRes, DiffusionSegmentor.extract_feat) with stubs for
+    its mmseg / mmengine imports and its relative `.base` import: only the registry decorator, the type aliases and a
+    BaseSegmentor that is a plain nn.Module are needed to execute ResBlock.forward and extract_feat."""
+    import torch.nn as nn
+    saved = {n: sys.modules.get(n) for n in ("diffusion_feature",)}
+    for n in ("mmengine", "mmengine.logging", "mmseg", "mmseg.registry", "mmseg.utils", "ref_segmodels",
+              "ref_segmodels.base"):
+        if n not in sys.modules:
+            m = types.ModuleType(n)
+            m.__path__ = []
+            sys.modules[n] = m
+    sys.modules["mmengine.logging"].print_log = print
+
+    class _Registry:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+
+        def build(self, cfg):
+            raise RuntimeError("stub registry: nothing to build")
+
+    sys.modules["mmseg.registry"].MODELS = _Registry()
+    for n in ("ConfigType", "OptConfigType", "OptMultiConfig", "OptSampleList", "SampleList"):
+        setattr(sys.modules["mmseg.utils"], n, object)
+    sys.modules["mmseg.utils"].add_prefix = lambda d, p: d
+    sys.modules["ref_segmodels.base"].BaseSegmentor = nn.Module
+    stub = types.ModuleType("diffusion_feature")
+    stub.FeatureExtractor = object
+    sys.modules["diffusion_feature"] = stub
+    path = os.path.join(REF, "segmentation", "models", "diffusion_segmentor.py")
+    spec = importlib.util.spec_from_file_location("ref_segmodels.diffusion_segmentor", path)
+    m = importlib.util.module_from_spec(spec)
+    m.__package__ = "ref_segmodels"
+    try:
+        spec.loader.exec_module(m)
+    finally:
+        if saved["diffusion_feature"] is None:
+            del sys.modules["diffusion_feature"]
+        else:
+            sys.modules["diffusion_feature"] = saved["diffusion_feature"]
+    return m
