@@ -52,6 +52,8 @@ class Epilogue(ctypes.Structure):
         ("ln_sums_dev", c_void_p), ("ln_u_dev", c_void_p), ("ln_eps", c_float), ("row_sums_dev", c_void_p),
         ("gn_sums_dev", c_void_p), ("gn_cpg", c_int), ("gn_groups", c_int), ("gn_rows_per_img", c_int64),
         ("in_f16", c_int), ("res_f16", c_int),
+        ("k_split_ws_dev", c_void_p), ("k_split_ws_floats", c_int64), ("k_split_cnt_dev", c_void_p),
+        ("k_split_cnt_len", c_int),
     ]
 
 

@@ -38,6 +38,10 @@ static Epilogue to_epilogue(const gdf_epilogue* ep) {
   }
   e.in_f16 = ep->in_f16 != 0;
   e.res_f16 = ep->res_f16 != 0;
+  e.sk_ws = static_cast<float*>(ep->k_split_ws_dev);
+  e.sk_ws_floats = ep->k_split_ws_floats;
+  e.sk_cnt = static_cast<unsigned int*>(ep->k_split_cnt_dev);
+  e.sk_cnt_len = ep->k_split_cnt_len;
   e.ln_sums = static_cast<const float*>(ep->ln_sums_dev);
   e.ln_u = static_cast<const float*>(ep->ln_u_dev);
   e.ln_eps = ep->ln_eps;

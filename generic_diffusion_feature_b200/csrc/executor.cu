@@ -296,6 +296,10 @@ struct gdf_handle_s {
   std::vector<const float*> ctrl_down;
   const float* ctrl_mid = nullptr;
   int n_skips = 0;                   // skip tensors of the planned UNet (= expected number of down residuals)
+  // K-split tail wave of the linear layers (GemmParams::sk_*): one workspace per pipe, used by one launch at a time (the
+  // op lists run on one stream); the counters are zeroed here once and left zero by every launch
+  float* sk_ws = nullptr;
+  unsigned int* sk_cnt = nullptr;
   std::vector<std::pair<int, int>> skip_shapes;   // (channels, side) per skip, push order
 };
 
@@ -746,10 +750,10 @@ class Builder {
   void push_gemm(GemmLaunch& g, const Caps& caps, int at = -1) {   // at >= 0: replaces the placeholder op at that index
     GemmParams& p = g.p;
     {
-      char lbl[160];
-      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d cg=%d st=%d batch=%d act=%d res=%d caps=%d pre=%d tma=%d tiles=%d",
+      char lbl[192];
+      snprintf(lbl, sizeof(lbl), "gemm mode%d M=%d N=%d K=%d bn=%d cg=%d st=%d batch=%d act=%d res=%d caps=%d pre=%d tma=%d ksplit=%d tiles=%d",
                p.a_mode, p.M, p.N, p.K, p.block_n, p.cta_group, p.num_stages, p.batch, p.act, p.residual ? 1 : 0, caps.n,
-               caps.pre >= 0 ? 1 : 0, p.tma_store, p.batch * p.num_m_tiles * p.num_n_tiles);
+               caps.pre >= 0 ? 1 : 0, p.tma_store, p.sk_pieces > 1 ? p.sk_pieces : 0, p.batch * p.num_m_tiles * p.num_n_tiles);
       ops->tag(kKindGemm, 2.0 * (double)p.M * (double)p.K * (double)(p.act == kActGeglu ? 2 * p.n_out : p.n_out) *
                               (double)p.batch, lbl);
     }
@@ -794,6 +798,23 @@ class Builder {
       ops->tag(kKindOther, 0.0);
     }
   }
+  static constexpr long long kSkWsFloats = 74LL * 2 * 128 * 256;   // pieces <= resident CTA groups (74 pairs / 148 CTAs)
+  static constexpr int kSkCntLen = 74 * 2 * 8;
+  bool sk_workspace() {
+    static const bool on = [] { const char* e = getenv("GDF_STREAM_K"); return !(e && e[0] == '0'); }();
+    if (!on) return false;
+    if (h->sk_ws && h->sk_cnt) return true;
+    if (cudaMalloc(&h->sk_ws, kSkWsFloats * 4) != cudaSuccess || cudaMalloc(&h->sk_cnt, kSkCntLen * 4) != cudaSuccess ||
+        cudaMemset(h->sk_cnt, 0, kSkCntLen * 4) != cudaSuccess) {
+      cudaGetLastError();
+      if (h->sk_ws) cudaFree(h->sk_ws);
+      if (h->sk_cnt) cudaFree(h->sk_cnt);
+      h->sk_ws = nullptr;
+      h->sk_cnt = nullptr;
+      return false;
+    }
+    return true;
+  }
   void linear(const bf16* A, long long M, int K, int lda, const bf16* W, int N, const Epilogue& e0,
               const Caps& caps = Caps(), int batch = 1, long long abs = 0, long long wbs = 0, int ldw = 0,
               int block_n = 0, int at = -1) {
@@ -803,6 +824,12 @@ class Builder {
     if (dry) return;
     Epilogue e = e0;
     apply_caps(e, caps, e.n_out > 0 ? e.n_out : (e.act == kActGeglu ? N / 2 : N));
+    if (batch == 1 && M >= 4096 && sk_workspace()) {   // K-split of the last partial wave (ops_gemm.cu plan_k_split)
+      e.sk_ws = h->sk_ws;
+      e.sk_ws_floats = kSkWsFloats;
+      e.sk_cnt = h->sk_cnt;
+      e.sk_cnt_len = kSkCntLen;
+    }
     GemmLaunch g;
     if (int r = build_linear(&g, A, M, K, lda, W, N, ldw ? ldw : K, e, batch, abs, wbs, block_n)) {
       set_err(r);
@@ -2760,6 +2787,8 @@ static void free_plan(gdf_handle_s* h) {
   h->n_skips = 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->t_dev); fr(h->ctx_bf16); fr(h->add_in); fr(h->latent_nhwc); fr(h->key_bias); fr(h->g_dev);
+  fr(h->sk_ws); fr(h->sk_cnt);
+  h->sk_ws = nullptr; h->sk_cnt = nullptr;
   h->g_dev = nullptr;
   h->t_dev = nullptr; h->ctx_bf16 = nullptr; h->add_in = nullptr; h->latent_nhwc = nullptr; h->key_bias = nullptr;
   h->has_key_bias = false;

@@ -39,6 +39,19 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int t, int num_
     else { bz = q / p.num_n_tiles; n_tile = q - bz * p.num_n_tiles; }
   }
 }
+// K-split tail (GemmParams::sk_*): virtual unit -> (tile, k-block range). Returns the piece index, -1 for a whole tile.
+__device__ __forceinline__ int decode_piece(const GemmParams& p, int& t, int& kb0, int& kb1) {
+  kb0 = 0;
+  kb1 = p.num_k_blocks;
+  if (p.sk_pieces <= 1 || t < p.sk_first) return -1;
+  const int q = t - p.sk_first;
+  const int ti = q / p.sk_pieces;
+  const int piece = q - ti * p.sk_pieces;
+  t = p.sk_first + ti;
+  kb0 = piece * p.sk_kpp;
+  kb1 = min(p.num_k_blocks, kb0 + p.sk_kpp);
+  return piece;
+}
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
   TileCoord c;
   c.m_tile = t % p.num_m_tiles;
@@ -545,7 +558,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
   // work unit = CG vertically adjacent 128-row tiles x one block_n column tile
   const int num_m_units = (p.num_m_tiles + CG - 1) / CG;
-  const int total_units = p.batch * num_m_units * p.num_n_tiles;
+  const int real_units = p.batch * num_m_units * p.num_n_tiles;
+  // K-split tail: the units behind sk_first are pieces of tiles (decode_piece)
+  const int total_units = p.sk_pieces > 1 ? p.sk_first + (real_units - p.sk_first) * p.sk_pieces : real_units;
   const int unit0 = blockIdx.x / CG;
   const int unit_step = gridDim.x / CG;
   const uint32_t stage_tx_bytes = (CG * kBlockM + p.block_n) * kBlockK * 2;   // bytes landing per stage, all CTAs
@@ -568,8 +583,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       int s = 0;
       uint32_t ph = 0;
       const int cinb = p.cin_blocks;
-      for (int t = unit0; !halo && t < total_units; t += unit_step) {
+      for (int tv = unit0; !halo && tv < total_units; tv += unit_step) {
         int mu, n_tile, bz;
+        int t = tv, kb_begin, kb_end;
+        decode_piece(p, t, kb_begin, kb_end);
         decode_unit(p, t, num_m_units, mu, n_tile, bz);
         const int m_tile = mu * CG + (int)cta_rank;
         const int b_row0 = n_tile * p.block_n + (int)cta_rank * b_rows;
@@ -588,7 +605,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         if (p.a_mode == kALinear) {
           const int m0 = m_tile * kBlockM;
           const int bz_a = p.a_batched ? bz : 0;
-          for (int kb = 0, k0 = 0; kb < p.num_k_blocks; ++kb, k0 += kBlockK) {
+          for (int kb = kb_begin, k0 = kb_begin * kBlockK; kb < kb_end; ++kb, k0 += kBlockK) {
             uint8_t* a_dst = begin_stage();
             if (CG == 2) tma_load_3d_pair(a_dst, &maps.a, &full_bar[s], k0, m0, bz_a);
             else tma_load_3d(a_dst, &maps.a, &full_bar[s], k0, m0, bz_a);
@@ -814,7 +831,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (++as == acc_stages) { as = 0; aph ^= 1; }
           continue;
         }
-        for (int kb = 0; kb <= last_kb; ++kb) {
+        int kb_begin = 0, kb_last = last_kb;
+        if (p.sk_pieces > 1) {
+          int tt = t, kb_end;
+          decode_piece(p, tt, kb_begin, kb_end);
+          kb_last = kb_end - 1;
+        }
+        for (int kb = kb_begin; kb <= kb_last; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -823,15 +846,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           if (CG == 2) {
             umma_commit_pair(&empty_bar[s], 3);       // frees this stage in both CTAs
-            if (kb == last_kb) umma_commit_pair(&tfull_bar[as], 3);
+            if (kb == kb_last) umma_commit_pair(&tfull_bar[as], 3);
           } else {
             umma_commit(&empty_bar[s]);
-            if (kb == last_kb) umma_commit(&tfull_bar[as]);
+            if (kb == kb_last) umma_commit(&tfull_bar[as]);
           }
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
@@ -881,12 +904,80 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         gn_run1[hh] = 0.f;
       }
     };
-    for (int t = unit0; t < total_units; t += unit_step) {
+    for (int tv = unit0; tv < total_units; tv += unit_step) {
       TileCoord tc;
+      int t = tv;
       {
-        int mu;
+        int mu, kb_begin, kb_end;
+        const int piece = decode_piece(p, t, kb_begin, kb_end);
         decode_unit(p, t, num_m_units, mu, tc.n_tile, tc.bz);
         tc.m_tile = mu * CG + (int)cta_rank;
+        if (piece >= 0) {
+          // ---- K-split tail piece: publish the raw accumulators, count in; the last warp of this (tile, rank, warp) sums
+          // every piece in index order into TMEM and falls through to the normal epilogue, the others are done
+          mbar_wait(&tfull_bar[as], aph);
+          tc_fence_after();
+          const uint32_t taddr0 = tmem_base + (uint32_t(ew * 32) << 16) + as * acc_stride;
+          const int np = p.sk_pieces;
+          const int ti = t - p.sk_first;
+          const size_t piece_stride = (size_t)CG * kBlockM * p.block_n;
+          float* wsb = p.sk_ws + ((size_t)ti * np * CG + cta_rank) * (size_t)(kBlockM * p.block_n) + r_in_tile;
+          const int half_w = geglu ? p.block_n / 2 : p.block_n;   // GEGLU: value chunk c and its gate chunk half_w + c
+          {
+            float* dst = wsb + (size_t)piece * piece_stride;
+            for (int c = cset * 64; c < half_w; c += ((c & 32) ? 96 : 32)) {
+              for (int g2 = 0; g2 < (geglu ? 2 : 1); ++g2) {
+                const int ac = c + g2 * half_w;
+                uint32_t raw[32];
+                tmem_ld_32x32(taddr0 + ac, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(size_t)(ac + j) * kBlockM] = __uint_as_float(raw[j]);
+              }
+            }
+          }
+          __threadfence();
+          __syncwarp();
+          unsigned int* cnt = p.sk_cnt + ((size_t)ti * CG + cta_rank) * kEpilogueWarps + e;
+          unsigned int old = 0;
+          if (lane == 0) old = atomicAdd(cnt, 1u);
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old != (unsigned int)(np - 1)) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&tempty_bar[as], 0);
+              else mbar_arrive(&tempty_bar[as]);
+            }
+            if (++as == acc_stages) { as = 0; aph ^= 1; }
+            continue;
+          }
+          __threadfence();
+          if (lane == 0) *cnt = 0u;   // ready for the next launch
+          for (int c = cset * 64; c < half_w; c += ((c & 32) ? 96 : 32)) {
+            for (int g2 = 0; g2 < (geglu ? 2 : 1); ++g2) {
+              const int ac = c + g2 * half_w;
+              float acc[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+              for (int j2 = 0; j2 < np; ++j2) {   // index order, this piece's own share straight from TMEM: the sum does
+                if (j2 == piece) {                 // not depend on which piece arrived last
+                  uint32_t raw[32];
+                  tmem_ld_32x32(taddr0 + ac, raw);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(raw[j]);
+                } else {
+                  const float* src = wsb + (size_t)j2 * piece_stride + (size_t)ac * kBlockM;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc[j] += __ldcg(src + (size_t)j * kBlockM);
+                }
+              }
+              tmem_st_32x32(taddr0 + ac, *reinterpret_cast<uint32_t(*)[32]>(acc));
+            }
+          }
+          tmem_st_wait();
+        }
       }
       // ---- row of this thread, origin of this warp's 32-row slice
       long long row;
@@ -1317,6 +1408,11 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   if (simple) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 2>, maps, p);
   if (lean) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false, 1>, maps, p);
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, false>, maps, p);
+}
+
+int gemm_resident_groups(int cta_group) {
+  if (gemm_init_once() != cudaSuccess) return 0;
+  return cta_group == 2 ? g_pair_ctas / 2 : g_num_sms;
 }
 
 int gemm_num_sms() {

@@ -63,6 +63,15 @@ struct GemmParams {
   int in_f16;           // 1: A and B hold fp16 (not bf16) values (feature stacks of the correspondence GEMM)
   int a_batched;        // 1: A has a batch dimension, 0: shared across the batch
   int b_batched;        // 1: B has a batch dimension, 0: shared
+  // ---- K-split tail ("stream-K" for the last partial wave; linear mode, batch 1 only): work units >= sk_first are not
+  // whole tiles but pieces: unit sk_first + i * sk_pieces + j = k-blocks [j * sk_kpp, (j + 1) * sk_kpp) of tile
+  // sk_first + i. Every epilogue warp of a piece publishes its raw fp32 accumulators to sk_ws and counts itself in;
+  // the LAST warp to arrive for a (tile, CTA rank, warp) sums the pieces in index order (deterministic), writes the sum
+  // back to TMEM and runs the normal epilogue; the others just release their accumulator stage. No CTA waits for
+  // another one. sk_pieces <= 1: off.
+  int sk_first, sk_pieces, sk_kpp;
+  float* sk_ws;                // [tail tiles][sk_pieces][cta_group][block_n columns][128 rows] fp32
+  unsigned int* sk_cnt;        // [tail tiles][cta_group][kEpilogueWarps], zero between launches (the last arriver resets)
   // ---- implicit-GEMM geometry (output grid), tile = tb x th x tw pixels = 128 rows
   int B_img, H, W, tw, th, tb, tiles_x, tiles_y, cin_blocks, pad_lo;
   int tw_log2, th_log2;        // tw, th, tb are powers of two (gcd with 128)

@@ -41,10 +41,20 @@ struct Epilogue {           // everything optional; zero-initialise then fill
   long long gn_rows_per_img = 0;
   bool in_f16 = false;              // operands are fp16 instead of bf16
   bool res_f16 = false;             // residual holds fp16 (captured feature map) instead of bf16: general epilogue
+  // K-split of the last partial wave (GemmParams::sk_*): workspace of the caller (one launch at a time may use it: the
+  // executor's op list runs on one stream). Null: whole tiles only. sk_cnt must be zero before the first launch.
+  float* sk_ws = nullptr;
+  long long sk_ws_floats = 0;
+  unsigned int* sk_cnt = nullptr;
+  int sk_cnt_len = 0;
   bool defer_capture_maps = false;  // capture pointers are placeholders: maps are built later (build_capture_maps)
 };
 
-int choose_block_n(int N, bool geglu, int num_m_tiles);
+int choose_block_n(int N, bool geglu, int num_m_tiles, int num_k_blocks = 0, bool k_split = false);
+// K-split plan for a tail of `tail` tiles on `groups` resident CTA groups: pieces per tile (1 = do not split), k-blocks
+// per piece, and the cost of the tail in k-block times (num_k_blocks when not split).
+int plan_k_split(int num_k_blocks, int groups, int tail, int* kpp, float* tail_cost);
+int gemm_resident_groups(int cta_group);   // CTA groups (CTAs or CTA pairs) one launch keeps resident
 
 // C[M,N] = A[M,K] * W[N,K]^T, optionally batched (A: batch x M x K with a_batch_stride elements,
 // W shared when w_batch_stride == 0).

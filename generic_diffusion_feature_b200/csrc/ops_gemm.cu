@@ -26,7 +26,35 @@ static int env_int(const char* name, int dflt) {
 // columns), but 192 units at bn = 224 (3 waves of 224) or 256 units at bn = 160 (4 waves of 160).
 // Cost model: waves x (bn + kTileFixedCols), kTileFixedCols = per-tile fixed cost in column equivalents.
 // GDF_WAVE_POLICY=0 restores the padding-only rule (A/B timing).
-int choose_block_n(int N, bool geglu, int num_m_tiles) {
+// K-split of the tail wave: S pieces per tile cost ceil(nk / S) k-blocks of main loop + the fix-up: every piece writes its
+// 128 x bn fp32 accumulators per CTA (~2 k-block times) and the last one reads the other S - 1 back (~3 k-block times
+// each: one SM pulling 128 KB from L2). Split only when that beats the whole tile by > 15 %. GDF_STREAM_K=0 disables,
+// GDF_SK_MAX_PIECES bounds S (tuning knobs).
+int plan_k_split(int nk, int groups, int tail, int* kpp_out, float* tail_cost) {
+  int best_s = 1, best_kpp = nk;
+  float best = (float)nk * 0.85f;
+  const int smax = env_int("GDF_SK_MAX_PIECES", 4);
+  if (tail > 0 && env_int("GDF_STREAM_K", 1) != 0) {
+    for (int s = 2; s <= smax && s * tail <= groups; ++s) {
+      const int kpp = (nk + s - 1) / s;
+      if (kpp < 4) break;
+      const int se = (nk + kpp - 1) / kpp;   // every piece non-empty
+      if (se < 2) continue;
+      const float cost = (float)kpp + 2.f + 3.f * (float)(se - 1);
+      if (cost < best) {
+        best = cost;
+        best_s = se;
+        best_kpp = kpp;
+      }
+    }
+  }
+  if (best_s == 1) best = (float)nk;
+  if (kpp_out) *kpp_out = best_kpp;
+  if (tail_cost) *tail_cost = tail > 0 ? best : 0.f;
+  return best_s;
+}
+
+int choose_block_n(int N, bool geglu, int num_m_tiles, int num_k_blocks, bool k_split) {
   const int forced = env_int("GDF_BLOCK_N", 0);   // tuning knob
   if (forced > 0 && forced % 16 == 0 && forced <= kMaxBlockN && (!geglu || forced % 64 == 0)) return forced;
   if (geglu) return N >= 256 ? 256 : 128;
@@ -56,8 +84,15 @@ int choose_block_n(int N, bool geglu, int num_m_tiles) {
     for (int bn = 256; bn >= 128; bn -= 32) {   // multiples of 32: whole rounds of the lean epilogue path
       if (pass == 0 && N % bn != 0) continue;
       const long long units = m_units * ((N + bn - 1) / bn);
-      const long long waves = (units + resident - 1) / resident;
-      const long long cost = waves * (bn + kTileFixedCols);
+      long long waves = (units + resident - 1) / resident;
+      long long cost = waves * (bn + kTileFixedCols);
+      if (k_split && num_k_blocks > 0 && units > resident && units % resident != 0) {
+        // the last partial wave costs plan_k_split's tail instead of a whole tile (in 1/1024 of a wave)
+        float tail_cost = 0.f;
+        plan_k_split(num_k_blocks, (int)resident, (int)(units % resident), nullptr, &tail_cost);
+        const long long milli = (units / resident) * 1024 + (long long)(1024.f * tail_cost / (float)num_k_blocks);
+        cost = milli * (bn + kTileFixedCols) / 1024;
+      }
       if (best_cost < 0 || cost * 100 < best_cost * 97) {   // a narrower tile has to win by > 3 %
         best = bn;
         best_cost = cost;
@@ -250,7 +285,9 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   memset(g, 0, sizeof(*g));
   GemmParams& p = g->p;
   const bool geglu = (e.act == kActGeglu);
-  if (block_n <= 0) block_n = choose_block_n(N, geglu, (int)((M + kBlockM - 1) / kBlockM) * batch);
+  const bool sk_ok = e.sk_ws && e.sk_cnt && batch == 1;
+  if (block_n <= 0)
+    block_n = choose_block_n(N, geglu, (int)((M + kBlockM - 1) / kBlockM) * batch, (K + kBlockK - 1) / kBlockK, sk_ok);
   if (block_n % 16 != 0 || block_n > kMaxBlockN || (geglu && block_n % 64 != 0))
     return fail(GDF_ERR_INVALID, "build_linear: bad block_n %d", block_n);
   if (K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
@@ -284,6 +321,24 @@ int build_linear(GemmLaunch* g, const bf16* A, long long M, int K, int lda, cons
   }
   GDF_TRY(setup_stores(g));
   GDF_TRY(check_gn_stats(p, e));
+  if (sk_ok && block_n % 32 == 0) {
+    // K-split of the last partial wave (GemmParams::sk_*)
+    const int groups = gemm_resident_groups(p.cta_group);
+    const int units = ((p.num_m_tiles + p.cta_group - 1) / p.cta_group) * p.num_n_tiles;
+    const int tail = groups > 0 ? units % groups : 0;
+    if (groups > 0 && units > groups && tail != 0) {
+      int kpp = 0;
+      const int s = plan_k_split(p.num_k_blocks, groups, tail, &kpp, nullptr);
+      const long long need = (long long)tail * s * p.cta_group * kBlockM * block_n;
+      if (s > 1 && need <= e.sk_ws_floats && tail * p.cta_group * kEpilogueWarps <= e.sk_cnt_len) {
+        p.sk_first = units - tail;
+        p.sk_pieces = s;
+        p.sk_kpp = kpp;
+        p.sk_ws = e.sk_ws;
+        p.sk_cnt = e.sk_cnt;
+      }
+    }
+  }
   return e.defer_capture_maps ? GDF_OK : build_capture_maps(g);
 }
 

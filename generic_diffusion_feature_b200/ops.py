@@ -12,7 +12,8 @@ ACT_NONE, ACT_GEGLU, ACT_GELU_TANH, ACT_SILU, ACT_RELU = 0, 1, 2, 3, 4
 def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_per_batch=0, act=ACT_NONE,
                   col_scale=None, residual=None, out_scale=1.0, alpha=1.0, out2=None, out_f32=None, cap_pre=None,
                   caps=(), n_out=0, out_batch_stride=0, out_f16_from=0, ln_sums=None, ln_u=None, ln_eps=1e-5,
-                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0, in_f16=False, res_f16=False):
+                  row_sums=None, gn_sums=None, gn_cpg=0, gn_groups=0, gn_rows_per_img=0, in_f16=False, res_f16=False,
+                  k_split=None):
     e = Epilogue()
     e.alpha = alpha
     e.n_out = n_out
@@ -53,7 +54,17 @@ def make_epilogue(out=None, bias=None, bias_m=None, row_batch_bias=None, rows_pe
     e.gn_rows_per_img = gn_rows_per_img
     e.in_f16 = int(in_f16)           # A and W are fp16 (feature stacks) instead of bf16
     e.res_f16 = int(res_f16)         # residual is fp16 (a captured feature map) instead of bf16
+    if k_split is not None:          # (fp32 workspace, zeroed int32 counters) from k_split_workspace()
+        ws, cnt = k_split
+        e.k_split_ws_dev, e.k_split_ws_floats = ptr(ws), ws.numel()
+        e.k_split_cnt_dev, e.k_split_cnt_len = ptr(cnt), cnt.numel()
     return e
+
+
+def k_split_workspace(device="cuda"):
+    """Workspace of the K-split tail wave (gdf_epilogue.k_split_*): always-sufficient sizes."""
+    return (torch.empty(74 * 2 * 128 * 256, dtype=torch.float32, device=device),
+            torch.zeros(74 * 2 * 8, dtype=torch.int32, device=device))
 
 
 def linear(a, w, ep, batch=1, a_batch_stride=0, w_batch_stride=0, block_n=0, M=None):

@@ -268,6 +268,13 @@ typedef struct gdf_epilogue {
   /* 1: residual_dev holds fp16 (a captured feature map: the ResBlock heads of
    * segmentation/models/diffusion_segmentor.py:23-44 add their fp16 input back) instead of bf16 */
   int res_f16;
+  /* Optional K-split of the last partial wave of gdf_op_linear (batch 1): when the tiles do not fill a whole number of
+   * waves of the resident CTA groups, the tiles of the last wave are split along K into pieces that run side by side;
+   * partial fp32 accumulators go through k_split_ws_dev and are summed in a fixed order (deterministic). One launch at
+   * a time may use a workspace. k_split_cnt_dev must be zero before the first launch (launches leave it zero).
+   * Sizes: 74 x 2 x 128 x 256 floats and 74 x 2 x 8 counters are always enough. NULL: whole tiles only. */
+  void* k_split_ws_dev; int64_t k_split_ws_floats;
+  void* k_split_cnt_dev; int k_split_cnt_len;
 } gdf_epilogue;
 
 /* C[M,N] = A[M,K] W[N,K]^T (+ fused epilogue); batch > 1: A/out strided by *_batch_stride elements,

@@ -162,6 +162,67 @@ def test_linear_geglu(cuda_dev):
     check_close(cap, want, what="geglu capture")
 
 
+@pytest.mark.parametrize("M,N,K,res,bn", [(8192, 1280, 1280, True, 0), (8192, 1280, 5120, True, 0), (8192, 3840, 1280, False, 0),
+                                          (8192, 1280, 1280, False, 256), (9000, 1184, 1288, True, 0)])
+def test_linear_k_split_tail(cuda_dev, M, N, K, res, bn):
+    """K-split of the last partial wave (GemmParams::sk_*, ops_gemm.cu plan_k_split): the tiles that do not fill a
+    whole wave of the 74 resident CTA pairs are split along K into pieces that run side by side; partial fp32
+    accumulators meet in the workspace and the last piece's warps sum them in index order. Same product as the unsplit
+    launch up to fp32 summation order (bf16 outputs: equal except where a rounding boundary is crossed), bit-identical
+    run to run, counters left at zero."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(77)
+    a = _rand_bf16(g, M, K)
+    w = _rand_bf16(g, N, K, scale=K ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    r = _rand_bf16(g, M, N) if res else None
+    ws = ops.k_split_workspace()
+    outs = []
+    for ks in (None, ws, ws):
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+        cap = torch.zeros(M, N, dtype=torch.float16, device="cuda")
+        ops.linear(a, w, ops.make_epilogue(out=out, bias=bias, residual=r, caps=[(cap, 0, N)], k_split=ks), block_n=bn)
+        torch.cuda.synchronize()
+        outs.append((out, cap))
+    want = a.float() @ w.float().T + bias + (r.float() if res else 0)
+    for out, cap in outs:
+        check_close(out, want, what="k-split linear %dx%dx%d" % (M, N, K))
+        check_close(cap, want, what="k-split capture")
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])      # deterministic
+    assert int(ws[1].abs().sum().item()) == 0                                                # counters self-clean
+    diff = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
+    assert diff <= 2 ** -6 * want.abs().max().item()          # one bf16 ulp at the top of the range
+
+
+def test_linear_k_split_geglu(cuda_dev):
+    """K-split with the GEGLU epilogue: value and gate halves of a tile are summed by the warp that consumes them."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(78)
+    M, C = 8192, 1280
+    inner = 1280 + 256        # 12 n-tiles of 256 accumulator columns x 32 row units = 384 tiles: 5 waves + 14
+    a = _rand_bf16(g, M, C)
+    w = _rand_bf16(g, 2 * inner, C, scale=C ** -0.5)
+    bias = torch.randn(2 * inner, generator=g, device="cuda") * 0.1
+    half = 128
+    idx = []
+    for t in range(inner // half):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device="cuda")
+    ws = ops.k_split_workspace()
+    res = []
+    for ks in (None, ws):
+        out = torch.zeros(M, inner, dtype=torch.bfloat16, device="cuda")
+        ep = ops.make_epilogue(out=out, bias=bias[idx].contiguous(), act=ops.ACT_GEGLU, k_split=ks)
+        ops.linear(a, w[idx].contiguous(), ep, block_n=256)
+        torch.cuda.synchronize()
+        res.append(out)
+    proj = a.float() @ w.float().T + bias
+    want = proj[:, :inner] * F.gelu(proj[:, inner:])
+    check_close(res[0], want, what="geglu unsplit")
+    check_close(res[1], want, what="geglu k-split")
+    assert int(ws[1].abs().sum().item()) == 0
+
+
 def test_linear_batched_and_rowbias(cuda_dev):
     """QK^T-style batched product with alpha, and a transposed product with a row (M) bias."""
     ops = _ops()
@@ -292,8 +353,11 @@ def test_groupnorm(cuda_dev, B, HW, C, silu):
     check_close(y, want.permute(0, 2, 1), what="groupnorm C%d" % C)
 
 
-@pytest.mark.parametrize("M,C,mod", [(1000, 640, False), (333, 1280, False), (512, 1152, True), (64, 320, False)])
+@pytest.mark.parametrize("M,C,mod", [(1000, 640, False), (333, 1280, False), (512, 1152, True), (64, 320, False),
+                                     (20011, 1280, False), (9002, 1152, True), (70001, 320, False), (300, 3072, True)])
 def test_layernorm(cuda_dev, M, C, mod):
+    """The last-but-one three exceed the warp count of the persistent kernel (148 x 16): every warp walks several rows with
+    the next row prefetched; 3072 columns stay on the single-wave kernel."""
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(7)
     x = (torch.randn(M, C, generator=g, device="cuda") * 3 + 1).to(torch.bfloat16)
