@@ -22,7 +22,7 @@ GDF_MAX_LEVELS = 4
 EXPORTS = [
     "gdf_last_error", "gdf_abi_version",
     "gdf_create", "gdf_create_dit", "gdf_denoise_capture_dit", "gdf_create_flux", "gdf_denoise_capture_flux", "gdf_op_attention_bias", "gdf_destroy", "gdf_load_weights", "gdf_finalize_weights", "gdf_plan",
-    "gdf_encode_noise", "gdf_encode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
+    "gdf_encode_noise", "gdf_encode_latents", "gdf_plan_decoder", "gdf_decode_latents", "gdf_denoise_capture", "gdf_set_ctx_len", "gdf_num_launches", "gdf_workspace_bytes",
     "gdf_plan_generation", "gdf_control_residual_shapes", "gdf_set_control_residuals",
     "gdf_profile", "gdf_profile_read", "gdf_profile_dump",
     "gdf_op_linear", "gdf_op_conv3x3", "gdf_op_pack_conv_weight", "gdf_op_pack_conv_weight_f16", "gdf_op_conv_in", "gdf_op_groupnorm_workspace_floats",
@@ -160,6 +160,8 @@ def load():
                                  ctypes.POINTER(c_int64)]
         lib.gdf_encode_noise.argtypes = [P, P, P, P, c_float, c_float, c_float, P, P]
         lib.gdf_encode_latents.argtypes = [P, P, P, c_float, c_float, c_float, P, P]
+        lib.gdf_plan_decoder.argtypes = [P]
+        lib.gdf_decode_latents.argtypes = [P, P, c_float, P, c_float, P, P]
         lib.gdf_denoise_capture.argtypes = [P, c_float, P, c_int, P, P, P, c_int64, P, P]
         lib.gdf_control_residual_shapes.argtypes = [P, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int]
         lib.gdf_set_control_residuals.argtypes = [P, ctypes.POINTER(P), c_int, P]

@@ -295,7 +295,7 @@ def selected_ids(feature_store, pipe):
     for k in ids:
         if "map" in k:
             continue          # per-layer attention probabilities (slow materialising path, like the reference's)
-        if k in ("vae-out", "attn"):
-            raise NotImplementedError("feature id '%s': vae-out (scheduler.step + VAE decoder) is not built on the B200 "
-                                      "path; `attn` comes from FeatureExtractor(attention=[...])" % k)
-    return ids
+        if k == "attn":
+            raise NotImplementedError("feature id 'attn' comes from FeatureExtractor(attention=[...])")
+    # `vae-out` is not a capture site: FeatureExtractor.extract decodes it after the forward (diffusion_feature.py:477-485)
+    return [k for k in ids if k != "vae-out"]

@@ -311,6 +311,51 @@ def vae_param_specs(cfg):
     return out
 
 
+def vae_decoder_param_specs(cfg):
+    """(name, shape) of the VAE-DECODER parameters ('decoder.*', 'post_quant_conv.*'), diffusers naming [autoencoders/vae.py
+    Decoder + AutoencoderKL.post_quant_conv, un-vendored]. Optional: only the `vae-out` path (diffusion_feature.py:477-485)
+    reads them; a pipe without them raises when 'vae-out' is requested."""
+    bo = list(reversed(cfg["block_out"]))
+    out = []
+
+    def conv(n, o, i, k):
+        out.append((n + ".weight", (o, i, k, k)))
+        out.append((n + ".bias", (o,)))
+
+    def norm(n, c):
+        out.append((n + ".weight", (c,)))
+        out.append((n + ".bias", (c,)))
+
+    def resnet(n, cin, cout):
+        norm(n + ".norm1", cin)
+        conv(n + ".conv1", cout, cin, 3)
+        norm(n + ".norm2", cout)
+        conv(n + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(n + ".conv_shortcut", cout, cin, 1)
+
+    if cfg.get("quant_conv", True):
+        conv("post_quant_conv", cfg["latent"], cfg["latent"], 1)
+    ch = bo[0]
+    conv("decoder.conv_in", ch, cfg["latent"], 3)
+    resnet("decoder.mid_block.resnets.0", ch, ch)
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", ch)
+    for p in ("to_q", "to_k", "to_v", "to_out.0"):
+        out.append((a + "." + p + ".weight", (ch, ch)))
+        out.append((a + "." + p + ".bias", (ch,)))
+    resnet("decoder.mid_block.resnets.1", ch, ch)
+    for i, co in enumerate(bo):
+        for j in range(cfg["layers"] + 1):
+            resnet("decoder.up_blocks.%d.resnets.%d" % (i, j), ch if j == 0 else co, co)
+        ch = co
+        if i != len(bo) - 1:
+            conv("decoder.up_blocks.%d.upsamplers.0.conv" % i, ch, ch, 3)
+    norm("decoder.conv_norm_out", ch)
+    conv("decoder.conv_out", 3, ch, 3)
+    return out
+
+
 _RESIDUAL_OUT = ("conv2.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight")
 
 
@@ -335,10 +380,15 @@ def init_param(name, shape, device="cpu"):
     return r * (gain / fan_in ** 0.5)
 
 
-def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None, dit_cfg=None, flux_cfg=None):
-    """name -> fp32 tensor for 'unet.*' (or 'transformer.*') and 'vae.*' (random init; no checkpoints offline)."""
+def synthetic_state_dict(version, device="cpu", unet_cfg=None, vae_cfg=None, dit_cfg=None, flux_cfg=None,
+                         with_decoder=False):
+    """name -> fp32 tensor for 'unet.*' (or 'transformer.*') and 'vae.*' (random init; no checkpoints offline).
+    with_decoder: also the VAE decoder ('vae.decoder.*', 'vae.post_quant_conv.*') that only `vae-out` needs."""
     vcfg = vae_cfg or VAE_CONFIGS[version]
     sd = {}
+    if with_decoder:
+        for n, s_ in vae_decoder_param_specs(vcfg):
+            sd["vae." + n] = init_param("vae." + n, s_, device)
     fcfg = flux_cfg or (FLUX_CONFIGS.get(version) if (unet_cfg is None and dit_cfg is None) else None)
     if fcfg is not None:
         for n, s in flux_param_specs(fcfg):
@@ -437,6 +487,11 @@ def expected_shapes(unet_cfg=None, vae_cfg=None, dit_cfg=None, flux_cfg=None):
     return out
 
 
+def optional_shapes(vae_cfg):
+    """name -> shape of the parameters a checkpoint MAY bring: the VAE decoder of the `vae-out` path."""
+    return {"vae." + n: tuple(s) for n, s in vae_decoder_param_specs(vae_cfg)} if vae_cfg is not None else {}
+
+
 # AutoencoderKL checkpoints written before diffusers 0.18 name the mid-block attention projections query / key /
 # value / proj_attn ([diffusers modeling_utils._convert_deprecated_attention_blocks]); some store them as 1x1 convs
 _VAE_ATTN_RENAMES = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
@@ -460,12 +515,12 @@ def _read_safetensors_dir(folder):
     return out
 
 
-def load_diffusers_dir(model_dir, version):
+def load_diffusers_dir(model_dir, version, with_decoder=False):
     """Read a diffusers-layout checkpoint directory (the layout `from_pretrained(...).save_pretrained(dir)` writes and
     the hub snapshots models.py:18-172 downloads): <dir>/unet/*.safetensors (or <dir>/transformer/ for the DiT / Flux
     families) and <dir>/vae/*.safetensors. Returns the name -> tensor dict `B200Pipe.load_state_dict` takes: parameter
-    names exactly as diffusers writes them, prefixed 'unet.' / 'transformer.' / 'vae.' (decoder tensors are dropped:
-    the extraction path only encodes)."""
+    names exactly as diffusers writes them, prefixed 'unet.' / 'transformer.' / 'vae.' (decoder tensors are dropped
+    unless with_decoder: only `vae-out` decodes)."""
     import os
     if not os.path.isdir(model_dir):
         raise FileNotFoundError("model directory %s does not exist" % model_dir)
@@ -475,7 +530,8 @@ def load_diffusers_dir(model_dir, version):
     for k, v in _read_safetensors_dir(os.path.join(model_dir, sub)).items():
         sd[sub + "." + k] = v
     for k, v in _read_safetensors_dir(os.path.join(model_dir, "vae")).items():
-        if not (k.startswith("encoder.") or k.startswith("quant_conv.")):
+        if not (k.startswith("encoder.") or k.startswith("quant_conv.") or
+                (with_decoder and (k.startswith("decoder.") or k.startswith("post_quant_conv.")))):
             continue
         for a, b in _VAE_ATTN_RENAMES.items():
             k = k.replace(a, b)
@@ -527,12 +583,21 @@ class B200Pipe:
             ua = _unet_arch(unet_cfg)
             check(self.lib.gdf_create(ctypes.byref(ua), ctypes.byref(va), self.dev_index, ctypes.byref(self.handle)))
         self._finalized = False
+        self.has_decoder = False          # set by load_state_dict when the checkpoint brings 'vae.decoder.*'
 
     def load_state_dict(self, sd, chunk=256):
         """sd: name -> tensor ('unet.*', 'vae.*'), any float dtype / device; uploaded as fp32. Every tensor the
         architecture reads is checked against its expected shape first (a checkpoint / config mismatch raises here
         instead of reaching the device); names the architecture does not know (decoder, EMA copies, ...) are skipped."""
         want = expected_shapes(self.unet_cfg, self.vae_cfg, self.dit_cfg, self.flux_cfg)
+        opt = optional_shapes(self.vae_cfg)
+        if any(n in sd for n in opt):        # a decoder comes as a whole or not at all
+            missing = [n for n in opt if n not in sd]
+            if missing:
+                raise _lib.GdfError("gdf error -5: the checkpoint holds part of the VAE decoder only; missing %s"
+                                    % ", ".join(missing[:6]))
+            want = dict(want, **opt)
+            self.has_decoder = True
         bad = ["%s: checkpoint %s, architecture %s" % (n, tuple(sd[n].shape), want[n])
                for n in want if n in sd and tuple(sd[n].shape) != tuple(want[n])
                and not (n.endswith("pos_embed.pos_embed"))]      # position table: validated against img_size by gdf_plan

@@ -40,6 +40,11 @@ struct RunCtx {
   float qa = 1.f, qb = 0.f, qs = 1.f;
   float* latents_out = nullptr;
   float* noise_pred_out = nullptr;
+  // gdf_decode_latents (vae-out): z = dec_c_latent * dec_latents + dec_c_model * dec_model_out, image out fp32 NHWC
+  const float* dec_latents = nullptr;
+  const float* dec_model_out = nullptr;
+  float dec_c_latent = 1.f, dec_c_model = 0.f;
+  float* dec_image_out = nullptr;
 };
 typedef std::function<int(const RunCtx&)> Op;
 
@@ -273,6 +278,7 @@ struct gdf_handle_s {
   bool planned = false;
   int B = 0, img = 0, L = 0, ctx_len = 77;
   OpList vae_ops, unet_ops;
+  OpList dec_ops;                    // VAE decoder of the `vae-out` path (gdf_plan_decoder), empty unless requested
   bool profile = false;
   float prof_ms[kNumKinds] = {0, 0, 0, 0, 0};
   double prof_flops[kNumKinds] = {0, 0, 0, 0, 0};
@@ -801,7 +807,8 @@ class Builder {
   static constexpr long long kSkWsFloats = 74LL * 2 * 128 * 256;   // pieces <= resident CTA groups (74 pairs / 148 CTAs)
   static constexpr int kSkCntLen = 74 * 2 * 8;
   bool sk_workspace() {
-    static const bool on = [] { const char* e = getenv("GDF_STREAM_K"); return !(e && e[0] == '0'); }();
+    // off by default: measured slower than whole tiles on every SDXL shape (ops_gemm.cu plan_k_split)
+    static const bool on = [] { const char* e = getenv("GDF_STREAM_K"); return e && e[0] == '1'; }();
     if (!on) return false;
     if (h->sk_ws && h->sk_cnt) return true;
     if (cudaMalloc(&h->sk_ws, kSkWsFloats * 4) != cudaSuccess || cudaMalloc(&h->sk_cnt, kSkCntLen * 4) != cudaSuccess ||
@@ -2515,6 +2522,255 @@ static int build_flux(Builder& b) {
 }
 
 // ----------------------------------------------------------------------------------------- VAE encoder
+// UNetMidBlock2D of the VAE (encoder and decoder): resnet, single-head attention over all pixels (d = ch), resnet.
+// mp = "vae.encoder.mid_block" / "vae.decoder.mid_block". cur / cur_sums are replaced by the block's output.
+static void emit_vae_mid_block(Builder& b, const std::string& mp, bf16*& cur, float*& cur_sums, int B, int hw, int ch, int G,
+                               float eps) {
+  const long long M = (long long)B * hw * hw;
+  const int N = hw * hw;
+    bf16* r0 = b.buf(M, ch);
+    Dest d;
+    d.out = r0;
+    d.ld = ch;
+    d.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+    emit_resnet(b, mp + ".resnets.0", "", cur, B, hw, hw, ch, ch, nullptr, 0, G, eps, d, cur_sums);
+    b.rel(cur);
+    const std::string ap = mp + ".attentions.0";
+    bf16* hn = b.buf(M, ch);
+    if (d.gn_sums) b.groupnorm_from_sums(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false, d.gn_sums);
+    else b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
+    // Q | K fused projection
+    const bf16* wqk = b.rows_bf16(ap + "#qk", {ap + ".to_q.weight", ap + ".to_k.weight"}, nullptr);
+    // The concatenated q | k bias is a CONSTANT of the plan: it lives in weight storage (f32_cat), not in the activation
+    // pool. Round 1 filled a pool buffer at plan time and released it after the block: the pool handed it to a later
+    // layer, so from the second forward on (the first one still saw the plan-time contents) the VAE's mid-block
+    // attention added whatever activations that layer had left there instead of the bias. Found in round 2 through the
+    // bit-reproducibility probe (tools/probe_determinism_vae2.py: the latents changed for good after the first UNet
+    // forward); the error was small enough (logit shifts of one 512-wide head) to pass the cosine / max-relative bounds.
+    const float* bqk = b.f32_cat(ap + "#qk_bias", {ap + ".to_q.bias", ap + ".to_k.bias"});
+    bf16* qk = b.buf(M, 2 * ch);
+    {
+      Epilogue e;
+      e.bias = bqk;
+      e.out = qk;
+      e.ld_out = 2 * ch;
+      b.linear(hn, M, ch, ch, wqk, 2 * ch, e);
+    }
+    // V^T[b] = Wv hn[b]^T + bv[:, None]  -> [B, ch, N]
+    bf16* vt = b.buf((long long)B * ch, N);
+    {
+      Epilogue e;
+      e.bias_m = b.f32(ap + ".to_v.bias");
+      e.out = vt;
+      e.ld_out = N;
+      e.out_batch_stride = (long long)ch * N;
+      b.linear(b.lin(ap + ".to_v.weight"), ch, ch, ch, hn, N, e, Caps(), B, 0, (long long)N * ch, ch);
+    }
+    b.rel(hn);
+    // S[b] = Q[b] K[b]^T / sqrt(ch)
+    bf16* S = b.buf((long long)B * N, N);
+    {
+      Epilogue e;
+      e.alpha = 1.f / sqrtf((float)ch);
+      e.out = S;
+      e.ld_out = N;
+      e.out_batch_stride = (long long)N * N;
+      b.linear(qk, N, ch, 2 * ch, qk + ch, N, e, Caps(), B, (long long)N * 2 * ch, (long long)N * 2 * ch,
+               2 * ch);
+    }
+    b.rel(qk);
+    if (!b.dry) {
+      const long long rows = (long long)B * N;
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        OP_CUDA(launch_softmax_rows(S, rows, N, N, rc.stream));
+        return 0;
+      });
+    }
+    // O[b] = P[b] V[b]
+    bf16* o = b.buf(M, ch);
+    {
+      Epilogue e;
+      e.out = o;
+      e.ld_out = ch;
+      e.out_batch_stride = (long long)N * ch;
+      b.linear(S, N, N, N, vt, ch, e, Caps(), B, (long long)N * N, (long long)ch * N, N);
+    }
+    b.rel(S);
+    b.rel(vt);
+    bf16* ao = b.buf(M, ch);
+    {
+      Epilogue e;
+      e.bias = b.f32(ap + ".to_out.0.bias");
+      e.residual = r0;
+      e.ld_res = ch;
+      e.out = ao;
+      e.ld_out = ch;
+      cur_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+      Builder::want_gn_stats(e, cur_sums, ch, G, (long long)N);
+      b.linear(o, M, ch, ch, b.lin(ap + ".to_out.0.weight"), ch, e);
+    }
+    b.rel(o);
+    b.rel(r0);
+    bf16* r1 = b.buf(M, ch);
+    Dest d1;
+    d1.out = r1;
+    d1.ld = ch;
+    d1.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
+    emit_resnet(b, mp + ".resnets.1", "", ao, B, hw, hw, ch, ch, nullptr, 0, G, eps, d1, cur_sums);
+    b.rel(ao);
+    cur = r1;
+    cur_sums = d1.gn_sums;
+}
+
+// ------------------------------------------------------------------------------------------ VAE decoder (vae-out)
+// z = c_latent * latents + c_model * model_out (scheduler.step + the 1 / scaling_factor of diffusion_feature.py:478-483,
+// both linear in the two tensors: schedulers.step_coeffs), then AutoencoderKL.post_quant_conv (1x1, fp32) -> bf16 NHWC.
+__global__ void decode_prep_kernel(const float* __restrict__ latents, const float* __restrict__ model_out, float c_latent,
+                                   float c_model, const float* __restrict__ pq_w, const float* __restrict__ pq_b,
+                                   bf16* __restrict__ z, int B, int HW, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // pixel
+  if (i >= (long long)B * HW) return;
+  const long long bi = i / HW, px = i - bi * HW;
+  float v[16];
+  for (int c = 0; c < C; ++c) {
+    const long long src = (bi * C + c) * HW + px;
+    v[c] = c_latent * latents[src] + (model_out ? c_model * model_out[src] : 0.f);
+  }
+  for (int o = 0; o < C; ++o) {
+    float acc = v[o];
+    if (pq_w) {
+      acc = pq_b[o];
+      for (int c = 0; c < C; ++c) acc = fmaf(pq_w[o * C + c], v[c], acc);
+    }
+    z[i * C + o] = __float2bfloat16(acc);
+  }
+}
+
+// [diffusers autoencoders/vae.Decoder, un-vendored]: conv_in, mid block, up blocks over reversed(block_out_channels)
+// with layers_per_block + 1 resnets and nearest-x2 + conv upsamplers, GroupNorm + SiLU + conv_out -> fp32 NHWC image.
+static int build_vae_decoder(Builder& b) {
+  gdf_handle_s* h = b.h;
+  const gdf_vae_arch& a = h->va;
+  const int B = h->B, G = a.norm_num_groups, lat = a.latent_channels, nl = a.num_levels;
+  const float eps = a.norm_eps;
+  const std::string V = "vae.decoder.";
+  if (9 * lat > 64 || lat > 16)
+    return fail(GDF_ERR_UNSUPPORTED, "VAE decoder: %d latent channels (conv_in runs as a K = 64 im2col GEMM: <= 7)", lat);
+  b.ops = &h->dec_ops;
+  b.ops->scope = "vae-decoder";
+  int hw = h->L;
+  int ch = a.block_out_channels[nl - 1];
+  b.gn_begin(B, G, 64);
+  const bool has_pq = h->raw.count("vae.post_quant_conv.weight") != 0;
+  const float* pq_w = has_pq ? b.f32("vae.post_quant_conv.weight") : nullptr;
+  const float* pq_b = has_pq ? b.f32("vae.post_quant_conv.bias") : nullptr;
+  bf16* z = b.buf((long long)B * hw * hw, lat);
+  bf16* col = b.buf((long long)B * hw * hw, 64);
+  if (!b.dry) {
+    const int HW = hw * hw, S = hw;
+    b.ops->push_back([=](const RunCtx& rc) -> int {
+      const long long n = (long long)B * HW;
+      decode_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, rc.stream>>>(rc.dec_latents, rc.dec_model_out, rc.dec_c_latent,
+                                                                          rc.dec_c_model, pq_w, pq_b, z, B, HW, lat);
+      OP_CUDA(cudaGetLastError());
+      OP_CUDA(launch_im2col_small(nullptr, z, col, B, S, S, lat, rc.stream));
+      return 0;
+    });
+  }
+  float* cur_sums = b.gn_fusable(ch, G, (long long)hw * hw) ? b.gn_slot(B, G) : nullptr;
+  bf16* cur = b.buf((long long)B * hw * hw, ch);
+  {
+    int npad = 0;
+    const bf16* w = b.conv_w(V + "conv_in.weight", &npad, 64);
+    Epilogue e;
+    e.bias = b.f32_pad(V + "conv_in.bias", npad);
+    e.n_out = ch;
+    e.out = cur;
+    e.ld_out = ch;
+    Builder::want_gn_stats(e, cur_sums, ch, G, (long long)hw * hw);
+    b.linear(col, (long long)B * hw * hw, 64, 64, w, npad, e);
+  }
+  b.rel(col);
+  b.rel(z);
+  emit_vae_mid_block(b, "vae.decoder.mid_block", cur, cur_sums, B, hw, ch, G, eps);
+  for (int i = 0; i < nl; ++i) {
+    const int cout = a.block_out_channels[nl - 1 - i];
+    const std::string up = V + "up_blocks." + std::to_string(i);
+    for (int j = 0; j < a.layers_per_block + 1; ++j) {
+      bf16* o = b.buf((long long)B * hw * hw, cout);
+      Dest d;
+      d.out = o;
+      d.ld = cout;
+      // the output feeds a GroupNorm (next resnet / conv_norm_out) unless the upsampler follows
+      const bool before_up = (j == a.layers_per_block) && (i != nl - 1);
+      d.gn_sums = (!before_up && b.gn_fusable(cout, G, (long long)hw * hw)) ? b.gn_slot(B, G) : nullptr;
+      emit_resnet(b, up + ".resnets." + std::to_string(j), "", cur, B, hw, hw, ch, cout, nullptr, 0, G, eps, d, cur_sums);
+      b.rel(cur);
+      cur = o;
+      cur_sums = d.gn_sums;
+      ch = cout;
+    }
+    if (i != nl - 1) {   // Upsample2D: nearest x2 + conv3x3 (upsampling.py:176-193)
+      bf16* big = b.buf((long long)B * hw * hw * 4, ch);
+      if (!b.dry) {
+        const int hh = hw, cc = ch;
+        bf16* src = cur;
+        b.ops->push_back([=](const RunCtx& rc) -> int {
+          OP_CUDA(launch_upsample_nearest2x(src, big, B, hh, hh, cc, rc.stream));
+          return 0;
+        });
+      }
+      b.rel(cur);
+      hw *= 2;
+      int npad = 0;
+      const bf16* w = b.conv_w(up + ".upsamplers.0.conv.weight", &npad);
+      bf16* o = b.buf((long long)B * hw * hw, ch);
+      Epilogue e;
+      e.bias = b.f32_pad(up + ".upsamplers.0.conv.bias", npad);
+      e.n_out = ch;
+      e.out = o;
+      e.ld_out = ch;
+      cur_sums = (npad == ch && b.gn_fusable(ch, G, (long long)hw * hw)) ? b.gn_slot(B, G) : nullptr;
+      Builder::want_gn_stats(e, cur_sums, ch, G, (long long)hw * hw);
+      b.conv3(big, B, hw, hw, ch, w, npad, 1, 1, e);
+      b.rel(big);
+      cur = o;
+    }
+  }
+  const long long M = (long long)B * hw * hw;
+  bf16* t = b.buf(M, ch);
+  if (cur_sums) b.groupnorm_from_sums(cur, t, V + "conv_norm_out", B, hw * hw, ch, G, eps, true, cur_sums);
+  else b.groupnorm(cur, t, V + "conv_norm_out", B, hw * hw, ch, G, eps, true);
+  b.rel(cur);
+  {
+    int npad = 0;
+    const bf16* w = b.conv_w(V + "conv_out.weight", &npad);
+    const float* bias = b.f32_pad(V + "conv_out.bias", npad);
+    if (!b.dry && !b.err) {
+      // the destination comes with the call (rc.dec_image_out): the launch is built there, once per destination
+      const int S = hw, cc = ch;
+      struct Cached { float* dst = nullptr; GemmLaunch g; };
+      auto cache = std::make_shared<Cached>();
+      b.ops->tag(kKindGemm, 2.0 * (double)M * 3.0 * 9.0 * ch, "vae decoder conv_out -> fp32 NHWC image");
+      b.ops->push_back([=](const RunCtx& rc) -> int {
+        if (cache->dst != rc.dec_image_out) {
+          Epilogue e;
+          e.bias = bias;
+          e.n_out = 3;
+          e.out_f32 = rc.dec_image_out;
+          e.ld_out_f32 = 3;
+          GDF_TRY(build_conv3x3(&cache->g, t, B, S, S, cc, w, npad, 1, 1, e));
+          cache->dst = rc.dec_image_out;
+        }
+        OP_CUDA(launch_gemm(cache->g, rc.stream));
+        return 0;
+      });
+    }
+  }
+  b.rel(t);
+  return b.err;
+}
+
 static int build_vae(Builder& b) {
   gdf_handle_s* h = b.h;
   const gdf_vae_arch& a = h->va;
@@ -2608,100 +2864,7 @@ static int build_vae(Builder& b) {
   }
   const long long M = (long long)B * hw * hw;
   const int N = hw * hw;
-  {  // mid block: resnet, single-head attention (d = ch), resnet
-    bf16* r0 = b.buf(M, ch);
-    Dest d;
-    d.out = r0;
-    d.ld = ch;
-    d.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
-    emit_resnet(b, V + "mid_block.resnets.0", "", cur, B, hw, hw, ch, ch, nullptr, 0, G, eps, d, cur_sums);
-    b.rel(cur);
-    const std::string ap = V + "mid_block.attentions.0";
-    bf16* hn = b.buf(M, ch);
-    if (d.gn_sums) b.groupnorm_from_sums(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false, d.gn_sums);
-    else b.groupnorm(r0, hn, ap + ".group_norm", B, N, ch, G, eps, false);
-    // Q | K fused projection
-    const bf16* wqk = b.rows_bf16(ap + "#qk", {ap + ".to_q.weight", ap + ".to_k.weight"}, nullptr);
-    // The concatenated q | k bias is a CONSTANT of the plan: it lives in weight storage (f32_cat), not in the activation
-    // pool. Round 1 filled a pool buffer at plan time and released it after the block: the pool handed it to a later
-    // layer, so from the second forward on (the first one still saw the plan-time contents) the VAE's mid-block
-    // attention added whatever activations that layer had left there instead of the bias. Found in round 2 through the
-    // bit-reproducibility probe (tools/probe_determinism_vae2.py: the latents changed for good after the first UNet
-    // forward); the error was small enough (logit shifts of one 512-wide head) to pass the cosine / max-relative bounds.
-    const float* bqk = b.f32_cat(ap + "#qk_bias", {ap + ".to_q.bias", ap + ".to_k.bias"});
-    bf16* qk = b.buf(M, 2 * ch);
-    {
-      Epilogue e;
-      e.bias = bqk;
-      e.out = qk;
-      e.ld_out = 2 * ch;
-      b.linear(hn, M, ch, ch, wqk, 2 * ch, e);
-    }
-    // V^T[b] = Wv hn[b]^T + bv[:, None]  -> [B, ch, N]
-    bf16* vt = b.buf((long long)B * ch, N);
-    {
-      Epilogue e;
-      e.bias_m = b.f32(ap + ".to_v.bias");
-      e.out = vt;
-      e.ld_out = N;
-      e.out_batch_stride = (long long)ch * N;
-      b.linear(b.lin(ap + ".to_v.weight"), ch, ch, ch, hn, N, e, Caps(), B, 0, (long long)N * ch, ch);
-    }
-    b.rel(hn);
-    // S[b] = Q[b] K[b]^T / sqrt(ch)
-    bf16* S = b.buf((long long)B * N, N);
-    {
-      Epilogue e;
-      e.alpha = 1.f / sqrtf((float)ch);
-      e.out = S;
-      e.ld_out = N;
-      e.out_batch_stride = (long long)N * N;
-      b.linear(qk, N, ch, 2 * ch, qk + ch, N, e, Caps(), B, (long long)N * 2 * ch, (long long)N * 2 * ch,
-               2 * ch);
-    }
-    b.rel(qk);
-    if (!b.dry) {
-      const long long rows = (long long)B * N;
-      b.ops->push_back([=](const RunCtx& rc) -> int {
-        OP_CUDA(launch_softmax_rows(S, rows, N, N, rc.stream));
-        return 0;
-      });
-    }
-    // O[b] = P[b] V[b]
-    bf16* o = b.buf(M, ch);
-    {
-      Epilogue e;
-      e.out = o;
-      e.ld_out = ch;
-      e.out_batch_stride = (long long)N * ch;
-      b.linear(S, N, N, N, vt, ch, e, Caps(), B, (long long)N * N, (long long)ch * N, N);
-    }
-    b.rel(S);
-    b.rel(vt);
-    bf16* ao = b.buf(M, ch);
-    {
-      Epilogue e;
-      e.bias = b.f32(ap + ".to_out.0.bias");
-      e.residual = r0;
-      e.ld_res = ch;
-      e.out = ao;
-      e.ld_out = ch;
-      cur_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
-      Builder::want_gn_stats(e, cur_sums, ch, G, (long long)N);
-      b.linear(o, M, ch, ch, b.lin(ap + ".to_out.0.weight"), ch, e);
-    }
-    b.rel(o);
-    b.rel(r0);
-    bf16* r1 = b.buf(M, ch);
-    Dest d1;
-    d1.out = r1;
-    d1.ld = ch;
-    d1.gn_sums = b.gn_fusable(ch, G, (long long)N) ? b.gn_slot(B, G) : nullptr;
-    emit_resnet(b, V + "mid_block.resnets.1", "", ao, B, hw, hw, ch, ch, nullptr, 0, G, eps, d1, cur_sums);
-    b.rel(ao);
-    cur = r1;
-    cur_sums = d1.gn_sums;
-  }
+  emit_vae_mid_block(b, "vae.encoder.mid_block", cur, cur_sums, B, hw, ch, G, eps);
   // conv_norm_out + SiLU + (conv_out . quant_conv folded into one 3x3 conv) -> fp32 moments [M, 8]
   bf16* t = b.buf(M, ch);
   if (cur_sums) b.groupnorm_from_sums(cur, t, V + "conv_norm_out", B, N, ch, G, eps, true, cur_sums);
@@ -2776,6 +2939,7 @@ static int build_vae(Builder& b) {
 static void free_plan(gdf_handle_s* h) {
   h->vae_ops.clear();
   h->unet_ops.clear();
+  h->dec_ops.clear();
   h->pool.clear();
   h->sites.clear();
   h->slots.clear();
@@ -2974,6 +3138,7 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   Builder b(h, true);
   std::vector<Site> keep_sites = h->sites;
   int r = build_vae(b);
+  if (!r && h->raw.count("vae.decoder.conv_in.weight")) r = build_vae_decoder(b);   // optional: only `vae-out` decodes
   if (!r) r = h->is_flux ? build_flux(b) : h->is_dit ? build_dit(b) : build_unet(b);
   h->sites = keep_sites;
   h->B = B0;
@@ -3052,6 +3217,37 @@ int gdf_plan(gdf_handle h, const char* const* feature_ids, int n_ids, int batch,
   h->planned = true;
   ++h->plan_generation;
   h->gpu_launches = (int)(h->vae_ops.size() + h->unet_ops.size());
+  return GDF_OK;
+}
+
+int gdf_plan_decoder(gdf_handle h) {
+  if (!h || !h->planned) return fail(GDF_ERR_INVALID, "gdf_plan_decoder: call gdf_plan first");
+  if (!h->dec_ops.fns.empty()) return GDF_OK;
+  if (!h->raw.count("vae.decoder.conv_in.weight"))
+    return fail(GDF_ERR_MISSING_WEIGHT, "gdf_plan_decoder: no VAE decoder weights ('vae.decoder.*') were loaded");
+  GDF_CUDA(cudaSetDevice(h->device));
+  Builder b(h, false);
+  b.gn_ws = static_cast<float*>(h->pool.acquire(gn_workspace_floats(h->B, 64) * 4));
+  const int r = build_vae_decoder(b);
+  if (r) {
+    h->dec_ops.clear();
+    return r;
+  }
+  return GDF_OK;
+}
+
+int gdf_decode_latents(gdf_handle h, const void* latents_dev, float c_latent, const void* model_out_dev, float c_model,
+                       void* image_out_dev, void* stream) {
+  if (!h || !h->planned || h->dec_ops.fns.empty()) return fail(GDF_ERR_INVALID, "gdf_decode_latents: call gdf_plan_decoder first");
+  if (!latents_dev || !image_out_dev) return fail(GDF_ERR_INVALID, "gdf_decode_latents: null argument");
+  RunCtx rc;
+  rc.stream = static_cast<cudaStream_t>(stream);
+  rc.dec_latents = static_cast<const float*>(latents_dev);
+  rc.dec_model_out = static_cast<const float*>(model_out_dev);
+  rc.dec_c_latent = c_latent;
+  rc.dec_c_model = c_model;
+  rc.dec_image_out = static_cast<float*>(image_out_dev);
+  GDF_TRY(run_ops(h, h->dec_ops, rc));
   return GDF_OK;
 }
 

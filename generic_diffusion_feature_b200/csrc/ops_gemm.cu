@@ -28,13 +28,16 @@ static int env_int(const char* name, int dflt) {
 // GDF_WAVE_POLICY=0 restores the padding-only rule (A/B timing).
 // K-split of the tail wave: S pieces per tile cost ceil(nk / S) k-blocks of main loop + the fix-up: every piece writes its
 // 128 x bn fp32 accumulators per CTA (~2 k-block times) and the last one reads the other S - 1 back (~3 k-block times
-// each: one SM pulling 128 KB from L2). Split only when that beats the whole tile by > 15 %. GDF_STREAM_K=0 disables,
-// GDF_SK_MAX_PIECES bounds S (tuning knobs).
+// each: one SM pulling 128 KB from L2). Split only when that beats the whole tile by > 15 %. GDF_SK_MAX_PIECES bounds S.
+// MEASURED (profiles/r02_ksplit_ab.md): a net loss on the SDXL step (71.7 vs 73.2 images/s on the same box). The saved
+// main-loop time of a short-K tail (10 of 20 k-blocks = ~3.5 us) is of the order of the fix-up's dependent latencies
+// (publish 128 KB, fence, counter, read the peer's 128 KB back, TMEM store), and the pieces add 10-30 us per launch. The
+// executor therefore only passes a workspace with GDF_STREAM_K=1; the op-level API splits whenever the caller gives one.
 int plan_k_split(int nk, int groups, int tail, int* kpp_out, float* tail_cost) {
   int best_s = 1, best_kpp = nk;
   float best = (float)nk * 0.85f;
   const int smax = env_int("GDF_SK_MAX_PIECES", 4);
-  if (tail > 0 && env_int("GDF_STREAM_K", 1) != 0) {
+  if (tail > 0) {
     for (int s = 2; s <= smax && s * tail <= groups; ++s) {
       const int kpp = (nk + s - 1) / s;
       if (kpp < 4) break;

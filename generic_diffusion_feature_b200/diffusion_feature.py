@@ -62,6 +62,18 @@ class FeatureExtractor(nn.Module):
             pipe = get_diffusion_model(version, dtype, offline_lora, offline_lora_filename, device=device)
         self.feature_store = prepare_feature_extractor(version, pipe, layer, feature_resize, train_unet)
         self.store_vae_output = bool(self.feature_store.to_store.get('vae-out', False))
+        if self.store_vae_output:
+            # diffusion_feature.py:477-485: scheduler.step + vae.decode. UNet families only (the reference's own vae-out
+            # does not run for the transformer pipes either: an 8-channel PixArt output goes unsplit into step(), the
+            # Flux branch returns before it), and the pipe must have been given the VAE decoder weights.
+            if getattr(pipe, "dit_cfg", None) is not None or getattr(pipe, "flux_cfg", None) is not None:
+                raise NotImplementedError("vae-out: only the UNet families (xl, pgv2, 2-1, 1-5) have a scheduler.step + "
+                                          "vae.decode path")
+            schedulers.step_coeffs(version, 50)      # raises for a version without a restated scheduler.step
+            if not getattr(pipe, "has_decoder", False):
+                raise ValueError("vae-out needs the VAE decoder: load a state dict / model_dir that holds "
+                                 "'vae.decoder.*' and 'vae.post_quant_conv.*' (load_diffusers_dir(..., "
+                                 "with_decoder=True) / synthetic_state_dict(..., with_decoder=True))")
         self.pipe = pipe
         self.control_pipe = None
         self.attention_store = None
@@ -243,13 +255,17 @@ class FeatureExtractor(nn.Module):
             time_ids = torch.tensor([[s, s, 0.0, 0.0, s, s]], device=dev).repeat(batch_size, 1).contiguous()
         arena = torch.empty(plan.arena_bytes, dtype=torch.uint8, device=dev)
         lib = pipe.lib
+        # vae-out: the noised latents (before input scaling) and the noise prediction leave the two passes as fp32 NCHW
+        lat_out = torch.empty(batch_size, lat_ch, L, L, device=dev) if self.store_vae_output else None
+        npred_out = torch.empty(batch_size, lat_ch, L, L, device=dev) if self.store_vae_output else None
         with torch.cuda.device(pipe.dev_index):
             st = _lib.stream_ptr()
             if is_latents:
-                check(lib.gdf_encode_latents(pipe.handle, _lib.ptr(image), _lib.ptr(eps_q), qa, qb, qs, None, st))
+                check(lib.gdf_encode_latents(pipe.handle, _lib.ptr(image), _lib.ptr(eps_q), qa, qb, qs,
+                                             _lib.ptr(lat_out), st))
             else:
                 check(lib.gdf_encode_noise(pipe.handle, _lib.ptr(image), _lib.ptr(eps_vae), _lib.ptr(eps_q), qa, qb,
-                                           qs, None, st))
+                                           qs, _lib.ptr(lat_out), st))
             if is_flux:
                 mask_d = None
                 key = (ctx.shape[1], L // 2)
@@ -269,11 +285,23 @@ class FeatureExtractor(nn.Module):
                 mask_d = None
                 ctrl_keep = self._set_control_residuals(control_residuals, batch_size)
                 check(lib.gdf_denoise_capture(pipe.handle, timestep, _lib.ptr(ctx), ctx.shape[1], _lib.ptr(pooled_d),
-                                              _lib.ptr(time_ids), _lib.ptr(arena), arena.numel(), None, st))
+                                              _lib.ptr(time_ids), _lib.ptr(arena), arena.numel(), _lib.ptr(npred_out),
+                                              st))
+                if self.store_vae_output:
+                    # latents = scheduler.step(noise_pred, t, latents)[0]; vae.decode(latents / scaling_factor)
+                    # (diffusion_feature.py:478-484): both steps are linear in (latents, noise_pred)
+                    c_s, c_m = schedulers.step_coeffs(self.version, t)
+                    sf = pipe.vae_cfg["scaling_factor"]
+                    vae_img = torch.empty(batch_size, self.img_size, self.img_size, 3, device=dev)
+                    check(lib.gdf_plan_decoder(pipe.handle))
+                    check(lib.gdf_decode_latents(pipe.handle, _lib.ptr(lat_out), c_s / sf, _lib.ptr(npred_out), c_m / sf,
+                                                 _lib.ptr(vae_img), st))
         feats = plan.views(arena)
         if self.feature_store.resize_ratio > 1:                  # feature_extractor.py:51-53
             with torch.cuda.device(pipe.dev_index):
                 feats = pool_views(lib, feats, self.feature_store.resize_ratio)
+        if self.store_vae_output:      # stored as the pipe's dtype, outside FeatureStore.store (diffusion_feature.py:485)
+            feats['vae-out'] = vae_img.permute(0, 3, 1, 2).to(torch.float16)
         if self.attention:                                       # diffusion_feature.py:488-500
             feats['attn'] = aggregate_attention(plan.attention_means(arena), list(self.attention), self.img_size,
                                                 transformer=(getattr(self.pipe, 'dit_cfg', None) is not None or
@@ -283,7 +311,7 @@ class FeatureExtractor(nn.Module):
         self.feature_store.feats = feats
         # keep inputs alive until the stream has consumed them
         self._keepalive = (image, eps_vae, eps_q, ctx, pooled_d, time_ids, arena, mask_d,
-                           locals().get("ctrl_keep"))
+                           locals().get("ctrl_keep"), lat_out, npred_out, locals().get("vae_img"))
         return self.feature_store.stored_feats
 
     def _set_control_residuals(self, control_residuals, batch_size):

@@ -80,3 +80,32 @@ def resolve(version, t, img_size=None):
         ac_lin = np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32)
         return float(ts), math.sqrt(float(ac_lin[ts])), math.sqrt(1.0 - float(ac_lin[ts])), 1.0
     raise NotImplementedError(version)
+
+
+def step_coeffs(version, t):
+    """`scheduler.step(noise_pred, t, latents)[0]` of diffusion_feature.py:478-480 (the `vae-out` path) as
+    prev = c_s * latents + c_m * noise_pred, for the first step after set_timesteps(1000) (module docstring):
+      Euler (xl / pgv2 / 2-1, epsilon prediction, s_churn 0): derivative = noise_pred, prev = latents + noise_pred *
+          (sigma_next - sigma), sigmas = interp(timesteps) followed by 0
+      PNDM (1-5, skip_prk_steps: the first step_plms call, counter 0, ets = [noise_pred]): _get_prev_sample with
+          prev_timestep = timestep - 1, final_alpha_cumprod = abar_0 (set_alpha_to_one False)
+    PixArt (DPM-Solver on an 8-channel output the reference does not split before step()) and Flux (whole pipeline call)
+    have no working `vae-out` in the reference either."""
+    ts = int(resolve(version, t)[0])
+    ac = alphas_cumprod().astype(np.float64)
+    if version in ("xl", "pgv2", "2-1"):
+        def sig(k):
+            k = min(k, 999)
+            return math.sqrt((1.0 - ac[k]) / ac[k])
+        last = 1 if version != "2-1" else 0
+        sigma_next = 0.0 if ts == last else sig(ts - 1)
+        return 1.0, sigma_next - sig(ts)
+    if version == "1-5":
+        a_t = float(ac[min(ts, 999)])
+        prev = ts - 1
+        a_p = float(ac[prev]) if prev >= 0 else float(ac[0])
+        b_t, b_p = 1.0 - a_t, 1.0 - a_p
+        denom = a_t * math.sqrt(b_p) + math.sqrt(a_t * b_t * a_p)
+        return math.sqrt(a_p / a_t), -(a_p - a_t) / denom
+    raise NotImplementedError("vae-out: scheduler.step for version '%s' is not built (the reference's own vae-out "
+                              "path only runs for the UNet families)" % version)

@@ -176,6 +176,19 @@ int gdf_encode_noise(gdf_handle h, const void* images_dev, const void* eps_vae_d
                      float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float input_scale, void* latents_out_dev,
                      void* stream);
 
+/* `vae-out` (feature/diffusion_feature.py:477-485: latents = scheduler.step(noise_pred, t, latents)[0];
+ * vae.decode(latents / scaling_factor)). gdf_plan_decoder builds the decoder op list for the current plan's batch and
+ * image size (needs the 'vae.decoder.*' / 'vae.post_quant_conv.*' weights, loaded like every other weight; error
+ * GDF_ERR_MISSING_WEIGHT otherwise). gdf_decode_latents computes z = c_latent * latents + c_model * model_out - the
+ * scheduler step and the 1 / scaling_factor are both linear in the two tensors, the host supplies the coefficients
+ * (schedulers.step_coeffs) - and decodes it:
+ *   latents_dev / model_out_dev : fp32 (B, latent, S/8, S/8), the latents_out / noise_pred_out of the calls above
+ *                                 (model_out_dev may be NULL: plain vae.decode(c_latent * latents))
+ *   image_out_dev               : fp32 NHWC (B, S, S, 3) */
+int gdf_plan_decoder(gdf_handle h);
+int gdf_decode_latents(gdf_handle h, const void* latents_dev, float c_latent, const void* model_out_dev, float c_model,
+                       void* image_out_dev, void* stream);
+
 /* Latents supplied directly: the `image.shape[1] == 4` branch of prepare_latents (pipeline_pixart_sigma.py:623-624)
  * - no VAE pass; x_t = a*latents + b*eps_q (eps_q_dev may be NULL = no noise), model input = x_t * input_scale. */
 int gdf_encode_latents(gdf_handle h, const void* latents_dev, const void* eps_q_dev, float sqrt_alpha_bar,

@@ -1093,20 +1093,71 @@ class VaeEncoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(h)))
 
 
+class VaeUpBlock(nn.Module):
+    """[diffusers unet_2d_blocks.UpDecoderBlock2D, un-vendored]: layers + 1 resnets (no time embedding), then
+    Upsample2D (nearest x2 + conv3x3, upsampling.py:142-195) on every level but the last."""
+
+    def __init__(self, cin, cout, n_resnets, add_up, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, 0, eps=eps)
+                                      for i in range(n_resnets)])
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, h):
+        for r in self.resnets:
+            h = r(h)
+        if self.upsamplers:
+            h = self.upsamplers[0](h)
+        return h
+
+
+class VaeDecoder(nn.Module):
+    """[diffusers autoencoders/vae.Decoder, un-vendored; PARITY UNPINNED] the `vae.decode` of diffusion_feature.py:481-484:
+    conv_in -> mid block (resnet, single-head attention, resnet) -> up blocks over reversed(block_out_channels) with
+    layers_per_block + 1 resnets each -> GroupNorm + SiLU + conv_out."""
+
+    def __init__(self, block_out=(128, 256, 512, 512), layers=2, latent=4, eps=1e-6):
+        super().__init__()
+        rev = list(reversed(block_out))
+        self.conv_in = nn.Conv2d(latent, rev[0], 3, padding=1)
+        self.mid_block = VaeMidBlock(rev[0], eps)
+        self.up_blocks = nn.ModuleList()
+        ch = rev[0]
+        for i, co in enumerate(rev):
+            self.up_blocks.append(VaeUpBlock(ch, co, layers + 1, i != len(rev) - 1, eps))
+            ch = co
+        self.conv_norm_out = nn.GroupNorm(32, ch, eps=eps)
+        self.conv_out = nn.Conv2d(ch, 3, 3, padding=1)
+
+    def forward(self, z):
+        h = self.mid_block(self.conv_in(z))
+        for b in self.up_blocks:
+            h = b(h)
+        return self.conv_out(F.silu(self.conv_norm_out(h)))
+
+
 class Vae(nn.Module):
-    def __init__(self, scaling_factor, shift_factor=0.0, quant_conv=True, **kw):
+    def __init__(self, scaling_factor, shift_factor=0.0, quant_conv=True, decoder=False, **kw):
         super().__init__()
         self.encoder = VaeEncoder(**kw)
         lat = kw.get("latent", 4)
         if quant_conv:                      # Flux's AutoencoderKL has use_quant_conv False
             self.quant_conv = nn.Conv2d(2 * lat, 2 * lat, 1)
         self.has_quant = quant_conv
+        if decoder:                         # only the `vae-out` path needs it (diffusion_feature.py:477-485)
+            self.decoder = VaeDecoder(**kw)
+            if quant_conv:
+                self.post_quant_conv = nn.Conv2d(lat, lat, 1)
         self.scaling_factor = scaling_factor
         self.shift_factor = shift_factor
 
     def moments(self, x):
         m = self.encoder(x)
         return self.quant_conv(m) if self.has_quant else m
+
+    def decode(self, z):
+        """[AutoencoderKL._decode]: post_quant_conv then the decoder."""
+        return self.decoder(self.post_quant_conv(z) if self.has_quant else z)
 
 
 # ------------------------------------------------------------------------------------------ scheduler math
@@ -1148,6 +1199,40 @@ def resolve_timestep(version, t):
         ac_lin = torch.cumprod(1.0 - betas, dim=0)
         return ts, float(ac_lin[int(ts)] ** 0.5), float((1 - ac_lin[int(ts)]) ** 0.5), 1.0
     raise NotImplementedError(version)
+
+
+def scheduler_step_coeffs(version, t):
+    """`scheduler.step(noise_pred, t, latents)[0]` of diffusion_feature.py:478-480 as prev = c_s * latents + c_m * noise_pred,
+    for the first step after set_timesteps(1000) [diffusers 0.32.2 schedulers, un-vendored; PARITY UNPINNED]:
+      Euler (xl, pgv2, 2-1; epsilon prediction, s_churn 0): derivative = noise_pred, dt = sigma_next - sigma,
+          prev = latents + noise_pred * dt; sigmas = interp(timesteps) ++ [0]
+      PNDM (1-5; skip_prk_steps, first step_plms call: counter 0, ets = [noise_pred]): _get_prev_sample with
+          prev_timestep = timestep - 1."""
+    ts, _, _, _ = resolve_timestep(version, t)
+    ts = int(ts)
+    ac = alphas_cumprod().double()
+    if version in ("xl", "pgv2", "2-1"):
+        sig = lambda k: float(((1 - ac[min(k, 999)]) / ac[min(k, 999)]) ** 0.5)
+        last = 1 if version != "2-1" else 0          # final timestep of the schedule: the appended sigma 0 follows it
+        sigma_next = 0.0 if ts == last else sig(ts - 1)
+        return 1.0, sigma_next - sig(ts)
+    if version == "1-5":
+        a_t = float(ac[min(ts, 999)])
+        prev = ts - 1
+        a_p = float(ac[prev]) if prev >= 0 else float(ac[0])       # set_alpha_to_one False: final_alpha_cumprod = abar_0
+        b_t, b_p = 1.0 - a_t, 1.0 - a_p
+        denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
+        return (a_p / a_t) ** 0.5, -(a_p - a_t) / denom
+    raise NotImplementedError("vae-out: scheduler.step of version '%s'" % version)
+
+
+@torch.no_grad()
+def vae_out(version, vae, latents, noise_pred, t):
+    """diffusion_feature.py:477-485: latents = scheduler.step(noise_pred, t, latents)[0];
+    vae.decode(latents / scaling_factor)."""
+    c_s, c_m = scheduler_step_coeffs(version, t)
+    prev = c_s * latents + c_m * noise_pred
+    return vae.decode(prev / vae.scaling_factor)
 
 
 def prepare_latents(vae, image, eps_vae, eps_q, a, b):

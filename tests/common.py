@@ -49,8 +49,8 @@ def make_inputs(batch, img, ctx_dim, pooled_dim=None, ctx_len=77):
 def build_oracle(unet_cfg, vae_cfg, sd):
     """Oracle modules loaded from a 'unet.*' / 'vae.*' state dict (fp32, CPU)."""
     unet = O.UNet2DConditionModel(unet_cfg)
-    vae = O.Vae(vae_cfg["scaling_factor"], block_out=vae_cfg["block_out"], layers=vae_cfg["layers"],
-                latent=vae_cfg["latent"], eps=vae_cfg["eps"])
+    vae = O.Vae(vae_cfg["scaling_factor"], decoder=any(k.startswith("vae.decoder.") for k in sd),
+                block_out=vae_cfg["block_out"], layers=vae_cfg["layers"], latent=vae_cfg["latent"], eps=vae_cfg["eps"])
     usd = {k[len("unet."):]: v.float().cpu() for k, v in sd.items() if k.startswith("unet.")}
     vsd = {k[len("vae."):]: v.float().cpu() for k, v in sd.items() if k.startswith("vae.")}
     unet.load_state_dict(usd, strict=True)

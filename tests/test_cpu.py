@@ -411,6 +411,40 @@ def test_oracle_segmentor_head_matches_reference():
     assert torch.allclose(folded, plain, atol=1e-4, rtol=1e-4)
 
 
+def test_vae_out_host_logic_matches_oracle():
+    """`vae-out` host side (diffusion_feature.py:477-485): scheduler.step coefficients of the product equal the
+    oracle's for every UNet family over the timestep range, the Euler step equals the textbook form computed from the
+    sigma table, and the decoder parameter list equals the oracle decoder's state dict (names + shapes)."""
+    from generic_diffusion_feature_b200 import schedulers
+    models = _models()
+    for version in ("xl", "pgv2", "2-1", "1-5"):
+        for t in (1, 2, 50, 261, 500, 998, 999):
+            a, b = schedulers.step_coeffs(version, t), O.scheduler_step_coeffs(version, t)
+            assert abs(a[0] - b[0]) < 1e-6 and abs(a[1] - b[1]) < 1e-6, (version, t, a, b)   # fp32 cumprod tables: numpy vs torch
+    # Euler: prev = x + eps * (sigma_next - sigma); at t = 50 (timestep 50 of [1000..1]) sigma_next = sigma(49)
+    ac = schedulers.alphas_cumprod().astype(np.float64)
+    sig = lambda k: ((1 - ac[k]) / ac[k]) ** 0.5
+    c_s, c_m = schedulers.step_coeffs("xl", 50)
+    assert c_s == 1.0 and abs(c_m - (sig(49) - sig(50))) < 1e-12
+    # PNDM first PLMS step reproduces x_{t-1} of the DDIM-like closed form when noise_pred is the true noise:
+    # x_t = sqrt(a_t) z + sqrt(1 - a_t) eps  ->  _get_prev_sample gives approximately sqrt(a_p) z + sqrt(1 - a_p) eps
+    ts = int(schedulers.resolve("1-5", 261)[0])
+    c_s, c_m = schedulers.step_coeffs("1-5", 261)
+    z_coef = c_s * ac[ts] ** 0.5
+    e_coef = c_s * (1 - ac[ts]) ** 0.5 + c_m
+    assert abs(z_coef - ac[ts - 1] ** 0.5) < 1e-9 and abs(e_coef - (1 - ac[ts - 1]) ** 0.5) < 2e-4
+    with pytest.raises(NotImplementedError):
+        schedulers.step_coeffs("pixart-sigma", 50)
+    vae = O.Vae(TINY_VAE["scaling_factor"], decoder=True, block_out=TINY_VAE["block_out"], layers=TINY_VAE["layers"],
+                latent=TINY_VAE["latent"], eps=TINY_VAE["eps"])
+    want = {k: tuple(v.shape) for k, v in vae.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    got = {n: tuple(s) for n, s in models.vae_decoder_param_specs(TINY_VAE)}
+    assert got == want
+    sd = models.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE, with_decoder=True)
+    assert "vae.decoder.conv_out.weight" in sd and "vae.decoder.conv_in.weight" not in models.synthetic_state_dict(
+        "xl", "cpu", TINY_XL, TINY_VAE)
+
+
 def test_oracle_whole_path_digest():
     gold = torch.load(os.path.join(GOLD, "extract_tiny_xl.pt"), weights_only=False)
     sd = _models().synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE)

@@ -384,7 +384,7 @@ def test_unknown_id_and_unbuilt_features(cuda_dev):
     fe = FeatureExtractor({"up-level9-repeat0-res-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
     with pytest.raises(GdfError):
         fe.extract((ctx, ctx, pooled, pooled), 1, image, image_type="tensors")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):      # vae-out needs the decoder weights, this pipe was loaded without them
         FeatureExtractor({"vae-out": True}, "xl", "cuda:0", img_size=128, external_model=pipe)
     # cross-k / cross-v are accepted and silently dropped, like FeatureStore.store (feature_extractor.py:38-39)
     fe = FeatureExtractor({"mid-vit-block0-cross-k": True, "mid-vit-out": True}, "xl", "cuda:0", img_size=128,
@@ -395,6 +395,44 @@ def test_unknown_id_and_unbuilt_features(cuda_dev):
         models.get_diffusion_model("xl", "bfloat16")      # models.py:15-16
     with pytest.raises(NotImplementedError):
         models.get_diffusion_model("no-such-version", "float16")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version,ucfg,t", [("xl", TINY_XL, 50), ("1-5", TINY_15, 261), ("2-1", TINY_21, 50)])
+def test_vae_out_matches_oracle(cuda_dev, version, ucfg, t):
+    """`vae-out` (diffusion_feature.py:477-485): scheduler.step (Euler / first PLMS step of PNDM, restated: un-vendored
+    diffusers schedulers, PARITY UNPINNED) + vae.decode (post_quant_conv + decoder op list: conv_in as a K = 36 im2col GEMM,
+    mid block with the single-head attention, four up blocks with nearest-x2 + conv upsamplers, conv_out to fp32) against
+    the CPU oracle on the same seeded inputs. It is the last key, fp16, (B, 3, S, S), and the other maps are unchanged."""
+    from generic_diffusion_feature_b200.components import models
+    from generic_diffusion_feature_b200.diffusion_feature import FeatureExtractor
+    batch, img = 2, 128
+    sd = models.synthetic_state_dict(version, "cpu", ucfg, TINY_VAE, with_decoder=True)
+    pooled_dim = (ucfg["add_in"] - 6 * ucfg["add_time_dim"]) if ucfg["add_time_dim"] else None
+    image, ctx, pooled, eps_vae, eps_q = make_inputs(batch, img, ucfg["ctx_dim"], pooled_dim)
+    layer = {"mid-vit-out": True, "vae-out": True, "unet-out": True}
+    unet, vae = build_oracle(ucfg, TINY_VAE, sd)
+    store = O.FeatureStore({k: v for k, v in layer.items() if k != "vae-out"})
+    O.attach_gatherers(unet, store)
+    want, latents, npred = O.extract(version, unet, vae, store, image, ctx, pooled, eps_vae, eps_q, t=t, img_size=img)
+    want_img = O.vae_out(version, vae, latents, npred, t)
+    pipe = models.get_diffusion_model(version, "float16", device="cuda:0", state_dict=sd, unet_cfg=ucfg,
+                                      vae_cfg=TINY_VAE)
+    assert pipe.has_decoder
+    fe = FeatureExtractor(layer, version, "cuda:0", img_size=img, external_model=pipe)
+    got = fe.extract((ctx, ctx, pooled, pooled), batch, image.cuda(), image_type="tensors", t=t, noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert list(got.keys())[-1] == "vae-out"
+    v = got["vae-out"]
+    assert v.dtype == torch.float16 and tuple(v.shape) == (batch, 3, img, img)
+    rows = compare_maps({"vae-out": v, "mid-vit-out": got["mid-vit-out"]},
+                        {"vae-out": want_img, "mid-vit-out": want["mid-vit-out"]})
+    for r in rows:
+        assert r[1] >= COS_MIN and r[3] <= MAXREL_MAX, rows
+    # a second call reuses the decoder plan and gives the same image
+    got2 = fe.extract((ctx, ctx, pooled, pooled), batch, image.cuda(), image_type="tensors", t=t, noise=(eps_vae, eps_q))
+    torch.cuda.synchronize()
+    assert (got2["vae-out"].float() - v.float()).abs().max().item() <= 2e-2 * v.float().abs().max().item()
 
 
 @pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21),
