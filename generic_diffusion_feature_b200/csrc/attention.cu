@@ -328,6 +328,85 @@ cudaError_t launch_softmax_rows(bf16* S, long long rows, int cols, int ld, cudaS
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------- tensor-core form of the probability-map path (self maps)
+// P = softmax(S) for fp32 scores S (written by the batched tcgen05 GEMM of Q K^T with alpha = scale) -> fp16
+// probabilities, the `...-self-map` feature itself. One block per row; the row is read twice from L2 (max + sum of
+// exponentials in one pass over registers would need cols / 256 live values: <= 16 for 4096 keys, kept in registers).
+constexpr int kSmThreads = 256, kSmMaxPer = 32;   // rows of up to 8192 keys
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_f32_f16_kernel(const float* __restrict__ S, __half* __restrict__ P, long long rows, int cols) {
+  __shared__ float red[kSmThreads / 32];
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  const float* s = S + row * cols;
+  __half* p = P + row * cols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float v[kSmMaxPer];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    const int c = tid + i * kSmThreads;
+    v[i] = c < cols ? __ldcs(s + c) : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < kSmThreads / 32; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    v[i] = __expf(v[i] - mx);     // exp(-inf) = 0 for the padding lanes
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmThreads / 32; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    const int c = tid + i * kSmThreads;
+    if (c < cols) p[c] = __float2half_rn(v[i] * inv);
+  }
+}
+cudaError_t launch_softmax_rows_f32_f16(const float* S, __half* P, long long rows, int cols, cudaStream_t stream) {
+  if (cols < 1 || cols > kSmThreads * kSmMaxPer || rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+  softmax_rows_f32_f16_kernel<<<(unsigned)rows, kSmThreads, 0, stream>>>(S, P, rows, cols);
+  return cudaGetLastError();
+}
+
+// V of one image, token-major bf16 [Nk, heads * D] (row pitch ldv) -> V^T fp16 [heads][D][Nk]: the K-major B operand
+// of the P V product on the fp16 GEMM path (P is fp16).
+__global__ void __launch_bounds__(256)
+transpose_v_f16_kernel(const bf16* __restrict__ V, int ldv, __half* __restrict__ VT, int Nk, int D) {
+  __shared__ float tile[32][33];
+  const int h = blockIdx.z;
+  const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, d = d0 + tx;
+    tile[r][tx] = (k < Nk && d < D) ? __bfloat162float(V[(long long)k * ldv + h * D + d]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, k = k0 + tx;
+    if (d < D && k < Nk) VT[((long long)h * D + d) * Nk + k] = __float2half_rn(tile[tx][r]);
+  }
+}
+cudaError_t launch_transpose_v_f16(const bf16* V, int ldv, __half* VT, int heads, int Nk, int D, cudaStream_t stream) {
+  const dim3 grid((Nk + 31) / 32, (D + 31) / 32, heads);
+  transpose_v_f16_kernel<<<grid, 256, 0, stream>>>(V, ldv, VT, Nk, D);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- attention with the probability matrix as an output
 // Slow path of the reference (AttnStoreProcessor, feature/components/attention.py:165-263): P = softmax(scale Q K^T)
 // is materialised per head - it is the `...-self-map` / `...-cross-map` feature, (B, heads, Nq, Nk), and its head mean

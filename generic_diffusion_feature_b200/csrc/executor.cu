@@ -955,6 +955,62 @@ class Builder {
     const int64_t mean_off = site("#attnmean:" + block_id + "-" + kind, 1, Nq, Nk);
     __half* scratch = map_off < 0 ? reinterpret_cast<__half*>(buf((long long)B * heads * Nq, Nk)) : nullptr;
     if (err) return;
+    // Tensor-core form (self maps: Nk a multiple of 8, no key bias): per image, S = scale Q K^T for every head as ONE
+    // batched tcgen05 GEMM (batch = heads, batch stride = head_dim columns) into fp32 scores, softmax -> fp16
+    // probabilities straight into the map's arena slot, V^T in fp16, O = P V as a second batched GEMM on the fp16
+    // operand path. The CUDA-core kernel below stays for the text cross maps (77 keys: rows of 154 bytes are not TMA
+    // addressable, and they are 50x smaller) and for PixArt's key bias. GDF_MAPS_TC=0 forces it everywhere (A/B).
+    static const bool maps_tc = [] { const char* e = getenv("GDF_MAPS_TC"); return !(e && e[0] == '0'); }();
+    if (maps_tc && !use_key_bias && !v_f16 && Nk % 8 == 0 && Nk >= 64 && Nk <= 8192 && head_dim % 8 == 0 && ldq % 8 == 0 &&
+        ldk % 8 == 0 && ldo % 8 == 0) {
+      float* S = fbuf((long long)heads * Nq * Nk);
+      __half* vt = reinterpret_cast<__half*>(buf((long long)heads * head_dim, Nk));
+      if (err) return;
+      struct Cached { __half* P = nullptr; std::vector<GemmLaunch> g; };
+      auto cache = std::make_shared<Cached>();
+      ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * head_dim,
+               "attention-probs(tcgen05 GEMMs) heads=" + std::to_string(heads) + " d=" + std::to_string(head_dim) + " Nq=" +
+                   std::to_string(Nq) + " Nk=" + std::to_string(Nk));
+      ops->push_back([=](const RunCtx& rc) -> int {
+        __half* P = map_off >= 0 ? reinterpret_cast<__half*>(rc.arena + map_off) : scratch;
+        if (cache->P != P) {   // launches hold the arena address: built once per arena
+          cache->g.assign(2 * (size_t)B, GemmLaunch());
+          for (int b = 0; b < B; ++b) {
+            Epilogue es;
+            es.alpha = scale;
+            es.out_f32 = S;
+            es.ld_out_f32 = Nk;
+            es.out_batch_stride = (long long)Nq * Nk;
+            GDF_TRY(build_linear(&cache->g[2 * b], q + (long long)b * Nq * ldq, Nq, head_dim, ldq, k + (long long)b * Nk * ldk,
+                                 Nk, ldk, es, heads, head_dim, head_dim));
+            Epilogue eo;
+            eo.in_f16 = true;
+            eo.out = o + (long long)b * Nq * ldo;
+            eo.ld_out = ldo;
+            eo.out_batch_stride = head_dim;
+            GDF_TRY(build_linear(&cache->g[2 * b + 1],
+                                 reinterpret_cast<const bf16*>(P + (long long)b * heads * Nq * Nk), Nq, Nk, Nk,
+                                 reinterpret_cast<const bf16*>(vt), head_dim, Nk, eo, heads, (long long)Nq * Nk,
+                                 (long long)head_dim * Nk));
+          }
+          cache->P = P;
+        }
+        for (int b = 0; b < B; ++b) {
+          OP_CUDA(launch_gemm(cache->g[2 * b], rc.stream));
+          OP_CUDA(launch_softmax_rows_f32_f16(S, P + (long long)b * heads * Nq * Nk, (long long)heads * Nq, Nk, rc.stream));
+          OP_CUDA(launch_transpose_v_f16(v + (long long)b * Nk * ldv, ldv, vt, heads, Nk, head_dim, rc.stream));
+          OP_CUDA(launch_gemm(cache->g[2 * b + 1], rc.stream));
+        }
+        if (mean_off >= 0)
+          OP_CUDA(launch_head_mean(P, reinterpret_cast<__half*>(rc.arena + mean_off), B, heads, (long long)Nq * Nk,
+                                   rc.stream));
+        return 0;
+      });
+      rel(S);
+      rel(vt);
+      if (scratch) rel(scratch);
+      return;
+    }
     ops->tag(kKindAttention, 4.0 * B * heads * (double)Nq * (double)Nk * head_dim,
              "attention-probs heads=" + std::to_string(heads) + " d=" + std::to_string(head_dim) + " Nq=" +
                  std::to_string(Nq) + " Nk=" + std::to_string(Nk));

@@ -214,10 +214,15 @@ __device__ __forceinline__ void direct_store32(const GemmParams& p, const float*
         if (ocol0 + j < lim) dst[j] = __float2bfloat16_rn(v[j]);
     }
   }
-  if (p.out_f32) {
-    float* dst = p.out_f32 + row * p.ld_out_f32 + ocol0;
-    for (int j = 0; j < 32; ++j)
-      if (ocol0 + j < lim) dst[j] = v[j];
+  if (p.out_f32) {   // (batched launches: out_batch_stride counts fp32 elements here)
+    float* dst = p.out_f32 + out_batch_off + row * p.ld_out_f32 + ocol0;
+    if (full && (p.ld_out_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (ocol0 + j < lim) dst[j] = v[j];
+    }
   }
   if (!skip16) {
 #pragma unroll

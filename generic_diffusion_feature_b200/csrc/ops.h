@@ -115,6 +115,9 @@ cudaError_t launch_attention_probs(const bf16* Q, int ldq, const bf16* K, int ld
                                    cudaStream_t stream, const float* key_bias = nullptr, __half* P2 = nullptr,
                                    int split = 0);
 cudaError_t launch_head_mean(const __half* P, __half* out, int B, int heads, long long n, cudaStream_t stream);
+// tensor-core form of the map path: fp32 scores -> fp16 probabilities; V of one image -> V^T fp16 [heads][D][Nk]
+cudaError_t launch_softmax_rows_f32_f16(const float* S, __half* P, long long rows, int cols, cudaStream_t stream);
+cudaError_t launch_transpose_v_f16(const bf16* V, int ldv, __half* VT, int heads, int Nk, int D, cudaStream_t stream);
 // tcgen05 / TMEM flash attention (attention_sm100.cu); launch_attention64 dispatches to it for Nk >= 128.
 int launch_attention64_tcgen05(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
                                int B, int heads, int Nq, int Nk, float scale, cudaStream_t stream);
