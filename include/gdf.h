@@ -36,7 +36,8 @@ extern "C" {
 #define GDF_ERR_MISSING_WEIGHT (-4)
 #define GDF_ERR_SHAPE (-5)
 
-#define GDF_ABI_VERSION 2
+/* 3: gdf_epilogue grew (act 4 = ReLU, out_f16_from < 0, res_f16, k_split_*); gdf_plan_decoder / gdf_decode_latents */
+#define GDF_ABI_VERSION 3
 
 typedef struct gdf_handle_s* gdf_handle;
 

@@ -600,7 +600,7 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, "declared in gdf.h but not exported: %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding list out of sync with gdf.h"
     lib.gdf_abi_version.restype = ctypes.c_int
-    assert lib.gdf_abi_version() == 2
+    assert lib.gdf_abi_version() == 3
     # error plumbing without touching the GPU: null handle -> negative code + message
     lib.gdf_last_error.restype = ctypes.c_char_p
     assert lib.gdf_plan(None, None, 0, 1, 1024, None, None) < 0
