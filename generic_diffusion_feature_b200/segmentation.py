@@ -67,14 +67,16 @@ class MultiRes:
         self.block = ResBlock(sd, prefix + ".res.0", dim, device)
         self.n = n
 
-    def __call__(self, x):
+    def __call__(self, x, out_f16=None, want_f32=True):
+        """out_f16 / want_f32 as in ResBlock.__call__, for the LAST application."""
         B, H, W, C = x.shape
         for i in range(self.n):
             last = i == self.n - 1
-            nxt = None if last else torch.empty(B * H * W, C, dtype=torch.float16, device=x.device)
-            y = self.block(x, out_f16=nxt, want_f32=last)
-            x = y if last else nxt.view(B, H, W, C)
-        return x
+            if last:
+                return self.block(x, out_f16=out_f16, want_f32=want_f32)
+            nxt = torch.empty(B * H * W, C, dtype=torch.float16, device=x.device)
+            self.block(x, out_f16=nxt, want_f32=False)
+            x = nxt.view(B, H, W, C)
 
 
 class SegmentorFeatureHead:
@@ -112,6 +114,58 @@ class SegmentorFeatureHead:
                 off += layer[1]
             y = self.sums[level](cat.view(B, H, W, sum_dim))
             outs.append(y.permute(0, 3, 1, 2))
+        return outs
+
+    extract_feat = __call__
+
+
+class MultiSegmentorFeatureHead:
+    """`DiffusionSegmentor.extract_feat`, several-extractors branch (diffusion_segmentor.py:248-297), after the
+    `extract` calls: per model i and level a `MultiRes(dim, 4)` per captured map, channel concat, `MultiRes(sum, 2)`;
+    then per level the models' results are concatenated and go through `ResBlock(c_per_level[level])` ('amalgemated').
+
+        head = MultiSegmentorFeatureHead([layers_model0, layers_model1], c_per_level, state_dict)
+        outs = head([features_model0, features_model1])        # -> list of fp32 (B, c_per_level[l], h, w)
+    """
+
+    def __init__(self, feature_layers, c_per_level, sd, device="cuda"):
+        self.feature_layers = feature_layers
+        self.c_per_level = list(c_per_level)
+        self.blocks, self.sums = {}, {}
+        for i, layers in enumerate(feature_layers):
+            for level, res in enumerate(layers):
+                for layer in res:
+                    self.blocks[(i, layer[0])] = MultiRes(sd, layer_conv_name(layer[0], i), 4, layer[1], device)
+                if res:
+                    self.sums[(i, level)] = MultiRes(sd, layer_conv_name("sum%d" % level, i), 2, sum(l[1] for l in res),
+                                                     device)
+        self.amalgamated = [ResBlock(sd, layer_conv_name("amalgemated", l), c, device) for l, c in enumerate(c_per_level)]
+
+    def __call__(self, features_per_model):
+        outs = []
+        for level, c_total in enumerate(self.c_per_level):
+            parts = [(i, res[level]) for i, res in enumerate(self.feature_layers) if level < len(res) and res[level]]
+            f0 = features_per_model[parts[0][0]][parts[0][1][0][0]]
+            B, _, H, W = f0.shape
+            cat = torch.empty(B * H * W, c_total, dtype=torch.float16, device=f0.device)
+            off = 0
+            for i, res in parts:
+                sum_dim = sum(l[1] for l in res)
+                per = torch.empty(B * H * W, sum_dim, dtype=torch.float16, device=f0.device)
+                o2 = 0
+                for layer in res:
+                    f = features_per_model[i][layer[0]]
+                    if tuple(f.shape) != (B, layer[1], H, W):
+                        raise ValueError("model %d level %d: map %s has shape %s, expected %s"
+                                         % (i, level, layer[0], tuple(f.shape), (B, layer[1], H, W)))
+                    self.blocks[(i, layer[0])](f.permute(0, 2, 3, 1).contiguous(), out_f16=per[:, o2:o2 + layer[1]],
+                                               want_f32=False)
+                    o2 += layer[1]
+                self.sums[(i, level)](per.view(B, H, W, sum_dim), out_f16=cat[:, off:off + sum_dim], want_f32=False)
+                off += sum_dim
+            if off != c_total:
+                raise ValueError("level %d: the models bring %d channels, c_per_level says %d" % (level, off, c_total))
+            outs.append(self.amalgamated[level](cat.view(B, H, W, c_total)).permute(0, 3, 1, 2))
         return outs
 
     extract_feat = __call__

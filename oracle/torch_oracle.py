@@ -1338,3 +1338,21 @@ def seg_extract_feat(features, feature_layers, sd):
         per = [seg_resblock(features[layer[0]].float(), sd, seg_layer_conv_name(layer[0])) for layer in res_level]
         outs.append(seg_resblock(torch.cat(per, dim=1), sd, seg_layer_conv_name("sum%d" % level)))
     return outs
+
+
+def seg_extract_feat_multi(features_per_model, feature_layers, c_per_level, sd):
+    """DiffusionSegmentor.extract_feat, several-extractors branch, segmentation/models/diffusion_segmentor.py:248-297:
+    MultiRes(dim, 4) per map (ONE shared ResBlock applied four times, :46-53), concat, MultiRes(sum, 2) per model and
+    level; then the models' results per level are concatenated and go through ResBlock 'amalgemated'."""
+    def multires(x, prefix, n):
+        for _ in range(n):
+            x = seg_resblock(x, sd, prefix + ".res.0")
+        return x
+    outs = [[] for _ in c_per_level]
+    for i, layers in enumerate(feature_layers):
+        for level, res_level in enumerate(layers):
+            per = [multires(features_per_model[i][layer[0]].float(), seg_layer_conv_name(layer[0], i), 4)
+                   for layer in res_level]
+            if per:
+                outs[level].append(multires(torch.cat(per, dim=1), seg_layer_conv_name("sum%d" % level, i), 2))
+    return [seg_resblock(torch.cat(o, dim=1), sd, seg_layer_conv_name("amalgemated", l)) for l, o in enumerate(outs)]

@@ -401,6 +401,13 @@ def test_oracle_segmentor_head_matches_reference():
     for _ in range(gold["multires_n"]):
         y = O.seg_resblock(y, sd, "up_level1_upsampler_out")
     assert (y - gold["multires_out"].float()).abs().max().item() <= 2e-3 * y.abs().max().item()
+    # several-extractors branch (diffusion_segmentor.py:248-297): MultiRes per map / per level sum, 'amalgemated' ResBlock
+    mg = gold["multi"]
+    msd = {k: v.float() for k, v in mg["state_dict"].items()}
+    mouts = O.seg_extract_feat_multi(mg["features"], mg["feature_layers"], mg["c_per_level"], msd)
+    for got, want in zip(mouts, mg["outs"]):
+        assert got.shape == want.shape
+        assert (got - want.float()).abs().max().item() <= 2e-3 * want.float().abs().max().item()
     # fold: conv(x, w * s) + (b - mean) * s + beta == BN(conv(x, w) + b)
     p = "up_level1_upsampler_out.conv1"
     s = sd[p + ".1.weight"] * torch.rsqrt(sd[p + ".1.running_var"] + 1e-5)

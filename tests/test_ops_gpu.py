@@ -691,6 +691,17 @@ def test_segmentor_feature_head_matches_reference(cuda_dev):
     with pytest.raises(ValueError):
         S.ResBlock({k.replace(pre, "q."): v[:32, :32] if v.dim() == 4 else v[:32] for k, v in sd.items()
                     if k.startswith(pre)}, "q")
+    # several-extractors branch (diffusion_segmentor.py:248-297) vs the reference's real extract_feat: up to 4 + 2 + 1
+    # ResBlocks in sequence with fp16 intermediates
+    mg = gold["multi"]
+    msd = {k: v.float() for k, v in mg["state_dict"].items()}
+    mhead = S.MultiSegmentorFeatureHead(mg["feature_layers"], mg["c_per_level"], msd)
+    mouts = mhead([{k: v.cuda() for k, v in f.items()} for f in mg["features"]])
+    torch.cuda.synchronize()
+    assert len(mouts) == len(mg["outs"])
+    for got, want in zip(mouts, mg["outs"]):
+        assert got.shape == want.shape
+        assert rel_err(got.cpu(), want.float()) < 8e-3
 
 
 @pytest.mark.gpu

@@ -525,6 +525,72 @@ def golden_correspondence():
                 "idx": torch.from_numpy(idx)}, os.path.join(OUT, "correspondence.pt"))
 
 
+def _seed_head(m, g):
+    for n, p in m.named_parameters():
+        with torch.no_grad():
+            if n.endswith(".0.weight"):     # fp16-representable, stored as fp16 (fixture size)
+                p.copy_((torch.randn(p.shape, generator=g) * (0.5 / (9 * p.shape[1]) ** 0.5)).half().float())
+            elif n.endswith(".1.weight"):
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    for n, b in m.named_buffers():
+        if n.endswith("running_mean"):
+            b.copy_(0.1 * torch.randn(b.shape, generator=g))
+        elif n.endswith("running_var"):
+            b.copy_(0.5 + torch.rand(b.shape, generator=g))
+
+
+def _golden_segmentor_multi(seg, g):
+    """Several-extractors branch of the REAL DiffusionSegmentor.extract_feat (diffusion_segmentor.py:248-297): two stand-in
+    extractors, MultiRes(dim, 4) per map, MultiRes(sum, 2) per model and level, ResBlock 'amalgemated' per level."""
+    layers = [[[("up-level0-upsampler-out", 64)], [("up-level1-upsampler-out", 64)]],
+              [[("mid-vit-out", 64)], []]]
+    c_per_level = [128, 64]
+    sizes = [8, 16]
+    B = 1
+    feats = [{}, {}]
+    for i, ls in enumerate(layers):
+        for level, res in enumerate(ls):
+            for lname, c in res:
+                feats[i][lname] = torch.randn(B, c, sizes[level], sizes[level], generator=g).to(torch.float16)
+
+    class _FE:
+        def __init__(self, i):
+            self.i = i
+
+        def extract(self, **kw):
+            assert kw["image_type"] == "tensors"
+            return feats[self.i]
+
+    m = object.__new__(seg.DiffusionSegmentor)
+    torch.nn.Module.__init__(m)
+    m.multiple_diffusion = True
+    m.feature_extractors = [{"model": _FE(i), "prompt_embeds": None, "t": 50, "layers": ls} for i, ls in enumerate(layers)]
+    for i, ls in enumerate(layers):
+        for rank, res in enumerate(ls):
+            for lname, c in res:
+                setattr(m, m.layer_conv_name(lname, i), seg.MultiRes(c, 4))
+            if res:
+                setattr(m, m.layer_conv_name("sum%d" % rank, i), seg.MultiRes(sum(c for _, c in res), 2))
+    for i, dim in enumerate(c_per_level):
+        setattr(m, m.layer_conv_name("amalgemated", i), seg.ResBlock(dim))
+    _seed_head(m, g)
+    m.eval()
+    with torch.no_grad():
+        outs = m.extract_feat(torch.zeros(B, 3, 8, 8), is_test=True)
+    sd = {k: v.clone() for k, v in m.state_dict().items() if "num_batches_tracked" not in k and ".res." not in k
+          or ".res.0." in k}
+    sd = {k: v for k, v in sd.items() if "num_batches_tracked" not in k}
+    o_outs = O.seg_extract_feat_multi(feats, layers, c_per_level, sd)
+    for a, b in zip(outs, o_outs):
+        assert torch.allclose(a, b, atol=2e-5, rtol=1e-5), "oracle several-extractors segmentor head differs from the reference's"
+    sd = {k: (v.half() if k.endswith(".0.weight") else v) for k, v in sd.items()}
+    print("segmentor_head.pt[multi]: %s, oracle == reference" % [tuple(o.shape) for o in outs])
+    return {"feature_layers": layers, "c_per_level": c_per_level, "features": feats, "state_dict": sd,
+            "outs": [o.half() for o in outs]}
+
+
 def golden_segmentor(name="segmentor_head.pt"):
     """Real ResBlock / DiffusionSegmentor.extract_feat of segmentation/models/diffusion_segmentor.py (single-extractor
     branch, eval mode) on seeded fp16 maps. The reference initialises every ResBlock parameter to zero (an identity at
@@ -584,7 +650,8 @@ def golden_segmentor(name="segmentor_head.pt"):
     with torch.no_grad():
         mr_out = mr(feats["up-level1-upsampler-out"].float())
     sd = {k: (v.half() if k.endswith(".0.weight") else v) for k, v in sd.items()}
-    torch.save({"feature_layers": feature_layers, "features": feats, "state_dict": sd,
+    multi = _golden_segmentor_multi(seg, g)
+    torch.save({"multi": multi, "feature_layers": feature_layers, "features": feats, "state_dict": sd,
                 "outs": [o.half() for o in outs], "multires_n": 3, "multires_out": mr_out.half()}, os.path.join(OUT, name))
     print("%s: %d levels %s, oracle == reference" % (name, len(outs), [tuple(o.shape) for o in outs]))
 

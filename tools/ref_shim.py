@@ -612,6 +612,17 @@ def load_reference_segmentor():
     m.__package__ = "ref_segmodels"
     try:
         spec.loader.exec_module(m)
+
+        class _TorchOnCpu:
+            """The several-extractors branch of extract_feat moves every map `.to(torch.device("cuda:0"))`
+            (diffusion_segmentor.py:267): in this GPU-less container that one name resolves to the CPU."""
+            def __getattr__(self, n):
+                return getattr(torch, n)
+
+            def device(self, *a, **k):
+                return torch.device("cpu")
+
+        m.torch = _TorchOnCpu()
     finally:
         if saved["diffusion_feature"] is None:
             del sys.modules["diffusion_feature"]
