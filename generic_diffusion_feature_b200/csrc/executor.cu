@@ -3194,7 +3194,8 @@ int gdf_finalize_weights(gdf_handle h, void* stream) {
   Builder b(h, true);
   std::vector<Site> keep_sites = h->sites;
   int r = build_vae(b);
-  if (!r && h->raw.count("vae.decoder.conv_in.weight")) r = build_vae_decoder(b);   // optional: only `vae-out` decodes
+  // optional: only `vae-out` decodes (UNet families: 4 latent channels; a 16-channel Flux decoder is never walked)
+  if (!r && h->raw.count("vae.decoder.conv_in.weight") && 9 * h->va.latent_channels <= 64) r = build_vae_decoder(b);
   if (!r) r = h->is_flux ? build_flux(b) : h->is_dit ? build_dit(b) : build_unet(b);
   h->sites = keep_sites;
   h->B = B0;
