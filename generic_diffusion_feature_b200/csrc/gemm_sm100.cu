@@ -917,6 +917,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int piece = decode_piece(p, t, kb_begin, kb_end);
         decode_unit(p, t, num_m_units, mu, tc.n_tile, tc.bz);
         tc.m_tile = mu * CG + (int)cta_rank;
+        // (general epilogue instantiation only: launch_gemm sends K-split launches there, so that the ~2.8 k instructions of
+        // the fix-up do not sit inside the tile loop of the lean / simple images, which are instruction-fetch sensitive)
+        if constexpr (kLevel == 0)
         if (piece >= 0) {
           // ---- K-split tail piece: publish the raw accumulators, count in; the last warp of this (tile, rank, warp) sums
           // every piece in index order into TMEM and falls through to the normal epilogue, the others are done
@@ -1400,7 +1403,7 @@ cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   const bool geglu = p.act == kActGeglu;
   const int out_w = geglu ? p.block_n / 2 : p.block_n;
   const bool act_rt = p.act == kActGeluTanh || p.act == kActSilu;
-  const bool lean = max_level >= 1 && (geglu || p.act == kActNone || act_rt) && !p.ln_sums && !p.row_sums && !p.bias_m &&
+  const bool lean = max_level >= 1 && p.sk_pieces <= 1 && (geglu || p.act == kActNone || act_rt) && !p.ln_sums && !p.row_sums && !p.bias_m &&
                     p.out_scale == 1.f && !p.out_f32 && p.fast_epi && p.tma_store &&
                     p.N % p.block_n == 0 && out_w % 32 == 0 && p.n_out == (geglu ? p.N / 2 : p.N);
   if (geglu) {
