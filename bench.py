@@ -682,7 +682,7 @@ def run_hbm_kernels(args, rank, world, dev):
     for M, Cc in ((8192, 1280), (32768, 640), (262144, 1152)):
         x = rnd(M, Cc).bfloat16()
         gm, bt = rnd(Cc), rnd(Cc)
-        bench("layernorm_kernel M=%d C=%d" % (M, Cc), 2 * M * Cc * 2, lambda x=x, gm=gm, bt=bt: ops.layernorm(x, gm, bt, 1e-5),
+        bench("layernorm_rows_kernel M=%d C=%d" % (M, Cc), 2 * M * Cc * 2, lambda x=x, gm=gm, bt=bt: ops.layernorm(x, gm, bt, 1e-5),
               "L2-resident" if M * Cc * 4 < 120e6 else "")
     # GroupNorm + SiLU at the VAE shapes (2 reads + 1 write of the tensor)
     for HW, Cc in ((1024 * 1024, 128), (512 * 512, 256), (128 * 128, 512), (128 * 128, 320), (32 * 32, 1280)):
