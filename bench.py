@@ -407,7 +407,15 @@ class Workload:
         return self._step(self.images)
 
     def step_e2e(self):
-        out = self._step(self.images_host)
+        # Every step issues ONE pinned host -> device copy of a full input batch and one device -> host read of its result,
+        # both inside the timed region. The copy runs on the extractor's side stream (FeatureExtractor.stage_images, the
+        # public prefetch hook): the batch a step consumes was put in flight by the previous step, the one it issues
+        # overlaps its own forward - the way a caller looping over a dataset uses the API (and the CLI does).
+        if getattr(self, "_staged", None) is None:
+            self._staged = self.fe.stage_images(self.images_host)
+        images, self._staged = self._staged, None
+        out = self._step(images)
+        self._staged = self.fe.stage_images(self.images_host)
         if self.config == "sd21_768_mt":
             r = out[:, :, :4].contiguous().cpu()          # D2H read of the step's result (syncs the step)
         elif self.config == "corr_sdxl":
@@ -607,7 +615,10 @@ def run_ours(args, rank, world, local):
                 "units_per_step_per_gpu": wl.units_per_step}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": wl.h2d,
-                    "d2h_bytes_per_step": wl.d2h, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": wl.d2h, "ms_per_step": ms_e2e / args.steps,
+                    "overlap": "every step issues one pinned H2D of a full batch (FeatureExtractor.stage_images, side "
+                               "stream) that overlaps its own forward and feeds the next step, and one D2H read of its "
+                               "result; both inside the timed region"},
             "gpu_launches": wl.launches_per_step() * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base,
         }

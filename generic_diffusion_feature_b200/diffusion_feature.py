@@ -84,6 +84,7 @@ class FeatureExtractor(nn.Module):
         self.attention = attention
         self._plan = None
         self._plan_ctx_len = None
+        self._copy_stream = None
         self._ids = selected_ids(self.feature_store, pipe)
         if attention:
             # register_attention_store (diffusion_feature.py:67-68): the head-mean probabilities of every attention
@@ -108,6 +109,21 @@ class FeatureExtractor(nn.Module):
         from PIL import Image
         x = ((x.detach().float().cpu() / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
         return [Image.fromarray(i.permute(1, 2, 0).numpy()) for i in x]
+
+    def stage_images(self, images_host):
+        """Start the host -> device copy of a pinned (B, 3, S, S) float32 batch on a side stream and return the device
+        tensor; `extract(image=<that tensor>, image_type='tensors')` makes its stream wait for the copy. Lets a caller
+        that loops over batches overlap the copy of batch i + 1 with the forward of batch i (what the CLI's prefetch
+        thread does, extract_feature.py). Extension: the reference copies synchronously inside `extract`."""
+        dev = torch.device(self.pipe.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            t = images_host.to(dev, torch.float32, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        t._gdf_ready = ev
+        return t
 
     # ------------------------------------------------------------------------------------------ prompts
     def encode_prompt(self, prompt_str=None, prompt_file=None):
@@ -205,7 +221,12 @@ class FeatureExtractor(nn.Module):
         # 6. prepare image (diffusion_feature.py:357-364)
         if image_type == 'image':
             image = torch.concat([self.preprocess_image(r) for r in image], dim=0)
+        ready = getattr(image, "_gdf_ready", None)      # staged by stage_images(): the copy runs on a side stream
         image = image.to(dev, torch.float32, non_blocking=True)
+        if ready is not None:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ready)
+            image.record_stream(cur)
         lat_ch = pipe.vae_cfg["latent"]
         is_latents = image.shape[1] == lat_ch  # prepare_latents: latent-channel input is taken as latents (:623-624)
         if not is_latents and image.shape[-2:] != (self.img_size, self.img_size):
