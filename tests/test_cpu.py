@@ -582,6 +582,13 @@ def test_no_cpu_fallback():
     m = _models()
     with pytest.raises(GdfError):
         m.B200Pipe("xl", m.UNET_CONFIGS["xl"], m.VAE_CONFIGS["xl"], "cpu")
+    # the downstream heads have no CPU path either: building one without a GPU fails loudly
+    from generic_diffusion_feature_b200 import segmentation as S
+    gold = torch.load(os.path.join(GOLD, "segmentor_head.pt"), weights_only=False)
+    with pytest.raises(Exception):
+        S.SegmentorFeatureHead(gold["feature_layers"], {k: v.float() for k, v in gold["state_dict"].items()})
+    assert S.layer_conv_name("up-level0-upsampler-out") == "up_level0_upsampler_out"      # diffusion_segmentor.py:188-192
+    assert S.layer_conv_name("sum1", 0) == "0_sum1"
 
 
 def test_product_never_imports_oracle():
