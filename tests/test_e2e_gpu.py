@@ -432,7 +432,10 @@ def test_vae_out_matches_oracle(cuda_dev, version, ucfg, t):
     # a second call reuses the decoder plan and gives the same image
     got2 = fe.extract((ctx, ctx, pooled, pooled), batch, image.cuda(), image_type="tensors", t=t, noise=(eps_vae, eps_q))
     torch.cuda.synchronize()
-    assert (got2["vae-out"].float() - v.float()).abs().max().item() <= 2e-2 * v.float().abs().max().item()
+    # (two runs of one plan differ at the bf16 noise floor: GroupNorm statistics through atomics, see
+    # test_two_extractors_share_one_pipe for the measured spread and the same bound)
+    assert F.cosine_similarity(got2["vae-out"].float().flatten(), v.float().flatten(), dim=0).item() >= COS_MIN
+    assert (got2["vae-out"].float() - v.float()).abs().max().item() <= 5e-2 * max(1.0, v.float().abs().max().item())
 
 
 @pytest.mark.parametrize("fixture,version,cfg", [("unet_tiny_xl.pt", "xl", TINY_XL), ("unet_tiny_21.pt", "2-1", TINY_21),
