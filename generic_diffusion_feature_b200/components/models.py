@@ -646,7 +646,7 @@ class B200Pipe:
 
 def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename=None, device="cuda",
                         state_dict=None, unet_cfg=None, vae_cfg=None, weight_device=None, dit_cfg=None, flux_cfg=None,
-                        model_dir=None, synthetic=False):
+                        model_dir=None, synthetic=False, with_decoder=False):
     """Mirror of feature/components/models.py:10 for the B200 path.
 
     Where the reference calls `Pipeline.from_pretrained(model_id)` (hub download, models.py:18-172), the weights come
@@ -657,7 +657,7 @@ def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename
       3. `synthetic=True` (or GDF_SYNTHETIC=1) - deterministic random weights generated by parameter name
                          (`synthetic_state_dict`): benchmarks and parity tests, never a silent default.
     With none of the three the call raises: features of a random network are not what a caller of the reference's
-    factory expects to get."""
+    factory expects to get. with_decoder: also load (or generate) the VAE decoder, which only `vae-out` needs."""
     import os
     if dtype not in ("float32", "float16"):
         raise NotImplementedError                      # models.py:11-16
@@ -678,9 +678,10 @@ def get_diffusion_model(version, dtype, offline_lora=None, offline_lora_filename
         if model_dir is None and env_dir:
             model_dir = os.path.join(env_dir, version) if os.path.isdir(os.path.join(env_dir, version)) else env_dir
         if model_dir is not None:
-            state_dict = load_diffusers_dir(model_dir, version)
+            state_dict = load_diffusers_dir(model_dir, version, with_decoder=with_decoder)
         elif synthetic or os.environ.get("GDF_SYNTHETIC") == "1":
-            state_dict = synthetic_state_dict(version, weight_device or "cpu", ucfg, vcfg, dcfg, fcfg)
+            state_dict = synthetic_state_dict(version, weight_device or "cpu", ucfg, vcfg, dcfg, fcfg,
+                                              with_decoder=with_decoder)
         else:
             raise _lib.GdfError(
                 "get_diffusion_model('%s'): no weights. Pass state_dict=, model_dir= (or set GDF_MODEL_DIR) pointing at "

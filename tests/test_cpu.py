@@ -704,6 +704,15 @@ def test_checkpoint_dir_round_trip(tmp_path):
     save_file(legacy, os.path.join(d, "vae", "diffusion_pytorch_model.safetensors"))
     back = m.load_diffusers_dir(d, "xl")
     assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    # with the decoder (vae-out): its tensors round-trip too (mid-block attention in the old naming included) and are
+    # dropped unless asked for
+    sd_dec = m.synthetic_state_dict("xl", "cpu", TINY_XL, TINY_VAE, with_decoder=True)
+    d2 = str(tmp_path / "ckpt_dec")
+    m.save_diffusers_dir(sd_dec, d2)
+    assert set(m.load_diffusers_dir(d2, "xl")) == set(sd)
+    back = m.load_diffusers_dir(d2, "xl", with_decoder=True)
+    assert set(back) == set(sd_dec) and all(torch.equal(back[k], sd_dec[k]) for k in sd_dec)
+    assert set(back) - set(sd) == set(m.optional_shapes(TINY_VAE))
 
 
 def test_no_silent_synthetic_weights(monkeypatch):
