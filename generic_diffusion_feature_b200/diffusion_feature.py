@@ -59,7 +59,15 @@ class FeatureExtractor(nn.Module):
         if external_model:
             pipe = external_model            # diffusion_feature.py:46-47: the seam for pre-built pipes
         else:
-            pipe = get_diffusion_model(version, dtype, offline_lora, offline_lora_filename, device=device)
+            # the VAE decoder is only loaded when the layer selection asks for `vae-out` (diffusion_feature.py:477-485)
+            try:
+                import json
+                sel = layer if isinstance(layer, dict) else (json.load(open(layer)) if layer else {})
+                wants_decoder = bool(sel.get('vae-out', False))
+            except (OSError, ValueError, AttributeError):
+                wants_decoder = False
+            pipe = get_diffusion_model(version, dtype, offline_lora, offline_lora_filename, device=device,
+                                       with_decoder=wants_decoder)
         self.feature_store = prepare_feature_extractor(version, pipe, layer, feature_resize, train_unet)
         self.store_vae_output = bool(self.feature_store.to_store.get('vae-out', False))
         if self.store_vae_output:
