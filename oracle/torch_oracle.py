@@ -10,8 +10,10 @@ resnet.py, attention.py, attention_processor.py, transformers/transformer_2d.py,
 upsampling.py, unet/unet_2d_condition.py) ARE executed in this container through an import shim
 (tools/make_golden.py) and this restatement is checked against them module by module and end to end; the
 resulting vectors are committed under tests/golden/. The un-vendored pieces (unet_2d_blocks wiring,
-embeddings.Timesteps/TimestepEmbedding, activations.GEGLU, AutoencoderKL encoder, schedulers) are restated from
-the published diffusers 0.32.2 semantics -> for those: PARITY UNPINNED.
+embeddings.Timesteps/TimestepEmbedding, activations.GEGLU, AutoencoderKL encoder and decoder, scheduler tables and
+the first `step()` of Euler / PNDM) are restated from the published diffusers 0.32.2 semantics -> for those: PARITY
+UNPINNED. The segmentation heads (seg_*) ARE pinned: tests/golden/segmentor_head.pt comes from the reference's own
+ResBlock / MultiRes / DiffusionSegmentor.extract_feat.
 
 Every class cites the reference file:line it follows. Attribute names mirror diffusers so that (a) the
 reference's own prepare_feature_extractor (feature/components/feature_extractor.py:92-288) can attach its
